@@ -1,0 +1,460 @@
+// abi.cu — the extern "C" boundary declared in include/dpfhe.h.
+//
+// Conventions follow the reference HAL (see the header's citations): cudaSetDevice at the top
+// of every call, the context owns its tables/scratch and frees them in destroy, CUDA errors
+// are reported with file:line (as hal::CUDADevice::check_cuda_error does) — but as a status
+// code plus thread-local message, because exceptions cannot cross a C ABI.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/dpfhe.h"
+#include "host_params.hpp"
+#include "launch.hpp"
+
+using namespace dpfhe;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                          \
+    do {                                                                                                      \
+        cudaError_t e_ = (expr);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(DPFHE_ERR_CUDA, "CUDA error at %s:%d: %s (%s)", __FILE__, __LINE__, cudaGetErrorString(e_), #expr); \
+    } while (0)
+
+constexpr int PIPE_DEPTH = 3;
+
+}  // namespace
+
+struct dpfhe_ctx {
+    HostParams hp;
+    LaunchCtx lc;
+    cudaStream_t stream = nullptr;          // the context's own stream (used when the caller passes NULL)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    LimbParams *d_lp = nullptr;
+    Twiddle *d_tw = nullptr, *d_itw = nullptr;
+    size_t device_bytes = 0;
+    uint64_t launches = 0;
+    // staging for the host-buffer entry points (allocated on first use)
+    u64 *stage_in[PIPE_DEPTH] = {}, *stage_out[PIPE_DEPTH] = {}, *stage_key = nullptr;
+    size_t stage_in_bytes = 0, stage_out_bytes = 0, stage_key_bytes = 0;
+    cudaEvent_t ev_h2d[PIPE_DEPTH] = {}, ev_comp[PIPE_DEPTH] = {}, ev_d2h[PIPE_DEPTH] = {};
+    size_t N() const { return (size_t)1 << hp.log_n; }
+    size_t P() const { return N() * hp.L; }
+};
+
+namespace {
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int enter(const dpfhe_ctx *ctx) {
+    if (!ctx) return fail(DPFHE_ERR_INVALID, "null context");
+    CU_TRY(cudaSetDevice(ctx->lc.device));
+    return DPFHE_OK;
+}
+
+cudaStream_t pick(dpfhe_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+int ensure_staging(dpfhe_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t key_bytes) {
+    if (in_bytes > ctx->stage_in_bytes) {
+        for (int k = 0; k < PIPE_DEPTH; ++k) {
+            if (ctx->stage_in[k]) cudaFree(ctx->stage_in[k]);
+            ctx->stage_in[k] = nullptr;
+            CU_TRY(cudaMalloc(&ctx->stage_in[k], in_bytes));
+        }
+        ctx->stage_in_bytes = in_bytes;
+    }
+    if (out_bytes > ctx->stage_out_bytes) {
+        for (int k = 0; k < PIPE_DEPTH; ++k) {
+            if (ctx->stage_out[k]) cudaFree(ctx->stage_out[k]);
+            ctx->stage_out[k] = nullptr;
+            CU_TRY(cudaMalloc(&ctx->stage_out[k], out_bytes));
+        }
+        ctx->stage_out_bytes = out_bytes;
+    }
+    if (key_bytes > ctx->stage_key_bytes) {
+        if (ctx->stage_key) cudaFree(ctx->stage_key);
+        ctx->stage_key = nullptr;
+        CU_TRY(cudaMalloc(&ctx->stage_key, key_bytes));
+        ctx->stage_key_bytes = key_bytes;
+    }
+    return DPFHE_OK;
+}
+
+// Generic three-stage pipeline over `n_items` items split into chunks:
+//   upload(chunk -> stage_in[slot]) on s_h2d, compute on ctx->stream, download(stage_out[slot]) on s_d2h.
+// in_item_bytes / out_item_bytes are per item; h_in may be two arrays (a and b) laid out back to back in the stage.
+template <class Compute>
+int run_pipeline(dpfhe_ctx *ctx, const u64 *h_in0, const u64 *h_in1, u64 *h_out, size_t n_items, size_t in_item_words,
+                 size_t out_item_words, size_t chunk_items, Compute compute) {
+    const size_t n_in = h_in1 ? 2 : 1;
+    int rc = ensure_staging(ctx, n_in * chunk_items * in_item_words * 8, chunk_items * out_item_words * 8, 0);
+    if (rc) return rc;
+    size_t k = 0;
+    for (size_t first = 0; first < n_items; first += chunk_items, ++k) {
+        const size_t cnt = n_items - first < chunk_items ? n_items - first : chunk_items;
+        const int slot = (int)(k % PIPE_DEPTH);
+        u64 *din0 = ctx->stage_in[slot], *din1 = din0 + chunk_items * in_item_words, *dout = ctx->stage_out[slot];
+        if (k >= PIPE_DEPTH) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[slot], 0));   // stage_in[slot] free again
+        CU_TRY(cudaMemcpyAsync(din0, h_in0 + first * in_item_words, cnt * in_item_words * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (h_in1)
+            CU_TRY(cudaMemcpyAsync(din1, h_in1 + first * in_item_words, cnt * in_item_words * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CU_TRY(cudaEventRecord(ctx->ev_h2d[slot], ctx->s_h2d));
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+        if (k >= PIPE_DEPTH) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[slot], 0));   // stage_out[slot] drained
+        rc = compute(din0, din1, dout, cnt, ctx->stream);
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(ctx->ev_comp[slot], ctx->stream));
+        CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[slot], 0));
+        CU_TRY(cudaMemcpyAsync(h_out + first * out_item_words, dout, cnt * out_item_words * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CU_TRY(cudaEventRecord(ctx->ev_d2h[slot], ctx->s_d2h));
+    }
+    CU_TRY(cudaStreamSynchronize(ctx->s_d2h));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return DPFHE_OK;
+}
+
+size_t pick_chunk(const dpfhe_ctx *ctx, size_t item_bytes, size_t n_items) {
+    // ~64 MiB per staged operand keeps PCIe transfers long and the staging footprint small
+    size_t c = ((size_t)64 << 20) / item_bytes;
+    if (c < 1) c = 1;
+    // keep at least one full wave of work items per launch where the batch allows it
+    const size_t wave = (size_t)ctx->lc.num_sms;
+    if (c < wave && n_items >= wave) c = wave;
+    if (c > n_items) c = n_items;
+    return c;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *dpfhe_last_error(void) { return g_err.c_str(); }
+const char *dpfhe_version(void) { return "dpfhe 0.1 sm_100a"; }
+
+int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) {
+    if (!p || !out) return fail(DPFHE_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev <= 0)
+        return fail(DPFHE_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                    ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+    if (device_id < 0 || device_id >= n_dev) return fail(DPFHE_ERR_INVALID, "device_id %d out of range [0,%d)", device_id, n_dev);
+    dpfhe_ctx *ctx = new (std::nothrow) dpfhe_ctx();
+    if (!ctx) return fail(DPFHE_ERR_NOMEM, "out of host memory");
+    std::string msg = build_host_params(p->log_n, p->n_limbs, p->moduli, ctx->hp);
+    if (!msg.empty()) {
+        delete ctx;
+        return fail(DPFHE_ERR_INVALID, "%s", msg.c_str());
+    }
+    ctx->lc.device = device_id;
+#define CTX_TRY(expr)                                                                                              \
+    do {                                                                                                           \
+        cudaError_t e_ = (expr);                                                                                   \
+        if (e_ != cudaSuccess) {                                                                                   \
+            int rc_ = fail(DPFHE_ERR_CUDA, "CUDA error at %s:%d: %s (%s)", __FILE__, __LINE__, cudaGetErrorString(e_), #expr); \
+            dpfhe_context_destroy(ctx);                                                                            \
+            return rc_;                                                                                            \
+        }                                                                                                          \
+    } while (0)
+    CTX_TRY(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    CTX_TRY(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major < 10) {
+        dpfhe_context_destroy(ctx);
+        return fail(DPFHE_ERR_INVALID, "device %d is sm_%d%d; this build targets sm_100a only", device_id, prop.major, prop.minor);
+    }
+    CTX_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CTX_TRY(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CTX_TRY(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < PIPE_DEPTH; ++k) {
+        CTX_TRY(cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
+        CTX_TRY(cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming));
+        CTX_TRY(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
+    }
+    const size_t N = ctx->N(), L = ctx->hp.L;
+    CTX_TRY(cudaMalloc(&ctx->d_lp, L * sizeof(LimbParams)));
+    CTX_TRY(cudaMalloc(&ctx->d_tw, L * N * sizeof(Twiddle)));
+    CTX_TRY(cudaMalloc(&ctx->d_itw, L * N * sizeof(Twiddle)));
+    ctx->device_bytes += L * sizeof(LimbParams) + 2 * L * N * sizeof(Twiddle);
+    std::vector<LimbParams> lps(L);
+    for (size_t l = 0; l < L; ++l) {
+        lps[l] = ctx->hp.limbs[l].lp;
+        CTX_TRY(cudaMemcpy(ctx->d_tw + l * N, ctx->hp.limbs[l].tw.data(), N * sizeof(Twiddle), cudaMemcpyHostToDevice));
+        CTX_TRY(cudaMemcpy(ctx->d_itw + l * N, ctx->hp.limbs[l].itw.data(), N * sizeof(Twiddle), cudaMemcpyHostToDevice));
+    }
+    CTX_TRY(cudaMemcpy(ctx->d_lp, lps.data(), L * sizeof(LimbParams), cudaMemcpyHostToDevice));
+    LaunchCtx &lc = ctx->lc;
+    lc.num_sms = prop.multiProcessorCount;
+    lc.log_n = ctx->hp.log_n;
+    lc.L = ctx->hp.L;
+    lc.lp = ctx->d_lp;
+    lc.tw = ctx->d_tw;
+    lc.itw = ctx->d_itw;
+    // digit-exchange scratch for the fused key-switch kernel: one slot per resident CTA, two parities
+    lc.ks_slots = (size_t)lc.num_sms * 2;
+    CTX_TRY(cudaMalloc(&lc.ks_scratch, lc.ks_slots * 2 * N * 8));
+    CTX_TRY(cudaMalloc(&lc.ks_flags, lc.ks_slots * sizeof(u32)));
+    CTX_TRY(cudaMemset(lc.ks_flags, 0, lc.ks_slots * sizeof(u32)));
+    ctx->device_bytes += lc.ks_slots * 2 * N * 8 + lc.ks_slots * sizeof(u32);
+    CTX_TRY(cudaDeviceSynchronize());
+#undef CTX_TRY
+    *out = ctx;
+    return DPFHE_OK;
+}
+
+void dpfhe_context_destroy(dpfhe_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->lc.device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_lp);
+    cudaFree(ctx->d_tw);
+    cudaFree(ctx->d_itw);
+    cudaFree(ctx->lc.ks_scratch);
+    cudaFree(ctx->lc.ks_flags);
+    cudaFree(ctx->stage_key);
+    for (int k = 0; k < PIPE_DEPTH; ++k) {
+        cudaFree(ctx->stage_in[k]);
+        cudaFree(ctx->stage_out[k]);
+        if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
+        if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
+        if (ctx->ev_d2h[k]) cudaEventDestroy(ctx->ev_d2h[k]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+}
+
+int dpfhe_get_modulus(const dpfhe_ctx *ctx, uint32_t limb, uint64_t *q) {
+    if (!ctx || !q || limb >= ctx->hp.L) return fail(DPFHE_ERR_INVALID, "bad argument");
+    *q = ctx->hp.limbs[limb].lp.q;
+    return DPFHE_OK;
+}
+int dpfhe_get_psi(const dpfhe_ctx *ctx, uint32_t limb, uint64_t *psi) {
+    if (!ctx || !psi || limb >= ctx->hp.L) return fail(DPFHE_ERR_INVALID, "bad argument");
+    *psi = ctx->hp.limbs[limb].psi;
+    return DPFHE_OK;
+}
+int dpfhe_get_root_powers(const dpfhe_ctx *ctx, uint32_t limb, int inverse, uint64_t *h_out) {
+    if (!ctx || !h_out || limb >= ctx->hp.L) return fail(DPFHE_ERR_INVALID, "bad argument");
+    const auto &v = inverse ? ctx->hp.limbs[limb].inv_root_powers : ctx->hp.limbs[limb].root_powers;
+    memcpy(h_out, v.data(), v.size() * sizeof(uint64_t));
+    return DPFHE_OK;
+}
+size_t dpfhe_context_device_bytes(const dpfhe_ctx *ctx) {
+    return ctx ? ctx->device_bytes + PIPE_DEPTH * (ctx->stage_in_bytes + ctx->stage_out_bytes) + ctx->stage_key_bytes : 0;
+}
+uint64_t dpfhe_launch_count(const dpfhe_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+#define CHECK_PTR(p)                                                                          \
+    do {                                                                                      \
+        if (!(p)) return fail(DPFHE_ERR_INVALID, "null pointer: %s", #p);                     \
+        if (!aligned16(p)) return fail(DPFHE_ERR_INVALID, "%s must be 16-byte aligned", #p);  \
+    } while (0)
+
+int dpfhe_ntt_fwd(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (n_polys == 0) return DPFHE_OK;
+    CHECK_PTR(d_data);
+    CU_TRY(launch_ntt(ctx->lc, d_data, n_polys, false, pick(ctx, stream)));
+    ctx->launches++;
+    return DPFHE_OK;
+}
+int dpfhe_ntt_inv(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (n_polys == 0) return DPFHE_OK;
+    CHECK_PTR(d_data);
+    CU_TRY(launch_ntt(ctx->lc, d_data, n_polys, true, pick(ctx, stream)));
+    ctx->launches++;
+    return DPFHE_OK;
+}
+
+int dpfhe_poly_mul_pointwise(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, size_t n_polys, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (n_polys == 0) return DPFHE_OK;
+    CHECK_PTR(d_a); CHECK_PTR(d_b); CHECK_PTR(d_out);
+    CU_TRY(launch_pointwise_mul(ctx->lc, d_a, d_b, d_out, n_polys, pick(ctx, stream)));
+    ctx->launches++;
+    return DPFHE_OK;
+}
+
+int dpfhe_ct_tensor(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_d, size_t batch, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    CHECK_PTR(d_a); CHECK_PTR(d_b); CHECK_PTR(d_d);
+    CU_TRY(launch_ct_tensor(ctx->lc, d_a, d_b, d_d, batch, pick(ctx, stream)));
+    ctx->launches++;
+    return DPFHE_OK;
+}
+
+static int ks_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const uint64_t *b, const uint64_t *key, uint64_t *out,
+                     size_t batch, uint64_t galois, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    CHECK_PTR(a); CHECK_PTR(key); CHECK_PTR(out);
+    if (mode == KS_MUL_RELIN) CHECK_PTR(b);
+    if (ctx->hp.log_n > 13) return fail(DPFHE_ERR_INVALID, "key switching supports log_n <= 13 in this build (log_n = %u)", ctx->hp.log_n);
+    if (mode == KS_ROTATE) {
+        const uint64_t two_n = (uint64_t)2 << ctx->hp.log_n;
+        if (!(galois & 1) || galois >= two_n) return fail(DPFHE_ERR_INVALID, "galois element must be odd and < 2N");
+    }
+    if (out == a || out == b) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
+    CU_TRY(launch_ks(ctx->lc, mode, a, b, key, out, batch, (u32)galois, pick(ctx, stream)));
+    ctx->launches++;
+    return DPFHE_OK;
+}
+
+int dpfhe_keyswitch(dpfhe_ctx *ctx, const uint64_t *d_d, const uint64_t *d_key, uint64_t *d_out, size_t batch, void *stream) {
+    return ks_common(ctx, KS_PLAIN, d_d, nullptr, d_key, d_out, batch, 0, stream);
+}
+int dpfhe_ct_mul_relin(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, const uint64_t *d_evk, uint64_t *d_out,
+                       size_t batch, void *stream) {
+    return ks_common(ctx, KS_MUL_RELIN, d_a, d_b, d_evk, d_out, batch, 0, stream);
+}
+int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk, uint64_t *d_out, size_t batch,
+                 void *stream) {
+    return ks_common(ctx, KS_ROTATE, d_ct, nullptr, d_gk, d_out, batch, galois_elt, stream);
+}
+
+int dpfhe_ct_mul_plain(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_pt, uint64_t *d_out, size_t batch, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    CHECK_PTR(d_ct); CHECK_PTR(d_pt); CHECK_PTR(d_out);
+    CU_TRY(launch_ct_mul_plain(ctx->lc, d_ct, d_pt, d_out, batch, pick(ctx, stream)));
+    ctx->launches++;
+    return DPFHE_OK;
+}
+
+int dpfhe_fill_uniform(dpfhe_ctx *ctx, uint64_t seed, uint64_t first_poly, uint64_t *d_data, size_t n_polys, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (n_polys == 0) return DPFHE_OK;
+    CHECK_PTR(d_data);
+    CU_TRY(launch_fill_uniform(ctx->lc, seed, first_poly, d_data, n_polys, pick(ctx, stream)));
+    ctx->launches++;
+    return DPFHE_OK;
+}
+
+// ---------------------------------------------------------------- host-buffer entry points
+
+static int ntt_host(dpfhe_ctx *ctx, uint64_t *h_data, size_t n_polys, bool inverse) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (n_polys == 0) return DPFHE_OK;
+    if (!h_data) return fail(DPFHE_ERR_INVALID, "null pointer: h_data");
+    const size_t P = ctx->P();
+    const size_t chunk = pick_chunk(ctx, P * 8, n_polys);
+    return run_pipeline(ctx, h_data, nullptr, h_data, n_polys, P, P, chunk,
+                        [&](u64 *din, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
+                            CU_TRY(launch_ntt(ctx->lc, din, cnt, inverse, st));
+                            ctx->launches++;
+                            CU_TRY(cudaMemcpyAsync(dout, din, cnt * P * 8, cudaMemcpyDeviceToDevice, st));
+                            return DPFHE_OK;
+                        });
+}
+int dpfhe_ntt_fwd_host(dpfhe_ctx *ctx, uint64_t *h_data, size_t n_polys) { return ntt_host(ctx, h_data, n_polys, false); }
+int dpfhe_ntt_inv_host(dpfhe_ctx *ctx, uint64_t *h_data, size_t n_polys) { return ntt_host(ctx, h_data, n_polys, true); }
+
+static int upload_key(dpfhe_ctx *ctx, const uint64_t *h_key, size_t words) {
+    int rc = ensure_staging(ctx, 0, 0, words * 8);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(ctx->stage_key, h_key, words * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return DPFHE_OK;
+}
+
+int dpfhe_ct_mul_relin_host(dpfhe_ctx *ctx, const uint64_t *h_a, const uint64_t *h_b, const uint64_t *h_evk, uint64_t *h_out, size_t batch) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    if (!h_a || !h_b || !h_evk || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
+    const size_t P = ctx->P();
+    rc = upload_key(ctx, h_evk, 2 * ctx->hp.L * P);
+    if (rc) return rc;
+    const size_t chunk = pick_chunk(ctx, 2 * P * 8, batch);
+    return run_pipeline(ctx, h_a, h_b, h_out, batch, 2 * P, 2 * P, chunk,
+                        [&](u64 *da, u64 *db, u64 *dout, size_t cnt, cudaStream_t st) -> int {
+                            return ks_common(ctx, KS_MUL_RELIN, da, db, ctx->stage_key, dout, cnt, 0, st);
+                        });
+}
+
+int dpfhe_rotate_host(dpfhe_ctx *ctx, const uint64_t *h_ct, uint64_t galois_elt, const uint64_t *h_gk, uint64_t *h_out, size_t batch) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    if (!h_ct || !h_gk || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
+    const size_t P = ctx->P();
+    rc = upload_key(ctx, h_gk, 2 * ctx->hp.L * P);
+    if (rc) return rc;
+    const size_t chunk = pick_chunk(ctx, 2 * P * 8, batch);
+    return run_pipeline(ctx, h_ct, nullptr, h_out, batch, 2 * P, 2 * P, chunk,
+                        [&](u64 *dc, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
+                            return ks_common(ctx, KS_ROTATE, dc, nullptr, ctx->stage_key, dout, cnt, galois_elt, st);
+                        });
+}
+
+int dpfhe_ct_mul_plain_host(dpfhe_ctx *ctx, const uint64_t *h_ct, const uint64_t *h_pt, uint64_t *h_out, size_t batch) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    if (!h_ct || !h_pt || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
+    const size_t P = ctx->P();
+    rc = upload_key(ctx, h_pt, P);
+    if (rc) return rc;
+    const size_t chunk = pick_chunk(ctx, 2 * P * 8, batch);
+    return run_pipeline(ctx, h_ct, nullptr, h_out, batch, 2 * P, 2 * P, chunk,
+                        [&](u64 *dc, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
+                            CU_TRY(launch_ct_mul_plain(ctx->lc, dc, ctx->stage_key, dout, cnt, st));
+                            ctx->launches++;
+                            return DPFHE_OK;
+                        });
+}
+
+int dpfhe_host_alloc(void **out, size_t bytes) {
+    if (!out) return fail(DPFHE_ERR_INVALID, "null argument");
+    CU_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return DPFHE_OK;
+}
+int dpfhe_host_free(void *p) {
+    if (!p) return DPFHE_OK;
+    CU_TRY(cudaFreeHost(p));
+    return DPFHE_OK;
+}
+
+int dpfhe_describe(const dpfhe_ctx *ctx, char *buf, size_t buf_len) {
+    if (!ctx || !buf || !buf_len) return fail(DPFHE_ERR_INVALID, "bad argument");
+    const unsigned nt = ctx->hp.log_n == 12 ? 256 : 512;
+    int n = snprintf(buf, buf_len,
+                     "{\"log_n\": %u, \"n_limbs\": %u, \"num_sms\": %d, \"ntt_kernel\": {\"threads\": %u, \"smem_bytes\": %zu, "
+                     "\"grid\": \"one CTA per limb\"}, \"ks_fused_kernel\": {\"threads\": %u, \"smem_bytes\": %zu, "
+                     "\"grid\": \"persistent cooperative, multiple of L, <= %zu slots\"}}",
+                     ctx->hp.log_n, ctx->hp.L, ctx->lc.num_sms, nt, ctx->N() * 8, nt, 3 * ctx->N() * 8, ctx->lc.ks_slots);
+    return n;
+}
+
+}  // extern "C"

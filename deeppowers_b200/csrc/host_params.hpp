@@ -1,0 +1,34 @@
+// host_params.hpp — host-side derivation of the parameter set:
+// NTT-friendly primes, smallest primitive 2N-th roots, twiddle tables in the device layout.
+// Independent of oracle/ (the product never links the oracle); tests compare the two.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "modarith.cuh"
+
+namespace dpfhe {
+
+struct HostLimb {
+    LimbParams lp;
+    uint64_t psi;
+    std::vector<uint64_t> root_powers;      // psi^bitrev(i), natural table order
+    std::vector<uint64_t> inv_root_powers;  // psi^-bitrev(i)
+    std::vector<U64x2> tw;                  // device layout (tw_pos), with Shoup companions
+    std::vector<U64x2> itw;
+};
+
+struct HostParams {
+    unsigned log_n = 0, L = 0;
+    std::vector<HostLimb> limbs;
+};
+
+// returns "" on success, else an error message
+std::string build_host_params(unsigned log_n, unsigned L, const uint64_t *moduli, HostParams &out);
+
+uint64_t host_mulmod(uint64_t a, uint64_t b, uint64_t q);
+uint64_t host_powmod(uint64_t a, uint64_t e, uint64_t q);
+bool host_is_prime(uint64_t n);
+
+}  // namespace dpfhe

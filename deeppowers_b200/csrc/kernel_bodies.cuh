@@ -1,0 +1,266 @@
+// kernel_bodies.cuh — CTA-level bodies of every kernel.
+//
+// Each body is written against a tiny CTA policy:
+//     cta.par(f)   run f(tid) for all NT threads, then barrier
+// On the GPU (kernels.cu) par() is "f(threadIdx.x); __syncthreads();".  tests/emu provides
+// a sequential policy so the identical bodies run on the CPU for index-algebra checks
+// (test infrastructure only — the product has no CPU path).
+#pragma once
+#include "ntt_core.cuh"
+
+namespace dpfhe {
+
+DPFHE_HD u32 bitrev_n(u32 x, int bits) {
+#if defined(__CUDA_ARCH__)
+    return __brev(x) >> (32 - bits);
+#else
+    u32 r = 0;
+    for (int i = 0; i < bits; ++i) {
+        r = (r << 1) | (x & 1);
+        x >>= 1;
+    }
+    return r;
+#endif
+}
+
+// Evaluation-form index map of the automorphism X -> X^g:
+// out[i] = in[pi(i)],  2*br(pi(i)) + 1 = g * (2*br(i) + 1)  mod 2N.
+template <int LOGN>
+DPFHE_HD int galois_index(int i, u32 g) {
+    const u32 mask2n = (2u << LOGN) - 1;
+    u32 e = (g * (2u * bitrev_n((u32)i, LOGN) + 1u)) & mask2n;
+    return (int)bitrev_n((e - 1u) >> 1, LOGN);
+}
+
+// ---- memory access policy -------------------------------------------------------------
+// ld_stream / st_stream: data touched once (ciphertext in/out)   -> read-only path, no L1 allocation
+// ld_cg / st_cg        : cross-CTA scratch written in this launch -> L2-coherent (.cg)
+// ld_keep              : tables / keys shared by the whole batch  -> default caching
+DPFHE_HD U64x2 ld_stream(const U64x2 *p) {
+#if defined(__CUDA_ARCH__)
+    U64x2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+DPFHE_HD void st_stream(U64x2 *p, const U64x2 &v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+#else
+    *p = v;
+#endif
+}
+DPFHE_HD U64x2 ld_cg(const U64x2 *p) {
+#if defined(__CUDA_ARCH__)
+    U64x2 v;
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
+DPFHE_HD void st_cg(U64x2 *p, const U64x2 &v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.cg.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+#else
+    *p = v;
+#endif
+}
+DPFHE_HD U64x2 ld_keep(const U64x2 *p) {
+#if defined(__CUDA_ARCH__)
+    return *reinterpret_cast<const U64x2 *>(__builtin_assume_aligned(p, 16));
+#else
+    return *p;
+#endif
+}
+
+// ---- standalone transforms (one limb per call) ----------------------------------------
+// data: [N] coefficients of limb `p`, in place.  buf: N words of shared memory.
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void ntt_fwd_body(CTA &cta, u64 *buf, u64 *data, const Twiddle *tw, const LimbParams &p) {
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(data);
+    cta.par([&](int tid) {
+        fwd_load_stage<LOGN, NT, false>(buf, tw, p, tid, [&](int c) { return ld_stream(src + c); });
+    });
+    fwd_passes<LOGN, NT>(cta, buf, tw, p);
+    U64x2 *dst = reinterpret_cast<U64x2 *>(data);
+    cta.par([&](int tid) {
+        for (int c = tid; c < (1 << (LOGN - 1)); c += NT) {
+            U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)];
+            v.x = canon(v.x, p);
+            v.y = canon(v.y, p);
+            st_stream(dst + c, v);
+        }
+    });
+}
+
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void ntt_inv_body(CTA &cta, u64 *buf, u64 *data, const Twiddle *itw, const LimbParams &p) {
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(data);
+    cta.par([&](int tid) {
+        for (int c = tid; c < (1 << (LOGN - 1)); c += NT)
+            reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = ld_stream(src + c);
+    });
+    inv_passes<LOGN, NT>(cta, buf, itw, p);
+    U64x2 *dst = reinterpret_cast<U64x2 *>(data);
+    cta.par([&](int tid) {
+        inv_store_stage<LOGN, NT>(buf, itw, p, tid, [&](int c, const U64x2 &v) { st_stream(dst + c, v); });
+    });
+}
+
+// ---- element-wise kernels -------------------------------------------------------------
+// chunk-granular (two coefficients); `l` is the limb of the chunk.
+DPFHE_HD U64x2 mul_chunk(const U64x2 &a, const U64x2 &b, const LimbParams &p) {
+    U64x2 r;
+    r.x = mulmod(a.x, b.x, p);
+    r.y = mulmod(a.y, b.y, p);
+    return r;
+}
+
+// 128-bit accumulate of a product
+DPFHE_HD void mac128(u64 &hi, u64 &lo, u64 a, u64 b) {
+    u64 h, l;
+    mul128(a, b, h, l);
+    lo += l;
+    hi += h + (lo < l ? 1ull : 0ull);
+}
+
+// tensor of one coefficient: canonical inputs; d0,d2 in [0,2q), d1 in [0,3q)
+DPFHE_HD void tensor_coeff(u64 a0, u64 a1, u64 b0, u64 b1, const LimbParams &p, u64 &d0, u64 &d1, u64 &d2) {
+    d0 = mulmod_lazy(a0, b0, p);
+    d2 = mulmod_lazy(a1, b1, p);
+    u64 hi, lo;
+    mul128(a0, b1, hi, lo);
+    mac128(hi, lo, a1, b0);
+    d1 = barrett_lazy(hi, lo, p);
+}
+
+// ---- fused key-switch family ------------------------------------------
+// One work item = (ciphertext ct, output limb i).  Shared memory: buf[N] (swizzled transform
+// buffer), acc0[N], acc1[N] (linear, lazy accumulators kept below 4q).
+//   phase 1: build the digit d = d2[i] (tensor / input / permuted c1), initialise
+//            acc = (own terms) + d o key[i][.][i], INTT(d) -> t_i, publish t_i to the slot.
+//   phase 2: for every other digit j: u = NTT_i(t_j mod q_i); acc += u o key[j][.][i];
+//            finally write canon(acc) to out[ct][.][i].
+enum KsMode { KS_MUL_RELIN = 0, KS_PLAIN = 1, KS_ROTATE = 2 };
+
+struct KsArgs {
+    const u64 *a;        // MUL_RELIN: a [batch][2][L][N]; PLAIN: d [batch][L][N]; ROTATE: ct [batch][2][L][N]
+    const u64 *b;        // MUL_RELIN: b
+    const u64 *key;      // [L][2][L][N]
+    u64 *out;            // [batch][2][L][N]
+    u64 *scratch;        // [slots][2 parities][N]
+    const LimbParams *lp;
+    const Twiddle *tw;   // [L][N] forward tables
+    const Twiddle *itw;  // [L][N] inverse tables
+    u32 L;
+    u32 galois;          // ROTATE only
+};
+
+template <int LOGN, int NT, int MODE, class CTA>
+DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const KsArgs &A, size_t ct, u32 i, u64 *t_slot) {
+    constexpr int N = 1 << LOGN, NC = N / 2;
+    const size_t P = (size_t)A.L * N;
+    const LimbParams p = A.lp[i];   // by value: keeps the constants in registers
+    const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + ((size_t)i * 2 + 0) * P + (size_t)i * N);
+    const U64x2 *ka = reinterpret_cast<const U64x2 *>(A.key + ((size_t)i * 2 + 1) * P + (size_t)i * N);
+    const u64 q4 = 2 * p.q2;
+    cta.par([&](int tid) {
+        for (int c = tid; c < NC; c += NT) {
+            U64x2 d, s0, s1;   // digit, own contributions to acc0 / acc1 (lazy < 3q)
+            if (MODE == KS_MUL_RELIN) {
+                const U64x2 *pa0 = reinterpret_cast<const U64x2 *>(A.a + ct * 2 * P + (size_t)i * N);
+                const U64x2 *pa1 = reinterpret_cast<const U64x2 *>(A.a + ct * 2 * P + P + (size_t)i * N);
+                const U64x2 *pb0 = reinterpret_cast<const U64x2 *>(A.b + ct * 2 * P + (size_t)i * N);
+                const U64x2 *pb1 = reinterpret_cast<const U64x2 *>(A.b + ct * 2 * P + P + (size_t)i * N);
+                U64x2 a0 = ld_stream(pa0 + c), a1 = ld_stream(pa1 + c), b0 = ld_stream(pb0 + c), b1 = ld_stream(pb1 + c);
+                tensor_coeff(a0.x, a1.x, b0.x, b1.x, p, s0.x, s1.x, d.x);
+                tensor_coeff(a0.y, a1.y, b0.y, b1.y, p, s0.y, s1.y, d.y);
+            } else if (MODE == KS_PLAIN) {
+                const U64x2 *pd = reinterpret_cast<const U64x2 *>(A.a + ct * P + (size_t)i * N);
+                d = ld_stream(pd + c);
+                s0.x = s0.y = s1.x = s1.y = 0;
+            } else {
+                const u64 *c0 = A.a + ct * 2 * P + (size_t)i * N, *c1 = c0 + P;
+                const int n0 = galois_index<LOGN>(2 * c, A.galois), n1 = galois_index<LOGN>(2 * c + 1, A.galois);
+                d.x = c1[n0];
+                d.y = c1[n1];
+                s0.x = c0[n0];
+                s0.y = c0[n1];
+                s1.x = s1.y = 0;
+            }
+            // digit enters the inverse transform in [0,2q)
+            reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = d;
+            const U64x2 vb = ld_keep(kb + c), va = ld_keep(ka + c);
+            U64x2 r0, r1;
+            r0.x = csub(s0.x + mulmod_lazy(d.x, vb.x, p), q4);
+            r0.y = csub(s0.y + mulmod_lazy(d.y, vb.y, p), q4);
+            r1.x = csub(s1.x + mulmod_lazy(d.x, va.x, p), q4);
+            r1.y = csub(s1.y + mulmod_lazy(d.y, va.y, p), q4);
+            reinterpret_cast<U64x2 *>(acc0)[c] = r0;
+            reinterpret_cast<U64x2 *>(acc1)[c] = r1;
+        }
+    });
+    if (A.L == 1) return;   // no other digit needs t
+    inv_passes<LOGN, NT>(cta, buf, A.itw + (size_t)i * N, p);
+    U64x2 *dst = reinterpret_cast<U64x2 *>(t_slot);
+    cta.par([&](int tid) {
+        inv_store_stage<LOGN, NT>(buf, A.itw + (size_t)i * N, p, tid, [&](int c, const U64x2 &v) { st_cg(dst + c, v); });
+    });
+}
+
+// t_src: the published t of digit j (N words, natural order, canonical mod q_j)
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const KsArgs &A, u32 i, u32 j, const u64 *t_src) {
+    constexpr int N = 1 << LOGN, NC = N / 2;
+    const size_t P = (size_t)A.L * N;
+    const LimbParams p = A.lp[i];   // by value: keeps the constants in registers
+    const Twiddle *tw = A.tw + (size_t)i * N;
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(t_src);
+    cta.par([&](int tid) {
+        fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); });
+    });
+    fwd_passes<LOGN, NT>(cta, buf, tw, p);
+    const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + ((size_t)j * 2 + 0) * P + (size_t)i * N);
+    const U64x2 *ka = reinterpret_cast<const U64x2 *>(A.key + ((size_t)j * 2 + 1) * P + (size_t)i * N);
+    const u64 q4 = 2 * p.q2;
+    cta.par([&](int tid) {
+        for (int c = tid; c < NC; c += NT) {
+            U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)];
+            u.x = word_reduce(u.x, p);   // < 3q
+            u.y = word_reduce(u.y, p);
+            const U64x2 vb = ld_keep(kb + c), va = ld_keep(ka + c);
+            U64x2 r0 = reinterpret_cast<U64x2 *>(acc0)[c], r1 = reinterpret_cast<U64x2 *>(acc1)[c];
+            r0.x = csub(r0.x + mulmod_lazy(u.x, vb.x, p), q4);
+            r0.y = csub(r0.y + mulmod_lazy(u.y, vb.y, p), q4);
+            r1.x = csub(r1.x + mulmod_lazy(u.x, va.x, p), q4);
+            r1.y = csub(r1.y + mulmod_lazy(u.y, va.y, p), q4);
+            reinterpret_cast<U64x2 *>(acc0)[c] = r0;
+            reinterpret_cast<U64x2 *>(acc1)[c] = r1;
+        }
+    });
+}
+
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void ks_finish(CTA &cta, const u64 *acc0, const u64 *acc1, const KsArgs &A, size_t ct, u32 i) {
+    constexpr int N = 1 << LOGN, NC = N / 2;
+    const size_t P = (size_t)A.L * N;
+    const LimbParams p = A.lp[i];   // by value: keeps the constants in registers
+    U64x2 *o0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N);
+    U64x2 *o1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
+    cta.par([&](int tid) {
+        for (int c = tid; c < NC; c += NT) {
+            U64x2 r0 = reinterpret_cast<const U64x2 *>(acc0)[c], r1 = reinterpret_cast<const U64x2 *>(acc1)[c];
+            r0.x = canon4(r0.x, p);
+            r0.y = canon4(r0.y, p);
+            r1.x = canon4(r1.x, p);
+            r1.y = canon4(r1.y, p);
+            st_stream(o0 + c, r0);
+            st_stream(o1 + c, r1);
+        }
+    });
+}
+
+}  // namespace dpfhe

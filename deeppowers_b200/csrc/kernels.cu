@@ -1,0 +1,311 @@
+// kernels.cu — sm_100a kernels and their launchers.
+//
+// No tensor cores (pure 64-bit modular integer work), no Triton, no CPU fallback.
+//   ntt_kernel            one CTA per limb transform, limb resident in swizzled shared memory
+//   ks_fused_kernel       persistent cooperative kernel: tensor / permute -> INTT -> publish digit
+//                         -> (L-1) x [lift + NTT + multiply-accumulate with the switch key] -> out
+//   pointwise kernels     128-bit vectorised grid-stride loops
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include "kernel_bodies.cuh"
+#include "launch.hpp"
+
+namespace dpfhe {
+
+struct DevCta {
+    template <class F>
+    __device__ __forceinline__ void par(F f) {
+        f((int)threadIdx.x);
+        __syncthreads();
+    }
+};
+
+// ------------------------------------------------------------------ standalone transforms
+template <int LOGN, int NT, bool INVERSE>
+__global__ void __launch_bounds__(NT) ntt_kernel(u64 *data, const Twiddle *__restrict__ tables,
+                                                  const LimbParams *__restrict__ lps, u32 L, size_t n_limbs) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    constexpr size_t N = (size_t)1 << LOGN;
+    DevCta cta;
+    for (size_t w = blockIdx.x; w < n_limbs; w += gridDim.x) {
+        const u32 l = (u32)(w % L);
+        const LimbParams p = lps[l];
+        if (INVERSE) ntt_inv_body<LOGN, NT>(cta, buf, data + w * N, tables + (size_t)l * N, p);
+        else ntt_fwd_body<LOGN, NT>(cta, buf, data + w * N, tables + (size_t)l * N, p);
+    }
+}
+
+// ------------------------------------------------------------------ fused key-switch family
+__device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(u32 *p, u32 v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// grid = G CTAs, G a multiple of L, all co-resident (cooperative launch).  CTA `slot` owns output
+// limb i = slot % L of ciphertexts (r*G + slot) / L, r = 0, 1, ...  The L CTAs of one ciphertext sit
+// in adjacent slots of the same round and exchange their INTT'd digits through `scratch`
+// (double-buffered by round parity, L2 resident) under release/acquire flags.
+template <int LOGN, int NT, int MODE>
+__global__ void __launch_bounds__(NT, 1) ks_fused_kernel(KsArgs A, size_t batch, u32 *flags, u32 epoch) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr size_t N = (size_t)1 << LOGN;
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    u64 *acc0 = buf + N, *acc1 = buf + 2 * N;
+    DevCta cta;
+    const u32 L = A.L, G = gridDim.x, slot = blockIdx.x, i = slot % L;
+    const size_t n_work = batch * L;
+    u32 round = 0;
+    for (size_t w = slot; w < n_work; w += G, ++round) {
+        const size_t ct = w / L;
+        const u32 parity = round & 1u;
+        ks_phase1<LOGN, NT, MODE>(cta, buf, acc0, acc1, A, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N);
+        if (L > 1) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_u32(flags + slot, epoch + round + 1);
+            for (u32 jj = 1; jj < L; ++jj) {
+                const u32 j = (i + jj) % L, sib = slot - i + j;
+                if (threadIdx.x == 0) {
+                    while ((int)(ld_acquire_u32(flags + sib) - (epoch + round + 1)) < 0) {
+                    }
+                }
+                __syncthreads();
+                ks_phase2_digit<LOGN, NT>(cta, buf, acc0, acc1, A, i, j, A.scratch + ((size_t)sib * 2 + parity) * N);
+            }
+        }
+        ks_finish<LOGN, NT>(cta, acc0, acc1, A, ct, i);
+    }
+}
+
+// ------------------------------------------------------------------ element-wise kernels
+// all operate on 16-byte chunks; chunk index -> limb = (chunk / (N/2)) % L
+template <int LOGN>
+__global__ void __launch_bounds__(256) pointwise_mul_kernel(const U64x2 *__restrict__ a, const U64x2 *__restrict__ b,
+                                                            U64x2 *__restrict__ out, const LimbParams *__restrict__ lps,
+                                                            u32 L, size_t n_chunks) {
+    constexpr size_t NC = (size_t)1 << (LOGN - 1);
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += (size_t)gridDim.x * blockDim.x) {
+        const LimbParams p = lps[(c / NC) % L];
+        st_stream(out + c, mul_chunk(ld_stream(a + c), ld_stream(b + c), p));
+    }
+}
+
+// ct [batch][2][L][N] x pt [L][N]
+template <int LOGN>
+__global__ void __launch_bounds__(256) ct_mul_plain_kernel(const U64x2 *__restrict__ ct, const U64x2 *__restrict__ pt,
+                                                           U64x2 *__restrict__ out, const LimbParams *__restrict__ lps,
+                                                           u32 L, size_t n_chunks) {
+    constexpr size_t NC = (size_t)1 << (LOGN - 1);
+    const size_t pc = NC * L;   // chunks per polynomial
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += (size_t)gridDim.x * blockDim.x) {
+        const size_t in_poly = c % pc;
+        const LimbParams p = lps[in_poly / NC];
+        st_stream(out + c, mul_chunk(ld_stream(ct + c), ld_keep(pt + in_poly), p));
+    }
+}
+
+// a,b [batch][2][L][N] -> d [batch][3][L][N]; one thread per chunk of one polynomial position
+template <int LOGN>
+__global__ void __launch_bounds__(256) ct_tensor_kernel(const U64x2 *__restrict__ a, const U64x2 *__restrict__ b,
+                                                        U64x2 *__restrict__ d, const LimbParams *__restrict__ lps,
+                                                        u32 L, size_t batch) {
+    constexpr size_t NC = (size_t)1 << (LOGN - 1);
+    const size_t pc = NC * L, total = batch * pc;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t ct = t / pc, in_poly = t % pc;
+        const LimbParams p = lps[in_poly / NC];
+        const U64x2 a0 = ld_stream(a + ct * 2 * pc + in_poly), a1 = ld_stream(a + ct * 2 * pc + pc + in_poly);
+        const U64x2 b0 = ld_stream(b + ct * 2 * pc + in_poly), b1 = ld_stream(b + ct * 2 * pc + pc + in_poly);
+        U64x2 d0, d1, d2;
+        tensor_coeff(a0.x, a1.x, b0.x, b1.x, p, d0.x, d1.x, d2.x);
+        tensor_coeff(a0.y, a1.y, b0.y, b1.y, p, d0.y, d1.y, d2.y);
+        d0.x = canon4(d0.x, p); d0.y = canon4(d0.y, p);
+        d1.x = canon4(d1.x, p); d1.y = canon4(d1.y, p);
+        d2.x = canon4(d2.x, p); d2.y = canon4(d2.y, p);
+        st_stream(d + ct * 3 * pc + in_poly, d0);
+        st_stream(d + ct * 3 * pc + pc + in_poly, d1);
+        st_stream(d + ct * 3 * pc + 2 * pc + in_poly, d2);
+    }
+}
+
+// synthetic residues: x[k] = mulhi64(splitmix64(seed + k), q_limb)
+template <int LOGN>
+__global__ void __launch_bounds__(256) fill_uniform_kernel(U64x2 *__restrict__ out, const LimbParams *__restrict__ lps, u32 L,
+                                                           u64 seed, u64 first_elem, size_t n_chunks) {
+    constexpr size_t NC = (size_t)1 << (LOGN - 1);
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += (size_t)gridDim.x * blockDim.x) {
+        const u64 q = lps[(c / NC) % L].q;
+        U64x2 v;
+        v.x = __umul64hi(splitmix64(seed + first_elem + 2 * c), q);
+        v.y = __umul64hi(splitmix64(seed + first_elem + 2 * c + 1), q);
+        st_stream(out + c, v);
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+template <int LOGN>
+struct Geometry {
+    static constexpr int NT = LOGN == 12 ? 256 : 512;
+    static constexpr size_t LIMB_BYTES = (size_t)8 << LOGN;
+};
+
+static int g_num_sms(int dev) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+template <int LOGN, bool INV>
+static cudaError_t launch_ntt_t(const LaunchCtx &lc, u64 *data, size_t n_limbs, cudaStream_t st) {
+    constexpr int NT = Geometry<LOGN>::NT;
+    auto kern = ntt_kernel<LOGN, NT, INV>;
+    const size_t smem = Geometry<LOGN>::LIMB_BYTES;
+    static bool configured[64] = {};
+    if (!configured[lc.device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[lc.device & 63] = true;
+    }
+    // one CTA per limb transform; the grid-stride loop only matters beyond 2^31-1 limbs
+    const size_t grid = n_limbs < 0x7fffffffull ? n_limbs : 0x7fffffffull;
+    kern<<<(unsigned)grid, NT, smem, st>>>(data, INV ? lc.itw : lc.tw, lc.lp, lc.L, n_limbs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inverse, cudaStream_t st) {
+    const size_t n_limbs = n_polys * lc.L;
+    if (n_limbs == 0) return cudaSuccess;
+    switch (lc.log_n) {
+        case 12: return inverse ? launch_ntt_t<12, true>(lc, data, n_limbs, st) : launch_ntt_t<12, false>(lc, data, n_limbs, st);
+        case 13: return inverse ? launch_ntt_t<13, true>(lc, data, n_limbs, st) : launch_ntt_t<13, false>(lc, data, n_limbs, st);
+        case 14: return inverse ? launch_ntt_t<14, true>(lc, data, n_limbs, st) : launch_ntt_t<14, false>(lc, data, n_limbs, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int LOGN, int MODE>
+static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cudaStream_t st) {
+    constexpr int NT = Geometry<LOGN>::NT;
+    auto kern = ks_fused_kernel<LOGN, NT, MODE>;
+    const size_t smem = 3 * Geometry<LOGN>::LIMB_BYTES;
+    static bool configured[64] = {};
+    if (!configured[lc.device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[lc.device & 63] = true;
+    }
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    size_t G = (size_t)lc.num_sms * occ;
+    if (G > lc.ks_slots) G = lc.ks_slots;
+    G = (G / lc.L) * lc.L;
+    const size_t n_work = batch * lc.L;
+    if (G > n_work) G = n_work;
+    if (G == 0) return cudaErrorInvalidConfiguration;
+    // rounds this launch will consume from the flag epoch space
+    const u32 rounds = (u32)((n_work + G - 1) / G);
+    KsArgs args = A;
+    size_t batch_arg = batch;
+    u32 *flags = lc.ks_flags;
+    u32 epoch = lc.ks_epoch;
+    void *params[] = {&args, &batch_arg, &flags, &epoch};
+    e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)G), dim3(NT), params, smem, st);
+    lc.ks_epoch += rounds;
+    return e;
+}
+
+cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch,
+                      u32 galois, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    KsArgs A;
+    A.a = a; A.b = b; A.key = key; A.out = out; A.scratch = lc.ks_scratch;
+    A.lp = lc.lp; A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L; A.galois = galois;
+#define KS_DISPATCH(LOGN)                                                              \
+    switch (mode) {                                                                    \
+        case KS_MUL_RELIN: return launch_ks_t<LOGN, KS_MUL_RELIN>(lc, A, batch, st);   \
+        case KS_PLAIN: return launch_ks_t<LOGN, KS_PLAIN>(lc, A, batch, st);           \
+        case KS_ROTATE: return launch_ks_t<LOGN, KS_ROTATE>(lc, A, batch, st);         \
+    }                                                                                  \
+    return cudaErrorInvalidValue;
+    switch (lc.log_n) {
+        case 12: KS_DISPATCH(12)
+        case 13: KS_DISPATCH(13)
+    }
+    return cudaErrorNotSupported;
+}
+
+static unsigned ew_grid(const LaunchCtx &lc, size_t work_items) {
+    size_t blocks = (work_items + 255) / 256;
+    const size_t cap = (size_t)lc.num_sms * 32;   // 8 resident CTAs of 256 threads per SM, 4 waves
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks ? blocks : 1);
+}
+
+#define LOGN_SWITCH(call12, call13, call14)  \
+    switch (lc.log_n) {                      \
+        case 12: call12; break;              \
+        case 13: call13; break;              \
+        case 14: call14; break;              \
+        default: return cudaErrorInvalidValue; \
+    }
+
+cudaError_t launch_pointwise_mul(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *out, size_t n_polys, cudaStream_t st) {
+    const size_t n_chunks = n_polys * lc.L * ((size_t)1 << (lc.log_n - 1));
+    if (!n_chunks) return cudaSuccess;
+    const unsigned grid = ew_grid(lc, n_chunks);
+    auto A = reinterpret_cast<const U64x2 *>(a), B = reinterpret_cast<const U64x2 *>(b);
+    auto O = reinterpret_cast<U64x2 *>(out);
+    LOGN_SWITCH((pointwise_mul_kernel<12><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
+                (pointwise_mul_kernel<13><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
+                (pointwise_mul_kernel<14><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)))
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ct_mul_plain(const LaunchCtx &lc, const u64 *ct, const u64 *pt, u64 *out, size_t batch, cudaStream_t st) {
+    const size_t n_chunks = batch * 2 * lc.L * ((size_t)1 << (lc.log_n - 1));
+    if (!n_chunks) return cudaSuccess;
+    const unsigned grid = ew_grid(lc, n_chunks);
+    auto A = reinterpret_cast<const U64x2 *>(ct), B = reinterpret_cast<const U64x2 *>(pt);
+    auto O = reinterpret_cast<U64x2 *>(out);
+    LOGN_SWITCH((ct_mul_plain_kernel<12><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
+                (ct_mul_plain_kernel<13><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
+                (ct_mul_plain_kernel<14><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)))
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ct_tensor(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *d, size_t batch, cudaStream_t st) {
+    const size_t items = batch * lc.L * ((size_t)1 << (lc.log_n - 1));
+    if (!items) return cudaSuccess;
+    const unsigned grid = ew_grid(lc, items);
+    auto A = reinterpret_cast<const U64x2 *>(a), B = reinterpret_cast<const U64x2 *>(b);
+    auto D = reinterpret_cast<U64x2 *>(d);
+    LOGN_SWITCH((ct_tensor_kernel<12><<<grid, 256, 0, st>>>(A, B, D, lc.lp, lc.L, batch)),
+                (ct_tensor_kernel<13><<<grid, 256, 0, st>>>(A, B, D, lc.lp, lc.L, batch)),
+                (ct_tensor_kernel<14><<<grid, 256, 0, st>>>(A, B, D, lc.lp, lc.L, batch)))
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_uniform(const LaunchCtx &lc, u64 seed, u64 first_poly, u64 *data, size_t n_polys, cudaStream_t st) {
+    const size_t P = (size_t)lc.L << lc.log_n;
+    const size_t n_chunks = n_polys * P / 2;
+    if (!n_chunks) return cudaSuccess;
+    const unsigned grid = ew_grid(lc, n_chunks);
+    auto O = reinterpret_cast<U64x2 *>(data);
+    const u64 first_elem = first_poly * P;
+    LOGN_SWITCH((fill_uniform_kernel<12><<<grid, 256, 0, st>>>(O, lc.lp, lc.L, seed, first_elem, n_chunks)),
+                (fill_uniform_kernel<13><<<grid, 256, 0, st>>>(O, lc.lp, lc.L, seed, first_elem, n_chunks)),
+                (fill_uniform_kernel<14><<<grid, 256, 0, st>>>(O, lc.lp, lc.L, seed, first_elem, n_chunks)))
+    return cudaGetLastError();
+}
+
+int query_num_sms(int dev) { return g_num_sms(dev); }
+
+}  // namespace dpfhe

@@ -1,0 +1,33 @@
+// launch.hpp — interface between the C ABI (abi.cu) and the kernel launchers (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernel_bodies.cuh"
+
+namespace dpfhe {
+
+// device-resident state shared by all launches of one context
+struct LaunchCtx {
+    int device = 0;
+    int num_sms = 0;
+    u32 log_n = 0, L = 0;
+    const LimbParams *lp = nullptr;   // [L]
+    const Twiddle *tw = nullptr;      // [L][N] forward twiddles, device layout (ntt_core.cuh:tw_pos)
+    const Twiddle *itw = nullptr;     // [L][N] inverse twiddles
+    // fused key-switch pipeline
+    u64 *ks_scratch = nullptr;        // [ks_slots][2][N] digit exchange buffers
+    u32 *ks_flags = nullptr;          // [ks_slots] monotonically increasing round counters
+    size_t ks_slots = 0;
+    u32 ks_epoch = 0;                 // rounds consumed so far (flag values already used)
+};
+
+int query_num_sms(int dev);
+cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inverse, cudaStream_t st);
+cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch,
+                      u32 galois, cudaStream_t st);
+cudaError_t launch_pointwise_mul(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *out, size_t n_polys, cudaStream_t st);
+cudaError_t launch_ct_mul_plain(const LaunchCtx &lc, const u64 *ct, const u64 *pt, u64 *out, size_t batch, cudaStream_t st);
+cudaError_t launch_ct_tensor(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *d, size_t batch, cudaStream_t st);
+cudaError_t launch_fill_uniform(const LaunchCtx &lc, u64 seed, u64 first_poly, u64 *data, size_t n_polys, cudaStream_t st);
+
+}  // namespace dpfhe

@@ -1,0 +1,122 @@
+// modarith.cuh — 64-bit modular arithmetic for moduli 2^33 < q < 2^60.
+//
+// Everything is __host__ __device__ so the same code is exercised by the host emulator
+// in tests/emu (test infrastructure; never part of libdpfhe.so's product path).
+//
+// Lazy-range conventions ("bound B" means value < B*q; 16q < 2^64 because q < 2^60):
+//   shoup_lazy(x, w)      any 64-bit x        -> [0, 2q)
+//   word_reduce(x)        any 64-bit x        -> [0, 3q)   (3 integer multiplies)
+//   barrett_lazy(a*b)     a*b < 2^(2b+4)      -> [0, 3q)   (b = bit length of q)
+//   canon(x)              x < 16q             -> [0, q)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DPFHE_HD __host__ __device__ __forceinline__
+#else
+#define DPFHE_HD inline
+#endif
+
+namespace dpfhe {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+struct alignas(16) U64x2 {
+    u64 x, y;
+};
+
+// Per-limb constants (host-built in params.cpp, resident in device global memory).
+struct alignas(16) LimbParams {
+    u64 q;           // modulus
+    u64 q2;          // 2q
+    u64 bar_mu;      // floor(2^(bar_shift+64) / q)
+    u64 ninv;        // N^-1 mod q                    } folded into the last inverse stage
+    u64 ninv_s;      // Shoup companion of ninv
+    u64 wninv;       // psi^-bitrev(1) * N^-1 mod q
+    u64 wninv_s;     // Shoup companion of wninv
+    u32 bar_shift;   // bitlen(q) - 2
+    u32 mu32;        // floor(2^64 / q)  (< 2^31 because q > 2^33)
+};
+
+DPFHE_HD u64 umulhi64(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+DPFHE_HD u32 umulhi32(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (u32)(((u64)a * b) >> 32);
+#endif
+}
+
+// x >= m ? x - m : x, branch-free.  Correct for every 64-bit x when m <= 2^63.
+DPFHE_HD u64 csub(u64 x, u64 m) {
+    u64 t = x - m;
+    return t < x ? t : x;   // unsigned wrap makes t > x exactly when x < m
+}
+
+// Shoup multiplication by a fixed w < q with ws = floor(w * 2^64 / q): valid for ANY 64-bit x.
+DPFHE_HD u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {
+    u64 h = umulhi64(x, ws);
+    return x * w - h * q;   // in [0, 2q)
+}
+
+// One-word quotient estimate: k = floor(x_hi * mu32 / 2^32) <= floor(x/q), off by at most 2.
+DPFHE_HD u64 word_reduce(u64 x, const LimbParams &p) {
+    u32 k = umulhi32((u32)(x >> 32), p.mu32);
+    return x - (u64)k * p.q;   // in [0, 3q)
+}
+
+// 128-bit product (hi:lo) of two 64-bit words.
+DPFHE_HD void mul128(u64 a, u64 b, u64 &hi, u64 &lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umul64hi(a, b);
+#else
+    unsigned __int128 z = (unsigned __int128)a * b;
+    lo = (u64)z;
+    hi = (u64)(z >> 64);
+#endif
+}
+
+// Barrett reduction of z = hi:lo.  Requires z < 2^(2b+4) (e.g. both factors < 4q), gives [0, 3q).
+// With both factors < q the result is in [0, 2q).
+DPFHE_HD u64 barrett_lazy(u64 hi, u64 lo, const LimbParams &p) {
+    const u32 s = p.bar_shift;                       // 31 <= s <= 58
+    u64 zt = (hi << (64 - s)) | (lo >> s);           // floor(z / 2^s) < 2^64
+    u64 qh = umulhi64(zt, p.bar_mu);
+    return lo - qh * p.q;
+}
+
+DPFHE_HD u64 mulmod_lazy(u64 a, u64 b, const LimbParams &p) {
+    u64 hi, lo;
+    mul128(a, b, hi, lo);
+    return barrett_lazy(hi, lo, p);
+}
+
+// x < 16q  ->  [0, q)
+DPFHE_HD u64 canon(u64 x, const LimbParams &p) {
+    u64 r = word_reduce(x, p);   // < 3q
+    r = csub(r, p.q2);
+    return csub(r, p.q);
+}
+// x < 4q -> [0, q)
+DPFHE_HD u64 canon4(u64 x, const LimbParams &p) { return csub(csub(x, p.q2), p.q); }
+
+DPFHE_HD u64 mulmod(u64 a, u64 b, const LimbParams &p) { return canon4(mulmod_lazy(a, b, p), p); }
+
+// splitmix64 finaliser, the synthetic-data hash of DESIGN.md §5
+DPFHE_HD u64 splitmix64(u64 x) {
+    u64 z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+}  // namespace dpfhe

@@ -1,0 +1,289 @@
+// ntt_core.cuh — the in-shared-memory negacyclic NTT of one limb.
+//
+// A limb of N = 2^LOGN coefficients lives in shared memory in the TMA SWIZZLE_128B
+// layout (16-byte chunk index XOR row index mod 8, rows of 128 B = 16 coefficients), so
+// that every access pattern below is bank-conflict free:
+//   - "column" accesses (32 lanes -> 32 consecutive coefficients, 8 B each),
+//   - "row" accesses (each lane owns one whole 128-B row, 16 B at a time).
+//
+// The transform is split as  [K = LOGN-12 outer stages, fused into the global load/store]
+//                          + [three radix-16 register passes A, B, C over shared memory].
+// Forward = Cooley-Tukey butterflies, natural -> bit-reversed order, twist merged (Harvey);
+// inverse = Gentleman-Sande, bit-reversed -> natural, N^-1 folded into the last stage.
+//
+// All functions are __host__ __device__: tests/emu runs the identical code on the CPU
+// thread-by-thread to check the index algebra against the oracle (test infrastructure only).
+#pragma once
+#include "modarith.cuh"
+
+namespace dpfhe {
+
+// (w, floor(w*2^64/q)) pairs, 16 B each, so one 128-bit load fetches a twiddle.
+typedef U64x2 Twiddle;
+
+// ---- shared-memory layout -------------------------------------------------------------
+// coefficient index -> u64 slot (TMA SWIZZLE_128B: chunk ^= row & 7)
+DPFHE_HD int swz(int idx) { return idx ^ (((idx >> 4) & 7) << 1); }
+// 16-byte chunk index (two coefficients) -> chunk slot
+DPFHE_HD int swz_chunk(int cg) { return cg ^ ((cg >> 3) & 7); }
+
+// ---- twiddle table layout (must match params.cpp:tw_pos) --------------------------------
+// natural index of the twiddle of group i at stage s is 2^s + i.  Stages of the last
+// register pass (s >= LOGN-4) are stored transposed so that lane-consecutive rows read
+// consecutive table entries:  i = row * 2^u + j  ->  2^s + j * (N/16) + row,  u = s - (LOGN-4).
+template <int LOGN>
+DPFHE_HD int tw_pos(int s, int i) {
+    if (s < LOGN - 4) return (1 << s) + i;
+    const int u = s - (LOGN - 4);
+    const int row = i >> u, j = i & ((1 << u) - 1);
+    return (1 << s) + j * (1 << (LOGN - 4)) + row;
+}
+
+// ---- butterflies -----------------------------------------------------------------------
+// forward, fully lazy: x' = x + w*y, y' = x - w*y + 2q; bound grows by 2 per stage.
+DPFHE_HD void ct_bfly(u64 &x, u64 &y, const Twiddle &w, const LimbParams &p) {
+    u64 t = shoup_lazy(y, w.x, w.y, p.q);
+    u64 a = x;
+    x = a + t;
+    y = a + p.q2 - t;
+}
+// inverse, Harvey: inputs and outputs in [0, 2q)
+DPFHE_HD void gs_bfly(u64 &x, u64 &y, const Twiddle &w, const LimbParams &p) {
+    u64 a = x, b = y;
+    x = csub(a + b, p.q2);
+    y = shoup_lazy(a + p.q2 - b, w.x, w.y, p.q);
+}
+
+// 16-point register kernels.  `x[k]` holds element k of a radix-16 group; stage u pairs
+// k with k + (8 >> u).  tw(u, j) returns the twiddle of sub-group j at local stage u.
+template <class TW>
+DPFHE_HD void fwd16(u64 (&x)[16], const LimbParams &p, TW tw) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int half = 8 >> u;
+#pragma unroll
+        for (int j = 0; j < (1 << u); ++j) {
+            const Twiddle w = tw(u, j);
+#pragma unroll
+            for (int i = 0; i < half; ++i) ct_bfly(x[j * 2 * half + i], x[j * 2 * half + half + i], w, p);
+        }
+    }
+}
+template <class TW>
+DPFHE_HD void inv16(u64 (&x)[16], const LimbParams &p, TW tw) {
+#pragma unroll
+    for (int u = 3; u >= 0; --u) {
+        const int half = 8 >> u;
+#pragma unroll
+        for (int j = 0; j < (1 << u); ++j) {
+            const Twiddle w = tw(u, j);
+#pragma unroll
+            for (int i = 0; i < half; ++i) gs_bfly(x[j * 2 * half + i], x[j * 2 * half + half + i], w, p);
+        }
+    }
+}
+
+// ---- register passes over shared memory ----------------------------------------------
+// A pass covers stages [S0, S0+4).  Group p in [0, N/16) splits as (hi, lo) with
+// lo = p mod 2^NLO, NLO = LOGN-S0-4; its 16 elements are idx = hi*2^(LOGN-S0) + k*2^NLO + lo.
+// Thread `tid` of NT handles groups p = tid + g*NT.
+// REDUCE: apply word_reduce to every element on load (keeps the lazy bound under 16q).
+
+template <int LOGN, int S0, int NT, bool REDUCE>
+DPFHE_HD void fwd_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid) {
+    constexpr int NLO = LOGN - S0 - 4;
+    constexpr int NGROUPS = 1 << (LOGN - 4);
+    static_assert(NLO == 0 || NLO >= 4, "pass split must keep column accesses row-aligned");
+#pragma unroll 1
+    for (int g = tid; g < NGROUPS; g += NT) {
+        const int lo = g & ((1 << NLO) - 1), hi = g >> NLO;
+        const int base = (hi << (LOGN - S0)) + lo;
+        u64 x[16];
+        if (NLO == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(g * 8 + c)];
+                x[2 * c] = v.x;
+                x[2 * c + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = buf[swz(base + (k << NLO))];
+        }
+        if (REDUCE) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = word_reduce(x[k], p);
+        }
+        fwd16(x, p, [&](int u, int j) { return tw[tw_pos<LOGN>(S0 + u, (hi << u) + j)]; });
+        if (NLO == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                U64x2 v;
+                v.x = x[2 * c];
+                v.y = x[2 * c + 1];
+                reinterpret_cast<U64x2 *>(buf)[swz_chunk(g * 8 + c)] = v;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) buf[swz(base + (k << NLO))] = x[k];
+        }
+    }
+}
+
+template <int LOGN, int S0, int NT>
+DPFHE_HD void inv_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid) {
+    constexpr int NLO = LOGN - S0 - 4;
+    constexpr int NGROUPS = 1 << (LOGN - 4);
+    static_assert(NLO == 0 || NLO >= 4, "pass split must keep column accesses row-aligned");
+#pragma unroll 1
+    for (int g = tid; g < NGROUPS; g += NT) {
+        const int lo = g & ((1 << NLO) - 1), hi = g >> NLO;
+        const int base = (hi << (LOGN - S0)) + lo;
+        u64 x[16];
+        if (NLO == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(g * 8 + c)];
+                x[2 * c] = v.x;
+                x[2 * c + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = buf[swz(base + (k << NLO))];
+        }
+        inv16(x, p, [&](int u, int j) { return tw[tw_pos<LOGN>(S0 + u, (hi << u) + j)]; });
+        if (NLO == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                U64x2 v;
+                v.x = x[2 * c];
+                v.y = x[2 * c + 1];
+                reinterpret_cast<U64x2 *>(buf)[swz_chunk(g * 8 + c)] = v;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) buf[swz(base + (k << NLO))] = x[k];
+        }
+    }
+}
+
+// ---- outer stages fused with the global <-> shared copies -----------------------------
+// K = LOGN-12 outer stages (radix 2^K across the limb).  Work item c in [0, N/2/2^K) names a
+// 16-byte chunk column: coefficients n = 2c, 2c+1 of each of the 2^K blocks of size N/2^K.
+
+// SRC(chunk_index) -> U64x2 loads the 16-byte chunk `chunk_index` of the source limb.
+// IN_REDUCE: the source is not canonical for this modulus (key-switch digit lift): word_reduce it.
+template <int LOGN, int NT, bool IN_REDUCE, class SRC>
+DPFHE_HD void fwd_load_stage(u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid, SRC src) {
+    constexpr int K = LOGN - 12;
+    constexpr int NB = 1 << K;                  // blocks
+    constexpr int CPB = (1 << (LOGN - 1)) / NB; // chunks per block
+#pragma unroll 1
+    for (int c = tid; c < CPB; c += NT) {
+        u64 x[NB][2];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            U64x2 v = src(b * CPB + c);
+            x[b][0] = IN_REDUCE ? word_reduce(v.x, p) : v.x;
+            x[b][1] = IN_REDUCE ? word_reduce(v.y, p) : v.y;
+        }
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            const int half = NB >> (u + 1);
+#pragma unroll
+            for (int j = 0; j < (1 << u); ++j) {
+                const Twiddle w = tw[tw_pos<LOGN>(u, j)];
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                    ct_bfly(x[j * 2 * half + i][0], x[j * 2 * half + half + i][0], w, p);
+                    ct_bfly(x[j * 2 * half + i][1], x[j * 2 * half + half + i][1], w, p);
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            U64x2 v;
+            v.x = x[b][0];
+            v.y = x[b][1];
+            reinterpret_cast<U64x2 *>(buf)[swz_chunk(b * CPB + c)] = v;
+        }
+    }
+}
+
+// Inverse counterpart: reads shared memory (values in [0,2q)), applies the K outermost
+// Gentleman-Sande stages with N^-1 folded into the very last one, and hands canonical
+// chunks to DST(chunk_index, U64x2).
+template <int LOGN, int NT, class DST>
+DPFHE_HD void inv_store_stage(const u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid, DST dst) {
+    constexpr int K = LOGN - 12;
+    constexpr int NB = 1 << K;
+    constexpr int CPB = (1 << (LOGN - 1)) / NB;
+#pragma unroll 1
+    for (int c = tid; c < CPB; c += NT) {
+        u64 x[NB][2];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(b * CPB + c)];
+            x[b][0] = v.x;
+            x[b][1] = v.y;
+        }
+#pragma unroll
+        for (int u = K - 1; u >= 1; --u) {
+            const int half = NB >> (u + 1);
+#pragma unroll
+            for (int j = 0; j < (1 << u); ++j) {
+                const Twiddle w = tw[tw_pos<LOGN>(u, j)];
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                    gs_bfly(x[j * 2 * half + i][0], x[j * 2 * half + half + i][0], w, p);
+                    gs_bfly(x[j * 2 * half + i][1], x[j * 2 * half + half + i][1], w, p);
+                }
+            }
+        }
+        if (K >= 1) {
+            // stage 0: x' = (x + y) * N^-1, y' = (x - y) * (w * N^-1)
+#pragma unroll
+            for (int i = 0; i < NB / 2; ++i) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    u64 a = x[i][e], b = x[NB / 2 + i][e];
+                    x[i][e] = csub(shoup_lazy(a + b, p.ninv, p.ninv_s, p.q), p.q);
+                    x[NB / 2 + i][e] = csub(shoup_lazy(a + p.q2 - b, p.wninv, p.wninv_s, p.q), p.q);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) x[0][e] = csub(shoup_lazy(x[0][e], p.ninv, p.ninv_s, p.q), p.q);
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            U64x2 v;
+            v.x = x[b][0];
+            v.y = x[b][1];
+            dst(b * CPB + c, v);
+        }
+    }
+}
+
+// ---- whole-limb drivers --------------------------------------------------------------
+// `cta.sync()` is __syncthreads() on the device and a no-op in the emulator, where
+// `cta.par(f)` runs f(tid) for every thread of the CTA before returning.
+
+// forward: buf already holds the output of fwd_load_stage (lazy bound BIN + 2K <= 8)
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void fwd_passes(CTA &cta, u64 *buf, const Twiddle *tw, const LimbParams &p) {
+    constexpr int K = LOGN - 12;
+    cta.par([&](int tid) { fwd_pass<LOGN, K, NT, false>(buf, tw, p, tid); });      // bound <= 15
+    cta.par([&](int tid) { fwd_pass<LOGN, K + 4, NT, true>(buf, tw, p, tid); });   // 3 -> 11
+    cta.par([&](int tid) { fwd_pass<LOGN, K + 8, NT, true>(buf, tw, p, tid); });   // 3 -> 11
+}
+// inverse: buf holds [0,2q) values in bit-reversed order; afterwards run inv_store_stage
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void inv_passes(CTA &cta, u64 *buf, const Twiddle *itw, const LimbParams &p) {
+    constexpr int K = LOGN - 12;
+    cta.par([&](int tid) { inv_pass<LOGN, K + 8, NT>(buf, itw, p, tid); });
+    cta.par([&](int tid) { inv_pass<LOGN, K + 4, NT>(buf, itw, p, tid); });
+    cta.par([&](int tid) { inv_pass<LOGN, K, NT>(buf, itw, p, tid); });
+}
+
+}  // namespace dpfhe

@@ -1,0 +1,185 @@
+"""Host-side mirror of the C++ `deeppowers::api::fhe` wrappers (include/deeppowers_fhe.hpp).
+
+Thin, allocation-free calls into the C ABI.  Device buffers are torch tensors (any 8-byte
+integer dtype, contiguous, on the context's device) or raw device pointers; host buffers are
+C-contiguous numpy uint64 arrays.  Errors surface as RuntimeError carrying dpfhe_last_error(),
+mirroring the reference's std::runtime_error convention (src/core/hal/cuda/cuda_device.cpp:9-16).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class DpfheError(RuntimeError):
+    pass
+
+
+def _ptr(x):
+    """device pointer of a torch tensor / int; validates dtype width and contiguity"""
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if hasattr(x, "data_ptr"):
+        if x.element_size() != 8 or not x.is_contiguous():
+            raise ValueError("device buffers must be contiguous 8-byte integer tensors")
+        if not x.is_cuda:
+            raise ValueError("expected a CUDA tensor (use the *_host entry points for host arrays)")
+        return C.c_void_p(x.data_ptr())
+    raise TypeError("unsupported buffer type %r" % type(x))
+
+
+def _hptr(a, writable=False):
+    if not isinstance(a, np.ndarray) or a.dtype != np.uint64 or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("host buffers must be C-contiguous numpy uint64 arrays")
+    if writable and not a.flags["WRITEABLE"]:
+        raise ValueError("output array is read-only")
+    return C.c_void_p(a.ctypes.data)
+
+
+_CUDA_STREAM_LEGACY = 1   # cudaStreamLegacy: the ABI reserves NULL for "the context's own stream"
+
+
+def _stream(s):
+    """cudaStream_t for the ABI.  None -> torch's current stream (so torch-side copies/events are ordered
+    with our kernels); an int is passed through; objects must expose .cuda_stream."""
+    if s is None:
+        import torch
+        h = torch.cuda.current_stream().cuda_stream
+    elif isinstance(s, int):
+        h = s
+    else:
+        h = s.cuda_stream
+    return C.c_void_p(h if h else _CUDA_STREAM_LEGACY)
+
+
+class Context:
+    """One parameter set bound to one GPU (dpfhe_ctx).  Not thread-safe; one per GPU/process."""
+
+    def __init__(self, log_n, n_limbs, moduli=None, device=0):
+        self._l = _lib.load()
+        self._h = C.c_void_p()
+        arr = None
+        if moduli is not None:
+            if len(moduli) != n_limbs:
+                raise ValueError("need exactly n_limbs moduli")
+            arr = (C.c_uint64 * n_limbs)(*[int(m) for m in moduli])
+        p = _lib.dpfhe_params(log_n, n_limbs, arr)
+        rc = self._l.dpfhe_context_create(C.byref(p), int(device), C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise DpfheError(self._l.dpfhe_last_error().decode())
+        self.log_n, self.L, self.N = log_n, n_limbs, 1 << log_n
+        self.P = self.L * self.N
+        self.device = device
+        self.moduli, self.psi = [], []
+        for l in range(n_limbs):
+            v = C.c_uint64()
+            self._chk(self._l.dpfhe_get_modulus(self._h, l, C.byref(v)))
+            self.moduli.append(v.value)
+            self._chk(self._l.dpfhe_get_psi(self._h, l, C.byref(v)))
+            self.psi.append(v.value)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._l.dpfhe_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise DpfheError(self._l.dpfhe_last_error().decode())
+
+    # ---- introspection
+    def root_powers(self, limb, inverse=False):
+        out = np.empty(self.N, dtype=np.uint64)
+        self._chk(self._l.dpfhe_get_root_powers(self._h, limb, int(inverse), _hptr(out, True)))
+        return out
+
+    def launch_count(self):
+        return int(self._l.dpfhe_launch_count(self._h))
+
+    def device_bytes(self):
+        return int(self._l.dpfhe_context_device_bytes(self._h))
+
+    def describe(self):
+        buf = C.create_string_buffer(1024)
+        self._l.dpfhe_describe(self._h, buf, 1024)
+        return buf.value.decode()
+
+    # ---- device-pointer ops (asynchronous on `stream`, default: torch's current stream)
+    def ntt_fwd(self, data, n_polys, stream=None):
+        self._chk(self._l.dpfhe_ntt_fwd(self._h, _ptr(data), n_polys, _stream(stream)))
+
+    def ntt_inv(self, data, n_polys, stream=None):
+        self._chk(self._l.dpfhe_ntt_inv(self._h, _ptr(data), n_polys, _stream(stream)))
+
+    def poly_mul_pointwise(self, a, b, out, n_polys, stream=None):
+        self._chk(self._l.dpfhe_poly_mul_pointwise(self._h, _ptr(a), _ptr(b), _ptr(out), n_polys, _stream(stream)))
+
+    def ct_tensor(self, a, b, d, batch, stream=None):
+        self._chk(self._l.dpfhe_ct_tensor(self._h, _ptr(a), _ptr(b), _ptr(d), batch, _stream(stream)))
+
+    def keyswitch(self, d, key, out, batch, stream=None):
+        self._chk(self._l.dpfhe_keyswitch(self._h, _ptr(d), _ptr(key), _ptr(out), batch, _stream(stream)))
+
+    def ct_mul_relin(self, a, b, evk, out, batch, stream=None):
+        self._chk(self._l.dpfhe_ct_mul_relin(self._h, _ptr(a), _ptr(b), _ptr(evk), _ptr(out), batch, _stream(stream)))
+
+    def ct_mul_plain(self, ct, pt, out, batch, stream=None):
+        self._chk(self._l.dpfhe_ct_mul_plain(self._h, _ptr(ct), _ptr(pt), _ptr(out), batch, _stream(stream)))
+
+    def rotate(self, ct, galois_elt, gk, out, batch, stream=None):
+        self._chk(self._l.dpfhe_rotate(self._h, _ptr(ct), int(galois_elt), _ptr(gk), _ptr(out), batch, _stream(stream)))
+
+    def fill_uniform(self, seed, data, n_polys, first_poly=0, stream=None):
+        self._chk(self._l.dpfhe_fill_uniform(self._h, int(seed), int(first_poly), _ptr(data), n_polys, _stream(stream)))
+
+    # ---- host-buffer ops (synchronous; H2D/compute/D2H pipelined inside the library)
+    def ntt_fwd_host(self, data):
+        self._chk(self._l.dpfhe_ntt_fwd_host(self._h, _hptr(data, True), data.size // self.P))
+
+    def ntt_inv_host(self, data):
+        self._chk(self._l.dpfhe_ntt_inv_host(self._h, _hptr(data, True), data.size // self.P))
+
+    def ct_mul_relin_host(self, a, b, evk, out):
+        self._chk(self._l.dpfhe_ct_mul_relin_host(self._h, _hptr(a), _hptr(b), _hptr(evk), _hptr(out, True), a.size // (2 * self.P)))
+
+    def ct_mul_plain_host(self, ct, pt, out):
+        self._chk(self._l.dpfhe_ct_mul_plain_host(self._h, _hptr(ct), _hptr(pt), _hptr(out, True), ct.size // (2 * self.P)))
+
+    def rotate_host(self, ct, galois_elt, gk, out):
+        self._chk(self._l.dpfhe_rotate_host(self._h, _hptr(ct), int(galois_elt), _hptr(gk), _hptr(out, True), ct.size // (2 * self.P)))
+
+    def galois_elt(self, k):
+        """Galois element 5^k mod 2N of a rotation by k slots (k may be negative)."""
+        return pow(5, k % (self.N // 2), 2 * self.N)
+
+
+def pinned_empty(n_words):
+    """numpy uint64 array over pinned host memory from dpfhe_host_alloc (freed when garbage collected)."""
+    l = _lib.load()
+    p = C.c_void_p()
+    if l.dpfhe_host_alloc(C.byref(p), n_words * 8) != 0:
+        raise DpfheError(l.dpfhe_last_error().decode())
+    buf = (C.c_uint64 * n_words).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint64)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                l.dpfhe_host_free(self.ptr)
+            except Exception:
+                pass
+
+    owner = _Owner(p)
+    holder = np.lib.stride_tricks.as_strided(arr)   # view keeping `arr` alive
+    _PINNED_OWNERS[id(holder)] = (owner, buf)
+    return holder
+
+
+_PINNED_OWNERS = {}

@@ -1,0 +1,135 @@
+/*
+ * dpfhe.h — C ABI of the B200-native FHE ciphertext-arithmetic engine (libdpfhe.so).
+ *
+ * This is the drop-in boundary for the hot path named by BASELINE.json:north_star:
+ * RNS negacyclic NTT/INTT, Barrett pointwise multiply, key-switch / relinearise,
+ * ct x ct, ct x pt and rotate.  The reference (deeppowers/deeppowers @1cf6449) has NO
+ * FFI or operator for this path (SURVEY.md §0, §8a row a-0, §8b "Nothing calls an FHE
+ * boundary today"), so each entry point below cites the reference interface whose
+ * *conventions* it follows rather than one it replaces:
+ *
+ *   - device-bound context owning its tables, freed in destroy:
+ *       hal::CUDADevice ctor/dtor        src/core/hal/cuda/cuda_device.cpp:18-41
+ *   - cudaSetDevice at the top of every call, one default stream per device:
+ *       src/core/hal/cuda/cuda_device.cpp:23,64,79
+ *   - errors: the reference throws std::runtime_error from CUDA_CHECK
+ *       (cuda_device.cpp:9-16); exceptions cannot cross a C ABI, so every call
+ *       returns a status and the message is fetched with dpfhe_last_error();
+ *       the C++ wrapper (include/deeppowers_fhe.hpp) re-throws std::runtime_error.
+ *   - caller-owned data buffers, as hal::Tensor buffers are owned by their creator
+ *       src/core/hal/cuda/cuda_tensor.cpp:36-58
+ *   - the public API the examples include and that the wrapper attaches to:
+ *       src/api/cpp/include/deeppowers.hpp:41-87
+ *
+ * Layouts (uint64 little-endian, row-major, all residues canonical in [0, q_l)):
+ *   polynomial [L][N]; ciphertext [2][L][N] (c0,c1) in evaluation (NTT) form;
+ *   batch [batch][2][L][N]; switch key [L digits][2 {b,a}][L limbs][N] evaluation form;
+ *   plaintext [L][N] evaluation form.
+ * Ring Z_q[X]/(X^N+1); forward NTT natural -> bit-reversed order, inverse the opposite
+ * (DESIGN.md §2).  Inputs outside [0,q_l) give unspecified (but memory-safe) results.
+ *
+ * Threading: a context is bound to one device and is NOT thread-safe; use one context
+ * per host thread / GPU (matches the reference's one-default-stream-per-device usage).
+ * `stream` is a cudaStream_t passed as void* (NULL = the context's own stream).
+ * Device-pointer entry points are asynchronous with respect to the host.
+ * There is no CPU fallback: without a usable CUDA device dpfhe_context_create fails.
+ */
+#ifndef DPFHE_H
+#define DPFHE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPFHE_MAX_LIMBS 16
+
+typedef struct dpfhe_ctx dpfhe_ctx;
+
+typedef struct dpfhe_params {
+    uint32_t log_n;         /* N = 1 << log_n; supported: 12, 13, 14                       */
+    uint32_t n_limbs;       /* L in [1, DPFHE_MAX_LIMBS]                                   */
+    const uint64_t *moduli; /* L distinct primes, 2^33 < q < 2^60, q = 1 mod 2N; NULL =    */
+                            /* derive the L largest such primes below 2^60 */
+} dpfhe_params;
+
+enum {
+    DPFHE_OK = 0,
+    DPFHE_ERR_INVALID = -1,    /* bad argument / unsupported parameter set */
+    DPFHE_ERR_CUDA = -2,       /* CUDA runtime error (message has file:line) */
+    DPFHE_ERR_NOMEM = -3
+};
+
+/* thread-local message of the last failing call on this thread */
+const char *dpfhe_last_error(void);
+/* library / build identification, e.g. "dpfhe 0.1 sm_100a" */
+const char *dpfhe_version(void);
+
+/* ---- context ---- */
+int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out);
+void dpfhe_context_destroy(dpfhe_ctx *ctx);
+int dpfhe_get_modulus(const dpfhe_ctx *ctx, uint32_t limb, uint64_t *q);
+int dpfhe_get_psi(const dpfhe_ctx *ctx, uint32_t limb, uint64_t *psi);
+/* copies psi^bitrev(i), i<N (inverse: psi^-bitrev(i)) in natural table order to a HOST buffer of N words */
+int dpfhe_get_root_powers(const dpfhe_ctx *ctx, uint32_t limb, int inverse, uint64_t *h_out);
+/* bytes of device scratch the context holds (tables + pipeline scratch), for reporting */
+size_t dpfhe_context_device_bytes(const dpfhe_ctx *ctx);
+
+/* ---- transforms: d_data is [n_polys][L][N], in place ---- */
+int dpfhe_ntt_fwd(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream);
+int dpfhe_ntt_inv(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream);
+
+/* ---- pointwise ---- */
+/* out[p][l][n] = a*b mod q_l, [n_polys][L][N]; out may alias a or b */
+int dpfhe_poly_mul_pointwise(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out,
+                             size_t n_polys, void *stream);
+/* a,b: [batch][2][L][N] -> d: [batch][3][L][N] (d0,d1,d2) */
+int dpfhe_ct_tensor(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_d,
+                    size_t batch, void *stream);
+
+/* ---- key switching ---- */
+/* d: [batch][L][N] (evaluation form) -> out: [batch][2][L][N] = sum_j NTT(INTT(d[j])) o key[j] */
+int dpfhe_keyswitch(dpfhe_ctx *ctx, const uint64_t *d_d, const uint64_t *d_key, uint64_t *d_out,
+                    size_t batch, void *stream);
+/* out = relinearise(a (x) b); a,b,out: [batch][2][L][N]; out must not alias a or b */
+int dpfhe_ct_mul_relin(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, const uint64_t *d_evk,
+                       uint64_t *d_out, size_t batch, void *stream);
+/* out = (c0 o pt, c1 o pt); pt [L][N] shared by the batch; out may alias ct */
+int dpfhe_ct_mul_plain(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_pt, uint64_t *d_out,
+                       size_t batch, void *stream);
+/* out = (sigma_g(c0) + ks0, ks1), ks = keyswitch(sigma_g(c1), gk); galois_elt odd in [1,2N);
+ * out must not alias ct */
+int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk,
+                 uint64_t *d_out, size_t batch, void *stream);
+
+/* ---- synthetic data: x[k] = mulhi64(splitmix64(seed + k), q_limb),
+ *      k = (first_poly + p)*L*N + l*N + n.  Fills [n_polys][L][N]. ---- */
+int dpfhe_fill_uniform(dpfhe_ctx *ctx, uint64_t seed, uint64_t first_poly, uint64_t *d_data,
+                       size_t n_polys, void *stream);
+
+/* ---- host-buffer entry points (what a non-CUDA caller of the reference API would bind):
+ *      H2D, compute and D2H are pipelined in chunks on the context's streams; synchronous. ---- */
+int dpfhe_ntt_fwd_host(dpfhe_ctx *ctx, uint64_t *h_data, size_t n_polys);
+int dpfhe_ntt_inv_host(dpfhe_ctx *ctx, uint64_t *h_data, size_t n_polys);
+int dpfhe_ct_mul_relin_host(dpfhe_ctx *ctx, const uint64_t *h_a, const uint64_t *h_b, const uint64_t *h_evk,
+                            uint64_t *h_out, size_t batch);
+int dpfhe_ct_mul_plain_host(dpfhe_ctx *ctx, const uint64_t *h_ct, const uint64_t *h_pt, uint64_t *h_out,
+                            size_t batch);
+int dpfhe_rotate_host(dpfhe_ctx *ctx, const uint64_t *h_ct, uint64_t galois_elt, const uint64_t *h_gk,
+                      uint64_t *h_out, size_t batch);
+/* pinned host memory helpers so callers can reach full PCIe bandwidth */
+int dpfhe_host_alloc(void **out, size_t bytes);
+int dpfhe_host_free(void *p);
+
+/* ---- diagnostics ---- */
+/* number of kernel launches issued through this context since creation */
+uint64_t dpfhe_launch_count(const dpfhe_ctx *ctx);
+/* name + launch geometry of the kernels behind an op, for bench/DESIGN reporting; returns bytes written */
+int dpfhe_describe(const dpfhe_ctx *ctx, char *buf, size_t buf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPFHE_H */

@@ -1,0 +1,106 @@
+// int_pipes.cu — integer-pipe throughput microbenchmark for sm_100a (B200).
+// Measures warp-instruction issue rates that bound the 64-bit modular butterflies:
+// IMAD.WIDE.U32, IMAD (lo), IMAD.HI, 64-bit add (IADD3 + IADD3.X), __umul64hi, and the
+// library's own shoup_lazy / ct_bfly.  Output: results per SM per clock.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I ../../deeppowers_b200/csrc int_pipes.cu -o int_pipes
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "ntt_core.cuh"
+using namespace dpfhe;
+
+constexpr int ITERS = 4096, CH = 8;
+
+template <int OP>
+__global__ void __launch_bounds__(1024) bench(unsigned long long *out, long long *cycles, unsigned a0, unsigned b0, LimbParams p) {
+    unsigned a = a0 + threadIdx.x, b = b0 ^ threadIdx.x;
+    u64 acc[CH];
+    unsigned r32[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { acc[c] = threadIdx.x * 977ull + c; r32[c] = threadIdx.x + c; }
+    Twiddle w; w.x = p.ninv; w.y = p.ninv_s;
+    __syncthreads();
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < ITERS; ++i) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            if (OP == 0) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b));
+            if (OP == 1) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r32[c]) : "r"(a), "r"(b));
+            if (OP == 2) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(r32[c]) : "r"(a), "r"(b));
+            if (OP == 3) asm volatile("add.u64 %0, %0, %1;" : "+l"(acc[c]) : "l"((unsigned long long)a << 20 | b));
+            if (OP == 4) acc[c] = __umul64hi(acc[c], p.bar_mu) + c;
+            if (OP == 5) acc[c] = shoup_lazy(acc[c], w.x, w.y, p.q);
+            if (OP == 6) acc[c] = csub(acc[c] + p.q, p.q2);
+            if (OP == 7) acc[c] = word_reduce(acc[c] * 5 + 1, p);
+            if (OP == 8) acc[c] = mulmod_lazy(acc[c], p.wninv + c, p);
+        }
+        if (OP == 9) {
+#pragma unroll
+            for (int c = 0; c < CH; c += 2) ct_bfly(acc[c], acc[c + 1], w, p);
+#pragma unroll
+            for (int c = 0; c < CH; c += 1) acc[c] &= 0x0fffffffffffffffull;   // keep the lazy bound (1 LOP3 per element)
+        }
+        if (OP == 10) {
+#pragma unroll
+            for (int c = 0; c < CH; c += 2) gs_bfly(acc[c], acc[c + 1], w, p);
+        }
+    }
+    long long t1 = clock64();
+    u64 s = 0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) s += acc[c] + r32[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+void run(const char *name, double per_iter_results, LimbParams p, int threads) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    unsigned long long *out;
+    long long *cyc;
+    cudaMalloc(&out, sizeof(unsigned long long) * sms * 1024);
+    cudaMalloc(&cyc, sizeof(long long) * sms);
+    bench<OP><<<sms, threads>>>(out, cyc, 12345u, 67891u, p);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    bench<OP><<<sms, threads>>>(out, cyc, 12345u, 67891u, p);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long h[256];
+    cudaMemcpy(h, cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < sms; ++i) avg += h[i];
+    avg /= sms;
+    double results = (double)threads * ITERS * per_iter_results;
+    printf("%-34s threads/SM=%4d  %8.2f results/clk/SM   %7.3f clk per warp-result/SMSP   (%.3f ms, %.0f MHz eff)\n", name, threads,
+           results / avg, avg / (results / 32.0 / 4.0), ms, avg / ms / 1e3);
+    cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+    LimbParams p;
+    p.q = 0xfffffffffffc001ull; p.q2 = 2 * p.q;
+    p.bar_shift = 58; p.bar_mu = (unsigned long long)(((unsigned __int128)1 << 122) / p.q);
+    p.mu32 = (unsigned)(((unsigned __int128)1 << 64) / p.q);
+    p.ninv = 0x123456789abcdefull % p.q; p.ninv_s = (unsigned long long)(((unsigned __int128)p.ninv << 64) / p.q);
+    p.wninv = 0xfedcba987654321ull % p.q; p.wninv_s = 0;
+    for (int threads : {256, 512, 1024}) {
+        run<0>("mad.wide.u32 (IMAD.WIDE)", CH, p, threads);
+        run<1>("mad.lo.u32 (IMAD)", CH, p, threads);
+        run<2>("mad.hi.u32 (IMAD.HI)", CH, p, threads);
+        run<3>("add.u64 (IADD3+IADD3.X)", CH, p, threads);
+        run<4>("__umul64hi + add", CH, p, threads);
+        run<5>("shoup_lazy", CH, p, threads);
+        run<6>("csub(x+q, 2q)", CH, p, threads);
+        run<7>("word_reduce(5x+1)", CH, p, threads);
+        run<8>("mulmod_lazy (128b product+Barrett)", CH, p, threads);
+        run<9>("ct_bfly (+1 LOP3/elt)", CH / 2, p, threads);
+        run<10>("gs_bfly", CH / 2, p, threads);
+        printf("\n");
+    }
+    return 0;
+}

@@ -1,0 +1,116 @@
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _gpu_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _gpu_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    import oracle
+    oracle.build()
+    return oracle
+
+
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+class Emu:
+    """ctypes view of tests/_emu/libdpfhe_emu.so: the kernel bodies compiled for the host (test infra)."""
+
+    def __init__(self, lib, log_n, L, moduli=None):
+        self._l = lib
+        arr = (C.c_uint64 * L)(*[int(m) for m in moduli]) if moduli is not None else None
+        self._h = lib.emu_create(log_n, L, arr)
+        if not self._h:
+            raise ValueError("emu_create rejected the parameters")
+        self.log_n, self.L, self.N = log_n, L, 1 << log_n
+        self.moduli = [int(lib.emu_modulus(self._h, l)) for l in range(L)]
+        self.psi = [int(lib.emu_psi(self._h, l)) for l in range(L)]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.emu_destroy(self._h)
+            self._h = None
+
+    def root_powers(self, l, inverse=False):
+        out = np.empty(self.N, dtype=np.uint64)
+        self._l.emu_root_powers(self._h, l, int(inverse), out)
+        return out
+
+    def ntt(self, data, inverse=False):
+        d = np.ascontiguousarray(data, dtype=np.uint64).copy()
+        assert self._l.emu_ntt(self._h, d.reshape(-1), d.size // (self.L * self.N), int(inverse)) == 0
+        return d
+
+    def ks(self, mode, a, b, key, batch, galois=0, G=None):
+        out = np.zeros((batch, 2, self.L, self.N), dtype=np.uint64)
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64)
+        assert self._l.emu_ks(self._h, mode, a.reshape(-1), b.reshape(-1), np.ascontiguousarray(key).reshape(-1),
+                              out.reshape(-1), batch, int(galois), G or 2 * self.L) == 0
+        return out
+
+    def scalar(self, name, l, *args):
+        return int(getattr(self._l, "emu_" + name)(self._h, l, *[C.c_uint64(int(a)) for a in args]))
+
+
+@pytest.fixture(scope="session")
+def emu_lib():
+    out_dir = os.path.join(ROOT, "tests", "_emu")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libdpfhe_emu.so")
+    csrc = os.path.join(ROOT, "deeppowers_b200", "csrc")
+    srcs = [os.path.join(ROOT, "tests", "emu", "emu.cpp"), os.path.join(csrc, "host_params.cpp")]
+    deps = srcs + [os.path.join(csrc, f) for f in ("modarith.cuh", "ntt_core.cuh", "kernel_bodies.cuh", "host_params.hpp")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-I", csrc] + srcs + ["-o", so])
+    lib = C.CDLL(so)
+    lib.emu_create.restype = C.c_void_p
+    lib.emu_create.argtypes = [C.c_uint, C.c_uint, C.c_void_p]
+    lib.emu_destroy.argtypes = [C.c_void_p]
+    lib.emu_modulus.restype = C.c_uint64
+    lib.emu_modulus.argtypes = [C.c_void_p, C.c_uint]
+    lib.emu_psi.restype = C.c_uint64
+    lib.emu_psi.argtypes = [C.c_void_p, C.c_uint]
+    lib.emu_root_powers.argtypes = [C.c_void_p, C.c_uint, C.c_int, _u64p]
+    lib.emu_ntt.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int]
+    lib.emu_ks.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint]
+    for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2)):
+        f = getattr(lib, "emu_" + nm)
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_uint] + [C.c_uint64] * nargs
+    return lib
+
+
+@pytest.fixture(scope="session")
+def make_emu(emu_lib):
+    return lambda log_n, L, moduli=None: Emu(emu_lib, log_n, L, moduli)

@@ -1,0 +1,164 @@
+// emu.cpp — host emulator of the CTA-level kernel bodies (TEST INFRASTRUCTURE ONLY).
+//
+// Compiles deeppowers_b200/csrc/kernel_bodies.cuh with a sequential CTA policy so that the
+// index algebra (swizzle, pass decomposition, twiddle layout, digit exchange) is checked
+// against the oracle on a machine without a GPU.  It is built into tests/_emu/libdpfhe_emu.so
+// by tests/conftest.py, is never linked into libdpfhe.so and is not a fallback for anything.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_params.hpp"
+#include "kernel_bodies.cuh"
+
+using namespace dpfhe;
+
+namespace {
+struct HostCta {
+    int nt;
+    template <class F>
+    void par(F f) {
+        for (int t = 0; t < nt; ++t) f(t);
+    }
+};
+
+template <class T>
+T *aligned_new(size_t n) {
+    void *p = nullptr;
+    if (posix_memalign(&p, 128, n * sizeof(T))) return nullptr;
+    return (T *)p;
+}
+
+struct Emu {
+    HostParams hp;
+    std::vector<LimbParams> lp;
+    Twiddle *tw = nullptr, *itw = nullptr;
+    ~Emu() {
+        free(tw);
+        free(itw);
+    }
+};
+
+template <int LOGN, int NT>
+void run_ntt(Emu &e, uint64_t *data, size_t n_polys, bool inverse) {
+    const size_t N = (size_t)1 << LOGN;
+    uint64_t *buf = aligned_new<uint64_t>(N);
+    HostCta cta{NT};
+    for (size_t w = 0; w < n_polys * e.hp.L; ++w) {
+        const unsigned l = (unsigned)(w % e.hp.L);
+        const LimbParams p = e.lp[l];
+        if (inverse) ntt_inv_body<LOGN, NT>(cta, buf, data + w * N, e.itw + l * N, p);
+        else ntt_fwd_body<LOGN, NT>(cta, buf, data + w * N, e.tw + l * N, p);
+    }
+    free(buf);
+}
+
+// persistent-grid emulation: G slots, rounds of G work items; all phase 1 of a round before its phase 2
+template <int LOGN, int NT, int MODE>
+void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, uint64_t *out, size_t batch,
+            uint32_t galois, unsigned G) {
+    const size_t N = (size_t)1 << LOGN;
+    const unsigned L = e.hp.L;
+    G = (G / L) * L;
+    if (G == 0) G = L;
+    std::vector<uint64_t *> buf(G), acc0(G), acc1(G);
+    for (unsigned s = 0; s < G; ++s) {
+        buf[s] = aligned_new<uint64_t>(N);
+        acc0[s] = aligned_new<uint64_t>(N);
+        acc1[s] = aligned_new<uint64_t>(N);
+    }
+    uint64_t *scratch = aligned_new<uint64_t>((size_t)G * 2 * N);
+    KsArgs A;
+    A.a = a; A.b = b; A.key = key; A.out = out; A.scratch = scratch;
+    A.lp = e.lp.data(); A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois;
+    HostCta cta{NT};
+    const size_t n_work = batch * L;
+    for (size_t r = 0; r * G < n_work; ++r) {
+        const unsigned par = (unsigned)(r & 1);
+        for (unsigned s = 0; s < G; ++s) {
+            const size_t w = r * G + s;
+            if (w >= n_work) break;
+            ks_phase1<LOGN, NT, MODE>(cta, buf[s], acc0[s], acc1[s], A, w / L, (uint32_t)(w % L), scratch + ((size_t)s * 2 + par) * N);
+        }
+        for (unsigned s = 0; s < G; ++s) {
+            const size_t w = r * G + s;
+            if (w >= n_work) break;
+            const uint32_t i = (uint32_t)(w % L);
+            for (uint32_t jj = 1; jj < L; ++jj) {
+                const uint32_t j = (i + jj) % L;
+                const unsigned sib = s - i + j;
+                ks_phase2_digit<LOGN, NT>(cta, buf[s], acc0[s], acc1[s], A, i, j, scratch + ((size_t)sib * 2 + par) * N);
+            }
+            ks_finish<LOGN, NT>(cta, acc0[s], acc1[s], A, w / L, i);
+        }
+    }
+    for (unsigned s = 0; s < G; ++s) {
+        free(buf[s]);
+        free(acc0[s]);
+        free(acc1[s]);
+    }
+    free(scratch);
+}
+}  // namespace
+
+extern "C" {
+
+void *emu_create(unsigned log_n, unsigned L, const uint64_t *moduli) {
+    Emu *e = new Emu();
+    if (!build_host_params(log_n, L, moduli, e->hp).empty()) {
+        delete e;
+        return nullptr;
+    }
+    const size_t N = (size_t)1 << log_n;
+    e->tw = aligned_new<Twiddle>(N * L);
+    e->itw = aligned_new<Twiddle>(N * L);
+    for (unsigned l = 0; l < L; ++l) {
+        e->lp.push_back(e->hp.limbs[l].lp);
+        memcpy(e->tw + l * N, e->hp.limbs[l].tw.data(), N * sizeof(Twiddle));
+        memcpy(e->itw + l * N, e->hp.limbs[l].itw.data(), N * sizeof(Twiddle));
+    }
+    return e;
+}
+void emu_destroy(void *h) { delete (Emu *)h; }
+uint64_t emu_modulus(void *h, unsigned l) { return ((Emu *)h)->hp.limbs[l].lp.q; }
+uint64_t emu_psi(void *h, unsigned l) { return ((Emu *)h)->hp.limbs[l].psi; }
+void emu_root_powers(void *h, unsigned l, int inverse, uint64_t *out) {
+    Emu *e = (Emu *)h;
+    const auto &v = inverse ? e->hp.limbs[l].inv_root_powers : e->hp.limbs[l].root_powers;
+    memcpy(out, v.data(), v.size() * 8);
+}
+
+int emu_ntt(void *h, uint64_t *data, size_t n_polys, int inverse) {
+    Emu *e = (Emu *)h;
+    switch (e->hp.log_n) {
+        case 12: run_ntt<12, 256>(*e, data, n_polys, inverse != 0); return 0;
+        case 13: run_ntt<13, 512>(*e, data, n_polys, inverse != 0); return 0;
+        case 14: run_ntt<14, 512>(*e, data, n_polys, inverse != 0); return 0;
+    }
+    return -1;
+}
+
+// mode: 0 ct_mul_relin (a,b), 1 keyswitch (a = d), 2 rotate (a = ct, galois)
+int emu_ks(void *h, int mode, const uint64_t *a, const uint64_t *b, const uint64_t *key, uint64_t *out, size_t batch,
+           uint32_t galois, unsigned G) {
+    Emu *e = (Emu *)h;
+#define DISPATCH(LOGN, NT)                                                                       \
+    if (mode == 0) run_ks<LOGN, NT, KS_MUL_RELIN>(*e, a, b, key, out, batch, galois, G);          \
+    else if (mode == 1) run_ks<LOGN, NT, KS_PLAIN>(*e, a, b, key, out, batch, galois, G);         \
+    else run_ks<LOGN, NT, KS_ROTATE>(*e, a, b, key, out, batch, galois, G);                       \
+    return 0;
+    switch (e->hp.log_n) {
+        case 12: DISPATCH(12, 256)
+        case 13: DISPATCH(13, 512)
+    }
+    return -1;
+}
+
+// scalar checks
+uint64_t emu_mulmod(void *h, unsigned l, uint64_t a, uint64_t b) { return mulmod(a, b, ((Emu *)h)->lp[l]); }
+uint64_t emu_word_reduce(void *h, unsigned l, uint64_t x) { return word_reduce(x, ((Emu *)h)->lp[l]); }
+uint64_t emu_canon(void *h, unsigned l, uint64_t x) { return canon(x, ((Emu *)h)->lp[l]); }
+uint64_t emu_mulmod_lazy(void *h, unsigned l, uint64_t a, uint64_t b) { return mulmod_lazy(a, b, ((Emu *)h)->lp[l]); }
+}

@@ -1,0 +1,254 @@
+"""GPU parity tests: every entry point of the C ABI (include/dpfhe.h) against the CPU oracle, bit-exact.
+
+The reference has no tests for this path, so the cases follow the oracle's own
+pins: seeded uniform residues, edge values (0, q-1), ragged batches, every supported N, custom moduli,
+and size-independent properties at the BASELINE.json config-2 shape.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+@pytest.fixture(scope="module")
+def dp():
+    import deeppowers_b200
+    return deeppowers_b200
+
+
+@pytest.fixture(scope="module")
+def ctxs(dp, oracle_mod):
+    cache = {}
+
+    def get(log_n, L, moduli=None):
+        key = (log_n, L, tuple(moduli) if moduli else None)
+        if key not in cache:
+            cache[key] = (dp.Context(log_n, L, moduli), oracle_mod.Oracle(log_n, L, moduli))
+        return cache[key]
+
+    yield get
+    for c, _ in cache.values():
+        c.close()
+
+
+def edge_polys(o, n_polys, seed):
+    """uniform residues with a few adversarial rows: all zero, all q-1, alternating 0 / q-1"""
+    x = o.fill_uniform(seed, n_polys)
+    q = np.array(o.moduli, dtype=np.uint64)
+    if n_polys >= 3:
+        x[0] = 0
+        x[1] = (q - 1)[:, None]
+        x[2, :, ::2] = 0
+        x[2, :, 1::2] = (q - 1)[:, None]
+    return x
+
+
+@pytest.mark.parametrize("log_n,L", [(12, 1), (12, 3), (13, 4), (14, 2), (14, 8)])
+def test_tables_match_oracle(ctxs, log_n, L):
+    c, o = ctxs(log_n, L)
+    assert c.moduli == o.moduli
+    assert c.psi == o.psi
+    for l in (0, L - 1):
+        assert np.array_equal(c.root_powers(l), o.root_powers(l))
+        assert np.array_equal(c.root_powers(l, inverse=True), o.inv_root_powers(l))
+
+
+@pytest.mark.parametrize("log_n,L,n_polys", [(12, 1, 1), (12, 3, 5), (13, 4, 7), (14, 2, 3), (14, 8, 2)])
+def test_ntt_fwd_inv(ctxs, log_n, L, n_polys):
+    c, o = ctxs(log_n, L)
+    x = edge_polys(o, n_polys, 0xD3390001)
+    d = dev(x)
+    c.ntt_fwd(d, n_polys)
+    y = host(d).reshape(x.shape)
+    assert np.array_equal(y, o.ntt_fwd(x))
+    c.ntt_inv(d, n_polys)
+    assert np.array_equal(host(d).reshape(x.shape), x)
+
+
+def test_ntt_custom_moduli(ctxs, oracle_mod):
+    # 50-bit and 36-bit NTT-friendly primes exercise the generic Barrett / word-reduce constants
+    mods = []
+    two_n = 2 << 12
+    for start in ((1 << 50), (1 << 36), (1 << 59)):
+        cand = (start // two_n) * two_n + 1
+        while True:
+            cand -= two_n
+            if oracle_mod.lib().dpo_is_prime(cand):
+                mods.append(cand)
+                break
+    c, o = ctxs(12, 3, mods)
+    x = edge_polys(o, 4, 77)
+    d = dev(x)
+    c.ntt_fwd(d, 4)
+    assert np.array_equal(host(d).reshape(x.shape), o.ntt_fwd(x))
+    c.ntt_inv(d, 4)
+    assert np.array_equal(host(d).reshape(x.shape), x)
+    # ct x ct with mixed-size moduli: the digit lift t mod q_i really reduces here
+    s = o.keygen_secret(1)
+    evk = o.keygen_relin(2, 65537, s)
+    a = o.fill_uniform(3, 2 * 3).reshape(3, 2, 3, o.N)
+    b = o.fill_uniform(4, 2 * 3).reshape(3, 2, 3, o.N)
+    out = torch.zeros(a.shape, dtype=torch.int64, device="cuda")
+    c.ct_mul_relin(dev(a), dev(b), dev(evk), out, 3)
+    assert np.array_equal(host(out).reshape(a.shape), o.ct_mul_relin(a, b, evk))
+
+
+@pytest.mark.parametrize("log_n,L", [(12, 2), (13, 4), (14, 2)])
+def test_pointwise_and_tensor_and_plain(ctxs, log_n, L):
+    c, o = ctxs(log_n, L)
+    B = 3
+    a = edge_polys(o, 2 * B, 11).reshape(B, 2, L, o.N)
+    b = edge_polys(o, 2 * B, 12)[::-1].copy().reshape(B, 2, L, o.N)
+    da, db = dev(a), dev(b)
+    out = torch.empty_like(da)
+    c.poly_mul_pointwise(da, db, out, 2 * B)
+    assert np.array_equal(host(out).reshape(a.shape), o.poly_mul_pointwise(a, b))
+    d = torch.empty((B, 3, L, o.N), dtype=torch.int64, device="cuda")
+    c.ct_tensor(da, db, d, B)
+    assert np.array_equal(host(d).reshape(B, 3, L, o.N), o.ct_tensor(a, b))
+    pt = o.fill_uniform(13, 1)[0]
+    c.ct_mul_plain(da, dev(pt), out, B)
+    assert np.array_equal(host(out).reshape(a.shape), o.ct_mul_plain(a, pt))
+
+
+@pytest.mark.parametrize("log_n,L,batch", [(12, 2, 1), (12, 3, 5), (13, 4, 3), (13, 1, 2), (13, 4, 41)])
+def test_ct_mul_relin(ctxs, log_n, L, batch):
+    c, o = ctxs(log_n, L)
+    s = o.keygen_secret(21)
+    evk = o.keygen_relin(22, 65537, s)
+    a = edge_polys(o, 2 * batch, 23).reshape(batch, 2, L, o.N)
+    b = o.fill_uniform(24, 2 * batch).reshape(batch, 2, L, o.N)
+    out = torch.zeros(a.shape, dtype=torch.int64, device="cuda")
+    c.ct_mul_relin(dev(a), dev(b), dev(evk), out, batch)
+    got = host(out).reshape(a.shape)
+    ref = o.ct_mul_relin(a, b, evk)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("log_n,L,batch", [(12, 3, 4), (13, 4, 5)])
+def test_keyswitch_and_rotate(ctxs, log_n, L, batch):
+    c, o = ctxs(log_n, L)
+    s = o.keygen_secret(31)
+    evk = o.keygen_relin(32, 65537, s)
+    d = edge_polys(o, batch, 33)
+    out = torch.zeros((batch, 2, L, o.N), dtype=torch.int64, device="cuda")
+    c.keyswitch(dev(d), dev(evk), out, batch)
+    ref = np.stack([np.stack(o.keyswitch(d[k], evk)) for k in range(batch)])
+    assert np.array_equal(host(out).reshape(ref.shape), ref)
+    ct = o.fill_uniform(34, 2 * batch).reshape(batch, 2, L, o.N)
+    for k in (1, -1, 7):
+        g = o.galois_elt(k)
+        assert g == c.galois_elt(k)
+        gk = o.keygen_galois(35 + k, 65537, s, g)
+        c.rotate(dev(ct), g, dev(gk), out, batch)
+        assert np.array_equal(host(out).reshape(ct.shape), o.rotate(ct, g, gk))
+
+
+def test_semantics_decrypt_of_product(ctxs):
+    """Dec(GPU ct x ct) == a*b mod (X^N+1, t): checks the scheme meaning, not just oracle agreement."""
+    c, o = ctxs(12, 3)
+    t = 65537
+    rng = np.random.default_rng(5)
+    s = o.keygen_secret(41)
+    evk = o.keygen_relin(42, t, s)
+    m1 = rng.integers(0, t, o.N).astype(np.uint64)
+    m2 = np.zeros(o.N, dtype=np.uint64)
+    m2[1] = 3   # multiply by 3X: a negacyclic shift scaled by 3
+    c1, c2 = o.encrypt(43, t, s, m1), o.encrypt(44, t, s, m2)
+    out = torch.zeros((1, 2, 3, o.N), dtype=torch.int64, device="cuda")
+    c.ct_mul_relin(dev(c1[None]), dev(c2[None]), dev(evk), out, 1)
+    dec = o.decrypt(s, host(out).reshape(2, 3, o.N), t)
+    exp = np.empty_like(m1)
+    exp[1:] = (3 * m1[:-1]) % t
+    exp[0] = (t - (3 * m1[-1]) % t) % t
+    assert np.array_equal(dec, exp)
+
+
+def test_fill_uniform_matches_oracle(ctxs):
+    c, o = ctxs(13, 4)
+    d = torch.empty((3, 4, o.N), dtype=torch.int64, device="cuda")
+    c.fill_uniform(0xD3390002, d, 3, first_poly=5)
+    assert np.array_equal(host(d).reshape(3, 4, o.N), o.fill_uniform(0xD3390002, 3, first_poly=5))
+
+
+def test_host_entry_points(ctxs):
+    c, o = ctxs(13, 4)
+    s = o.keygen_secret(51)
+    evk = o.keygen_relin(52, 65537, s)
+    B = 9
+    a = o.fill_uniform(53, 2 * B).reshape(B, 2, 4, o.N)
+    b = o.fill_uniform(54, 2 * B).reshape(B, 2, 4, o.N)
+    out = np.zeros_like(a)
+    c.ct_mul_relin_host(a, b, evk, out)
+    assert np.array_equal(out, o.ct_mul_relin(a, b, evk))
+    x = o.fill_uniform(55, 6)
+    y = x.copy()
+    c.ntt_fwd_host(y)
+    assert np.array_equal(y, o.ntt_fwd(x))
+    c.ntt_inv_host(y)
+    assert np.array_equal(y, x)
+    pt = o.fill_uniform(56, 1)[0]
+    c.ct_mul_plain_host(a, pt, out)
+    assert np.array_equal(out, o.ct_mul_plain(a, pt))
+    g = o.galois_elt(2)
+    gk = o.keygen_galois(57, 65537, s, g)
+    c.rotate_host(a, g, gk, out)
+    assert np.array_equal(out, o.rotate(a, g, gk))
+
+
+def test_errors_are_reported(dp, ctxs):
+    c, o = ctxs(12, 2)
+    with pytest.raises(dp.DpfheError):
+        dp.Context(9, 2)                       # unsupported N
+    with pytest.raises(dp.DpfheError):
+        dp.Context(12, 2, [97, 193])           # moduli out of range
+    d = torch.zeros((1, 2, 2, o.N), dtype=torch.int64, device="cuda")
+    with pytest.raises(dp.DpfheError):
+        c.rotate(d, 4, d, torch.zeros_like(d), 1)   # even Galois element
+    with pytest.raises(dp.DpfheError):
+        c.ct_mul_relin(d, d, d, d, 1)          # aliasing output
+    c.ntt_fwd(d, 0)                            # empty batch is a no-op
+
+
+def test_config2_shape_properties(ctxs):
+    """BASELINE.json config 2 shape (N=8192, L=4) on a larger batch than the oracle can chew through:
+    size-independent properties + spot checks of individual ciphertexts against the oracle."""
+    c, o = ctxs(13, 4)
+    B = 1184   # 8 full waves of 148 CTAs x 4 limbs
+    P2 = 2 * o.P
+    a = torch.empty((B, 2, 4, o.N), dtype=torch.int64, device="cuda")
+    b = torch.empty_like(a)
+    c.fill_uniform(0xD3390002, a, 2 * B, first_poly=0)
+    c.fill_uniform(0xD3390002, b, 2 * B, first_poly=2 * B)
+    s = o.keygen_secret(61)
+    evk = o.keygen_relin(62, 65537, s)
+    devk = dev(evk)
+    out = torch.zeros_like(a)
+    c.ct_mul_relin(a, b, devk, out, B)
+    # (1) commutativity: a (x) b == b (x) a, bit for bit
+    out2 = torch.zeros_like(a)
+    c.ct_mul_relin(b, a, devk, out2, B)
+    assert torch.equal(out, out2)
+    # (2) all residues canonical
+    q = torch.tensor(np.array(o.moduli, dtype=np.uint64).view(np.int64), device="cuda").view(1, 1, 4, 1)
+    assert bool(((out >= 0) & (out < q)).all())
+    # (3) spot-check ciphertexts across waves against the oracle
+    for k in (0, 1, 147, 148, 591, 592, B - 1):
+        ak = o.fill_uniform(0xD3390002, 2, first_poly=2 * k).reshape(1, 2, 4, o.N)
+        bk = o.fill_uniform(0xD3390002, 2, first_poly=2 * B + 2 * k).reshape(1, 2, 4, o.N)
+        assert np.array_equal(host(a[k]).reshape(1, 2, 4, o.N), ak)
+        assert np.array_equal(host(out[k]).reshape(1, 2, 4, o.N), o.ct_mul_relin(ak, bk, evk)), k
+    # (4) NTT round trip and linearity at this size
+    x = a.clone()
+    c.ntt_inv(x, 2 * B)
+    c.ntt_fwd(x, 2 * B)
+    assert torch.equal(x, a)
