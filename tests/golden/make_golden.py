@@ -1,0 +1,65 @@
+"""Regenerates tests/golden/kat.json from the CPU oracle.
+
+The reference tree holds no golden vectors for this path, so these are
+self-generated pins: they freeze the spec as implemented by the oracle at the
+commit that introduced them, so any later change of convention (prime choice, root choice,
+bit-reversed ordering, digit decomposition) is caught on CPU.  Run from the repo root:
+    python tests/golden/make_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import Oracle  # noqa: E402
+
+
+def h(a):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype=np.uint64).tobytes()).hexdigest()
+
+
+def main():
+    out = {"params": {}, "cases": []}
+    for log_n, L in [(12, 1), (12, 3), (13, 4), (14, 8)]:
+        o = Oracle(log_n, L)
+        out["params"]["%d,%d" % (log_n, L)] = {"moduli": [str(q) for q in o.moduli], "psi": [str(p) for p in o.psi]}
+    # config 1 of BASELINE.json: single forward NTT, N=4096, one 60-bit modulus
+    o = Oracle(12, 1)
+    x = o.fill_uniform(0xD3390001, 1)
+    y = o.ntt_fwd(x)
+    out["cases"].append({"name": "cfg1_ntt_fwd_n4096_l1", "log_n": 12, "L": 1, "seed": 0xD3390001, "n_polys": 1,
+                         "in_sha256": h(x), "out_sha256": h(y), "in_head": [str(v) for v in x.reshape(-1)[:8]],
+                         "out_head": [str(v) for v in y.reshape(-1)[:8]]})
+    for log_n, L, seed in [(13, 4, 0xD3390002), (14, 8, 0xD3390003)]:
+        o = Oracle(log_n, L)
+        x = o.fill_uniform(seed, 2)
+        y = o.ntt_fwd(x)
+        out["cases"].append({"name": "ntt_fwd_n%d_l%d" % (1 << log_n, L), "log_n": log_n, "L": L, "seed": seed, "n_polys": 2,
+                             "in_sha256": h(x), "out_sha256": h(y), "in_head": [str(v) for v in x.reshape(-1)[:8]],
+                             "out_head": [str(v) for v in y.reshape(-1)[:8]]})
+    # ct x ct + relin and rotate at config-2 shape, keys from the seeded test scheme
+    o = Oracle(13, 4)
+    s = o.keygen_secret(1)
+    evk = o.keygen_relin(2, 65537, s)
+    a = o.fill_uniform(0xD3390002, 4).reshape(2, 2, 4, o.N)
+    b = o.fill_uniform(0xD3390002, 4, first_poly=4).reshape(2, 2, 4, o.N)
+    r = o.ct_mul_relin(a, b, evk)
+    g = o.galois_elt(1)
+    gk = o.keygen_galois(3, 65537, s, g)
+    rot = o.rotate(a, g, gk)
+    out["cases"].append({"name": "cfg2_ct_mul_relin_n8192_l4", "log_n": 13, "L": 4, "seed": 0xD3390002,
+                         "secret_sha256": h(s), "evk_sha256": h(evk), "out_sha256": h(r),
+                         "out_head": [str(v) for v in r.reshape(-1)[:8]]})
+    out["cases"].append({"name": "rotate1_n8192_l4", "log_n": 13, "L": 4, "seed": 0xD3390002, "galois": int(g),
+                         "gk_sha256": h(gk), "out_sha256": h(rot), "out_head": [str(v) for v in rot.reshape(-1)[:8]]})
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kat.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()

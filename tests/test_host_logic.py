@@ -1,0 +1,138 @@
+"""CPU tests of the product's host logic: parameter derivation in libdpfhe.so's host code, the kernel
+bodies run through the host emulator (index algebra, swizzle, twiddle layout, digit exchange order,
+lazy-reduction bounds) against the oracle, and the C-ABI export list."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("log_n,L", [(12, 1), (12, 3), (13, 4), (14, 2)])
+def test_host_params_match_oracle(make_emu, oracle_mod, log_n, L):
+    e, o = make_emu(log_n, L), oracle_mod.Oracle(log_n, L)
+    assert e.moduli == o.moduli and e.psi == o.psi
+    for l in range(L):
+        assert np.array_equal(e.root_powers(l), o.root_powers(l))
+        assert np.array_equal(e.root_powers(l, inverse=True), o.inv_root_powers(l))
+
+
+def test_device_scalar_arithmetic_bounds(make_emu, oracle_mod):
+    """modarith.cuh on adversarial inputs: every lazy routine stays inside its documented range"""
+    lib = oracle_mod.lib()
+    small = (1 << 34) - (1 << 34) % (2 << 12) + 1
+    while not lib.dpo_is_prime(small):
+        small += 2 << 12
+    e = make_emu(12, 2, [oracle_mod.Oracle(12, 1).moduli[0], small])
+    rng = np.random.default_rng(2)
+    for l, q in enumerate(e.moduli):
+        xs = [0, 1, q - 1, q, 2 * q, 3 * q - 1, 2**64 - 1, 2**63, 16 * q - 1 if 16 * q < 2**64 else 2**64 - 1]
+        xs += [int(v) for v in rng.integers(0, 2**64, 2000, dtype=np.uint64)]
+        for x in xs:
+            r = e.scalar("word_reduce", l, x)
+            assert r % q == x % q and r < 3 * q
+            if x < 16 * q:
+                assert e.scalar("canon", l, x) == x % q
+        vals = [0, 1, q - 1, q - 2] + [int(v) for v in rng.integers(0, q, 1500, dtype=np.uint64)]
+        for a, b in zip(vals, reversed(vals)):
+            assert e.scalar("mulmod", l, a, b) == (a * b) % q
+            r = e.scalar("mulmod_lazy", l, a, b)
+            assert r % q == (a * b) % q and r < 2 * q
+        # lazy operands as used by the fused kernel: u < 3q times key < q stays below 3q
+        for a in (3 * q - 1, 2 * q + 5, q):
+            for b in (q - 1, 1, q // 3):
+                r = e.scalar("mulmod_lazy", l, a, b)
+                assert r % q == (a * b) % q and r < 3 * q
+
+
+@pytest.mark.parametrize("log_n,L,n_polys", [(12, 1, 1), (12, 3, 2), (13, 4, 2), (14, 2, 1)])
+def test_emulated_ntt_bodies(make_emu, oracle_mod, log_n, L, n_polys):
+    e, o = make_emu(log_n, L), oracle_mod.Oracle(log_n, L)
+    x = o.fill_uniform(0xD3390001, n_polys)
+    q = np.array(o.moduli, dtype=np.uint64)
+    x[0, :, : o.N // 2] = (q - 1)[:, None]          # worst case for the lazy bounds
+    y = e.ntt(x)
+    assert np.array_equal(y, o.ntt_fwd(x))
+    assert np.array_equal(e.ntt(y, inverse=True), x)
+
+
+@pytest.mark.parametrize("log_n,L,batch,G", [(12, 2, 3, 2), (12, 3, 4, 9), (13, 4, 2, 8), (12, 1, 2, 1)])
+def test_emulated_fused_keyswitch_bodies(make_emu, oracle_mod, log_n, L, batch, G):
+    e, o = make_emu(log_n, L), oracle_mod.Oracle(log_n, L)
+    s = o.keygen_secret(1)
+    evk = o.keygen_relin(2, 65537, s)
+    a = o.fill_uniform(3, 2 * batch).reshape(batch, 2, L, o.N)
+    b = o.fill_uniform(4, 2 * batch).reshape(batch, 2, L, o.N)
+    q = np.array(o.moduli, dtype=np.uint64)
+    a[0] = (q - 1)[None, :, None]
+    b[0] = (q - 1)[None, :, None]
+    assert np.array_equal(e.ks(0, a, b, evk, batch, G=G), o.ct_mul_relin(a, b, evk))
+    d = o.fill_uniform(5, batch)
+    ref = np.stack([np.stack(o.keyswitch(d[k], evk)) for k in range(batch)])
+    assert np.array_equal(e.ks(1, d, None, evk, batch, G=G), ref)
+    g = o.galois_elt(-2)
+    gk = o.keygen_galois(6, 65537, s, g)
+    assert np.array_equal(e.ks(2, a, None, gk, batch, galois=g, G=G), o.rotate(a, g, gk))
+
+
+def test_emulated_mixed_size_moduli(make_emu, oracle_mod):
+    lib = oracle_mod.lib()
+    two_n = 2 << 12
+    mods = []
+    for start in ((1 << 59), (1 << 40), (1 << 34) + (1 << 33)):
+        c = (start // two_n) * two_n + 1
+        while not lib.dpo_is_prime(c):
+            c -= two_n
+        mods.append(c)
+    e, o = make_emu(12, 3, mods), oracle_mod.Oracle(12, 3, mods)
+    s = o.keygen_secret(1)
+    evk = o.keygen_relin(2, 65537, s)
+    a = o.fill_uniform(3, 4).reshape(2, 2, 3, o.N)
+    b = o.fill_uniform(4, 4).reshape(2, 2, 3, o.N)
+    assert np.array_equal(e.ks(0, a, b, evk, 2), o.ct_mul_relin(a, b, evk))
+
+
+def test_abi_exports_every_declared_symbol():
+    """libdpfhe.so loads (no GPU needed for that) and exports exactly what include/dpfhe.h declares."""
+    import deeppowers_b200
+    from deeppowers_b200 import _lib
+    lib = deeppowers_b200.load_library()
+    with open(os.path.join(ROOT, "include", "dpfhe.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(dpfhe_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dpfhe_ctx", "dpfhe_params"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libdpfhe.so does not export %s" % name
+    assert declared == set(_lib.SYMBOLS), "python binding and header disagree: %s" % (declared ^ set(_lib.SYMBOLS))
+    assert lib.dpfhe_version().decode().startswith("dpfhe")
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    import deeppowers_b200 as dp
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less container")
+    with pytest.raises(dp.DpfheError) as ei:
+        dp.Context(13, 4)
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_touches_oracle():
+    """the shipped path (deeppowers_b200/, include/) must not import, include or link anything under oracle/"""
+    bad = []
+    for base in ("deeppowers_b200", "include"):
+        for dp_, _, files in os.walk(os.path.join(ROOT, base)):
+            if "build" in dp_.split(os.sep) or "__pycache__" in dp_:
+                continue
+            for fn in files:
+                if fn.endswith((".so", ".o", ".pyc")):
+                    continue
+                with open(os.path.join(dp_, fn), errors="ignore") as f:
+                    txt = f.read()
+                if re.search(r"(import\s+oracle|from\s+oracle|dpfhe_oracle|dpo_[a-z])", txt):
+                    bad.append(os.path.join(dp_, fn))
+    assert not bad, bad
