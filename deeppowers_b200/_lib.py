@@ -37,6 +37,7 @@ SYMBOLS = {
     "dpfhe_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "dpfhe_host_free": (C.c_int, [C.c_void_p]),
     "dpfhe_launch_count": (C.c_uint64, [C.c_void_p]),
+    "dpfhe_debug_phase_cycles": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dpfhe_describe": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
 }
 

@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -208,6 +209,9 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     lc.log_n = ctx->hp.log_n;
     lc.L = ctx->hp.L;
     lc.lp = ctx->d_lp;
+    memset(&lc.lt, 0, sizeof(lc.lt));
+    for (size_t l = 0; l < L; ++l) lc.lt.lp[l] = lps[l];
+    if (const char *env = getenv("DPFHE_NTT_CFG")) lc.ntt_cfg = atoi(env);
     lc.tw = ctx->d_tw;
     lc.itw = ctx->d_itw;
     // digit-exchange scratch for the fused key-switch kernel: one slot per resident CTA, two parities
@@ -216,6 +220,10 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     CTX_TRY(cudaMalloc(&lc.ks_flags, lc.ks_slots * sizeof(u32)));
     CTX_TRY(cudaMemset(lc.ks_flags, 0, lc.ks_slots * sizeof(u32)));
     ctx->device_bytes += lc.ks_slots * 2 * N * 8 + lc.ks_slots * sizeof(u32);
+    if (getenv("DPFHE_KS_PROF")) {   // diagnostics: per-phase cycle counters of the fused kernel
+        CTX_TRY(cudaMalloc(&lc.ks_prof, lc.ks_slots * 16 * sizeof(unsigned long long)));
+        CTX_TRY(cudaMemset(lc.ks_prof, 0, lc.ks_slots * 16 * sizeof(unsigned long long)));
+    }
     CTX_TRY(cudaDeviceSynchronize());
 #undef CTX_TRY
     *out = ctx;
@@ -231,6 +239,7 @@ void dpfhe_context_destroy(dpfhe_ctx *ctx) {
     cudaFree(ctx->d_itw);
     cudaFree(ctx->lc.ks_scratch);
     cudaFree(ctx->lc.ks_flags);
+    cudaFree(ctx->lc.ks_prof);
     cudaFree(ctx->stage_key);
     for (int k = 0; k < PIPE_DEPTH; ++k) {
         cudaFree(ctx->stage_in[k]);
@@ -443,6 +452,22 @@ int dpfhe_host_alloc(void **out, size_t bytes) {
 int dpfhe_host_free(void *p) {
     if (!p) return DPFHE_OK;
     CU_TRY(cudaFreeHost(p));
+    return DPFHE_OK;
+}
+
+// Diagnostics (not part of the drop-in surface): sums the fused kernel's per-phase clock64 counters over
+// all CTAs into out[16] and clears them.  Only available when the context was created with DPFHE_KS_PROF set.
+int dpfhe_debug_phase_cycles(dpfhe_ctx *ctx, uint64_t *out16) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (!out16 || !ctx->lc.ks_prof) return fail(DPFHE_ERR_INVALID, "phase profiling is not enabled (DPFHE_KS_PROF)");
+    std::vector<unsigned long long> h(ctx->lc.ks_slots * 16);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(h.data(), ctx->lc.ks_prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemset(ctx->lc.ks_prof, 0, h.size() * sizeof(unsigned long long)));
+    for (int k = 0; k < 16; ++k) out16[k] = 0;
+    for (size_t s = 0; s < ctx->lc.ks_slots; ++s)
+        for (int k = 0; k < 16; ++k) out16[k] += h[s * 16 + k];
     return DPFHE_OK;
 }
 

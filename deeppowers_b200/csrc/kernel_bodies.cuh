@@ -84,7 +84,7 @@ DPFHE_HD void ntt_fwd_body(CTA &cta, u64 *buf, u64 *data, const Twiddle *tw, con
     cta.par([&](int tid) {
         fwd_load_stage<LOGN, NT, false>(buf, tw, p, tid, [&](int c) { return ld_stream(src + c); });
     });
-    fwd_passes<LOGN, NT>(cta, buf, tw, p);
+    fwd_passes<LOGN, NT, 1>(cta, buf, tw, p);
     U64x2 *dst = reinterpret_cast<U64x2 *>(data);
     cta.par([&](int tid) {
         for (int c = tid; c < (1 << (LOGN - 1)); c += NT) {
@@ -152,7 +152,6 @@ struct KsArgs {
     const u64 *key;      // [L][2][L][N]
     u64 *out;            // [batch][2][L][N]
     u64 *scratch;        // [slots][2 parities][N]
-    const LimbParams *lp;
     const Twiddle *tw;   // [L][N] forward tables
     const Twiddle *itw;  // [L][N] inverse tables
     u32 L;
@@ -160,13 +159,12 @@ struct KsArgs {
 };
 
 template <int LOGN, int NT, int MODE, class CTA>
-DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const KsArgs &A, size_t ct, u32 i, u64 *t_slot) {
+DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     const size_t P = (size_t)A.L * N;
-    const LimbParams p = A.lp[i];   // by value: keeps the constants in registers
     const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + ((size_t)i * 2 + 0) * P + (size_t)i * N);
     const U64x2 *ka = reinterpret_cast<const U64x2 *>(A.key + ((size_t)i * 2 + 1) * P + (size_t)i * N);
-    const u64 q4 = 2 * p.q2;
+    const u64 q4 = p.q4;
     cta.par([&](int tid) {
         for (int c = tid; c < NC; c += NT) {
             U64x2 d, s0, s1;   // digit, own contributions to acc0 / acc1 (lazy < 3q)
@@ -203,29 +201,33 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const KsArgs &
             reinterpret_cast<U64x2 *>(acc1)[c] = r1;
         }
     });
+    cta.mark(0);   // tensor / digit build + own key terms
     if (A.L == 1) return;   // no other digit needs t
     inv_passes<LOGN, NT>(cta, buf, A.itw + (size_t)i * N, p);
+    cta.mark(1);   // inverse register passes
     U64x2 *dst = reinterpret_cast<U64x2 *>(t_slot);
     cta.par([&](int tid) {
         inv_store_stage<LOGN, NT>(buf, A.itw + (size_t)i * N, p, tid, [&](int c, const U64x2 &v) { st_cg(dst + c, v); });
     });
+    cta.mark(2);   // outer inverse stage + digit publish
 }
 
 // t_src: the published t of digit j (N words, natural order, canonical mod q_j)
 template <int LOGN, int NT, class CTA>
-DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const KsArgs &A, u32 i, u32 j, const u64 *t_src) {
+DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const KsArgs &A, const LimbParams &p, u32 i, u32 j, const u64 *t_src) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     const size_t P = (size_t)A.L * N;
-    const LimbParams p = A.lp[i];   // by value: keeps the constants in registers
     const Twiddle *tw = A.tw + (size_t)i * N;
     const U64x2 *src = reinterpret_cast<const U64x2 *>(t_src);
     cta.par([&](int tid) {
         fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); });
     });
-    fwd_passes<LOGN, NT>(cta, buf, tw, p);
+    cta.mark(4);   // digit fetch + lift + outer forward stage
+    fwd_passes<LOGN, NT, 3>(cta, buf, tw, p);
+    cta.mark(5);   // forward register passes
     const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + ((size_t)j * 2 + 0) * P + (size_t)i * N);
     const U64x2 *ka = reinterpret_cast<const U64x2 *>(A.key + ((size_t)j * 2 + 1) * P + (size_t)i * N);
-    const u64 q4 = 2 * p.q2;
+    const u64 q4 = p.q4;
     cta.par([&](int tid) {
         for (int c = tid; c < NC; c += NT) {
             U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)];
@@ -241,13 +243,13 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const Ks
             reinterpret_cast<U64x2 *>(acc1)[c] = r1;
         }
     });
+    cta.mark(6);   // multiply-accumulate with the key column
 }
 
 template <int LOGN, int NT, class CTA>
-DPFHE_HD void ks_finish(CTA &cta, const u64 *acc0, const u64 *acc1, const KsArgs &A, size_t ct, u32 i) {
+DPFHE_HD void ks_finish(CTA &cta, const u64 *acc0, const u64 *acc1, const KsArgs &A, const LimbParams &p, size_t ct, u32 i) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     const size_t P = (size_t)A.L * N;
-    const LimbParams p = A.lp[i];   // by value: keeps the constants in registers
     U64x2 *o0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N);
     U64x2 *o1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
     cta.par([&](int tid) {
@@ -261,6 +263,7 @@ DPFHE_HD void ks_finish(CTA &cta, const u64 *acc0, const u64 *acc1, const KsArgs
             st_stream(o1 + c, r1);
         }
     });
+    cta.mark(7);   // canonicalise + store
 }
 
 }  // namespace dpfhe

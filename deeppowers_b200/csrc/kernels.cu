@@ -13,25 +13,50 @@
 
 namespace dpfhe {
 
+// barrier scopes of the CTA policy (ntt_core.cuh): CTA, 256-thread domain, warp.
+// PROF: thread 0 accumulates clock64() deltas per phase id into prof[blockIdx][id] (diagnostics only).
+template <int NT, bool PROF = false>
 struct DevCta {
+    unsigned long long *prof = nullptr;
+    long long last = 0;
+    __device__ __forceinline__ void mark(int id) {
+        if (PROF && threadIdx.x == 0) {
+            const long long now = clock64();
+            prof[id] += (unsigned long long)(now - last);
+            last = now;
+        }
+    }
     template <class F>
     __device__ __forceinline__ void par(F f) {
         f((int)threadIdx.x);
         __syncthreads();
     }
+    template <class F>
+    __device__ __forceinline__ void par_dom(F f) {
+        f((int)threadIdx.x);
+        if (NT <= 256) __syncthreads();
+        else asm volatile("bar.sync %0, 256;" ::"r"(1 + ((int)threadIdx.x >> 8)) : "memory");
+    }
+    template <class F>
+    __device__ __forceinline__ void par_warp(F f) {
+        f((int)threadIdx.x);
+        __syncwarp();
+    }
 };
 
 // ------------------------------------------------------------------ standalone transforms
-template <int LOGN, int NT, bool INVERSE>
-__global__ void __launch_bounds__(NT) ntt_kernel(u64 *data, const Twiddle *__restrict__ tables,
-                                                  const LimbParams *__restrict__ lps, u32 L, size_t n_limbs) {
+// The per-limb constants travel in the kernel parameter block (constant bank), so q, 2q, 8q ...
+// are read through uniform registers / constant operands instead of occupying vector registers.
+template <int LOGN, int NT, int MINB, bool INVERSE>
+__global__ void __launch_bounds__(NT, MINB) ntt_kernel(u64 *data, const Twiddle *__restrict__ tables,
+                                                        const __grid_constant__ LimbTable lt, u32 L, size_t n_limbs) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     u64 *buf = reinterpret_cast<u64 *>(smem_raw);
     constexpr size_t N = (size_t)1 << LOGN;
-    DevCta cta;
+    DevCta<NT> cta;
     for (size_t w = blockIdx.x; w < n_limbs; w += gridDim.x) {
         const u32 l = (u32)(w % L);
-        const LimbParams p = lps[l];
+        const LimbParams &p = lt.lp[l];
         if (INVERSE) ntt_inv_body<LOGN, NT>(cta, buf, data + w * N, tables + (size_t)l * N, p);
         else ntt_fwd_body<LOGN, NT>(cta, buf, data + w * N, tables + (size_t)l * N, p);
     }
@@ -51,20 +76,26 @@ __device__ __forceinline__ void st_release_u32(u32 *p, u32 v) {
 // limb i = slot % L of ciphertexts (r*G + slot) / L, r = 0, 1, ...  The L CTAs of one ciphertext sit
 // in adjacent slots of the same round and exchange their INTT'd digits through `scratch`
 // (double-buffered by round parity, L2 resident) under release/acquire flags.
-template <int LOGN, int NT, int MODE>
-__global__ void __launch_bounds__(NT, 1) ks_fused_kernel(KsArgs A, size_t batch, u32 *flags, u32 epoch) {
+template <int LOGN, int NT, int MODE, bool PROF>
+__global__ void __launch_bounds__(NT, 1) ks_fused_kernel(KsArgs A, const __grid_constant__ LimbTable lt, size_t batch, u32 *flags, u32 epoch,
+                                                         unsigned long long *prof) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr size_t N = (size_t)1 << LOGN;
     u64 *buf = reinterpret_cast<u64 *>(smem_raw);
     u64 *acc0 = buf + N, *acc1 = buf + 2 * N;
-    DevCta cta;
+    DevCta<NT, PROF> cta;
+    if (PROF) {
+        cta.prof = prof + (size_t)blockIdx.x * 16;
+        cta.last = clock64();
+    }
     const u32 L = A.L, G = gridDim.x, slot = blockIdx.x, i = slot % L;
     const size_t n_work = batch * L;
+    const LimbParams &p = lt.lp[i];
     u32 round = 0;
     for (size_t w = slot; w < n_work; w += G, ++round) {
         const size_t ct = w / L;
         const u32 parity = round & 1u;
-        ks_phase1<LOGN, NT, MODE>(cta, buf, acc0, acc1, A, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N);
+        ks_phase1<LOGN, NT, MODE>(cta, buf, acc0, acc1, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N);
         if (L > 1) {
             __threadfence();
             __syncthreads();
@@ -76,10 +107,11 @@ __global__ void __launch_bounds__(NT, 1) ks_fused_kernel(KsArgs A, size_t batch,
                     }
                 }
                 __syncthreads();
-                ks_phase2_digit<LOGN, NT>(cta, buf, acc0, acc1, A, i, j, A.scratch + ((size_t)sib * 2 + parity) * N);
+                cta.mark(3);   // waiting for the sibling's digit
+                ks_phase2_digit<LOGN, NT>(cta, buf, acc0, acc1, A, p, i, j, A.scratch + ((size_t)sib * 2 + parity) * N);
             }
         }
-        ks_finish<LOGN, NT>(cta, acc0, acc1, A, ct, i);
+        ks_finish<LOGN, NT>(cta, acc0, acc1, A, p, ct, i);
     }
 }
 
@@ -161,10 +193,9 @@ static int g_num_sms(int dev) {
     return n;
 }
 
-template <int LOGN, bool INV>
+template <int LOGN, int NT, int MINB, bool INV>
 static cudaError_t launch_ntt_t(const LaunchCtx &lc, u64 *data, size_t n_limbs, cudaStream_t st) {
-    constexpr int NT = Geometry<LOGN>::NT;
-    auto kern = ntt_kernel<LOGN, NT, INV>;
+    auto kern = ntt_kernel<LOGN, NT, MINB, INV>;
     const size_t smem = Geometry<LOGN>::LIMB_BYTES;
     static bool configured[64] = {};
     if (!configured[lc.device & 63]) {
@@ -174,17 +205,28 @@ static cudaError_t launch_ntt_t(const LaunchCtx &lc, u64 *data, size_t n_limbs, 
     }
     // one CTA per limb transform; the grid-stride loop only matters beyond 2^31-1 limbs
     const size_t grid = n_limbs < 0x7fffffffull ? n_limbs : 0x7fffffffull;
-    kern<<<(unsigned)grid, NT, smem, st>>>(data, INV ? lc.itw : lc.tw, lc.lp, lc.L, n_limbs);
+    kern<<<(unsigned)grid, NT, smem, st>>>(data, INV ? lc.itw : lc.tw, lc.lt, lc.L, n_limbs);
     return cudaGetLastError();
+}
+
+template <int LOGN, int NT, int MINB>
+static cudaError_t launch_ntt_dir(const LaunchCtx &lc, u64 *data, size_t n_limbs, bool inverse, cudaStream_t st) {
+    return inverse ? launch_ntt_t<LOGN, NT, MINB, true>(lc, data, n_limbs, st) : launch_ntt_t<LOGN, NT, MINB, false>(lc, data, n_limbs, st);
 }
 
 cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inverse, cudaStream_t st) {
     const size_t n_limbs = n_polys * lc.L;
     if (n_limbs == 0) return cudaSuccess;
     switch (lc.log_n) {
-        case 12: return inverse ? launch_ntt_t<12, true>(lc, data, n_limbs, st) : launch_ntt_t<12, false>(lc, data, n_limbs, st);
-        case 13: return inverse ? launch_ntt_t<13, true>(lc, data, n_limbs, st) : launch_ntt_t<13, false>(lc, data, n_limbs, st);
-        case 14: return inverse ? launch_ntt_t<14, true>(lc, data, n_limbs, st) : launch_ntt_t<14, false>(lc, data, n_limbs, st);
+        case 12: return launch_ntt_dir<12, 256, 2>(lc, data, n_limbs, inverse, st);
+        case 13:
+            switch (lc.ntt_cfg) {   // tuning variants (DPFHE_NTT_CFG), default 0
+                case 1: return launch_ntt_dir<13, 512, 1>(lc, data, n_limbs, inverse, st);   //  9.9 M NTT/s
+                case 2: return launch_ntt_dir<13, 512, 2>(lc, data, n_limbs, inverse, st);   // 12.6 M (64 regs, spills)
+                case 3: return launch_ntt_dir<13, 256, 2>(lc, data, n_limbs, inverse, st);   // 12.3 M
+                default: return launch_ntt_dir<13, 256, 3>(lc, data, n_limbs, inverse, st);  // 13.2 M: 3 CTAs/SM (smem-limited), 80 regs
+            }
+        case 14: return launch_ntt_dir<14, 512, 1>(lc, data, n_limbs, inverse, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -192,13 +234,13 @@ cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inve
 template <int LOGN, int MODE>
 static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cudaStream_t st) {
     constexpr int NT = Geometry<LOGN>::NT;
-    auto kern = ks_fused_kernel<LOGN, NT, MODE>;
+    auto kern = lc.ks_prof ? ks_fused_kernel<LOGN, NT, MODE, true> : ks_fused_kernel<LOGN, NT, MODE, false>;
     const size_t smem = 3 * Geometry<LOGN>::LIMB_BYTES;
-    static bool configured[64] = {};
-    if (!configured[lc.device & 63]) {
+    static bool configured[2][64] = {};
+    if (!configured[lc.ks_prof ? 1 : 0][lc.device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[lc.device & 63] = true;
+        configured[lc.ks_prof ? 1 : 0][lc.device & 63] = true;
     }
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
@@ -216,7 +258,9 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
     size_t batch_arg = batch;
     u32 *flags = lc.ks_flags;
     u32 epoch = lc.ks_epoch;
-    void *params[] = {&args, &batch_arg, &flags, &epoch};
+    LimbTable lt = lc.lt;
+    unsigned long long *prof = lc.ks_prof;
+    void *params[] = {&args, &lt, &batch_arg, &flags, &epoch, &prof};
     e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)G), dim3(NT), params, smem, st);
     lc.ks_epoch += rounds;
     return e;
@@ -227,7 +271,7 @@ cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const
     if (batch == 0) return cudaSuccess;
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.out = out; A.scratch = lc.ks_scratch;
-    A.lp = lc.lp; A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L; A.galois = galois;
+    A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L; A.galois = galois;
 #define KS_DISPATCH(LOGN)                                                              \
     switch (mode) {                                                                    \
         case KS_MUL_RELIN: return launch_ks_t<LOGN, KS_MUL_RELIN>(lc, A, batch, st);   \

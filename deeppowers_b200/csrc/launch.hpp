@@ -6,12 +6,19 @@
 
 namespace dpfhe {
 
+// per-limb constants passed by value in the kernel parameter block
+struct LimbTable {
+    LimbParams lp[16];
+};
+
 // device-resident state shared by all launches of one context
 struct LaunchCtx {
     int device = 0;
     int num_sms = 0;
     u32 log_n = 0, L = 0;
-    const LimbParams *lp = nullptr;   // [L]
+    const LimbParams *lp = nullptr;   // [L] device copy (element-wise kernels)
+    LimbTable lt;                     // host copy, passed by value to the transform kernels
+    int ntt_cfg = 0;                  // tuning variant of the N=8192 transform kernel (DPFHE_NTT_CFG)
     const Twiddle *tw = nullptr;      // [L][N] forward twiddles, device layout (ntt_core.cuh:tw_pos)
     const Twiddle *itw = nullptr;     // [L][N] inverse twiddles
     // fused key-switch pipeline
@@ -19,6 +26,7 @@ struct LaunchCtx {
     u32 *ks_flags = nullptr;          // [ks_slots] monotonically increasing round counters
     size_t ks_slots = 0;
     u32 ks_epoch = 0;                 // rounds consumed so far (flag values already used)
+    unsigned long long *ks_prof = nullptr;   // [ks_slots][16] phase cycle counters; non-null selects the profiling build
 };
 
 int query_num_sms(int dev);

@@ -30,6 +30,8 @@ struct alignas(16) U64x2 {
 struct alignas(16) LimbParams {
     u64 q;           // modulus
     u64 q2;          // 2q
+    u64 q4;          // 4q
+    u64 q8;          // 8q  (< 2^63)
     u64 bar_mu;      // floor(2^(bar_shift+64) / q)
     u64 ninv;        // N^-1 mod q                    } folded into the last inverse stage
     u64 ninv_s;      // Shoup companion of ninv
@@ -48,17 +50,24 @@ DPFHE_HD u64 umulhi64(u64 a, u64 b) {
 }
 
 DPFHE_HD u32 umulhi32(u32 a, u32 b) {
-#if defined(__CUDA_ARCH__)
-    return __umulhi(a, b);
-#else
+    // high half of a 32x32 wide multiply (IMAD.WIDE, not the much slower IMAD.HI)
     return (u32)(((u64)a * b) >> 32);
-#endif
 }
 
 // x >= m ? x - m : x, branch-free.  Correct for every 64-bit x when m <= 2^63.
+// Device: subtract with borrow and select on the borrow (IADD3, IADD3.X, 2x SEL).
 DPFHE_HD u64 csub(u64 x, u64 m) {
+#if defined(__CUDA_ARCH__)
+    u32 xl = (u32)x, xh = (u32)(x >> 32), ml = (u32)m, mh = (u32)(m >> 32), tl, th, b;
+    asm("sub.cc.u32 %0, %3, %5;\n\tsubc.cc.u32 %1, %4, %6;\n\tsubc.u32 %2, 0, 0;"
+        : "=&r"(tl), "=&r"(th), "=&r"(b)
+        : "r"(xl), "r"(xh), "r"(ml), "r"(mh));
+    const u32 rl = b ? xl : tl, rh = b ? xh : th;
+    return ((u64)rh << 32) | rl;
+#else
     u64 t = x - m;
     return t < x ? t : x;   // unsigned wrap makes t > x exactly when x < m
+#endif
 }
 
 // Shoup multiplication by a fixed w < q with ws = floor(w * 2^64 / q): valid for ANY 64-bit x.

@@ -54,9 +54,25 @@ DPFHE_HD void gs_bfly(u64 &x, u64 &y, const Twiddle &w, const LimbParams &p) {
     y = shoup_lazy(a + p.q2 - b, w.x, w.y, p.q);
 }
 
+// ---- lazy-bound schedule of the forward transform ------------------------------------------
+// Values are tracked as "< B*q".  A forward stage maps X-inputs below B*q to outputs below
+// (B+2)*q (shoup_lazy yields < 2q for any 64-bit input).  16*q < 2^64, so when B + 2 would
+// exceed 16 the X inputs of that stage first take one conditional subtraction of 8q
+// (B <= 16 -> 8).  Everything is resolved at compile time from the bound at entry.
+DPFHE_HD constexpr bool fwd_needs_csub(int bin, int stage) {
+    int b = bin;
+    for (int s = 0; s < stage; ++s) b = (b + 2 > 16 ? 8 : b) + 2;
+    return b + 2 > 16;
+}
+DPFHE_HD constexpr int fwd_bound_after(int bin, int stages) {
+    int b = bin;
+    for (int s = 0; s < stages; ++s) b = (b + 2 > 16 ? 8 : b) + 2;
+    return b;
+}
+
 // 16-point register kernels.  `x[k]` holds element k of a radix-16 group; stage u pairs
 // k with k + (8 >> u).  tw(u, j) returns the twiddle of sub-group j at local stage u.
-template <class TW>
+template <int BIN, class TW>
 DPFHE_HD void fwd16(u64 (&x)[16], const LimbParams &p, TW tw) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -65,7 +81,10 @@ DPFHE_HD void fwd16(u64 (&x)[16], const LimbParams &p, TW tw) {
         for (int j = 0; j < (1 << u); ++j) {
             const Twiddle w = tw(u, j);
 #pragma unroll
-            for (int i = 0; i < half; ++i) ct_bfly(x[j * 2 * half + i], x[j * 2 * half + half + i], w, p);
+            for (int i = 0; i < half; ++i) {
+                if (fwd_needs_csub(BIN, u)) x[j * 2 * half + i] = csub(x[j * 2 * half + i], p.q8);
+                ct_bfly(x[j * 2 * half + i], x[j * 2 * half + half + i], w, p);
+            }
         }
     }
 }
@@ -87,9 +106,9 @@ DPFHE_HD void inv16(u64 (&x)[16], const LimbParams &p, TW tw) {
 // A pass covers stages [S0, S0+4).  Group p in [0, N/16) splits as (hi, lo) with
 // lo = p mod 2^NLO, NLO = LOGN-S0-4; its 16 elements are idx = hi*2^(LOGN-S0) + k*2^NLO + lo.
 // Thread `tid` of NT handles groups p = tid + g*NT.
-// REDUCE: apply word_reduce to every element on load (keeps the lazy bound under 16q).
+// BIN: lazy bound (in units of q) of the values at entry; the pass leaves fwd_bound_after(BIN, 4).
 
-template <int LOGN, int S0, int NT, bool REDUCE>
+template <int LOGN, int S0, int NT, int BIN>
 DPFHE_HD void fwd_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid) {
     constexpr int NLO = LOGN - S0 - 4;
     constexpr int NGROUPS = 1 << (LOGN - 4);
@@ -110,11 +129,7 @@ DPFHE_HD void fwd_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParam
 #pragma unroll
             for (int k = 0; k < 16; ++k) x[k] = buf[swz(base + (k << NLO))];
         }
-        if (REDUCE) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = word_reduce(x[k], p);
-        }
-        fwd16(x, p, [&](int u, int j) { return tw[tw_pos<LOGN>(S0 + u, (hi << u) + j)]; });
+        fwd16<BIN>(x, p, [&](int u, int j) { return tw[tw_pos<LOGN>(S0 + u, (hi << u) + j)]; });
         if (NLO == 0) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -187,6 +202,7 @@ DPFHE_HD void fwd_load_stage(u64 *buf, const Twiddle *__restrict__ tw, const Lim
             x[b][0] = IN_REDUCE ? word_reduce(v.x, p) : v.x;
             x[b][1] = IN_REDUCE ? word_reduce(v.y, p) : v.y;
         }
+        // entry bound is 1 (canonical) or 3 (word-reduced); K <= 2 stages never need a csub
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             const int half = NB >> (u + 1);
@@ -266,23 +282,37 @@ DPFHE_HD void inv_store_stage(const u64 *buf, const Twiddle *__restrict__ tw, co
 }
 
 // ---- whole-limb drivers --------------------------------------------------------------
-// `cta.sync()` is __syncthreads() on the device and a no-op in the emulator, where
-// `cta.par(f)` runs f(tid) for every thread of the CTA before returning.
+// The CTA policy provides three barrier scopes (all of them "run f(tid) for every thread, then sync"):
+//   cta.par(f)       whole CTA                     (__syncthreads)
+//   cta.par_dom(f)   256-thread domain tid >> 8    (named barrier): after the outer stages the limb is
+//                    2^K independent 4096-point blocks and pass A of block b only involves the threads
+//                    g >> 8 == b (mod NT/256), so the two halves of a 512-thread CTA run decoupled;
+//   cta.par_warp(f)  one warp                      (__syncwarp): passes B and C of a 256-coefficient
+//                    sub-block touch only the 16 groups g with equal g >> 4, i.e. 16 lanes of one warp.
+// The host emulator runs every segment for all threads in order, whatever the scope.
 
-// forward: buf already holds the output of fwd_load_stage (lazy bound BIN + 2K <= 8)
-template <int LOGN, int NT, class CTA>
+// forward: buf already holds the output of fwd_load_stage, whose inputs were below BIN*q
+// (BIN = 1 canonical, 3 word-reduced).  Returns with values below fwd_out_bound<LOGN,BIN>()*q <= 16q.
+template <int LOGN, int BIN>
+DPFHE_HD constexpr int fwd_out_bound() {
+    return fwd_bound_after(BIN, LOGN);
+}
+template <int LOGN, int NT, int BIN, class CTA>
 DPFHE_HD void fwd_passes(CTA &cta, u64 *buf, const Twiddle *tw, const LimbParams &p) {
     constexpr int K = LOGN - 12;
-    cta.par([&](int tid) { fwd_pass<LOGN, K, NT, false>(buf, tw, p, tid); });      // bound <= 15
-    cta.par([&](int tid) { fwd_pass<LOGN, K + 4, NT, true>(buf, tw, p, tid); });   // 3 -> 11
-    cta.par([&](int tid) { fwd_pass<LOGN, K + 8, NT, true>(buf, tw, p, tid); });   // 3 -> 11
+    constexpr int B0 = fwd_bound_after(BIN, K), B1 = fwd_bound_after(BIN, K + 4), B2 = fwd_bound_after(BIN, K + 8);
+    static_assert(BIN + 2 * K <= 16, "load stage applies no conditional subtraction");
+    static_assert(NT % 32 == 0 && (NT >= 256 ? NT % 256 == 0 : true), "thread count must tile the barrier domains");
+    cta.par_dom([&](int tid) { fwd_pass<LOGN, K, NT, B0>(buf, tw, p, tid); });
+    cta.par_warp([&](int tid) { fwd_pass<LOGN, K + 4, NT, B1>(buf, tw, p, tid); });
+    cta.par([&](int tid) { fwd_pass<LOGN, K + 8, NT, B2>(buf, tw, p, tid); });
 }
 // inverse: buf holds [0,2q) values in bit-reversed order; afterwards run inv_store_stage
 template <int LOGN, int NT, class CTA>
 DPFHE_HD void inv_passes(CTA &cta, u64 *buf, const Twiddle *itw, const LimbParams &p) {
     constexpr int K = LOGN - 12;
-    cta.par([&](int tid) { inv_pass<LOGN, K + 8, NT>(buf, itw, p, tid); });
-    cta.par([&](int tid) { inv_pass<LOGN, K + 4, NT>(buf, itw, p, tid); });
+    cta.par_warp([&](int tid) { inv_pass<LOGN, K + 8, NT>(buf, itw, p, tid); });
+    cta.par_dom([&](int tid) { inv_pass<LOGN, K + 4, NT>(buf, itw, p, tid); });
     cta.par([&](int tid) { inv_pass<LOGN, K, NT>(buf, itw, p, tid); });
 }
 

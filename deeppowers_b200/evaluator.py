@@ -103,6 +103,12 @@ class Context:
     def device_bytes(self):
         return int(self._l.dpfhe_context_device_bytes(self._h))
 
+    def phase_cycles(self):
+        """diagnostics: per-phase clock64 totals of the fused kernel (needs DPFHE_KS_PROF at context creation)"""
+        out = np.zeros(16, dtype=np.uint64)
+        self._chk(self._l.dpfhe_debug_phase_cycles(self._h, _hptr(out, True)))
+        return out
+
     def describe(self):
         buf = C.create_string_buffer(1024)
         self._l.dpfhe_describe(self._h, buf, 1024)

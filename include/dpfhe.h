@@ -126,6 +126,9 @@ int dpfhe_host_free(void *p);
 /* ---- diagnostics ---- */
 /* number of kernel launches issued through this context since creation */
 uint64_t dpfhe_launch_count(const dpfhe_ctx *ctx);
+/* per-phase clock64 totals of the fused key-switch kernel (summed over CTAs, then cleared); needs the
+ * context to have been created with DPFHE_KS_PROF set in the environment.  out16: 16 words. */
+int dpfhe_debug_phase_cycles(dpfhe_ctx *ctx, uint64_t *out16);
 /* name + launch geometry of the kernels behind an op, for bench/DESIGN reporting; returns bytes written */
 int dpfhe_describe(const dpfhe_ctx *ctx, char *buf, size_t buf_len);
 

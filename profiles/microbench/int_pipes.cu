@@ -83,7 +83,7 @@ void run(const char *name, double per_iter_results, LimbParams p, int threads) {
 
 int main() {
     LimbParams p;
-    p.q = 0xfffffffffffc001ull; p.q2 = 2 * p.q;
+    p.q = 0xfffffffffffc001ull; p.q2 = 2 * p.q; p.q4 = 4 * p.q; p.q8 = 8 * p.q;
     p.bar_shift = 58; p.bar_mu = (unsigned long long)(((unsigned __int128)1 << 122) / p.q);
     p.mu32 = (unsigned)(((unsigned __int128)1 << 64) / p.q);
     p.ninv = 0x123456789abcdefull % p.q; p.ninv_s = (unsigned long long)(((unsigned __int128)p.ninv << 64) / p.q);

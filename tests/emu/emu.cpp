@@ -22,6 +22,12 @@ struct HostCta {
     void par(F f) {
         for (int t = 0; t < nt; ++t) f(t);
     }
+    // the emulator runs whole segments in order, so every barrier scope degenerates to "all threads"
+    template <class F>
+    void par_dom(F f) { par(f); }
+    template <class F>
+    void par_warp(F f) { par(f); }
+    void mark(int) {}
 };
 
 template <class T>
@@ -72,7 +78,7 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
     uint64_t *scratch = aligned_new<uint64_t>((size_t)G * 2 * N);
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.out = out; A.scratch = scratch;
-    A.lp = e.lp.data(); A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois;
+    A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois;
     HostCta cta{NT};
     const size_t n_work = batch * L;
     for (size_t r = 0; r * G < n_work; ++r) {
@@ -80,7 +86,7 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
         for (unsigned s = 0; s < G; ++s) {
             const size_t w = r * G + s;
             if (w >= n_work) break;
-            ks_phase1<LOGN, NT, MODE>(cta, buf[s], acc0[s], acc1[s], A, w / L, (uint32_t)(w % L), scratch + ((size_t)s * 2 + par) * N);
+            ks_phase1<LOGN, NT, MODE>(cta, buf[s], acc0[s], acc1[s], A, e.lp[w % L], w / L, (uint32_t)(w % L), scratch + ((size_t)s * 2 + par) * N);
         }
         for (unsigned s = 0; s < G; ++s) {
             const size_t w = r * G + s;
@@ -89,9 +95,9 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
             for (uint32_t jj = 1; jj < L; ++jj) {
                 const uint32_t j = (i + jj) % L;
                 const unsigned sib = s - i + j;
-                ks_phase2_digit<LOGN, NT>(cta, buf[s], acc0[s], acc1[s], A, i, j, scratch + ((size_t)sib * 2 + par) * N);
+                ks_phase2_digit<LOGN, NT>(cta, buf[s], acc0[s], acc1[s], A, e.lp[i], i, j, scratch + ((size_t)sib * 2 + par) * N);
             }
-            ks_finish<LOGN, NT>(cta, acc0[s], acc1[s], A, w / L, i);
+            ks_finish<LOGN, NT>(cta, acc0[s], acc1[s], A, e.lp[i], w / L, i);
         }
     }
     for (unsigned s = 0; s < G; ++s) {

@@ -1,0 +1,18 @@
+"""small ct_mul_relin + NTT run for compute-sanitizer racecheck/memcheck"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import deeppowers_b200 as dp
+for log_n, L, B in ((13, 4, 3), (12, 2, 2), (14, 2, 1)):
+    c = dp.Context(log_n, L)
+    N = 1 << log_n
+    a = torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda"); b = torch.empty_like(a); out = torch.empty_like(a)
+    evk = torch.empty((L, 2, L, N), dtype=torch.int64, device="cuda")
+    c.fill_uniform(1, a, 2 * B); c.fill_uniform(2, b, 2 * B); c.fill_uniform(3, evk, 2 * L)
+    c.ntt_fwd(a, 2 * B); c.ntt_inv(a, 2 * B)
+    if log_n <= 13:
+        c.ct_mul_relin(a, b, evk, out, B)
+        c.rotate(a, 5, evk, out, B)
+    torch.cuda.synchronize()
+    c.close()
+print("ok")
