@@ -212,13 +212,19 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     memset(&lc.lt, 0, sizeof(lc.lt));
     for (size_t l = 0; l < L; ++l) lc.lt.lp[l] = lps[l];
     if (const char *env = getenv("DPFHE_NTT_CFG")) lc.ntt_cfg = atoi(env);
+    if (const char *env = getenv("DPFHE_KS_OCC")) lc.ks_occ_cap = atoi(env);
     lc.tw = ctx->d_tw;
     lc.itw = ctx->d_itw;
     // digit-exchange scratch for the fused key-switch kernel: one slot per resident CTA, two parities
-    lc.ks_slots = (size_t)lc.num_sms * 2;
+    lc.ks_slots = (size_t)lc.num_sms * 4;
     CTX_TRY(cudaMalloc(&lc.ks_scratch, lc.ks_slots * 2 * N * 8));
+    CTX_TRY(cudaMalloc(&lc.ks_key_s, 2 * L * L * N * 8));
+    ctx->device_bytes += 2 * L * L * N * 8;
     CTX_TRY(cudaMalloc(&lc.ks_flags, lc.ks_slots * sizeof(u32)));
     CTX_TRY(cudaMemset(lc.ks_flags, 0, lc.ks_slots * sizeof(u32)));
+    CTX_TRY(cudaMalloc(&lc.ks_ticket, 64));
+    CTX_TRY(cudaMalloc(&lc.ks_mail, lc.ks_slots * sizeof(u64)));
+    CTX_TRY(cudaMemset(lc.ks_mail, 0, lc.ks_slots * sizeof(u64)));
     ctx->device_bytes += lc.ks_slots * 2 * N * 8 + lc.ks_slots * sizeof(u32);
     if (getenv("DPFHE_KS_PROF")) {   // diagnostics: per-phase cycle counters of the fused kernel
         CTX_TRY(cudaMalloc(&lc.ks_prof, lc.ks_slots * 16 * sizeof(unsigned long long)));
@@ -239,6 +245,9 @@ void dpfhe_context_destroy(dpfhe_ctx *ctx) {
     cudaFree(ctx->d_itw);
     cudaFree(ctx->lc.ks_scratch);
     cudaFree(ctx->lc.ks_flags);
+    cudaFree(ctx->lc.ks_key_s);
+    cudaFree(ctx->lc.ks_ticket);
+    cudaFree(ctx->lc.ks_mail);
     cudaFree(ctx->lc.ks_prof);
     cudaFree(ctx->stage_key);
     for (int k = 0; k < PIPE_DEPTH; ++k) {
@@ -334,7 +343,7 @@ static int ks_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const uint64_t
     }
     if (out == a || out == b) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
     CU_TRY(launch_ks(ctx->lc, mode, a, b, key, out, batch, (u32)galois, pick(ctx, stream)));
-    ctx->launches++;
+    ctx->launches += 2;   // key_prepare_kernel + ks_fused_kernel
     return DPFHE_OK;
 }
 
@@ -468,6 +477,13 @@ int dpfhe_debug_phase_cycles(dpfhe_ctx *ctx, uint64_t *out16) {
     for (int k = 0; k < 16; ++k) out16[k] = 0;
     for (size_t s = 0; s < ctx->lc.ks_slots; ++s)
         for (int k = 0; k < 16; ++k) out16[k] += h[s * 16 + k];
+    out16[12] = out16[13] = 0;   // [12] = min, [13] = max CTA lifetime (ns) over the CTAs that ran
+    for (size_t s = 0; s < ctx->lc.ks_slots; ++s) {
+        const uint64_t ns = h[s * 16 + 14];
+        if (!ns) continue;
+        if (ns > out16[13]) out16[13] = ns;
+        if (!out16[12] || ns < out16[12]) out16[12] = ns;
+    }
     return DPFHE_OK;
 }
 
@@ -478,7 +494,7 @@ int dpfhe_describe(const dpfhe_ctx *ctx, char *buf, size_t buf_len) {
                      "{\"log_n\": %u, \"n_limbs\": %u, \"num_sms\": %d, \"ntt_kernel\": {\"threads\": %u, \"smem_bytes\": %zu, "
                      "\"grid\": \"one CTA per limb\"}, \"ks_fused_kernel\": {\"threads\": %u, \"smem_bytes\": %zu, "
                      "\"grid\": \"persistent cooperative, multiple of L, <= %zu slots\"}}",
-                     ctx->hp.log_n, ctx->hp.L, ctx->lc.num_sms, nt, ctx->N() * 8, nt, 3 * ctx->N() * 8, ctx->lc.ks_slots);
+                     ctx->hp.log_n, ctx->hp.L, ctx->lc.num_sms, nt, ctx->N() * 8, 256u, ctx->N() * 8, ctx->lc.ks_slots);
     return n;
 }
 

@@ -138,18 +138,21 @@ DPFHE_HD void tensor_coeff(u64 a0, u64 a1, u64 b0, u64 b1, const LimbParams &p, 
 }
 
 // ---- fused key-switch family ------------------------------------------
-// One work item = (ciphertext ct, output limb i).  Shared memory: buf[N] (swizzled transform
-// buffer), acc0[N], acc1[N] (linear, lazy accumulators kept below 4q).
-//   phase 1: build the digit d = d2[i] (tensor / input / permuted c1), initialise
+// One work item = (ciphertext ct, output limb i).  Shared memory holds only the swizzled transform
+// buffer buf[N]; the two lazy accumulators live in the OUTPUT rows out[ct][0|1][i] themselves
+// (L2-resident read-modify-write by the owning thread, values kept below 16q), which keeps the CTA at
+// one limb of shared memory so that three CTAs share an SM and hide each other's memory phases.
+//   phase 1: build the digit d = d2[i] (tensor / input / permuted c1), write
 //            acc = (own terms) + d o key[i][.][i], INTT(d) -> t_i, publish t_i to the slot.
 //   phase 2: for every other digit j: u = NTT_i(t_j mod q_i); acc += u o key[j][.][i];
-//            finally write canon(acc) to out[ct][.][i].
+//            the last digit writes canon(acc).
 enum KsMode { KS_MUL_RELIN = 0, KS_PLAIN = 1, KS_ROTATE = 2 };
 
 struct KsArgs {
     const u64 *a;        // MUL_RELIN: a [batch][2][L][N]; PLAIN: d [batch][L][N]; ROTATE: ct [batch][2][L][N]
     const u64 *b;        // MUL_RELIN: b
     const u64 *key;      // [L][2][L][N]
+    const u64 *key_s;    // Shoup companions floor(key * 2^64 / q_limb), same layout (built per launch)
     u64 *out;            // [batch][2][L][N]
     u64 *scratch;        // [slots][2 parities][N]
     const Twiddle *tw;   // [L][N] forward tables
@@ -158,47 +161,79 @@ struct KsArgs {
     u32 galois;          // ROTATE only
 };
 
+// operands of one 16-byte chunk position of phase 1, fetched one iteration ahead of their use
+struct KsP1Operands {
+    U64x2 a0, a1, b0, b1;   // MUL_RELIN: the four input chunks; PLAIN: a0 = digit; ROTATE: a0 = c0 gather, a1 = c1 gather
+    U64x2 kb, ka, kbs, kas; // key[i][b|a][i] chunk and Shoup companions
+};
+
+template <int LOGN, int MODE>
+DPFHE_HD KsP1Operands ks_p1_fetch(const KsArgs &A, size_t ct, u32 i, int c) {
+    constexpr int N = 1 << LOGN;
+    const size_t P = (size_t)A.L * N;
+    KsP1Operands o;
+    const size_t koff_b = ((size_t)i * 2 + 0) * P + (size_t)i * N, koff_a = ((size_t)i * 2 + 1) * P + (size_t)i * N;
+    o.kb = ld_keep(reinterpret_cast<const U64x2 *>(A.key + koff_b) + c);
+    o.ka = ld_keep(reinterpret_cast<const U64x2 *>(A.key + koff_a) + c);
+    o.kbs = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + koff_b) + c);
+    o.kas = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + koff_a) + c);
+    if (MODE == KS_MUL_RELIN) {
+        o.a0 = ld_stream(reinterpret_cast<const U64x2 *>(A.a + ct * 2 * P + (size_t)i * N) + c);
+        o.a1 = ld_stream(reinterpret_cast<const U64x2 *>(A.a + ct * 2 * P + P + (size_t)i * N) + c);
+        o.b0 = ld_stream(reinterpret_cast<const U64x2 *>(A.b + ct * 2 * P + (size_t)i * N) + c);
+        o.b1 = ld_stream(reinterpret_cast<const U64x2 *>(A.b + ct * 2 * P + P + (size_t)i * N) + c);
+    } else if (MODE == KS_PLAIN) {
+        o.a0 = ld_stream(reinterpret_cast<const U64x2 *>(A.a + ct * P + (size_t)i * N) + c);
+        o.a1 = o.b0 = o.b1 = o.a0;
+    } else {
+        const u64 *c0 = A.a + ct * 2 * P + (size_t)i * N, *c1 = c0 + P;
+        const int n0 = galois_index<LOGN>(2 * c, A.galois), n1 = galois_index<LOGN>(2 * c + 1, A.galois);
+        o.a0.x = c0[n0];
+        o.a0.y = c0[n1];
+        o.a1.x = c1[n0];
+        o.a1.y = c1[n1];
+        o.b0 = o.b1 = o.a0;
+    }
+    return o;
+}
+
 template <int LOGN, int NT, int MODE, class CTA>
-DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot) {
+DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     const size_t P = (size_t)A.L * N;
-    const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + ((size_t)i * 2 + 0) * P + (size_t)i * N);
-    const U64x2 *ka = reinterpret_cast<const U64x2 *>(A.key + ((size_t)i * 2 + 1) * P + (size_t)i * N);
-    const u64 q4 = p.q4;
+    U64x2 *acc0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N);
+    U64x2 *acc1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
+    const bool only = A.L == 1;   // a single digit: no phase 2, write the canonical result here
     cta.par([&](int tid) {
+        KsP1Operands nxt = ks_p1_fetch<LOGN, MODE>(A, ct, i, tid);
         for (int c = tid; c < NC; c += NT) {
+            const KsP1Operands o = nxt;
+            if (c + NT < NC) nxt = ks_p1_fetch<LOGN, MODE>(A, ct, i, c + NT);   // next chunk's loads fly during this chunk's math
             U64x2 d, s0, s1;   // digit, own contributions to acc0 / acc1 (lazy < 3q)
             if (MODE == KS_MUL_RELIN) {
-                const U64x2 *pa0 = reinterpret_cast<const U64x2 *>(A.a + ct * 2 * P + (size_t)i * N);
-                const U64x2 *pa1 = reinterpret_cast<const U64x2 *>(A.a + ct * 2 * P + P + (size_t)i * N);
-                const U64x2 *pb0 = reinterpret_cast<const U64x2 *>(A.b + ct * 2 * P + (size_t)i * N);
-                const U64x2 *pb1 = reinterpret_cast<const U64x2 *>(A.b + ct * 2 * P + P + (size_t)i * N);
-                U64x2 a0 = ld_stream(pa0 + c), a1 = ld_stream(pa1 + c), b0 = ld_stream(pb0 + c), b1 = ld_stream(pb1 + c);
-                tensor_coeff(a0.x, a1.x, b0.x, b1.x, p, s0.x, s1.x, d.x);
-                tensor_coeff(a0.y, a1.y, b0.y, b1.y, p, s0.y, s1.y, d.y);
+                tensor_coeff(o.a0.x, o.a1.x, o.b0.x, o.b1.x, p, s0.x, s1.x, d.x);
+                tensor_coeff(o.a0.y, o.a1.y, o.b0.y, o.b1.y, p, s0.y, s1.y, d.y);
             } else if (MODE == KS_PLAIN) {
-                const U64x2 *pd = reinterpret_cast<const U64x2 *>(A.a + ct * P + (size_t)i * N);
-                d = ld_stream(pd + c);
+                d = o.a0;
                 s0.x = s0.y = s1.x = s1.y = 0;
             } else {
-                const u64 *c0 = A.a + ct * 2 * P + (size_t)i * N, *c1 = c0 + P;
-                const int n0 = galois_index<LOGN>(2 * c, A.galois), n1 = galois_index<LOGN>(2 * c + 1, A.galois);
-                d.x = c1[n0];
-                d.y = c1[n1];
-                s0.x = c0[n0];
-                s0.y = c0[n1];
+                d = o.a1;
+                s0 = o.a0;
                 s1.x = s1.y = 0;
             }
             // digit enters the inverse transform in [0,2q)
             reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = d;
-            const U64x2 vb = ld_keep(kb + c), va = ld_keep(ka + c);
-            U64x2 r0, r1;
-            r0.x = csub(s0.x + mulmod_lazy(d.x, vb.x, p), q4);
-            r0.y = csub(s0.y + mulmod_lazy(d.y, vb.y, p), q4);
-            r1.x = csub(s1.x + mulmod_lazy(d.x, va.x, p), q4);
-            r1.y = csub(s1.y + mulmod_lazy(d.y, va.y, p), q4);
-            reinterpret_cast<U64x2 *>(acc0)[c] = r0;
-            reinterpret_cast<U64x2 *>(acc1)[c] = r1;
+            U64x2 r0, r1;   // s < 3q, Shoup term < 2q  ->  accumulator starts below 5q
+            r0.x = s0.x + shoup_lazy(d.x, o.kb.x, o.kbs.x, p.q);
+            r0.y = s0.y + shoup_lazy(d.y, o.kb.y, o.kbs.y, p.q);
+            r1.x = s1.x + shoup_lazy(d.x, o.ka.x, o.kas.x, p.q);
+            r1.y = s1.y + shoup_lazy(d.y, o.ka.y, o.kas.y, p.q);
+            if (only) {
+                r0.x = canon(r0.x, p); r0.y = canon(r0.y, p);
+                r1.x = canon(r1.x, p); r1.y = canon(r1.y, p);
+            }
+            st_cg(acc0 + c, r0);
+            st_cg(acc1 + c, r1);
         }
     });
     cta.mark(0);   // tensor / digit build + own key terms
@@ -214,7 +249,7 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const KsArgs &
 
 // t_src: the published t of digit j (N words, natural order, canonical mod q_j)
 template <int LOGN, int NT, class CTA>
-DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const KsArgs &A, const LimbParams &p, u32 i, u32 j, const u64 *t_src) {
+DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u32 j, u32 jj, const u64 *t_src) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     const size_t P = (size_t)A.L * N;
     const Twiddle *tw = A.tw + (size_t)i * N;
@@ -225,45 +260,49 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, u64 *acc0, u64 *acc1, const Ks
     cta.mark(4);   // digit fetch + lift + outer forward stage
     fwd_passes<LOGN, NT, 3>(cta, buf, tw, p);
     cta.mark(5);   // forward register passes
-    const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + ((size_t)j * 2 + 0) * P + (size_t)i * N);
-    const U64x2 *ka = reinterpret_cast<const U64x2 *>(A.key + ((size_t)j * 2 + 1) * P + (size_t)i * N);
-    const u64 q4 = p.q4;
+    const size_t koff_b = ((size_t)j * 2 + 0) * P + (size_t)i * N, koff_a = ((size_t)j * 2 + 1) * P + (size_t)i * N;
+    const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + koff_b), *ka = reinterpret_cast<const U64x2 *>(A.key + koff_a);
+    const U64x2 *kbs = reinterpret_cast<const U64x2 *>(A.key_s + koff_b), *kas = reinterpret_cast<const U64x2 *>(A.key_s + koff_a);
+    U64x2 *acc0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N);
+    U64x2 *acc1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
+    // lazy accumulator bound: < 5q after phase 1, +2q per digit; every 4th digit one csub(8q) keeps it <= 16q
+    const bool trim = (jj & 3u) == 0u, last = jj + 1 == A.L;
     cta.par([&](int tid) {
+        U64x2 nb = ld_keep(kb + tid), na = ld_keep(ka + tid), nbs = ld_keep(kbs + tid), nas = ld_keep(kas + tid);
+        U64x2 n0 = ld_cg(acc0 + tid), n1 = ld_cg(acc1 + tid);
         for (int c = tid; c < NC; c += NT) {
-            U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)];
-            u.x = word_reduce(u.x, p);   // < 3q
-            u.y = word_reduce(u.y, p);
-            const U64x2 vb = ld_keep(kb + c), va = ld_keep(ka + c);
-            U64x2 r0 = reinterpret_cast<U64x2 *>(acc0)[c], r1 = reinterpret_cast<U64x2 *>(acc1)[c];
-            r0.x = csub(r0.x + mulmod_lazy(u.x, vb.x, p), q4);
-            r0.y = csub(r0.y + mulmod_lazy(u.y, vb.y, p), q4);
-            r1.x = csub(r1.x + mulmod_lazy(u.x, va.x, p), q4);
-            r1.y = csub(r1.y + mulmod_lazy(u.y, va.y, p), q4);
-            reinterpret_cast<U64x2 *>(acc0)[c] = r0;
-            reinterpret_cast<U64x2 *>(acc1)[c] = r1;
+            const U64x2 vb = nb, va = na, vbs = nbs, vas = nas;
+            U64x2 r0 = n0, r1 = n1;
+            if (c + NT < NC) {
+                nb = ld_keep(kb + c + NT);
+                na = ld_keep(ka + c + NT);
+                nbs = ld_keep(kbs + c + NT);
+                nas = ld_keep(kas + c + NT);
+                n0 = ld_cg(acc0 + c + NT);
+                n1 = ld_cg(acc1 + c + NT);
+            }
+            // u < 16q straight from the transform: Shoup multiplication accepts any 64-bit operand
+            const U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)];
+            r0.x += shoup_lazy(u.x, vb.x, vbs.x, p.q);
+            r0.y += shoup_lazy(u.y, vb.y, vbs.y, p.q);
+            r1.x += shoup_lazy(u.x, va.x, vas.x, p.q);
+            r1.y += shoup_lazy(u.y, va.y, vas.y, p.q);
+            if (trim) {
+                r0.x = csub(r0.x, p.q8); r0.y = csub(r0.y, p.q8);
+                r1.x = csub(r1.x, p.q8); r1.y = csub(r1.y, p.q8);
+            }
+            if (last) {
+                r0.x = canon(r0.x, p); r0.y = canon(r0.y, p);
+                r1.x = canon(r1.x, p); r1.y = canon(r1.y, p);
+                st_stream(acc0 + c, r0);
+                st_stream(acc1 + c, r1);
+            } else {
+                st_cg(acc0 + c, r0);
+                st_cg(acc1 + c, r1);
+            }
         }
     });
-    cta.mark(6);   // multiply-accumulate with the key column
-}
-
-template <int LOGN, int NT, class CTA>
-DPFHE_HD void ks_finish(CTA &cta, const u64 *acc0, const u64 *acc1, const KsArgs &A, const LimbParams &p, size_t ct, u32 i) {
-    constexpr int N = 1 << LOGN, NC = N / 2;
-    const size_t P = (size_t)A.L * N;
-    U64x2 *o0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N);
-    U64x2 *o1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
-    cta.par([&](int tid) {
-        for (int c = tid; c < NC; c += NT) {
-            U64x2 r0 = reinterpret_cast<const U64x2 *>(acc0)[c], r1 = reinterpret_cast<const U64x2 *>(acc1)[c];
-            r0.x = canon4(r0.x, p);
-            r0.y = canon4(r0.y, p);
-            r1.x = canon4(r1.x, p);
-            r1.y = canon4(r1.y, p);
-            st_stream(o0 + c, r0);
-            st_stream(o1 + c, r1);
-        }
-    });
-    cta.mark(7);   // canonicalise + store
+    cta.mark(6);   // multiply-accumulate with the key column (the last digit also canonicalises and stores)
 }
 
 }  // namespace dpfhe

@@ -71,31 +71,57 @@ __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
 __device__ __forceinline__ void st_release_u32(u32 *p, u32 v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ u64 ld_acquire_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(u64 *p, u64 v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
-// grid = G CTAs, G a multiple of L, all co-resident (cooperative launch).  CTA `slot` owns output
-// limb i = slot % L of ciphertexts (r*G + slot) / L, r = 0, 1, ...  The L CTAs of one ciphertext sit
-// in adjacent slots of the same round and exchange their INTT'd digits through `scratch`
-// (double-buffered by round parity, L2 resident) under release/acquire flags.
-template <int LOGN, int NT, int MODE, bool PROF>
-__global__ void __launch_bounds__(NT, 1) ks_fused_kernel(KsArgs A, const __grid_constant__ LimbTable lt, size_t batch, u32 *flags, u32 epoch,
-                                                         unsigned long long *prof) {
+// grid = G CTAs, G a multiple of L, all co-resident (cooperative launch).  The L CTAs of slots
+// [g*L, (g+1)*L) form a group that processes one ciphertext at a time: CTA `slot` owns output limb
+// i = slot % L.  The group leader (i == 0) draws the next ciphertext index from a global ticket counter
+// and posts it in the group's mailbox (dynamic balancing: groups that run ahead take more work);
+// the members exchange their INTT'd digits through `scratch` (double-buffered by round parity,
+// L2 resident) under release/acquire flags.
+template <int LOGN, int NT, int MINB, int MODE, bool PROF>
+__global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __grid_constant__ LimbTable lt, size_t batch, u32 *flags, u32 epoch,
+                                                            u32 *ticket, u64 *mail, unsigned long long *prof) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr size_t N = (size_t)1 << LOGN;
     u64 *buf = reinterpret_cast<u64 *>(smem_raw);
-    u64 *acc0 = buf + N, *acc1 = buf + 2 * N;
     DevCta<NT, PROF> cta;
+    unsigned long long t_start = 0, c_start = 0;
     if (PROF) {
         cta.prof = prof + (size_t)blockIdx.x * 16;
         cta.last = clock64();
+        c_start = (unsigned long long)cta.last;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     }
-    const u32 L = A.L, G = gridDim.x, slot = blockIdx.x, i = slot % L;
-    const size_t n_work = batch * L;
+    __shared__ u32 s_ct;
+    const u32 L = A.L, slot = blockIdx.x, i = slot % L, group = slot / L;
     const LimbParams &p = lt.lp[i];
-    u32 round = 0;
-    for (size_t w = slot; w < n_work; w += G, ++round) {
-        const size_t ct = w / L;
+    for (u32 round = 0;; ++round) {
+        if (threadIdx.x == 0) {
+            const u32 tag = epoch + round + 1;
+            if (i == 0) {
+                const u32 t = atomicAdd(ticket, 1u);
+                if (L > 1) st_release_u64(mail + group, ((u64)tag << 32) | t);
+                s_ct = t;
+            } else {
+                u64 m;
+                do m = ld_acquire_u64(mail + group);
+                while ((u32)(m >> 32) != tag);
+                s_ct = (u32)m;
+            }
+        }
+        __syncthreads();
+        const size_t ct = s_ct;
+        if (ct >= batch) break;   // every member of the group reads the same ticket, so they leave together
         const u32 parity = round & 1u;
-        ks_phase1<LOGN, NT, MODE>(cta, buf, acc0, acc1, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N);
+        ks_phase1<LOGN, NT, MODE>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N);
         if (L > 1) {
             __threadfence();
             __syncthreads();
@@ -108,10 +134,15 @@ __global__ void __launch_bounds__(NT, 1) ks_fused_kernel(KsArgs A, const __grid_
                 }
                 __syncthreads();
                 cta.mark(3);   // waiting for the sibling's digit
-                ks_phase2_digit<LOGN, NT>(cta, buf, acc0, acc1, A, p, i, j, A.scratch + ((size_t)sib * 2 + parity) * N);
+                ks_phase2_digit<LOGN, NT>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)sib * 2 + parity) * N);
             }
         }
-        ks_finish<LOGN, NT>(cta, acc0, acc1, A, p, ct, i);
+    }
+    if (PROF && threadIdx.x == 0) {   // CTA lifetime in nanoseconds (globaltimer) and in SM cycles
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        cta.prof[14] += t_end - t_start;
+        cta.prof[15] += (unsigned long long)clock64() - c_start;
     }
 }
 
@@ -180,12 +211,29 @@ __global__ void __launch_bounds__(256) fill_uniform_kernel(U64x2 *__restrict__ o
     }
 }
 
+// Shoup companions of a switch key: ks[e] = floor(key[e] * 2^64 / q_limb(e)); layout [L][2][L][N]
+template <int LOGN>
+__global__ void __launch_bounds__(256) key_prepare_kernel(const u64 *__restrict__ key, u64 *__restrict__ key_s,
+                                                          const LimbParams *__restrict__ lps, u32 L, size_t n) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const u64 q = lps[(e >> LOGN) % L].q;
+        key_s[e] = (u64)((((unsigned __int128)key[e]) << 64) / q);
+    }
+}
+
 // ------------------------------------------------------------------ launchers
 template <int LOGN>
 struct Geometry {
     static constexpr int NT = LOGN == 12 ? 256 : 512;
     static constexpr size_t LIMB_BYTES = (size_t)8 << LOGN;
 };
+
+static unsigned ew_grid(const LaunchCtx &lc, size_t work_items) {
+    size_t blocks = (work_items + 255) / 256;
+    const size_t cap = (size_t)lc.num_sms * 32;   // 8 resident CTAs of 256 threads per SM, 4 waves
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks ? blocks : 1);
+}
 
 static int g_num_sms(int dev) {
     int n = 0;
@@ -233,9 +281,9 @@ cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inve
 
 template <int LOGN, int MODE>
 static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cudaStream_t st) {
-    constexpr int NT = Geometry<LOGN>::NT;
-    auto kern = lc.ks_prof ? ks_fused_kernel<LOGN, NT, MODE, true> : ks_fused_kernel<LOGN, NT, MODE, false>;
-    const size_t smem = 3 * Geometry<LOGN>::LIMB_BYTES;
+    constexpr int NT = 256, MINB = 3;   // one limb of shared memory per CTA -> three CTAs per SM
+    auto kern = lc.ks_prof ? ks_fused_kernel<LOGN, NT, MINB, MODE, true> : ks_fused_kernel<LOGN, NT, MINB, MODE, false>;
+    const size_t smem = Geometry<LOGN>::LIMB_BYTES;
     static bool configured[2][64] = {};
     if (!configured[lc.ks_prof ? 1 : 0][lc.device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -246,21 +294,26 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
+    if (lc.ks_occ_cap > 0 && occ > lc.ks_occ_cap) occ = lc.ks_occ_cap;
     size_t G = (size_t)lc.num_sms * occ;
     if (G > lc.ks_slots) G = lc.ks_slots;
     G = (G / lc.L) * lc.L;
     const size_t n_work = batch * lc.L;
     if (G > n_work) G = n_work;
     if (G == 0) return cudaErrorInvalidConfiguration;
-    // rounds this launch will consume from the flag epoch space
-    const u32 rounds = (u32)((n_work + G - 1) / G);
+    // flag / mailbox tags this launch may consume: one per round, and a group runs at most batch + 1 rounds
+    const u32 rounds = (u32)(batch + 1);
+    cudaError_t em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
+    if (em != cudaSuccess) return em;
     KsArgs args = A;
     size_t batch_arg = batch;
     u32 *flags = lc.ks_flags;
     u32 epoch = lc.ks_epoch;
     LimbTable lt = lc.lt;
     unsigned long long *prof = lc.ks_prof;
-    void *params[] = {&args, &lt, &batch_arg, &flags, &epoch, &prof};
+    u32 *ticket = lc.ks_ticket;
+    u64 *mail = lc.ks_mail;
+    void *params[] = {&args, &lt, &batch_arg, &flags, &epoch, &ticket, &mail, &prof};
     e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)G), dim3(NT), params, smem, st);
     lc.ks_epoch += rounds;
     return e;
@@ -269,8 +322,17 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
 cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch,
                       u32 galois, cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
+    // Shoup companions of the key for this launch (2*L*P words, a few microseconds; batch-amortised)
+    {
+        const size_t n = (size_t)2 * lc.L * lc.L << lc.log_n;
+        const unsigned grid = ew_grid(lc, n);
+        if (lc.log_n == 12) key_prepare_kernel<12><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        else key_prepare_kernel<13><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     KsArgs A;
-    A.a = a; A.b = b; A.key = key; A.out = out; A.scratch = lc.ks_scratch;
+    A.a = a; A.b = b; A.key = key; A.key_s = lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
     A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L; A.galois = galois;
 #define KS_DISPATCH(LOGN)                                                              \
     switch (mode) {                                                                    \
@@ -284,13 +346,6 @@ cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const
         case 13: KS_DISPATCH(13)
     }
     return cudaErrorNotSupported;
-}
-
-static unsigned ew_grid(const LaunchCtx &lc, size_t work_items) {
-    size_t blocks = (work_items + 255) / 256;
-    const size_t cap = (size_t)lc.num_sms * 32;   // 8 resident CTAs of 256 threads per SM, 4 waves
-    if (blocks > cap) blocks = cap;
-    return (unsigned)(blocks ? blocks : 1);
 }
 
 #define LOGN_SWITCH(call12, call13, call14)  \

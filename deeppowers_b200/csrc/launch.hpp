@@ -24,8 +24,12 @@ struct LaunchCtx {
     // fused key-switch pipeline
     u64 *ks_scratch = nullptr;        // [ks_slots][2][N] digit exchange buffers
     u32 *ks_flags = nullptr;          // [ks_slots] monotonically increasing round counters
+    u32 *ks_ticket = nullptr;         // next ciphertext index (reset per launch)
+    u64 *ks_mail = nullptr;           // [ks_slots] per-group mailbox: (round tag << 32) | ciphertext index
+    u64 *ks_key_s = nullptr;          // [L][2][L][N] Shoup companions of the current switch key
     size_t ks_slots = 0;
     u32 ks_epoch = 0;                 // rounds consumed so far (flag values already used)
+    int ks_occ_cap = 0;               // tuning: cap on resident fused-kernel CTAs per SM (DPFHE_KS_OCC), 0 = no cap
     unsigned long long *ks_prof = nullptr;   // [ks_slots][16] phase cycle counters; non-null selects the profiling build
 };
 

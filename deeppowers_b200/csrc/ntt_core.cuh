@@ -193,14 +193,21 @@ DPFHE_HD void fwd_load_stage(u64 *buf, const Twiddle *__restrict__ tw, const Lim
     constexpr int K = LOGN - 12;
     constexpr int NB = 1 << K;                  // blocks
     constexpr int CPB = (1 << (LOGN - 1)) / NB; // chunks per block
+    U64x2 nxt[NB];   // loads of the next iteration are issued before this iteration's butterflies
+#pragma unroll
+    for (int b = 0; b < NB; ++b) nxt[b] = src(b * CPB + tid);
 #pragma unroll 1
     for (int c = tid; c < CPB; c += NT) {
         u64 x[NB][2];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            U64x2 v = src(b * CPB + c);
+            const U64x2 v = nxt[b];
             x[b][0] = IN_REDUCE ? word_reduce(v.x, p) : v.x;
             x[b][1] = IN_REDUCE ? word_reduce(v.y, p) : v.y;
+        }
+        if (c + NT < CPB) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) nxt[b] = src(b * CPB + c + NT);
         }
         // entry bound is 1 (canonical) or 3 (word-reduced); K <= 2 stages never need a csub
 #pragma unroll

@@ -69,15 +69,18 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
     const unsigned L = e.hp.L;
     G = (G / L) * L;
     if (G == 0) G = L;
-    std::vector<uint64_t *> buf(G), acc0(G), acc1(G);
+    std::vector<uint64_t *> buf(G);
     for (unsigned s = 0; s < G; ++s) {
         buf[s] = aligned_new<uint64_t>(N);
-        acc0[s] = aligned_new<uint64_t>(N);
-        acc1[s] = aligned_new<uint64_t>(N);
     }
     uint64_t *scratch = aligned_new<uint64_t>((size_t)G * 2 * N);
+    // Shoup companions of the key (the device builds them with key_prepare_kernel)
+    const size_t key_words = (size_t)2 * L * L * N;
+    uint64_t *key_s = aligned_new<uint64_t>(key_words);
+    for (size_t k = 0; k < key_words; ++k)
+        key_s[k] = (uint64_t)((((unsigned __int128)key[k]) << 64) / e.lp[(k / N) % L].q);
     KsArgs A;
-    A.a = a; A.b = b; A.key = key; A.out = out; A.scratch = scratch;
+    A.a = a; A.b = b; A.key = key; A.key_s = key_s; A.out = out; A.scratch = scratch;
     A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois;
     HostCta cta{NT};
     const size_t n_work = batch * L;
@@ -86,7 +89,7 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
         for (unsigned s = 0; s < G; ++s) {
             const size_t w = r * G + s;
             if (w >= n_work) break;
-            ks_phase1<LOGN, NT, MODE>(cta, buf[s], acc0[s], acc1[s], A, e.lp[w % L], w / L, (uint32_t)(w % L), scratch + ((size_t)s * 2 + par) * N);
+            ks_phase1<LOGN, NT, MODE>(cta, buf[s], A, e.lp[w % L], w / L, (uint32_t)(w % L), scratch + ((size_t)s * 2 + par) * N);
         }
         for (unsigned s = 0; s < G; ++s) {
             const size_t w = r * G + s;
@@ -95,17 +98,15 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
             for (uint32_t jj = 1; jj < L; ++jj) {
                 const uint32_t j = (i + jj) % L;
                 const unsigned sib = s - i + j;
-                ks_phase2_digit<LOGN, NT>(cta, buf[s], acc0[s], acc1[s], A, e.lp[i], i, j, scratch + ((size_t)sib * 2 + par) * N);
+                ks_phase2_digit<LOGN, NT>(cta, buf[s], A, e.lp[i], w / L, i, j, jj, scratch + ((size_t)sib * 2 + par) * N);
             }
-            ks_finish<LOGN, NT>(cta, acc0[s], acc1[s], A, e.lp[i], w / L, i);
         }
     }
     for (unsigned s = 0; s < G; ++s) {
         free(buf[s]);
-        free(acc0[s]);
-        free(acc1[s]);
     }
     free(scratch);
+    free(key_s);
 }
 }  // namespace
 
@@ -157,7 +158,7 @@ int emu_ks(void *h, int mode, const uint64_t *a, const uint64_t *b, const uint64
     return 0;
     switch (e->hp.log_n) {
         case 12: DISPATCH(12, 256)
-        case 13: DISPATCH(13, 512)
+        case 13: DISPATCH(13, 256)
     }
     return -1;
 }
