@@ -1,0 +1,136 @@
+// deeppowers_fhe.hpp — C++ host API of the encrypted hot path, in the reference's house style.
+//
+// The reference's public header (src/api/cpp/include/deeppowers.hpp:41-87) exposes
+// deeppowers::api::{Model, GenerationConfig, load_model, ...} and has no Ciphertext/Evaluator types
+// (SURVEY.md §0); this header adds them next to it, as namespace deeppowers::api::fhe, following
+// the same conventions:
+//   - errors are C++ exceptions (std::runtime_error), as CUDA_CHECK does in
+//     src/core/hal/cuda/cuda_device.cpp:9-16 — every non-zero status of the C ABI is re-thrown
+//     with dpfhe_last_error() as the message;
+//   - resource-owning classes are non-copyable RAII handles (compare Model's pimpl,
+//     deeppowers.hpp:73-75, and CUDADevice's dtor, cuda_device.cpp:26-41);
+//   - one Evaluator is bound to one device (compare hal::CUDADevice(0), src/api/cpp/src/deeppowers.cpp:15).
+// Header-only over the extern "C" library (include/dpfhe.h, libdpfhe.so); no CUDA headers needed.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dpfhe.h"
+
+namespace deeppowers {
+namespace api {
+namespace fhe {
+
+// Parameters of the ring Z_q[X]/(X^N+1) in RNS form.
+struct EncryptionParameters {
+    unsigned log_n = 13;                   // N = 8192
+    unsigned n_limbs = 4;                  // L
+    std::vector<std::uint64_t> moduli;     // empty: the L largest NTT-friendly primes below 2^60
+};
+
+// Non-owning view of `count` ciphertexts [count][2][L][N] (evaluation form) in host or device memory.
+struct CiphertextBatch {
+    std::uint64_t *data = nullptr;
+    std::size_t count = 0;
+};
+struct ConstCiphertextBatch {
+    const std::uint64_t *data = nullptr;
+    std::size_t count = 0;
+    ConstCiphertextBatch() = default;
+    ConstCiphertextBatch(const std::uint64_t *d, std::size_t c) : data(d), count(c) {}
+    ConstCiphertextBatch(const CiphertextBatch &b) : data(b.data), count(b.count) {}
+};
+
+class Evaluator {
+public:
+    explicit Evaluator(const EncryptionParameters &parms, int device_id = 0) : log_n_(parms.log_n), limbs_(parms.n_limbs) {
+        dpfhe_params p;
+        p.log_n = parms.log_n;
+        p.n_limbs = parms.n_limbs;
+        p.moduli = parms.moduli.empty() ? nullptr : parms.moduli.data();
+        if (!parms.moduli.empty() && parms.moduli.size() != parms.n_limbs)
+            throw std::runtime_error("EncryptionParameters: moduli.size() must equal n_limbs");
+        check(dpfhe_context_create(&p, device_id, &ctx_));
+    }
+    ~Evaluator() { dpfhe_context_destroy(ctx_); }
+    Evaluator(const Evaluator &) = delete;
+    Evaluator &operator=(const Evaluator &) = delete;
+
+    std::size_t poly_degree() const { return std::size_t(1) << log_n_; }
+    unsigned limbs() const { return limbs_; }
+    std::size_t poly_words() const { return poly_degree() * limbs_; }           // [L][N]
+    std::size_t ciphertext_words() const { return 2 * poly_words(); }           // [2][L][N]
+    std::size_t switch_key_words() const { return 2 * limbs_ * poly_words(); }  // [L][2][L][N]
+    std::uint64_t modulus(unsigned limb) const {
+        std::uint64_t q = 0;
+        check(dpfhe_get_modulus(ctx_, limb, &q));
+        return q;
+    }
+    // Galois element of a rotation by `steps` slots: 5^steps mod 2N
+    std::uint64_t galois_element(long steps) const {
+        const std::uint64_t two_n = std::uint64_t(2) << log_n_, half = poly_degree() / 2;
+        std::uint64_t e = ((steps % (long)half) + (long)half) % (long)half, g = 1, b = 5;
+        for (; e; e >>= 1, b = b * b % two_n)
+            if (e & 1) g = g * b % two_n;
+        return g;
+    }
+
+    // ---- host-buffer calls: synchronous; H2D / compute / D2H are pipelined inside the library ----
+    void multiply_relin(ConstCiphertextBatch a, ConstCiphertextBatch b, const std::uint64_t *relin_key, CiphertextBatch out) {
+        same(a.count, b.count, out.count);
+        check(dpfhe_ct_mul_relin_host(ctx_, a.data, b.data, relin_key, out.data, a.count));
+    }
+    void multiply_plain(ConstCiphertextBatch ct, const std::uint64_t *plain_eval, CiphertextBatch out) {
+        same(ct.count, ct.count, out.count);
+        check(dpfhe_ct_mul_plain_host(ctx_, ct.data, plain_eval, out.data, ct.count));
+    }
+    void rotate(ConstCiphertextBatch ct, long steps, const std::uint64_t *galois_key, CiphertextBatch out) {
+        same(ct.count, ct.count, out.count);
+        check(dpfhe_rotate_host(ctx_, ct.data, galois_element(steps), galois_key, out.data, ct.count));
+    }
+    void transform_to_ntt(std::uint64_t *polys, std::size_t n_polys) { check(dpfhe_ntt_fwd_host(ctx_, polys, n_polys)); }
+    void transform_from_ntt(std::uint64_t *polys, std::size_t n_polys) { check(dpfhe_ntt_inv_host(ctx_, polys, n_polys)); }
+
+    // ---- device-pointer calls: asynchronous on `stream` (a cudaStream_t; nullptr = the evaluator's own) ----
+    void multiply_relin_device(const std::uint64_t *a, const std::uint64_t *b, const std::uint64_t *relin_key, std::uint64_t *out,
+                               std::size_t count, void *stream = nullptr) {
+        check(dpfhe_ct_mul_relin(ctx_, a, b, relin_key, out, count, stream));
+    }
+    void multiply_plain_device(const std::uint64_t *ct, const std::uint64_t *plain_eval, std::uint64_t *out, std::size_t count,
+                               void *stream = nullptr) {
+        check(dpfhe_ct_mul_plain(ctx_, ct, plain_eval, out, count, stream));
+    }
+    void rotate_device(const std::uint64_t *ct, long steps, const std::uint64_t *galois_key, std::uint64_t *out, std::size_t count,
+                       void *stream = nullptr) {
+        check(dpfhe_rotate(ctx_, ct, galois_element(steps), galois_key, out, count, stream));
+    }
+    void keyswitch_device(const std::uint64_t *digits, const std::uint64_t *key, std::uint64_t *out, std::size_t count, void *stream = nullptr) {
+        check(dpfhe_keyswitch(ctx_, digits, key, out, count, stream));
+    }
+    void transform_to_ntt_device(std::uint64_t *polys, std::size_t n_polys, void *stream = nullptr) {
+        check(dpfhe_ntt_fwd(ctx_, polys, n_polys, stream));
+    }
+    void transform_from_ntt_device(std::uint64_t *polys, std::size_t n_polys, void *stream = nullptr) {
+        check(dpfhe_ntt_inv(ctx_, polys, n_polys, stream));
+    }
+
+    dpfhe_ctx *native_handle() { return ctx_; }
+
+private:
+    static void check(int status) {
+        if (status != DPFHE_OK) throw std::runtime_error(dpfhe_last_error());
+    }
+    static void same(std::size_t a, std::size_t b, std::size_t c) {
+        if (a != b || a != c) throw std::runtime_error("ciphertext batches must have the same count");
+    }
+    dpfhe_ctx *ctx_ = nullptr;
+    unsigned log_n_, limbs_;
+};
+
+}  // namespace fhe
+}  // namespace api
+}  // namespace deeppowers
