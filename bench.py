@@ -57,11 +57,13 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_for(kernel):
-    """dram bytes per launch from the committed ncu --set full capture, if one is recorded"""
+def traffic_for(kernel, units):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `units` work units, scaled from the committed
+    ncu --set full capture (profiles/traffic.json holds bytes per unit at the profiled batch); None if absent"""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            rec = json.load(f).get(kernel)
+        return float(rec["dram_bytes_per_unit"]) * units if rec else None
     except Exception:
         return None
 
@@ -229,24 +231,25 @@ def main():
         sampler.start()
     n0 = ctx.launch_count()
     total_ms = timed(lambda: ctx.ct_mul_relin(a, b, evk, out, B), args.steps, args.warmup)
-    launches = ctx.launch_count() - n0 - args.warmup
+    # launches inside the timed region only: key_prepare_kernel + ks_fused_kernel per step
+    launches = (ctx.launch_count() - n0) * args.steps // (args.steps + args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
     peak, peak_src = peaks()
     kern_gbs = B * ALGO_BYTES_CT_MUL / (ms_per_step * 1e-3) / 1e9      # per GPU: one launch per step
-    roofline = {"bound": "hbm", "kernel": "ks_fused_kernel<13,512,MUL_RELIN>", "achieved": kern_gbs, "peak": peak,
-                "unit": "GB/s", "frac": kern_gbs / peak, "traffic": traffic_for("ks_fused_kernel_mul_relin"),
+    roofline = {"bound": "hbm", "kernel": "ks_fused_kernel<13,256,3,MUL_RELIN> (persistent cooperative, 3 CTAs/SM)", "achieved": kern_gbs, "peak": peak,
+                "unit": "GB/s", "frac": kern_gbs / peak, "traffic": traffic_for("ks_fused_kernel_mul_relin", B),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B * ALGO_BYTES_CT_MUL,
-                "note": "64-bit modular integer work: the IMAD/ALU pipes bound this kernel below the HBM roofline (DESIGN.md §6)"}
+                "note": "64-bit modular integer work: integer issue (IMAD 2.0, IMAD.WIDE 2.55, IADD3 1.5 clk per warp-instruction per SM sub-partition, no ALU/IMAD overlap: profiles/r01/int_pipes*.txt) bounds this kernel below the HBM roofline; ncu: issue slots 56% busy (DESIGN.md section 6)"}
 
     # standalone NTT on the same data (NTTs/s half of the BASELINE metric)
     ntt_ms = timed(lambda: ctx.ntt_fwd(a, 2 * B), max(3, args.steps // 2), 2) / max(3, args.steps // 2)
     n_ntt = 2 * B * L
     ntt_gbs = n_ntt * ALGO_BYTES_NTT / (ntt_ms * 1e-3) / 1e9
     ntt = {"metric": "ntt_fwd_per_s", "value": world * n_ntt / (ntt_ms * 1e-3), "unit": "NTT/s", "ms_per_step": ntt_ms,
-           "roofline": {"bound": "hbm", "kernel": "ntt_kernel<13,512,fwd>", "achieved": ntt_gbs, "peak": peak, "unit": "GB/s",
-                        "frac": ntt_gbs / peak, "traffic": traffic_for("ntt_kernel_fwd")}}
+           "roofline": {"bound": "hbm", "kernel": "ntt_kernel<13,256,3,fwd> (one CTA per limb, 3 CTAs/SM)", "achieved": ntt_gbs, "peak": peak, "unit": "GB/s",
+                        "frac": ntt_gbs / peak, "traffic": traffic_for("ntt_kernel_fwd", n_ntt)}}
     ctx.fill_uniform(SEED, a, 2 * B, first_poly=first)     # restore `a` (the NTT ran in place)
 
     # end to end through the host-buffer ABI: pinned host memory, H2D + D2H inside the timed region
@@ -278,6 +281,8 @@ def main():
     gather = None
     if world > 1:
         bufs = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        warm = [torch.empty_like(out[:8]) for _ in range(world)] if rank == 0 else None
+        dist.gather(out[:8].contiguous(), warm, dst=0)      # NCCL channel set-up happens on the first call
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()

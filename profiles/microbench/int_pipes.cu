@@ -34,6 +34,52 @@ __global__ void __launch_bounds__(1024) bench(unsigned long long *out, long long
             if (OP == 7) acc[c] = word_reduce(acc[c] * 5 + 1, p);
             if (OP == 8) acc[c] = mulmod_lazy(acc[c], p.wninv + c, p);
         }
+        if (OP == 11) {   // pure 32-bit ALU adds (LOP3-free): 8 independent chains
+#pragma unroll
+            for (int c = 0; c < CH; ++c) asm volatile("add.u32 %0, %0, %1;" : "+r"(r32[c]) : "r"(a));
+        }
+        if (OP == 12) {   // mixed: 4 IMAD chains + 4 IADD chains per iteration, all independent
+#pragma unroll
+            for (int c = 0; c < CH / 2; ++c) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r32[c]) : "r"(a), "r"(b));
+#pragma unroll
+            for (int c = CH / 2; c < CH; ++c) asm volatile("add.u32 %0, %0, %1;" : "+r"(r32[c]) : "r"(a));
+        }
+        if (OP == 13) {   // mixed: 4 IMAD.WIDE chains + 4 x 64-bit add chains
+#pragma unroll
+            for (int c = 0; c < CH / 2; ++c) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b));
+#pragma unroll
+            for (int c = CH / 2; c < CH; ++c) asm volatile("add.u64 %0, %0, %1;" : "+l"(acc[c]) : "l"((unsigned long long)a << 20 | b));
+        }
+        if (OP == 14) {   // LOP3 only
+#pragma unroll
+            for (int c = 0; c < CH; ++c) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r32[c]) : "r"(a), "r"(b));
+        }
+        if (OP == 15) {   // FFMA only (fp32 pipe) for comparison
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { float f = __uint_as_float(r32[c]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0001f), "f"(0.5f)); r32[c] = __float_as_uint(f); }
+        }
+        if (OP == 16) {   // mixed IMAD + FFMA
+#pragma unroll
+            for (int c = 0; c < CH / 2; ++c) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r32[c]) : "r"(a), "r"(b));
+#pragma unroll
+            for (int c = CH / 2; c < CH; ++c) { float f = __uint_as_float(r32[c]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0001f), "f"(0.5f)); r32[c] = __float_as_uint(f); }
+        }
+        if (OP == 17) {   // IMAD with a uniform (kernel-parameter) multiplier: 2 vector-register reads
+#pragma unroll
+            for (int c = 0; c < CH; ++c) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r32[c]) : "r"(a0), "r"(b));
+        }
+        if (OP == 18) {   // IMAD.WIDE reg x uniform + 0-ish: result does not feed itself as addend
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { unsigned long long t; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(r32[c]), "r"(a0)); r32[c] = (unsigned)(t >> 32) ^ (unsigned)t; }
+        }
+        if (OP == 19) {   // IMAD.WIDE reg x reg, no addend
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { unsigned long long t; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(r32[c]), "r"(b)); r32[c] = (unsigned)(t >> 32) ^ (unsigned)t; }
+        }
+        if (OP == 20) {   // shoup_lazy with a uniform twiddle (kernel parameter)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[c] = shoup_lazy(acc[c], p.ninv, p.ninv_s, p.q);
+        }
         if (OP == 9) {
 #pragma unroll
             for (int c = 0; c < CH; c += 2) ct_bfly(acc[c], acc[c + 1], w, p);
@@ -88,7 +134,7 @@ int main() {
     p.mu32 = (unsigned)(((unsigned __int128)1 << 64) / p.q);
     p.ninv = 0x123456789abcdefull % p.q; p.ninv_s = (unsigned long long)(((unsigned __int128)p.ninv << 64) / p.q);
     p.wninv = 0xfedcba987654321ull % p.q; p.wninv_s = 0;
-    for (int threads : {256, 512, 1024}) {
+    for (int threads : {1024}) {
         run<0>("mad.wide.u32 (IMAD.WIDE)", CH, p, threads);
         run<1>("mad.lo.u32 (IMAD)", CH, p, threads);
         run<2>("mad.hi.u32 (IMAD.HI)", CH, p, threads);
@@ -100,6 +146,16 @@ int main() {
         run<8>("mulmod_lazy (128b product+Barrett)", CH, p, threads);
         run<9>("ct_bfly (+1 LOP3/elt)", CH / 2, p, threads);
         run<10>("gs_bfly", CH / 2, p, threads);
+        run<17>("IMAD reg*uniform+reg", CH, p, threads);
+        run<18>("IMAD.WIDE reg*uniform (+LOP)", CH, p, threads);
+        run<19>("IMAD.WIDE reg*reg (+LOP)", CH, p, threads);
+        run<20>("shoup_lazy, uniform twiddle", CH, p, threads);
+        run<11>("add.u32 (IADD3) x8", CH, p, threads);
+        run<12>("4 IMAD + 4 IADD3 mixed", CH, p, threads);
+        run<13>("4 IMAD.WIDE + 4 add.u64 mixed", CH, p, threads);
+        run<14>("lop3 x8", CH, p, threads);
+        run<15>("FFMA x8", CH, p, threads);
+        run<16>("4 IMAD + 4 FFMA mixed", CH, p, threads);
         printf("\n");
     }
     return 0;
