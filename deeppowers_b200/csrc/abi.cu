@@ -336,7 +336,6 @@ static int ks_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const uint64_t
     if (batch == 0) return DPFHE_OK;
     CHECK_PTR(a); CHECK_PTR(key); CHECK_PTR(out);
     if (mode == KS_MUL_RELIN) CHECK_PTR(b);
-    if (ctx->hp.log_n > 13) return fail(DPFHE_ERR_INVALID, "key switching supports log_n <= 13 in this build (log_n = %u)", ctx->hp.log_n);
     if (mode == KS_ROTATE) {
         const uint64_t two_n = (uint64_t)2 << ctx->hp.log_n;
         if (!(galois & 1) || galois >= two_n) return fail(DPFHE_ERR_INVALID, "galois element must be odd and < 2N");
@@ -494,7 +493,7 @@ int dpfhe_describe(const dpfhe_ctx *ctx, char *buf, size_t buf_len) {
                      "{\"log_n\": %u, \"n_limbs\": %u, \"num_sms\": %d, \"ntt_kernel\": {\"threads\": %u, \"smem_bytes\": %zu, "
                      "\"grid\": \"one CTA per limb\"}, \"ks_fused_kernel\": {\"threads\": %u, \"smem_bytes\": %zu, "
                      "\"grid\": \"persistent cooperative, multiple of L, <= %zu slots\"}}",
-                     ctx->hp.log_n, ctx->hp.L, ctx->lc.num_sms, nt, ctx->N() * 8, 256u, ctx->N() * 8, ctx->lc.ks_slots);
+                     ctx->hp.log_n, ctx->hp.L, ctx->lc.num_sms, nt, ctx->N() * 8, ctx->hp.log_n <= 13 ? 256u : 512u, ctx->N() * 8, ctx->lc.ks_slots);
     return n;
 }
 

@@ -281,7 +281,8 @@ cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inve
 
 template <int LOGN, int MODE>
 static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cudaStream_t st) {
-    constexpr int NT = 256, MINB = 3;   // one limb of shared memory per CTA -> three CTAs per SM
+    // one limb of shared memory per CTA: 64 KiB (N <= 8192) -> three CTAs per SM; 128 KiB (N = 16384) -> one
+    constexpr int NT = LOGN <= 13 ? 256 : 512, MINB = LOGN <= 13 ? 3 : 1;
     auto kern = lc.ks_prof ? ks_fused_kernel<LOGN, NT, MINB, MODE, true> : ks_fused_kernel<LOGN, NT, MINB, MODE, false>;
     const size_t smem = Geometry<LOGN>::LIMB_BYTES;
     static bool configured[2][64] = {};
@@ -327,7 +328,8 @@ cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const
         const size_t n = (size_t)2 * lc.L * lc.L << lc.log_n;
         const unsigned grid = ew_grid(lc, n);
         if (lc.log_n == 12) key_prepare_kernel<12><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
-        else key_prepare_kernel<13><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        else if (lc.log_n == 13) key_prepare_kernel<13><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        else key_prepare_kernel<14><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -344,6 +346,7 @@ cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const
     switch (lc.log_n) {
         case 12: KS_DISPATCH(12)
         case 13: KS_DISPATCH(13)
+        case 14: KS_DISPATCH(14)
     }
     return cudaErrorNotSupported;
 }

@@ -120,7 +120,7 @@ def test_pointwise_and_tensor_and_plain(ctxs, log_n, L):
     assert np.array_equal(host(out).reshape(a.shape), o.ct_mul_plain(a, pt))
 
 
-@pytest.mark.parametrize("log_n,L,batch", [(12, 2, 1), (12, 3, 5), (13, 4, 3), (13, 1, 2), (13, 4, 41)])
+@pytest.mark.parametrize("log_n,L,batch", [(12, 2, 1), (12, 3, 5), (13, 4, 3), (13, 1, 2), (13, 4, 41), (14, 2, 3), (14, 8, 2), (12, 9, 3)])
 def test_ct_mul_relin(ctxs, log_n, L, batch):
     c, o = ctxs(log_n, L)
     s = o.keygen_secret(21)
@@ -134,7 +134,7 @@ def test_ct_mul_relin(ctxs, log_n, L, batch):
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("log_n,L,batch", [(12, 3, 4), (13, 4, 5)])
+@pytest.mark.parametrize("log_n,L,batch", [(12, 3, 4), (13, 4, 5), (14, 8, 2)])
 def test_keyswitch_and_rotate(ctxs, log_n, L, batch):
     c, o = ctxs(log_n, L)
     s = o.keygen_secret(31)

@@ -59,7 +59,7 @@ def test_emulated_ntt_bodies(make_emu, oracle_mod, log_n, L, n_polys):
     assert np.array_equal(e.ntt(y, inverse=True), x)
 
 
-@pytest.mark.parametrize("log_n,L,batch,G", [(12, 2, 3, 2), (12, 3, 4, 9), (13, 4, 2, 8), (12, 1, 2, 1)])
+@pytest.mark.parametrize("log_n,L,batch,G", [(12, 2, 3, 2), (12, 3, 4, 9), (13, 4, 2, 8), (12, 1, 2, 1), (14, 2, 2, 4), (12, 9, 2, 9)])
 def test_emulated_fused_keyswitch_bodies(make_emu, oracle_mod, log_n, L, batch, G):
     e, o = make_emu(log_n, L), oracle_mod.Oracle(log_n, L)
     s = o.keygen_secret(1)
