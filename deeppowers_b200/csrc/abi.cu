@@ -319,6 +319,16 @@ int dpfhe_poly_mul_pointwise(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t
     return DPFHE_OK;
 }
 
+int dpfhe_poly_add(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, size_t n_polys, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (n_polys == 0) return DPFHE_OK;
+    CHECK_PTR(d_a); CHECK_PTR(d_b); CHECK_PTR(d_out);
+    CU_TRY(launch_poly_add(ctx->lc, d_a, d_b, d_out, n_polys, pick(ctx, stream)));
+    ctx->launches++;
+    return DPFHE_OK;
+}
+
 int dpfhe_ct_tensor(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_d, size_t batch, void *stream) {
     int rc = enter(ctx);
     if (rc) return rc;

@@ -159,6 +159,21 @@ __global__ void __launch_bounds__(256) pointwise_mul_kernel(const U64x2 *__restr
     }
 }
 
+// out = a + b mod q (canonical operands); out may alias either input
+template <int LOGN>
+__global__ void __launch_bounds__(256) poly_add_kernel(const U64x2 *__restrict__ a, const U64x2 *__restrict__ b, U64x2 *__restrict__ out,
+                                                       const LimbParams *__restrict__ lps, u32 L, size_t n_chunks) {
+    constexpr size_t NC = (size_t)1 << (LOGN - 1);
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += (size_t)gridDim.x * blockDim.x) {
+        const u64 q = lps[(c / NC) % L].q;
+        const U64x2 x = ld_stream(a + c), y = ld_stream(b + c);
+        U64x2 r;
+        r.x = csub(x.x + y.x, q);
+        r.y = csub(x.y + y.y, q);
+        st_stream(out + c, r);
+    }
+}
+
 // ct [batch][2][L][N] x pt [L][N]
 template <int LOGN>
 __global__ void __launch_bounds__(256) ct_mul_plain_kernel(const U64x2 *__restrict__ ct, const U64x2 *__restrict__ pt,
@@ -368,6 +383,18 @@ cudaError_t launch_pointwise_mul(const LaunchCtx &lc, const u64 *a, const u64 *b
     LOGN_SWITCH((pointwise_mul_kernel<12><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
                 (pointwise_mul_kernel<13><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
                 (pointwise_mul_kernel<14><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)))
+    return cudaGetLastError();
+}
+
+cudaError_t launch_poly_add(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *out, size_t n_polys, cudaStream_t st) {
+    const size_t n_chunks = n_polys * lc.L * ((size_t)1 << (lc.log_n - 1));
+    if (!n_chunks) return cudaSuccess;
+    const unsigned grid = ew_grid(lc, n_chunks);
+    auto A = reinterpret_cast<const U64x2 *>(a), B = reinterpret_cast<const U64x2 *>(b);
+    auto O = reinterpret_cast<U64x2 *>(out);
+    LOGN_SWITCH((poly_add_kernel<12><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
+                (poly_add_kernel<13><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
+                (poly_add_kernel<14><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)))
     return cudaGetLastError();
 }
 

@@ -124,6 +124,9 @@ class Context:
     def poly_mul_pointwise(self, a, b, out, n_polys, stream=None):
         self._chk(self._l.dpfhe_poly_mul_pointwise(self._h, _ptr(a), _ptr(b), _ptr(out), n_polys, _stream(stream)))
 
+    def poly_add(self, a, b, out, n_polys, stream=None):
+        self._chk(self._l.dpfhe_poly_add(self._h, _ptr(a), _ptr(b), _ptr(out), n_polys, _stream(stream)))
+
     def ct_tensor(self, a, b, d, batch, stream=None):
         self._chk(self._l.dpfhe_ct_tensor(self._h, _ptr(a), _ptr(b), _ptr(d), batch, _stream(stream)))
 

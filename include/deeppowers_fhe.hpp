@@ -108,6 +108,9 @@ public:
                        void *stream = nullptr) {
         check(dpfhe_rotate(ctx_, ct, galois_element(steps), galois_key, out, count, stream));
     }
+    void add_device(const std::uint64_t *a, const std::uint64_t *b, std::uint64_t *out, std::size_t count, void *stream = nullptr) {
+        check(dpfhe_poly_add(ctx_, a, b, out, 2 * count, stream));   // a ciphertext is two polynomials
+    }
     void keyswitch_device(const std::uint64_t *digits, const std::uint64_t *key, std::uint64_t *out, std::size_t count, void *stream = nullptr) {
         check(dpfhe_keyswitch(ctx_, digits, key, out, count, stream));
     }

@@ -85,6 +85,9 @@ int dpfhe_ntt_inv(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream
 /* out[p][l][n] = a*b mod q_l, [n_polys][L][N]; out may alias a or b */
 int dpfhe_poly_mul_pointwise(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out,
                              size_t n_polys, void *stream);
+/* out = a + b mod q_l, [n_polys][L][N] (a ciphertext is two polynomials); out may alias a or b */
+int dpfhe_poly_add(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out,
+                   size_t n_polys, void *stream);
 /* a,b: [batch][2][L][N] -> d: [batch][3][L][N] (d0,d1,d2) */
 int dpfhe_ct_tensor(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_d,
                     size_t batch, void *stream);

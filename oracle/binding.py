@@ -48,6 +48,7 @@ def lib():
         "dpo_ntt_fwd_limb_slow": (None, [vp, u32, u64p]),
         "dpo_negacyclic_schoolbook": (None, [vp, u32, u64p, u64p, u64p]),
         "dpo_poly_mul_pointwise": (None, [vp, u64p, u64p, u64p, sz]),
+        "dpo_poly_add": (None, [vp, u64p, u64p, u64p, sz]),
         "dpo_ct_tensor": (None, [vp, u64p, u64p, u64p, sz]),
         "dpo_keyswitch": (None, [vp, u64p, u64p, u64p, u64p]),
         "dpo_ct_mul_relin": (None, [vp, u64p, u64p, u64p, u64p, sz]),
@@ -130,6 +131,12 @@ class Oracle:
         a = np.ascontiguousarray(a, dtype=np.uint64)
         out = np.empty_like(a)
         self._l.dpo_poly_mul_pointwise(self._c, a.reshape(-1), np.ascontiguousarray(b).reshape(-1), out.reshape(-1), a.size // self.P)
+        return out
+
+    def poly_add(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        self._l.dpo_poly_add(self._c, a.reshape(-1), np.ascontiguousarray(b).reshape(-1), out.reshape(-1), a.size // self.P)
         return out
 
     def ct_tensor(self, a, b):

@@ -306,6 +306,17 @@ void dpo_poly_mul_pointwise(const dpo_ctx *c, const uint64_t *a, const uint64_t 
     }
 }
 
+/* DESIGN.md §2.4 poly_add */
+void dpo_poly_add(const dpo_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n_polys) {
+    long total = (long)(n_polys * c->L);
+#pragma omp parallel for schedule(static)
+    for (long k = 0; k < total; k++) {
+        uint64_t q = c->q[k % c->L];
+        size_t off = (size_t)k * c->N;
+        for (size_t j = 0; j < c->N; j++) out[off + j] = addmod(a[off + j], b[off + j], q);
+    }
+}
+
 /* DESIGN.md §2.4 ct_tensor: d0 = a0*b0, d1 = a0*b1 + a1*b0, d2 = a1*b1 (pointwise, per limb). */
 static void ct_tensor_one(const dpo_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *d) {
     size_t P = c->L * c->N;

@@ -67,6 +67,7 @@ void dpo_negacyclic_schoolbook(const dpo_ctx *, unsigned limb, const uint64_t *a
 /* ---- evaluator ops (evaluation form) ---- */
 void dpo_poly_mul_pointwise(const dpo_ctx *, const uint64_t *a, const uint64_t *b,
                             uint64_t *out, size_t n_polys);
+void dpo_poly_add(const dpo_ctx *, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n_polys);
 /* a,b: [batch][2][L][N] -> d: [batch][3][L][N] */
 void dpo_ct_tensor(const dpo_ctx *, const uint64_t *a, const uint64_t *b, uint64_t *d, size_t batch);
 /* d: [L][N] eval form; key [L][2][L][N]; out c0,c1: [L][N] each (overwritten) */

@@ -1,0 +1,89 @@
+"""BASELINE.json config 4 as a parity/semantics case: an encrypted 768x768 int8 linear layer (the GPT-2-small
+projection shape, reference src/core/execution/model.hpp:47, gpt_weights.cpp:187-190; symmetric int8 range
+per quantization_manager.cpp:272-276) evaluated with the diagonal method on top of the hot-path ops
+ct_mul_plain + rotate + add, N=8192, L=4.  Decrypting the GPU result must give W @ x exactly."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from slots import SlotEncoder  # noqa: E402
+
+T_PLAIN = 167772161      # 5 * 2^25 + 1, prime, = 1 mod 2N, > 2 * 768 * 127 * 127
+DIM = 768
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def to_rns_eval(o, coeffs_mod_t):
+    """centred lift of a plaintext polynomial to every limb, then forward NTT (oracle) -> [L][N]"""
+    c = coeffs_mod_t.astype(np.int64)
+    c = np.where(c > T_PLAIN // 2, c - T_PLAIN, c)
+    limbs = np.stack([(c % q).astype(np.uint64) for q in o.moduli])
+    return o.ntt_fwd(limbs[None])[0]
+
+
+def test_encrypted_linear_layer_768(oracle_mod):
+    import deeppowers_b200 as dp
+    log_n, L, B = 13, 4, 2
+    o = oracle_mod.Oracle(log_n, L)
+    ctx = dp.Context(log_n, L)
+    N = o.N
+    enc = SlotEncoder(N, T_PLAIN)
+    rng = np.random.default_rng(0xD3390004)
+    W = rng.integers(-127, 128, (DIM, DIM))
+    X = rng.integers(-127, 128, (B, DIM))
+    g = o.galois_elt(1)   # rotate every row of slots left by one (tests/test_slots_cpu.py pins that meaning)
+    s = o.keygen_secret(1)
+    gk = o.keygen_galois(2, T_PLAIN, s, g)
+    # inputs: x duplicated so that slot i+d holds x[(i+d) mod 768] for i, d < 768
+    cts = []
+    for b in range(B):
+        slots = np.zeros((2, N // 2), dtype=np.int64)
+        slots[0, :DIM] = X[b]
+        slots[0, DIM:2 * DIM] = X[b]
+        cts.append(o.encrypt(10 + b, T_PLAIN, s, enc.encode(slots)))
+    ct = np.stack(cts)
+    assert np.array_equal(enc.decode(o.decrypt(s, ct[0], T_PLAIN))[0, :DIM].astype(np.int64), X[0] % T_PLAIN)
+    # weight diagonals, pre-NTT'd plaintexts (768 x 256 KiB = 192 MiB)
+    diag = torch.empty((DIM, L, N), dtype=torch.int64, device="cuda")
+    ar = np.arange(DIM)
+    for d in range(DIM):
+        slots = np.zeros((2, N // 2), dtype=np.int64)
+        slots[0, :DIM] = W[ar, (ar + d) % DIM]
+        diag[d] = dev(to_rns_eval(o, enc.encode(slots)))
+    d_gk = dev(gk)
+    cur, nxt = dev(ct), torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda")
+    acc, tmp = torch.empty_like(nxt), torch.empty_like(nxt)
+    ctx.ct_mul_plain(cur, diag[0], acc, B)
+    first_steps = {}
+    for d in range(1, DIM):
+        ctx.rotate(cur, g, d_gk, nxt, B)
+        cur, nxt = nxt, cur
+        ctx.ct_mul_plain(cur, diag[d], tmp, B)
+        ctx.poly_add(acc, tmp, acc, 2 * B)
+        if d <= 2:
+            first_steps[d] = (host(cur).reshape(B, 2, L, N).copy(), host(acc).reshape(B, 2, L, N).copy())
+    torch.cuda.synchronize()
+    # (1) bit-exact against the oracle running the same first steps
+    r = ct
+    a = o.ct_mul_plain(ct, host(diag[0]).reshape(L, N))
+    for d in (1, 2):
+        r = o.rotate(r, g, gk)
+        a = o.poly_add(a, o.ct_mul_plain(r, host(diag[d]).reshape(L, N)))
+        assert np.array_equal(first_steps[d][0], r)
+        assert np.array_equal(first_steps[d][1], a)
+    # (2) semantics of the whole chain: Dec(result) slots == W @ x
+    res = host(acc).reshape(B, 2, L, N)
+    for b in range(B):
+        y = enc.decode(o.decrypt(s, res[b], T_PLAIN))[0, :DIM].astype(np.int64)
+        y = np.where(y > T_PLAIN // 2, y - T_PLAIN, y)
+        assert np.array_equal(y, W @ X[b])
+    ctx.close()

@@ -1,0 +1,89 @@
+"""Throughput of the other BASELINE.json configs (parity-test shapes, not the driver's bench line):
+  cfg3  key-switch rotation sweep, N=16384, L=8, batch=1024, k in {+-2^0..+-2^12} (index-outer, batch-inner)
+  cfg4  encrypted 768x768 linear layer, N=8192, L=4, batch=512: 768 ct x pt + 767 rotations + 767 adds per batch
+Kernel-only CUDA-event timings on synthetic residues; writes one JSON object."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import deeppowers_b200 as dp
+
+PEAK = 6564.8
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, iters):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def cfg3():
+    log_n, L, B = 14, 8, 1024
+    c = dp.Context(log_n, L)
+    N = 1 << log_n
+    ct = torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda")
+    out = torch.empty_like(ct)
+    c.fill_uniform(0xD3390003, ct, 2 * B)
+    ks = [s * (1 << e) for e in range(13) for s in (1, -1)]
+    keys = torch.empty((len(ks), L, 2, L, N), dtype=torch.int64, device="cuda")     # 26 x 16 MiB
+    c.fill_uniform(0xD3390103, keys, len(ks) * 2 * L)
+
+    def sweep():
+        for i, k in enumerate(ks):
+            c.rotate(ct, c.galois_elt(k), keys[i], out, B)
+
+    ms = timed(sweep, 2)
+    n = len(ks) * B
+    P = L * N * 8
+    c.close()
+    return {"config": "cfg3 rotation sweep N=16384 L=8 batch=1024 x 26 indices", "ms_per_sweep": ms, "rotations_per_s": n / ms * 1e3,
+            "roofline": {"bound": "hbm", "achieved": n * 4 * P / ms / 1e6, "peak": PEAK, "unit": "GB/s", "frac": n * 4 * P / ms / 1e6 / PEAK,
+                         "algorithmic_bytes_per_rotation": 4 * P}}
+
+
+def cfg4():
+    log_n, L, B, DIM = 13, 4, 512, 768
+    c = dp.Context(log_n, L)
+    N = 1 << log_n
+    cur = torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda")
+    nxt, acc, tmp = torch.empty_like(cur), torch.empty_like(cur), torch.empty_like(cur)
+    c.fill_uniform(0xD3390004, cur, 2 * B)
+    diag = torch.empty((DIM, L, N), dtype=torch.int64, device="cuda")
+    c.fill_uniform(0xD3390104, diag, DIM)
+    gk = torch.empty((L, 2, L, N), dtype=torch.int64, device="cuda")
+    c.fill_uniform(0xD3390204, gk, 2 * L)
+    g = c.galois_elt(1)
+    P = L * N * 8
+    t_pt = timed(lambda: c.ct_mul_plain(cur, diag[1], tmp, B), 20)
+    t_rot = timed(lambda: c.rotate(cur, g, gk, nxt, B), 5)
+    t_add = timed(lambda: c.poly_add(acc, tmp, acc, 2 * B), 20)
+
+    def layer():
+        a, b = cur, nxt
+        c.ct_mul_plain(a, diag[0], acc, B)
+        for d in range(1, DIM):
+            c.rotate(a, g, gk, b, B)
+            a, b = b, a
+            c.ct_mul_plain(a, diag[d], tmp, B)
+            c.poly_add(acc, tmp, acc, 2 * B)
+
+    ms = timed(layer, 1)
+    c.close()
+    return {"config": "cfg4 encrypted 768x768 linear layer N=8192 L=4 batch=512 (diagonal method, one Galois key)",
+            "ms_per_layer_batch": ms, "prompts_per_s": B / ms * 1e3,
+            "ct_mul_plain": {"per_s": B / t_pt * 1e3, "GBps": B * 4 * P / t_pt / 1e6, "frac_hbm": B * 4 * P / t_pt / 1e6 / PEAK},
+            "rotate": {"per_s": B / t_rot * 1e3, "GBps": B * 4 * P / t_rot / 1e6, "frac_hbm": B * 4 * P / t_rot / 1e6 / PEAK},
+            "ct_add": {"per_s": B / t_add * 1e3, "GBps": B * 6 * P / t_add / 1e6, "frac_hbm": B * 6 * P / t_add / 1e6 / PEAK}}
+
+
+if __name__ == "__main__":
+    print(json.dumps({"cfg3": cfg3(), "cfg4": cfg4()}, indent=1))
