@@ -1,0 +1,38 @@
+"""Python mirror of include/dpfhe_wire.hpp (flat DPFHEv1 files: 160-byte header + raw u64 payload)."""
+import struct
+
+import numpy as np
+
+MAGIC = b"DPFHEv1\x00"
+CIPHERTEXTS, SWITCH_KEY, PLAINTEXTS = 1, 2, 3
+_HDR = struct.Struct("<8sIIIIQ16Q")
+
+
+def payload_words(log_n, n_limbs, kind, count):
+    poly = (1 << log_n) * n_limbs
+    return {CIPHERTEXTS: count * 2 * poly, SWITCH_KEY: 2 * n_limbs * poly, PLAINTEXTS: count * poly}[kind]
+
+
+def write(path, log_n, n_limbs, kind, count, moduli, payload, form=1):
+    payload = np.ascontiguousarray(payload, dtype="<u8").reshape(-1)
+    if payload.size != payload_words(log_n, n_limbs, kind, count):
+        raise ValueError("payload size does not match the header")
+    mods = list(int(m) for m in moduli) + [0] * (16 - len(moduli))
+    with open(path, "wb") as f:
+        f.write(_HDR.pack(MAGIC, log_n, n_limbs, kind, form, count, *mods))
+        f.write(payload.tobytes())
+
+
+def read(path):
+    with open(path, "rb") as f:
+        raw = f.read(_HDR.size)
+        if len(raw) != _HDR.size:
+            raise ValueError("truncated header")
+        magic, log_n, n_limbs, kind, form, count, *mods = _HDR.unpack(raw)
+        if magic != MAGIC:
+            raise ValueError("not a DPFHEv1 file")
+        words = payload_words(log_n, n_limbs, kind, count)
+        data = np.frombuffer(f.read(words * 8), dtype="<u8")
+        if data.size != words:
+            raise ValueError("truncated payload")
+    return {"log_n": log_n, "n_limbs": n_limbs, "kind": kind, "form": form, "count": count, "moduli": mods[:n_limbs]}, data.astype(np.uint64)

@@ -1,0 +1,94 @@
+// dpfhe_wire.hpp — flat wire / disk format for ciphertexts, plaintexts and switch keys.
+//
+// The reference has no ciphertext format of its own: its demo exchanges opaque Concrete blobs through temp
+// files (demo/fhe_server.py:126-130) and its only binary format is the rank/dims/raw-bytes weight file of
+// GPTWeights (src/core/execution/models/gpt_weights.cpp:40-55).  This format follows the latter's spirit:
+// a fixed little-endian header, then the raw u64 payload exactly as the C ABI consumes it.
+//
+//   offset  size  field
+//   0       8     magic "DPFHEv1\0"
+//   8       4     log_n
+//   12      4     n_limbs (L)
+//   16      4     kind: 1 = ciphertext batch [count][2][L][N], 2 = switch key [L][2][L][N] (count = 1),
+//                       3 = plaintext [count][L][N]
+//   20      4     form: 1 = evaluation (NTT, bit-reversed order), 0 = coefficient
+//   24      8     count
+//   32      128   moduli[16] (unused entries 0)
+//   160     ...   payload, u64 little-endian
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace deeppowers {
+namespace api {
+namespace fhe {
+
+enum class WireKind : std::uint32_t { Ciphertexts = 1, SwitchKey = 2, Plaintexts = 3 };
+
+struct WireHeader {
+    char magic[8];
+    std::uint32_t log_n, n_limbs, kind, form;
+    std::uint64_t count;
+    std::uint64_t moduli[16];
+};
+static_assert(sizeof(WireHeader) == 160, "wire header must be 160 bytes");
+
+inline std::size_t wire_payload_words(const WireHeader &h) {
+    const std::size_t poly = (std::size_t(1) << h.log_n) * h.n_limbs;
+    switch (static_cast<WireKind>(h.kind)) {
+        case WireKind::Ciphertexts: return h.count * 2 * poly;
+        case WireKind::SwitchKey: return std::size_t(2) * h.n_limbs * poly;
+        case WireKind::Plaintexts: return h.count * poly;
+    }
+    throw std::runtime_error("dpfhe wire: unknown kind");
+}
+
+inline WireHeader make_wire_header(unsigned log_n, unsigned n_limbs, WireKind kind, std::uint64_t count, const std::uint64_t *moduli) {
+    WireHeader h;
+    std::memset(&h, 0, sizeof(h));
+    std::memcpy(h.magic, "DPFHEv1", 8);
+    h.log_n = log_n;
+    h.n_limbs = n_limbs;
+    h.kind = static_cast<std::uint32_t>(kind);
+    h.form = 1;
+    h.count = count;
+    for (unsigned l = 0; l < n_limbs && l < 16; ++l) h.moduli[l] = moduli[l];
+    return h;
+}
+
+inline void write_wire_file(const std::string &path, const WireHeader &h, const std::uint64_t *payload) {
+    std::FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("dpfhe wire: cannot open " + path + " for writing");
+    const std::size_t words = wire_payload_words(h);
+    const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(payload, 8, words, f) == words;
+    std::fclose(f);
+    if (!ok) throw std::runtime_error("dpfhe wire: short write to " + path);
+}
+
+inline WireHeader read_wire_file(const std::string &path, std::vector<std::uint64_t> &payload) {
+    std::FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("dpfhe wire: cannot open " + path);
+    WireHeader h;
+    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "DPFHEv1", 8) != 0) {
+        std::fclose(f);
+        throw std::runtime_error("dpfhe wire: " + path + " is not a DPFHEv1 file");
+    }
+    if (h.log_n < 1 || h.log_n > 17 || h.n_limbs < 1 || h.n_limbs > 16) {
+        std::fclose(f);
+        throw std::runtime_error("dpfhe wire: bad parameters in " + path);
+    }
+    payload.resize(wire_payload_words(h));
+    const bool ok = std::fread(payload.data(), 8, payload.size(), f) == payload.size();
+    std::fclose(f);
+    if (!ok) throw std::runtime_error("dpfhe wire: truncated payload in " + path);
+    return h;
+}
+
+}  // namespace fhe
+}  // namespace api
+}  // namespace deeppowers
