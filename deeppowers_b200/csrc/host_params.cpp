@@ -129,6 +129,7 @@ std::string build_host_params(unsigned log_n, unsigned L, const uint64_t *moduli
         lp.q2 = 2 * q;
         lp.q4 = 4 * q;
         lp.q8 = 8 * q;
+        lp.nq = 0 - q;
         unsigned bits = 64 - (unsigned)__builtin_clzll(q);
         lp.bar_shift = bits - 2;
         lp.bar_mu = (uint64_t)(((u128)1 << (lp.bar_shift + 64)) / q);

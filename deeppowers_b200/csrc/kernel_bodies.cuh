@@ -224,10 +224,10 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
             // digit enters the inverse transform in [0,2q)
             reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = d;
             U64x2 r0, r1;   // s < 3q, Shoup term < 2q  ->  accumulator starts below 5q
-            r0.x = s0.x + shoup_lazy(d.x, o.kb.x, o.kbs.x, p.q);
-            r0.y = s0.y + shoup_lazy(d.y, o.kb.y, o.kbs.y, p.q);
-            r1.x = s1.x + shoup_lazy(d.x, o.ka.x, o.kas.x, p.q);
-            r1.y = s1.y + shoup_lazy(d.y, o.ka.y, o.kas.y, p.q);
+            r0.x = s0.x + shoup_lazy(d.x, o.kb.x, o.kbs.x, p);
+            r0.y = s0.y + shoup_lazy(d.y, o.kb.y, o.kbs.y, p);
+            r1.x = s1.x + shoup_lazy(d.x, o.ka.x, o.kas.x, p);
+            r1.y = s1.y + shoup_lazy(d.y, o.ka.y, o.kas.y, p);
             if (only) {
                 r0.x = canon(r0.x, p); r0.y = canon(r0.y, p);
                 r1.x = canon(r1.x, p); r1.y = canon(r1.y, p);
@@ -283,10 +283,10 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
             }
             // u < 16q straight from the transform: Shoup multiplication accepts any 64-bit operand
             const U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)];
-            r0.x += shoup_lazy(u.x, vb.x, vbs.x, p.q);
-            r0.y += shoup_lazy(u.y, vb.y, vbs.y, p.q);
-            r1.x += shoup_lazy(u.x, va.x, vas.x, p.q);
-            r1.y += shoup_lazy(u.y, va.y, vas.y, p.q);
+            r0.x += shoup_lazy(u.x, vb.x, vbs.x, p);
+            r0.y += shoup_lazy(u.y, vb.y, vbs.y, p);
+            r1.x += shoup_lazy(u.x, va.x, vas.x, p);
+            r1.y += shoup_lazy(u.y, va.y, vas.y, p);
             if (trim) {
                 r0.x = csub(r0.x, p.q8); r0.y = csub(r0.y, p.q8);
                 r1.x = csub(r1.x, p.q8); r1.y = csub(r1.y, p.q8);

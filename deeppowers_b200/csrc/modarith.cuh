@@ -32,6 +32,7 @@ struct alignas(16) LimbParams {
     u64 q2;          // 2q
     u64 q4;          // 4q
     u64 q8;          // 8q  (< 2^63)
+    u64 nq;          // 2^64 - q: adding h*nq subtracts h*q without a separate negation
     u64 bar_mu;      // floor(2^(bar_shift+64) / q)
     u64 ninv;        // N^-1 mod q                    } folded into the last inverse stage
     u64 ninv_s;      // Shoup companion of ninv
@@ -70,17 +71,71 @@ DPFHE_HD u64 csub(u64 x, u64 m) {
 #endif
 }
 
-// Shoup multiplication by a fixed w < q with ws = floor(w * 2^64 / q): valid for ANY 64-bit x.
-DPFHE_HD u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {
-    u64 h = umulhi64(x, ws);
-    return x * w - h * q;   // in [0, 2q)
+// c + a*b mod 2^64 as ONE multiply-add chain (IMAD.WIDE + 2 IMAD, no separate adds)
+DPFHE_HD u64 mad_lo64(u64 a, u64 b, u64 c) {
+#if defined(__CUDA_ARCH__)
+    u64 t;
+    asm("{\n\t"
+        ".reg .u32 al, ah, bl, bh, t0, t1;\n\t"
+        ".reg .u64 T;\n\t"
+        "mov.b64 {al, ah}, %1;\n\t"
+        "mov.b64 {bl, bh}, %2;\n\t"
+        "mad.wide.u32 T, al, bl, %3;\n\t"
+        "mov.b64 {t0, t1}, T;\n\t"
+        "mad.lo.u32 t1, al, bh, t1;\n\t"
+        "mad.lo.u32 t1, ah, bl, t1;\n\t"
+        "mov.b64 %0, {t0, t1};\n\t"
+        "}"
+        : "=l"(t)
+        : "l"(a), "l"(b), "l"(c));
+    return t;
+#else
+    return c + a * b;
+#endif
 }
 
+// Shoup multiplication by a fixed w < q with ws = floor(w * 2^64 / q): valid for ANY 64-bit x.
+// r = x*w - floor(x*ws / 2^64) * q  (mod 2^64), r in [0, 2q).
+// Device form: the quotient uses ptxas' own mul.hi.u64 expansion (4 IMAD.WIDE with carry predicates); the
+// low 64 bits are one explicit chain t = xl*wl + hl*nql (2 IMAD.WIDE), t.hi += xl*wh + xh*wl + hl*nqh + hh*nql
+// (4 IMAD) with nq = 2^64 - q, which avoids the negation and the split adds nvcc otherwise emits.
+DPFHE_HD u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 q, u64 nq) {
+#if defined(__CUDA_ARCH__)
+    const u64 h = __umul64hi(x, ws);
+    u64 t;
+    asm("{\n\t"
+        ".reg .u32 xl, xh, wl, wh, hl, hh, nl, nh, t0, t1;\n\t"
+        ".reg .u64 T;\n\t"
+        "mov.b64 {xl, xh}, %1;\n\t"
+        "mov.b64 {wl, wh}, %2;\n\t"
+        "mov.b64 {hl, hh}, %3;\n\t"
+        "mov.b64 {nl, nh}, %4;\n\t"
+        "mul.wide.u32 T, xl, wl;\n\t"
+        "mad.wide.u32 T, hl, nl, T;\n\t"
+        "mov.b64 {t0, t1}, T;\n\t"
+        "mad.lo.u32 t1, xl, wh, t1;\n\t"
+        "mad.lo.u32 t1, xh, wl, t1;\n\t"
+        "mad.lo.u32 t1, hl, nh, t1;\n\t"
+        "mad.lo.u32 t1, hh, nl, t1;\n\t"
+        "mov.b64 %0, {t0, t1};\n\t"
+        "}"
+        : "=l"(t)
+        : "l"(x), "l"(w), "l"(h), "l"(nq));
+    (void)q;
+    return t;
+#else
+    (void)nq;
+    u64 h = umulhi64(x, ws);
+    return x * w - h * q;   // in [0, 2q)
+#endif
+}
 // One-word quotient estimate: k = floor(x_hi * mu32 / 2^32) <= floor(x/q), off by at most 2.
 DPFHE_HD u64 word_reduce(u64 x, const LimbParams &p) {
     u32 k = umulhi32((u32)(x >> 32), p.mu32);
-    return x - (u64)k * p.q;   // in [0, 3q)
+    return mad_lo64((u64)k, p.nq, x);   // x - k*q, in [0, 3q)
 }
+
+DPFHE_HD u64 shoup_lazy(u64 x, u64 w, u64 ws, const LimbParams &p) { return shoup_lazy(x, w, ws, p.q, p.nq); }
 
 // 128-bit product (hi:lo) of two 64-bit words.
 DPFHE_HD void mul128(u64 a, u64 b, u64 &hi, u64 &lo) {
@@ -100,7 +155,7 @@ DPFHE_HD u64 barrett_lazy(u64 hi, u64 lo, const LimbParams &p) {
     const u32 s = p.bar_shift;                       // 31 <= s <= 58
     u64 zt = (hi << (64 - s)) | (lo >> s);           // floor(z / 2^s) < 2^64
     u64 qh = umulhi64(zt, p.bar_mu);
-    return lo - qh * p.q;
+    return mad_lo64(qh, p.nq, lo);   // lo - qh*q
 }
 
 DPFHE_HD u64 mulmod_lazy(u64 a, u64 b, const LimbParams &p) {

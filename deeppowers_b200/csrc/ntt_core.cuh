@@ -42,7 +42,7 @@ DPFHE_HD int tw_pos(int s, int i) {
 // ---- butterflies -----------------------------------------------------------------------
 // forward, fully lazy: x' = x + w*y, y' = x - w*y + 2q; bound grows by 2 per stage.
 DPFHE_HD void ct_bfly(u64 &x, u64 &y, const Twiddle &w, const LimbParams &p) {
-    u64 t = shoup_lazy(y, w.x, w.y, p.q);
+    u64 t = shoup_lazy(y, w.x, w.y, p);
     u64 a = x;
     x = a + t;
     y = a + p.q2 - t;
@@ -51,7 +51,7 @@ DPFHE_HD void ct_bfly(u64 &x, u64 &y, const Twiddle &w, const LimbParams &p) {
 DPFHE_HD void gs_bfly(u64 &x, u64 &y, const Twiddle &w, const LimbParams &p) {
     u64 a = x, b = y;
     x = csub(a + b, p.q2);
-    y = shoup_lazy(a + p.q2 - b, w.x, w.y, p.q);
+    y = shoup_lazy(a + p.q2 - b, w.x, w.y, p);
 }
 
 // ---- lazy-bound schedule of the forward transform ------------------------------------------
@@ -270,13 +270,13 @@ DPFHE_HD void inv_store_stage(const u64 *buf, const Twiddle *__restrict__ tw, co
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     u64 a = x[i][e], b = x[NB / 2 + i][e];
-                    x[i][e] = csub(shoup_lazy(a + b, p.ninv, p.ninv_s, p.q), p.q);
-                    x[NB / 2 + i][e] = csub(shoup_lazy(a + p.q2 - b, p.wninv, p.wninv_s, p.q), p.q);
+                    x[i][e] = csub(shoup_lazy(a + b, p.ninv, p.ninv_s, p), p.q);
+                    x[NB / 2 + i][e] = csub(shoup_lazy(a + p.q2 - b, p.wninv, p.wninv_s, p), p.q);
                 }
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) x[0][e] = csub(shoup_lazy(x[0][e], p.ninv, p.ninv_s, p.q), p.q);
+            for (int e = 0; e < 2; ++e) x[0][e] = csub(shoup_lazy(x[0][e], p.ninv, p.ninv_s, p), p.q);
         }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {

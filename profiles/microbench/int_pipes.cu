@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(1024) bench(unsigned long long *out, long long
             if (OP == 2) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(r32[c]) : "r"(a), "r"(b));
             if (OP == 3) asm volatile("add.u64 %0, %0, %1;" : "+l"(acc[c]) : "l"((unsigned long long)a << 20 | b));
             if (OP == 4) acc[c] = __umul64hi(acc[c], p.bar_mu) + c;
-            if (OP == 5) acc[c] = shoup_lazy(acc[c], w.x, w.y, p.q);
+            if (OP == 5) acc[c] = shoup_lazy(acc[c], w.x, w.y, p);
             if (OP == 6) acc[c] = csub(acc[c] + p.q, p.q2);
             if (OP == 7) acc[c] = word_reduce(acc[c] * 5 + 1, p);
             if (OP == 8) acc[c] = mulmod_lazy(acc[c], p.wninv + c, p);
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(1024) bench(unsigned long long *out, long long
         }
         if (OP == 20) {   // shoup_lazy with a uniform twiddle (kernel parameter)
 #pragma unroll
-            for (int c = 0; c < CH; ++c) acc[c] = shoup_lazy(acc[c], p.ninv, p.ninv_s, p.q);
+            for (int c = 0; c < CH; ++c) acc[c] = shoup_lazy(acc[c], p.ninv, p.ninv_s, p);
         }
         if (OP == 9) {
 #pragma unroll
@@ -129,7 +129,7 @@ void run(const char *name, double per_iter_results, LimbParams p, int threads) {
 
 int main() {
     LimbParams p;
-    p.q = 0xfffffffffffc001ull; p.q2 = 2 * p.q; p.q4 = 4 * p.q; p.q8 = 8 * p.q;
+    p.q = 0xfffffffffffc001ull; p.q2 = 2 * p.q; p.q4 = 4 * p.q; p.q8 = 8 * p.q; p.nq = 0 - p.q;
     p.bar_shift = 58; p.bar_mu = (unsigned long long)(((unsigned __int128)1 << 122) / p.q);
     p.mu32 = (unsigned)(((unsigned __int128)1 << 64) / p.q);
     p.ninv = 0x123456789abcdefull % p.q; p.ninv_s = (unsigned long long)(((unsigned __int128)p.ninv << 64) / p.q);
