@@ -167,73 +167,110 @@ struct KsP1Operands {
     U64x2 kb, ka, kbs, kas; // key[i][b|a][i] chunk and Shoup companions
 };
 
+// base pointers of one work item's phase-1 streams (computed once, outside the chunk loop)
+struct KsP1Pointers {
+    const U64x2 *a0, *a1, *b0, *b1, *kb, *ka, *kbs, *kas;
+    const u64 *c0, *c1;   // ROTATE: scalar gathers
+};
+
 template <int LOGN, int MODE>
-DPFHE_HD KsP1Operands ks_p1_fetch(const KsArgs &A, size_t ct, u32 i, int c) {
-    constexpr int N = 1 << LOGN;
-    const size_t P = (size_t)A.L * N;
+DPFHE_HD KsP1Operands ks_p1_fetch(const KsP1Pointers &ptr, u32 galois, int c) {
     KsP1Operands o;
-    const size_t koff_b = ((size_t)i * 2 + 0) * P + (size_t)i * N, koff_a = ((size_t)i * 2 + 1) * P + (size_t)i * N;
-    o.kb = ld_keep(reinterpret_cast<const U64x2 *>(A.key + koff_b) + c);
-    o.ka = ld_keep(reinterpret_cast<const U64x2 *>(A.key + koff_a) + c);
-    o.kbs = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + koff_b) + c);
-    o.kas = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + koff_a) + c);
+    o.kb = ld_keep(ptr.kb + c);
+    o.ka = ld_keep(ptr.ka + c);
+    o.kbs = ld_keep(ptr.kbs + c);
+    o.kas = ld_keep(ptr.kas + c);
     if (MODE == KS_MUL_RELIN) {
-        o.a0 = ld_stream(reinterpret_cast<const U64x2 *>(A.a + ct * 2 * P + (size_t)i * N) + c);
-        o.a1 = ld_stream(reinterpret_cast<const U64x2 *>(A.a + ct * 2 * P + P + (size_t)i * N) + c);
-        o.b0 = ld_stream(reinterpret_cast<const U64x2 *>(A.b + ct * 2 * P + (size_t)i * N) + c);
-        o.b1 = ld_stream(reinterpret_cast<const U64x2 *>(A.b + ct * 2 * P + P + (size_t)i * N) + c);
+        o.a0 = ld_stream(ptr.a0 + c);
+        o.a1 = ld_stream(ptr.a1 + c);
+        o.b0 = ld_stream(ptr.b0 + c);
+        o.b1 = ld_stream(ptr.b1 + c);
     } else if (MODE == KS_PLAIN) {
-        o.a0 = ld_stream(reinterpret_cast<const U64x2 *>(A.a + ct * P + (size_t)i * N) + c);
+        o.a0 = ld_stream(ptr.a0 + c);
         o.a1 = o.b0 = o.b1 = o.a0;
     } else {
-        const u64 *c0 = A.a + ct * 2 * P + (size_t)i * N, *c1 = c0 + P;
-        const int n0 = galois_index<LOGN>(2 * c, A.galois), n1 = galois_index<LOGN>(2 * c + 1, A.galois);
-        o.a0.x = c0[n0];
-        o.a0.y = c0[n1];
-        o.a1.x = c1[n0];
-        o.a1.y = c1[n1];
+        const int n0 = galois_index<LOGN>(2 * c, galois), n1 = galois_index<LOGN>(2 * c + 1, galois);
+        o.a0.x = ptr.c0[n0];
+        o.a0.y = ptr.c0[n1];
+        o.a1.x = ptr.c1[n0];
+        o.a1.y = ptr.c1[n1];
         o.b0 = o.b1 = o.a0;
     }
     return o;
 }
 
+// digit + accumulator start values of one chunk position
+template <int MODE>
+DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only, u64 *buf, U64x2 *acc0, U64x2 *acc1, int c) {
+    U64x2 d, s0, s1;   // digit, own contributions to acc0 / acc1 (lazy < 3q)
+    if (MODE == KS_MUL_RELIN) {
+        tensor_coeff(o.a0.x, o.a1.x, o.b0.x, o.b1.x, p, s0.x, s1.x, d.x);
+        tensor_coeff(o.a0.y, o.a1.y, o.b0.y, o.b1.y, p, s0.y, s1.y, d.y);
+    } else if (MODE == KS_PLAIN) {
+        d = o.a0;
+        s0.x = s0.y = s1.x = s1.y = 0;
+    } else {
+        d = o.a1;
+        s0 = o.a0;
+        s1.x = s1.y = 0;
+    }
+    // digit enters the inverse transform in [0,2q)
+    reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = d;
+    U64x2 r0, r1;   // s < 3q, Shoup term < 2q  ->  accumulator starts below 5q
+    r0.x = s0.x + shoup_lazy(d.x, o.kb.x, o.kbs.x, p);
+    r0.y = s0.y + shoup_lazy(d.y, o.kb.y, o.kbs.y, p);
+    r1.x = s1.x + shoup_lazy(d.x, o.ka.x, o.kas.x, p);
+    r1.y = s1.y + shoup_lazy(d.y, o.ka.y, o.kas.y, p);
+    if (only) {
+        r0.x = canon(r0.x, p); r0.y = canon(r0.y, p);
+        r1.x = canon(r1.x, p); r1.y = canon(r1.y, p);
+    }
+    st_cg(acc0 + c, r0);
+    st_cg(acc1 + c, r1);
+}
+
 template <int LOGN, int NT, int MODE, class CTA>
 DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot) {
     constexpr int N = 1 << LOGN, NC = N / 2;
+    static_assert((NC / NT) % 2 == 0, "chunk loops may be unrolled by two (ping-pong operand buffers)");
     const size_t P = (size_t)A.L * N;
     U64x2 *acc0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N);
     U64x2 *acc1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
     const bool only = A.L == 1;   // a single digit: no phase 2, write the canonical result here
+    KsP1Pointers ptr;
+    {
+        const size_t koff_b = ((size_t)i * 2 + 0) * P + (size_t)i * N, koff_a = ((size_t)i * 2 + 1) * P + (size_t)i * N;
+        ptr.kb = reinterpret_cast<const U64x2 *>(A.key + koff_b);
+        ptr.ka = reinterpret_cast<const U64x2 *>(A.key + koff_a);
+        ptr.kbs = reinterpret_cast<const U64x2 *>(A.key_s + koff_b);
+        ptr.kas = reinterpret_cast<const U64x2 *>(A.key_s + koff_a);
+        const size_t in_off = (MODE == KS_PLAIN ? ct * P : ct * 2 * P) + (size_t)i * N;
+        ptr.a0 = reinterpret_cast<const U64x2 *>(A.a + in_off);
+        ptr.a1 = reinterpret_cast<const U64x2 *>(A.a + in_off + P);
+        ptr.b0 = reinterpret_cast<const U64x2 *>((MODE == KS_MUL_RELIN ? A.b : A.a) + in_off);
+        ptr.b1 = reinterpret_cast<const U64x2 *>((MODE == KS_MUL_RELIN ? A.b : A.a) + in_off + P);
+        ptr.c0 = A.a + in_off;
+        ptr.c1 = A.a + in_off + P;
+    }
+    const u32 galois = A.galois;
     cta.par([&](int tid) {
-        KsP1Operands nxt = ks_p1_fetch<LOGN, MODE>(A, ct, i, tid);
-        for (int c = tid; c < NC; c += NT) {
-            const KsP1Operands o = nxt;
-            if (c + NT < NC) nxt = ks_p1_fetch<LOGN, MODE>(A, ct, i, c + NT);   // next chunk's loads fly during this chunk's math
-            U64x2 d, s0, s1;   // digit, own contributions to acc0 / acc1 (lazy < 3q)
-            if (MODE == KS_MUL_RELIN) {
-                tensor_coeff(o.a0.x, o.a1.x, o.b0.x, o.b1.x, p, s0.x, s1.x, d.x);
-                tensor_coeff(o.a0.y, o.a1.y, o.b0.y, o.b1.y, p, s0.y, s1.y, d.y);
-            } else if (MODE == KS_PLAIN) {
-                d = o.a0;
-                s0.x = s0.y = s1.x = s1.y = 0;
-            } else {
-                d = o.a1;
-                s0 = o.a0;
-                s1.x = s1.y = 0;
+        if (MODE == KS_MUL_RELIN) {
+            // No software prefetch for the tensor product: three co-resident CTAs hide the load latency, and a
+            // second operand set (32 registers) would push the 80-register kernel into spills (+5% instructions).
+#pragma unroll 1
+            for (int c = tid; c < NC; c += NT) {
+                const KsP1Operands o = ks_p1_fetch<LOGN, MODE>(ptr, galois, c);
+                ks_p1_chunk<MODE>(o, p, only, buf, acc0, acc1, c);
             }
-            // digit enters the inverse transform in [0,2q)
-            reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = d;
-            U64x2 r0, r1;   // s < 3q, Shoup term < 2q  ->  accumulator starts below 5q
-            r0.x = s0.x + shoup_lazy(d.x, o.kb.x, o.kbs.x, p);
-            r0.y = s0.y + shoup_lazy(d.y, o.kb.y, o.kbs.y, p);
-            r1.x = s1.x + shoup_lazy(d.x, o.ka.x, o.kas.x, p);
-            r1.y = s1.y + shoup_lazy(d.y, o.ka.y, o.kas.y, p);
-            if (only) {
-                r0.x = canon(r0.x, p); r0.y = canon(r0.y, p);
-                r1.x = canon(r1.x, p); r1.y = canon(r1.y, p);
+        } else {
+            // rotate / key switch: the gathered operands have long latency and are few: fetch one chunk ahead
+            KsP1Operands nxt = ks_p1_fetch<LOGN, MODE>(ptr, galois, tid);
+#pragma unroll 1
+            for (int c = tid; c < NC; c += NT) {
+                const KsP1Operands o = nxt;
+                if (c + NT < NC) nxt = ks_p1_fetch<LOGN, MODE>(ptr, galois, c + NT);
+                ks_p1_chunk<MODE>(o, p, only, buf, acc0, acc1, c);
             }
-            st_cg(acc0 + c, r0);
-            st_cg(acc1 + c, r1);
         }
     });
     cta.mark(0);   // tensor / digit build + own key terms
@@ -267,39 +304,48 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
     U64x2 *acc1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
     // lazy accumulator bound: < 5q after phase 1, +2q per digit; every 4th digit one csub(8q) keeps it <= 16q
     const bool trim = (jj & 3u) == 0u, last = jj + 1 == A.L;
+    struct MacOperands {
+        U64x2 vb, va, vbs, vas, r0, r1;
+    };
+    auto fetch = [&](int c) {
+        MacOperands m;
+        m.vb = ld_keep(kb + c);
+        m.va = ld_keep(ka + c);
+        m.vbs = ld_keep(kbs + c);
+        m.vas = ld_keep(kas + c);
+        m.r0 = ld_cg(acc0 + c);
+        m.r1 = ld_cg(acc1 + c);
+        return m;
+    };
+    auto mac = [&](MacOperands &m, int c) {
+        // u < 16q straight from the transform: Shoup multiplication accepts any 64-bit operand
+        const U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)];
+        m.r0.x += shoup_lazy(u.x, m.vb.x, m.vbs.x, p);
+        m.r0.y += shoup_lazy(u.y, m.vb.y, m.vbs.y, p);
+        m.r1.x += shoup_lazy(u.x, m.va.x, m.vas.x, p);
+        m.r1.y += shoup_lazy(u.y, m.va.y, m.vas.y, p);
+        if (trim) {
+            m.r0.x = csub(m.r0.x, p.q8); m.r0.y = csub(m.r0.y, p.q8);
+            m.r1.x = csub(m.r1.x, p.q8); m.r1.y = csub(m.r1.y, p.q8);
+        }
+        if (last) {
+            m.r0.x = canon(m.r0.x, p); m.r0.y = canon(m.r0.y, p);
+            m.r1.x = canon(m.r1.x, p); m.r1.y = canon(m.r1.y, p);
+            st_stream(acc0 + c, m.r0);
+            st_stream(acc1 + c, m.r1);
+        } else {
+            st_cg(acc0 + c, m.r0);
+            st_cg(acc1 + c, m.r1);
+        }
+    };
+    static_assert((NC / NT) % 2 == 0, "the chunk loop is unrolled by two (ping-pong operand buffers)");
     cta.par([&](int tid) {
-        U64x2 nb = ld_keep(kb + tid), na = ld_keep(ka + tid), nbs = ld_keep(kbs + tid), nas = ld_keep(kas + tid);
-        U64x2 n0 = ld_cg(acc0 + tid), n1 = ld_cg(acc1 + tid);
+        MacOperands nxt = fetch(tid);
+#pragma unroll 1
         for (int c = tid; c < NC; c += NT) {
-            const U64x2 vb = nb, va = na, vbs = nbs, vas = nas;
-            U64x2 r0 = n0, r1 = n1;
-            if (c + NT < NC) {
-                nb = ld_keep(kb + c + NT);
-                na = ld_keep(ka + c + NT);
-                nbs = ld_keep(kbs + c + NT);
-                nas = ld_keep(kas + c + NT);
-                n0 = ld_cg(acc0 + c + NT);
-                n1 = ld_cg(acc1 + c + NT);
-            }
-            // u < 16q straight from the transform: Shoup multiplication accepts any 64-bit operand
-            const U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)];
-            r0.x += shoup_lazy(u.x, vb.x, vbs.x, p);
-            r0.y += shoup_lazy(u.y, vb.y, vbs.y, p);
-            r1.x += shoup_lazy(u.x, va.x, vas.x, p);
-            r1.y += shoup_lazy(u.y, va.y, vas.y, p);
-            if (trim) {
-                r0.x = csub(r0.x, p.q8); r0.y = csub(r0.y, p.q8);
-                r1.x = csub(r1.x, p.q8); r1.y = csub(r1.y, p.q8);
-            }
-            if (last) {
-                r0.x = canon(r0.x, p); r0.y = canon(r0.y, p);
-                r1.x = canon(r1.x, p); r1.y = canon(r1.y, p);
-                st_stream(acc0 + c, r0);
-                st_stream(acc1 + c, r1);
-            } else {
-                st_cg(acc0 + c, r0);
-                st_cg(acc1 + c, r1);
-            }
+            MacOperands m = nxt;
+            if (c + NT < NC) nxt = fetch(c + NT);   // next chunk's key / accumulator loads fly during this chunk's math
+            mac(m, c);
         }
     });
     cta.mark(6);   // multiply-accumulate with the key column (the last digit also canonicalises and stores)

@@ -80,6 +80,11 @@ __device__ __forceinline__ void st_release_u64(u64 *p, u64 v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// TMA-unit bulk prefetch of a contiguous region into L2 (SASS: UBLKPF.L2); bytes must be a multiple of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, u32 bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // grid = G CTAs, G a multiple of L, all co-resident (cooperative launch).  The L CTAs of slots
 // [g*L, (g+1)*L) form a group that processes one ciphertext at a time: CTA `slot` owns output limb
 // i = slot % L.  The group leader (i == 0) draws the next ciphertext index from a global ticket counter
@@ -88,7 +93,7 @@ __device__ __forceinline__ void st_release_u64(u64 *p, u64 v) {
 // L2 resident) under release/acquire flags.
 template <int LOGN, int NT, int MINB, int MODE, bool PROF>
 __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __grid_constant__ LimbTable lt, size_t batch, u32 *flags, u32 epoch,
-                                                            u32 *ticket, u64 *mail, unsigned long long *prof) {
+                                                            u32 *ticket, u64 *mail, unsigned long long *prof, u32 pf_dist) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr size_t N = (size_t)1 << LOGN;
     u64 *buf = reinterpret_cast<u64 *>(smem_raw);
@@ -120,6 +125,23 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
         __syncthreads();
         const size_t ct = s_ct;
         if (ct >= batch) break;   // every member of the group reads the same ticket, so they leave together
+        // Tickets are drawn in order, so ciphertext ct + pf_dist will be started by some group a few microseconds
+        // from now: pull this CTA's limb of its inputs from HBM into L2 with the TMA unit's bulk prefetch, so the
+        // tensor phase that consumes them is L2- rather than HBM-latency bound.
+        if (pf_dist && threadIdx.x == 0 && ct + pf_dist < batch) {
+            const size_t nc = ct + pf_dist, P = (size_t)L * N;
+            constexpr u32 LB = (u32)(N * 8);
+            if (MODE == KS_PLAIN) {
+                bulk_prefetch_l2(A.a + nc * P + (size_t)i * N, LB);
+            } else {
+                bulk_prefetch_l2(A.a + nc * 2 * P + (size_t)i * N, LB);
+                bulk_prefetch_l2(A.a + nc * 2 * P + P + (size_t)i * N, LB);
+                if (MODE == KS_MUL_RELIN) {
+                    bulk_prefetch_l2(A.b + nc * 2 * P + (size_t)i * N, LB);
+                    bulk_prefetch_l2(A.b + nc * 2 * P + P + (size_t)i * N, LB);
+                }
+            }
+        }
         const u32 parity = round & 1u;
         ks_phase1<LOGN, NT, MODE>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N);
         if (L > 1) {
@@ -329,7 +351,8 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
     unsigned long long *prof = lc.ks_prof;
     u32 *ticket = lc.ks_ticket;
     u64 *mail = lc.ks_mail;
-    void *params[] = {&args, &lt, &batch_arg, &flags, &epoch, &ticket, &mail, &prof};
+    u32 pf_dist = (u32)lc.ks_prefetch;
+    void *params[] = {&args, &lt, &batch_arg, &flags, &epoch, &ticket, &mail, &prof, &pf_dist};
     e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)G), dim3(NT), params, smem, st);
     lc.ks_epoch += rounds;
     return e;

@@ -29,6 +29,7 @@ struct LaunchCtx {
     u64 *ks_key_s = nullptr;          // [L][2][L][N] Shoup companions of the current switch key
     size_t ks_slots = 0;
     u32 ks_epoch = 0;                 // rounds consumed so far (flag values already used)
+    int ks_prefetch = 0;              // ciphertexts ahead for the bulk L2 prefetch of inputs (DPFHE_KS_PF), 0 = off
     int ks_occ_cap = 0;               // tuning: cap on resident fused-kernel CTAs per SM (DPFHE_KS_OCC), 0 = no cap
     unsigned long long *ks_prof = nullptr;   // [ks_slots][16] phase cycle counters; non-null selects the profiling build
 };

@@ -152,8 +152,15 @@ DPFHE_HD void mul128(u64 a, u64 b, u64 &hi, u64 &lo) {
 // Barrett reduction of z = hi:lo.  Requires z < 2^(2b+4) (e.g. both factors < 4q), gives [0, 3q).
 // With both factors < q the result is in [0, 2q).
 DPFHE_HD u64 barrett_lazy(u64 hi, u64 lo, const LimbParams &p) {
-    const u32 s = p.bar_shift;                       // 31 <= s <= 58
-    u64 zt = (hi << (64 - s)) | (lo >> s);           // floor(z / 2^s) < 2^64
+    const u32 s = p.bar_shift;                       // 32 <= s <= 58 because 2^33 < q < 2^60
+#if defined(__CUDA_ARCH__)
+    // floor(z / 2^s) with two funnel shifts over the three upper words of z
+    const u32 w1 = (u32)(lo >> 32), w2 = (u32)hi, w3 = (u32)(hi >> 32);
+    const u32 zl = __funnelshift_r(w1, w2, s - 32), zh = __funnelshift_r(w2, w3, s - 32);
+    const u64 zt = ((u64)zh << 32) | zl;
+#else
+    const u64 zt = (hi << (64 - s)) | (lo >> s);     // floor(z / 2^s) < 2^64
+#endif
     u64 qh = umulhi64(zt, p.bar_mu);
     return mad_lo64(qh, p.nq, lo);   // lo - qh*q
 }
