@@ -123,8 +123,12 @@ DPFHE_HD U64x2 mul_chunk(const U64x2 &a, const U64x2 &b, const LimbParams &p) {
 DPFHE_HD void mac128(u64 &hi, u64 &lo, u64 a, u64 b) {
     u64 h, l;
     mul128(a, b, h, l);
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(lo), "+l"(hi) : "l"(l), "l"(h));
+#else
     lo += l;
     hi += h + (lo < l ? 1ull : 0ull);
+#endif
 }
 
 // tensor of one coefficient: canonical inputs; d0,d2 in [0,2q), d1 in [0,3q)

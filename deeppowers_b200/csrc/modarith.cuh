@@ -137,11 +137,32 @@ DPFHE_HD u64 word_reduce(u64 x, const LimbParams &p) {
 
 DPFHE_HD u64 shoup_lazy(u64 x, u64 w, u64 ws, const LimbParams &p) { return shoup_lazy(x, w, ws, p.q, p.nq); }
 
-// 128-bit product (hi:lo) of two 64-bit words.
+// 128-bit product (hi:lo) of two 64-bit words.  Device: four IMAD.WIDE partial products combined once
+// (nvcc's separate a*b and __umul64hi(a,b) would recompute the low partial product: 5 IMAD.WIDE + 2 IMAD).
 DPFHE_HD void mul128(u64 a, u64 b, u64 &hi, u64 &lo) {
 #if defined(__CUDA_ARCH__)
-    lo = a * b;
-    hi = __umul64hi(a, b);
+    asm("{\n\t"
+        ".reg .u32 al, ah, bl, bh, p0l, p0h, ml, mh, cy;\n\t"
+        ".reg .u64 p0, p1, p2, p3, m, t;\n\t"
+        "mov.b64 {al, ah}, %2;\n\t"
+        "mov.b64 {bl, bh}, %3;\n\t"
+        "mul.wide.u32 p0, al, bl;\n\t"
+        "mul.wide.u32 p1, al, bh;\n\t"
+        "mul.wide.u32 p2, ah, bl;\n\t"
+        "mul.wide.u32 p3, ah, bh;\n\t"
+        "mov.b64 {p0l, p0h}, p0;\n\t"
+        "add.cc.u64 m, p1, p2;\n\t"
+        "addc.u32 cy, 0, 0;\n\t"
+        "cvt.u64.u32 t, p0h;\n\t"
+        "add.cc.u64 m, m, t;\n\t"
+        "addc.u32 cy, cy, 0;\n\t"
+        "mov.b64 {ml, mh}, m;\n\t"
+        "mov.b64 %1, {p0l, ml};\n\t"
+        "mov.b64 t, {mh, cy};\n\t"
+        "add.u64 %0, p3, t;\n\t"
+        "}"
+        : "=l"(hi), "=l"(lo)
+        : "l"(a), "l"(b));
 #else
     unsigned __int128 z = (unsigned __int128)a * b;
     lo = (u64)z;
