@@ -379,6 +379,16 @@ int dpfhe_ct_mul_plain(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_p
     return DPFHE_OK;
 }
 
+int dpfhe_ct_mul_plain_acc(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_pt, uint64_t *d_acc, size_t batch, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    CHECK_PTR(d_ct); CHECK_PTR(d_pt); CHECK_PTR(d_acc);
+    CU_TRY(launch_ct_mul_plain_acc(ctx->lc, d_ct, d_pt, d_acc, batch, pick(ctx, stream)));
+    ctx->launches++;
+    return DPFHE_OK;
+}
+
 int dpfhe_fill_uniform(dpfhe_ctx *ctx, uint64_t seed, uint64_t first_poly, uint64_t *d_data, size_t n_polys, void *stream) {
     int rc = enter(ctx);
     if (rc) return rc;

@@ -210,6 +210,24 @@ __global__ void __launch_bounds__(256) ct_mul_plain_kernel(const U64x2 *__restri
     }
 }
 
+// acc += ct o pt  (fused multiply-accumulate used by diagonal-method linear layers); acc may be lazy-free: all canonical
+template <int LOGN>
+__global__ void __launch_bounds__(256) ct_mul_plain_acc_kernel(const U64x2 *__restrict__ ct, const U64x2 *__restrict__ pt,
+                                                               U64x2 *__restrict__ acc, const LimbParams *__restrict__ lps,
+                                                               u32 L, size_t n_chunks) {
+    constexpr size_t NC = (size_t)1 << (LOGN - 1);
+    const size_t pc = NC * L;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += (size_t)gridDim.x * blockDim.x) {
+        const size_t in_poly = c % pc;
+        const LimbParams p = lps[in_poly / NC];
+        const U64x2 x = ld_stream(ct + c), m = ld_keep(pt + in_poly), a = ld_stream(acc + c);
+        U64x2 r;
+        r.x = csub(a.x + canon4(mulmod_lazy(x.x, m.x, p), p), p.q);
+        r.y = csub(a.y + canon4(mulmod_lazy(x.y, m.y, p), p), p.q);
+        st_stream(acc + c, r);
+    }
+}
+
 // a,b [batch][2][L][N] -> d [batch][3][L][N]; one thread per chunk of one polynomial position
 template <int LOGN>
 __global__ void __launch_bounds__(256) ct_tensor_kernel(const U64x2 *__restrict__ a, const U64x2 *__restrict__ b,
@@ -430,6 +448,18 @@ cudaError_t launch_ct_mul_plain(const LaunchCtx &lc, const u64 *ct, const u64 *p
     LOGN_SWITCH((ct_mul_plain_kernel<12><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
                 (ct_mul_plain_kernel<13><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
                 (ct_mul_plain_kernel<14><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)))
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ct_mul_plain_acc(const LaunchCtx &lc, const u64 *ct, const u64 *pt, u64 *acc, size_t batch, cudaStream_t st) {
+    const size_t n_chunks = batch * 2 * lc.L * ((size_t)1 << (lc.log_n - 1));
+    if (!n_chunks) return cudaSuccess;
+    const unsigned grid = ew_grid(lc, n_chunks);
+    auto A = reinterpret_cast<const U64x2 *>(ct), B = reinterpret_cast<const U64x2 *>(pt);
+    auto O = reinterpret_cast<U64x2 *>(acc);
+    LOGN_SWITCH((ct_mul_plain_acc_kernel<12><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
+                (ct_mul_plain_acc_kernel<13><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)),
+                (ct_mul_plain_acc_kernel<14><<<grid, 256, 0, st>>>(A, B, O, lc.lp, lc.L, n_chunks)))
     return cudaGetLastError();
 }
 

@@ -139,6 +139,40 @@ class Context:
     def ct_mul_plain(self, ct, pt, out, batch, stream=None):
         self._chk(self._l.dpfhe_ct_mul_plain(self._h, _ptr(ct), _ptr(pt), _ptr(out), batch, _stream(stream)))
 
+    def ct_mul_plain_acc(self, ct, pt, acc, batch, stream=None):
+        self._chk(self._l.dpfhe_ct_mul_plain_acc(self._h, _ptr(ct), _ptr(pt), _ptr(acc), batch, _stream(stream)))
+
+    def linear_bsgs(self, ct, diags, gk_baby, gk_giant, baby, out, batch, scratch=None, stream=None):
+        """Encrypted matrix-vector product by baby-step/giant-step diagonals (row f-4, config 4).
+
+        y = sum_g rot_{g*baby}( sum_b D[g*baby + b] o rot_b(x) ), D pre-rotated by -g*baby (caller encodes them so),
+        diags: [n][L][N] plaintexts in evaluation form, n a multiple of `baby`; gk_baby / gk_giant: Galois keys of
+        rotations by 1 and by `baby`.  Uses (baby-1) + (n/baby-1) rotations instead of n-1.  `scratch` must hold
+        (baby + 2) ciphertext batches; `out` must not alias `ct`."""
+        import torch
+        n = diags.shape[0]
+        assert n % baby == 0, "number of diagonals must be a multiple of the baby-step count"
+        giant = n // baby
+        shape = (batch, 2, self.L, self.N)
+        if scratch is None:
+            scratch = torch.empty((baby + 2,) + shape, dtype=torch.int64, device=ct.device)
+        steps, inner, tmp = scratch[:baby], scratch[baby], scratch[baby + 1]
+        g1, gb = self.galois_elt(1), self.galois_elt(baby)
+        steps[0].copy_(ct.view(shape))
+        for b in range(1, baby):
+            self.rotate(steps[b - 1], g1, gk_baby, steps[b], batch, stream)
+        acc = out
+        for g in range(giant - 1, -1, -1):
+            self.ct_mul_plain(steps[0], diags[g * baby], inner, batch, stream)
+            for b in range(1, baby):
+                self.ct_mul_plain_acc(steps[b], diags[g * baby + b], inner, batch, stream)
+            if g == giant - 1:
+                acc.view(shape).copy_(inner)
+            else:
+                self.rotate(acc, gb, gk_giant, tmp, batch, stream)          # Horner step: acc = rot_baby(acc) + inner_g
+                self.poly_add(tmp, inner, acc, 2 * batch, stream)
+        return out
+
     def rotate(self, ct, galois_elt, gk, out, batch, stream=None):
         self._chk(self._l.dpfhe_rotate(self._h, _ptr(ct), int(galois_elt), _ptr(gk), _ptr(out), batch, _stream(stream)))
 

@@ -111,6 +111,10 @@ public:
     void add_device(const std::uint64_t *a, const std::uint64_t *b, std::uint64_t *out, std::size_t count, void *stream = nullptr) {
         check(dpfhe_poly_add(ctx_, a, b, out, 2 * count, stream));   // a ciphertext is two polynomials
     }
+    void multiply_plain_accumulate_device(const std::uint64_t *ct, const std::uint64_t *plain_eval, std::uint64_t *acc, std::size_t count,
+                                          void *stream = nullptr) {
+        check(dpfhe_ct_mul_plain_acc(ctx_, ct, plain_eval, acc, count, stream));
+    }
     void keyswitch_device(const std::uint64_t *digits, const std::uint64_t *key, std::uint64_t *out, std::size_t count, void *stream = nullptr) {
         check(dpfhe_keyswitch(ctx_, digits, key, out, count, stream));
     }

@@ -102,6 +102,9 @@ int dpfhe_ct_mul_relin(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b,
 /* out = (c0 o pt, c1 o pt); pt [L][N] shared by the batch; out may alias ct */
 int dpfhe_ct_mul_plain(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_pt, uint64_t *d_out,
                        size_t batch, void *stream);
+/* acc += (c0 o pt, c1 o pt): fused multiply-accumulate for diagonal-method linear layers; acc [batch][2][L][N] */
+int dpfhe_ct_mul_plain_acc(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_pt, uint64_t *d_acc,
+                           size_t batch, void *stream);
 /* out = (sigma_g(c0) + ks0, ks1), ks = keyswitch(sigma_g(c1), gk); galois_elt odd in [1,2N);
  * out must not alias ct */
 int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk,

@@ -87,3 +87,52 @@ def test_encrypted_linear_layer_768(oracle_mod):
         y = np.where(y > T_PLAIN // 2, y - T_PLAIN, y)
         assert np.array_equal(y, W @ X[b])
     ctx.close()
+
+
+def test_encrypted_linear_layer_bsgs(oracle_mod):
+    """same layer through Context.linear_bsgs: 31 baby + 23 giant rotations instead of 767, fused multiply-accumulate"""
+    import deeppowers_b200 as dp
+    log_n, L, B, BABY = 13, 4, 2, 32
+    o = oracle_mod.Oracle(log_n, L)
+    ctx = dp.Context(log_n, L)
+    N = o.N
+    enc = SlotEncoder(N, T_PLAIN)
+    rng = np.random.default_rng(0xD3390044)
+    W = rng.integers(-127, 128, (DIM, DIM))
+    X = rng.integers(-127, 128, (B, DIM))
+    s = o.keygen_secret(1)
+    gk1 = o.keygen_galois(2, T_PLAIN, s, o.galois_elt(1))
+    gkb = o.keygen_galois(3, T_PLAIN, s, o.galois_elt(BABY))
+    cts = []
+    for b in range(B):
+        slots = np.zeros((2, N // 2), dtype=np.int64)
+        slots[0, :DIM] = X[b]
+        slots[0, DIM:2 * DIM] = X[b]
+        cts.append(o.encrypt(10 + b, T_PLAIN, s, enc.encode(slots)))
+    ct = np.stack(cts)
+    diag = torch.empty((DIM, L, N), dtype=torch.int64, device="cuda")
+    ar = np.arange(DIM)
+    for d in range(DIM):
+        g = d // BABY
+        slots = np.zeros((2, N // 2), dtype=np.int64)
+        slots[0, :DIM] = W[ar, (ar + d) % DIM]
+        slots = np.roll(slots, g * BABY, axis=1)          # D_{g,b} = rot_{-g*baby}(diag_d)
+        diag[d] = dev(to_rns_eval(o, enc.encode(slots)))
+    out = torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda")
+    n0 = ctx.launch_count()
+    ctx.linear_bsgs(dev(ct), diag, dev(gk1), dev(gkb), BABY, out, B)
+    torch.cuda.synchronize()
+    n_rot = (BABY - 1) + (DIM // BABY - 1)
+    assert ctx.launch_count() - n0 == 2 * n_rot + DIM + (DIM // BABY - 1)     # rotations (2 launches each), mults, adds
+    res = host(out).reshape(B, 2, L, N)
+    for b in range(B):
+        y = enc.decode(o.decrypt(s, res[b], T_PLAIN))[0, :DIM].astype(np.int64)
+        y = np.where(y > T_PLAIN // 2, y - T_PLAIN, y)
+        assert np.array_equal(y, W @ X[b])
+    # the fused multiply-accumulate itself, bit-exact against the oracle
+    pt = host(diag[5]).reshape(L, N)
+    acc = o.fill_uniform(77, 2 * B).reshape(B, 2, L, N)
+    d_acc = dev(acc)
+    ctx.ct_mul_plain_acc(dev(ct), diag[5], d_acc, B)
+    assert np.array_equal(host(d_acc).reshape(acc.shape), o.poly_add(acc, o.ct_mul_plain(ct, pt)))
+    ctx.close()
