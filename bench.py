@@ -198,6 +198,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL's banner ("NCCL version ...") otherwise lands there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.batch
     ctx = dp.Context(LOG_N, L, device=local_rank)
