@@ -200,29 +200,25 @@ class Context:
         return pow(5, k % (self.N // 2), 2 * self.N)
 
 
+class PinnedBuffer:
+    """Pinned host memory from dpfhe_host_alloc, exposed as a numpy uint64 array (`.array`); freed on close()/GC."""
+
+    def __init__(self, n_words):
+        self._l = _lib.load()
+        self._p = C.c_void_p()
+        if self._l.dpfhe_host_alloc(C.byref(self._p), n_words * 8) != 0:
+            raise DpfheError(self._l.dpfhe_last_error().decode())
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint64)), shape=(n_words,))
+
+    def close(self):
+        if self._p and self._p.value:
+            self.array = None
+            self._l.dpfhe_host_free(self._p)
+            self._p = C.c_void_p()
+
+    __del__ = close
+
+
 def pinned_empty(n_words):
-    """numpy uint64 array over pinned host memory from dpfhe_host_alloc (freed when garbage collected)."""
-    l = _lib.load()
-    p = C.c_void_p()
-    if l.dpfhe_host_alloc(C.byref(p), n_words * 8) != 0:
-        raise DpfheError(l.dpfhe_last_error().decode())
-    buf = (C.c_uint64 * n_words).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=np.uint64)
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                l.dpfhe_host_free(self.ptr)
-            except Exception:
-                pass
-
-    owner = _Owner(p)
-    holder = np.lib.stride_tricks.as_strided(arr)   # view keeping `arr` alive
-    _PINNED_OWNERS[id(holder)] = (owner, buf)
-    return holder
-
-
-_PINNED_OWNERS = {}
+    """convenience: a PinnedBuffer (keep the object alive while its `.array` is in use)"""
+    return PinnedBuffer(n_words)
