@@ -514,7 +514,7 @@ int dpfhe_describe(const dpfhe_ctx *ctx, char *buf, size_t buf_len) {
                      "{\"log_n\": %u, \"n_limbs\": %u, \"num_sms\": %d, \"ntt_kernel\": {\"threads\": %u, \"smem_bytes\": %zu, "
                      "\"grid\": \"one CTA per limb\"}, \"ks_fused_kernel\": {\"threads\": %u, \"smem_bytes\": %zu, "
                      "\"grid\": \"persistent cooperative, multiple of L, <= %zu slots\"}}",
-                     ctx->hp.log_n, ctx->hp.L, ctx->lc.num_sms, nt, ctx->N() * 8, ctx->hp.log_n <= 13 ? 256u : 512u, ctx->N() * 8, ctx->lc.ks_slots);
+                     ctx->hp.log_n, ctx->hp.L, ctx->lc.num_sms, nt, ctx->N() * 8, 256u, ctx->hp.log_n <= 13 ? ctx->N() * 8 : ctx->N() * 4, ctx->lc.ks_slots);
     return n;
 }
 

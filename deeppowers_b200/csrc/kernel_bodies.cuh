@@ -205,7 +205,7 @@ DPFHE_HD KsP1Operands ks_p1_fetch(const KsP1Pointers &ptr, u32 galois, int c) {
 
 // digit + accumulator start values of one chunk position
 template <int MODE>
-DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only, u64 *buf, U64x2 *acc0, U64x2 *acc1, int c) {
+DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only, u64 *buf, U64x2 *acc0, U64x2 *acc1, int c, int c_buf) {
     U64x2 d, s0, s1;   // digit, own contributions to acc0 / acc1 (lazy < 3q)
     if (MODE == KS_MUL_RELIN) {
         tensor_coeff(o.a0.x, o.a1.x, o.b0.x, o.b1.x, p, s0.x, s1.x, d.x);
@@ -219,7 +219,7 @@ DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only,
         s1.x = s1.y = 0;
     }
     // digit enters the inverse transform in [0,2q)
-    reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = d;
+    reinterpret_cast<U64x2 *>(buf)[swz_chunk(c_buf)] = d;
     U64x2 r0, r1;   // s < 3q, Shoup term < 2q  ->  accumulator starts below 5q
     r0.x = s0.x + shoup_lazy(d.x, o.kb.x, o.kbs.x, p);
     r0.y = s0.y + shoup_lazy(d.y, o.kb.y, o.kbs.y, p);
@@ -257,35 +257,62 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
         ptr.c1 = A.a + in_off + P;
     }
     const u32 galois = A.galois;
-    cta.par([&](int tid) {
-        if (MODE == KS_MUL_RELIN) {
-            // No software prefetch for the tensor product: three co-resident CTAs hide the load latency, and a
-            // second operand set (32 registers) would push the 80-register kernel into spills (+5% instructions).
+    // chunk range [c_lo, c_lo + n_c) of the limb goes to shared-memory chunks [0, n_c)
+    auto build = [&](int c_lo, int n_c) {
+        cta.par([&](int tid) {
+            if (MODE == KS_MUL_RELIN) {
+                // No software prefetch for the tensor product: three co-resident CTAs hide the load latency, and a
+                // second operand set (32 registers) would push the 80-register kernel into spills (+5% instructions).
 #pragma unroll 1
-            for (int c = tid; c < NC; c += NT) {
-                const KsP1Operands o = ks_p1_fetch<LOGN, MODE>(ptr, galois, c);
-                ks_p1_chunk<MODE>(o, p, only, buf, acc0, acc1, c);
-            }
-        } else {
-            // rotate / key switch: the gathered operands have long latency and are few: fetch one chunk ahead
-            KsP1Operands nxt = ks_p1_fetch<LOGN, MODE>(ptr, galois, tid);
+                for (int lc = tid; lc < n_c; lc += NT) {
+                    const KsP1Operands o = ks_p1_fetch<LOGN, MODE>(ptr, galois, c_lo + lc);
+                    ks_p1_chunk<MODE>(o, p, only, buf, acc0, acc1, c_lo + lc, lc);
+                }
+            } else {
+                // rotate / key switch: the gathered operands have long latency and are few: fetch one chunk ahead
+                KsP1Operands nxt = ks_p1_fetch<LOGN, MODE>(ptr, galois, c_lo + tid);
 #pragma unroll 1
-            for (int c = tid; c < NC; c += NT) {
-                const KsP1Operands o = nxt;
-                if (c + NT < NC) nxt = ks_p1_fetch<LOGN, MODE>(ptr, galois, c + NT);
-                ks_p1_chunk<MODE>(o, p, only, buf, acc0, acc1, c);
+                for (int lc = tid; lc < n_c; lc += NT) {
+                    const KsP1Operands o = nxt;
+                    if (lc + NT < n_c) nxt = ks_p1_fetch<LOGN, MODE>(ptr, galois, c_lo + lc + NT);
+                    ks_p1_chunk<MODE>(o, p, only, buf, acc0, acc1, c_lo + lc, lc);
+                }
             }
-        }
-    });
-    cta.mark(0);   // tensor / digit build + own key terms
-    if (A.L == 1) return;   // no other digit needs t
-    inv_passes<LOGN, NT>(cta, buf, A.itw + (size_t)i * N, p);
-    cta.mark(1);   // inverse register passes
+        });
+    };
+    const Twiddle *itw = A.itw + (size_t)i * N;
     U64x2 *dst = reinterpret_cast<U64x2 *>(t_slot);
-    cta.par([&](int tid) {
-        inv_store_stage<LOGN, NT>(buf, A.itw + (size_t)i * N, p, tid, [&](int c, const U64x2 &v) { st_cg(dst + c, v); });
-    });
-    cta.mark(2);   // outer inverse stage + digit publish
+    if constexpr (LOGN <= 13) {
+        build(0, NC);
+        cta.mark(0);   // tensor / digit build + own key terms
+        if (A.L == 1) return;   // no other digit needs t
+        inv_passes<LOGN, NT>(cta, buf, itw, p);
+        cta.mark(1);   // inverse register passes
+        cta.par([&](int tid) {
+            inv_store_stage<LOGN, NT>(buf, itw, p, tid, [&](int c, const U64x2 &v) { st_cg(dst + c, v); });
+        });
+        cta.mark(2);   // outer inverse stage + digit publish
+    } else {
+        // N = 16384: the limb is processed as two halves of two 4096-blocks each (64 KiB of shared memory, so three
+        // CTAs share an SM); the block-local register passes leave their result in the digit slot, and the two
+        // outermost stages then run in place over the slot (each thread reads and rewrites its own four chunks).
+        constexpr int HC = NC / 2;
+        for (int h = 0; h < 2; ++h) {
+            build(h * HC, HC);
+            cta.mark(0);
+            if (A.L == 1) continue;
+            inv_passes_blk<LOGN, NT, 2>(cta, buf, itw, p, 2 * h);
+            cta.mark(1);
+            cta.par([&](int tid) {
+                for (int lc = tid; lc < HC; lc += NT) st_cg(dst + h * HC + lc, reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lc)]);
+            });
+        }
+        if (A.L == 1) return;
+        cta.par([&](int tid) {
+            inv_outer_stage<LOGN, NT>(itw, p, tid, [&](int c) { return ld_cg(dst + c); }, [&](int c, const U64x2 &v) { st_cg(dst + c, v); });
+        });
+        cta.mark(2);
+    }
 }
 
 // t_src: the published t of digit j (N words, natural order, canonical mod q_j)
@@ -295,12 +322,6 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
     const size_t P = (size_t)A.L * N;
     const Twiddle *tw = A.tw + (size_t)i * N;
     const U64x2 *src = reinterpret_cast<const U64x2 *>(t_src);
-    cta.par([&](int tid) {
-        fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); });
-    });
-    cta.mark(4);   // digit fetch + lift + outer forward stage
-    fwd_passes<LOGN, NT, 3>(cta, buf, tw, p);
-    cta.mark(5);   // forward register passes
     const size_t koff_b = ((size_t)j * 2 + 0) * P + (size_t)i * N, koff_a = ((size_t)j * 2 + 1) * P + (size_t)i * N;
     const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + koff_b), *ka = reinterpret_cast<const U64x2 *>(A.key + koff_a);
     const U64x2 *kbs = reinterpret_cast<const U64x2 *>(A.key_s + koff_b), *kas = reinterpret_cast<const U64x2 *>(A.key_s + koff_a);
@@ -321,9 +342,10 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
         m.r1 = ld_cg(acc1 + c);
         return m;
     };
-    auto mac = [&](MacOperands &m, int c) {
+    // c: chunk of the limb (key / accumulator position); c_buf: where its transform output sits in shared memory
+    auto mac = [&](MacOperands &m, int c, int c_buf) {
         // u < 16q straight from the transform: Shoup multiplication accepts any 64-bit operand
-        const U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)];
+        const U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c_buf)];
         m.r0.x += shoup_lazy(u.x, m.vb.x, m.vbs.x, p);
         m.r0.y += shoup_lazy(u.y, m.vb.y, m.vbs.y, p);
         m.r1.x += shoup_lazy(u.x, m.va.x, m.vas.x, p);
@@ -342,17 +364,41 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
             st_cg(acc1 + c, m.r1);
         }
     };
-    static_assert((NC / NT) % 2 == 0, "the chunk loop is unrolled by two (ping-pong operand buffers)");
-    cta.par([&](int tid) {
-        MacOperands nxt = fetch(tid);
+    // multiply-accumulate of the chunk range [c_lo, c_lo + n_c), whose transform output sits in chunks [0, n_c)
+    auto mac_range = [&](int c_lo, int n_c) {
+        cta.par([&](int tid) {
+            MacOperands nxt = fetch(c_lo + tid);
 #pragma unroll 1
-        for (int c = tid; c < NC; c += NT) {
-            MacOperands m = nxt;
-            if (c + NT < NC) nxt = fetch(c + NT);   // next chunk's key / accumulator loads fly during this chunk's math
-            mac(m, c);
+            for (int lc = tid; lc < n_c; lc += NT) {
+                MacOperands m = nxt;
+                if (lc + NT < n_c) nxt = fetch(c_lo + lc + NT);   // next chunk's key / accumulator loads fly during this chunk's math
+                mac(m, c_lo + lc, lc);
+            }
+        });
+    };
+    if constexpr (LOGN <= 13) {
+        cta.par([&](int tid) {
+            fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); });
+        });
+        cta.mark(4);   // digit fetch + lift + outer forward stage
+        fwd_passes<LOGN, NT, 3>(cta, buf, tw, p);
+        cta.mark(5);   // forward register passes
+        mac_range(0, NC);
+        cta.mark(6);   // multiply-accumulate with the key column (the last digit also canonicalises and stores)
+    } else {
+        // N = 16384: two halves of two 4096-blocks; each half re-reads the digit and keeps its two output blocks
+        constexpr int HC = NC / 2;
+        for (int h = 0; h < 2; ++h) {
+            cta.par([&](int tid) {
+                fwd_load_stage_half<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); }, h);
+            });
+            cta.mark(4);
+            fwd_passes_blk<LOGN, NT, 3, 2>(cta, buf, tw, p, 2 * h);
+            cta.mark(5);
+            mac_range(h * HC, HC);
+            cta.mark(6);
         }
-    });
-    cta.mark(6);   // multiply-accumulate with the key column (the last digit also canonicalises and stores)
+    }
 }
 
 }  // namespace dpfhe

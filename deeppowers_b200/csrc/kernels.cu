@@ -336,10 +336,10 @@ cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inve
 
 template <int LOGN, int MODE>
 static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cudaStream_t st) {
-    // one limb of shared memory per CTA: 64 KiB (N <= 8192) -> three CTAs per SM; 128 KiB (N = 16384) -> one
-    constexpr int NT = LOGN <= 13 ? 256 : 512, MINB = LOGN <= 13 ? 3 : 1;
+    // at most 64 KiB of shared memory per CTA (N = 16384 is processed as two half-limbs) -> three CTAs per SM
+    constexpr int NT = 256, MINB = 3;
     auto kern = lc.ks_prof ? ks_fused_kernel<LOGN, NT, MINB, MODE, true> : ks_fused_kernel<LOGN, NT, MINB, MODE, false>;
-    const size_t smem = Geometry<LOGN>::LIMB_BYTES;
+    const size_t smem = LOGN <= 13 ? Geometry<LOGN>::LIMB_BYTES : Geometry<13>::LIMB_BYTES;
     static bool configured[2][64] = {};
     if (!configured[lc.ks_prof ? 1 : 0][lc.device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -108,20 +108,25 @@ DPFHE_HD void inv16(u64 (&x)[16], const LimbParams &p, TW tw) {
 // Thread `tid` of NT handles groups p = tid + g*NT.
 // BIN: lazy bound (in units of q) of the values at entry; the pass leaves fwd_bound_after(BIN, 4).
 
-template <int LOGN, int S0, int NT, int BIN>
-DPFHE_HD void fwd_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid) {
+// BLKS / blk0: the buffer holds BLKS consecutive 4096-coefficient blocks of the limb starting at block blk0
+// (the whole limb when BLKS = 2^K, blk0 = 0).  Every pass with S0 >= K stays inside one block, so twiddles use
+// the global group index while shared-memory indices are relative to the first resident block.
+template <int LOGN, int S0, int NT, int BIN, int BLKS>
+DPFHE_HD void fwd_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid, int blk0) {
     constexpr int NLO = LOGN - S0 - 4;
-    constexpr int NGROUPS = 1 << (LOGN - 4);
+    constexpr int NGROUPS = BLKS * 256;
     static_assert(NLO == 0 || NLO >= 4, "pass split must keep column accesses row-aligned");
+    static_assert(S0 >= LOGN - 12, "register passes operate inside 4096-coefficient blocks");
 #pragma unroll 1
-    for (int g = tid; g < NGROUPS; g += NT) {
+    for (int lg = tid; lg < NGROUPS; lg += NT) {
+        const int g = (blk0 << 8) + lg;
         const int lo = g & ((1 << NLO) - 1), hi = g >> NLO;
-        const int base = (hi << (LOGN - S0)) + lo;
+        const int base = (hi << (LOGN - S0)) + lo - (blk0 << 12);
         u64 x[16];
         if (NLO == 0) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(g * 8 + c)];
+                U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lg * 8 + c)];
                 x[2 * c] = v.x;
                 x[2 * c + 1] = v.y;
             }
@@ -136,7 +141,7 @@ DPFHE_HD void fwd_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParam
                 U64x2 v;
                 v.x = x[2 * c];
                 v.y = x[2 * c + 1];
-                reinterpret_cast<U64x2 *>(buf)[swz_chunk(g * 8 + c)] = v;
+                reinterpret_cast<U64x2 *>(buf)[swz_chunk(lg * 8 + c)] = v;
             }
         } else {
 #pragma unroll
@@ -145,20 +150,22 @@ DPFHE_HD void fwd_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParam
     }
 }
 
-template <int LOGN, int S0, int NT>
-DPFHE_HD void inv_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid) {
+template <int LOGN, int S0, int NT, int BLKS>
+DPFHE_HD void inv_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid, int blk0) {
     constexpr int NLO = LOGN - S0 - 4;
-    constexpr int NGROUPS = 1 << (LOGN - 4);
+    constexpr int NGROUPS = BLKS * 256;
     static_assert(NLO == 0 || NLO >= 4, "pass split must keep column accesses row-aligned");
+    static_assert(S0 >= LOGN - 12, "register passes operate inside 4096-coefficient blocks");
 #pragma unroll 1
-    for (int g = tid; g < NGROUPS; g += NT) {
+    for (int lg = tid; lg < NGROUPS; lg += NT) {
+        const int g = (blk0 << 8) + lg;
         const int lo = g & ((1 << NLO) - 1), hi = g >> NLO;
-        const int base = (hi << (LOGN - S0)) + lo;
+        const int base = (hi << (LOGN - S0)) + lo - (blk0 << 12);
         u64 x[16];
         if (NLO == 0) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(g * 8 + c)];
+                U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lg * 8 + c)];
                 x[2 * c] = v.x;
                 x[2 * c + 1] = v.y;
             }
@@ -173,7 +180,7 @@ DPFHE_HD void inv_pass(u64 *buf, const Twiddle *__restrict__ tw, const LimbParam
                 U64x2 v;
                 v.x = x[2 * c];
                 v.y = x[2 * c + 1];
-                reinterpret_cast<U64x2 *>(buf)[swz_chunk(g * 8 + c)] = v;
+                reinterpret_cast<U64x2 *>(buf)[swz_chunk(lg * 8 + c)] = v;
             }
         } else {
 #pragma unroll
@@ -233,11 +240,11 @@ DPFHE_HD void fwd_load_stage(u64 *buf, const Twiddle *__restrict__ tw, const Lim
     }
 }
 
-// Inverse counterpart: reads shared memory (values in [0,2q)), applies the K outermost
-// Gentleman-Sande stages with N^-1 folded into the very last one, and hands canonical
-// chunks to DST(chunk_index, U64x2).
-template <int LOGN, int NT, class DST>
-DPFHE_HD void inv_store_stage(const u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid, DST dst) {
+// Inverse counterpart: SRC(chunk_index) yields the chunks left by the register passes (values in [0,2q));
+// applies the K outermost Gentleman-Sande stages with N^-1 folded into the very last one, and hands
+// canonical chunks to DST(chunk_index, U64x2).
+template <int LOGN, int NT, class SRC, class DST>
+DPFHE_HD void inv_outer_stage(const Twiddle *__restrict__ tw, const LimbParams &p, int tid, SRC src, DST dst) {
     constexpr int K = LOGN - 12;
     constexpr int NB = 1 << K;
     constexpr int CPB = (1 << (LOGN - 1)) / NB;
@@ -246,7 +253,7 @@ DPFHE_HD void inv_store_stage(const u64 *buf, const Twiddle *__restrict__ tw, co
         u64 x[NB][2];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(b * CPB + c)];
+            U64x2 v = src(b * CPB + c);
             x[b][0] = v.x;
             x[b][1] = v.y;
         }
@@ -288,6 +295,45 @@ DPFHE_HD void inv_store_stage(const u64 *buf, const Twiddle *__restrict__ tw, co
     }
 }
 
+template <int LOGN, int NT, class DST>
+DPFHE_HD void inv_store_stage(const u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid, DST dst) {
+    inv_outer_stage<LOGN, NT>(tw, p, tid, [&](int c) { return reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)]; }, dst);
+}
+
+// Half-limb variant of fwd_load_stage for N = 16384 (K = 2, four blocks): reads all four input blocks but keeps
+// only the two output blocks {2h, 2h+1} of the outer radix-4 step (3 multiplications per column instead of 4),
+// so the register passes run on 64 KiB of shared memory and three CTAs fit an SM.
+template <int LOGN, int NT, bool IN_REDUCE, class SRC>
+DPFHE_HD void fwd_load_stage_half(u64 *buf, const Twiddle *__restrict__ tw, const LimbParams &p, int tid, SRC src, int h) {
+    static_assert(LOGN == 14, "the half-limb load stage is written for K = 2");
+    constexpr int CPB = 1 << (LOGN - 3);   // chunks per block: (N/2) / 4
+    const Twiddle w0 = tw[tw_pos<LOGN>(0, 0)], w1 = tw[tw_pos<LOGN>(1, h)];
+#pragma unroll 1
+    for (int c = tid; c < CPB; c += NT) {
+        u64 x[4][2];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const U64x2 v = src(b * CPB + c);
+            x[b][0] = IN_REDUCE ? word_reduce(v.x, p) : v.x;
+            x[b][1] = IN_REDUCE ? word_reduce(v.y, p) : v.y;
+        }
+        U64x2 o0, o1;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            // stage 0 pairs (0,2) and (1,3); half 0 keeps the sums, half 1 the differences
+            const u64 t02 = shoup_lazy(x[2][e], w0.x, w0.y, p), t13 = shoup_lazy(x[3][e], w0.x, w0.y, p);
+            const u64 a = h == 0 ? x[0][e] + t02 : x[0][e] + p.q2 - t02;
+            const u64 b = h == 0 ? x[1][e] + t13 : x[1][e] + p.q2 - t13;
+            // stage 1 pairs (2h, 2h+1) with the twiddle of group h
+            const u64 t = shoup_lazy(b, w1.x, w1.y, p);
+            (e == 0 ? o0.x : o0.y) = a + t;
+            (e == 0 ? o1.x : o1.y) = a + p.q2 - t;
+        }
+        reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = o0;
+        reinterpret_cast<U64x2 *>(buf)[swz_chunk(CPB + c)] = o1;
+    }
+}
+
 // ---- whole-limb drivers --------------------------------------------------------------
 // The CTA policy provides three barrier scopes (all of them "run f(tid) for every thread, then sync"):
 //   cta.par(f)       whole CTA                     (__syncthreads)
@@ -304,23 +350,33 @@ template <int LOGN, int BIN>
 DPFHE_HD constexpr int fwd_out_bound() {
     return fwd_bound_after(BIN, LOGN);
 }
-template <int LOGN, int NT, int BIN, class CTA>
-DPFHE_HD void fwd_passes(CTA &cta, u64 *buf, const Twiddle *tw, const LimbParams &p) {
+template <int LOGN, int NT, int BIN, int BLKS, class CTA>
+DPFHE_HD void fwd_passes_blk(CTA &cta, u64 *buf, const Twiddle *tw, const LimbParams &p, int blk0) {
     constexpr int K = LOGN - 12;
     constexpr int B0 = fwd_bound_after(BIN, K), B1 = fwd_bound_after(BIN, K + 4), B2 = fwd_bound_after(BIN, K + 8);
     static_assert(BIN + 2 * K <= 16, "load stage applies no conditional subtraction");
     static_assert(NT % 32 == 0 && (NT >= 256 ? NT % 256 == 0 : true), "thread count must tile the barrier domains");
-    cta.par_dom([&](int tid) { fwd_pass<LOGN, K, NT, B0>(buf, tw, p, tid); });
-    cta.par_warp([&](int tid) { fwd_pass<LOGN, K + 4, NT, B1>(buf, tw, p, tid); });
-    cta.par([&](int tid) { fwd_pass<LOGN, K + 8, NT, B2>(buf, tw, p, tid); });
+    static_assert(BLKS == (1 << K) || NT <= 256, "partial-limb buffers use whole-CTA barriers");
+    cta.par_dom([&](int tid) { fwd_pass<LOGN, K, NT, B0, BLKS>(buf, tw, p, tid, blk0); });
+    cta.par_warp([&](int tid) { fwd_pass<LOGN, K + 4, NT, B1, BLKS>(buf, tw, p, tid, blk0); });
+    cta.par([&](int tid) { fwd_pass<LOGN, K + 8, NT, B2, BLKS>(buf, tw, p, tid, blk0); });
 }
-// inverse: buf holds [0,2q) values in bit-reversed order; afterwards run inv_store_stage
+template <int LOGN, int NT, int BIN, class CTA>
+DPFHE_HD void fwd_passes(CTA &cta, u64 *buf, const Twiddle *tw, const LimbParams &p) {
+    fwd_passes_blk<LOGN, NT, BIN, (1 << (LOGN - 12))>(cta, buf, tw, p, 0);
+}
+// inverse: buf holds [0,2q) values in bit-reversed order; afterwards run inv_store_stage / inv_outer_stage
+template <int LOGN, int NT, int BLKS, class CTA>
+DPFHE_HD void inv_passes_blk(CTA &cta, u64 *buf, const Twiddle *itw, const LimbParams &p, int blk0) {
+    constexpr int K = LOGN - 12;
+    static_assert(BLKS == (1 << K) || NT <= 256, "partial-limb buffers use whole-CTA barriers");
+    cta.par_warp([&](int tid) { inv_pass<LOGN, K + 8, NT, BLKS>(buf, itw, p, tid, blk0); });
+    cta.par_dom([&](int tid) { inv_pass<LOGN, K + 4, NT, BLKS>(buf, itw, p, tid, blk0); });
+    cta.par([&](int tid) { inv_pass<LOGN, K, NT, BLKS>(buf, itw, p, tid, blk0); });
+}
 template <int LOGN, int NT, class CTA>
 DPFHE_HD void inv_passes(CTA &cta, u64 *buf, const Twiddle *itw, const LimbParams &p) {
-    constexpr int K = LOGN - 12;
-    cta.par_warp([&](int tid) { inv_pass<LOGN, K + 8, NT>(buf, itw, p, tid); });
-    cta.par_dom([&](int tid) { inv_pass<LOGN, K + 4, NT>(buf, itw, p, tid); });
-    cta.par([&](int tid) { inv_pass<LOGN, K, NT>(buf, itw, p, tid); });
+    inv_passes_blk<LOGN, NT, (1 << (LOGN - 12))>(cta, buf, itw, p, 0);
 }
 
 }  // namespace dpfhe

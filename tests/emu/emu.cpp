@@ -159,7 +159,7 @@ int emu_ks(void *h, int mode, const uint64_t *a, const uint64_t *b, const uint64
     switch (e->hp.log_n) {
         case 12: DISPATCH(12, 256)
         case 13: DISPATCH(13, 256)
-        case 14: DISPATCH(14, 512)
+        case 14: DISPATCH(14, 256)
     }
     return -1;
 }
