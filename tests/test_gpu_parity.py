@@ -120,7 +120,7 @@ def test_pointwise_and_tensor_and_plain(ctxs, log_n, L):
     assert np.array_equal(host(out).reshape(a.shape), o.ct_mul_plain(a, pt))
 
 
-@pytest.mark.parametrize("log_n,L,batch", [(12, 2, 1), (12, 3, 5), (13, 4, 3), (13, 1, 2), (13, 4, 41), (14, 2, 3), (14, 8, 2), (12, 9, 3)])
+@pytest.mark.parametrize("log_n,L,batch", [(12, 2, 1), (12, 3, 5), (13, 4, 3), (13, 1, 2), (13, 4, 41), (14, 2, 3), (14, 8, 2), (12, 9, 3), (12, 16, 2)])
 def test_ct_mul_relin(ctxs, log_n, L, batch):
     c, o = ctxs(log_n, L)
     s = o.keygen_secret(21)
@@ -252,3 +252,44 @@ def test_config2_shape_properties(ctxs):
     c.ntt_inv(x, 2 * B)
     c.ntt_fwd(x, 2 * B)
     assert torch.equal(x, a)
+
+
+def test_host_pipeline_wraps_staging_slots(ctxs):
+    """host-buffer ct x ct on a batch spanning more chunks than staging slots (3): result must equal the device path"""
+    c, o = ctxs(13, 4)
+    B = 700
+    a = torch.empty((B, 2, 4, o.N), dtype=torch.int64, device="cuda")
+    b = torch.empty_like(a)
+    c.fill_uniform(71, a, 2 * B)
+    c.fill_uniform(72, b, 2 * B)
+    evk = o.fill_uniform(73, 8).reshape(4, 2, 4, o.N)
+    out_dev = torch.zeros_like(a)
+    c.ct_mul_relin(a, b, dev(evk), out_dev, B)
+    ha, hb = host(a).reshape(B, 2, 4, o.N).copy(), host(b).reshape(B, 2, 4, o.N).copy()
+    out_host = np.zeros_like(ha)
+    c.ct_mul_relin_host(ha, hb, evk, out_host)
+    assert np.array_equal(out_host, host(out_dev).reshape(out_host.shape))
+    for k in (0, 299, 699):
+        assert np.array_equal(out_host[k:k + 1], o.ct_mul_relin(ha[k:k + 1], hb[k:k + 1], evk))
+
+
+def test_explicit_stream_and_two_contexts(dp, ctxs):
+    """ops run on a caller-provided non-default stream; two contexts on one device do not share scratch"""
+    c, o = ctxs(12, 2)
+    c2 = dp.Context(12, 2)
+    s = o.keygen_secret(81)
+    evk = o.keygen_relin(82, 65537, s)
+    a = o.fill_uniform(83, 6).reshape(3, 2, 2, o.N)
+    b = o.fill_uniform(84, 6).reshape(3, 2, 2, o.N)
+    ref = o.ct_mul_relin(a, b, evk)
+    st = torch.cuda.Stream()
+    da, db, dk = dev(a), dev(b), dev(evk)
+    out1, out2 = torch.zeros_like(da), torch.zeros_like(da)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(st):
+        c.ct_mul_relin(da, db, dk, out1, 3, stream=st)
+        c2.ct_mul_relin(da, db, dk, out2, 3, stream=st)
+    st.synchronize()
+    assert np.array_equal(host(out1).reshape(ref.shape), ref)
+    assert np.array_equal(host(out2).reshape(ref.shape), ref)
+    c2.close()
