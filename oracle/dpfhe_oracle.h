@@ -12,7 +12,8 @@
  * (SURVEY.md §8c).  This oracle therefore restates the textbook constructions
  * frozen in DESIGN.md §2 (Harvey-style merged negacyclic NTT, Shoup/Barrett
  * modular multiply, per-limb-digit RNS key switching) and is pinned by its own
- * known-answer tests (tests/test_oracle_kat.py, tests/golden/).
+ * known-answer tests (tests/test_oracle_kat.py, tests/golden/) and cross-checked against sympy's
+ * independent number-theory / NTT-convolution code (tests/test_oracle_vs_sympy.py).
  *
  * Layout everywhere: uint64 little-endian, row-major
  *   polynomial  : [L][N]            (limb-major)
