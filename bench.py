@@ -253,6 +253,22 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B * ALGO_BYTES_CT_MUL,
                 "note": "64-bit modular integer work: integer issue (IMAD 2.0, IMAD.WIDE 2.55, IADD3 1.5 clk per warp-instruction per SM sub-partition, no ALU/IMAD overlap: profiles/r01/int_pipes*.txt) bounds this kernel below the HBM roofline; ncu: issue slots 56% busy (DESIGN.md section 6)"}
 
+    # Secondary, explanatory roofline: issued warp-instructions per second against what the integer pipes sustain for
+    # this instruction mix (profiles/r01/int_pipes_final.txt: IMAD.WIDE 2.55, IMAD 2.0, ALU ~1.4 clk per warp-instruction
+    # per SM sub-partition, not overlapping; mix and instructions per ciphertext from profiles/r01/ncu_full_summary.json).
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            instr_per_ct = float(json.load(f)["ks_fused_kernel_mul_relin"]["warp_instructions_per_unit"])
+        mix_clk = 0.28 * 2.55 + 0.24 * 2.0 + 0.40 * 1.4 + 0.08 * 1.0          # clocks per warp-instruction per sub-partition
+        sm_clock = 1.965e9
+        int_peak = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * sm_clock / mix_clk
+        achieved_int = (B / (ms_per_step * 1e-3)) * instr_per_ct
+        roofline["int_issue"] = {"achieved_warp_instr_per_s": achieved_int, "peak_warp_instr_per_s": int_peak,
+                                 "frac": achieved_int / int_peak, "warp_instr_per_ct_mult": instr_per_ct,
+                                 "source": "ncu smsp__inst_executed.sum per launch / batch; pipe costs from the committed microbenchmark"}
+    except Exception:
+        pass
+
     # standalone NTT on the same data (NTTs/s half of the BASELINE metric)
     ntt_ms = timed(lambda: ctx.ntt_fwd(a, 2 * B), max(3, args.steps // 2), 2) / max(3, args.steps // 2)
     n_ntt = 2 * B * L

@@ -80,6 +80,18 @@ __global__ void __launch_bounds__(1024) bench(unsigned long long *out, long long
 #pragma unroll
             for (int c = 0; c < CH; ++c) acc[c] = shoup_lazy(acc[c], p.ninv, p.ninv_s, p);
         }
+        if (OP == 21) {   // IMAD.WIDE without addend (RZ), result folded with one IADD3
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { unsigned lo, hi; asm volatile("{.reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0,%1}, t;}" : "=r"(lo), "=r"(hi) : "r"(r32[c]), "r"(b)); r32[c] = lo + hi; }
+        }
+        if (OP == 22) {   // IMAD.WIDE with a live 64-bit addend, result folded with one IADD3
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { unsigned lo, hi; asm volatile("{.reg .u64 t; mad.wide.u32 t, %2, %3, %4; mov.b64 {%0,%1}, t;}" : "=r"(lo), "=r"(hi) : "r"(r32[c]), "r"(b), "l"(acc[c])); r32[c] = lo + hi; }
+        }
+        if (OP == 23) {   // two IADD3 only (reference for the fold cost)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { r32[c] = r32[c] + b; asm volatile("" : "+r"(r32[c])); r32[c] = r32[c] + a; asm volatile("" : "+r"(r32[c])); }
+        }
         if (OP == 9) {
 #pragma unroll
             for (int c = 0; c < CH; c += 2) ct_bfly(acc[c], acc[c + 1], w, p);
@@ -150,6 +162,9 @@ int main() {
         run<18>("IMAD.WIDE reg*uniform (+LOP)", CH, p, threads);
         run<19>("IMAD.WIDE reg*reg (+LOP)", CH, p, threads);
         run<20>("shoup_lazy, uniform twiddle", CH, p, threads);
+        run<21>("IMAD.WIDE no addend + IADD3", CH, p, threads);
+        run<22>("IMAD.WIDE 64-bit addend + IADD3", CH, p, threads);
+        run<23>("2 x IADD3", CH, p, threads);
         run<11>("add.u32 (IADD3) x8", CH, p, threads);
         run<12>("4 IMAD + 4 IADD3 mixed", CH, p, threads);
         run<13>("4 IMAD.WIDE + 4 add.u64 mixed", CH, p, threads);
