@@ -55,6 +55,8 @@ struct dpfhe_ctx {
     size_t device_bytes = 0;
     uint64_t launches = 0;
     // staging for the host-buffer entry points (allocated on first use)
+    u64 *ms_tau = nullptr;                   // scratch of dpfhe_mod_switch_down: [n_polys][N]
+    size_t ms_tau_bytes = 0;
     u64 *stage_in[PIPE_DEPTH] = {}, *stage_out[PIPE_DEPTH] = {}, *stage_key = nullptr;
     size_t stage_in_bytes = 0, stage_out_bytes = 0, stage_key_bytes = 0;
     cudaEvent_t ev_h2d[PIPE_DEPTH] = {}, ev_comp[PIPE_DEPTH] = {}, ev_d2h[PIPE_DEPTH] = {};
@@ -251,6 +253,7 @@ void dpfhe_context_destroy(dpfhe_ctx *ctx) {
     cudaFree(ctx->lc.ks_mail);
     cudaFree(ctx->lc.ks_prof);
     cudaFree(ctx->stage_key);
+    cudaFree(ctx->ms_tau);
     for (int k = 0; k < PIPE_DEPTH; ++k) {
         cudaFree(ctx->stage_in[k]);
         cudaFree(ctx->stage_out[k]);
@@ -386,6 +389,46 @@ int dpfhe_ct_mul_plain_acc(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t 
     CHECK_PTR(d_ct); CHECK_PTR(d_pt); CHECK_PTR(d_acc);
     CU_TRY(launch_ct_mul_plain_acc(ctx->lc, d_ct, d_pt, d_acc, batch, pick(ctx, stream)));
     ctx->launches++;
+    return DPFHE_OK;
+}
+
+int dpfhe_mod_switch_down(dpfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, size_t n_polys, uint64_t t_plain, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (n_polys == 0) return DPFHE_OK;
+    CHECK_PTR(d_in); CHECK_PTR(d_out);
+    const unsigned L = ctx->hp.L;
+    if (L < 2) return fail(DPFHE_ERR_INVALID, "mod_switch_down needs at least two limbs");
+    if (d_in == d_out) return fail(DPFHE_ERR_INVALID, "output must not alias the input");
+    const uint64_t ql = ctx->hp.limbs[L - 1].lp.q;
+    if (t_plain >= ql || (t_plain && t_plain % ql == 0)) return fail(DPFHE_ERR_INVALID, "plaintext modulus must be below the dropped modulus");
+    const size_t need = n_polys * ctx->N() * 8;
+    if (need > ctx->ms_tau_bytes) {
+        CU_TRY(cudaStreamSynchronize(pick(ctx, stream)));   // the old scratch may still be in use on this stream
+        if (ctx->ms_tau) cudaFree(ctx->ms_tau);
+        ctx->ms_tau = nullptr;
+        ctx->ms_tau_bytes = 0;
+        CU_TRY(cudaMalloc(&ctx->ms_tau, need));
+        ctx->ms_tau_bytes = need;
+    }
+    MsConsts K;
+    memset(&K, 0, sizeof(K));
+    typedef unsigned __int128 u128;
+    auto shoup = [](uint64_t w, uint64_t q) { return (uint64_t)((((u128)w) << 64) / q); };
+    K.half = ql >> 1;
+    K.has_t = t_plain ? 1u : 0u;
+    K.tinv = t_plain ? host_powmod(t_plain % ql, ql - 2, ql) : 1;
+    K.tinv_s = shoup(K.tinv, ql);
+    for (unsigned i = 0; i + 1 < L; ++i) {
+        const uint64_t q = ctx->hp.limbs[i].lp.q;
+        K.qlm[i] = ql % q;
+        K.inv[i] = host_powmod(K.qlm[i], q - 2, q);
+        K.inv_s[i] = shoup(K.inv[i], q);
+        K.sinv[i] = t_plain ? host_mulmod(t_plain % q, K.inv[i], q) : K.inv[i];
+        K.sinv_s[i] = shoup(K.sinv[i], q);
+    }
+    CU_TRY(launch_mod_switch(ctx->lc, d_in, ctx->ms_tau, d_out, K, n_polys, pick(ctx, stream)));
+    ctx->launches += 2;
     return DPFHE_OK;
 }
 

@@ -401,4 +401,68 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
     }
 }
 
+// ---- modulus switching: drop the last limb -------------------------------------
+// Host-built constants of one call (passed by value in the kernel parameter block).
+struct MsConsts {
+    u64 inv[16], inv_s[16];     // q_last^-1 mod q_i and its Shoup companion
+    u64 sinv[16], sinv_s[16];   // s * q_last^-1 mod q_i (s = t_plain, or 1 for plain rounding)
+    u64 qlm[16];                // q_last mod q_i
+    u64 tinv, tinv_s;           // t_plain^-1 mod q_last (BGV correction), used when has_t
+    u64 half;                   // floor(q_last / 2)
+    u32 has_t;
+};
+
+// step 1, one polynomial: tau' = INTT_last(c[L-1]) (times t^-1 mod q_last for BGV), canonical, to `tau`
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void ms_tau_body(CTA &cta, u64 *buf, const u64 *last_limb, const Twiddle *itw, const LimbParams &p, u64 *tau, const MsConsts &K) {
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(last_limb);
+    cta.par([&](int tid) {
+        for (int c = tid; c < (1 << (LOGN - 1)); c += NT)
+            reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = ld_stream(src + c);
+    });
+    inv_passes<LOGN, NT>(cta, buf, itw, p);
+    U64x2 *dst = reinterpret_cast<U64x2 *>(tau);
+    const bool has_t = K.has_t != 0;
+    cta.par([&](int tid) {
+        inv_store_stage<LOGN, NT>(buf, itw, p, tid, [&](int c, const U64x2 &v) {
+            U64x2 r = v;
+            if (has_t) {
+                r.x = csub(shoup_lazy(v.x, K.tinv, K.tinv_s, p), p.q);
+                r.y = csub(shoup_lazy(v.y, K.tinv, K.tinv_s, p), p.q);
+            }
+            st_cg(dst + c, r);
+        });
+    });
+}
+
+// step 2, one (polynomial, kept limb i): out = (c[i] - s * NTT_i(centred(tau') mod q_i)) * q_last^-1 mod q_i
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void ms_limb_body(CTA &cta, u64 *buf, const u64 *tau, const u64 *c_limb, u64 *out_limb, const Twiddle *tw, const LimbParams &p,
+                           const MsConsts &K, u32 i) {
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(tau);
+    const u64 half = K.half, neg_ql = p.q - K.qlm[i];   // adding (q_i - q_last mod q_i) subtracts q_last
+    cta.par([&](int tid) {
+        fwd_load_stage<LOGN, NT, false>(buf, tw, p, tid, [&](int c) {
+            const U64x2 v = ld_cg(src + c);
+            U64x2 r;                                 // centred lift, lazy: < 3q (+ < q when tau' is "negative")
+            r.x = word_reduce(v.x, p) + (v.x > half ? neg_ql : 0);
+            r.y = word_reduce(v.y, p) + (v.y > half ? neg_ql : 0);
+            return r;
+        });
+    });
+    fwd_passes<LOGN, NT, 4>(cta, buf, tw, p);
+    const U64x2 *cin = reinterpret_cast<const U64x2 *>(c_limb);
+    U64x2 *dst = reinterpret_cast<U64x2 *>(out_limb);
+    const u64 inv = K.inv[i], inv_s = K.inv_s[i], sinv = K.sinv[i], sinv_s = K.sinv_s[i];
+    cta.par([&](int tid) {
+        for (int c = tid; c < (1 << (LOGN - 1)); c += NT) {
+            const U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)], cv = ld_stream(cin + c);
+            U64x2 r;   // c*inv - u*(s*inv): both Shoup products below 2q, difference kept positive with + 2q
+            r.x = canon4(shoup_lazy(cv.x, inv, inv_s, p) + p.q2 - shoup_lazy(u.x, sinv, sinv_s, p), p);
+            r.y = canon4(shoup_lazy(cv.y, inv, inv_s, p) + p.q2 - shoup_lazy(u.y, sinv, sinv_s, p), p);
+            st_stream(dst + c, r);
+        }
+    });
+}
+
 }  // namespace dpfhe

@@ -62,6 +62,36 @@ __global__ void __launch_bounds__(NT, MINB) ntt_kernel(u64 *data, const Twiddle 
     }
 }
 
+// ------------------------------------------------------------------ modulus switching (two launches)
+template <int LOGN, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ms_tau_kernel(const u64 *in, u64 *tau, const Twiddle *__restrict__ itw,
+                                                           const __grid_constant__ LimbTable lt, const __grid_constant__ MsConsts K,
+                                                           u32 L, size_t n_polys) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    constexpr size_t N = (size_t)1 << LOGN;
+    DevCta<NT> cta;
+    const LimbParams &p = lt.lp[L - 1];
+    for (size_t w = blockIdx.x; w < n_polys; w += gridDim.x)
+        ms_tau_body<LOGN, NT>(cta, buf, in + (w * L + (L - 1)) * N, itw + (size_t)(L - 1) * N, p, tau + w * N, K);
+}
+
+template <int LOGN, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ms_limb_kernel(const u64 *in, const u64 *tau, u64 *out, const Twiddle *__restrict__ tw,
+                                                            const __grid_constant__ LimbTable lt, const __grid_constant__ MsConsts K,
+                                                            u32 L, size_t n_items) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    constexpr size_t N = (size_t)1 << LOGN;
+    DevCta<NT> cta;
+    const u32 Lo = L - 1;
+    for (size_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const size_t poly = w / Lo;
+        const u32 i = (u32)(w % Lo);
+        ms_limb_body<LOGN, NT>(cta, buf, tau + poly * N, in + (poly * L + i) * N, out + (poly * Lo + i) * N, tw + (size_t)i * N, lt.lp[i], K, i);
+    }
+}
+
 // ------------------------------------------------------------------ fused key-switch family
 __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
     u32 v;
@@ -330,6 +360,36 @@ cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inve
                 default: return launch_ntt_dir<13, 256, 3>(lc, data, n_limbs, inverse, st);  // 13.2 M: 3 CTAs/SM (smem-limited), 80 regs
             }
         case 14: return launch_ntt_dir<14, 512, 1>(lc, data, n_limbs, inverse, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int LOGN, int NT, int MINB>
+static cudaError_t launch_ms_t(const LaunchCtx &lc, const u64 *in, u64 *tau, u64 *out, const MsConsts &K, size_t n_polys, cudaStream_t st) {
+    auto k1 = ms_tau_kernel<LOGN, NT, MINB>;
+    auto k2 = ms_limb_kernel<LOGN, NT, MINB>;
+    const size_t smem = Geometry<LOGN>::LIMB_BYTES;
+    static bool configured[64] = {};
+    if (!configured[lc.device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[lc.device & 63] = true;
+    }
+    const size_t n_items = n_polys * (lc.L - 1);
+    k1<<<(unsigned)(n_polys < 0x7fffffffull ? n_polys : 0x7fffffffull), NT, smem, st>>>(in, tau, lc.itw, lc.lt, K, lc.L, n_polys);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k2<<<(unsigned)(n_items < 0x7fffffffull ? n_items : 0x7fffffffull), NT, smem, st>>>(in, tau, out, lc.tw, lc.lt, K, lc.L, n_items);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mod_switch(const LaunchCtx &lc, const u64 *in, u64 *tau, u64 *out, const MsConsts &K, size_t n_polys, cudaStream_t st) {
+    if (n_polys == 0) return cudaSuccess;
+    switch (lc.log_n) {
+        case 12: return launch_ms_t<12, 256, 2>(lc, in, tau, out, K, n_polys, st);
+        case 13: return launch_ms_t<13, 256, 3>(lc, in, tau, out, K, n_polys, st);
+        case 14: return launch_ms_t<14, 512, 1>(lc, in, tau, out, K, n_polys, st);
     }
     return cudaErrorInvalidValue;
 }

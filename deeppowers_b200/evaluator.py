@@ -176,6 +176,10 @@ class Context:
     def rotate(self, ct, galois_elt, gk, out, batch, stream=None):
         self._chk(self._l.dpfhe_rotate(self._h, _ptr(ct), int(galois_elt), _ptr(gk), _ptr(out), batch, _stream(stream)))
 
+    def mod_switch_down(self, polys, out, n_polys, t_plain=0, stream=None):
+        """drop the last limb: [n_polys][L][N] -> [n_polys][L-1][N] (BGV correction when t_plain > 0)"""
+        self._chk(self._l.dpfhe_mod_switch_down(self._h, _ptr(polys), _ptr(out), n_polys, int(t_plain), _stream(stream)))
+
     def fill_uniform(self, seed, data, n_polys, first_poly=0, stream=None):
         self._chk(self._l.dpfhe_fill_uniform(self._h, int(seed), int(first_poly), _ptr(data), n_polys, _stream(stream)))
 

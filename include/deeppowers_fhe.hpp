@@ -115,6 +115,11 @@ public:
                                           void *stream = nullptr) {
         check(dpfhe_ct_mul_plain_acc(ctx_, ct, plain_eval, acc, count, stream));
     }
+    // drop the last limb of `count` ciphertexts (2*count polynomials); the result belongs to the first L-1 moduli
+    void mod_switch_to_next_device(const std::uint64_t *ct, std::uint64_t *out, std::size_t count, std::uint64_t plain_modulus = 0,
+                                   void *stream = nullptr) {
+        check(dpfhe_mod_switch_down(ctx_, ct, out, 2 * count, plain_modulus, stream));
+    }
     void keyswitch_device(const std::uint64_t *digits, const std::uint64_t *key, std::uint64_t *out, std::size_t count, void *stream = nullptr) {
         check(dpfhe_keyswitch(ctx_, digits, key, out, count, stream));
     }

@@ -54,6 +54,7 @@ def lib():
         "dpo_ct_mul_relin": (None, [vp, u64p, u64p, u64p, u64p, sz]),
         "dpo_ct_mul_plain": (None, [vp, u64p, u64p, u64p, sz]),
         "dpo_rotate": (None, [vp, u64p, u64, u64p, u64p, sz]),
+        "dpo_mod_switch_down": (None, [vp, u64p, u64, u64p, sz]),
         "dpo_galois_perm": (None, [vp, u64, u32p]),
         "dpo_galois_coeff": (None, [vp, u32, u64, u64p, u64p]),
         "dpo_splitmix64": (u64, [u64]),
@@ -168,6 +169,13 @@ class Oracle:
         ct = np.ascontiguousarray(ct, dtype=np.uint64)
         out = np.empty_like(ct)
         self._l.dpo_rotate(self._c, ct.reshape(-1), int(galois_elt), np.ascontiguousarray(gk).reshape(-1), out.reshape(-1), ct.size // (2 * self.P))
+        return out
+
+    def mod_switch_down(self, polys, t_plain=0):
+        """[n][L][N] -> [n][L-1][N]; decrypt the result with Oracle(logn, L-1, moduli[:-1])"""
+        x = np.ascontiguousarray(polys, dtype=np.uint64).reshape(-1, self.L, self.N)
+        out = np.empty((x.shape[0], self.L - 1, self.N), dtype=np.uint64)
+        self._l.dpo_mod_switch_down(self._c, x.reshape(-1), int(t_plain), out.reshape(-1), x.shape[0])
         return out
 
     def galois_perm(self, g):

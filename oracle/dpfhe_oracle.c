@@ -448,6 +448,43 @@ void dpo_rotate(const dpo_ctx *c, const uint64_t *ct, uint64_t g, const uint64_t
     free(perm);
 }
 
+/* DESIGN.md §2.9 mod_switch_down: drop the last limb q_last of every polynomial (BGV modulus switch when
+ * t_plain > 0, plain rounding "rescale" when t_plain == 0):
+ *   tau = INTT_last(c[L-1]);  w = centred(tau * t^-1 mod q_last)   (t = 0: w = centred(tau), s = 1; else s = t)
+ *   out[i] = (c[i] - s * NTT_i(w mod q_i)) * q_last^-1  mod q_i,   i < L-1.
+ * in: [n_polys][L][N], out: [n_polys][L-1][N], both evaluation form. */
+void dpo_mod_switch_down(const dpo_ctx *c, const uint64_t *in, uint64_t t_plain, uint64_t *out, size_t n_polys) {
+    const size_t N = c->N;
+    const unsigned L = c->L;
+    if (L < 2) return;
+    const uint64_t ql = c->q[L - 1], half = ql >> 1;
+    const uint64_t tinv = t_plain ? dpo_invmod(t_plain % ql, ql) : 1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long pidx = 0; pidx < (long)n_polys; pidx++) {
+        uint64_t *tau = (uint64_t *)malloc(N * 8), *u = (uint64_t *)malloc(N * 8);
+        const uint64_t *src = in + (size_t)pidx * L * N;
+        memcpy(tau, src + (size_t)(L - 1) * N, N * 8);
+        ntt_inv_limb(c, L - 1, tau);
+        if (t_plain)
+            for (size_t n = 0; n < N; n++) tau[n] = mulmod(tau[n], tinv, ql);
+        for (unsigned i = 0; i + 1 < L; i++) {
+            const uint64_t q = c->q[i];
+            const uint64_t inv = dpo_invmod(ql % q, q), sfac = t_plain ? t_plain % q : 1, qlm = ql % q;
+            for (size_t n = 0; n < N; n++) {
+                uint64_t r = tau[n] % q;
+                if (tau[n] > half) r = submod(r, qlm, q);      /* centred lift: tau - q_last */
+                u[n] = r;
+            }
+            ntt_fwd_limb(c, i, u);
+            uint64_t *dst = out + ((size_t)pidx * (L - 1) + i) * N;
+            for (size_t n = 0; n < N; n++)
+                dst[n] = mulmod(submod(src[(size_t)i * N + n], mulmod(u[n], sfac, q), q), inv, q);
+        }
+        free(tau);
+        free(u);
+    }
+}
+
 /* ------------------------------------------------------------------ synthetic data */
 
 uint64_t dpo_splitmix64(uint64_t x) {

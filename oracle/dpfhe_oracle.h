@@ -80,6 +80,9 @@ void dpo_ct_mul_plain(const dpo_ctx *, const uint64_t *ct, const uint64_t *pt, u
 /* galois_elt odd in [1, 2N); gk is the switch key for sigma_g(s) */
 void dpo_rotate(const dpo_ctx *, const uint64_t *ct, uint64_t galois_elt, const uint64_t *gk,
                 uint64_t *out, size_t batch);
+/* drop the last limb (BGV modulus switch for t_plain > 0, plain rounding for t_plain == 0);
+ * in [n_polys][L][N] -> out [n_polys][L-1][N] */
+void dpo_mod_switch_down(const dpo_ctx *, const uint64_t *in, uint64_t t_plain, uint64_t *out, size_t n_polys);
 /* permutation table of sigma_g in evaluation form: out[i] = in[perm[i]] */
 void dpo_galois_perm(const dpo_ctx *, uint64_t galois_elt, uint32_t *perm);
 /* sigma_g in coefficient form on one limb: out(X) = in(X^g) */

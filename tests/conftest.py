@@ -78,6 +78,12 @@ class Emu:
                               out.reshape(-1), batch, int(galois), G or 2 * self.L) == 0
         return out
 
+    def mod_switch(self, polys, t_plain=0):
+        x = np.ascontiguousarray(polys, dtype=np.uint64).reshape(-1, self.L, self.N)
+        out = np.zeros((x.shape[0], self.L - 1, self.N), dtype=np.uint64)
+        assert self._l.emu_mod_switch(self._h, x.reshape(-1), out.reshape(-1), x.shape[0], int(t_plain)) == 0
+        return out
+
     def scalar(self, name, l, *args):
         return int(getattr(self._l, "emu_" + name)(self._h, l, *[C.c_uint64(int(a)) for a in args]))
 
@@ -104,6 +110,7 @@ def emu_lib():
     lib.emu_root_powers.argtypes = [C.c_void_p, C.c_uint, C.c_int, _u64p]
     lib.emu_ntt.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int]
     lib.emu_ks.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint]
+    lib.emu_mod_switch.argtypes = [C.c_void_p, _u64p, _u64p, C.c_size_t, C.c_uint64]
     for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2)):
         f = getattr(lib, "emu_" + nm)
         f.restype = C.c_uint64

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "host_params.hpp"
@@ -162,6 +163,51 @@ int emu_ks(void *h, int mode, const uint64_t *a, const uint64_t *b, const uint64
         case 14: DISPATCH(14, 256)
     }
     return -1;
+}
+
+// modulus switching through the same bodies the device runs
+int emu_mod_switch(void *h, const uint64_t *in, uint64_t *out, size_t n_polys, uint64_t t_plain) {
+    Emu *e = (Emu *)h;
+    const unsigned L = e->hp.L;
+    const size_t N = (size_t)1 << e->hp.log_n;
+    if (L < 2) return -1;
+    typedef unsigned __int128 u128;
+    auto shoup = [](uint64_t w, uint64_t q) { return (uint64_t)((((u128)w) << 64) / q); };
+    const uint64_t ql = e->lp[L - 1].q;
+    MsConsts K;
+    memset(&K, 0, sizeof(K));
+    K.half = ql >> 1;
+    K.has_t = t_plain ? 1u : 0u;
+    K.tinv = t_plain ? host_powmod(t_plain % ql, ql - 2, ql) : 1;
+    K.tinv_s = shoup(K.tinv, ql);
+    for (unsigned i = 0; i + 1 < L; ++i) {
+        const uint64_t q = e->lp[i].q;
+        K.qlm[i] = ql % q;
+        K.inv[i] = host_powmod(K.qlm[i], q - 2, q);
+        K.inv_s[i] = shoup(K.inv[i], q);
+        K.sinv[i] = t_plain ? host_mulmod(t_plain % q, K.inv[i], q) : K.inv[i];
+        K.sinv_s[i] = shoup(K.sinv[i], q);
+    }
+    uint64_t *buf = aligned_new<uint64_t>(N), *tau = aligned_new<uint64_t>(N);
+    auto run = [&](auto logn_tag, auto nt_tag) {
+        constexpr int LOGN = decltype(logn_tag)::value, NT = decltype(nt_tag)::value;
+        HostCta cta{NT};
+        for (size_t w = 0; w < n_polys; ++w) {
+            ms_tau_body<LOGN, NT>(cta, buf, in + (w * L + (L - 1)) * N, e->itw + (size_t)(L - 1) * N, e->lp[L - 1], tau, K);
+            for (unsigned i = 0; i + 1 < L; ++i)
+                ms_limb_body<LOGN, NT>(cta, buf, tau, in + (w * L + i) * N, out + (w * (L - 1) + i) * N, e->tw + (size_t)i * N, e->lp[i], K, i);
+        }
+    };
+    int rc = 0;
+    switch (e->hp.log_n) {
+        case 12: run(std::integral_constant<int, 12>{}, std::integral_constant<int, 256>{}); break;
+        case 13: run(std::integral_constant<int, 13>{}, std::integral_constant<int, 256>{}); break;
+        case 14: run(std::integral_constant<int, 14>{}, std::integral_constant<int, 512>{}); break;
+        default: rc = -1;
+    }
+    free(buf);
+    free(tau);
+    return rc;
 }
 
 // scalar checks

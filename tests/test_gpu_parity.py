@@ -173,6 +173,41 @@ def test_semantics_decrypt_of_product(ctxs):
     assert np.array_equal(dec, exp)
 
 
+@pytest.mark.parametrize("log_n,L,n_polys,t", [(12, 2, 3, 0), (12, 3, 6, 65537), (13, 4, 10, 65537), (13, 4, 4, 167772161), (14, 8, 4, 65537), (12, 16, 2, 0)])
+def test_mod_switch_down(ctxs, log_n, L, n_polys, t):
+    c, o = ctxs(log_n, L)
+    x = edge_polys(o, n_polys, 71)
+    out = torch.full((n_polys, L - 1, o.N), -1, dtype=torch.int64, device="cuda")
+    c.mod_switch_down(dev(x), out, n_polys, t)
+    assert np.array_equal(host(out).reshape(n_polys, L - 1, o.N), o.mod_switch_down(x, t))
+    # a second call with more polynomials regrows the scratch
+    x2 = o.fill_uniform(72, 3 * n_polys)
+    out2 = torch.empty((3 * n_polys, L - 1, o.N), dtype=torch.int64, device="cuda")
+    c.mod_switch_down(dev(x2), out2, 3 * n_polys, t)
+    assert np.array_equal(host(out2).reshape(3 * n_polys, L - 1, o.N), o.mod_switch_down(x2, t))
+
+
+def test_semantics_multiply_then_mod_switch(ctxs, oracle_mod):
+    """Dec_{L-1}(modswitch(GPU ct x ct)) == m1*m2 * q_last^-1 mod t: the level-dropping step keeps the BGV meaning."""
+    c, o = ctxs(12, 3)
+    t = 65537
+    rng = np.random.default_rng(6)
+    s = o.keygen_secret(51)
+    evk = o.keygen_relin(52, t, s)
+    m1 = rng.integers(0, t, o.N).astype(np.uint64)
+    m2 = np.zeros(o.N, dtype=np.uint64)
+    m2[0] = 7
+    c1, c2 = o.encrypt(53, t, s, m1), o.encrypt(54, t, s, m2)
+    prod = torch.zeros((1, 2, 3, o.N), dtype=torch.int64, device="cuda")
+    c.ct_mul_relin(dev(c1[None]), dev(c2[None]), dev(evk), prod, 1)
+    low = torch.zeros((2, 2, o.N), dtype=torch.int64, device="cuda")
+    c.mod_switch_down(prod, low, 2, t)
+    o2 = oracle_mod.Oracle(12, 2, o.moduli[:2])
+    dec = o2.decrypt(np.ascontiguousarray(s[:2]), host(low).reshape(2, 2, o.N), t)
+    scale = pow(o.moduli[2], -1, t)
+    assert np.array_equal(dec, (7 * m1.astype(object) * scale % t).astype(np.uint64))
+
+
 def test_fill_uniform_matches_oracle(ctxs):
     c, o = ctxs(13, 4)
     d = torch.empty((3, 4, o.N), dtype=torch.int64, device="cuda")
@@ -203,6 +238,17 @@ def test_host_entry_points(ctxs):
     gk = o.keygen_galois(57, 65537, s, g)
     c.rotate_host(a, g, gk, out)
     assert np.array_equal(out, o.rotate(a, g, gk))
+
+
+def test_mod_switch_errors(dp, ctxs):
+    c, o = ctxs(12, 1)
+    x = torch.zeros((1, 1, o.N), dtype=torch.int64, device="cuda")
+    with pytest.raises(RuntimeError, match="two limbs"):
+        c.mod_switch_down(x, x.clone(), 1)
+    c3, _ = ctxs(12, 3)
+    y = torch.zeros((1, 3, o.N), dtype=torch.int64, device="cuda")
+    with pytest.raises(RuntimeError, match="alias"):
+        c3.mod_switch_down(y, y, 1)
 
 
 def test_errors_are_reported(dp, ctxs):

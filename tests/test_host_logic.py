@@ -78,6 +78,16 @@ def test_emulated_fused_keyswitch_bodies(make_emu, oracle_mod, log_n, L, batch, 
     assert np.array_equal(e.ks(2, a, None, gk, batch, galois=g, G=G), o.rotate(a, g, gk))
 
 
+@pytest.mark.parametrize("log_n,L,t", [(12, 3, 65537), (12, 2, 0), (13, 4, 167772161), (14, 2, 65537)])
+def test_emulated_mod_switch_bodies(make_emu, oracle_mod, log_n, L, t):
+    e, o = make_emu(log_n, L), oracle_mod.Oracle(log_n, L)
+    x = o.fill_uniform(9, 3)
+    q = np.array(o.moduli, dtype=np.uint64)
+    x[0] = (q - 1)[:, None]
+    x[1, -1] = 0
+    assert np.array_equal(e.mod_switch(x, t), o.mod_switch_down(x, t))
+
+
 def test_emulated_mixed_size_moduli(make_emu, oracle_mod):
     lib = oracle_mod.lib()
     two_n = 2 << 12
