@@ -254,6 +254,7 @@ void dpfhe_context_destroy(dpfhe_ctx *ctx) {
     cudaFree(ctx->lc.ks_prof);
     cudaFree(ctx->stage_key);
     cudaFree(ctx->ms_tau);
+    cudaFree(ctx->lc.ks_hyb);
     for (int k = 0; k < PIPE_DEPTH; ++k) {
         cudaFree(ctx->stage_in[k]);
         cudaFree(ctx->stage_out[k]);
@@ -372,6 +373,46 @@ int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, cons
     return ks_common(ctx, KS_ROTATE, d_ct, nullptr, d_gk, d_out, batch, galois_elt, stream);
 }
 
+// hybrid (special-prime) variants: the context's last limb is the special prime, data carries L-1 limbs
+static int ks_hybrid_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const uint64_t *b, const uint64_t *key, uint64_t *out,
+                            size_t batch, uint64_t galois, uint64_t t_plain, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    CHECK_PTR(a); CHECK_PTR(key); CHECK_PTR(out);
+    if (mode == KS_MUL_RELIN) CHECK_PTR(b);
+    const unsigned L = ctx->hp.L;
+    if (L < 2) return fail(DPFHE_ERR_INVALID, "hybrid key switching needs a special prime: create the context with at least two limbs");
+    if (t_plain >= ctx->hp.limbs[L - 1].lp.q) return fail(DPFHE_ERR_INVALID, "plaintext modulus must be below the special prime");
+    if (mode == KS_ROTATE) {
+        const uint64_t two_n = (uint64_t)2 << ctx->hp.log_n;
+        if (!(galois & 1) || galois >= two_n) return fail(DPFHE_ERR_INVALID, "galois element must be odd and < 2N");
+    }
+    if (out == a || out == b) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
+    if (!ctx->lc.ks_hyb) {
+        u64 *hyb = nullptr;
+        CU_TRY(cudaMalloc(&hyb, (ctx->lc.ks_slots / 2 + 1) * 4 * ctx->N() * sizeof(u64)));
+        ctx->lc.ks_hyb = hyb;
+    }
+    MsConsts K;
+    build_ms_consts(ctx->hp, t_plain, K);
+    CU_TRY(launch_ks_hybrid(ctx->lc, mode, a, b, key, out, batch, (u32)galois, K, pick(ctx, stream)));
+    ctx->launches += 2;   // key_prepare_kernel + ks_hybrid_kernel
+    return DPFHE_OK;
+}
+int dpfhe_keyswitch_hybrid(dpfhe_ctx *ctx, const uint64_t *d_d, const uint64_t *d_key, uint64_t *d_out, size_t batch, uint64_t t_plain,
+                           void *stream) {
+    return ks_hybrid_common(ctx, KS_PLAIN, d_d, nullptr, d_key, d_out, batch, 0, t_plain, stream);
+}
+int dpfhe_ct_mul_relin_hybrid(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, const uint64_t *d_evk, uint64_t *d_out,
+                              size_t batch, uint64_t t_plain, void *stream) {
+    return ks_hybrid_common(ctx, KS_MUL_RELIN, d_a, d_b, d_evk, d_out, batch, 0, t_plain, stream);
+}
+int dpfhe_rotate_hybrid(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk, uint64_t *d_out, size_t batch,
+                        uint64_t t_plain, void *stream) {
+    return ks_hybrid_common(ctx, KS_ROTATE, d_ct, nullptr, d_gk, d_out, batch, galois_elt, t_plain, stream);
+}
+
 int dpfhe_ct_mul_plain(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_pt, uint64_t *d_out, size_t batch, void *stream) {
     int rc = enter(ctx);
     if (rc) return rc;
@@ -412,21 +453,7 @@ int dpfhe_mod_switch_down(dpfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out,
         ctx->ms_tau_bytes = need;
     }
     MsConsts K;
-    memset(&K, 0, sizeof(K));
-    typedef unsigned __int128 u128;
-    auto shoup = [](uint64_t w, uint64_t q) { return (uint64_t)((((u128)w) << 64) / q); };
-    K.half = ql >> 1;
-    K.has_t = t_plain ? 1u : 0u;
-    K.tinv = t_plain ? host_powmod(t_plain % ql, ql - 2, ql) : 1;
-    K.tinv_s = shoup(K.tinv, ql);
-    for (unsigned i = 0; i + 1 < L; ++i) {
-        const uint64_t q = ctx->hp.limbs[i].lp.q;
-        K.qlm[i] = ql % q;
-        K.inv[i] = host_powmod(K.qlm[i], q - 2, q);
-        K.inv_s[i] = shoup(K.inv[i], q);
-        K.sinv[i] = t_plain ? host_mulmod(t_plain % q, K.inv[i], q) : K.inv[i];
-        K.sinv_s[i] = shoup(K.sinv[i], q);
-    }
+    build_ms_consts(ctx->hp, t_plain, K);
     CU_TRY(launch_mod_switch(ctx->lc, d_in, ctx->ms_tau, d_out, K, n_polys, pick(ctx, stream)));
     ctx->launches += 2;
     return DPFHE_OK;

@@ -147,4 +147,25 @@ std::string build_host_params(unsigned log_n, unsigned L, const uint64_t *moduli
     return "";
 }
 
+void build_ms_consts(const HostParams &hp, uint64_t t_plain, MsConsts &K) {
+    typedef unsigned __int128 u128;
+    auto shoup = [](uint64_t w, uint64_t q) { return (uint64_t)((((u128)w) << 64) / q); };
+    const unsigned L = hp.L;
+    const uint64_t ql = hp.limbs[L - 1].lp.q;
+    K = MsConsts();
+    K.half = ql >> 1;
+    K.has_t = t_plain ? 1u : 0u;
+    K.tinv = t_plain ? host_powmod(t_plain % ql, ql - 2, ql) : 1;
+    K.tinv_s = shoup(K.tinv, ql);
+    for (unsigned i = 0; i + 1 < L; ++i) {
+        const uint64_t q = hp.limbs[i].lp.q;
+        K.qlm[i] = ql % q;
+        K.qlm_s[i] = shoup(K.qlm[i], q);
+        K.inv[i] = host_powmod(K.qlm[i], q - 2, q);
+        K.inv_s[i] = shoup(K.inv[i], q);
+        K.sinv[i] = t_plain ? host_mulmod(t_plain % q, K.inv[i], q) : K.inv[i];
+        K.sinv_s[i] = shoup(K.sinv[i], q);
+    }
+}
+
 }  // namespace dpfhe

@@ -27,6 +27,9 @@ struct HostParams {
 // returns "" on success, else an error message
 std::string build_host_params(unsigned log_n, unsigned L, const uint64_t *moduli, HostParams &out);
 
+// constants for dropping the last limb of `hp` (t_plain = 0: plain rounding); requires hp.L >= 2 and t_plain < q_last
+void build_ms_consts(const HostParams &hp, uint64_t t_plain, MsConsts &K);
+
 uint64_t host_mulmod(uint64_t a, uint64_t b, uint64_t q);
 uint64_t host_powmod(uint64_t a, uint64_t e, uint64_t q);
 bool host_is_prime(uint64_t n);

@@ -161,8 +161,10 @@ struct KsArgs {
     u64 *scratch;        // [slots][2 parities][N]
     const Twiddle *tw;   // [L][N] forward tables
     const Twiddle *itw;  // [L][N] inverse tables
-    u32 L;
+    u32 L;               // limbs of a ciphertext polynomial = number of digits
     u32 galois;          // ROTATE only
+    u32 Lk;              // limbs of a key polynomial: L, or L + 1 with a special prime (hybrid)
+    u64 *hyb;            // hybrid only: [groups][4][N] special-limb accumulators (rows 0,1) and tau' (rows 2,3)
 };
 
 // operands of one 16-byte chunk position of phase 1, fetched one iteration ahead of their use
@@ -204,8 +206,11 @@ DPFHE_HD KsP1Operands ks_p1_fetch(const KsP1Pointers &ptr, u32 galois, int c) {
 }
 
 // digit + accumulator start values of one chunk position
-template <int MODE>
-DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only, u64 *buf, U64x2 *acc0, U64x2 *acc1, int c, int c_buf) {
+// HYB: the own terms are scaled by the special prime (pm = p_special mod q_i), so that the final division by it
+// leaves them unchanged: out = ((p*d + sum) - s*u) / p.
+template <int MODE, bool HYB = false>
+DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only, u64 *buf, U64x2 *acc0, U64x2 *acc1, int c, int c_buf,
+                          u64 pm = 0, u64 pm_s = 0) {
     U64x2 d, s0, s1;   // digit, own contributions to acc0 / acc1 (lazy < 3q)
     if (MODE == KS_MUL_RELIN) {
         tensor_coeff(o.a0.x, o.a1.x, o.b0.x, o.b1.x, p, s0.x, s1.x, d.x);
@@ -217,6 +222,14 @@ DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only,
         d = o.a1;
         s0 = o.a0;
         s1.x = s1.y = 0;
+    }
+    if (HYB && MODE != KS_PLAIN) {
+        s0.x = shoup_lazy(s0.x, pm, pm_s, p);
+        s0.y = shoup_lazy(s0.y, pm, pm_s, p);
+        if (MODE == KS_MUL_RELIN) {
+            s1.x = shoup_lazy(s1.x, pm, pm_s, p);
+            s1.y = shoup_lazy(s1.y, pm, pm_s, p);
+        }
     }
     // digit enters the inverse transform in [0,2q)
     reinterpret_cast<U64x2 *>(buf)[swz_chunk(c_buf)] = d;
@@ -233,17 +246,17 @@ DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only,
     st_cg(acc1 + c, r1);
 }
 
-template <int LOGN, int NT, int MODE, class CTA>
-DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot) {
+template <int LOGN, int NT, int MODE, bool HYB = false, class CTA>
+DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot, u64 pm = 0, u64 pm_s = 0) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     static_assert((NC / NT) % 2 == 0, "chunk loops may be unrolled by two (ping-pong operand buffers)");
-    const size_t P = (size_t)A.L * N;
+    const size_t P = (size_t)A.L * N, PK = HYB ? (size_t)A.Lk * N : P;
     U64x2 *acc0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N);
     U64x2 *acc1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
-    const bool only = A.L == 1;   // a single digit: no phase 2, write the canonical result here
+    const bool only = !HYB && A.L == 1;   // a single digit: no phase 2, write the canonical result here
     KsP1Pointers ptr;
     {
-        const size_t koff_b = ((size_t)i * 2 + 0) * P + (size_t)i * N, koff_a = ((size_t)i * 2 + 1) * P + (size_t)i * N;
+        const size_t koff_b = ((size_t)i * 2 + 0) * PK + (size_t)i * N, koff_a = ((size_t)i * 2 + 1) * PK + (size_t)i * N;
         ptr.kb = reinterpret_cast<const U64x2 *>(A.key + koff_b);
         ptr.ka = reinterpret_cast<const U64x2 *>(A.key + koff_a);
         ptr.kbs = reinterpret_cast<const U64x2 *>(A.key_s + koff_b);
@@ -266,7 +279,7 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
 #pragma unroll 1
                 for (int lc = tid; lc < n_c; lc += NT) {
                     const KsP1Operands o = ks_p1_fetch<LOGN, MODE>(ptr, galois, c_lo + lc);
-                    ks_p1_chunk<MODE>(o, p, only, buf, acc0, acc1, c_lo + lc, lc);
+                    ks_p1_chunk<MODE, HYB>(o, p, only, buf, acc0, acc1, c_lo + lc, lc, pm, pm_s);
                 }
             } else {
                 // rotate / key switch: the gathered operands have long latency and are few: fetch one chunk ahead
@@ -275,7 +288,7 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
                 for (int lc = tid; lc < n_c; lc += NT) {
                     const KsP1Operands o = nxt;
                     if (lc + NT < n_c) nxt = ks_p1_fetch<LOGN, MODE>(ptr, galois, c_lo + lc + NT);
-                    ks_p1_chunk<MODE>(o, p, only, buf, acc0, acc1, c_lo + lc, lc);
+                    ks_p1_chunk<MODE, HYB>(o, p, only, buf, acc0, acc1, c_lo + lc, lc, pm, pm_s);
                 }
             }
         });
@@ -285,7 +298,7 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
     if constexpr (LOGN <= 13) {
         build(0, NC);
         cta.mark(0);   // tensor / digit build + own key terms
-        if (A.L == 1) return;   // no other digit needs t
+        if (only) return;   // no other digit needs t
         inv_passes<LOGN, NT>(cta, buf, itw, p);
         cta.mark(1);   // inverse register passes
         cta.par([&](int tid) {
@@ -300,14 +313,14 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
         for (int h = 0; h < 2; ++h) {
             build(h * HC, HC);
             cta.mark(0);
-            if (A.L == 1) continue;
+            if (only) continue;
             inv_passes_blk<LOGN, NT, 2>(cta, buf, itw, p, 2 * h);
             cta.mark(1);
             cta.par([&](int tid) {
                 for (int lc = tid; lc < HC; lc += NT) st_cg(dst + h * HC + lc, reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lc)]);
             });
         }
-        if (A.L == 1) return;
+        if (only) return;
         cta.par([&](int tid) {
             inv_outer_stage<LOGN, NT>(itw, p, tid, [&](int c) { return ld_cg(dst + c); }, [&](int c, const U64x2 &v) { st_cg(dst + c, v); });
         });
@@ -316,19 +329,26 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
 }
 
 // t_src: the published t of digit j (N words, natural order, canonical mod q_j)
-template <int LOGN, int NT, class CTA>
-DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u32 j, u32 jj, const u64 *t_src) {
+// HYB: key polynomials carry A.Lk limbs and nothing is final here (the division by the special prime follows).
+// SPECIAL (hybrid only): limb i = A.L is the special prime; jj = 0 .. L-1 counts its digits and its accumulators
+// are the two scratch rows acc_rows[0..N), acc_rows[N..2N), which start from zero.
+template <int LOGN, int NT, bool HYB = false, bool SPECIAL = false, class CTA>
+DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u32 j, u32 jj, const u64 *t_src,
+                              u64 *acc_rows = nullptr) {
     constexpr int N = 1 << LOGN, NC = N / 2;
-    const size_t P = (size_t)A.L * N;
+    static_assert(HYB || !SPECIAL, "the special limb exists only in hybrid key switching");
+    const size_t P = (size_t)A.L * N, PK = HYB ? (size_t)A.Lk * N : P;
     const Twiddle *tw = A.tw + (size_t)i * N;
     const U64x2 *src = reinterpret_cast<const U64x2 *>(t_src);
-    const size_t koff_b = ((size_t)j * 2 + 0) * P + (size_t)i * N, koff_a = ((size_t)j * 2 + 1) * P + (size_t)i * N;
+    const size_t koff_b = ((size_t)j * 2 + 0) * PK + (size_t)i * N, koff_a = ((size_t)j * 2 + 1) * PK + (size_t)i * N;
     const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + koff_b), *ka = reinterpret_cast<const U64x2 *>(A.key + koff_a);
     const U64x2 *kbs = reinterpret_cast<const U64x2 *>(A.key_s + koff_b), *kas = reinterpret_cast<const U64x2 *>(A.key_s + koff_a);
-    U64x2 *acc0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N);
-    U64x2 *acc1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
-    // lazy accumulator bound: < 5q after phase 1, +2q per digit; every 4th digit one csub(8q) keeps it <= 16q
-    const bool trim = (jj & 3u) == 0u, last = jj + 1 == A.L;
+    U64x2 *acc0 = reinterpret_cast<U64x2 *>(SPECIAL ? acc_rows : A.out + ct * 2 * P + (size_t)i * N);
+    U64x2 *acc1 = reinterpret_cast<U64x2 *>(SPECIAL ? acc_rows + N : A.out + ct * 2 * P + P + (size_t)i * N);
+    // lazy accumulator bound: < 5q after phase 1 (0 for the special limb), +2q per digit; every 4th digit one
+    // csub(8q) keeps it <= 16q
+    const bool trim = SPECIAL ? ((jj + 1) & 3u) == 0u : (jj & 3u) == 0u, last = !HYB && jj + 1 == A.L;
+    const bool first = SPECIAL && jj == 0;
     struct MacOperands {
         U64x2 vb, va, vbs, vas, r0, r1;
     };
@@ -338,8 +358,12 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
         m.va = ld_keep(ka + c);
         m.vbs = ld_keep(kbs + c);
         m.vas = ld_keep(kas + c);
-        m.r0 = ld_cg(acc0 + c);
-        m.r1 = ld_cg(acc1 + c);
+        if (first) {
+            m.r0.x = m.r0.y = m.r1.x = m.r1.y = 0;
+        } else {
+            m.r0 = ld_cg(acc0 + c);
+            m.r1 = ld_cg(acc1 + c);
+        }
         return m;
     };
     // c: chunk of the limb (key / accumulator position); c_buf: where its transform output sits in shared memory
@@ -402,67 +426,96 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
 }
 
 // ---- modulus switching: drop the last limb -------------------------------------
-// Host-built constants of one call (passed by value in the kernel parameter block).
-struct MsConsts {
-    u64 inv[16], inv_s[16];     // q_last^-1 mod q_i and its Shoup companion
-    u64 sinv[16], sinv_s[16];   // s * q_last^-1 mod q_i (s = t_plain, or 1 for plain rounding)
-    u64 qlm[16];                // q_last mod q_i
-    u64 tinv, tinv_s;           // t_plain^-1 mod q_last (BGV correction), used when has_t
-    u64 half;                   // floor(q_last / 2)
-    u32 has_t;
-};
 
-// step 1, one polynomial: tau' = INTT_last(c[L-1]) (times t^-1 mod q_last for BGV), canonical, to `tau`
-template <int LOGN, int NT, class CTA>
-DPFHE_HD void ms_tau_body(CTA &cta, u64 *buf, const u64 *last_limb, const Twiddle *itw, const LimbParams &p, u64 *tau, const MsConsts &K) {
-    const U64x2 *src = reinterpret_cast<const U64x2 *>(last_limb);
-    cta.par([&](int tid) {
-        for (int c = tid; c < (1 << (LOGN - 1)); c += NT)
-            reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = ld_stream(src + c);
-    });
-    inv_passes<LOGN, NT>(cta, buf, itw, p);
+// step 1, one polynomial: tau' = INTT_last(c[L-1]) (times t^-1 mod q_last for BGV), canonical, to `tau`.
+// LAZY: the source row is L2-resident scratch written in this launch, with values below 16q (hybrid key switching);
+// otherwise canonical streamed input.  With 256 threads and N = 16384 the limb is transformed as two halves through
+// the `work` row (N words of scratch, may be the source row itself when that is scratch).
+template <int LOGN, int NT, bool LAZY = false, class CTA>
+DPFHE_HD void ms_tau_body(CTA &cta, u64 *buf, const u64 *row, u64 *work, const Twiddle *itw, const LimbParams &p, u64 *tau, const MsConsts &K) {
+    constexpr int NC = 1 << (LOGN - 1);
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(row);
+    auto fetch = [&](int c) {
+        if (!LAZY) return ld_stream(src + c);
+        U64x2 v = ld_cg(src + c);   // < 16q  ->  [0, 2q), what the inverse passes expect
+        v.x = csub(word_reduce(v.x, p), p.q2);
+        v.y = csub(word_reduce(v.y, p), p.q2);
+        return v;
+    };
     U64x2 *dst = reinterpret_cast<U64x2 *>(tau);
     const bool has_t = K.has_t != 0;
-    cta.par([&](int tid) {
-        inv_store_stage<LOGN, NT>(buf, itw, p, tid, [&](int c, const U64x2 &v) {
-            U64x2 r = v;
-            if (has_t) {
-                r.x = csub(shoup_lazy(v.x, K.tinv, K.tinv_s, p), p.q);
-                r.y = csub(shoup_lazy(v.y, K.tinv, K.tinv_s, p), p.q);
-            }
-            st_cg(dst + c, r);
+    auto emit = [&](int c, const U64x2 &v) {
+        U64x2 r = v;
+        if (has_t) {
+            r.x = csub(shoup_lazy(v.x, K.tinv, K.tinv_s, p), p.q);
+            r.y = csub(shoup_lazy(v.y, K.tinv, K.tinv_s, p), p.q);
+        }
+        st_cg(dst + c, r);
+    };
+    if constexpr (LOGN <= 13 || NT >= 512) {
+        cta.par([&](int tid) {
+            for (int c = tid; c < NC; c += NT) reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = fetch(c);
         });
-    });
+        inv_passes<LOGN, NT>(cta, buf, itw, p);
+        cta.par([&](int tid) { inv_store_stage<LOGN, NT>(buf, itw, p, tid, emit); });
+    } else {
+        constexpr int HC = NC / 2;
+        U64x2 *wrk = reinterpret_cast<U64x2 *>(work);
+        for (int h = 0; h < 2; ++h) {
+            cta.par([&](int tid) {
+                for (int lc = tid; lc < HC; lc += NT) reinterpret_cast<U64x2 *>(buf)[swz_chunk(lc)] = fetch(h * HC + lc);
+            });
+            inv_passes_blk<LOGN, NT, 2>(cta, buf, itw, p, 2 * h);
+            cta.par([&](int tid) {
+                for (int lc = tid; lc < HC; lc += NT) st_cg(wrk + h * HC + lc, reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lc)]);
+            });
+        }
+        cta.par([&](int tid) { inv_outer_stage<LOGN, NT>(itw, p, tid, [&](int c) { return ld_cg(wrk + c); }, emit); });
+    }
 }
 
-// step 2, one (polynomial, kept limb i): out = (c[i] - s * NTT_i(centred(tau') mod q_i)) * q_last^-1 mod q_i
-template <int LOGN, int NT, class CTA>
+// step 2, one (polynomial, kept limb i): out = (c[i] - s * NTT_i(centred(tau') mod q_i)) * q_last^-1 mod q_i.
+// COHERENT: c[i] is an L2-resident lazy accumulator written in this launch (any 64-bit value; may be `out_limb`).
+template <int LOGN, int NT, bool COHERENT = false, class CTA>
 DPFHE_HD void ms_limb_body(CTA &cta, u64 *buf, const u64 *tau, const u64 *c_limb, u64 *out_limb, const Twiddle *tw, const LimbParams &p,
                            const MsConsts &K, u32 i) {
+    constexpr int NC = 1 << (LOGN - 1);
     const U64x2 *src = reinterpret_cast<const U64x2 *>(tau);
     const u64 half = K.half, neg_ql = p.q - K.qlm[i];   // adding (q_i - q_last mod q_i) subtracts q_last
-    cta.par([&](int tid) {
-        fwd_load_stage<LOGN, NT, false>(buf, tw, p, tid, [&](int c) {
-            const U64x2 v = ld_cg(src + c);
-            U64x2 r;                                 // centred lift, lazy: < 3q (+ < q when tau' is "negative")
-            r.x = word_reduce(v.x, p) + (v.x > half ? neg_ql : 0);
-            r.y = word_reduce(v.y, p) + (v.y > half ? neg_ql : 0);
-            return r;
-        });
-    });
-    fwd_passes<LOGN, NT, 4>(cta, buf, tw, p);
+    auto lift = [&](int c) {
+        const U64x2 v = ld_cg(src + c);
+        U64x2 r;                                 // centred lift, lazy: < 3q (+ < q when tau' is "negative")
+        r.x = word_reduce(v.x, p) + (v.x > half ? neg_ql : 0);
+        r.y = word_reduce(v.y, p) + (v.y > half ? neg_ql : 0);
+        return r;
+    };
     const U64x2 *cin = reinterpret_cast<const U64x2 *>(c_limb);
     U64x2 *dst = reinterpret_cast<U64x2 *>(out_limb);
     const u64 inv = K.inv[i], inv_s = K.inv_s[i], sinv = K.sinv[i], sinv_s = K.sinv_s[i];
-    cta.par([&](int tid) {
-        for (int c = tid; c < (1 << (LOGN - 1)); c += NT) {
-            const U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)], cv = ld_stream(cin + c);
-            U64x2 r;   // c*inv - u*(s*inv): both Shoup products below 2q, difference kept positive with + 2q
-            r.x = canon4(shoup_lazy(cv.x, inv, inv_s, p) + p.q2 - shoup_lazy(u.x, sinv, sinv_s, p), p);
-            r.y = canon4(shoup_lazy(cv.y, inv, inv_s, p) + p.q2 - shoup_lazy(u.y, sinv, sinv_s, p), p);
-            st_stream(dst + c, r);
+    // c: chunk of the limb; c_buf: where its transform output sits in shared memory
+    auto finish = [&](int c, int c_buf) {
+        const U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c_buf)], cv = COHERENT ? ld_cg(cin + c) : ld_stream(cin + c);
+        U64x2 r;   // c*inv - u*(s*inv): both Shoup products below 2q, difference kept positive with + 2q
+        r.x = canon4(shoup_lazy(cv.x, inv, inv_s, p) + p.q2 - shoup_lazy(u.x, sinv, sinv_s, p), p);
+        r.y = canon4(shoup_lazy(cv.y, inv, inv_s, p) + p.q2 - shoup_lazy(u.y, sinv, sinv_s, p), p);
+        st_stream(dst + c, r);
+    };
+    if constexpr (LOGN <= 13 || NT >= 512) {
+        cta.par([&](int tid) { fwd_load_stage<LOGN, NT, false>(buf, tw, p, tid, lift); });
+        fwd_passes<LOGN, NT, 4>(cta, buf, tw, p);
+        cta.par([&](int tid) {
+            for (int c = tid; c < NC; c += NT) finish(c, c);
+        });
+    } else {
+        constexpr int HC = NC / 2;
+        for (int h = 0; h < 2; ++h) {
+            cta.par([&](int tid) { fwd_load_stage_half<LOGN, NT, false>(buf, tw, p, tid, lift, h); });
+            fwd_passes_blk<LOGN, NT, 4, 2>(cta, buf, tw, p, 2 * h);
+            cta.par([&](int tid) {
+                for (int lc = tid; lc < HC; lc += NT) finish(h * HC + lc, lc);
+            });
         }
-    });
+    }
 }
 
 }  // namespace dpfhe

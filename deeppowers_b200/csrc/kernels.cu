@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(NT, MINB) ms_tau_kernel(const u64 *in, u64 *ta
     DevCta<NT> cta;
     const LimbParams &p = lt.lp[L - 1];
     for (size_t w = blockIdx.x; w < n_polys; w += gridDim.x)
-        ms_tau_body<LOGN, NT>(cta, buf, in + (w * L + (L - 1)) * N, itw + (size_t)(L - 1) * N, p, tau + w * N, K);
+        ms_tau_body<LOGN, NT>(cta, buf, in + (w * L + (L - 1)) * N, nullptr, itw + (size_t)(L - 1) * N, p, tau + w * N, K);
 }
 
 template <int LOGN, int NT, int MINB>
@@ -195,6 +195,84 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
         cta.prof[14] += t_end - t_start;
         cta.prof[15] += (unsigned long long)clock64() - c_start;
+    }
+}
+
+// Hybrid (special-prime) variant, DESIGN.md §2.10.  A group is L + 1 CTAs: CTA i < L owns ciphertext limb i,
+// CTA L owns the special limb.  Per ciphertext:
+//   limb CTA    tensor/permute, p*own terms + first key term, INTT, publish digit        (as above)
+//               L-1 x [lift + NTT + MAC]                                                  (as above, nothing final)
+//               wait for tau'; 2 x [centred lift + NTT], out = (acc - s*u) / p           (ms_limb_body)
+//   special CTA L x [lift + NTT_p + MAC into its scratch rows]; 2 x INTT_p (* t^-1) -> tau', publish
+// Both roles run six transforms per ciphertext at L = 4.  tau' and the digits are exchanged through L2 scratch under
+// the same release/acquire flags; a limb CTA cannot start its next ciphertext before tau' of this one arrived and
+// the special CTA needs every digit of a round, which orders all reuse of the scratch rows.
+template <int LOGN, int NT, int MINB, int MODE>
+__global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __grid_constant__ LimbTable lt, const __grid_constant__ MsConsts K,
+                                                             size_t batch, u32 *flags, u32 epoch, u32 *ticket, u64 *mail) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr size_t N = (size_t)1 << LOGN;
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    DevCta<NT> cta;
+    __shared__ u32 s_ct;
+    const u32 L = A.L, GS = L + 1, slot = blockIdx.x, i = slot % GS, group = slot / GS, base = slot - i;
+    const bool special = i == L;
+    const LimbParams &p = lt.lp[i];
+    u64 *hyb = A.hyb + (size_t)group * 4 * N;   // rows 0,1: special-limb accumulators; rows 2,3: tau'
+    auto wait_for = [&](u32 sib, u32 tag) {
+        if (threadIdx.x == 0) {
+            while ((int)(ld_acquire_u32(flags + sib) - tag) < 0) {
+            }
+        }
+        __syncthreads();
+    };
+    auto publish = [&](u32 tag) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_u32(flags + slot, tag);
+    };
+    for (u32 round = 0;; ++round) {
+        const u32 tag = epoch + round + 1;
+        if (threadIdx.x == 0) {
+            if (i == 0) {
+                const u32 t = atomicAdd(ticket, 1u);
+                st_release_u64(mail + group, ((u64)tag << 32) | t);
+                s_ct = t;
+            } else {
+                u64 m;
+                do m = ld_acquire_u64(mail + group);
+                while ((u32)(m >> 32) != tag);
+                s_ct = (u32)m;
+            }
+        }
+        __syncthreads();
+        const size_t ct = s_ct;
+        if (ct >= batch) break;
+        const u32 parity = round & 1u;
+        if (!special) {
+            ks_phase1<LOGN, NT, MODE, true>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N, K.qlm[i], K.qlm_s[i]);
+            publish(tag);
+            for (u32 jj = 1; jj < L; ++jj) {
+                const u32 j = (i + jj) % L;
+                wait_for(base + j, tag);
+                ks_phase2_digit<LOGN, NT, true, false>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)(base + j) * 2 + parity) * N);
+            }
+            wait_for(base + L, tag);
+            const size_t P = (size_t)L * N;
+            for (u32 c = 0; c < 2; ++c) {
+                u64 *row = A.out + ct * 2 * P + c * P + (size_t)i * N;   // lazy accumulator -> final value, in place
+                ms_limb_body<LOGN, NT, true>(cta, buf, hyb + (2 + c) * N, row, row, A.tw + (size_t)i * N, p, K, i);
+            }
+        } else {
+            for (u32 jj = 0; jj < L; ++jj) {
+                const u32 j = (group + jj) % L;   // groups start at different digits: spreads the key-column reads
+                wait_for(base + j, tag);
+                ks_phase2_digit<LOGN, NT, true, true>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)(base + j) * 2 + parity) * N, hyb);
+            }
+            for (u32 c = 0; c < 2; ++c)
+                ms_tau_body<LOGN, NT, true>(cta, buf, hyb + c * N, hyb + c * N, A.itw + (size_t)i * N, p, hyb + (2 + c) * N, K);
+            publish(tag);
+        }
     }
 }
 
@@ -436,6 +514,77 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
     return e;
 }
 
+template <int LOGN, int MODE>
+static cudaError_t launch_ks_hybrid_t(LaunchCtx &lc, const KsArgs &A, const MsConsts &K, size_t batch, cudaStream_t st) {
+    constexpr int NT = 256, MINB = 3;
+    auto kern = ks_hybrid_kernel<LOGN, NT, MINB, MODE>;
+    const size_t smem = LOGN <= 13 ? Geometry<LOGN>::LIMB_BYTES : Geometry<13>::LIMB_BYTES;
+    static bool configured[64] = {};
+    if (!configured[lc.device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[lc.device & 63] = true;
+    }
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    if (lc.ks_occ_cap > 0 && occ > lc.ks_occ_cap) occ = lc.ks_occ_cap;
+    const size_t GS = lc.L;   // group size: L-1 ciphertext limbs + the special limb
+    size_t G = (size_t)lc.num_sms * occ;
+    if (G > lc.ks_slots) G = lc.ks_slots;
+    G = (G / GS) * GS;
+    if (G > batch * GS) G = batch * GS;
+    if (G == 0) return cudaErrorInvalidConfiguration;
+    const u32 rounds = (u32)(batch + 1);
+    cudaError_t em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
+    if (em != cudaSuccess) return em;
+    KsArgs args = A;
+    LimbTable lt = lc.lt;
+    MsConsts consts = K;
+    size_t batch_arg = batch;
+    u32 *flags = lc.ks_flags;
+    u32 epoch = lc.ks_epoch;
+    u32 *ticket = lc.ks_ticket;
+    u64 *mail = lc.ks_mail;
+    void *params[] = {&args, &lt, &consts, &batch_arg, &flags, &epoch, &ticket, &mail};
+    e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)G), dim3(NT), params, smem, st);
+    lc.ks_epoch += rounds;
+    return e;
+}
+
+// data has L-1 limbs, the key [L-1][2][L][N]; lc.ks_hyb must hold (ks_slots / 2 + 1) * 4 * N words
+cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, u32 galois,
+                             const MsConsts &K, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    if (lc.L < 2 || !lc.ks_hyb) return cudaErrorInvalidValue;
+    {
+        const size_t n = (size_t)2 * (lc.L - 1) * lc.L << lc.log_n;
+        const unsigned grid = ew_grid(lc, n);
+        if (lc.log_n == 12) key_prepare_kernel<12><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        else if (lc.log_n == 13) key_prepare_kernel<13><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        else key_prepare_kernel<14><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    KsArgs A;
+    A.a = a; A.b = b; A.key = key; A.key_s = lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
+    A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L - 1; A.galois = galois; A.Lk = lc.L; A.hyb = lc.ks_hyb;
+#define KS_HYB_DISPATCH(LOGN)                                                                   \
+    switch (mode) {                                                                             \
+        case KS_MUL_RELIN: return launch_ks_hybrid_t<LOGN, KS_MUL_RELIN>(lc, A, K, batch, st);   \
+        case KS_PLAIN: return launch_ks_hybrid_t<LOGN, KS_PLAIN>(lc, A, K, batch, st);           \
+        case KS_ROTATE: return launch_ks_hybrid_t<LOGN, KS_ROTATE>(lc, A, K, batch, st);         \
+    }                                                                                           \
+    return cudaErrorInvalidValue;
+    switch (lc.log_n) {
+        case 12: KS_HYB_DISPATCH(12)
+        case 13: KS_HYB_DISPATCH(13)
+        case 14: KS_HYB_DISPATCH(14)
+    }
+    return cudaErrorNotSupported;
+}
+
 cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch,
                       u32 galois, cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
@@ -451,7 +600,7 @@ cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const
     }
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
-    A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L; A.galois = galois;
+    A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L; A.galois = galois; A.Lk = lc.L; A.hyb = nullptr;
 #define KS_DISPATCH(LOGN)                                                              \
     switch (mode) {                                                                    \
         case KS_MUL_RELIN: return launch_ks_t<LOGN, KS_MUL_RELIN>(lc, A, batch, st);   \

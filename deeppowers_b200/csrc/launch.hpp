@@ -27,6 +27,7 @@ struct LaunchCtx {
     u32 *ks_ticket = nullptr;         // next ciphertext index (reset per launch)
     u64 *ks_mail = nullptr;           // [ks_slots] per-group mailbox: (round tag << 32) | ciphertext index
     u64 *ks_key_s = nullptr;          // [L][2][L][N] Shoup companions of the current switch key
+    u64 *ks_hyb = nullptr;            // hybrid key switching: [ks_slots / 2 + 1][4][N], allocated at the first hybrid call
     size_t ks_slots = 0;
     u32 ks_epoch = 0;                 // rounds consumed so far (flag values already used)
     int ks_prefetch = 0;              // ciphertexts ahead for the bulk L2 prefetch of inputs (DPFHE_KS_PF), 0 = off
@@ -38,6 +39,8 @@ int query_num_sms(int dev);
 cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inverse, cudaStream_t st);
 cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch,
                       u32 galois, cudaStream_t st);
+cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, u32 galois,
+                             const MsConsts &K, cudaStream_t st);
 cudaError_t launch_pointwise_mul(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *out, size_t n_polys, cudaStream_t st);
 cudaError_t launch_mod_switch(const LaunchCtx &lc, const u64 *in, u64 *tau, u64 *out, const MsConsts &K, size_t n_polys, cudaStream_t st);
 cudaError_t launch_poly_add(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *out, size_t n_polys, cudaStream_t st);

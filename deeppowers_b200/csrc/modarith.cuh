@@ -203,6 +203,17 @@ DPFHE_HD u64 canon4(u64 x, const LimbParams &p) { return csub(csub(x, p.q2), p.q
 
 DPFHE_HD u64 mulmod(u64 a, u64 b, const LimbParams &p) { return canon4(mulmod_lazy(a, b, p), p); }
 
+// Modulus switching / special-prime division: constants of one call, built on the host
+// (host_params.cpp:build_ms_consts) and passed by value in the kernel parameter block.
+struct MsConsts {
+    u64 inv[16], inv_s[16];     // q_last^-1 mod q_i and its Shoup companion
+    u64 sinv[16], sinv_s[16];   // s * q_last^-1 mod q_i (s = t_plain, or 1 for plain rounding)
+    u64 qlm[16], qlm_s[16];     // q_last mod q_i and its Shoup companion (hybrid key switching scales by it)
+    u64 tinv, tinv_s;           // t_plain^-1 mod q_last (BGV correction), used when has_t
+    u64 half;                   // floor(q_last / 2)
+    u32 has_t;
+};
+
 // splitmix64 finaliser, the synthetic-data hash of DESIGN.md §5
 DPFHE_HD u64 splitmix64(u64 x) {
     u64 z = x + 0x9E3779B97F4A7C15ull;

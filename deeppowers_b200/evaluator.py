@@ -180,6 +180,16 @@ class Context:
         """drop the last limb: [n_polys][L][N] -> [n_polys][L-1][N] (BGV correction when t_plain > 0)"""
         self._chk(self._l.dpfhe_mod_switch_down(self._h, _ptr(polys), _ptr(out), n_polys, int(t_plain), _stream(stream)))
 
+    # hybrid key switching: this context's last limb is the special prime; data has L-1 limbs, keys [L-1][2][L][N]
+    def keyswitch_hybrid(self, d, key, out, batch, t_plain=0, stream=None):
+        self._chk(self._l.dpfhe_keyswitch_hybrid(self._h, _ptr(d), _ptr(key), _ptr(out), batch, int(t_plain), _stream(stream)))
+
+    def ct_mul_relin_hybrid(self, a, b, evk, out, batch, t_plain=0, stream=None):
+        self._chk(self._l.dpfhe_ct_mul_relin_hybrid(self._h, _ptr(a), _ptr(b), _ptr(evk), _ptr(out), batch, int(t_plain), _stream(stream)))
+
+    def rotate_hybrid(self, ct, galois_elt, gk, out, batch, t_plain=0, stream=None):
+        self._chk(self._l.dpfhe_rotate_hybrid(self._h, _ptr(ct), int(galois_elt), _ptr(gk), _ptr(out), batch, int(t_plain), _stream(stream)))
+
     def fill_uniform(self, seed, data, n_polys, first_poly=0, stream=None):
         self._chk(self._l.dpfhe_fill_uniform(self._h, int(seed), int(first_poly), _ptr(data), n_polys, _stream(stream)))
 

@@ -120,6 +120,16 @@ public:
                                    void *stream = nullptr) {
         check(dpfhe_mod_switch_down(ctx_, ct, out, 2 * count, plain_modulus, stream));
     }
+    // hybrid (special-prime) key switching: this evaluator's last limb is the special prime, ciphertexts carry
+    // limbs()-1 limbs and keys are [limbs()-1][2][limbs()][N]
+    void multiply_relin_hybrid_device(const std::uint64_t *a, const std::uint64_t *b, const std::uint64_t *relin_key, std::uint64_t *out,
+                                      std::size_t count, std::uint64_t plain_modulus = 0, void *stream = nullptr) {
+        check(dpfhe_ct_mul_relin_hybrid(ctx_, a, b, relin_key, out, count, plain_modulus, stream));
+    }
+    void rotate_hybrid_device(const std::uint64_t *ct, long steps, const std::uint64_t *galois_key, std::uint64_t *out, std::size_t count,
+                              std::uint64_t plain_modulus = 0, void *stream = nullptr) {
+        check(dpfhe_rotate_hybrid(ctx_, ct, galois_element(steps), galois_key, out, count, plain_modulus, stream));
+    }
     void keyswitch_device(const std::uint64_t *digits, const std::uint64_t *key, std::uint64_t *out, std::size_t count, void *stream = nullptr) {
         check(dpfhe_keyswitch(ctx_, digits, key, out, count, stream));
     }

@@ -117,6 +117,18 @@ int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, cons
 int dpfhe_mod_switch_down(dpfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, size_t n_polys, uint64_t t_plain,
                           void *stream);
 
+/* ---- hybrid (special-prime) key switching.  The context's LAST limb is the special prime p:
+ *      ciphertexts carry L-1 limbs ([batch][2][L-1][N]) and switch keys are [L-1 digits][2][L limbs][N], encrypting
+ *      p * g_j * target.  The key-switched pair is accumulated over all L limbs and divided by p (rounding as in
+ *      dpfhe_mod_switch_down, t_plain > 0 = BGV correction), which divides the key-switching noise by p.
+ *      Same fused persistent kernel family as the calls above; outputs must not alias inputs. ---- */
+int dpfhe_keyswitch_hybrid(dpfhe_ctx *ctx, const uint64_t *d_d, const uint64_t *d_key, uint64_t *d_out, size_t batch,
+                           uint64_t t_plain, void *stream);
+int dpfhe_ct_mul_relin_hybrid(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, const uint64_t *d_evk,
+                              uint64_t *d_out, size_t batch, uint64_t t_plain, void *stream);
+int dpfhe_rotate_hybrid(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk,
+                        uint64_t *d_out, size_t batch, uint64_t t_plain, void *stream);
+
 /* ---- synthetic data: x[k] = mulhi64(splitmix64(seed + k), q_limb),
  *      k = (first_poly + p)*L*N + l*N + n.  Fills [n_polys][L][N]. ---- */
 int dpfhe_fill_uniform(dpfhe_ctx *ctx, uint64_t seed, uint64_t first_poly, uint64_t *d_data,

@@ -55,6 +55,11 @@ def lib():
         "dpo_ct_mul_plain": (None, [vp, u64p, u64p, u64p, sz]),
         "dpo_rotate": (None, [vp, u64p, u64, u64p, u64p, sz]),
         "dpo_mod_switch_down": (None, [vp, u64p, u64, u64p, sz]),
+        "dpo_keyswitch_hybrid": (None, [vp, u64p, u64p, u64, u64p, u64p]),
+        "dpo_ct_mul_relin_hybrid": (None, [vp, u64p, u64p, u64p, u64, u64p, sz]),
+        "dpo_rotate_hybrid": (None, [vp, u64p, u64, u64p, u64, u64p, sz]),
+        "dpo_keygen_relin_hybrid": (None, [vp, u64, u64, u64p, u64p]),
+        "dpo_keygen_galois_hybrid": (None, [vp, u64, u64, u64p, u64, u64p]),
         "dpo_galois_perm": (None, [vp, u64, u32p]),
         "dpo_galois_coeff": (None, [vp, u32, u64, u64p, u64p]),
         "dpo_splitmix64": (u64, [u64]),
@@ -177,6 +182,38 @@ class Oracle:
         out = np.empty((x.shape[0], self.L - 1, self.N), dtype=np.uint64)
         self._l.dpo_mod_switch_down(self._c, x.reshape(-1), int(t_plain), out.reshape(-1), x.shape[0])
         return out
+
+    # hybrid (special-prime) key switching: this context's last limb is the special prime, data has L-1 limbs
+    def keyswitch_hybrid(self, d, key, t_plain=0):
+        c0 = np.empty((self.L - 1, self.N), dtype=np.uint64)
+        c1 = np.empty((self.L - 1, self.N), dtype=np.uint64)
+        self._l.dpo_keyswitch_hybrid(self._c, np.ascontiguousarray(d).reshape(-1), np.ascontiguousarray(key).reshape(-1), int(t_plain),
+                                     c0.reshape(-1), c1.reshape(-1))
+        return c0, c1
+
+    def ct_mul_relin_hybrid(self, a, b, evk, t_plain=0):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        self._l.dpo_ct_mul_relin_hybrid(self._c, a.reshape(-1), np.ascontiguousarray(b).reshape(-1), np.ascontiguousarray(evk).reshape(-1),
+                                        int(t_plain), out.reshape(-1), a.size // (2 * (self.L - 1) * self.N))
+        return out
+
+    def rotate_hybrid(self, ct, galois_elt, gk, t_plain=0):
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        out = np.empty_like(ct)
+        self._l.dpo_rotate_hybrid(self._c, ct.reshape(-1), int(galois_elt), np.ascontiguousarray(gk).reshape(-1), int(t_plain),
+                                  out.reshape(-1), ct.size // (2 * (self.L - 1) * self.N))
+        return out
+
+    def keygen_relin_hybrid(self, seed, t, s):
+        k = np.empty((self.L - 1, 2, self.L, self.N), dtype=np.uint64)
+        self._l.dpo_keygen_relin_hybrid(self._c, int(seed), int(t), s.reshape(-1), k.reshape(-1))
+        return k
+
+    def keygen_galois_hybrid(self, seed, t, s, g):
+        k = np.empty((self.L - 1, 2, self.L, self.N), dtype=np.uint64)
+        self._l.dpo_keygen_galois_hybrid(self._c, int(seed), int(t), s.reshape(-1), int(g), k.reshape(-1))
+        return k
 
     def galois_perm(self, g):
         p = np.empty(self.N, dtype=np.uint32)

@@ -318,9 +318,9 @@ void dpo_poly_add(const dpo_ctx *c, const uint64_t *a, const uint64_t *b, uint64
 }
 
 /* DESIGN.md §2.4 ct_tensor: d0 = a0*b0, d1 = a0*b1 + a1*b0, d2 = a1*b1 (pointwise, per limb). */
-static void ct_tensor_one(const dpo_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *d) {
-    size_t P = c->L * c->N;
-    for (unsigned l = 0; l < c->L; l++) {
+static void ct_tensor_limbs(const dpo_ctx *c, unsigned nl, const uint64_t *a, const uint64_t *b, uint64_t *d) {
+    size_t P = nl * c->N;
+    for (unsigned l = 0; l < nl; l++) {
         uint64_t q = c->q[l], r0 = c->br0[l], r1 = c->br1[l];
         for (size_t j = 0; j < c->N; j++) {
             size_t o = l * c->N + j;
@@ -331,6 +331,7 @@ static void ct_tensor_one(const dpo_ctx *c, const uint64_t *a, const uint64_t *b
         }
     }
 }
+static void ct_tensor_one(const dpo_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *d) { ct_tensor_limbs(c, c->L, a, b, d); }
 void dpo_ct_tensor(const dpo_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *d, size_t batch) {
     size_t P = c->L * c->N;
 #pragma omp parallel for schedule(static)
@@ -485,6 +486,92 @@ void dpo_mod_switch_down(const dpo_ctx *c, const uint64_t *in, uint64_t t_plain,
     }
 }
 
+/* DESIGN.md §2.10 hybrid key switching with one special prime p = q[L-1] (GHS variant, one digit per ciphertext
+ * limb).  Ciphertext polynomials carry Lq = L-1 limbs; the switch key is [Lq digits][2][L][N] over all L limbs and
+ * encrypts p * g_j * target (dpo_keygen_switch_hybrid).
+ *   acc_c[i] = sum_j u_ji o key[j][c][i]   (i < L; u_ji = d[j] if i == j, else NTT_i(INTT_j(d[j]) mod q_i))
+ *   (c0, c1) = mod_switch_down(acc_0, acc_1)   -- divides the switched pair, and its noise, by p. */
+void dpo_keyswitch_hybrid(const dpo_ctx *c, const uint64_t *d, const uint64_t *key, uint64_t t_plain, uint64_t *c0, uint64_t *c1) {
+    const size_t N = c->N, PK = c->L * N;
+    const unsigned Lq = c->L - 1;
+    uint64_t *t = (uint64_t *)malloc(N * 8), *u = (uint64_t *)malloc(N * 8);
+    uint64_t *acc = (uint64_t *)calloc(2 * PK, 8), *low = (uint64_t *)malloc(2 * (size_t)Lq * N * 8);
+    for (unsigned j = 0; j < Lq; j++) {
+        memcpy(t, d + j * N, N * 8);
+        ntt_inv_limb(c, j, t);
+        for (unsigned i = 0; i < c->L; i++) {
+            uint64_t q = c->q[i], r0 = c->br0[i], r1 = c->br1[i];
+            const uint64_t *src;
+            if (i == j) src = d + j * N;
+            else {
+                for (size_t n = 0; n < N; n++) u[n] = t[n] % q;
+                ntt_fwd_limb(c, i, u);
+                src = u;
+            }
+            const uint64_t *kb = key + ((size_t)j * 2 + 0) * PK + i * N;
+            const uint64_t *ka = key + ((size_t)j * 2 + 1) * PK + i * N;
+            for (size_t n = 0; n < N; n++) {
+                acc[i * N + n] = addmod(acc[i * N + n], barrett_mul(src[n], kb[n], q, r0, r1), q);
+                acc[PK + i * N + n] = addmod(acc[PK + i * N + n], barrett_mul(src[n], ka[n], q, r0, r1), q);
+            }
+        }
+    }
+    dpo_mod_switch_down(c, acc, t_plain, low, 2);
+    memcpy(c0, low, (size_t)Lq * N * 8);
+    memcpy(c1, low + (size_t)Lq * N, (size_t)Lq * N * 8);
+    free(t); free(u); free(acc); free(low);
+}
+
+static void ct_mul_relin_hybrid_one(const dpo_ctx *c, const uint64_t *a, const uint64_t *b, const uint64_t *evk, uint64_t t_plain, uint64_t *out) {
+    const unsigned Lq = c->L - 1;
+    const size_t N = c->N, P = (size_t)Lq * N;
+    uint64_t *d = (uint64_t *)malloc(3 * P * 8), *k = (uint64_t *)malloc(2 * P * 8);
+    ct_tensor_limbs(c, Lq, a, b, d);
+    dpo_keyswitch_hybrid(c, d + 2 * P, evk, t_plain, k, k + P);
+    for (unsigned l = 0; l < Lq; l++)
+        for (size_t n = 0; n < N; n++) {
+            size_t o = l * N + n;
+            out[o] = addmod(d[o], k[o], c->q[l]);
+            out[P + o] = addmod(d[P + o], k[P + o], c->q[l]);
+        }
+    free(d); free(k);
+}
+/* a, b, out: [batch][2][L-1][N] */
+void dpo_ct_mul_relin_hybrid(const dpo_ctx *c, const uint64_t *a, const uint64_t *b, const uint64_t *evk, uint64_t t_plain,
+                             uint64_t *out, size_t batch) {
+    if (c->L < 2) return;
+    size_t P = (size_t)(c->L - 1) * c->N;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long k = 0; k < (long)batch; k++) ct_mul_relin_hybrid_one(c, a + 2 * P * k, b + 2 * P * k, evk, t_plain, out + 2 * P * k);
+}
+
+/* ct, out: [batch][2][L-1][N] */
+void dpo_rotate_hybrid(const dpo_ctx *c, const uint64_t *ct, uint64_t g, const uint64_t *gk, uint64_t t_plain, uint64_t *out, size_t batch) {
+    if (c->L < 2) return;
+    const unsigned Lq = c->L - 1;
+    const size_t N = c->N, P = (size_t)Lq * N;
+    uint32_t *perm = (uint32_t *)malloc(N * 4);
+    dpo_galois_perm(c, g, perm);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long b = 0; b < (long)batch; b++) {
+        const uint64_t *src = ct + 2 * P * b;
+        uint64_t *dst = out + 2 * P * b;
+        uint64_t *p = (uint64_t *)malloc(2 * P * 8), *k = (uint64_t *)malloc(2 * P * 8);
+        for (unsigned comp = 0; comp < 2; comp++)
+            for (unsigned l = 0; l < Lq; l++)
+                for (size_t n = 0; n < N; n++) p[comp * P + l * N + n] = src[comp * P + l * N + perm[n]];
+        dpo_keyswitch_hybrid(c, p + P, gk, t_plain, k, k + P);
+        for (unsigned l = 0; l < Lq; l++)
+            for (size_t n = 0; n < N; n++) {
+                size_t o = l * N + n;
+                dst[o] = addmod(p[o], k[o], c->q[l]);
+                dst[P + o] = k[P + o];
+            }
+        free(p); free(k);
+    }
+    free(perm);
+}
+
 /* ------------------------------------------------------------------ synthetic data */
 
 uint64_t dpo_splitmix64(uint64_t x) {
@@ -579,23 +666,73 @@ void dpo_keygen_switch(const dpo_ctx *c, uint64_t seed, uint64_t t_plain, const 
     free(e_eval);
 }
 
+/* hybrid key: digits j < L-1, limbs over all L moduli; b_j = -a_j*s + t*e_j + p*g_j*target,
+ * i.e. (p mod q_j) * target in limb j and nothing in the other limbs (p*g_j = 0 mod p and mod q_i, i != j). */
+void dpo_keygen_switch_hybrid(const dpo_ctx *c, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
+                              const uint64_t *target_eval, uint64_t *key) {
+    size_t N = c->N, P = c->L * N;
+    const uint64_t sp = c->q[c->L - 1];
+    xo_t x; xo_seed(&x, seed);
+    int64_t *e = (int64_t *)malloc(N * 8);
+    uint64_t *e_eval = (uint64_t *)malloc(P * 8);
+    for (unsigned j = 0; j + 1 < c->L; j++) {
+        uint64_t *kb = key + ((size_t)j * 2 + 0) * P, *ka = key + ((size_t)j * 2 + 1) * P;
+        for (unsigned l = 0; l < c->L; l++)
+            for (size_t n = 0; n < N; n++) ka[l * N + n] = xo_uniform(&x, c->q[l]);
+        for (size_t n = 0; n < N; n++) e[n] = xo_cbd(&x);
+        small_to_eval(c, e, t_plain, e_eval);
+        for (unsigned l = 0; l < c->L; l++) {
+            uint64_t q = c->q[l];
+            for (size_t n = 0; n < N; n++) {
+                size_t o = l * N + n;
+                uint64_t v = submod(e_eval[o], mulmod(ka[o], s_eval[o], q), q);
+                if (l == j) v = addmod(v, mulmod(target_eval[o], sp % q, q), q);
+                kb[o] = v;
+            }
+        }
+    }
+    free(e);
+    free(e_eval);
+}
+
+/* hybrid != 0: special-prime key layout [L-1][2][L][N] */
+static void keygen_switch_any(const dpo_ctx *c, int hybrid, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
+                              const uint64_t *target_eval, uint64_t *key) {
+    if (hybrid) dpo_keygen_switch_hybrid(c, seed, t_plain, s_eval, target_eval, key);
+    else dpo_keygen_switch(c, seed, t_plain, s_eval, target_eval, key);
+}
+static void keygen_relin_any(const dpo_ctx *c, int hybrid, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t *evk);
+static void keygen_galois_any(const dpo_ctx *c, int hybrid, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t g, uint64_t *gk);
+void dpo_keygen_relin_hybrid(const dpo_ctx *c, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t *evk) {
+    keygen_relin_any(c, 1, seed, t_plain, s_eval, evk);
+}
+void dpo_keygen_galois_hybrid(const dpo_ctx *c, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t g, uint64_t *gk) {
+    keygen_galois_any(c, 1, seed, t_plain, s_eval, g, gk);
+}
+
 void dpo_keygen_relin(const dpo_ctx *c, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t *evk) {
+    keygen_relin_any(c, 0, seed, t_plain, s_eval, evk);
+}
+static void keygen_relin_any(const dpo_ctx *c, int hybrid, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t *evk) {
     size_t P = c->L * c->N;
     uint64_t *s2 = (uint64_t *)malloc(P * 8);
     for (unsigned l = 0; l < c->L; l++)
         for (size_t n = 0; n < c->N; n++) s2[l * c->N + n] = mulmod(s_eval[l * c->N + n], s_eval[l * c->N + n], c->q[l]);
-    dpo_keygen_switch(c, seed, t_plain, s_eval, s2, evk);
+    keygen_switch_any(c, hybrid, seed, t_plain, s_eval, s2, evk);
     free(s2);
 }
 
 void dpo_keygen_galois(const dpo_ctx *c, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t g, uint64_t *gk) {
+    keygen_galois_any(c, 0, seed, t_plain, s_eval, g, gk);
+}
+static void keygen_galois_any(const dpo_ctx *c, int hybrid, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t g, uint64_t *gk) {
     size_t N = c->N, P = c->L * N;
     uint32_t *perm = (uint32_t *)malloc(N * 4);
     uint64_t *sg = (uint64_t *)malloc(P * 8);
     dpo_galois_perm(c, g, perm);
     for (unsigned l = 0; l < c->L; l++)
         for (size_t n = 0; n < N; n++) sg[l * N + n] = s_eval[l * N + perm[n]];
-    dpo_keygen_switch(c, seed, t_plain, s_eval, sg, gk);
+    keygen_switch_any(c, hybrid, seed, t_plain, s_eval, sg, gk);
     free(perm);
     free(sg);
 }

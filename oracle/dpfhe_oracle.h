@@ -83,6 +83,13 @@ void dpo_rotate(const dpo_ctx *, const uint64_t *ct, uint64_t galois_elt, const 
 /* drop the last limb (BGV modulus switch for t_plain > 0, plain rounding for t_plain == 0);
  * in [n_polys][L][N] -> out [n_polys][L-1][N] */
 void dpo_mod_switch_down(const dpo_ctx *, const uint64_t *in, uint64_t t_plain, uint64_t *out, size_t n_polys);
+/* hybrid (special-prime) key switching, DESIGN.md §2.10: the context's LAST limb is the special prime p;
+ * ciphertext polynomials carry L-1 limbs, keys are [L-1 digits][2][L][N].  t_plain as in dpo_mod_switch_down. */
+void dpo_keyswitch_hybrid(const dpo_ctx *, const uint64_t *d, const uint64_t *key, uint64_t t_plain, uint64_t *c0, uint64_t *c1);
+void dpo_ct_mul_relin_hybrid(const dpo_ctx *, const uint64_t *a, const uint64_t *b, const uint64_t *evk, uint64_t t_plain,
+                             uint64_t *out, size_t batch);
+void dpo_rotate_hybrid(const dpo_ctx *, const uint64_t *ct, uint64_t galois_elt, const uint64_t *gk, uint64_t t_plain,
+                       uint64_t *out, size_t batch);
 /* permutation table of sigma_g in evaluation form: out[i] = in[perm[i]] */
 void dpo_galois_perm(const dpo_ctx *, uint64_t galois_elt, uint32_t *perm);
 /* sigma_g in coefficient form on one limb: out(X) = in(X^g) */
@@ -102,6 +109,11 @@ void dpo_keygen_switch(const dpo_ctx *, uint64_t seed, uint64_t t_plain, const u
 void dpo_keygen_relin(const dpo_ctx *, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t *evk);
 void dpo_keygen_galois(const dpo_ctx *, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
                        uint64_t galois_elt, uint64_t *gk);
+void dpo_keygen_switch_hybrid(const dpo_ctx *, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
+                              const uint64_t *target_eval, uint64_t *key);
+void dpo_keygen_relin_hybrid(const dpo_ctx *, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t *evk);
+void dpo_keygen_galois_hybrid(const dpo_ctx *, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
+                              uint64_t galois_elt, uint64_t *gk);
 /* msg: N coefficients in [0,t); ct out [2][L][N] eval form */
 void dpo_encrypt(const dpo_ctx *, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
                  const uint64_t *msg, uint64_t *ct);

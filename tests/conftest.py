@@ -78,6 +78,14 @@ class Emu:
                               out.reshape(-1), batch, int(galois), G or 2 * self.L) == 0
         return out
 
+    def ks_hybrid(self, mode, a, b, key, batch, galois=0, t_plain=0, G=None):
+        out = np.zeros((batch, 2, self.L - 1, self.N), dtype=np.uint64)
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64)
+        assert self._l.emu_ks_hybrid(self._h, mode, a.reshape(-1), b.reshape(-1), np.ascontiguousarray(key).reshape(-1),
+                                     out.reshape(-1), batch, int(galois), int(t_plain), G or 2 * self.L) == 0
+        return out
+
     def mod_switch(self, polys, t_plain=0):
         x = np.ascontiguousarray(polys, dtype=np.uint64).reshape(-1, self.L, self.N)
         out = np.zeros((x.shape[0], self.L - 1, self.N), dtype=np.uint64)
@@ -110,6 +118,7 @@ def emu_lib():
     lib.emu_root_powers.argtypes = [C.c_void_p, C.c_uint, C.c_int, _u64p]
     lib.emu_ntt.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int]
     lib.emu_ks.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint]
+    lib.emu_ks_hybrid.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_uint]
     lib.emu_mod_switch.argtypes = [C.c_void_p, _u64p, _u64p, C.c_size_t, C.c_uint64]
     for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2)):
         f = getattr(lib, "emu_" + nm)

@@ -109,6 +109,62 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
     free(scratch);
     free(key_s);
 }
+
+// hybrid key switching: groups of L+1 slots (L ciphertext limbs + the special limb), the same role programs as
+// ks_hybrid_kernel, run in dependency order (all digits, then the multiply-accumulates, tau', the final division)
+template <int LOGN, int NT, int MODE>
+void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, uint64_t *out, size_t batch,
+                   uint32_t galois, uint64_t t_plain, unsigned G) {
+    const size_t N = (size_t)1 << LOGN;
+    const unsigned LK = e.hp.L, L = LK - 1, GS = LK;
+    unsigned groups = G / GS;
+    if (groups == 0) groups = 1;
+    uint64_t *buf = aligned_new<uint64_t>(N);
+    uint64_t *scratch = aligned_new<uint64_t>((size_t)groups * GS * 2 * N);
+    uint64_t *hyb_all = aligned_new<uint64_t>((size_t)groups * 4 * N);
+    const size_t key_words = (size_t)2 * L * LK * N;
+    uint64_t *key_s = aligned_new<uint64_t>(key_words);
+    for (size_t k = 0; k < key_words; ++k)
+        key_s[k] = (uint64_t)((((unsigned __int128)key[k]) << 64) / e.lp[(k / N) % LK].q);
+    MsConsts K;
+    build_ms_consts(e.hp, t_plain, K);
+    KsArgs A;
+    A.a = a; A.b = b; A.key = key; A.key_s = key_s; A.out = out; A.scratch = scratch;
+    A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois; A.Lk = LK; A.hyb = hyb_all;
+    HostCta cta{NT};
+    for (size_t r = 0; r * groups < batch; ++r) {
+        const unsigned par = (unsigned)(r & 1);
+        for (unsigned g = 0; g < groups; ++g) {
+            const size_t ct = r * groups + g;
+            if (ct >= batch) break;
+            const unsigned base = g * GS;
+            uint64_t *hyb = hyb_all + (size_t)g * 4 * N;
+            for (unsigned i = 0; i < L; ++i)
+                ks_phase1<LOGN, NT, MODE, true>(cta, buf, A, e.lp[i], ct, i, scratch + ((size_t)(base + i) * 2 + par) * N, K.qlm[i], K.qlm_s[i]);
+            for (unsigned i = 0; i < L; ++i)
+                for (uint32_t jj = 1; jj < L; ++jj) {
+                    const uint32_t j = (i + jj) % L;
+                    ks_phase2_digit<LOGN, NT, true, false>(cta, buf, A, e.lp[i], ct, i, j, jj, scratch + ((size_t)(base + j) * 2 + par) * N);
+                }
+            for (uint32_t jj = 0; jj < L; ++jj) {
+                const uint32_t j = (g + jj) % L;
+                ks_phase2_digit<LOGN, NT, true, true>(cta, buf, A, e.lp[L], ct, L, j, jj, scratch + ((size_t)(base + j) * 2 + par) * N, hyb);
+            }
+            for (unsigned c = 0; c < 2; ++c)
+                ms_tau_body<LOGN, NT, true>(cta, buf, hyb + c * N, hyb + c * N, A.itw + (size_t)L * N, e.lp[L], hyb + (2 + c) * N, K);
+            const size_t P = (size_t)L * N;
+            for (unsigned i = 0; i < L; ++i)
+                for (unsigned c = 0; c < 2; ++c) {
+                    uint64_t *row = out + ct * 2 * P + c * P + (size_t)i * N;
+                    ms_limb_body<LOGN, NT, true>(cta, buf, hyb + (2 + c) * N, row, row, A.tw + (size_t)i * N, e.lp[i], K, i);
+                }
+        }
+    }
+    free(buf);
+    free(scratch);
+    free(hyb_all);
+    free(key_s);
+}
 }  // namespace
 
 extern "C" {
@@ -165,35 +221,38 @@ int emu_ks(void *h, int mode, const uint64_t *a, const uint64_t *b, const uint64
     return -1;
 }
 
+// hybrid variants of emu_ks: the context's last limb is the special prime, data has L-1 limbs
+int emu_ks_hybrid(void *h, int mode, const uint64_t *a, const uint64_t *b, const uint64_t *key, uint64_t *out, size_t batch,
+                  uint32_t galois, uint64_t t_plain, unsigned G) {
+    Emu *e = (Emu *)h;
+    if (e->hp.L < 2) return -1;
+#define DISPATCH_H(LOGN, NT)                                                                               \
+    if (mode == 0) run_ks_hybrid<LOGN, NT, KS_MUL_RELIN>(*e, a, b, key, out, batch, galois, t_plain, G);    \
+    else if (mode == 1) run_ks_hybrid<LOGN, NT, KS_PLAIN>(*e, a, b, key, out, batch, galois, t_plain, G);   \
+    else run_ks_hybrid<LOGN, NT, KS_ROTATE>(*e, a, b, key, out, batch, galois, t_plain, G);                 \
+    return 0;
+    switch (e->hp.log_n) {
+        case 12: DISPATCH_H(12, 256)
+        case 13: DISPATCH_H(13, 256)
+        case 14: DISPATCH_H(14, 256)
+    }
+    return -1;
+}
+
 // modulus switching through the same bodies the device runs
 int emu_mod_switch(void *h, const uint64_t *in, uint64_t *out, size_t n_polys, uint64_t t_plain) {
     Emu *e = (Emu *)h;
     const unsigned L = e->hp.L;
     const size_t N = (size_t)1 << e->hp.log_n;
     if (L < 2) return -1;
-    typedef unsigned __int128 u128;
-    auto shoup = [](uint64_t w, uint64_t q) { return (uint64_t)((((u128)w) << 64) / q); };
-    const uint64_t ql = e->lp[L - 1].q;
     MsConsts K;
-    memset(&K, 0, sizeof(K));
-    K.half = ql >> 1;
-    K.has_t = t_plain ? 1u : 0u;
-    K.tinv = t_plain ? host_powmod(t_plain % ql, ql - 2, ql) : 1;
-    K.tinv_s = shoup(K.tinv, ql);
-    for (unsigned i = 0; i + 1 < L; ++i) {
-        const uint64_t q = e->lp[i].q;
-        K.qlm[i] = ql % q;
-        K.inv[i] = host_powmod(K.qlm[i], q - 2, q);
-        K.inv_s[i] = shoup(K.inv[i], q);
-        K.sinv[i] = t_plain ? host_mulmod(t_plain % q, K.inv[i], q) : K.inv[i];
-        K.sinv_s[i] = shoup(K.sinv[i], q);
-    }
+    build_ms_consts(e->hp, t_plain, K);
     uint64_t *buf = aligned_new<uint64_t>(N), *tau = aligned_new<uint64_t>(N);
     auto run = [&](auto logn_tag, auto nt_tag) {
         constexpr int LOGN = decltype(logn_tag)::value, NT = decltype(nt_tag)::value;
         HostCta cta{NT};
         for (size_t w = 0; w < n_polys; ++w) {
-            ms_tau_body<LOGN, NT>(cta, buf, in + (w * L + (L - 1)) * N, e->itw + (size_t)(L - 1) * N, e->lp[L - 1], tau, K);
+            ms_tau_body<LOGN, NT>(cta, buf, in + (w * L + (L - 1)) * N, nullptr, e->itw + (size_t)(L - 1) * N, e->lp[L - 1], tau, K);
             for (unsigned i = 0; i + 1 < L; ++i)
                 ms_limb_body<LOGN, NT>(cta, buf, tau, in + (w * L + i) * N, out + (w * (L - 1) + i) * N, e->tw + (size_t)i * N, e->lp[i], K, i);
         }

@@ -208,6 +208,87 @@ def test_semantics_multiply_then_mod_switch(ctxs, oracle_mod):
     assert np.array_equal(dec, (7 * m1.astype(object) * scale % t).astype(np.uint64))
 
 
+def hybrid_inputs(o, batch, seed):
+    """[batch][2][L-1][N] residues (with edge rows) under the first L-1 moduli, and a uniform hybrid key"""
+    Lq = o.L - 1
+    x = o.fill_uniform(seed, 2 * batch)[:, :Lq].reshape(batch, 2, Lq, o.N).copy()
+    q = np.array(o.moduli[:Lq], dtype=np.uint64)
+    x[0, 0] = (q - 1)[:, None]
+    x[0, 1, :, ::2] = 0
+    key = o.fill_uniform(seed + 1, 2 * Lq).reshape(Lq, 2, o.L, o.N)
+    return x, key
+
+
+@pytest.mark.parametrize("log_n,L,batch,t", [(12, 2, 3, 65537), (12, 4, 7, 65537), (13, 5, 4, 65537), (13, 5, 131, 0), (14, 3, 3, 65537),
+                                             (14, 9, 2, 65537), (12, 16, 2, 0)])
+def test_hybrid_keyswitch_family(ctxs, log_n, L, batch, t):
+    """special-prime key switching (context limb L-1 = special prime): ct x ct, rotate and bare key switch, bit-exact"""
+    c, o = ctxs(log_n, L)
+    Lq = L - 1
+    a, key = hybrid_inputs(o, batch, 81)
+    b, _ = hybrid_inputs(o, batch, 83)
+    out = torch.full((batch, 2, Lq, o.N), -1, dtype=torch.int64, device="cuda")
+    c.ct_mul_relin_hybrid(dev(a), dev(b), dev(key), out, batch, t)
+    assert np.array_equal(host(out).reshape(a.shape), o.ct_mul_relin_hybrid(a, b, key, t))
+    if batch > 16:
+        return   # the large ragged batch exercises scheduling; one mode is enough
+    g = o.galois_elt(-2)
+    c.rotate_hybrid(dev(a), g, dev(key), out, batch, t)
+    assert np.array_equal(host(out).reshape(a.shape), o.rotate_hybrid(a, g, key, t))
+    d = np.ascontiguousarray(a[:, 1])
+    c.keyswitch_hybrid(dev(d), dev(key), out, batch, t)
+    got = host(out).reshape(a.shape)
+    for k in range(batch):
+        c0, c1 = o.keyswitch_hybrid(d[k], key, t)
+        assert np.array_equal(got[k, 0], c0) and np.array_equal(got[k, 1], c1)
+
+
+def test_semantics_hybrid_product_and_noise(ctxs, oracle_mod):
+    """Dec(GPU hybrid ct x ct) == m1*m2, and its noise is far below the per-limb-digit variant's (the point of the special prime)"""
+    c, o = ctxs(12, 4)
+    o3 = oracle_mod.Oracle(12, 3, o.moduli[:3])
+    c3, _ = ctxs(12, 3, o.moduli[:3])
+    t = 65537
+    rng = np.random.default_rng(8)
+    s = o.keygen_secret(61)
+    s3 = np.ascontiguousarray(s[:3])
+    m1 = rng.integers(0, t, o.N).astype(np.uint64)
+    m2 = np.zeros(o.N, dtype=np.uint64)
+    m2[2] = 5
+    c1, c2 = o3.encrypt(63, t, s3, m1), o3.encrypt(64, t, s3, m2)
+    exp = np.empty_like(m1)
+    exp[2:] = (5 * m1[:-2]) % t
+    exp[:2] = (t - (5 * m1[-2:]) % t) % t
+
+    def noise_bits(ct):
+        ph = o3.phase(s3, ct)
+        Q = 1
+        for q in o3.moduli:
+            Q *= q
+        coef = [(Q // q) * pow(Q // q, -1, q) for q in o3.moduli]
+        worst = 0
+        for n in range(0, o.N, 61):
+            v = sum(int(ph[l][n]) * coef[l] for l in range(3)) % Q
+            worst = max(worst, min(v, Q - v))
+        return worst.bit_length()
+
+    out = torch.zeros((1, 2, 3, o.N), dtype=torch.int64, device="cuda")
+    c.ct_mul_relin_hybrid(dev(c1[None]), dev(c2[None]), dev(o.keygen_relin_hybrid(62, t, s)), out, 1, t)
+    hyb = host(out).reshape(2, 3, o.N).copy()
+    assert np.array_equal(o3.decrypt(s3, hyb, t), exp)
+    c3.ct_mul_relin(dev(c1[None]), dev(c2[None]), dev(o3.keygen_relin(62, t, s3)), out, 1)
+    bv = host(out).reshape(2, 3, o.N).copy()
+    assert np.array_equal(o3.decrypt(s3, bv, t), exp)
+    assert noise_bits(hyb) + 30 < noise_bits(bv)
+
+
+def test_hybrid_errors(ctxs):
+    c, o = ctxs(12, 1)
+    x = torch.zeros((1, 2, 1, o.N), dtype=torch.int64, device="cuda")
+    with pytest.raises(RuntimeError, match="special prime"):
+        c.ct_mul_relin_hybrid(x, x.clone(), x.clone(), x.clone(), 1)
+
+
 def test_fill_uniform_matches_oracle(ctxs):
     c, o = ctxs(13, 4)
     d = torch.empty((3, 4, o.N), dtype=torch.int64, device="cuda")

@@ -88,6 +88,34 @@ def test_emulated_mod_switch_bodies(make_emu, oracle_mod, log_n, L, t):
     assert np.array_equal(e.mod_switch(x, t), o.mod_switch_down(x, t))
 
 
+def _hybrid_inputs(o, batch, seed):
+    """[batch][2][L-1][N] uniform residues (with edge rows) under the first L-1 moduli, and a uniform hybrid key"""
+    Lq = o.L - 1
+    x = o.fill_uniform(seed, 2 * batch)[:, :Lq].reshape(batch, 2, Lq, o.N).copy()
+    q = np.array(o.moduli[:Lq], dtype=np.uint64)
+    x[0, 0] = (q - 1)[:, None]
+    x[0, 1, :, ::2] = 0
+    key = o.fill_uniform(seed + 1, 2 * Lq).reshape(Lq, 2, o.L, o.N)
+    return x, key
+
+
+@pytest.mark.parametrize("log_n,L,batch,t,G", [(12, 2, 2, 65537, None), (12, 4, 3, 65537, 10), (13, 5, 2, 0, None), (14, 3, 1, 65537, None),
+                                               (12, 9, 2, 65537, None)])
+def test_emulated_hybrid_keyswitch_bodies(make_emu, oracle_mod, log_n, L, batch, t, G):
+    """special-prime key switching: the device bodies in the kernel's role order against the oracle, all three modes"""
+    e, o = make_emu(log_n, L), oracle_mod.Oracle(log_n, L)
+    a, key = _hybrid_inputs(o, batch, 21)
+    b, _ = _hybrid_inputs(o, batch, 23)
+    assert np.array_equal(e.ks_hybrid(0, a, b, key, batch, t_plain=t, G=G), o.ct_mul_relin_hybrid(a, b, key, t))
+    g = o.galois_elt(3)
+    assert np.array_equal(e.ks_hybrid(2, a, None, key, batch, galois=g, t_plain=t, G=G), o.rotate_hybrid(a, g, key, t))
+    d = a[:, 1]
+    got = e.ks_hybrid(1, d, None, key, batch, t_plain=t, G=G)
+    for k in range(batch):
+        c0, c1 = o.keyswitch_hybrid(d[k], key, t)
+        assert np.array_equal(got[k, 0], c0) and np.array_equal(got[k, 1], c1)
+
+
 def test_emulated_mixed_size_moduli(make_emu, oracle_mod):
     lib = oracle_mod.lib()
     two_n = 2 << 12
