@@ -23,7 +23,7 @@ def h(a):
 
 def main():
     out = {"params": {}, "cases": []}
-    for log_n, L in [(12, 1), (12, 3), (13, 4), (14, 8)]:
+    for log_n, L in [(12, 1), (12, 3), (13, 4), (13, 5), (14, 8)]:
         o = Oracle(log_n, L)
         out["params"]["%d,%d" % (log_n, L)] = {"moduli": [str(q) for q in o.moduli], "psi": [str(p) for p in o.psi]}
     # config 1 of BASELINE.json: single forward NTT, N=4096, one 60-bit modulus
@@ -55,6 +55,22 @@ def main():
                          "out_head": [str(v) for v in r.reshape(-1)[:8]]})
     out["cases"].append({"name": "rotate1_n8192_l4", "log_n": 13, "L": 4, "seed": 0xD3390002, "galois": int(g),
                          "gk_sha256": h(gk), "out_sha256": h(rot), "out_head": [str(v) for v in rot.reshape(-1)[:8]]})
+    # modulus switching (BGV, t = 65537) of the same four polynomials, and the special-prime hybrid variants:
+    # context (13, 5) = the four ciphertext moduli above + the next prime as the special one
+    ms = o.mod_switch_down(a.reshape(4, 4, o.N), 65537)
+    out["cases"].append({"name": "mod_switch_down_n8192_l4", "log_n": 13, "L": 4, "seed": 0xD3390002, "t": 65537,
+                         "out_sha256": h(ms), "out_head": [str(v) for v in ms.reshape(-1)[:8]]})
+    o5 = Oracle(13, 5)
+    assert o5.moduli[:4] == o.moduli
+    s5 = o5.keygen_secret(1)
+    hk = o5.keygen_relin_hybrid(2, 65537, s5)
+    hr = o5.ct_mul_relin_hybrid(a, b, hk, 65537)
+    hgk = o5.keygen_galois_hybrid(3, 65537, s5, g)
+    hrot = o5.rotate_hybrid(a, g, hgk, 65537)
+    out["cases"].append({"name": "ct_mul_relin_hybrid_n8192_l4p1", "log_n": 13, "L": 5, "seed": 0xD3390002, "t": 65537,
+                         "evk_sha256": h(hk), "out_sha256": h(hr), "out_head": [str(v) for v in hr.reshape(-1)[:8]]})
+    out["cases"].append({"name": "rotate1_hybrid_n8192_l4p1", "log_n": 13, "L": 5, "seed": 0xD3390002, "t": 65537, "galois": int(g),
+                         "gk_sha256": h(hgk), "out_sha256": h(hrot), "out_head": [str(v) for v in hrot.reshape(-1)[:8]]})
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kat.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)

@@ -69,6 +69,36 @@ def test_golden_ct_mul_relin_and_rotate(kat, oracle_mod):
     c.close()
 
 
+def test_golden_mod_switch_and_hybrid(kat, oracle_mod):
+    """the level-dropping and special-prime paths against the committed hashes (keys regenerated, their hashes pinned)"""
+    import deeppowers_b200 as dp
+    ms = next(c for c in kat["cases"] if c["name"] == "mod_switch_down_n8192_l4")
+    mul = next(c for c in kat["cases"] if c["name"] == "ct_mul_relin_hybrid_n8192_l4p1")
+    rot = next(c for c in kat["cases"] if c["name"] == "rotate1_hybrid_n8192_l4p1")
+    c4, c5 = dp.Context(13, 4), dp.Context(13, 5)
+    assert [str(q) for q in c5.moduli] == kat["params"]["13,5"]["moduli"] and c5.moduli[:4] == c4.moduli
+    a = torch.empty((2, 2, 4, 8192), dtype=torch.int64, device="cuda")
+    b = torch.empty_like(a)
+    c4.fill_uniform(ms["seed"], a, 4, first_poly=0)
+    c4.fill_uniform(ms["seed"], b, 4, first_poly=4)
+    low = torch.zeros((4, 3, 8192), dtype=torch.int64, device="cuda")
+    c4.mod_switch_down(a, low, 4, ms["t"])
+    assert sha(low) == ms["out_sha256"]
+    o5 = oracle_mod.Oracle(13, 5)
+    s5 = o5.keygen_secret(1)
+    evk = o5.keygen_relin_hybrid(2, mul["t"], s5)
+    gk = o5.keygen_galois_hybrid(3, rot["t"], s5, rot["galois"])
+    assert hashlib.sha256(evk.tobytes()).hexdigest() == mul["evk_sha256"]
+    assert hashlib.sha256(gk.tobytes()).hexdigest() == rot["gk_sha256"]
+    out = torch.zeros_like(a)
+    c5.ct_mul_relin_hybrid(a, b, dev(evk), out, 2, mul["t"])
+    assert sha(out) == mul["out_sha256"]
+    c5.rotate_hybrid(a, rot["galois"], dev(gk), out, 2, rot["t"])
+    assert sha(out) == rot["out_sha256"]
+    c4.close()
+    c5.close()
+
+
 def test_shard_equality_on_one_gpu():
     """G-way sharded evaluation == 1-way evaluation, byte for byte (logical shards on one device)"""
     import deeppowers_b200 as dp

@@ -126,6 +126,22 @@ def test_golden_vectors(oracle_mod, kat):
             y = o.ntt_fwd(x)
             assert sha(y) == case["out_sha256"]
             assert [str(v) for v in y.reshape(-1)[:8]] == case["out_head"]
+        elif "hybrid" in case["name"]:
+            o4 = oracle_mod.Oracle(13, 4)
+            s = o.keygen_secret(1)
+            a = o4.fill_uniform(case["seed"], 4).reshape(2, 2, 4, o.N)
+            b = o4.fill_uniform(case["seed"], 4, first_poly=4).reshape(2, 2, 4, o.N)
+            if "rotate" in case["name"]:
+                gk = o.keygen_galois_hybrid(3, case["t"], s, case["galois"])
+                assert sha(gk) == case["gk_sha256"]
+                assert sha(o.rotate_hybrid(a, case["galois"], gk, case["t"])) == case["out_sha256"]
+            else:
+                evk = o.keygen_relin_hybrid(2, case["t"], s)
+                assert sha(evk) == case["evk_sha256"]
+                assert sha(o.ct_mul_relin_hybrid(a, b, evk, case["t"])) == case["out_sha256"]
+        elif "mod_switch" in case["name"]:
+            x = o.fill_uniform(case["seed"], 4)
+            assert sha(o.mod_switch_down(x, case["t"])) == case["out_sha256"]
         elif "ct_mul_relin" in case["name"]:
             s = o.keygen_secret(1)
             evk = o.keygen_relin(2, 65537, s)
@@ -184,6 +200,82 @@ def test_scheme_semantics(oracle_mod):
             else:
                 exp[e - o.N] = (t - m1[i]) % t
         assert np.array_equal(o.decrypt(s, r, t), exp)
+
+
+@pytest.mark.parametrize("t", [0, 65537])
+def test_mod_switch_down_is_exact_rounded_division(oracle_mod, t):
+    """out == (X - w) / q_last over the integers, w = the centred representative of X (t = 0) or t * centred(X / t) (BGV)
+    modulo q_last: checked coefficient by coefficient with Python integers through the CRT."""
+    o = oracle_mod.Oracle(8, 3)
+    lo = oracle_mod.Oracle(8, 2, o.moduli[:2])
+    x = o.fill_uniform(31, 2)
+    x[1, 2] = 0   # divisible by q_last already: nothing to round
+    y = lo.ntt_inv(o.mod_switch_down(x, t))
+    xc = o.ntt_inv(x)
+    ql = o.moduli[2]
+    Q = o.moduli[0] * o.moduli[1] * ql
+    coef = [(Q // q) * pow(Q // q, -1, q) for q in o.moduli]
+    for pidx in range(2):
+        for n in range(o.N):
+            X = sum(int(xc[pidx, l, n]) * coef[l] for l in range(3)) % Q
+            r = (X * pow(t, -1, ql)) % ql if t else X % ql
+            if r > ql // 2:
+                r -= ql
+            w = r * (t if t else 1)
+            assert (X - w) % ql == 0
+            Y = (X - w) // ql
+            assert [int(y[pidx, l, n]) for l in range(2)] == [Y % q for q in o.moduli[:2]]
+            if t:
+                assert (Y * ql - X) % t == 0   # the plaintext moves by exactly q_last^-1 mod t
+
+
+def test_hybrid_key_switching_semantics(oracle_mod):
+    """special-prime variant: Dec(ct x ct) = m1*m2 and Dec(rotate) = sigma_g(m) under the L-1 ciphertext moduli, with
+    far less noise than the per-limb-digit variant; keyswitch_hybrid == mod_switch_down of the (L)-limb inner product."""
+    o = oracle_mod.Oracle(10, 4)
+    o3 = oracle_mod.Oracle(10, 3, o.moduli[:3])
+    t = 65537
+    rng = np.random.default_rng(4)
+    s = o.keygen_secret(7)
+    s3 = np.ascontiguousarray(s[:3])
+    assert np.array_equal(o3.keygen_secret(7), s3)
+    m1 = rng.integers(0, t, o.N).astype(np.uint64)
+    m2 = rng.integers(0, t, o.N).astype(np.uint64)
+    c1, c2 = o3.encrypt(9, t, s3, m1), o3.encrypt(10, t, s3, m2)
+    hyb = o.ct_mul_relin_hybrid(c1[None], c2[None], o.keygen_relin_hybrid(8, t, s), t)[0]
+    bv = o3.ct_mul_relin(c1[None], c2[None], o3.keygen_relin(8, t, s3))[0]
+    exp = negacyclic_mod_t(m1, m2, t)
+    assert np.array_equal(o3.decrypt(s3, hyb, t), exp) and np.array_equal(o3.decrypt(s3, bv, t), exp)
+
+    def noise_bits(ct):
+        ph = o3.phase(s3, ct)
+        Q = o3.moduli[0] * o3.moduli[1] * o3.moduli[2]
+        coef = [(Q // q) * pow(Q // q, -1, q) for q in o3.moduli]
+        worst = 0
+        for n in range(0, o.N, 7):
+            v = sum(int(ph[l][n]) * coef[l] for l in range(3)) % Q
+            worst = max(worst, min(v, Q - v))
+        return worst.bit_length()
+
+    assert noise_bits(hyb) + 30 < noise_bits(bv)
+    g = o.galois_elt(1)
+    r = o.rotate_hybrid(c1[None], g, o.keygen_galois_hybrid(11, t, s, g), t)[0]
+    r_bv = o3.rotate(c1[None], g, o3.keygen_galois(11, t, s3, g))[0]
+    assert np.array_equal(o3.decrypt(s3, r, t), o3.decrypt(s3, r_bv, t))
+    # definition check of the bare key switch against its parts
+    d = o3.fill_uniform(12, 1)[0]
+    key = o.fill_uniform(13, 6).reshape(3, 2, 4, o.N)
+    acc = np.zeros((2, 4, o.N), dtype=np.uint64)
+    for j in range(3):
+        tj = o3.ntt_inv(d[None])[0][j]
+        lifted = np.stack([tj % np.uint64(q) for q in o.moduli])
+        u = o.ntt_fwd(lifted[None])[0]
+        u[j] = d[j]
+        for c in range(2):
+            acc[c] = o.poly_add(acc[c][None], o.poly_mul_pointwise(u[None], key[j, c][None]))[0]
+    c0, c1_ = o.keyswitch_hybrid(d, key, t)
+    low = o.mod_switch_down(acc, t)
+    assert np.array_equal(c0, low[0]) and np.array_equal(c1_, low[1])
 
 
 def test_galois_perm_matches_coefficient_automorphism(oracle_mod):
