@@ -391,7 +391,7 @@ static int ks_hybrid_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const u
     if (out == a || out == b) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
     if (!ctx->lc.ks_hyb) {
         u64 *hyb = nullptr;
-        CU_TRY(cudaMalloc(&hyb, (ctx->lc.ks_slots / 2 + 1) * 4 * ctx->N() * sizeof(u64)));
+        CU_TRY(cudaMalloc(&hyb, (ctx->lc.ks_slots / 2 + 1) * KS_HYB_ROWS * ctx->N() * sizeof(u64)));
         ctx->lc.ks_hyb = hyb;
     }
     MsConsts K;

@@ -164,8 +164,11 @@ struct KsArgs {
     u32 L;               // limbs of a ciphertext polynomial = number of digits
     u32 galois;          // ROTATE only
     u32 Lk;              // limbs of a key polynomial: L, or L + 1 with a special prime (hybrid)
-    u64 *hyb;            // hybrid only: [groups][4][N] special-limb accumulators (rows 0,1) and tau' (rows 2,3)
+    u64 *hyb;            // hybrid only: [groups][KS_HYB_ROWS][N]: special-limb accumulators (rows 0,1) and tau'
 };
+// tau' rows of a hybrid group are double-buffered by round parity (the division step runs one round late)
+constexpr int KS_HYB_ROWS = 6;
+DPFHE_HD u32 ks_hyb_tau_row(u32 parity, u32 c) { return 2u + 2u * parity + c; }
 
 // operands of one 16-byte chunk position of phase 1, fetched one iteration ahead of their use
 struct KsP1Operands {

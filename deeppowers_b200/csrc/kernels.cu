@@ -202,11 +202,12 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
 // CTA L owns the special limb.  Per ciphertext:
 //   limb CTA    tensor/permute, p*own terms + first key term, INTT, publish digit        (as above)
 //               L-1 x [lift + NTT + MAC]                                                  (as above, nothing final)
-//               wait for tau'; 2 x [centred lift + NTT], out = (acc - s*u) / p           (ms_limb_body)
+//               2 x [centred lift of tau' + NTT], out = (acc - s*u) / p                   (ms_limb_body)
 //   special CTA L x [lift + NTT_p + MAC into its scratch rows]; 2 x INTT_p (* t^-1) -> tau', publish
-// Both roles run six transforms per ciphertext at L = 4.  tau' and the digits are exchanged through L2 scratch under
-// the same release/acquire flags; a limb CTA cannot start its next ciphertext before tau' of this one arrived and
-// the special CTA needs every digit of a round, which orders all reuse of the scratch rows.
+// Both roles run six transforms per ciphertext at L = 4.  The special CTA can only finish after every digit arrived,
+// so a limb CTA postpones the division step of ciphertext r until it has done the digit and multiply-accumulate
+// work of ciphertext r + 1 (software pipeline of depth one): tau' rows, like the digits and the mailbox, are
+// double-buffered by round parity, and the output rows keep the lazy accumulators in between.
 template <int LOGN, int NT, int MINB, int MODE>
 __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __grid_constant__ LimbTable lt, const __grid_constant__ MsConsts K,
                                                              size_t batch, u32 *flags, u32 epoch, u32 *ticket, u64 *mail) {
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __g
     const u32 L = A.L, GS = L + 1, slot = blockIdx.x, i = slot % GS, group = slot / GS, base = slot - i;
     const bool special = i == L;
     const LimbParams &p = lt.lp[i];
-    u64 *hyb = A.hyb + (size_t)group * 4 * N;   // rows 0,1: special-limb accumulators; rows 2,3: tau'
+    u64 *hyb = A.hyb + (size_t)group * KS_HYB_ROWS * N;
     auto wait_for = [&](u32 sib, u32 tag) {
         if (threadIdx.x == 0) {
             while ((int)(ld_acquire_u32(flags + sib) - tag) < 0) {
@@ -231,16 +232,29 @@ __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __g
         __syncthreads();
         if (threadIdx.x == 0) st_release_u32(flags + slot, tag);
     };
+    // the postponed division of one ciphertext (limb CTAs): needs tau' of that round
+    auto divide = [&](size_t ct, u32 tag, u32 parity) {
+        wait_for(base + L, tag);
+        const size_t P = (size_t)L * N;
+        for (u32 c = 0; c < 2; ++c) {
+            u64 *row = A.out + ct * 2 * P + c * P + (size_t)i * N;   // lazy accumulator -> final value, in place
+            ms_limb_body<LOGN, NT, true>(cta, buf, hyb + ks_hyb_tau_row(parity, c) * N, row, row, A.tw + (size_t)i * N, p, K, i);
+        }
+    };
+    bool pending = false;
+    size_t prev_ct = 0;
+    u32 prev_tag = 0, prev_parity = 0;
     for (u32 round = 0;; ++round) {
-        const u32 tag = epoch + round + 1;
+        const u32 tag = epoch + round + 1, parity = round & 1u;
         if (threadIdx.x == 0) {
+            u64 *box = mail + (size_t)group * 2 + parity;
             if (i == 0) {
                 const u32 t = atomicAdd(ticket, 1u);
-                st_release_u64(mail + group, ((u64)tag << 32) | t);
+                st_release_u64(box, ((u64)tag << 32) | t);
                 s_ct = t;
             } else {
                 u64 m;
-                do m = ld_acquire_u64(mail + group);
+                do m = ld_acquire_u64(box);
                 while ((u32)(m >> 32) != tag);
                 s_ct = (u32)m;
             }
@@ -248,7 +262,6 @@ __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __g
         __syncthreads();
         const size_t ct = s_ct;
         if (ct >= batch) break;
-        const u32 parity = round & 1u;
         if (!special) {
             ks_phase1<LOGN, NT, MODE, true>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N, K.qlm[i], K.qlm_s[i]);
             publish(tag);
@@ -257,12 +270,11 @@ __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __g
                 wait_for(base + j, tag);
                 ks_phase2_digit<LOGN, NT, true, false>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)(base + j) * 2 + parity) * N);
             }
-            wait_for(base + L, tag);
-            const size_t P = (size_t)L * N;
-            for (u32 c = 0; c < 2; ++c) {
-                u64 *row = A.out + ct * 2 * P + c * P + (size_t)i * N;   // lazy accumulator -> final value, in place
-                ms_limb_body<LOGN, NT, true>(cta, buf, hyb + (2 + c) * N, row, row, A.tw + (size_t)i * N, p, K, i);
-            }
+            if (pending) divide(prev_ct, prev_tag, prev_parity);
+            pending = true;
+            prev_ct = ct;
+            prev_tag = tag;
+            prev_parity = parity;
         } else {
             for (u32 jj = 0; jj < L; ++jj) {
                 const u32 j = (group + jj) % L;   // groups start at different digits: spreads the key-column reads
@@ -270,10 +282,11 @@ __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __g
                 ks_phase2_digit<LOGN, NT, true, true>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)(base + j) * 2 + parity) * N, hyb);
             }
             for (u32 c = 0; c < 2; ++c)
-                ms_tau_body<LOGN, NT, true>(cta, buf, hyb + c * N, hyb + c * N, A.itw + (size_t)i * N, p, hyb + (2 + c) * N, K);
+                ms_tau_body<LOGN, NT, true>(cta, buf, hyb + c * N, hyb + c * N, A.itw + (size_t)i * N, p, hyb + ks_hyb_tau_row(parity, c) * N, K);
             publish(tag);
         }
     }
+    if (pending) divide(prev_ct, prev_tag, prev_parity);   // the group's last ciphertext
 }
 
 // ------------------------------------------------------------------ element-wise kernels
@@ -553,7 +566,7 @@ static cudaError_t launch_ks_hybrid_t(LaunchCtx &lc, const KsArgs &A, const MsCo
     return e;
 }
 
-// data has L-1 limbs, the key [L-1][2][L][N]; lc.ks_hyb must hold (ks_slots / 2 + 1) * 4 * N words
+// data has L-1 limbs, the key [L-1][2][L][N]; lc.ks_hyb must hold (ks_slots / 2 + 1) * KS_HYB_ROWS * N words
 cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, u32 galois,
                              const MsConsts &K, cudaStream_t st) {
     if (batch == 0) return cudaSuccess;

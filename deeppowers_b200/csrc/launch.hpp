@@ -27,7 +27,7 @@ struct LaunchCtx {
     u32 *ks_ticket = nullptr;         // next ciphertext index (reset per launch)
     u64 *ks_mail = nullptr;           // [ks_slots] per-group mailbox: (round tag << 32) | ciphertext index
     u64 *ks_key_s = nullptr;          // [L][2][L][N] Shoup companions of the current switch key
-    u64 *ks_hyb = nullptr;            // hybrid key switching: [ks_slots / 2 + 1][4][N], allocated at the first hybrid call
+    u64 *ks_hyb = nullptr;            // hybrid key switching: [ks_slots / 2 + 1][KS_HYB_ROWS][N], allocated at the first hybrid call
     size_t ks_slots = 0;
     u32 ks_epoch = 0;                 // rounds consumed so far (flag values already used)
     int ks_prefetch = 0;              // ciphertexts ahead for the bulk L2 prefetch of inputs (DPFHE_KS_PF), 0 = off

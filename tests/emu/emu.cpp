@@ -121,7 +121,7 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
     if (groups == 0) groups = 1;
     uint64_t *buf = aligned_new<uint64_t>(N);
     uint64_t *scratch = aligned_new<uint64_t>((size_t)groups * GS * 2 * N);
-    uint64_t *hyb_all = aligned_new<uint64_t>((size_t)groups * 4 * N);
+    uint64_t *hyb_all = aligned_new<uint64_t>((size_t)groups * KS_HYB_ROWS * N);
     const size_t key_words = (size_t)2 * L * LK * N;
     uint64_t *key_s = aligned_new<uint64_t>(key_words);
     for (size_t k = 0; k < key_words; ++k)
@@ -138,7 +138,7 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
             const size_t ct = r * groups + g;
             if (ct >= batch) break;
             const unsigned base = g * GS;
-            uint64_t *hyb = hyb_all + (size_t)g * 4 * N;
+            uint64_t *hyb = hyb_all + (size_t)g * KS_HYB_ROWS * N;
             for (unsigned i = 0; i < L; ++i)
                 ks_phase1<LOGN, NT, MODE, true>(cta, buf, A, e.lp[i], ct, i, scratch + ((size_t)(base + i) * 2 + par) * N, K.qlm[i], K.qlm_s[i]);
             for (unsigned i = 0; i < L; ++i)
@@ -151,12 +151,12 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
                 ks_phase2_digit<LOGN, NT, true, true>(cta, buf, A, e.lp[L], ct, L, j, jj, scratch + ((size_t)(base + j) * 2 + par) * N, hyb);
             }
             for (unsigned c = 0; c < 2; ++c)
-                ms_tau_body<LOGN, NT, true>(cta, buf, hyb + c * N, hyb + c * N, A.itw + (size_t)L * N, e.lp[L], hyb + (2 + c) * N, K);
+                ms_tau_body<LOGN, NT, true>(cta, buf, hyb + c * N, hyb + c * N, A.itw + (size_t)L * N, e.lp[L], hyb + ks_hyb_tau_row(par, c) * N, K);
             const size_t P = (size_t)L * N;
             for (unsigned i = 0; i < L; ++i)
                 for (unsigned c = 0; c < 2; ++c) {
                     uint64_t *row = out + ct * 2 * P + c * P + (size_t)i * N;
-                    ms_limb_body<LOGN, NT, true>(cta, buf, hyb + (2 + c) * N, row, row, A.tw + (size_t)i * N, e.lp[i], K, i);
+                    ms_limb_body<LOGN, NT, true>(cta, buf, hyb + ks_hyb_tau_row(par, c) * N, row, row, A.tw + (size_t)i * N, e.lp[i], K, i);
                 }
         }
     }
