@@ -526,6 +526,54 @@ int dpfhe_rotate_host(dpfhe_ctx *ctx, const uint64_t *h_ct, uint64_t galois_elt,
                         });
 }
 
+int dpfhe_ct_mul_relin_hybrid_host(dpfhe_ctx *ctx, const uint64_t *h_a, const uint64_t *h_b, const uint64_t *h_evk, uint64_t *h_out,
+                                   size_t batch, uint64_t t_plain) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    if (!h_a || !h_b || !h_evk || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
+    if (ctx->hp.L < 2) return fail(DPFHE_ERR_INVALID, "hybrid key switching needs a special prime: create the context with at least two limbs");
+    const size_t Pq = (ctx->hp.L - 1) * ctx->N();   // words of a ciphertext polynomial (L-1 limbs)
+    rc = upload_key(ctx, h_evk, 2 * (ctx->hp.L - 1) * ctx->P());
+    if (rc) return rc;
+    const size_t chunk = pick_chunk(ctx, 2 * Pq * 8, batch);
+    return run_pipeline(ctx, h_a, h_b, h_out, batch, 2 * Pq, 2 * Pq, chunk,
+                        [&](u64 *da, u64 *db, u64 *dout, size_t cnt, cudaStream_t st) -> int {
+                            return ks_hybrid_common(ctx, KS_MUL_RELIN, da, db, ctx->stage_key, dout, cnt, 0, t_plain, st);
+                        });
+}
+
+int dpfhe_rotate_hybrid_host(dpfhe_ctx *ctx, const uint64_t *h_ct, uint64_t galois_elt, const uint64_t *h_gk, uint64_t *h_out,
+                             size_t batch, uint64_t t_plain) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    if (!h_ct || !h_gk || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
+    if (ctx->hp.L < 2) return fail(DPFHE_ERR_INVALID, "hybrid key switching needs a special prime: create the context with at least two limbs");
+    const size_t Pq = (ctx->hp.L - 1) * ctx->N();
+    rc = upload_key(ctx, h_gk, 2 * (ctx->hp.L - 1) * ctx->P());
+    if (rc) return rc;
+    const size_t chunk = pick_chunk(ctx, 2 * Pq * 8, batch);
+    return run_pipeline(ctx, h_ct, nullptr, h_out, batch, 2 * Pq, 2 * Pq, chunk,
+                        [&](u64 *dc, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
+                            return ks_hybrid_common(ctx, KS_ROTATE, dc, nullptr, ctx->stage_key, dout, cnt, galois_elt, t_plain, st);
+                        });
+}
+
+int dpfhe_mod_switch_down_host(dpfhe_ctx *ctx, const uint64_t *h_in, uint64_t *h_out, size_t n_polys, uint64_t t_plain) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (n_polys == 0) return DPFHE_OK;
+    if (!h_in || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
+    if (ctx->hp.L < 2) return fail(DPFHE_ERR_INVALID, "mod_switch_down needs at least two limbs");
+    const size_t P = ctx->P(), Pq = (ctx->hp.L - 1) * ctx->N();
+    const size_t chunk = pick_chunk(ctx, P * 8, n_polys);
+    return run_pipeline(ctx, h_in, nullptr, h_out, n_polys, P, Pq, chunk,
+                        [&](u64 *din, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
+                            return dpfhe_mod_switch_down(ctx, din, dout, cnt, t_plain, st);
+                        });
+}
+
 int dpfhe_ct_mul_plain_host(dpfhe_ctx *ctx, const uint64_t *h_ct, const uint64_t *h_pt, uint64_t *h_out, size_t batch) {
     int rc = enter(ctx);
     if (rc) return rc;

@@ -209,6 +209,17 @@ class Context:
     def rotate_host(self, ct, galois_elt, gk, out):
         self._chk(self._l.dpfhe_rotate_host(self._h, _hptr(ct), int(galois_elt), _hptr(gk), _hptr(out, True), ct.size // (2 * self.P)))
 
+    def ct_mul_relin_hybrid_host(self, a, b, evk, out, t_plain=0):
+        pq = 2 * (self.L - 1) * self.N
+        self._chk(self._l.dpfhe_ct_mul_relin_hybrid_host(self._h, _hptr(a), _hptr(b), _hptr(evk), _hptr(out, True), a.size // pq, int(t_plain)))
+
+    def rotate_hybrid_host(self, ct, galois_elt, gk, out, t_plain=0):
+        pq = 2 * (self.L - 1) * self.N
+        self._chk(self._l.dpfhe_rotate_hybrid_host(self._h, _hptr(ct), int(galois_elt), _hptr(gk), _hptr(out, True), ct.size // pq, int(t_plain)))
+
+    def mod_switch_down_host(self, polys, out, t_plain=0):
+        self._chk(self._l.dpfhe_mod_switch_down_host(self._h, _hptr(polys), _hptr(out, True), polys.size // self.P, int(t_plain)))
+
     def galois_elt(self, k):
         """Galois element 5^k mod 2N of a rotation by k slots (k may be negative)."""
         return pow(5, k % (self.N // 2), 2 * self.N)

@@ -92,6 +92,22 @@ public:
         same(ct.count, ct.count, out.count);
         check(dpfhe_rotate_host(ctx_, ct.data, galois_element(steps), galois_key, out.data, ct.count));
     }
+    // special-prime (hybrid) forms: this evaluator's last limb is the special prime; batches hold limbs()-1 limbs
+    void multiply_relin_hybrid(ConstCiphertextBatch a, ConstCiphertextBatch b, const std::uint64_t *relin_key, CiphertextBatch out,
+                               std::uint64_t plain_modulus = 0) {
+        same(a.count, b.count, out.count);
+        check(dpfhe_ct_mul_relin_hybrid_host(ctx_, a.data, b.data, relin_key, out.data, a.count, plain_modulus));
+    }
+    void rotate_hybrid(ConstCiphertextBatch ct, long steps, const std::uint64_t *galois_key, CiphertextBatch out,
+                       std::uint64_t plain_modulus = 0) {
+        same(ct.count, ct.count, out.count);
+        check(dpfhe_rotate_hybrid_host(ctx_, ct.data, galois_element(steps), galois_key, out.data, ct.count, plain_modulus));
+    }
+    // drop the last limb: in holds limbs() limbs per polynomial, out limbs()-1
+    void mod_switch_to_next(ConstCiphertextBatch in, CiphertextBatch out, std::uint64_t plain_modulus = 0) {
+        same(in.count, in.count, out.count);
+        check(dpfhe_mod_switch_down_host(ctx_, in.data, out.data, 2 * in.count, plain_modulus));
+    }
     void transform_to_ntt(std::uint64_t *polys, std::size_t n_polys) { check(dpfhe_ntt_fwd_host(ctx_, polys, n_polys)); }
     void transform_from_ntt(std::uint64_t *polys, std::size_t n_polys) { check(dpfhe_ntt_inv_host(ctx_, polys, n_polys)); }
 

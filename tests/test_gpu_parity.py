@@ -332,6 +332,24 @@ def test_mod_switch_errors(dp, ctxs):
         c3.mod_switch_down(y, y, 1)
 
 
+def test_hybrid_and_mod_switch_host_entry_points(ctxs):
+    """the host-buffer forms run the same kernels behind the staging pipeline (ragged batch, several chunks)"""
+    c, o = ctxs(12, 4)
+    batch = 700   # three staging chunks at N=4096 (64 MiB / 192 KiB per ciphertext = 341 per chunk), the last one ragged
+    a, key = hybrid_inputs(o, batch, 91)
+    b, _ = hybrid_inputs(o, batch, 93)
+    out = np.zeros_like(a)
+    c.ct_mul_relin_hybrid_host(a, b, key, out, 65537)
+    assert np.array_equal(out, o.ct_mul_relin_hybrid(a, b, key, 65537))
+    g = o.galois_elt(7)
+    c.rotate_hybrid_host(a[:5], g, key, out[:5], 65537)
+    assert np.array_equal(out[:5], o.rotate_hybrid(a[:5], g, key, 65537))
+    x = o.fill_uniform(95, 9)
+    low = np.zeros((9, 3, o.N), dtype=np.uint64)
+    c.mod_switch_down_host(x, low, 65537)
+    assert np.array_equal(low, o.mod_switch_down(x, 65537))
+
+
 def test_errors_are_reported(dp, ctxs):
     c, o = ctxs(12, 2)
     with pytest.raises(dp.DpfheError):
