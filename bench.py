@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational hybrid key-switching timing")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -278,6 +279,22 @@ def main():
                         "frac": ntt_gbs / peak, "traffic": traffic_for("ntt_kernel_fwd", n_ntt)}}
     ctx.fill_uniform(SEED, a, 2 * B, first_poly=first)     # restore `a` (the NTT ran in place)
 
+    # SURVEY.md section 8 row f-2 (informational, not the headline): the same ciphertexts through special-prime hybrid
+    # key switching (context = the four ciphertext moduli + one special prime; 30 transforms per ct-mult instead of 16)
+    extras = None
+    if not args.no_extras:
+        ctx5 = dp.Context(LOG_N, L + 1, device=local_rank)
+        hkey = torch.empty((L, 2, L + 1, N), dtype=torch.int64, device="cuda")
+        ctx5.fill_uniform(SEED + 3, hkey, 2 * L)
+        k = max(3, args.steps // 3)
+        hyb_ms = timed(lambda: ctx5.ct_mul_relin_hybrid(a, b, hkey, out, B, 65537), k, 2) / k
+        extras = {"ct_mul_relin_hybrid": {"value": world * B / (hyb_ms * 1e-3), "unit": "ct-mult/s", "ms_per_step": hyb_ms,
+                                          "kernel": "ks_hybrid_kernel<13,256,3,MUL_RELIN>", "GBps": B * ALGO_BYTES_CT_MUL / (hyb_ms * 1e-3) / 1e9,
+                                          "note": "4 ciphertext limbs + 1 special prime, BGV rounding t=65537 (DESIGN.md 2.10)"}}
+        ctx5.close()
+        del hkey
+        ctx.ct_mul_relin(a, b, evk, out, B)     # `out` is compared with the end-to-end result below
+
     # end to end through the host-buffer ABI: pinned host memory, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -340,7 +357,7 @@ def main():
                        "global_batch": world * B, "parallelism": "batch-sharded x%d, no data-path collective" % world,
                        "l2": "inputs+outputs are %.1f GiB per GPU (>> 126 MB L2), no flush needed" % (3 * B * CT_BYTES / 2**30),
                        "seed": hex(SEED)},
-            "roofline": roofline, "ntt": ntt, "cpu_baseline": cpu, "e2e": e2e, "gather": gather,
+            "roofline": roofline, "ntt": ntt, "extras": extras, "cpu_baseline": cpu, "e2e": e2e, "gather": gather,
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line))
