@@ -4,13 +4,14 @@ import struct
 import numpy as np
 
 MAGIC = b"DPFHEv1\x00"
-CIPHERTEXTS, SWITCH_KEY, PLAINTEXTS = 1, 2, 3
+CIPHERTEXTS, SWITCH_KEY, PLAINTEXTS, HYBRID_SWITCH_KEY = 1, 2, 3, 4   # hybrid: n_limbs includes the special prime
 _HDR = struct.Struct("<8sIIIIQ16Q")
 
 
 def payload_words(log_n, n_limbs, kind, count):
     poly = (1 << log_n) * n_limbs
-    return {CIPHERTEXTS: count * 2 * poly, SWITCH_KEY: 2 * n_limbs * poly, PLAINTEXTS: count * poly}[kind]
+    return {CIPHERTEXTS: count * 2 * poly, SWITCH_KEY: 2 * n_limbs * poly, PLAINTEXTS: count * poly,
+            HYBRID_SWITCH_KEY: 2 * max(n_limbs - 1, 0) * poly}[kind]
 
 
 def write(path, log_n, n_limbs, kind, count, moduli, payload, form=1):

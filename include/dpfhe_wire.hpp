@@ -28,7 +28,8 @@ namespace deeppowers {
 namespace api {
 namespace fhe {
 
-enum class WireKind : std::uint32_t { Ciphertexts = 1, SwitchKey = 2, Plaintexts = 3 };
+// HybridSwitchKey: n_limbs counts the special prime (the last modulus); payload [n_limbs-1][2][n_limbs][N]
+enum class WireKind : std::uint32_t { Ciphertexts = 1, SwitchKey = 2, Plaintexts = 3, HybridSwitchKey = 4 };
 
 struct WireHeader {
     char magic[8];
@@ -44,6 +45,7 @@ inline std::size_t wire_payload_words(const WireHeader &h) {
         case WireKind::Ciphertexts: return h.count * 2 * poly;
         case WireKind::SwitchKey: return std::size_t(2) * h.n_limbs * poly;
         case WireKind::Plaintexts: return h.count * poly;
+        case WireKind::HybridSwitchKey: return h.n_limbs ? std::size_t(2) * (h.n_limbs - 1) * poly : 0;
     }
     throw std::runtime_error("dpfhe wire: unknown kind");
 }

@@ -30,6 +30,16 @@ def test_reference_examples_link_unchanged(tmp_path, name):
         assert "Hello there" in r.stdout or "Generated" in r.stdout
 
 
+def test_wire_hybrid_key_roundtrip(tmp_path, oracle_mod):
+    from deeppowers_b200 import wire
+    o = oracle_mod.Oracle(12, 3)
+    key = o.fill_uniform(6, 4).reshape(2, 2, 3, o.N)      # [L-1][2][L][N]
+    p = str(tmp_path / "hk.dpfhe")
+    wire.write(p, 12, 3, wire.HYBRID_SWITCH_KEY, 1, o.moduli, key)
+    hdr, data = wire.read(p)
+    assert hdr["kind"] == wire.HYBRID_SWITCH_KEY and hdr["moduli"] == o.moduli and np.array_equal(data.reshape(key.shape), key)
+
+
 def test_wire_format_roundtrip(tmp_path, oracle_mod):
     from deeppowers_b200 import wire
     o = oracle_mod.Oracle(12, 2)
