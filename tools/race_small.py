@@ -16,8 +16,9 @@ for log_n, L, B in ((13, 4, 3), (12, 2, 2), (14, 2, 1)):
     if L >= 2:   # hybrid variants (last limb = special prime) and modulus switching
         Lq = L - 1
         ha = torch.empty((B, 2, Lq, N), dtype=torch.int64, device="cuda"); hb = torch.empty_like(ha); ho = torch.empty_like(ha)
-        c.fill_uniform(4, ha, 2 * B); c.fill_uniform(5, hb, 2 * B)   # uniform below q_limb of the L-limb layout: fine as residues
-        ha %= (1 << 59); hb %= (1 << 59)
+        cq = dp.Context(log_n, Lq, c.moduli[:Lq])
+        cq.fill_uniform(4, ha, 2 * B); cq.fill_uniform(5, hb, 2 * B)
+        cq.close()
         hk = torch.empty((Lq, 2, L, N), dtype=torch.int64, device="cuda"); c.fill_uniform(6, hk, 2 * Lq)
         c.ct_mul_relin_hybrid(ha, hb, hk, ho, B, 65537)
         c.rotate_hybrid(ha, 5, hk, ho, B, 65537)
