@@ -92,6 +92,22 @@ __global__ void __launch_bounds__(1024) bench(unsigned long long *out, long long
 #pragma unroll
             for (int c = 0; c < CH; ++c) { r32[c] = r32[c] + b; asm volatile("" : "+r"(r32[c])); r32[c] = r32[c] + a; asm volatile("" : "+r"(r32[c])); }
         }
+        if (OP == 24) {   // DFMA only (fp64 pipe): could the idle fp64 lanes carry part of the modular arithmetic?
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { double f = __longlong_as_double((long long)acc[c]); asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f) : "d"(1.0000001), "d"(0.5)); acc[c] = (u64)__double_as_longlong(f); }
+        }
+        if (OP == 25) {   // mixed: 4 IMAD.WIDE chains + 4 DFMA chains
+#pragma unroll
+            for (int c = 0; c < CH / 2; ++c) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b));
+#pragma unroll
+            for (int c = CH / 2; c < CH; ++c) { double f = __longlong_as_double((long long)acc[c]); asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f) : "d"(1.0000001), "d"(0.5)); acc[c] = (u64)__double_as_longlong(f); }
+        }
+        if (OP == 26) {   // mixed: 4 IMAD chains + 4 DFMA chains
+#pragma unroll
+            for (int c = 0; c < CH / 2; ++c) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r32[c]) : "r"(a), "r"(b));
+#pragma unroll
+            for (int c = CH / 2; c < CH; ++c) { double f = __longlong_as_double((long long)acc[c]); asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f) : "d"(1.0000001), "d"(0.5)); acc[c] = (u64)__double_as_longlong(f); }
+        }
         if (OP == 9) {
 #pragma unroll
             for (int c = 0; c < CH; c += 2) ct_bfly(acc[c], acc[c + 1], w, p);
@@ -171,6 +187,9 @@ int main() {
         run<14>("lop3 x8", CH, p, threads);
         run<15>("FFMA x8", CH, p, threads);
         run<16>("4 IMAD + 4 FFMA mixed", CH, p, threads);
+        run<24>("DFMA x8", CH, p, threads);
+        run<25>("4 IMAD.WIDE + 4 DFMA mixed", CH, p, threads);
+        run<26>("4 IMAD + 4 DFMA mixed", CH, p, threads);
         printf("\n");
     }
     return 0;
