@@ -433,6 +433,21 @@ int dpfhe_ct_mul_plain_acc(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t 
     return DPFHE_OK;
 }
 
+int dpfhe_ct_mul_plain_inner(dpfhe_ctx *ctx, const uint64_t *d_steps, size_t n_steps, const uint64_t *d_pts, size_t n_groups, uint64_t *d_out,
+                             size_t batch, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0 || n_groups == 0) return DPFHE_OK;
+    CHECK_PTR(d_steps); CHECK_PTR(d_pts); CHECK_PTR(d_out);
+    if (n_steps == 0 || n_steps > 256) return fail(DPFHE_ERR_INVALID, "n_steps must be in [1, 256]");
+    if (n_groups > 65535) return fail(DPFHE_ERR_INVALID, "n_groups must be below 65536");
+    if (d_out == d_steps) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
+    unsigned launches = 0;
+    CU_TRY(launch_pt_inner(ctx->lc, d_steps, (u32)n_steps, d_pts, (u32)n_groups, d_out, batch, pick(ctx, stream), &launches));
+    ctx->launches += launches;
+    return DPFHE_OK;
+}
+
 int dpfhe_mod_switch_down(dpfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, size_t n_polys, uint64_t t_plain, void *stream) {
     int rc = enter(ctx);
     if (rc) return rc;

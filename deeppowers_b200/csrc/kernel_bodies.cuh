@@ -521,4 +521,125 @@ DPFHE_HD void ms_limb_body(CTA &cta, u64 *buf, const u64 *tau, const u64 *c_limb
     }
 }
 
+// ---- plaintext inner products: out[g] = sum_b steps[b] o pts[g][b]  (baby-step/giant-step inner loop) ----
+// One CTA owns a tile of PTI_COEFFS coefficients of one limb for a block of giant steps: the plaintext tile
+// [gcnt][nb][16] stays in shared memory while the whole batch streams through, so every ciphertext row is read once
+// and every output row written once (instead of one read-modify-write pass over the batch per diagonal).
+// Operands are pre-split into 30-bit halves when they are staged, so a multiply-accumulate is four IMAD.WIDE with
+// 64-bit accumulators and no carry handling: 16 products of two values below 2^30 fit in 64 bits.
+struct PtInnerArgs {
+    const u64 *steps;   // [nb][batch][2][L][N] ciphertext batches (e.g. the baby-step rotations)
+    const u64 *pts;     // [ng][nb][L][N] plaintexts, evaluation form, shared by the batch
+    u64 *out;           // [ng][batch][2][L][N]
+    size_t batch;
+    u32 L, nb, ng;
+};
+constexpr int PTI_COEFFS = 16;   // coefficients per tile: one 128-byte segment of a row
+constexpr int PTI_GBLK = 3;      // outputs a thread accumulates together (15 64-bit accumulators)
+constexpr int PTI_FLUSH = 16;    // products per accumulator before it is folded: 16 * 2^60 = 2^64
+
+// acc += a * b, one IMAD.WIDE (written as PTX: nvcc's u32 -> u64 promotion leaves a dead add on the high word)
+DPFHE_HD void mad_wide(u64 &acc, u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b));
+#else
+    acc += (u64)a * b;
+#endif
+}
+DPFHE_HD u64 pti_split(u64 x) { return (x & 0x3fffffffull) | ((x >> 30) << 32); }   // low / high 30-bit halves in the two words
+
+DPFHE_HD void st_stream64(u64 *p, u64 v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+    *p = v;
+#endif
+}
+
+// z = a0 + (a1a + a1b) * 2^30 + a2 * 2^60 < 16 q^2  ->  [0, 3q)   (barrett_lazy's own bound is z < 2^(s+64) ~ 4 q^2)
+DPFHE_HD u64 pti_fold(u64 a0, u64 a1a, u64 a1b, u64 a2, const LimbParams &p) {
+    const u64 m = a1a + a1b, mc = m < a1a ? 1ull : 0ull;   // 65-bit middle sum
+    u64 lo = a0, hi, t = m << 30;
+    lo += t;
+    hi = (lo < t ? 1ull : 0ull) + (m >> 34) + (mc << 30);
+    t = a2 << 60;
+    lo += t;
+    hi += (lo < t ? 1ull : 0ull) + (a2 >> 4);
+    return word_reduce(barrett_lazy_long(hi, lo, p), p);
+}
+
+// shared memory: (gcnt * nb + 2 * nb) * 16 words
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void pt_inner_tile(CTA &cta, u64 *smem, const PtInnerArgs &A, const LimbParams &p, u32 limb, u32 tile, u32 g0, u32 gcnt) {
+    constexpr size_t N = (size_t)1 << LOGN;
+    constexpr int NW = NT / 32;
+    static_assert(PTI_COEFFS == 16 && NT % 32 == 0, "a half-warp covers one tile row");
+    const size_t P = (size_t)A.L * N, col = (size_t)limb * N + (size_t)tile * PTI_COEFFS;
+    const u32 nb = A.nb;
+    u64 *ps = smem;                                       // [gcnt][nb][16] split plaintext values
+    u64 *xs = smem + (size_t)gcnt * nb * PTI_COEFFS;      // [nb][2][16] split ciphertext values of one batch element
+    cta.par([&](int tid) {
+        for (u32 idx = (u32)tid; idx < gcnt * nb * 8; idx += NT) {
+            const u32 r = idx >> 3, ch = idx & 7, g = r / nb, b = r % nb;
+            const U64x2 v = ld_keep(reinterpret_cast<const U64x2 *>(A.pts + ((size_t)(g0 + g) * nb + b) * P + col) + ch);
+            ps[r * 16 + ch * 2] = pti_split(v.x);
+            ps[r * 16 + ch * 2 + 1] = pti_split(v.y);
+        }
+    });
+    for (size_t k = 0; k < A.batch; ++k) {
+        cta.par([&](int tid) {
+            for (u32 idx = (u32)tid; idx < nb * 2 * 8; idx += NT) {
+                const u32 r = idx >> 3, ch = idx & 7, b = r >> 1, comp = r & 1;
+                const U64x2 v = ld_stream(reinterpret_cast<const U64x2 *>(A.steps + (((size_t)b * A.batch + k) * 2 + comp) * P + col) + ch);
+                xs[r * 16 + ch * 2] = pti_split(v.x);
+                xs[r * 16 + ch * 2 + 1] = pti_split(v.y);
+            }
+        });
+        cta.par([&](int tid) {
+            const u32 lane = (u32)tid & 31u, c = lane & 15u, comp = lane >> 4, w = (u32)tid >> 5;
+            const u64 *xrow = xs + comp * 16 + c;   // + b * 32
+            for (u32 gb = w; gb < gcnt; gb += NW * PTI_GBLK) {   // this thread's outputs: g = gb + j * NW (warp-uniform)
+                // rows past the end of the block are computed on a clamped index and not stored: no branches in the loop
+                const u64 *prow[PTI_GBLK];
+                u64 a0[PTI_GBLK], a1a[PTI_GBLK], a1b[PTI_GBLK], a2[PTI_GBLK], sum[PTI_GBLK];
+#pragma unroll
+                for (int j = 0; j < PTI_GBLK; ++j) {
+                    const u32 g = gb + (u32)j * NW;
+                    prow[j] = ps + (size_t)(g < gcnt ? g : gcnt - 1) * nb * 16 + c;   // + b * 16
+                    a0[j] = a1a[j] = a1b[j] = a2[j] = sum[j] = 0;
+                }
+                for (u32 b0 = 0; b0 < nb; b0 += PTI_FLUSH) {
+                    const u32 b1 = b0 + PTI_FLUSH < nb ? b0 + PTI_FLUSH : nb;
+// unrolled by four: ptxas lowers the accumulation to IMAD.WIDE (no addend) + one three-input IADD3 / IADD3.X pair per
+                    // two products; it does not keep a loop-carried 64-bit addend in the multiplier in any formulation tried
+#pragma unroll 4
+                    for (u32 b = b0; b < b1; ++b) {
+                        const u64 xv = xrow[b * 32];
+                        const u32 x0 = (u32)xv, x1 = (u32)(xv >> 32);
+#pragma unroll
+                        for (int j = 0; j < PTI_GBLK; ++j) {
+                            const u64 pv = prow[j][b * 16];
+                            const u32 p0 = (u32)pv, p1 = (u32)(pv >> 32);
+                            mad_wide(a0[j], x0, p0);
+                            mad_wide(a1a[j], x0, p1);
+                            mad_wide(a1b[j], x1, p0);
+                            mad_wide(a2[j], x1, p1);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < PTI_GBLK; ++j) {
+                        sum[j] = csub(sum[j] + pti_fold(a0[j], a1a[j], a1b[j], a2[j], p), p.q4);   // stays below 4q
+                        a0[j] = a1a[j] = a1b[j] = a2[j] = 0;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < PTI_GBLK; ++j) {
+                    const u32 g = gb + (u32)j * NW;
+                    if (g < gcnt) st_stream64(A.out + (((size_t)(g0 + g) * A.batch + k) * 2 + comp) * P + col + c, canon4(sum[j], p));
+                }
+            }
+        });
+    }
+}
+
 }  // namespace dpfhe

@@ -289,6 +289,16 @@ __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __g
     if (pending) divide(prev_ct, prev_tag, prev_parity);   // the group's last ciphertext
 }
 
+// ------------------------------------------------------------------ plaintext inner products (BSGS inner loop)
+template <int LOGN, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) pt_inner_kernel(PtInnerArgs A, const __grid_constant__ LimbTable lt, u32 g0, u32 gcnt) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr u32 TILES_PER_LIMB = (1u << LOGN) / PTI_COEFFS;
+    DevCta<NT> cta;
+    const u32 limb = blockIdx.x / TILES_PER_LIMB, tile = blockIdx.x % TILES_PER_LIMB;
+    pt_inner_tile<LOGN, NT>(cta, reinterpret_cast<u64 *>(smem_raw), A, lt.lp[limb], limb, tile, g0, gcnt);
+}
+
 // ------------------------------------------------------------------ element-wise kernels
 // all operate on 16-byte chunks; chunk index -> limb = (chunk / (N/2)) % L
 template <int LOGN>
@@ -596,6 +606,52 @@ cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b
         case 14: KS_HYB_DISPATCH(14)
     }
     return cudaErrorNotSupported;
+}
+
+template <int LOGN>
+static cudaError_t launch_pt_inner_t(const LaunchCtx &lc, const PtInnerArgs &A, cudaStream_t st) {
+    constexpr int NT = 256, MINB = 2;
+    auto kern = pt_inner_kernel<LOGN, NT, MINB>;
+    // two CTAs per SM: at most 112 KiB each; the plaintext tile takes nb * 128 bytes per giant step
+    const size_t budget = (size_t)112 << 10, row = (size_t)A.nb * PTI_COEFFS * 8;
+    if (3 * row > budget) return cudaErrorInvalidValue;
+    u32 gmax = (u32)((budget - 2 * row) / row);
+    if (gmax >= NT / 32) gmax -= gmax % (NT / 32);   // whole rounds of warps
+    static bool configured[64] = {};
+    if (!configured[lc.device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+        if (e != cudaSuccess) return e;
+        configured[lc.device & 63] = true;
+    }
+    const unsigned grid = (unsigned)(lc.L * (((size_t)1 << LOGN) / PTI_COEFFS));
+    for (u32 g0 = 0; g0 < A.ng; g0 += gmax) {
+        const u32 gcnt = A.ng - g0 < gmax ? A.ng - g0 : gmax;
+        const size_t smem = ((size_t)gcnt + 2) * row;
+        kern<<<grid, NT, smem, st>>>(A, lc.lt, g0, gcnt);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// out[g] = sum_b steps[b] o pts[g][b]; returns the number of kernel launches through *launches
+cudaError_t launch_pt_inner(const LaunchCtx &lc, const u64 *steps, u32 nb, const u64 *pts, u32 ng, u64 *out, size_t batch, cudaStream_t st,
+                            unsigned *launches) {
+    *launches = 0;
+    if (!batch || !nb || !ng) return cudaSuccess;
+    PtInnerArgs A;
+    A.steps = steps; A.pts = pts; A.out = out; A.batch = batch; A.L = lc.L; A.nb = nb; A.ng = ng;
+    const size_t budget = (size_t)112 << 10, row = (size_t)nb * PTI_COEFFS * 8;
+    if (3 * row > budget) return cudaErrorInvalidValue;
+    u32 gmax = (u32)((budget - 2 * row) / row);
+    if (gmax >= 8) gmax -= gmax % 8;
+    *launches = (ng + gmax - 1) / gmax;
+    switch (lc.log_n) {
+        case 12: return launch_pt_inner_t<12>(lc, A, st);
+        case 13: return launch_pt_inner_t<13>(lc, A, st);
+        case 14: return launch_pt_inner_t<14>(lc, A, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch,

@@ -6,7 +6,8 @@
 // Lazy-range conventions ("bound B" means value < B*q; 16q < 2^64 because q < 2^60):
 //   shoup_lazy(x, w)      any 64-bit x        -> [0, 2q)
 //   word_reduce(x)        any 64-bit x        -> [0, 3q)   (3 integer multiplies)
-//   barrett_lazy(a*b)     a*b < 2^(2b+4)      -> [0, 3q)   (b = bit length of q)
+//   barrett_lazy(a*b)     a*b <= 4 q^2        -> [0, 3q)
+//   barrett_lazy_long(z)  z < 2^(2b+4)        -> [0, 15q)  (b = bit length of q; sums of up to 16 products)
 //   canon(x)              x < 16q             -> [0, q)
 #pragma once
 #include <stdint.h>
@@ -170,7 +171,8 @@ DPFHE_HD void mul128(u64 a, u64 b, u64 &hi, u64 &lo) {
 #endif
 }
 
-// Barrett reduction of z = hi:lo.  Requires z < 2^(2b+4) (e.g. both factors < 4q), gives [0, 3q).
+// Barrett reduction of z = hi:lo.  Requires z < 2^(s+64), s = bitlen(q) - 2, i.e. z <= 4 q^2 (factor bounds Ba*Bb <= 4:
+// the shifted value must fit one word), gives [0, 3q).
 // With both factors < q the result is in [0, 2q).
 DPFHE_HD u64 barrett_lazy(u64 hi, u64 lo, const LimbParams &p) {
     const u32 s = p.bar_shift;                       // 32 <= s <= 58 because 2^33 < q < 2^60
@@ -184,6 +186,22 @@ DPFHE_HD u64 barrett_lazy(u64 hi, u64 lo, const LimbParams &p) {
 #endif
     u64 qh = umulhi64(zt, p.bar_mu);
     return mad_lo64(qh, p.nq, lo);   // lo - qh*q
+}
+
+// Barrett reduction of a longer sum z = hi:lo < 2^(2b+4), b = bit length of q (e.g. 16 products of canonical factors):
+// the quotient is estimated from z / 2^(s+2) so that the shifted value still fits one word; 4*qh is within 14 of
+// floor(z/q), so the result is in [0, 15q) (and 15q < 2^64).
+DPFHE_HD u64 barrett_lazy_long(u64 hi, u64 lo, const LimbParams &p) {
+    const u32 s = p.bar_shift + 2;                   // 34 <= s <= 60
+#if defined(__CUDA_ARCH__)
+    const u32 w1 = (u32)(lo >> 32), w2 = (u32)hi, w3 = (u32)(hi >> 32);
+    const u32 zl = __funnelshift_r(w1, w2, s - 32), zh = __funnelshift_r(w2, w3, s - 32);
+    const u64 zt = ((u64)zh << 32) | zl;
+#else
+    const u64 zt = (hi << (64 - s)) | (lo >> s);     // floor(z / 2^s) < 2^64
+#endif
+    const u64 qh = umulhi64(zt, p.bar_mu);
+    return mad_lo64(qh << 2, p.nq, lo);              // lo - 4*qh*q
 }
 
 DPFHE_HD u64 mulmod_lazy(u64 a, u64 b, const LimbParams &p) {

@@ -142,26 +142,44 @@ class Context:
     def ct_mul_plain_acc(self, ct, pt, acc, batch, stream=None):
         self._chk(self._l.dpfhe_ct_mul_plain_acc(self._h, _ptr(ct), _ptr(pt), _ptr(acc), batch, _stream(stream)))
 
-    def linear_bsgs(self, ct, diags, gk_baby, gk_giant, baby, out, batch, scratch=None, stream=None):
+    def ct_mul_plain_inner(self, steps, pts, out, n_steps, n_groups, batch, stream=None):
+        """out[g][k] = sum_b steps[b][k] o pts[g][b]: steps [n_steps][batch][2][L][N], pts [n_groups][n_steps][L][N],
+        out [n_groups][batch][2][L][N]; every ciphertext row is read once (the fused BSGS inner loop)"""
+        self._chk(self._l.dpfhe_ct_mul_plain_inner(self._h, _ptr(steps), n_steps, _ptr(pts), n_groups, _ptr(out), batch, _stream(stream)))
+
+    def linear_bsgs(self, ct, diags, gk_baby, gk_giant, baby, out, batch, scratch=None, stream=None, fused=True):
         """Encrypted matrix-vector product by baby-step/giant-step diagonals (row f-4, config 4).
 
         y = sum_g rot_{g*baby}( sum_b D[g*baby + b] o rot_b(x) ), D pre-rotated by -g*baby (caller encodes them so),
         diags: [n][L][N] plaintexts in evaluation form, n a multiple of `baby`; gk_baby / gk_giant: Galois keys of
-        rotations by 1 and by `baby`.  Uses (baby-1) + (n/baby-1) rotations instead of n-1.  `scratch` must hold
-        (baby + 2) ciphertext batches; `out` must not alias `ct`."""
+        rotations by 1 and by `baby`.  Uses (baby-1) + (n/baby-1) rotations instead of n-1.  fused=True computes all
+        inner sums with one dpfhe_ct_mul_plain_inner call (scratch: baby + n/baby + 1 ciphertext batches); fused=False
+        is the reference composition of ct_mul_plain / ct_mul_plain_acc (scratch: baby + 2).  Same bits either way.
+        `out` must not alias `ct`."""
         import torch
         n = diags.shape[0]
         assert n % baby == 0, "number of diagonals must be a multiple of the baby-step count"
         giant = n // baby
         shape = (batch, 2, self.L, self.N)
+        need = baby + giant + 1 if fused else baby + 2
         if scratch is None:
-            scratch = torch.empty((baby + 2,) + shape, dtype=torch.int64, device=ct.device)
-        steps, inner, tmp = scratch[:baby], scratch[baby], scratch[baby + 1]
+            scratch = torch.empty((need,) + shape, dtype=torch.int64, device=ct.device)
+        assert scratch.shape[0] >= need, "scratch too small for this schedule"
+        steps = scratch[:baby]
         g1, gb = self.galois_elt(1), self.galois_elt(baby)
         steps[0].copy_(ct.view(shape))
         for b in range(1, baby):
             self.rotate(steps[b - 1], g1, gk_baby, steps[b], batch, stream)
         acc = out
+        if fused:
+            inner, tmp = scratch[baby:baby + giant], scratch[baby + giant]
+            self.ct_mul_plain_inner(steps, diags, inner, baby, giant, batch, stream)
+            acc.view(shape).copy_(inner[giant - 1])
+            for g in range(giant - 2, -1, -1):
+                self.rotate(acc, gb, gk_giant, tmp, batch, stream)          # Horner step: acc = rot_baby(acc) + inner_g
+                self.poly_add(tmp, inner[g], acc, 2 * batch, stream)
+            return out
+        inner, tmp = scratch[baby], scratch[baby + 1]
         for g in range(giant - 1, -1, -1):
             self.ct_mul_plain(steps[0], diags[g * baby], inner, batch, stream)
             for b in range(1, baby):
@@ -169,7 +187,7 @@ class Context:
             if g == giant - 1:
                 acc.view(shape).copy_(inner)
             else:
-                self.rotate(acc, gb, gk_giant, tmp, batch, stream)          # Horner step: acc = rot_baby(acc) + inner_g
+                self.rotate(acc, gb, gk_giant, tmp, batch, stream)
                 self.poly_add(tmp, inner, acc, 2 * batch, stream)
         return out
 

@@ -110,6 +110,14 @@ int dpfhe_ct_mul_plain_acc(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t 
 int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk,
                  uint64_t *d_out, size_t batch, void *stream);
 
+/* ---- plaintext inner products (the inner loop of a baby-step/giant-step matrix-vector product):
+ *      out[g][k] = sum_{b < n_steps} steps[b][k] o pts[g][b]   for g < n_groups, k < batch
+ *      steps [n_steps][batch][2][L][N] ciphertext batches, pts [n_groups][n_steps][L][N] plaintexts (evaluation form,
+ *      shared by the batch), out [n_groups][batch][2][L][N].  Bit-identical to dpfhe_ct_mul_plain followed by
+ *      n_steps-1 dpfhe_ct_mul_plain_acc per group, but every ciphertext row is read once. n_steps <= 256. ---- */
+int dpfhe_ct_mul_plain_inner(dpfhe_ctx *ctx, const uint64_t *d_steps, size_t n_steps, const uint64_t *d_pts, size_t n_groups,
+                             uint64_t *d_out, size_t batch, void *stream);
+
 /* ---- modulus switching / rescale: drop the last limb of every polynomial.
  *      in [n_polys][L][N] -> out [n_polys][L-1][N] (a ciphertext is two polynomials), evaluation form.
  *      t_plain > 0: BGV modulus switch (the plaintext is scaled by q_last^-1 mod t); t_plain == 0: plain rounding.

@@ -53,6 +53,7 @@ def lib():
         "dpo_keyswitch": (None, [vp, u64p, u64p, u64p, u64p]),
         "dpo_ct_mul_relin": (None, [vp, u64p, u64p, u64p, u64p, sz]),
         "dpo_ct_mul_plain": (None, [vp, u64p, u64p, u64p, sz]),
+        "dpo_ct_mul_plain_inner": (None, [vp, u64p, sz, u64p, sz, u64p, sz]),
         "dpo_rotate": (None, [vp, u64p, u64, u64p, u64p, sz]),
         "dpo_mod_switch_down": (None, [vp, u64p, u64, u64p, sz]),
         "dpo_keyswitch_hybrid": (None, [vp, u64p, u64p, u64, u64p, u64p]),
@@ -168,6 +169,16 @@ class Oracle:
         ct = np.ascontiguousarray(ct, dtype=np.uint64)
         out = np.empty_like(ct)
         self._l.dpo_ct_mul_plain(self._c, ct.reshape(-1), np.ascontiguousarray(pt).reshape(-1), out.reshape(-1), ct.size // (2 * self.P))
+        return out
+
+    def ct_mul_plain_inner(self, steps, pts):
+        """steps [nb][batch][2][L][N], pts [ng][nb][L][N] -> [ng][batch][2][L][N]"""
+        steps = np.ascontiguousarray(steps, dtype=np.uint64)
+        pts = np.ascontiguousarray(pts, dtype=np.uint64)
+        nb, batch, ng = steps.shape[0], steps.shape[1], pts.shape[0]
+        assert pts.shape[1] == nb
+        out = np.empty((ng, batch, 2, self.L, self.N), dtype=np.uint64)
+        self._l.dpo_ct_mul_plain_inner(self._c, steps.reshape(-1), nb, pts.reshape(-1), ng, out.reshape(-1), batch)
         return out
 
     def rotate(self, ct, galois_elt, gk):

@@ -404,6 +404,25 @@ void dpo_ct_mul_plain(const dpo_ctx *c, const uint64_t *ct, const uint64_t *pt, 
     }
 }
 
+/* DESIGN.md §2.7b plaintext inner products (inner loop of a baby-step/giant-step matrix-vector product):
+ *   out[g][k] = sum_b steps[b][k] o pts[g][b];  steps [nb][batch][2][L][N], pts [ng][nb][L][N], out [ng][batch][2][L][N] */
+void dpo_ct_mul_plain_inner(const dpo_ctx *c, const uint64_t *steps, size_t nb, const uint64_t *pts, size_t ng, uint64_t *out, size_t batch) {
+    const size_t N = c->N, P = c->L * N;
+#pragma omp parallel for schedule(static)
+    for (long w = 0; w < (long)(ng * batch * 2); w++) {
+        const size_t g = (size_t)w / (batch * 2), kc = (size_t)w % (batch * 2);   /* kc = k*2 + comp */
+        uint64_t *dst = out + (g * batch * 2 + kc) * P;
+        for (unsigned l = 0; l < c->L; l++)
+            for (size_t n = 0; n < N; n++) {
+                uint64_t acc = 0;
+                for (size_t b = 0; b < nb; b++)
+                    acc = addmod(acc, barrett_mul(steps[(b * batch * 2 + kc) * P + l * N + n], pts[(g * nb + b) * P + l * N + n],
+                                                  c->q[l], c->br0[l], c->br1[l]), c->q[l]);
+                dst[l * N + n] = acc;
+            }
+    }
+}
+
 /* sigma_g in evaluation form is the index permutation
  *   out[i] = in[pi(i)],  2*br(pi(i)) + 1 = g * (2*br(i) + 1) mod 2N. */
 void dpo_galois_perm(const dpo_ctx *c, uint64_t g, uint32_t *perm) {

@@ -77,6 +77,9 @@ void dpo_ct_mul_relin(const dpo_ctx *, const uint64_t *a, const uint64_t *b, con
                       uint64_t *out, size_t batch);
 /* pt: [L][N] eval form, shared by the batch */
 void dpo_ct_mul_plain(const dpo_ctx *, const uint64_t *ct, const uint64_t *pt, uint64_t *out, size_t batch);
+/* out[g][k] = sum_b steps[b][k] o pts[g][b]; steps [nb][batch][2][L][N], pts [ng][nb][L][N], out [ng][batch][2][L][N] */
+void dpo_ct_mul_plain_inner(const dpo_ctx *, const uint64_t *steps, size_t nb, const uint64_t *pts, size_t ng, uint64_t *out,
+                            size_t batch);
 /* galois_elt odd in [1, 2N); gk is the switch key for sigma_g(s) */
 void dpo_rotate(const dpo_ctx *, const uint64_t *ct, uint64_t galois_elt, const uint64_t *gk,
                 uint64_t *out, size_t batch);

@@ -86,6 +86,14 @@ class Emu:
                                      out.reshape(-1), batch, int(galois), int(t_plain), G or 2 * self.L) == 0
         return out
 
+    def pt_inner(self, steps, pts, gmax=0):
+        steps = np.ascontiguousarray(steps, dtype=np.uint64)
+        pts = np.ascontiguousarray(pts, dtype=np.uint64)
+        nb, batch, ng = steps.shape[0], steps.shape[1], pts.shape[0]
+        out = np.zeros((ng, batch, 2, self.L, self.N), dtype=np.uint64)
+        assert self._l.emu_pt_inner(self._h, steps.reshape(-1), nb, pts.reshape(-1), ng, out.reshape(-1), batch, gmax) == 0
+        return out
+
     def mod_switch(self, polys, t_plain=0):
         x = np.ascontiguousarray(polys, dtype=np.uint64).reshape(-1, self.L, self.N)
         out = np.zeros((x.shape[0], self.L - 1, self.N), dtype=np.uint64)
@@ -119,6 +127,7 @@ def emu_lib():
     lib.emu_ntt.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int]
     lib.emu_ks.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint]
     lib.emu_ks_hybrid.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_uint]
+    lib.emu_pt_inner.argtypes = [C.c_void_p, _u64p, C.c_uint, _u64p, C.c_uint, _u64p, C.c_size_t, C.c_uint]
     lib.emu_mod_switch.argtypes = [C.c_void_p, _u64p, _u64p, C.c_size_t, C.c_uint64]
     for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2)):
         f = getattr(lib, "emu_" + nm)

@@ -239,6 +239,33 @@ int emu_ks_hybrid(void *h, int mode, const uint64_t *a, const uint64_t *b, const
     return -1;
 }
 
+// plaintext inner products: the device tile body over all (limb, tile) pairs, g-blocks of `gmax` giant steps
+int emu_pt_inner(void *h, const uint64_t *steps, unsigned nb, const uint64_t *pts, unsigned ng, uint64_t *out, size_t batch, unsigned gmax) {
+    Emu *e = (Emu *)h;
+    PtInnerArgs A;
+    A.steps = steps; A.pts = pts; A.out = out; A.batch = batch; A.L = e->hp.L; A.nb = nb; A.ng = ng;
+    if (gmax == 0) gmax = ng;
+    uint64_t *smem = aligned_new<uint64_t>(((size_t)gmax + 2) * nb * PTI_COEFFS);
+    auto run = [&](auto logn_tag) {
+        constexpr int LOGN = decltype(logn_tag)::value;
+        HostCta cta{256};
+        const unsigned tiles = (1u << LOGN) / PTI_COEFFS;
+        for (unsigned g0 = 0; g0 < ng; g0 += gmax)
+            for (unsigned l = 0; l < e->hp.L; ++l)
+                for (unsigned t = 0; t < tiles; ++t)
+                    pt_inner_tile<LOGN, 256>(cta, smem, A, e->lp[l], l, t, g0, ng - g0 < gmax ? ng - g0 : gmax);
+    };
+    int rc = 0;
+    switch (e->hp.log_n) {
+        case 12: run(std::integral_constant<int, 12>{}); break;
+        case 13: run(std::integral_constant<int, 13>{}); break;
+        case 14: run(std::integral_constant<int, 14>{}); break;
+        default: rc = -1;
+    }
+    free(smem);
+    return rc;
+}
+
 // modulus switching through the same bodies the device runs
 int emu_mod_switch(void *h, const uint64_t *in, uint64_t *out, size_t n_polys, uint64_t t_plain) {
     Emu *e = (Emu *)h;

@@ -120,10 +120,16 @@ def test_encrypted_linear_layer_bsgs(oracle_mod):
         diag[d] = dev(to_rns_eval(o, enc.encode(slots)))
     out = torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda")
     n0 = ctx.launch_count()
-    ctx.linear_bsgs(dev(ct), diag, dev(gk1), dev(gkb), BABY, out, B)
+    ctx.linear_bsgs(dev(ct), diag, dev(gk1), dev(gkb), BABY, out, B)                 # fused inner products (default)
     torch.cuda.synchronize()
     n_rot = (BABY - 1) + (DIM // BABY - 1)
-    assert ctx.launch_count() - n0 == 2 * n_rot + DIM + (DIM // BABY - 1)     # rotations (2 launches each), mults, adds
+    assert ctx.launch_count() - n0 == 2 * n_rot + 1 + (DIM // BABY - 1)     # rotations (2 launches each), one inner-product launch, adds
+    ref = torch.empty_like(out)
+    n0 = ctx.launch_count()
+    ctx.linear_bsgs(dev(ct), diag, dev(gk1), dev(gkb), BABY, ref, B, fused=False)    # composition of ct_mul_plain(_acc)
+    torch.cuda.synchronize()
+    assert ctx.launch_count() - n0 == 2 * n_rot + DIM + (DIM // BABY - 1)
+    assert torch.equal(out, ref)                                                     # same bits either way
     res = host(out).reshape(B, 2, L, N)
     for b in range(B):
         y = enc.decode(o.decrypt(s, res[b], T_PLAIN))[0, :DIM].astype(np.int64)
@@ -135,4 +141,26 @@ def test_encrypted_linear_layer_bsgs(oracle_mod):
     d_acc = dev(acc)
     ctx.ct_mul_plain_acc(dev(ct), diag[5], d_acc, B)
     assert np.array_equal(host(d_acc).reshape(acc.shape), o.poly_add(acc, o.ct_mul_plain(ct, pt)))
+    ctx.close()
+
+
+@pytest.mark.parametrize("log_n,L,nb,ng,batch", [(12, 2, 5, 3, 3), (12, 1, 33, 29, 2), (13, 4, 32, 24, 2), (14, 2, 16, 9, 1), (12, 3, 256, 2, 1)])
+def test_plain_inner_products(oracle_mod, log_n, L, nb, ng, batch):
+    """dpfhe_ct_mul_plain_inner against the oracle: ragged sizes, several giant-step blocks, worst-case residues"""
+    import deeppowers_b200 as dp
+    o = oracle_mod.Oracle(log_n, L)
+    ctx = dp.Context(log_n, L)
+    steps = o.fill_uniform(51, nb * batch * 2).reshape(nb, batch, 2, L, o.N)
+    pts = o.fill_uniform(52, ng * nb).reshape(ng, nb, L, o.N)
+    q = np.array(o.moduli, dtype=np.uint64)
+    steps[:, 0, 0] = (q - 1)[:, None]
+    pts[0] = (q - 1)[:, None]
+    pts[-1, :, :, ::3] = 0
+    out = torch.full((ng, batch, 2, L, o.N), -1, dtype=torch.int64, device="cuda")
+    n0 = ctx.launch_count()
+    ctx.ct_mul_plain_inner(dev(steps), dev(pts), out, nb, ng, batch)
+    assert np.array_equal(host(out).reshape(ng, batch, 2, L, o.N), o.ct_mul_plain_inner(steps, pts))
+    assert ctx.launch_count() - n0 >= 1
+    with pytest.raises(RuntimeError, match="n_steps"):
+        ctx.ct_mul_plain_inner(dev(steps), dev(pts), out, 257, ng, batch)
     ctx.close()

@@ -88,6 +88,19 @@ def test_emulated_mod_switch_bodies(make_emu, oracle_mod, log_n, L, t):
     assert np.array_equal(e.mod_switch(x, t), o.mod_switch_down(x, t))
 
 
+@pytest.mark.parametrize("log_n,L,nb,ng,batch,gmax", [(12, 2, 5, 3, 2, 0), (12, 1, 33, 10, 1, 4), (13, 2, 16, 9, 1, 8)])
+def test_emulated_plain_inner_products(make_emu, oracle_mod, log_n, L, nb, ng, batch, gmax):
+    """BSGS inner loop: split-operand accumulation, flush every 16 products, ragged giant-step blocks, edge residues"""
+    e, o = make_emu(log_n, L), oracle_mod.Oracle(log_n, L)
+    steps = o.fill_uniform(41, nb * batch * 2).reshape(nb, batch, 2, L, o.N)
+    pts = o.fill_uniform(42, ng * nb).reshape(ng, nb, L, o.N)
+    q = np.array(o.moduli, dtype=np.uint64)
+    steps[:, 0, 0] = (q - 1)[:, None]      # worst case for the 64-bit accumulators: every product (q-1)^2
+    pts[0] = (q - 1)[:, None]
+    pts[-1, :, :, ::3] = 0
+    assert np.array_equal(e.pt_inner(steps, pts, gmax), o.ct_mul_plain_inner(steps, pts))
+
+
 def _hybrid_inputs(o, batch, seed):
     """[batch][2][L-1][N] uniform residues (with edge rows) under the first L-1 moduli, and a uniform hybrid key"""
     Lq = o.L - 1

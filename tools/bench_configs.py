@@ -81,13 +81,20 @@ def cfg4():
     BABY = 32
     gkb = torch.empty((L, 2, L, N), dtype=torch.int64, device="cuda")
     c.fill_uniform(0xD3390304, gkb, 2 * L)
-    scratch = torch.empty((BABY + 2, B, 2, L, N), dtype=torch.int64, device="cuda")
+    GIANT = DIM // BABY
+    scratch = torch.empty((BABY + GIANT + 1, B, 2, L, N), dtype=torch.int64, device="cuda")
+    ms_bsgs_unfused = timed(lambda: c.linear_bsgs(cur, diag, gk, gkb, BABY, acc, B, scratch=scratch, fused=False), 2)
     ms_bsgs = timed(lambda: c.linear_bsgs(cur, diag, gk, gkb, BABY, acc, B, scratch=scratch), 2)
+    t_inner = timed(lambda: c.ct_mul_plain_inner(scratch[:BABY], diag, scratch[BABY:BABY + GIANT], BABY, GIANT, B), 3)
     t_fma = timed(lambda: c.ct_mul_plain_acc(cur, diag[1], acc, B), 20)
     c.close()
     return {"config": "cfg4 encrypted 768x768 linear layer N=8192 L=4 batch=512 (diagonal method, one Galois key)",
             "ms_per_layer_batch": ms, "prompts_per_s": B / ms * 1e3,
-            "bsgs": {"baby": BABY, "rotations": BABY - 1 + DIM // BABY - 1, "ms_per_layer_batch": ms_bsgs, "prompts_per_s": B / ms_bsgs * 1e3},
+            "bsgs": {"baby": BABY, "rotations": BABY - 1 + DIM // BABY - 1, "ms_per_layer_batch": ms_bsgs, "prompts_per_s": B / ms_bsgs * 1e3,
+                     "unfused_ms_per_layer_batch": ms_bsgs_unfused, "unfused_prompts_per_s": B / ms_bsgs_unfused * 1e3},
+            "ct_mul_plain_inner": {"ms": t_inner, "ct_pt_products_per_s": B * DIM / t_inner * 1e3,
+                                   "GBps": B * (BABY + GIANT) * 2 * P / t_inner / 1e6, "frac_hbm": B * (BABY + GIANT) * 2 * P / t_inner / 1e6 / PEAK,
+                                   "note": "768 ct x pt products per prompt in one launch; traffic = 32 ciphertext rows in + 24 out per prompt"},
             "ct_mul_plain_acc": {"per_s": B / t_fma * 1e3, "GBps": B * 6 * P / t_fma / 1e6, "frac_hbm": B * 6 * P / t_fma / 1e6 / PEAK},
             "ct_mul_plain": {"per_s": B / t_pt * 1e3, "GBps": B * 4 * P / t_pt / 1e6, "frac_hbm": B * 4 * P / t_pt / 1e6 / PEAK},
             "rotate": {"per_s": B / t_rot * 1e3, "GBps": B * 4 * P / t_rot / 1e6, "frac_hbm": B * 4 * P / t_rot / 1e6 / PEAK},
