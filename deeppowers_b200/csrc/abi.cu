@@ -439,7 +439,7 @@ int dpfhe_ct_mul_plain_inner(dpfhe_ctx *ctx, const uint64_t *d_steps, size_t n_s
     if (rc) return rc;
     if (batch == 0 || n_groups == 0) return DPFHE_OK;
     CHECK_PTR(d_steps); CHECK_PTR(d_pts); CHECK_PTR(d_out);
-    if (n_steps == 0 || n_steps > 256) return fail(DPFHE_ERR_INVALID, "n_steps must be in [1, 256]");
+    if (n_steps == 0 || n_steps > 128) return fail(DPFHE_ERR_INVALID, "n_steps must be in [1, 128]");
     if (n_groups > 65535) return fail(DPFHE_ERR_INVALID, "n_groups must be below 65536");
     if (d_out == d_steps) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
     unsigned launches = 0;

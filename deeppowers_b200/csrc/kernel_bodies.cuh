@@ -568,7 +568,7 @@ DPFHE_HD u64 pti_fold(u64 a0, u64 a1a, u64 a1b, u64 a2, const LimbParams &p) {
     return word_reduce(barrett_lazy_long(hi, lo, p), p);
 }
 
-// shared memory: (gcnt * nb + 2 * nb) * 16 words
+// shared memory: (gcnt * nb + 4 * nb) * 16 words (plaintext tile + two ciphertext-row buffers)
 template <int LOGN, int NT, class CTA>
 DPFHE_HD void pt_inner_tile(CTA &cta, u64 *smem, const PtInnerArgs &A, const LimbParams &p, u32 limb, u32 tile, u32 g0, u32 gcnt) {
     constexpr size_t N = (size_t)1 << LOGN;
@@ -577,7 +577,7 @@ DPFHE_HD void pt_inner_tile(CTA &cta, u64 *smem, const PtInnerArgs &A, const Lim
     const size_t P = (size_t)A.L * N, col = (size_t)limb * N + (size_t)tile * PTI_COEFFS;
     const u32 nb = A.nb;
     u64 *ps = smem;                                       // [gcnt][nb][16] split plaintext values
-    u64 *xs = smem + (size_t)gcnt * nb * PTI_COEFFS;      // [nb][2][16] split ciphertext values of one batch element
+    u64 *xs = smem + (size_t)gcnt * nb * PTI_COEFFS;      // 2 x [nb][2][16] split ciphertext values (double buffer)
     cta.par([&](int tid) {
         for (u32 idx = (u32)tid; idx < gcnt * nb * 8; idx += NT) {
             const u32 r = idx >> 3, ch = idx & 7, g = r / nb, b = r % nb;
@@ -586,18 +586,35 @@ DPFHE_HD void pt_inner_tile(CTA &cta, u64 *smem, const PtInnerArgs &A, const Lim
             ps[r * 16 + ch * 2 + 1] = pti_split(v.y);
         }
     });
+    // x rows of batch element k -> split halves in buffer xs + (k & 1) * nb * 32; a thread moves chunks tid, tid + NT, ...
+    auto x_src = [&](size_t k, u32 idx) {
+        const u32 r = idx >> 3, ch = idx & 7, b = r >> 1, comp = r & 1;
+        return reinterpret_cast<const U64x2 *>(A.steps + (((size_t)b * A.batch + k) * 2 + comp) * P + col) + ch;
+    };
+    const u32 n_chunks = nb * 2 * 8;
+    cta.par([&](int tid) {
+        for (u32 idx = (u32)tid; idx < n_chunks; idx += NT) {
+            const U64x2 v = ld_stream(x_src(0, idx));
+            xs[idx * 2] = pti_split(v.x);
+            xs[idx * 2 + 1] = pti_split(v.y);
+        }
+    });
     for (size_t k = 0; k < A.batch; ++k) {
-        cta.par([&](int tid) {
-            for (u32 idx = (u32)tid; idx < nb * 2 * 8; idx += NT) {
-                const u32 r = idx >> 3, ch = idx & 7, b = r >> 1, comp = r & 1;
-                const U64x2 v = ld_stream(reinterpret_cast<const U64x2 *>(A.steps + (((size_t)b * A.batch + k) * 2 + comp) * P + col) + ch);
-                xs[r * 16 + ch * 2] = pti_split(v.x);
-                xs[r * 16 + ch * 2 + 1] = pti_split(v.y);
-            }
-        });
+        const u64 *xcur = xs + (k & 1) * (size_t)nb * 32;
+        u64 *xnext = xs + ((k + 1) & 1) * (size_t)nb * 32;
         cta.par([&](int tid) {
             const u32 lane = (u32)tid & 31u, c = lane & 15u, comp = lane >> 4, w = (u32)tid >> 5;
-            const u64 *xrow = xs + comp * 16 + c;   // + b * 32
+            // the next batch element's rows are requested before this one's arithmetic and parked in the other buffer
+            // after it: one barrier per batch element, global latency hidden behind the multiply-accumulates
+            constexpr int PF = 4;   // 16-byte chunks a thread keeps in flight: covers nb <= 64; larger nb loads after the arithmetic
+            U64x2 nx[PF];
+            const bool more = k + 1 < A.batch, fits = n_chunks <= (u32)NT * PF;
+            if (more && fits) {
+#pragma unroll
+                for (int u = 0; u < PF; ++u)
+                    if ((u32)tid + (u32)u * NT < n_chunks) nx[u] = ld_stream(x_src(k + 1, (u32)tid + (u32)u * NT));
+            }
+            const u64 *xrow = xcur + comp * 16 + c;   // + b * 32
             for (u32 gb = w; gb < gcnt; gb += NW * PTI_GBLK) {   // this thread's outputs: g = gb + j * NW (warp-uniform)
                 // rows past the end of the block are computed on a clamped index and not stored: no branches in the loop
                 const u64 *prow[PTI_GBLK];
@@ -636,6 +653,24 @@ DPFHE_HD void pt_inner_tile(CTA &cta, u64 *smem, const PtInnerArgs &A, const Lim
                 for (int j = 0; j < PTI_GBLK; ++j) {
                     const u32 g = gb + (u32)j * NW;
                     if (g < gcnt) st_stream64(A.out + (((size_t)(g0 + g) * A.batch + k) * 2 + comp) * P + col + c, canon4(sum[j], p));
+                }
+            }
+            if (more) {
+                if (fits) {
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        const u32 idx = (u32)tid + (u32)u * NT;
+                        if (idx < n_chunks) {
+                            xnext[idx * 2] = pti_split(nx[u].x);
+                            xnext[idx * 2 + 1] = pti_split(nx[u].y);
+                        }
+                    }
+                } else {
+                    for (u32 idx = (u32)tid; idx < n_chunks; idx += NT) {
+                        const U64x2 v = ld_stream(x_src(k + 1, idx));
+                        xnext[idx * 2] = pti_split(v.x);
+                        xnext[idx * 2 + 1] = pti_split(v.y);
+                    }
                 }
             }
         });

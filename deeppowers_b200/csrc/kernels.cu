@@ -613,9 +613,9 @@ static cudaError_t launch_pt_inner_t(const LaunchCtx &lc, const PtInnerArgs &A, 
     constexpr int NT = 256, MINB = 2;
     auto kern = pt_inner_kernel<LOGN, NT, MINB>;
     // two CTAs per SM: at most 112 KiB each; the plaintext tile takes nb * 128 bytes per giant step
-    const size_t budget = (size_t)112 << 10, row = (size_t)A.nb * PTI_COEFFS * 8;
-    if (3 * row > budget) return cudaErrorInvalidValue;
-    u32 gmax = (u32)((budget - 2 * row) / row);
+    const size_t budget = (size_t)113 << 10, row = (size_t)A.nb * PTI_COEFFS * 8;
+    if (5 * row > budget) return cudaErrorInvalidValue;
+    u32 gmax = (u32)((budget - 4 * row) / row);
     if (gmax >= NT / 32) gmax -= gmax % (NT / 32);   // whole rounds of warps
     static bool configured[64] = {};
     if (!configured[lc.device & 63]) {
@@ -626,7 +626,7 @@ static cudaError_t launch_pt_inner_t(const LaunchCtx &lc, const PtInnerArgs &A, 
     const unsigned grid = (unsigned)(lc.L * (((size_t)1 << LOGN) / PTI_COEFFS));
     for (u32 g0 = 0; g0 < A.ng; g0 += gmax) {
         const u32 gcnt = A.ng - g0 < gmax ? A.ng - g0 : gmax;
-        const size_t smem = ((size_t)gcnt + 2) * row;
+        const size_t smem = ((size_t)gcnt + 4) * row;
         kern<<<grid, NT, smem, st>>>(A, lc.lt, g0, gcnt);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -641,9 +641,9 @@ cudaError_t launch_pt_inner(const LaunchCtx &lc, const u64 *steps, u32 nb, const
     if (!batch || !nb || !ng) return cudaSuccess;
     PtInnerArgs A;
     A.steps = steps; A.pts = pts; A.out = out; A.batch = batch; A.L = lc.L; A.nb = nb; A.ng = ng;
-    const size_t budget = (size_t)112 << 10, row = (size_t)nb * PTI_COEFFS * 8;
-    if (3 * row > budget) return cudaErrorInvalidValue;
-    u32 gmax = (u32)((budget - 2 * row) / row);
+    const size_t budget = (size_t)113 << 10, row = (size_t)nb * PTI_COEFFS * 8;
+    if (5 * row > budget) return cudaErrorInvalidValue;
+    u32 gmax = (u32)((budget - 4 * row) / row);
     if (gmax >= 8) gmax -= gmax % 8;
     *launches = (ng + gmax - 1) / gmax;
     switch (lc.log_n) {

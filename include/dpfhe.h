@@ -114,7 +114,7 @@ int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, cons
  *      out[g][k] = sum_{b < n_steps} steps[b][k] o pts[g][b]   for g < n_groups, k < batch
  *      steps [n_steps][batch][2][L][N] ciphertext batches, pts [n_groups][n_steps][L][N] plaintexts (evaluation form,
  *      shared by the batch), out [n_groups][batch][2][L][N].  Bit-identical to dpfhe_ct_mul_plain followed by
- *      n_steps-1 dpfhe_ct_mul_plain_acc per group, but every ciphertext row is read once. n_steps <= 256. ---- */
+ *      n_steps-1 dpfhe_ct_mul_plain_acc per group, but every ciphertext row is read once. n_steps <= 128. ---- */
 int dpfhe_ct_mul_plain_inner(dpfhe_ctx *ctx, const uint64_t *d_steps, size_t n_steps, const uint64_t *d_pts, size_t n_groups,
                              uint64_t *d_out, size_t batch, void *stream);
 

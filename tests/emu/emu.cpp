@@ -245,7 +245,7 @@ int emu_pt_inner(void *h, const uint64_t *steps, unsigned nb, const uint64_t *pt
     PtInnerArgs A;
     A.steps = steps; A.pts = pts; A.out = out; A.batch = batch; A.L = e->hp.L; A.nb = nb; A.ng = ng;
     if (gmax == 0) gmax = ng;
-    uint64_t *smem = aligned_new<uint64_t>(((size_t)gmax + 2) * nb * PTI_COEFFS);
+    uint64_t *smem = aligned_new<uint64_t>(((size_t)gmax + 4) * nb * PTI_COEFFS);
     auto run = [&](auto logn_tag) {
         constexpr int LOGN = decltype(logn_tag)::value;
         HostCta cta{256};

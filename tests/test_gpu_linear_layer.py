@@ -144,7 +144,7 @@ def test_encrypted_linear_layer_bsgs(oracle_mod):
     ctx.close()
 
 
-@pytest.mark.parametrize("log_n,L,nb,ng,batch", [(12, 2, 5, 3, 3), (12, 1, 33, 29, 2), (13, 4, 32, 24, 2), (14, 2, 16, 9, 1), (12, 3, 256, 2, 1)])
+@pytest.mark.parametrize("log_n,L,nb,ng,batch", [(12, 2, 5, 3, 3), (12, 1, 33, 29, 2), (13, 4, 32, 24, 2), (14, 2, 16, 9, 1), (12, 3, 128, 5, 1)])
 def test_plain_inner_products(oracle_mod, log_n, L, nb, ng, batch):
     """dpfhe_ct_mul_plain_inner against the oracle: ragged sizes, several giant-step blocks, worst-case residues"""
     import deeppowers_b200 as dp
@@ -162,5 +162,5 @@ def test_plain_inner_products(oracle_mod, log_n, L, nb, ng, batch):
     assert np.array_equal(host(out).reshape(ng, batch, 2, L, o.N), o.ct_mul_plain_inner(steps, pts))
     assert ctx.launch_count() - n0 >= 1
     with pytest.raises(RuntimeError, match="n_steps"):
-        ctx.ct_mul_plain_inner(dev(steps), dev(pts), out, 257, ng, batch)
+        ctx.ct_mul_plain_inner(dev(steps), dev(pts), out, 129, ng, batch)
     ctx.close()
