@@ -131,6 +131,12 @@ public:
                                           void *stream = nullptr) {
         check(dpfhe_ct_mul_plain_acc(ctx_, ct, plain_eval, acc, count, stream));
     }
+    // out[g][k] = sum_b steps[b][k] o plain[g][b]: the fused inner loop of a baby-step/giant-step matrix-vector product
+    // (steps [n_steps][count] ciphertexts, plain [n_groups][n_steps] plaintexts in evaluation form, out [n_groups][count])
+    void multiply_plain_inner_device(const std::uint64_t *steps, std::size_t n_steps, const std::uint64_t *plain, std::size_t n_groups,
+                                     std::uint64_t *out, std::size_t count, void *stream = nullptr) {
+        check(dpfhe_ct_mul_plain_inner(ctx_, steps, n_steps, plain, n_groups, out, count, stream));
+    }
     // drop the last limb of `count` ciphertexts (2*count polynomials); the result belongs to the first L-1 moduli
     void mod_switch_to_next_device(const std::uint64_t *ct, std::uint64_t *out, std::size_t count, std::uint64_t plain_modulus = 0,
                                    void *stream = nullptr) {
