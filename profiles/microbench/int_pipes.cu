@@ -92,6 +92,18 @@ __global__ void __launch_bounds__(1024) bench(unsigned long long *out, long long
 #pragma unroll
             for (int c = 0; c < CH; ++c) { r32[c] = r32[c] + b; asm volatile("" : "+r"(r32[c])); r32[c] = r32[c] + a; asm volatile("" : "+r"(r32[c])); }
         }
+        if (OP == 27) {   // IMAD.WIDE with 64-bit addend, multiplicand taken from the chain itself (OP 0's product is loop-invariant and hoisted)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) asm volatile("{.reg .u32 l, h; mov.b64 {l, h}, %0; mad.wide.u32 %0, l, %1, %0;}" : "+l"(acc[c]) : "r"(b));
+        }
+        if (OP == 28) {   // IMAD.WIDE without addend, same dependence
+#pragma unroll
+            for (int c = 0; c < CH; ++c) asm volatile("{.reg .u32 l, h; mov.b64 {l, h}, %0; mul.wide.u32 %0, l, %1;}" : "+l"(acc[c]) : "r"(b));
+        }
+        if (OP == 29) {   // IMAD (32-bit) with the multiplicand from the chain
+#pragma unroll
+            for (int c = 0; c < CH; ++c) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r32[c]) : "r"(b), "r"(a));
+        }
         if (OP == 24) {   // DFMA only (fp64 pipe): could the idle fp64 lanes carry part of the modular arithmetic?
 #pragma unroll
             for (int c = 0; c < CH; ++c) { double f = __longlong_as_double((long long)acc[c]); asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f) : "d"(1.0000001), "d"(0.5)); acc[c] = (u64)__double_as_longlong(f); }
@@ -187,6 +199,9 @@ int main() {
         run<14>("lop3 x8", CH, p, threads);
         run<15>("FFMA x8", CH, p, threads);
         run<16>("4 IMAD + 4 FFMA mixed", CH, p, threads);
+        run<27>("IMAD.WIDE + addend (chain-fed)", CH, p, threads);
+        run<28>("IMAD.WIDE no addend (chain-fed)", CH, p, threads);
+        run<29>("IMAD lo (chain-fed)", CH, p, threads);
         run<24>("DFMA x8", CH, p, threads);
         run<25>("4 IMAD.WIDE + 4 DFMA mixed", CH, p, threads);
         run<26>("4 IMAD + 4 DFMA mixed", CH, p, threads);
