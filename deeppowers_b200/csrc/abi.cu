@@ -57,6 +57,11 @@ struct dpfhe_ctx {
     // staging for the host-buffer entry points (allocated on first use)
     u64 *ms_tau = nullptr;                   // scratch of dpfhe_mod_switch_down: [n_polys][N]
     size_t ms_tau_bytes = 0;
+    // hoisted rotations (allocated on first use): shared transforms U [chunk][L][L][N], zero flags [chunk],
+    // per-rotation constants M [L][N] and kprime [2][L][N], and the table delta[j][i] = q_j mod q_i
+    u64 *hoist_U = nullptr, *hoist_M = nullptr, *hoist_kprime = nullptr, *hoist_delta = nullptr;
+    u32 *hoist_zero = nullptr;
+    size_t hoist_chunk = 0;                  // ciphertexts the current U / zero buffers hold
     u64 *stage_in[PIPE_DEPTH] = {}, *stage_out[PIPE_DEPTH] = {}, *stage_key = nullptr;
     size_t stage_in_bytes = 0, stage_out_bytes = 0, stage_key_bytes = 0;
     cudaEvent_t ev_h2d[PIPE_DEPTH] = {}, ev_comp[PIPE_DEPTH] = {}, ev_d2h[PIPE_DEPTH] = {};
@@ -254,6 +259,11 @@ void dpfhe_context_destroy(dpfhe_ctx *ctx) {
     cudaFree(ctx->lc.ks_prof);
     cudaFree(ctx->stage_key);
     cudaFree(ctx->ms_tau);
+    cudaFree(ctx->hoist_U);
+    cudaFree(ctx->hoist_M);
+    cudaFree(ctx->hoist_kprime);
+    cudaFree(ctx->hoist_delta);
+    cudaFree(ctx->hoist_zero);
     cudaFree(ctx->lc.ks_hyb);
     for (int k = 0; k < PIPE_DEPTH; ++k) {
         cudaFree(ctx->stage_in[k]);
@@ -411,6 +421,73 @@ int dpfhe_ct_mul_relin_hybrid(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_
 int dpfhe_rotate_hybrid(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk, uint64_t *d_out, size_t batch,
                         uint64_t t_plain, void *stream) {
     return ks_hybrid_common(ctx, KS_ROTATE, d_ct, nullptr, d_gk, d_out, batch, galois_elt, t_plain, stream);
+}
+
+// Hoisted rotations: n_rot rotations of the SAME ciphertexts.  Bit-identical to n_rot calls of dpfhe_rotate; the digit
+// decomposition and its L(L-1) forward transforms are done once per ciphertext (kernels.cu: ks_hoist_kernel), each
+// rotation is then gathers + multiply-accumulates (rot_apply_kernel).  Ciphertexts whose digit has a zero coefficient
+// (where the shared-transform identity does not hold) are recomputed by the ordinary rotate kernel.
+int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, const uint64_t *galois_elts, const uint64_t *const *d_gks,
+                         uint64_t *d_out, size_t batch, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0 || n_rot == 0) return DPFHE_OK;
+    CHECK_PTR(d_ct); CHECK_PTR(d_out);
+    if (!galois_elts || !d_gks) return fail(DPFHE_ERR_INVALID, "null argument");
+    const uint64_t two_n = (uint64_t)2 << ctx->hp.log_n;
+    const size_t N = ctx->N(), L = ctx->hp.L, P = ctx->P();
+    for (size_t r = 0; r < n_rot; ++r) {
+        if (!(galois_elts[r] & 1) || galois_elts[r] >= two_n) return fail(DPFHE_ERR_INVALID, "galois element must be odd and < 2N");
+        if (!d_gks[r] || !aligned16(d_gks[r])) return fail(DPFHE_ERR_INVALID, "null or misaligned Galois key");
+        const uint64_t *o = d_out + r * batch * 2 * P;
+        if (o == d_ct) return fail(DPFHE_ERR_INVALID, "output must not alias the input");
+    }
+    cudaStream_t st = pick(ctx, stream);
+    // scratch: at most ~4 GiB of shared transforms at a time (the batch is processed in chunks of that many ciphertexts)
+    const size_t per_ct = L * L * N * sizeof(u64);
+    size_t chunk = ((size_t)4 << 30) / per_ct;
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    if (chunk > ctx->hoist_chunk) {
+        CU_TRY(cudaStreamSynchronize(st));
+        cudaFree(ctx->hoist_U);
+        cudaFree(ctx->hoist_zero);
+        ctx->hoist_U = nullptr;
+        ctx->hoist_zero = nullptr;
+        ctx->hoist_chunk = 0;
+        CU_TRY(cudaMalloc(&ctx->hoist_U, chunk * per_ct));
+        CU_TRY(cudaMalloc(&ctx->hoist_zero, chunk * sizeof(u32)));
+        ctx->hoist_chunk = chunk;
+    }
+    if (!ctx->hoist_M) {
+        CU_TRY(cudaMalloc(&ctx->hoist_M, P * sizeof(u64)));
+        CU_TRY(cudaMalloc(&ctx->hoist_kprime, 2 * P * sizeof(u64)));
+        CU_TRY(cudaMalloc(&ctx->hoist_delta, L * L * sizeof(u64)));
+        std::vector<u64> delta(L * L);
+        for (size_t j = 0; j < L; ++j)
+            for (size_t i = 0; i < L; ++i) delta[j * L + i] = ctx->hp.limbs[j].lp.q % ctx->hp.limbs[i].lp.q;
+        CU_TRY(cudaMemcpy(ctx->hoist_delta, delta.data(), delta.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    }
+    for (size_t first = 0; first < batch; first += chunk) {
+        const size_t cnt = batch - first < chunk ? batch - first : chunk;
+        const u64 *in = d_ct + first * 2 * P;
+        CU_TRY(cudaMemsetAsync(ctx->hoist_zero, 0, cnt * sizeof(u32), st));
+        if (L > 1) {
+            CU_TRY(launch_hoist(ctx->lc, in, ctx->hoist_U, ctx->hoist_zero, cnt, st));
+            ctx->launches++;
+        }
+        for (size_t r = 0; r < n_rot; ++r) {
+            u64 *out = d_out + (r * batch + first) * 2 * P;
+            CU_TRY(launch_rot_prepare(ctx->lc, d_gks[r], (u32)galois_elts[r], ctx->hoist_delta, ctx->hoist_M, ctx->hoist_kprime, st));
+            CU_TRY(launch_rot_apply(ctx->lc, in, ctx->hoist_U, d_gks[r], ctx->hoist_kprime, (u32)galois_elts[r], out, cnt, st));
+            ctx->launches += 5;   // key_prepare, negmask, ntt, kprime, rot_apply
+            if (L > 1) {
+                CU_TRY(launch_ks(ctx->lc, KS_ROTATE, in, nullptr, d_gks[r], out, cnt, (u32)galois_elts[r], st, ctx->hoist_zero, true));
+                ctx->launches++;
+            }
+        }
+    }
+    return DPFHE_OK;
 }
 
 int dpfhe_ct_mul_plain(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_pt, uint64_t *d_out, size_t batch, void *stream) {

@@ -165,6 +165,7 @@ struct KsArgs {
     u32 galois;          // ROTATE only
     u32 Lk;              // limbs of a key polynomial: L, or L + 1 with a special prime (hybrid)
     u64 *hyb;            // hybrid only: [groups][KS_HYB_ROWS][N]: special-limb accumulators (rows 0,1) and tau'
+    const u32 *only;     // optional [batch]: process only the ciphertexts whose entry is non-zero (hoisted-rotation fallback)
 };
 // tau' rows of a hybrid group are double-buffered by round parity (the division step runs one round late)
 constexpr int KS_HYB_ROWS = 6;
@@ -519,6 +520,144 @@ DPFHE_HD void ms_limb_body(CTA &cta, u64 *buf, const u64 *tau, const u64 *c_limb
             });
         }
     }
+}
+
+// ---- hoisted rotations ---------------------------------------------------
+// Many rotations of the SAME ciphertexts share everything that does not depend on the Galois element: the inverse
+// transform of the digits and their forward transforms into every other limb.  With t_j = INTT_j(c1[j]) and
+// U_ji = NTT_i(t_j mod q_i), the digit of rotation g satisfies, in Z_{q_i},
+//     NTT_i( canonical(sigma_g t_j) mod q_i ) = perm_g(U_ji) + (q_j mod q_i) * NTT_i(negmask_g)
+// whenever no coefficient of t_j is zero: a negated coefficient is stored as q_j - t, and (q_j - t) mod q_i differs from
+// -(t mod q_i) by q_j mod q_i.  The data-independent second term is folded into a per-rotation constant (kprime).
+// Ciphertexts with a zero coefficient in some t_j are flagged and recomputed by the ordinary rotate kernel.
+struct HoistArgs {
+    const u64 *ct;       // [batch][2][L][N]
+    u64 *U;              // [batch][L j][L i][N]: NTT_i(t_j mod q_i), lazy (< 16 q_i); the diagonal j == i is not used
+    u64 *scratch;        // digit exchange slots, as KsArgs::scratch
+    u32 *zero;           // [batch] set to 1 when some t_j has a zero coefficient
+    const Twiddle *tw, *itw;
+    u32 L;
+};
+
+// digit = c1[i] as it is; publish its inverse transform
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void hoist_phase1(CTA &cta, u64 *buf, const HoistArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot) {
+    constexpr int N = 1 << LOGN, NC = N / 2;
+    const size_t P = (size_t)A.L * N;
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(A.ct + ct * 2 * P + P + (size_t)i * N);
+    const Twiddle *itw = A.itw + (size_t)i * N;
+    U64x2 *dst = reinterpret_cast<U64x2 *>(t_slot);
+    u32 *zero = A.zero + ct;
+    auto build = [&](int c_lo, int n_c) {
+        cta.par([&](int tid) {
+            for (int lc = tid; lc < n_c; lc += NT) reinterpret_cast<U64x2 *>(buf)[swz_chunk(lc)] = ld_stream(src + c_lo + lc);
+        });
+    };
+    auto emit = [&](int c, const U64x2 &v) {
+        if (v.x == 0 || v.y == 0) *zero = 1u;
+        st_cg(dst + c, v);
+    };
+    if constexpr (LOGN <= 13) {
+        build(0, NC);
+        inv_passes<LOGN, NT>(cta, buf, itw, p);
+        cta.par([&](int tid) { inv_store_stage<LOGN, NT>(buf, itw, p, tid, emit); });
+    } else {
+        constexpr int HC = NC / 2;
+        for (int h = 0; h < 2; ++h) {
+            build(h * HC, HC);
+            inv_passes_blk<LOGN, NT, 2>(cta, buf, itw, p, 2 * h);
+            cta.par([&](int tid) {
+                for (int lc = tid; lc < HC; lc += NT) st_cg(dst + h * HC + lc, reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lc)]);
+            });
+        }
+        cta.par([&](int tid) { inv_outer_stage<LOGN, NT>(itw, p, tid, [&](int c) { return ld_cg(dst + c); }, emit); });
+    }
+}
+
+// U[ct][j][i] = NTT_i(t_j mod q_i)
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void hoist_phase2(CTA &cta, u64 *buf, const HoistArgs &A, const LimbParams &p, size_t ct, u32 i, u32 j, const u64 *t_src) {
+    constexpr int N = 1 << LOGN, NC = N / 2;
+    const Twiddle *tw = A.tw + (size_t)i * N;
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(t_src);
+    U64x2 *dst = reinterpret_cast<U64x2 *>(A.U + ((ct * A.L + j) * A.L + i) * N);
+    if constexpr (LOGN <= 13) {
+        cta.par([&](int tid) { fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); }); });
+        fwd_passes<LOGN, NT, 3>(cta, buf, tw, p);
+        cta.par([&](int tid) {
+            for (int c = tid; c < NC; c += NT) st_stream(dst + c, reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)]);
+        });
+    } else {
+        constexpr int HC = NC / 2;
+        for (int h = 0; h < 2; ++h) {
+            cta.par([&](int tid) { fwd_load_stage_half<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); }, h); });
+            fwd_passes_blk<LOGN, NT, 3, 2>(cta, buf, tw, p, 2 * h);
+            cta.par([&](int tid) {
+                for (int lc = tid; lc < HC; lc += NT) st_stream(dst + h * HC + lc, reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lc)]);
+            });
+        }
+    }
+}
+
+// one (ciphertext, limb i) row pair of one rotation: out = (perm(c0) + ks0, ks1) with the switched pair assembled from the
+// shared transforms.  pi(2c + 1) = pi(2c) ^ 1 (flipping the lowest index bit flips the highest exponent bit, and g is odd),
+// so the two coefficients of an output chunk come from one 16-byte chunk of the source row.
+struct RotApplyArgs {
+    const u64 *ct;       // [batch][2][L][N]
+    const u64 *U;        // [batch][L][L][N]
+    const u64 *key;      // [L][2][L][N] Galois key of this rotation
+    const u64 *key_s;    // its Shoup companions
+    const u64 *kprime;   // [2][L][N] canonical: NTT_i(negmask_g) o sum_{j != i} (q_j mod q_i) * key[j][c][i]
+    u64 *out;            // [batch][2][L][N]
+    u32 L, galois;
+};
+
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void rot_apply_row(CTA &cta, const RotApplyArgs &A, const LimbParams &p, size_t ct, u32 i) {
+    constexpr int N = 1 << LOGN, NC = N / 2;
+    const u32 L = A.L, g = A.galois;
+    const size_t P = (size_t)L * N;
+    const U64x2 *c0 = reinterpret_cast<const U64x2 *>(A.ct + ct * 2 * P + (size_t)i * N);
+    const U64x2 *c1 = reinterpret_cast<const U64x2 *>(A.ct + ct * 2 * P + P + (size_t)i * N);
+    const U64x2 *kp0 = reinterpret_cast<const U64x2 *>(A.kprime + (size_t)i * N), *kp1 = reinterpret_cast<const U64x2 *>(A.kprime + P + (size_t)i * N);
+    U64x2 *o0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N), *o1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
+    cta.par([&](int tid) {
+#pragma unroll 1
+        for (int c = tid; c < NC; c += NT) {
+            const int pi0 = galois_index<LOGN>(2 * c, g);
+            const int pc = pi0 >> 1;
+            const bool swap = (pi0 & 1) != 0;
+            auto gather = [&](const U64x2 *row) {
+                const U64x2 v = ld_stream(row + pc);
+                U64x2 r;
+                r.x = swap ? v.y : v.x;
+                r.y = swap ? v.x : v.y;
+                return r;
+            };
+            U64x2 r0 = ld_keep(kp0 + c), r1 = ld_keep(kp1 + c);
+            const U64x2 s0 = gather(c0);
+            r0.x += s0.x;   // < 2q
+            r0.y += s0.y;
+            for (u32 j = 0; j < L; ++j) {
+                const U64x2 u = j == i ? gather(c1) : gather(reinterpret_cast<const U64x2 *>(A.U + ((ct * L + j) * L + i) * N));
+                const size_t kb = ((size_t)j * 2 + 0) * P + (size_t)i * N, ka = ((size_t)j * 2 + 1) * P + (size_t)i * N;
+                const U64x2 vb = ld_keep(reinterpret_cast<const U64x2 *>(A.key + kb) + c), vbs = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + kb) + c);
+                const U64x2 va = ld_keep(reinterpret_cast<const U64x2 *>(A.key + ka) + c), vas = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + ka) + c);
+                r0.x += shoup_lazy(u.x, vb.x, vbs.x, p);
+                r0.y += shoup_lazy(u.y, vb.y, vbs.y, p);
+                r1.x += shoup_lazy(u.x, va.x, vas.x, p);
+                r1.y += shoup_lazy(u.y, va.y, vas.y, p);
+                if ((j & 3u) == 3u) {   // + 2q per digit from below 2q: one csub(8q) every fourth digit keeps the sums below 16q
+                    r0.x = csub(r0.x, p.q8); r0.y = csub(r0.y, p.q8);
+                    r1.x = csub(r1.x, p.q8); r1.y = csub(r1.y, p.q8);
+                }
+            }
+            r0.x = canon(r0.x, p); r0.y = canon(r0.y, p);
+            r1.x = canon(r1.x, p); r1.y = canon(r1.y, p);
+            st_stream(o0 + c, r0);
+            st_stream(o1 + c, r1);
+        }
+    });
 }
 
 // ---- plaintext inner products: out[g] = sum_b steps[b] o pts[g][b]  (baby-step/giant-step inner loop) ----

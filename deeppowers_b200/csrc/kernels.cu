@@ -121,7 +121,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, u32 bytes) {
 // and posts it in the group's mailbox (dynamic balancing: groups that run ahead take more work);
 // the members exchange their INTT'd digits through `scratch` (double-buffered by round parity,
 // L2 resident) under release/acquire flags.
-template <int LOGN, int NT, int MINB, int MODE, bool PROF>
+// FILTER (hoisted-rotation fallback): only the ciphertexts flagged in A.only are processed; the digit slots then
+// alternate over the rounds that actually run.
+template <int LOGN, int NT, int MINB, int MODE, bool PROF, bool FILTER = false>
 __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __grid_constant__ LimbTable lt, size_t batch, u32 *flags, u32 epoch,
                                                             u32 *ticket, u64 *mail, unsigned long long *prof, u32 pf_dist) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
     __shared__ u32 s_ct;
     const u32 L = A.L, slot = blockIdx.x, i = slot % L, group = slot / L;
     const LimbParams &p = lt.lp[i];
+    u32 executed = 0;
     for (u32 round = 0;; ++round) {
         if (threadIdx.x == 0) {
             const u32 tag = epoch + round + 1;
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
         __syncthreads();
         const size_t ct = s_ct;
         if (ct >= batch) break;   // every member of the group reads the same ticket, so they leave together
+        if (FILTER && A.only[ct] == 0u) continue;
         // Tickets are drawn in order, so ciphertext ct + pf_dist will be started by some group a few microseconds
         // from now: pull this CTA's limb of its inputs from HBM into L2 with the TMA unit's bulk prefetch, so the
         // tensor phase that consumes them is L2- rather than HBM-latency bound.
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
                 }
             }
         }
-        const u32 parity = round & 1u;
+        const u32 parity = (FILTER ? executed++ : round) & 1u;
         ks_phase1<LOGN, NT, MODE>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N);
         if (L > 1) {
             __threadfence();
@@ -195,6 +199,92 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
         cta.prof[14] += t_end - t_start;
         cta.prof[15] += (unsigned long long)clock64() - c_start;
+    }
+}
+
+// Hoisted rotations, step 1: the same group / ticket / flag machinery as ks_fused_kernel, but the digits
+// are the unpermuted c1 limbs and phase 2 stores the lifted transforms U[ct][j][i] instead of multiplying them with a key.
+template <int LOGN, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ks_hoist_kernel(HoistArgs A, const __grid_constant__ LimbTable lt, size_t batch, u32 *flags, u32 epoch,
+                                                            u32 *ticket, u64 *mail) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr size_t N = (size_t)1 << LOGN;
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    DevCta<NT> cta;
+    __shared__ u32 s_ct;
+    const u32 L = A.L, slot = blockIdx.x, i = slot % L, group = slot / L;
+    const LimbParams &p = lt.lp[i];
+    for (u32 round = 0;; ++round) {
+        const u32 tag = epoch + round + 1;
+        if (threadIdx.x == 0) {
+            if (i == 0) {
+                const u32 t = atomicAdd(ticket, 1u);
+                st_release_u64(mail + group, ((u64)tag << 32) | t);
+                s_ct = t;
+            } else {
+                u64 m;
+                do m = ld_acquire_u64(mail + group);
+                while ((u32)(m >> 32) != tag);
+                s_ct = (u32)m;
+            }
+        }
+        __syncthreads();
+        const size_t ct = s_ct;
+        if (ct >= batch) break;
+        const u32 parity = round & 1u;
+        hoist_phase1<LOGN, NT>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_u32(flags + slot, tag);
+        for (u32 jj = 1; jj < L; ++jj) {
+            const u32 j = (i + jj) % L, sib = slot - i + j;
+            if (threadIdx.x == 0) {
+                while ((int)(ld_acquire_u32(flags + sib) - tag) < 0) {
+                }
+            }
+            __syncthreads();
+            hoist_phase2<LOGN, NT>(cta, buf, A, p, ct, i, j, A.scratch + ((size_t)sib * 2 + parity) * N);
+        }
+    }
+}
+
+// step 2: one rotation applied to every (ciphertext, limb) row pair; no transforms, only gathers and multiply-accumulates
+template <int LOGN, int NT>
+__global__ void __launch_bounds__(NT) rot_apply_kernel(RotApplyArgs A, const __grid_constant__ LimbTable lt, size_t n_rows) {
+    DevCta<NT> cta;
+    for (size_t w = blockIdx.x; w < n_rows; w += gridDim.x) {
+        const u32 i = (u32)(w % A.L);
+        rot_apply_row<LOGN, NT>(cta, A, lt.lp[i], w / A.L, i);
+    }
+}
+
+// coefficient-form indicator of the positions that sigma_g negates: X^k -> X^(kg mod 2N), negative when kg mod 2N >= N
+template <int LOGN>
+__global__ void __launch_bounds__(256) negmask_kernel(u64 *mask, u32 g, u32 L) {
+    constexpr u32 N = 1u << LOGN;
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
+        const u32 e = (k * g) & (2 * N - 1);
+        const u64 v = e >= N ? 1ull : 0ull;
+        for (u32 l = 0; l < L; ++l) mask[(size_t)l * N + (e & (N - 1))] = v;
+    }
+}
+
+// kprime[c][i][n] = M[i][n] * sum_{j != i} (q_j mod q_i) * key[j][c][i][n]  mod q_i, canonical
+template <int LOGN>
+__global__ void __launch_bounds__(256) kprime_kernel(const u64 *__restrict__ key, const u64 *__restrict__ M, const u64 *__restrict__ delta,
+                                                     u64 *__restrict__ out, const LimbParams *__restrict__ lps, u32 L) {
+    constexpr size_t N = (size_t)1 << LOGN;
+    const size_t P = (size_t)L * N, total = 2 * P;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const u32 c = (u32)(e / P), i = (u32)((e % P) / N);
+        const size_t n = e % N;
+        const LimbParams p = lps[i];
+        u64 s = 0;
+        for (u32 j = 0; j < L; ++j) {
+            if (j == i) continue;
+            s = csub(s + mulmod(key[((size_t)j * 2 + c) * P + (size_t)i * N + n], delta[j * L + i], p), p.q);
+        }
+        out[e] = mulmod(s, M[(size_t)i * N + n], p);
     }
 }
 
@@ -499,13 +589,17 @@ template <int LOGN, int MODE>
 static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cudaStream_t st) {
     // at most 64 KiB of shared memory per CTA (N = 16384 is processed as two half-limbs) -> three CTAs per SM
     constexpr int NT = 256, MINB = 3;
+    const bool filter = A.only != nullptr;
+    if (filter && MODE != KS_ROTATE) return cudaErrorInvalidValue;
     auto kern = lc.ks_prof ? ks_fused_kernel<LOGN, NT, MINB, MODE, true> : ks_fused_kernel<LOGN, NT, MINB, MODE, false>;
+    if (filter) kern = ks_fused_kernel<LOGN, NT, MINB, MODE == KS_ROTATE ? MODE : KS_ROTATE, false, MODE == KS_ROTATE>;
     const size_t smem = LOGN <= 13 ? Geometry<LOGN>::LIMB_BYTES : Geometry<13>::LIMB_BYTES;
-    static bool configured[2][64] = {};
-    if (!configured[lc.ks_prof ? 1 : 0][lc.device & 63]) {
+    static bool configured[3][64] = {};
+    const int variant = filter ? 2 : (lc.ks_prof ? 1 : 0);
+    if (!configured[variant][lc.device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[lc.ks_prof ? 1 : 0][lc.device & 63] = true;
+        configured[variant][lc.device & 63] = true;
     }
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
@@ -592,7 +686,7 @@ cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b
     }
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
-    A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L - 1; A.galois = galois; A.Lk = lc.L; A.hyb = lc.ks_hyb;
+    A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L - 1; A.galois = galois; A.Lk = lc.L; A.hyb = lc.ks_hyb; A.only = nullptr;
 #define KS_HYB_DISPATCH(LOGN)                                                                   \
     switch (mode) {                                                                             \
         case KS_MUL_RELIN: return launch_ks_hybrid_t<LOGN, KS_MUL_RELIN>(lc, A, K, batch, st);   \
@@ -654,11 +748,102 @@ cudaError_t launch_pt_inner(const LaunchCtx &lc, const u64 *steps, u32 nb, const
     return cudaErrorInvalidValue;
 }
 
+template <int LOGN>
+static cudaError_t launch_hoist_t(LaunchCtx &lc, const HoistArgs &A, size_t batch, cudaStream_t st) {
+    constexpr int NT = 256, MINB = 3;
+    auto kern = ks_hoist_kernel<LOGN, NT, MINB>;
+    const size_t smem = LOGN <= 13 ? Geometry<LOGN>::LIMB_BYTES : Geometry<13>::LIMB_BYTES;
+    static bool configured[64] = {};
+    if (!configured[lc.device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[lc.device & 63] = true;
+    }
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    size_t G = (size_t)lc.num_sms * occ;
+    if (G > lc.ks_slots) G = lc.ks_slots;
+    G = (G / lc.L) * lc.L;
+    if (G > batch * lc.L) G = batch * lc.L;
+    if (G == 0) return cudaErrorInvalidConfiguration;
+    cudaError_t em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
+    if (em != cudaSuccess) return em;
+    HoistArgs args = A;
+    LimbTable lt = lc.lt;
+    size_t batch_arg = batch;
+    u32 *flags = lc.ks_flags;
+    u32 epoch = lc.ks_epoch;
+    u32 *ticket = lc.ks_ticket;
+    u64 *mail = lc.ks_mail;
+    void *params[] = {&args, &lt, &batch_arg, &flags, &epoch, &ticket, &mail};
+    e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)G), dim3(NT), params, smem, st);
+    lc.ks_epoch += (u32)(batch + 1);
+    return e;
+}
+
+// hoisted rotations, step 1: U[ct][j][i] and the zero flags of `batch` ciphertexts (L >= 2)
+cudaError_t launch_hoist(LaunchCtx &lc, const u64 *ct, u64 *U, u32 *zero, size_t batch, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    HoistArgs A;
+    A.ct = ct; A.U = U; A.scratch = lc.ks_scratch; A.zero = zero; A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L;
+    switch (lc.log_n) {
+        case 12: return launch_hoist_t<12>(lc, A, batch, st);
+        case 13: return launch_hoist_t<13>(lc, A, batch, st);
+        case 14: return launch_hoist_t<14>(lc, A, batch, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// per-rotation constants: Shoup companions of the key (lc.ks_key_s), M = NTT(negmask_g) (in `M`, [L][N]) and kprime [2][L][N]
+cudaError_t launch_rot_prepare(LaunchCtx &lc, const u64 *key, u32 galois, const u64 *delta, u64 *M, u64 *kprime, cudaStream_t st) {
+    const size_t n = (size_t)2 * lc.L * lc.L << lc.log_n;
+    const unsigned grid = ew_grid(lc, n), gsmall = ew_grid(lc, (size_t)2 * lc.L << lc.log_n);
+#define ROT_PREP(LOGN)                                                                              \
+    key_prepare_kernel<LOGN><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);               \
+    negmask_kernel<LOGN><<<(1u << LOGN) / 256, 256, 0, st>>>(M, galois, lc.L);
+    switch (lc.log_n) {
+        case 12: ROT_PREP(12) break;
+        case 13: ROT_PREP(13) break;
+        case 14: ROT_PREP(14) break;
+        default: return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = launch_ntt(lc, M, 1, false, st);
+    if (e != cudaSuccess) return e;
+    switch (lc.log_n) {
+        case 12: kprime_kernel<12><<<gsmall, 256, 0, st>>>(key, M, delta, kprime, lc.lp, lc.L); break;
+        case 13: kprime_kernel<13><<<gsmall, 256, 0, st>>>(key, M, delta, kprime, lc.lp, lc.L); break;
+        case 14: kprime_kernel<14><<<gsmall, 256, 0, st>>>(key, M, delta, kprime, lc.lp, lc.L); break;
+    }
+    return cudaGetLastError();
+}
+
+// hoisted rotations, step 2: one rotation of `batch` ciphertexts from the shared transforms (constants from launch_rot_prepare)
+cudaError_t launch_rot_apply(const LaunchCtx &lc, const u64 *ct, const u64 *U, const u64 *key, const u64 *kprime, u32 galois, u64 *out,
+                             size_t batch, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    RotApplyArgs A;
+    A.ct = ct; A.U = U; A.key = key; A.key_s = lc.ks_key_s; A.kprime = kprime; A.out = out; A.L = lc.L; A.galois = galois;
+    const size_t n_rows = batch * lc.L;
+    const size_t cap = (size_t)lc.num_sms * 8;
+    const unsigned grid = (unsigned)(n_rows < cap ? n_rows : cap);
+    switch (lc.log_n) {
+        case 12: rot_apply_kernel<12, 256><<<grid, 256, 0, st>>>(A, lc.lt, n_rows); break;
+        case 13: rot_apply_kernel<13, 256><<<grid, 256, 0, st>>>(A, lc.lt, n_rows); break;
+        case 14: rot_apply_kernel<14, 256><<<grid, 256, 0, st>>>(A, lc.lt, n_rows); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch,
-                      u32 galois, cudaStream_t st) {
+                      u32 galois, cudaStream_t st, const u32 *only, bool key_ready) {
     if (batch == 0) return cudaSuccess;
     // Shoup companions of the key for this launch (2*L*P words, a few microseconds; batch-amortised)
-    {
+    if (!key_ready) {
         const size_t n = (size_t)2 * lc.L * lc.L << lc.log_n;
         const unsigned grid = ew_grid(lc, n);
         if (lc.log_n == 12) key_prepare_kernel<12><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
@@ -669,7 +854,7 @@ cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const
     }
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
-    A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L; A.galois = galois; A.Lk = lc.L; A.hyb = nullptr;
+    A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L; A.galois = galois; A.Lk = lc.L; A.hyb = nullptr; A.only = only;
 #define KS_DISPATCH(LOGN)                                                              \
     switch (mode) {                                                                    \
         case KS_MUL_RELIN: return launch_ks_t<LOGN, KS_MUL_RELIN>(lc, A, batch, st);   \

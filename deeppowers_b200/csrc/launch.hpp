@@ -37,8 +37,13 @@ struct LaunchCtx {
 
 int query_num_sms(int dev);
 cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inverse, cudaStream_t st);
+// only: optional [batch] filter (non-zero = process); key_ready: lc.ks_key_s already holds this key's Shoup companions
 cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch,
-                      u32 galois, cudaStream_t st);
+                      u32 galois, cudaStream_t st, const u32 *only = nullptr, bool key_ready = false);
+cudaError_t launch_hoist(LaunchCtx &lc, const u64 *ct, u64 *U, u32 *zero, size_t batch, cudaStream_t st);
+cudaError_t launch_rot_prepare(LaunchCtx &lc, const u64 *key, u32 galois, const u64 *delta, u64 *M, u64 *kprime, cudaStream_t st);
+cudaError_t launch_rot_apply(const LaunchCtx &lc, const u64 *ct, const u64 *U, const u64 *key, const u64 *kprime, u32 galois, u64 *out,
+                             size_t batch, cudaStream_t st);
 cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, u32 galois,
                              const MsConsts &K, cudaStream_t st);
 cudaError_t launch_pt_inner(const LaunchCtx &lc, const u64 *steps, u32 nb, const u64 *pts, u32 ng, u64 *out, size_t batch, cudaStream_t st,

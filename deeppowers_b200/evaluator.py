@@ -152,7 +152,8 @@ class Context:
 
         y = sum_g rot_{g*baby}( sum_b D[g*baby + b] o rot_b(x) ), D pre-rotated by -g*baby (caller encodes them so),
         diags: [n][L][N] plaintexts in evaluation form, n a multiple of `baby`; gk_baby / gk_giant: Galois keys of
-        rotations by 1 and by `baby`.  Uses (baby-1) + (n/baby-1) rotations instead of n-1.  fused=True computes all
+        rotations by 1 and by `baby` — or gk_baby = list of the baby-1 keys of the rotations by 1 .. baby-1, in which case
+        the baby steps are hoisted (one shared digit decomposition).  Uses (baby-1) + (n/baby-1) rotations instead of n-1.  fused=True computes all
         inner sums with one dpfhe_ct_mul_plain_inner call (scratch: baby + n/baby + 1 ciphertext batches); fused=False
         is the reference composition of ct_mul_plain / ct_mul_plain_acc (scratch: baby + 2).  Same bits either way.
         `out` must not alias `ct`."""
@@ -168,8 +169,14 @@ class Context:
         steps = scratch[:baby]
         g1, gb = self.galois_elt(1), self.galois_elt(baby)
         steps[0].copy_(ct.view(shape))
-        for b in range(1, baby):
-            self.rotate(steps[b - 1], g1, gk_baby, steps[b], batch, stream)
+        if isinstance(gk_baby, (list, tuple)):
+            # keys of the rotations by 1 .. baby-1: all baby steps are rotations of the same input and share its digit
+            # decomposition (dpfhe_rotate_hoisted)
+            assert len(gk_baby) == baby - 1, "need one Galois key per baby step"
+            self.rotate_hoisted(steps[0], [self.galois_elt(b) for b in range(1, baby)], list(gk_baby), steps[1:], batch, stream)
+        else:
+            for b in range(1, baby):
+                self.rotate(steps[b - 1], g1, gk_baby, steps[b], batch, stream)
         acc = out
         if fused:
             inner, tmp = scratch[baby:baby + giant], scratch[baby + giant]
@@ -193,6 +200,16 @@ class Context:
 
     def rotate(self, ct, galois_elt, gk, out, batch, stream=None):
         self._chk(self._l.dpfhe_rotate(self._h, _ptr(ct), int(galois_elt), _ptr(gk), _ptr(out), batch, _stream(stream)))
+
+    def rotate_hoisted(self, ct, galois_elts, gks, out, batch, stream=None):
+        """out[r] = rotate(ct, galois_elts[r], gks[r]) for all r, sharing the digit decomposition (bit-identical to rotate);
+        gks: list of device tensors, out: [n_rot][batch][2][L][N]"""
+        import ctypes as C
+        n = len(galois_elts)
+        assert len(gks) == n
+        ge = (C.c_uint64 * n)(*[int(g) for g in galois_elts])
+        kp = (C.c_void_p * n)(*[_ptr(k) for k in gks])
+        self._chk(self._l.dpfhe_rotate_hoisted(self._h, _ptr(ct), n, ge, kp, _ptr(out), batch, _stream(stream)))
 
     def mod_switch_down(self, polys, out, n_polys, t_plain=0, stream=None):
         """drop the last limb: [n_polys][L][N] -> [n_polys][L-1][N] (BGV correction when t_plain > 0)"""

@@ -110,6 +110,13 @@ int dpfhe_ct_mul_plain_acc(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t 
 int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk,
                  uint64_t *d_out, size_t batch, void *stream);
 
+/* ---- hoisted rotations: n_rot rotations of the SAME batch, out[r] = rotate(ct, galois_elts[r], gks[r]).
+ *      galois_elts and d_gks are HOST arrays of n_rot entries (d_gks[r] is a device pointer to a key [L][2][L][N]);
+ *      d_out is [n_rot][batch][2][L][N].  Bit-identical to n_rot dpfhe_rotate calls, but the digit decomposition and its
+ *      L(L-1) forward transforms are computed once per ciphertext.  The context keeps up to 4 GiB of scratch. ---- */
+int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, const uint64_t *galois_elts,
+                         const uint64_t *const *d_gks, uint64_t *d_out, size_t batch, void *stream);
+
 /* ---- plaintext inner products (the inner loop of a baby-step/giant-step matrix-vector product):
  *      out[g][k] = sum_{b < n_steps} steps[b][k] o pts[g][b]   for g < n_groups, k < batch
  *      steps [n_steps][batch][2][L][N] ciphertext batches, pts [n_groups][n_steps][L][N] plaintexts (evaluation form,

@@ -86,6 +86,16 @@ class Emu:
                                      out.reshape(-1), batch, int(galois), int(t_plain), G or 2 * self.L) == 0
         return out
 
+    def rotate_hoisted(self, ct, galois, keys, G=None):
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        batch = ct.size // (2 * self.L * self.N)
+        g = np.ascontiguousarray(galois, dtype=np.uint64)
+        out = np.zeros((len(g), batch, 2, self.L, self.N), dtype=np.uint64)
+        flagged = C.c_uint(0)
+        assert self._l.emu_rotate_hoisted(self._h, ct.reshape(-1), len(g), g, np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1),
+                                          out.reshape(-1), batch, G or 2 * self.L, C.byref(flagged)) == 0
+        return out, flagged.value
+
     def pt_inner(self, steps, pts, gmax=0):
         steps = np.ascontiguousarray(steps, dtype=np.uint64)
         pts = np.ascontiguousarray(pts, dtype=np.uint64)
@@ -127,6 +137,7 @@ def emu_lib():
     lib.emu_ntt.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int]
     lib.emu_ks.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint]
     lib.emu_ks_hybrid.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_uint]
+    lib.emu_rotate_hoisted.argtypes = [C.c_void_p, _u64p, C.c_size_t, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint, C.POINTER(C.c_uint)]
     lib.emu_pt_inner.argtypes = [C.c_void_p, _u64p, C.c_uint, _u64p, C.c_uint, _u64p, C.c_size_t, C.c_uint]
     lib.emu_mod_switch.argtypes = [C.c_void_p, _u64p, _u64p, C.c_size_t, C.c_uint64]
     for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2)):

@@ -82,7 +82,7 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
         key_s[k] = (uint64_t)((((unsigned __int128)key[k]) << 64) / e.lp[(k / N) % L].q);
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = key_s; A.out = out; A.scratch = scratch;
-    A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois;
+    A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois; A.Lk = L; A.hyb = nullptr; A.only = nullptr;
     HostCta cta{NT};
     const size_t n_work = batch * L;
     for (size_t r = 0; r * G < n_work; ++r) {
@@ -130,7 +130,7 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
     build_ms_consts(e.hp, t_plain, K);
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = key_s; A.out = out; A.scratch = scratch;
-    A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois; A.Lk = LK; A.hyb = hyb_all;
+    A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois; A.Lk = LK; A.hyb = hyb_all; A.only = nullptr;
     HostCta cta{NT};
     for (size_t r = 0; r * groups < batch; ++r) {
         const unsigned par = (unsigned)(r & 1);
@@ -164,6 +164,72 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
     free(scratch);
     free(hyb_all);
     free(key_s);
+}
+
+// hoisted rotations: the device bodies (hoist_phase1/2, rot_apply_row) in kernel order, the per-rotation constants
+// computed the way launch_rot_prepare does (negmask -> NTT -> kprime), flagged ciphertexts through the ordinary rotate
+template <int LOGN, int NT>
+void run_rotate_hoisted(Emu &e, const uint64_t *ct, size_t n_rot, const uint64_t *galois, const uint64_t *keys, uint64_t *out,
+                        size_t batch, unsigned G, unsigned *n_flagged) {
+    const size_t N = (size_t)1 << LOGN;
+    const unsigned L = e.hp.L;
+    const size_t P = (size_t)L * N, key_words = (size_t)2 * L * L * N;
+    G = (G / L) * L;
+    if (G == 0) G = L;
+    uint64_t *buf = aligned_new<uint64_t>(N);
+    uint64_t *scratch = aligned_new<uint64_t>((size_t)G * 2 * N);
+    uint64_t *U = aligned_new<uint64_t>(batch * L * L * N);
+    std::vector<uint32_t> zero(batch, 0);
+    HostCta cta{NT};
+    HoistArgs H;
+    H.ct = ct; H.U = U; H.scratch = scratch; H.zero = zero.data(); H.tw = e.tw; H.itw = e.itw; H.L = L;
+    if (L > 1) {
+        const size_t n_work = batch * L;
+        for (size_t r = 0; r * G < n_work; ++r) {
+            const unsigned par = (unsigned)(r & 1);
+            for (unsigned s = 0; s < G && r * G + s < n_work; ++s) {
+                const size_t w = r * G + s;
+                hoist_phase1<LOGN, NT>(cta, buf, H, e.lp[w % L], w / L, (uint32_t)(w % L), scratch + ((size_t)s * 2 + par) * N);
+            }
+            for (unsigned s = 0; s < G && r * G + s < n_work; ++s) {
+                const size_t w = r * G + s;
+                const uint32_t i = (uint32_t)(w % L);
+                for (uint32_t jj = 1; jj < L; ++jj) {
+                    const uint32_t j = (i + jj) % L;
+                    hoist_phase2<LOGN, NT>(cta, buf, H, e.lp[i], w / L, i, j, scratch + ((size_t)(s - i + j) * 2 + par) * N);
+                }
+            }
+        }
+    }
+    *n_flagged = 0;
+    for (size_t k = 0; k < batch; ++k) *n_flagged += zero[k] ? 1u : 0u;
+    uint64_t *key_s = aligned_new<uint64_t>(key_words), *M = aligned_new<uint64_t>(P), *kprime = aligned_new<uint64_t>(2 * P);
+    for (size_t r = 0; r < n_rot; ++r) {
+        const uint64_t *key = keys + r * key_words;
+        const uint32_t g = (uint32_t)galois[r];
+        for (size_t k = 0; k < key_words; ++k) key_s[k] = (uint64_t)((((unsigned __int128)key[k]) << 64) / e.lp[(k / N) % L].q);
+        for (uint32_t k = 0; k < N; ++k) {
+            const uint32_t ex = (k * g) & (uint32_t)(2 * N - 1);
+            for (unsigned l = 0; l < L; ++l) M[(size_t)l * N + (ex & (N - 1))] = ex >= N ? 1 : 0;
+        }
+        for (unsigned l = 0; l < L; ++l) ntt_fwd_body<LOGN, NT>(cta, buf, M + (size_t)l * N, e.tw + (size_t)l * N, e.lp[l]);
+        for (unsigned c = 0; c < 2; ++c)
+            for (unsigned i = 0; i < L; ++i)
+                for (size_t n = 0; n < N; ++n) {
+                    const uint64_t q = e.lp[i].q;
+                    uint64_t s = 0;
+                    for (unsigned j = 0; j < L; ++j)
+                        if (j != i) s = (s + host_mulmod(key[((size_t)j * 2 + c) * P + (size_t)i * N + n], e.lp[j].q % q, q)) % q;
+                    kprime[(size_t)c * P + (size_t)i * N + n] = host_mulmod(s, M[(size_t)i * N + n], q);
+                }
+        RotApplyArgs R;
+        R.ct = ct; R.U = U; R.key = key; R.key_s = key_s; R.kprime = kprime; R.out = out + r * batch * 2 * P; R.L = L; R.galois = g;
+        for (size_t k = 0; k < batch; ++k)
+            for (unsigned i = 0; i < L; ++i) rot_apply_row<LOGN, NT>(cta, R, e.lp[i], k, i);
+        for (size_t k = 0; k < batch; ++k)   // flagged ciphertexts: ordinary rotate, as the device does with its filter
+            if (zero[k]) run_ks<LOGN, NT, KS_ROTATE>(e, ct + k * 2 * P, ct + k * 2 * P, key, out + (r * batch + k) * 2 * P, 1, g, L);
+    }
+    free(buf); free(scratch); free(U); free(key_s); free(M); free(kprime);
 }
 }  // namespace
 
@@ -235,6 +301,17 @@ int emu_ks_hybrid(void *h, int mode, const uint64_t *a, const uint64_t *b, const
         case 12: DISPATCH_H(12, 256)
         case 13: DISPATCH_H(13, 256)
         case 14: DISPATCH_H(14, 256)
+    }
+    return -1;
+}
+
+int emu_rotate_hoisted(void *h, const uint64_t *ct, size_t n_rot, const uint64_t *galois, const uint64_t *keys, uint64_t *out, size_t batch,
+                       unsigned G, unsigned *n_flagged) {
+    Emu *e = (Emu *)h;
+    switch (e->hp.log_n) {
+        case 12: run_rotate_hoisted<12, 256>(*e, ct, n_rot, galois, keys, out, batch, G, n_flagged); return 0;
+        case 13: run_rotate_hoisted<13, 256>(*e, ct, n_rot, galois, keys, out, batch, G, n_flagged); return 0;
+        case 14: run_rotate_hoisted<14, 256>(*e, ct, n_rot, galois, keys, out, batch, G, n_flagged); return 0;
     }
     return -1;
 }

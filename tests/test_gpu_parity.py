@@ -153,6 +153,29 @@ def test_keyswitch_and_rotate(ctxs, log_n, L, batch):
         assert np.array_equal(host(out).reshape(ct.shape), o.rotate(ct, g, gk))
 
 
+@pytest.mark.parametrize("log_n,L,batch", [(12, 1, 2), (12, 3, 5), (13, 4, 37), (14, 8, 2), (12, 16, 2)])
+def test_rotate_hoisted(ctxs, log_n, L, batch):
+    """n rotations of the same batch sharing the digit transforms == n independent rotations, bit for bit"""
+    c, o = ctxs(log_n, L)
+    ct = edge_polys(o, 2 * batch, 91).reshape(batch, 2, L, o.N)      # includes an all-zero c0 and extreme rows
+    ct[batch - 1, 1] = 0                                              # c1 = 0: zero digits, the fallback path
+    if batch > 2:
+        ct[2, 1, L - 1] = 0
+    galois = [o.galois_elt(k) for k in (1, -1, 7)] + [2 * o.N - 1]
+    keys = [o.fill_uniform(100 + r, 2 * L).reshape(L, 2, L, o.N) for r in range(len(galois))]
+    d_keys = [dev(k) for k in keys]
+    out = torch.full((len(galois), batch, 2, L, o.N), -1, dtype=torch.int64, device="cuda")
+    d_ct = dev(ct)
+    c.rotate_hoisted(d_ct, galois, d_keys, out, batch)
+    single = torch.empty((batch, 2, L, o.N), dtype=torch.int64, device="cuda")
+    for r, g in enumerate(galois):
+        assert np.array_equal(host(out[r]).reshape(ct.shape), o.rotate(ct, g, keys[r])), "rotation %d vs oracle" % r
+        c.rotate(d_ct, g, d_keys[r], single, batch)
+        assert torch.equal(out[r], single), "rotation %d vs dpfhe_rotate" % r
+    with pytest.raises(RuntimeError, match="galois"):
+        c.rotate_hoisted(d_ct, [2], d_keys[:1], out, batch)
+
+
 def test_semantics_decrypt_of_product(ctxs):
     """Dec(GPU ct x ct) == a*b mod (X^N+1, t): checks the scheme meaning, not just oracle agreement."""
     c, o = ctxs(12, 3)

@@ -101,6 +101,23 @@ def test_emulated_plain_inner_products(make_emu, oracle_mod, log_n, L, nb, ng, b
     assert np.array_equal(e.pt_inner(steps, pts, gmax), o.ct_mul_plain_inner(steps, pts))
 
 
+@pytest.mark.parametrize("log_n,L,batch,G", [(12, 1, 2, None), (12, 3, 4, 6), (13, 4, 3, None), (14, 2, 2, None), (12, 5, 3, None)])
+def test_emulated_hoisted_rotations(make_emu, oracle_mod, log_n, L, batch, G):
+    """rotations that share the digit transforms == independent rotations, bit for bit; zero digits take the fallback"""
+    e, o = make_emu(log_n, L), oracle_mod.Oracle(log_n, L)
+    ct = o.fill_uniform(61, 2 * batch).reshape(batch, 2, L, o.N)
+    ct[1, 1] = 0                      # c1 = 0: every coefficient of every digit is zero
+    if batch > 2:
+        ct[2, 1, L - 1] = 0           # one zero digit
+    ks = [1, -1, 5]
+    galois = [o.galois_elt(k) for k in ks] + [2 * o.N - 1]    # plus the conjugation element
+    keys = np.stack([o.fill_uniform(70 + r, 2 * L).reshape(L, 2, L, o.N) for r in range(len(galois))])
+    got, flagged = e.rotate_hoisted(ct, galois, keys, G)
+    assert flagged == (0 if L == 1 else (1 if batch <= 2 else 2))
+    for r, g in enumerate(galois):
+        assert np.array_equal(got[r], o.rotate(ct, g, keys[r])), "rotation %d" % r
+
+
 def _hybrid_inputs(o, batch, seed):
     """[batch][2][L-1][N] uniform residues (with edge rows) under the first L-1 moduli, and a uniform hybrid key"""
     Lq = o.L - 1
