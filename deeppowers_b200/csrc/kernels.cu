@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
     const LimbParams &p = lt.lp[i];
     u32 executed = 0;
     for (u32 round = 0;; ++round) {
-        if (threadIdx.x == 0) {
+        if (!FILTER && threadIdx.x == 0) {
             const u32 tag = epoch + round + 1;
             if (i == 0) {
                 const u32 t = atomicAdd(ticket, 1u);
@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
             }
         }
         __syncthreads();
-        const size_t ct = s_ct;
+        // FILTER: static assignment computed by every thread.  Skipped rounds involve no exchange between the members of
+        // a group, so a leader handing out tickets could run ahead and overwrite a mailbox tag (or s_ct) before it was read.
+        const size_t ct = FILTER ? (size_t)round * (gridDim.x / L) + group : (size_t)s_ct;
         if (ct >= batch) break;   // every member of the group reads the same ticket, so they leave together
         if (FILTER && A.only[ct] == 0u) continue;
         // Tickets are drawn in order, so ciphertext ct + pf_dist will be started by some group a few microseconds
