@@ -56,7 +56,7 @@ def cfg3():
             c.rotate_hoisted(ct[first:first + SUB], galois, klist, outs, SUB)
 
     ms_h = timed(sweep_hoisted, 2)
-    c.rotate(ct[:SUB], galois[3], keys[3], out[:SUB], SUB)
+    c.rotate(ct[B - SUB:], galois[3], keys[3], out[:SUB], SUB)      # `outs` holds the last sub-batch of the sweep
     same = bool(torch.equal(outs[3], out[:SUB]))
     c.close()
     # per rotation: read the ciphertext and L(L-1) shared transforms, write the ciphertext
