@@ -124,6 +124,15 @@ public:
                        void *stream = nullptr) {
         check(dpfhe_rotate(ctx_, ct, galois_element(steps), galois_key, out, count, stream));
     }
+    // several rotations of the same batch, sharing the digit decomposition; out is [steps.size()][count] ciphertexts and
+    // galois_keys[r] the device pointer of the key for steps[r].  Same bits as rotate_device called steps.size() times.
+    void rotate_many_device(const std::uint64_t *ct, const std::vector<long> &steps, const std::vector<const std::uint64_t *> &galois_keys,
+                            std::uint64_t *out, std::size_t count, void *stream = nullptr) {
+        if (steps.size() != galois_keys.size()) throw std::runtime_error("one Galois key per rotation step");
+        std::vector<std::uint64_t> elts;
+        for (long k : steps) elts.push_back(galois_element(k));
+        check(dpfhe_rotate_hoisted(ctx_, ct, steps.size(), elts.data(), galois_keys.data(), out, count, stream));
+    }
     void add_device(const std::uint64_t *a, const std::uint64_t *b, std::uint64_t *out, std::size_t count, void *stream = nullptr) {
         check(dpfhe_poly_add(ctx_, a, b, out, 2 * count, stream));   // a ciphertext is two polynomials
     }

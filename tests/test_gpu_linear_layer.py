@@ -130,6 +130,14 @@ def test_encrypted_linear_layer_bsgs(oracle_mod):
     torch.cuda.synchronize()
     assert ctx.launch_count() - n0 == 2 * n_rot + DIM + (DIM // BABY - 1)
     assert torch.equal(out, ref)                                                     # same bits either way
+    # baby steps as hoisted rotations of the input (one key per step): different keys, same plaintext result
+    baby_keys = [dev(o.keygen_galois(100 + b, T_PLAIN, s, o.galois_elt(b))) for b in range(1, BABY)]
+    hoisted = torch.empty_like(out)
+    ctx.linear_bsgs(dev(ct), diag, baby_keys, dev(gkb), BABY, hoisted, B)
+    res_h = host(hoisted).reshape(B, 2, L, N)
+    for b in range(B):
+        y = enc.decode(o.decrypt(s, res_h[b], T_PLAIN))[0, :DIM].astype(np.int64)
+        assert np.array_equal(np.where(y > T_PLAIN // 2, y - T_PLAIN, y), W @ X[b])
     res = host(out).reshape(B, 2, L, N)
     for b in range(B):
         y = enc.decode(o.decrypt(s, res[b], T_PLAIN))[0, :DIM].astype(np.int64)
