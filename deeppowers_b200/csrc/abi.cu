@@ -445,7 +445,12 @@ int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, con
     cudaStream_t st = pick(ctx, stream);
     // scratch: at most ~4 GiB of shared transforms at a time (the batch is processed in chunks of that many ciphertexts)
     const size_t per_ct = L * L * N * sizeof(u64);
-    size_t chunk = ((size_t)4 << 30) / per_ct;
+    size_t cap = (size_t)4 << 30;
+    if (const char *e = getenv("DPFHE_HOIST_CAP_MB")) {   // diagnostics / tests: smaller scratch, more chunks
+        const long mb = atol(e);
+        if (mb > 0) cap = (size_t)mb << 20;
+    }
+    size_t chunk = cap / per_ct;
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
     if (chunk > ctx->hoist_chunk) {

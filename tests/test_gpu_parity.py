@@ -176,6 +176,23 @@ def test_rotate_hoisted(ctxs, log_n, L, batch):
         c.rotate_hoisted(d_ct, [2], d_keys[:1], out, batch)
 
 
+def test_rotate_hoisted_in_chunks(dp, oracle_mod, monkeypatch):
+    """a scratch cap smaller than the batch: the shared transforms are produced and consumed chunk by chunk"""
+    monkeypatch.setenv("DPFHE_HOIST_CAP_MB", "1")          # 288 KiB of shared transforms per ciphertext at (12, 3): 3 per chunk
+    o = oracle_mod.Oracle(12, 3)
+    c = dp.Context(12, 3)
+    batch = 8
+    ct = o.fill_uniform(93, 2 * batch).reshape(batch, 2, 3, o.N)
+    ct[4, 1] = 0
+    galois = [o.galois_elt(k) for k in (2, -3)]
+    keys = [o.fill_uniform(110 + r, 6).reshape(3, 2, 3, o.N) for r in range(2)]
+    out = torch.zeros((2, batch, 2, 3, o.N), dtype=torch.int64, device="cuda")
+    c.rotate_hoisted(dev(ct), galois, [dev(k) for k in keys], out, batch)
+    for r in range(2):
+        assert np.array_equal(host(out[r]).reshape(ct.shape), o.rotate(ct, galois[r], keys[r]))
+    c.close()
+
+
 def test_semantics_decrypt_of_product(ctxs):
     """Dec(GPU ct x ct) == a*b mod (X^N+1, t): checks the scheme meaning, not just oracle agreement."""
     c, o = ctxs(12, 3)
