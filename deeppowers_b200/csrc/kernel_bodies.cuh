@@ -612,50 +612,69 @@ struct RotApplyArgs {
     u32 L, galois;
 };
 
-template <int LOGN, int NT, class CTA>
-DPFHE_HD void rot_apply_row(CTA &cta, const RotApplyArgs &A, const LimbParams &p, size_t ct, u32 i) {
-    constexpr int N = 1 << LOGN, NC = N / 2;
+// CB ciphertexts ct0 .. ct0+n_ct-1 (n_ct <= CB) share every key chunk they multiply with: the key columns are the
+// dominant L2 traffic of this step (1 MiB per (ciphertext, limb) row at N = 8192, L = 4).
+template <int LOGN, int NT, int CB, class CTA>
+DPFHE_HD void rot_apply_rows(CTA &cta, const RotApplyArgs &A, const LimbParams &p, size_t ct0, u32 n_ct, u32 i, int c_lo = 0,
+                             int c_hi = 1 << (LOGN - 1)) {
+    constexpr int N = 1 << LOGN;
     const u32 L = A.L, g = A.galois;
     const size_t P = (size_t)L * N;
-    const U64x2 *c0 = reinterpret_cast<const U64x2 *>(A.ct + ct * 2 * P + (size_t)i * N);
-    const U64x2 *c1 = reinterpret_cast<const U64x2 *>(A.ct + ct * 2 * P + P + (size_t)i * N);
     const U64x2 *kp0 = reinterpret_cast<const U64x2 *>(A.kprime + (size_t)i * N), *kp1 = reinterpret_cast<const U64x2 *>(A.kprime + P + (size_t)i * N);
-    U64x2 *o0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N), *o1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
     cta.par([&](int tid) {
 #pragma unroll 1
-        for (int c = tid; c < NC; c += NT) {
+        for (int c = c_lo + tid; c < c_hi; c += NT) {   // chunk range [c_lo, c_hi) of the row
             const int pi0 = galois_index<LOGN>(2 * c, g);
             const int pc = pi0 >> 1;
             const bool swap = (pi0 & 1) != 0;
-            auto gather = [&](const U64x2 *row) {
-                const U64x2 v = ld_stream(row + pc);
+            auto gather = [&](const u64 *row) {
+                const U64x2 v = ld_stream(reinterpret_cast<const U64x2 *>(row) + pc);
                 U64x2 r;
                 r.x = swap ? v.y : v.x;
                 r.y = swap ? v.x : v.y;
                 return r;
             };
-            U64x2 r0 = ld_keep(kp0 + c), r1 = ld_keep(kp1 + c);
-            const U64x2 s0 = gather(c0);
-            r0.x += s0.x;   // < 2q
-            r0.y += s0.y;
+            U64x2 r0[CB], r1[CB];
+            {
+                const U64x2 k0 = ld_keep(kp0 + c), k1 = ld_keep(kp1 + c);
+#pragma unroll
+                for (int b = 0; b < CB; ++b) {
+                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);   // rows past the end repeat the last one, not stored
+                    const U64x2 s0 = gather(A.ct + ct * 2 * P + (size_t)i * N);
+                    r0[b].x = k0.x + s0.x;   // < 2q
+                    r0[b].y = k0.y + s0.y;
+                    r1[b] = k1;
+                }
+            }
             for (u32 j = 0; j < L; ++j) {
-                const U64x2 u = j == i ? gather(c1) : gather(reinterpret_cast<const U64x2 *>(A.U + ((ct * L + j) * L + i) * N));
                 const size_t kb = ((size_t)j * 2 + 0) * P + (size_t)i * N, ka = ((size_t)j * 2 + 1) * P + (size_t)i * N;
                 const U64x2 vb = ld_keep(reinterpret_cast<const U64x2 *>(A.key + kb) + c), vbs = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + kb) + c);
                 const U64x2 va = ld_keep(reinterpret_cast<const U64x2 *>(A.key + ka) + c), vas = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + ka) + c);
-                r0.x += shoup_lazy(u.x, vb.x, vbs.x, p);
-                r0.y += shoup_lazy(u.y, vb.y, vbs.y, p);
-                r1.x += shoup_lazy(u.x, va.x, vas.x, p);
-                r1.y += shoup_lazy(u.y, va.y, vas.y, p);
-                if ((j & 3u) == 3u) {   // + 2q per digit from below 2q: one csub(8q) every fourth digit keeps the sums below 16q
-                    r0.x = csub(r0.x, p.q8); r0.y = csub(r0.y, p.q8);
-                    r1.x = csub(r1.x, p.q8); r1.y = csub(r1.y, p.q8);
+                const bool trim = (j & 3u) == 3u;   // + 2q per digit from below 2q: one csub(8q) every fourth digit keeps the sums below 16q
+#pragma unroll
+                for (int b = 0; b < CB; ++b) {
+                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);
+                    const U64x2 u = gather(j == i ? A.ct + ct * 2 * P + P + (size_t)i * N : A.U + ((ct * L + j) * L + i) * N);
+                    r0[b].x += shoup_lazy(u.x, vb.x, vbs.x, p);
+                    r0[b].y += shoup_lazy(u.y, vb.y, vbs.y, p);
+                    r1[b].x += shoup_lazy(u.x, va.x, vas.x, p);
+                    r1[b].y += shoup_lazy(u.y, va.y, vas.y, p);
+                    if (trim) {
+                        r0[b].x = csub(r0[b].x, p.q8); r0[b].y = csub(r0[b].y, p.q8);
+                        r1[b].x = csub(r1[b].x, p.q8); r1[b].y = csub(r1[b].y, p.q8);
+                    }
                 }
             }
-            r0.x = canon(r0.x, p); r0.y = canon(r0.y, p);
-            r1.x = canon(r1.x, p); r1.y = canon(r1.y, p);
-            st_stream(o0 + c, r0);
-            st_stream(o1 + c, r1);
+#pragma unroll
+            for (int b = 0; b < CB; ++b) {
+                if ((u32)b < n_ct) {
+                    U64x2 o0, o1;
+                    o0.x = canon(r0[b].x, p); o0.y = canon(r0[b].y, p);
+                    o1.x = canon(r1[b].x, p); o1.y = canon(r1[b].y, p);
+                    st_stream(reinterpret_cast<U64x2 *>(A.out + (ct0 + b) * 2 * P + (size_t)i * N) + c, o0);
+                    st_stream(reinterpret_cast<U64x2 *>(A.out + (ct0 + b) * 2 * P + P + (size_t)i * N) + c, o1);
+                }
+            }
         }
     });
 }

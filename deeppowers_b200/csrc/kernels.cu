@@ -250,13 +250,19 @@ __global__ void __launch_bounds__(NT, MINB) ks_hoist_kernel(HoistArgs A, const _
     }
 }
 
-// step 2: one rotation applied to every (ciphertext, limb) row pair; no transforms, only gathers and multiply-accumulates
+// step 2: one rotation applied to blocks of ROT_CB ciphertexts x one limb; no transforms, only gathers and multiply-accumulates
+constexpr int ROT_CB = 4;
 template <int LOGN, int NT>
-__global__ void __launch_bounds__(NT) rot_apply_kernel(RotApplyArgs A, const __grid_constant__ LimbTable lt, size_t n_rows) {
+__global__ void __launch_bounds__(NT) rot_apply_kernel(RotApplyArgs A, const __grid_constant__ LimbTable lt, size_t batch, u32 nseg) {
     DevCta<NT> cta;
-    for (size_t w = blockIdx.x; w < n_rows; w += gridDim.x) {
-        const u32 i = (u32)(w % A.L);
-        rot_apply_row<LOGN, NT>(cta, A, lt.lp[i], w / A.L, i);
+    constexpr int NC = 1 << (LOGN - 1);
+    const size_t n_blocks = (batch + ROT_CB - 1) / ROT_CB, n_items = n_blocks * A.L * nseg;
+    const int seg_chunks = NC / (int)nseg;   // nseg is a power of two <= NC / NT
+    for (size_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const u32 seg = (u32)(w % nseg), i = (u32)((w / nseg) % A.L);
+        const size_t ct0 = (w / nseg / A.L) * ROT_CB;
+        const u32 n_ct = (u32)(batch - ct0 < (size_t)ROT_CB ? batch - ct0 : (size_t)ROT_CB);
+        rot_apply_rows<LOGN, NT, ROT_CB>(cta, A, lt.lp[i], ct0, n_ct, i, (int)seg * seg_chunks, ((int)seg + 1) * seg_chunks);
     }
 }
 
@@ -829,13 +835,17 @@ cudaError_t launch_rot_apply(const LaunchCtx &lc, const u64 *ct, const u64 *U, c
     if (batch == 0) return cudaSuccess;
     RotApplyArgs A;
     A.ct = ct; A.U = U; A.key = key; A.key_s = lc.ks_key_s; A.kprime = kprime; A.out = out; A.L = lc.L; A.galois = galois;
-    const size_t n_rows = batch * lc.L;
-    const size_t cap = (size_t)lc.num_sms * 8;
-    const unsigned grid = (unsigned)(n_rows < cap ? n_rows : cap);
+    // rows are cut into up to NC / 256 segments so that small batches still fill the machine several times over
+    const size_t rows = ((batch + ROT_CB - 1) / ROT_CB) * lc.L, want = (size_t)lc.num_sms * 12;
+    u32 nseg = 1;
+    const u32 max_seg = (1u << (lc.log_n - 1)) / 256;
+    while (nseg < max_seg && rows * nseg < want) nseg *= 2;
+    const size_t n_items = rows * nseg, cap = (size_t)lc.num_sms * 8;
+    const unsigned grid = (unsigned)(n_items < cap ? n_items : cap);
     switch (lc.log_n) {
-        case 12: rot_apply_kernel<12, 256><<<grid, 256, 0, st>>>(A, lc.lt, n_rows); break;
-        case 13: rot_apply_kernel<13, 256><<<grid, 256, 0, st>>>(A, lc.lt, n_rows); break;
-        case 14: rot_apply_kernel<14, 256><<<grid, 256, 0, st>>>(A, lc.lt, n_rows); break;
+        case 12: rot_apply_kernel<12, 256><<<grid, 256, 0, st>>>(A, lc.lt, batch, nseg); break;
+        case 13: rot_apply_kernel<13, 256><<<grid, 256, 0, st>>>(A, lc.lt, batch, nseg); break;
+        case 14: rot_apply_kernel<14, 256><<<grid, 256, 0, st>>>(A, lc.lt, batch, nseg); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -224,8 +224,8 @@ void run_rotate_hoisted(Emu &e, const uint64_t *ct, size_t n_rot, const uint64_t
                 }
         RotApplyArgs R;
         R.ct = ct; R.U = U; R.key = key; R.key_s = key_s; R.kprime = kprime; R.out = out + r * batch * 2 * P; R.L = L; R.galois = g;
-        for (size_t k = 0; k < batch; ++k)
-            for (unsigned i = 0; i < L; ++i) rot_apply_row<LOGN, NT>(cta, R, e.lp[i], k, i);
+        for (size_t k = 0; k < batch; k += 4)   // blocks of four ciphertexts, the last one ragged (as rot_apply_kernel)
+            for (unsigned i = 0; i < L; ++i) rot_apply_rows<LOGN, NT, 4>(cta, R, e.lp[i], k, (unsigned)(batch - k < 4 ? batch - k : 4), i);
         for (size_t k = 0; k < batch; ++k)   // flagged ciphertexts: ordinary rotate, as the device does with its filter
             if (zero[k]) run_ks<LOGN, NT, KS_ROTATE>(e, ct + k * 2 * P, ct + k * 2 * P, key, out + (r * batch + k) * 2 * P, 1, g, L);
     }
