@@ -612,9 +612,15 @@ struct RotApplyArgs {
     u32 L, galois;
 };
 
-// CB ciphertexts ct0 .. ct0+n_ct-1 (n_ct <= CB) share every key chunk they multiply with: the key columns are the
-// dominant L2 traffic of this step (1 MiB per (ciphertext, limb) row at N = 8192, L = 4).
-template <int LOGN, int NT, int CB, class CTA>
+// CB ciphertexts ct0 .. ct0+n_ct-1 (n_ct <= CB) share every key chunk they multiply with.  PF: the operands of digit
+// j + 1 (gathered transforms and key chunks) are requested before the arithmetic of digit j, which is what this
+// latency-bound loop needs (measured: sharing key chunks between ciphertexts does not help, more loads in flight do).
+template <int CB>
+struct RotOperands {
+    U64x2 vb, vbs, va, vas, u[CB];
+};
+
+template <int LOGN, int NT, int CB, bool PF, class CTA>
 DPFHE_HD void rot_apply_rows(CTA &cta, const RotApplyArgs &A, const LimbParams &p, size_t ct0, u32 n_ct, u32 i, int c_lo = 0,
                              int c_hi = 1 << (LOGN - 1)) {
     constexpr int N = 1 << LOGN;
@@ -634,12 +640,26 @@ DPFHE_HD void rot_apply_rows(CTA &cta, const RotApplyArgs &A, const LimbParams &
                 r.y = swap ? v.x : v.y;
                 return r;
             };
+            auto fetch = [&](u32 j, RotOperands<CB> &o) {
+                const size_t kb = ((size_t)j * 2 + 0) * P + (size_t)i * N, ka = ((size_t)j * 2 + 1) * P + (size_t)i * N;
+                o.vb = ld_keep(reinterpret_cast<const U64x2 *>(A.key + kb) + c);
+                o.vbs = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + kb) + c);
+                o.va = ld_keep(reinterpret_cast<const U64x2 *>(A.key + ka) + c);
+                o.vas = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + ka) + c);
+#pragma unroll
+                for (int b = 0; b < CB; ++b) {
+                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);   // rows past the end repeat the last one, not stored
+                    o.u[b] = gather(j == i ? A.ct + ct * 2 * P + P + (size_t)i * N : A.U + ((ct * L + j) * L + i) * N);
+                }
+            };
+            RotOperands<CB> nxt;
+            fetch(0, nxt);
             U64x2 r0[CB], r1[CB];
             {
                 const U64x2 k0 = ld_keep(kp0 + c), k1 = ld_keep(kp1 + c);
 #pragma unroll
                 for (int b = 0; b < CB; ++b) {
-                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);   // rows past the end repeat the last one, not stored
+                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);
                     const U64x2 s0 = gather(A.ct + ct * 2 * P + (size_t)i * N);
                     r0[b].x = k0.x + s0.x;   // < 2q
                     r0[b].y = k0.y + s0.y;
@@ -647,22 +667,24 @@ DPFHE_HD void rot_apply_rows(CTA &cta, const RotApplyArgs &A, const LimbParams &
                 }
             }
             for (u32 j = 0; j < L; ++j) {
-                const size_t kb = ((size_t)j * 2 + 0) * P + (size_t)i * N, ka = ((size_t)j * 2 + 1) * P + (size_t)i * N;
-                const U64x2 vb = ld_keep(reinterpret_cast<const U64x2 *>(A.key + kb) + c), vbs = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + kb) + c);
-                const U64x2 va = ld_keep(reinterpret_cast<const U64x2 *>(A.key + ka) + c), vas = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + ka) + c);
+                RotOperands<CB> o = nxt;
+                if (PF) {
+                    if (j + 1 < L) fetch(j + 1, nxt);
+                }
                 const bool trim = (j & 3u) == 3u;   // + 2q per digit from below 2q: one csub(8q) every fourth digit keeps the sums below 16q
 #pragma unroll
                 for (int b = 0; b < CB; ++b) {
-                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);
-                    const U64x2 u = gather(j == i ? A.ct + ct * 2 * P + P + (size_t)i * N : A.U + ((ct * L + j) * L + i) * N);
-                    r0[b].x += shoup_lazy(u.x, vb.x, vbs.x, p);
-                    r0[b].y += shoup_lazy(u.y, vb.y, vbs.y, p);
-                    r1[b].x += shoup_lazy(u.x, va.x, vas.x, p);
-                    r1[b].y += shoup_lazy(u.y, va.y, vas.y, p);
+                    r0[b].x += shoup_lazy(o.u[b].x, o.vb.x, o.vbs.x, p);
+                    r0[b].y += shoup_lazy(o.u[b].y, o.vb.y, o.vbs.y, p);
+                    r1[b].x += shoup_lazy(o.u[b].x, o.va.x, o.vas.x, p);
+                    r1[b].y += shoup_lazy(o.u[b].y, o.va.y, o.vas.y, p);
                     if (trim) {
                         r0[b].x = csub(r0[b].x, p.q8); r0[b].y = csub(r0[b].y, p.q8);
                         r1[b].x = csub(r1[b].x, p.q8); r1[b].y = csub(r1[b].y, p.q8);
                     }
+                }
+                if (!PF) {
+                    if (j + 1 < L) fetch(j + 1, nxt);
                 }
             }
 #pragma unroll

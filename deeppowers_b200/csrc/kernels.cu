@@ -251,9 +251,8 @@ __global__ void __launch_bounds__(NT, MINB) ks_hoist_kernel(HoistArgs A, const _
 }
 
 // step 2: one rotation applied to blocks of ROT_CB ciphertexts x one limb; no transforms, only gathers and multiply-accumulates
-constexpr int ROT_CB = 4;
-template <int LOGN, int NT>
-__global__ void __launch_bounds__(NT) rot_apply_kernel(RotApplyArgs A, const __grid_constant__ LimbTable lt, size_t batch, u32 nseg) {
+template <int LOGN, int NT, int MINB, int ROT_CB, bool PF>
+__global__ void __launch_bounds__(NT, MINB) rot_apply_kernel(RotApplyArgs A, const __grid_constant__ LimbTable lt, size_t batch, u32 nseg) {
     DevCta<NT> cta;
     constexpr int NC = 1 << (LOGN - 1);
     const size_t n_blocks = (batch + ROT_CB - 1) / ROT_CB, n_items = n_blocks * A.L * nseg;
@@ -262,7 +261,7 @@ __global__ void __launch_bounds__(NT) rot_apply_kernel(RotApplyArgs A, const __g
         const u32 seg = (u32)(w % nseg), i = (u32)((w / nseg) % A.L);
         const size_t ct0 = (w / nseg / A.L) * ROT_CB;
         const u32 n_ct = (u32)(batch - ct0 < (size_t)ROT_CB ? batch - ct0 : (size_t)ROT_CB);
-        rot_apply_rows<LOGN, NT, ROT_CB>(cta, A, lt.lp[i], ct0, n_ct, i, (int)seg * seg_chunks, ((int)seg + 1) * seg_chunks);
+        rot_apply_rows<LOGN, NT, ROT_CB, PF>(cta, A, lt.lp[i], ct0, n_ct, i, (int)seg * seg_chunks, ((int)seg + 1) * seg_chunks);
     }
 }
 
@@ -836,16 +835,25 @@ cudaError_t launch_rot_apply(const LaunchCtx &lc, const u64 *ct, const u64 *U, c
     RotApplyArgs A;
     A.ct = ct; A.U = U; A.key = key; A.key_s = lc.ks_key_s; A.kprime = kprime; A.out = out; A.L = lc.L; A.galois = galois;
     // rows are cut into up to NC / 256 segments so that small batches still fill the machine several times over
-    const size_t rows = ((batch + ROT_CB - 1) / ROT_CB) * lc.L, want = (size_t)lc.num_sms * 12;
+    // tuning variant (DPFHE_ROT_CFG): 0 (default) = two ciphertexts share each key chunk, next digit prefetched;
+    // 1 = one ciphertext per item, prefetched; 2 = one ciphertext, no prefetch.  Measured 11.1 / 12.1 / 11.9 ms for 31
+    // rotations of 512 ciphertexts at N = 8192, L = 4 and 31.9 / 36.5 / 34.8 ms for 26 x 256 at N = 16384, L = 8.
+    const int cfg = lc.rot_cfg;
+    const size_t cb = cfg == 0 ? 2 : 1;
+    const size_t rows = ((batch + cb - 1) / cb) * lc.L, want = (size_t)lc.num_sms * 12;
     u32 nseg = 1;
     const u32 max_seg = (1u << (lc.log_n - 1)) / 256;
     while (nseg < max_seg && rows * nseg < want) nseg *= 2;
     const size_t n_items = rows * nseg, cap = (size_t)lc.num_sms * 8;
     const unsigned grid = (unsigned)(n_items < cap ? n_items : cap);
+#define ROT_APPLY(LOGN)                                                                                          \
+    if (cfg == 1) rot_apply_kernel<LOGN, 256, 3, 1, true><<<grid, 256, 0, st>>>(A, lc.lt, batch, nseg);           \
+    else if (cfg == 2) rot_apply_kernel<LOGN, 256, 3, 1, false><<<grid, 256, 0, st>>>(A, lc.lt, batch, nseg);     \
+    else rot_apply_kernel<LOGN, 256, 3, 2, true><<<grid, 256, 0, st>>>(A, lc.lt, batch, nseg);
     switch (lc.log_n) {
-        case 12: rot_apply_kernel<12, 256><<<grid, 256, 0, st>>>(A, lc.lt, batch, nseg); break;
-        case 13: rot_apply_kernel<13, 256><<<grid, 256, 0, st>>>(A, lc.lt, batch, nseg); break;
-        case 14: rot_apply_kernel<14, 256><<<grid, 256, 0, st>>>(A, lc.lt, batch, nseg); break;
+        case 12: ROT_APPLY(12) break;
+        case 13: ROT_APPLY(13) break;
+        case 14: ROT_APPLY(14) break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -18,6 +18,7 @@ struct LaunchCtx {
     u32 log_n = 0, L = 0;
     const LimbParams *lp = nullptr;   // [L] device copy (element-wise kernels)
     LimbTable lt;                     // host copy, passed by value to the transform kernels
+    int rot_cfg = 0;                  // tuning variant of rot_apply_kernel (DPFHE_ROT_CFG)
     int ntt_cfg = 0;                  // tuning variant of the N=8192 transform kernel (DPFHE_NTT_CFG)
     const Twiddle *tw = nullptr;      // [L][N] forward twiddles, device layout (ntt_core.cuh:tw_pos)
     const Twiddle *itw = nullptr;     // [L][N] inverse twiddles

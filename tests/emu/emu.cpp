@@ -224,8 +224,13 @@ void run_rotate_hoisted(Emu &e, const uint64_t *ct, size_t n_rot, const uint64_t
                 }
         RotApplyArgs R;
         R.ct = ct; R.U = U; R.key = key; R.key_s = key_s; R.kprime = kprime; R.out = out + r * batch * 2 * P; R.L = L; R.galois = g;
-        for (size_t k = 0; k < batch; k += 4)   // blocks of four ciphertexts, the last one ragged (as rot_apply_kernel)
-            for (unsigned i = 0; i < L; ++i) rot_apply_rows<LOGN, NT, 4>(cta, R, e.lp[i], k, (unsigned)(batch - k < 4 ? batch - k : 4), i);
+        for (size_t k = 0; k < batch; k += 2)   // blocks of two ciphertexts, the last one ragged; odd rotations use the prefetching form
+            for (unsigned i = 0; i < L; ++i) {
+                const unsigned n_ct = (unsigned)(batch - k < 2 ? batch - k : 2);
+                if (r & 1) rot_apply_rows<LOGN, NT, 2, true>(cta, R, e.lp[i], k, n_ct, i);
+                else rot_apply_rows<LOGN, NT, 2, false>(cta, R, e.lp[i], k, n_ct, i, 0, 1 << (LOGN - 2)),
+                     rot_apply_rows<LOGN, NT, 2, false>(cta, R, e.lp[i], k, n_ct, i, 1 << (LOGN - 2), 1 << (LOGN - 1));
+            }
         for (size_t k = 0; k < batch; ++k)   // flagged ciphertexts: ordinary rotate, as the device does with its filter
             if (zero[k]) run_ks<LOGN, NT, KS_ROTATE>(e, ct + k * 2 * P, ct + k * 2 * P, key, out + (r * batch + k) * 2 * P, 1, g, L);
     }
