@@ -322,6 +322,37 @@ def test_semantics_hybrid_product_and_noise(ctxs, oracle_mod):
     assert noise_bits(hyb) + 30 < noise_bits(bv)
 
 
+def test_two_level_pipeline_on_gpu(ctxs, oracle_mod):
+    """multiply (hybrid) -> mod switch -> multiply at the lower level with that level's context (custom moduli q0 q1 | p) ->
+    decrypt: the modulus chain of SURVEY.md section 8 row f-2 through the C ABI (tests/test_levels_cpu.py is the oracle-only twin)"""
+    from test_levels_cpu import build_chain
+    from test_oracle_kat import negacyclic_mod_t
+    ch = build_chain(oracle_mod, 12)
+    top, l3, low, l2 = ch["top"], ch["l3"], ch["low"], ch["l2"]
+    g_top, _ = ctxs(12, 4)
+    g_l3, _ = ctxs(12, 3, l3.moduli)
+    g_low, _ = ctxs(12, 3, low.moduli)
+    t = 65537
+    rng = np.random.default_rng(22)
+    s_top, s3, s2, s_low = top.keygen_secret(31), l3.keygen_secret(31), l2.keygen_secret(31), low.keygen_secret(31)
+    m1 = rng.integers(0, t, top.N).astype(np.uint64)
+    m2 = np.zeros(top.N, dtype=np.uint64); m2[1] = 2          # sparse factors keep the host-side expectation cheap
+    m3 = np.zeros(top.N, dtype=np.uint64); m3[3] = 5
+    c1, c2, c3 = l3.encrypt(41, t, s3, m1), l3.encrypt(42, t, s3, m2), l2.encrypt(44, t, s2, m3)
+    prod = torch.zeros((1, 2, 3, top.N), dtype=torch.int64, device="cuda")
+    g_top.ct_mul_relin_hybrid(dev(c1[None]), dev(c2[None]), dev(top.keygen_relin_hybrid(43, t, s_top)), prod, 1, t)
+    down = torch.zeros((1, 2, 2, top.N), dtype=torch.int64, device="cuda")
+    g_l3.mod_switch_down(prod, down, 2, t)
+    prod2 = torch.zeros_like(down)
+    g_low.ct_mul_relin_hybrid(down, dev(c3[None]), dev(low.keygen_relin_hybrid(45, t, s_low)), prod2, 1, t)
+    scale = pow(top.moduli[2], -1, t)
+    exp = np.zeros(top.N, dtype=object)
+    for k in range(top.N):                                     # m1 * 2X * 5X^3 = 10 X^4 m1, negacyclic
+        v = 10 * int(m1[k]) * scale
+        exp[(k + 4) % top.N] = (v if k + 4 < top.N else -v) % t
+    assert np.array_equal(l2.decrypt(s2, host(prod2).reshape(2, 2, top.N), t), exp.astype(np.uint64))
+
+
 def test_hybrid_errors(ctxs):
     c, o = ctxs(12, 1)
     x = torch.zeros((1, 2, 1, o.N), dtype=torch.int64, device="cuda")
