@@ -140,7 +140,7 @@ def emu_lib():
     lib.emu_rotate_hoisted.argtypes = [C.c_void_p, _u64p, C.c_size_t, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint, C.POINTER(C.c_uint)]
     lib.emu_pt_inner.argtypes = [C.c_void_p, _u64p, C.c_uint, _u64p, C.c_uint, _u64p, C.c_size_t, C.c_uint]
     lib.emu_mod_switch.argtypes = [C.c_void_p, _u64p, _u64p, C.c_size_t, C.c_uint64]
-    for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2)):
+    for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2), ("barrett_long", 2), ("pti_fold", 4)):
         f = getattr(lib, "emu_" + nm)
         f.restype = C.c_uint64
         f.argtypes = [C.c_void_p, C.c_uint] + [C.c_uint64] * nargs

@@ -383,4 +383,7 @@ uint64_t emu_mulmod(void *h, unsigned l, uint64_t a, uint64_t b) { return mulmod
 uint64_t emu_word_reduce(void *h, unsigned l, uint64_t x) { return word_reduce(x, ((Emu *)h)->lp[l]); }
 uint64_t emu_canon(void *h, unsigned l, uint64_t x) { return canon(x, ((Emu *)h)->lp[l]); }
 uint64_t emu_mulmod_lazy(void *h, unsigned l, uint64_t a, uint64_t b) { return mulmod_lazy(a, b, ((Emu *)h)->lp[l]); }
+// reductions of a two-word value z = hi:lo
+uint64_t emu_barrett_long(void *h, unsigned l, uint64_t hi, uint64_t lo) { return barrett_lazy_long(hi, lo, ((Emu *)h)->lp[l]); }
+uint64_t emu_pti_fold(void *h, unsigned l, uint64_t a0, uint64_t a1a, uint64_t a1b, uint64_t a2) { return pti_fold(a0, a1a, a1b, a2, ((Emu *)h)->lp[l]); }
 }

@@ -41,6 +41,21 @@ def test_device_scalar_arithmetic_bounds(make_emu, oracle_mod):
             assert e.scalar("mulmod", l, a, b) == (a * b) % q
             r = e.scalar("mulmod_lazy", l, a, b)
             assert r % q == (a * b) % q and r < 2 * q
+        # sums of up to 16 products (the plaintext inner products): z < 16 q^2 -> [0, 15q), and the split-operand fold -> [0, 3q)
+        zs = [0, 16 * (q - 1) ** 2, (q - 1) ** 2, 2**64 - 1, 2**64] + [int(a) * int(b) * k for a, b, k in zip(vals[:200], vals[200:400], range(1, 201)) if k <= 16]
+        for z in zs:
+            r = e.scalar("barrett_long", l, z >> 64, z & (2**64 - 1))
+            assert r % q == z % q and r < 15 * q
+        m30 = (1 << 30) - 1
+        for n_terms in (1, 7, 16):
+            pairs = [(q - 1, q - 1)] * n_terms if n_terms != 7 else [(int(a), int(b)) for a, b in zip(vals[:7], vals[7:14])]
+            a0 = sum((x & m30) * (y & m30) for x, y in pairs)
+            a1a = sum((x & m30) * (y >> 30) for x, y in pairs)
+            a1b = sum((x >> 30) * (y & m30) for x, y in pairs)
+            a2 = sum((x >> 30) * (y >> 30) for x, y in pairs)
+            assert max(a0, a1a, a1b, a2) < 2**64
+            r = e.scalar("pti_fold", l, a0, a1a, a1b, a2)
+            assert r % q == sum(x * y for x, y in pairs) % q and r < 3 * q
         # lazy operands as used by the fused kernel: u < 3q times key < q stays below 3q
         for a in (3 * q - 1, 2 * q + 5, q):
             for b in (q - 1, 1, q // 3):
