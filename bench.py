@@ -151,7 +151,7 @@ def run_reference(args):
     import oracle
     oracle.build()
     o = oracle.Oracle(LOG_N, L)
-    threads = o.max_threads()
+    threads = o.host_threads()       # all host cores, also under torchrun (which sets OMP_NUM_THREADS=1 per rank)
     s = o.keygen_secret(1)
     evk = o.keygen_relin(2, 65537, s)
     # bounded sample per step: about 2 s of CPU work, at most 1024 ciphertexts
@@ -345,7 +345,7 @@ def main():
             import oracle
             oracle.build()
             o = oracle.Oracle(LOG_N, L)
-            threads = o.max_threads()
+            threads = o.host_threads()
             rate, n, t = cpu_sample(o, args.cpu_seconds, threads)
             cpu = {"value": rate, "unit": "ct-mult/s", "cores": threads, "kind": "port",
                    "sample": "%d ct-mults in %.1f s, oracle/dpfhe_oracle.c with OpenMP (the reference has no CPU evaluator)" % (n, t)}

@@ -72,6 +72,7 @@ def lib():
         "dpo_encrypt": (None, [vp, u64, u64, u64p, u64p, u64p]),
         "dpo_phase": (None, [vp, u64p, u64p, u32, u64p]),
         "dpo_max_threads": (i32, []),
+        "dpo_num_procs": (i32, []),
         "dpo_time_ct_mul_relin": (C.c_double, [vp, u64p, u64p, u64p, u64p, sz, i32]),
         "dpo_time_ntt_fwd": (C.c_double, [vp, u64p, sz, i32]),
     }
@@ -300,6 +301,11 @@ class Oracle:
     # timing (bench cpu_baseline)
     def max_threads(self):
         return int(self._l.dpo_max_threads())
+
+    def host_threads(self):
+        """all the threads the timing helpers can use: the processors OpenMP sees, even when a launcher (torchrun sets
+        OMP_NUM_THREADS=1 per rank) capped the default team size; 1 when the oracle was built without OpenMP"""
+        return max(int(self._l.dpo_num_procs()), int(self._l.dpo_max_threads()))
 
     def time_ct_mul_relin(self, a, b, evk, threads=0):
         a = np.ascontiguousarray(a, dtype=np.uint64)

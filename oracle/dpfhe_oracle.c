@@ -806,6 +806,14 @@ int dpo_max_threads(void) {
     return 1;
 #endif
 }
+/* processors OpenMP could use (independent of OMP_NUM_THREADS, which launchers such as torchrun set to 1); 1 without OpenMP */
+int dpo_num_procs(void) {
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
+}
 double dpo_time_ct_mul_relin(const dpo_ctx *c, const uint64_t *a, const uint64_t *b, const uint64_t *evk,
                              uint64_t *out, size_t batch, int threads) {
 #ifdef _OPENMP

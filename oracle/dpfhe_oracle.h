@@ -125,6 +125,7 @@ void dpo_phase(const dpo_ctx *, const uint64_t *s_eval, const uint64_t *ct, unsi
 
 /* ---- timing helpers for bench.py (OpenMP over ciphertexts) ---- */
 int dpo_max_threads(void);
+int dpo_num_procs(void);   /* processors available to OpenMP, ignoring OMP_NUM_THREADS */
 /* run ct_mul_relin on `batch` cts with `threads` OpenMP threads; returns seconds */
 double dpo_time_ct_mul_relin(const dpo_ctx *, const uint64_t *a, const uint64_t *b, const uint64_t *evk,
                              uint64_t *out, size_t batch, int threads);
