@@ -307,9 +307,13 @@ class Oracle:
         OMP_NUM_THREADS=1 per rank) capped the default team size; 1 when the oracle was built without OpenMP"""
         return max(int(self._l.dpo_num_procs()), int(self._l.dpo_max_threads()))
 
-    def time_ct_mul_relin(self, a, b, evk, threads=0):
+    def time_ct_mul_relin(self, a, b, evk, threads=0, out=None):
+        """seconds of one dpo_ct_mul_relin over the batch; pass `out` to reuse a touched output buffer (a fresh one makes the
+        timed region pay the page faults of first-touching it)"""
         a = np.ascontiguousarray(a, dtype=np.uint64)
-        out = np.empty_like(a)
+        if out is None:
+            out = np.empty_like(a)
+        assert out.shape == a.shape and out.dtype == np.uint64 and out.flags.c_contiguous
         return float(self._l.dpo_time_ct_mul_relin(self._c, a.reshape(-1), np.ascontiguousarray(b).reshape(-1), np.ascontiguousarray(evk).reshape(-1), out.reshape(-1), a.size // (2 * self.P), threads)), out
 
     def time_ntt_fwd(self, data, threads=0):
