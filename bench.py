@@ -118,6 +118,26 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pick_threads(o):
+    """thread count for the CPU arm: the fastest of {all processors, half of them (one per core on SMT hosts), OpenMP's own
+    default} on a short probe — more threads are not always faster (measured on this pool's host: 128 threads 2.8 k, 64
+    threads 6.6 k ct-mult/s), and launchers such as torchrun cap OMP_NUM_THREADS at 1"""
+    procs = o.host_threads()
+    cands = sorted({procs, max(1, procs // 2), max(1, o.max_threads())}, reverse=True)
+    s = o.keygen_secret(1)
+    evk = o.keygen_relin(2, 65537, s)
+    n = min(512, 8 * max(cands))     # several ciphertexts per thread: a probe of one each mostly times the thread start-up
+    a = o.fill_uniform(SEED, 2 * n).reshape(n, 2, L, N)
+    b = o.fill_uniform(SEED, 2 * n, first_poly=2 * n).reshape(n, 2, L, N)
+    _, out = o.time_ct_mul_relin(a, b, evk, cands[0])
+    best, best_t = cands[0], None
+    for c in cands:
+        t = min(o.time_ct_mul_relin(a, b, evk, c, out=out)[0] for _ in range(3))
+        if best_t is None or t < best_t:
+            best, best_t = c, t
+    return best
+
+
 def cpu_sample(oracle_ctx, seconds, threads):
     """times the oracle's ct_mul_relin on a bounded sample for about `seconds` of wall time;
     returns (ct-mults/s, ct-mults timed, seconds).  The sample is at most 1024 ciphertexts (1.5 GiB of host
@@ -151,7 +171,7 @@ def run_reference(args):
     import oracle
     oracle.build()
     o = oracle.Oracle(LOG_N, L)
-    threads = o.host_threads()       # all host cores, also under torchrun (which sets OMP_NUM_THREADS=1 per rank)
+    threads = pick_threads(o)
     s = o.keygen_secret(1)
     evk = o.keygen_relin(2, 65537, s)
     # bounded sample per step: about 2 s of CPU work, at most 1024 ciphertexts
@@ -346,7 +366,7 @@ def main():
             import oracle
             oracle.build()
             o = oracle.Oracle(LOG_N, L)
-            threads = o.host_threads()
+            threads = pick_threads(o)
             rate, n, t = cpu_sample(o, args.cpu_seconds, threads)
             cpu = {"value": rate, "unit": "ct-mult/s", "cores": threads, "kind": "port",
                    "sample": "%d ct-mults in %.1f s, oracle/dpfhe_oracle.c with OpenMP (the reference has no CPU evaluator)" % (n, t)}
