@@ -485,7 +485,7 @@ int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, con
         for (size_t r = 0; r < n_rot; ++r) {
             u64 *out = d_out + (r * batch + first) * 2 * P;
             CU_TRY(launch_rot_prepare(ctx->lc, d_gks[r], (u32)galois_elts[r], ctx->hoist_delta, ctx->hoist_M, ctx->hoist_kprime, st));
-            CU_TRY(launch_rot_apply(ctx->lc, in, ctx->hoist_U, d_gks[r], ctx->hoist_kprime, (u32)galois_elts[r], out, cnt, st));
+            CU_TRY(launch_rot_apply(ctx->lc, in, L > 1 ? ctx->hoist_U : nullptr, d_gks[r], ctx->hoist_kprime, (u32)galois_elts[r], out, cnt, st));
             ctx->launches += 5;   // key_prepare, negmask, ntt, kprime, rot_apply
             if (L > 1) {
                 CU_TRY(launch_ks(ctx->lc, KS_ROTATE, in, nullptr, d_gks[r], out, cnt, (u32)galois_elts[r], st, ctx->hoist_zero, true));

@@ -532,7 +532,7 @@ DPFHE_HD void ms_limb_body(CTA &cta, u64 *buf, const u64 *tau, const u64 *c_limb
 // Ciphertexts with a zero coefficient in some t_j are flagged and recomputed by the ordinary rotate kernel.
 struct HoistArgs {
     const u64 *ct;       // [batch][2][L][N]
-    u64 *U;              // [batch][L j][L i][N]: NTT_i(t_j mod q_i), lazy (< 16 q_i); the diagonal j == i is not used
+    u64 *U;              // [batch][L j][L i][N]: NTT_i(t_j mod q_i), lazy (< 16 q_i); the diagonal j == i holds c1[i] itself
     u64 *scratch;        // digit exchange slots, as KsArgs::scratch
     u32 *zero;           // [batch] set to 1 when some t_j has a zero coefficient
     const Twiddle *tw, *itw;
@@ -548,9 +548,15 @@ DPFHE_HD void hoist_phase1(CTA &cta, u64 *buf, const HoistArgs &A, const LimbPar
     const Twiddle *itw = A.itw + (size_t)i * N;
     U64x2 *dst = reinterpret_cast<U64x2 *>(t_slot);
     u32 *zero = A.zero + ct;
+    // the digit itself is the i == j entry of U (a plain copy), so that the apply step reads every digit the same way
+    U64x2 *diag = reinterpret_cast<U64x2 *>(A.U + ((ct * A.L + i) * A.L + i) * N);
     auto build = [&](int c_lo, int n_c) {
         cta.par([&](int tid) {
-            for (int lc = tid; lc < n_c; lc += NT) reinterpret_cast<U64x2 *>(buf)[swz_chunk(lc)] = ld_stream(src + c_lo + lc);
+            for (int lc = tid; lc < n_c; lc += NT) {
+                const U64x2 v = ld_stream(src + c_lo + lc);
+                reinterpret_cast<U64x2 *>(buf)[swz_chunk(lc)] = v;
+                st_stream(diag + c_lo + lc, v);
+            }
         });
     };
     auto emit = [&](int c, const U64x2 &v) {
@@ -604,7 +610,7 @@ DPFHE_HD void hoist_phase2(CTA &cta, u64 *buf, const HoistArgs &A, const LimbPar
 // so the two coefficients of an output chunk come from one 16-byte chunk of the source row.
 struct RotApplyArgs {
     const u64 *ct;       // [batch][2][L][N]
-    const u64 *U;        // [batch][L][L][N]
+    const u64 *U;        // [batch][L][L][N] (diagonal = c1 limbs); nullptr when L == 1: the only digit is c1[0] itself
     const u64 *key;      // [L][2][L][N] Galois key of this rotation
     const u64 *key_s;    // its Shoup companions
     const u64 *kprime;   // [2][L][N] canonical: NTT_i(negmask_g) o sum_{j != i} (q_j mod q_i) * key[j][c][i]
@@ -649,12 +655,25 @@ DPFHE_HD void rot_apply_rows(CTA &cta, const RotApplyArgs &A, const LimbParams &
 #pragma unroll
                 for (int b = 0; b < CB; ++b) {
                     const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);   // rows past the end repeat the last one, not stored
-                    o.u[b] = gather(j == i ? A.ct + ct * 2 * P + P + (size_t)i * N : A.U + ((ct * L + j) * L + i) * N);
+                    o.u[b] = gather(A.U != nullptr ? A.U + ((ct * L + j) * L + i) * N : A.ct + ct * 2 * P + P);
                 }
             };
-            RotOperands<CB> nxt;
-            fetch(0, nxt);
             U64x2 r0[CB], r1[CB];
+            auto mac = [&](const RotOperands<CB> &o, bool trim) {
+#pragma unroll
+                for (int b = 0; b < CB; ++b) {
+                    r0[b].x += shoup_lazy(o.u[b].x, o.vb.x, o.vbs.x, p);
+                    r0[b].y += shoup_lazy(o.u[b].y, o.vb.y, o.vbs.y, p);
+                    r1[b].x += shoup_lazy(o.u[b].x, o.va.x, o.vas.x, p);
+                    r1[b].y += shoup_lazy(o.u[b].y, o.va.y, o.vas.y, p);
+                    if (trim) {   // + 2q per digit from below 2q: one csub(8q) every fourth digit keeps the sums below 16q
+                        r0[b].x = csub(r0[b].x, p.q8); r0[b].y = csub(r0[b].y, p.q8);
+                        r1[b].x = csub(r1[b].x, p.q8); r1[b].y = csub(r1[b].y, p.q8);
+                    }
+                }
+            };
+            RotOperands<CB> oa, ob;   // two operand sets used alternately: the loads of one fly during the arithmetic of the other
+            fetch(0, oa);
             {
                 const U64x2 k0 = ld_keep(kp0 + c), k1 = ld_keep(kp1 + c);
 #pragma unroll
@@ -666,25 +685,14 @@ DPFHE_HD void rot_apply_rows(CTA &cta, const RotApplyArgs &A, const LimbParams &
                     r1[b] = k1;
                 }
             }
-            for (u32 j = 0; j < L; ++j) {
-                RotOperands<CB> o = nxt;
-                if (PF) {
-                    if (j + 1 < L) fetch(j + 1, nxt);
-                }
-                const bool trim = (j & 3u) == 3u;   // + 2q per digit from below 2q: one csub(8q) every fourth digit keeps the sums below 16q
-#pragma unroll
-                for (int b = 0; b < CB; ++b) {
-                    r0[b].x += shoup_lazy(o.u[b].x, o.vb.x, o.vbs.x, p);
-                    r0[b].y += shoup_lazy(o.u[b].y, o.vb.y, o.vbs.y, p);
-                    r1[b].x += shoup_lazy(o.u[b].x, o.va.x, o.vas.x, p);
-                    r1[b].y += shoup_lazy(o.u[b].y, o.va.y, o.vas.y, p);
-                    if (trim) {
-                        r0[b].x = csub(r0[b].x, p.q8); r0[b].y = csub(r0[b].y, p.q8);
-                        r1[b].x = csub(r1[b].x, p.q8); r1[b].y = csub(r1[b].y, p.q8);
-                    }
-                }
-                if (!PF) {
-                    if (j + 1 < L) fetch(j + 1, nxt);
+            for (u32 j = 0; j < L; j += 2) {
+                if (PF && j + 1 < L) fetch(j + 1, ob);
+                mac(oa, false);
+                if (j + 1 < L) {
+                    if (!PF) fetch(j + 1, ob);
+                    if (PF && j + 2 < L) fetch(j + 2, oa);
+                    mac(ob, (j & 2u) != 0u);   // digits 3, 7, 11, 15
+                    if (!PF && j + 2 < L) fetch(j + 2, oa);
                 }
             }
 #pragma unroll

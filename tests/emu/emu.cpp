@@ -223,7 +223,7 @@ void run_rotate_hoisted(Emu &e, const uint64_t *ct, size_t n_rot, const uint64_t
                     kprime[(size_t)c * P + (size_t)i * N + n] = host_mulmod(s, M[(size_t)i * N + n], q);
                 }
         RotApplyArgs R;
-        R.ct = ct; R.U = U; R.key = key; R.key_s = key_s; R.kprime = kprime; R.out = out + r * batch * 2 * P; R.L = L; R.galois = g;
+        R.ct = ct; R.U = L > 1 ? U : nullptr; R.key = key; R.key_s = key_s; R.kprime = kprime; R.out = out + r * batch * 2 * P; R.L = L; R.galois = g;
         for (size_t k = 0; k < batch; k += 2)   // blocks of two ciphertexts, the last one ragged; odd rotations use the prefetching form
             for (unsigned i = 0; i < L; ++i) {
                 const unsigned n_ct = (unsigned)(batch - k < 2 ? batch - k : 2);
