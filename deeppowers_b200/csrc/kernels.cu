@@ -709,26 +709,32 @@ cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b
     return cudaErrorNotSupported;
 }
 
+// shared-memory plan of pt_inner_kernel: two CTAs per SM (113 KiB each); the plaintext tile takes nb * 128 bytes per
+// giant step and the two ciphertext-row buffers 2 * nb * 128 bytes each.  Returns giant steps per launch (0: nb too large).
+static constexpr size_t PTI_SMEM_BUDGET = (size_t)113 << 10;
+static u32 pt_inner_gmax(u32 nb) {
+    const size_t row = (size_t)nb * PTI_COEFFS * 8;
+    if (5 * row > PTI_SMEM_BUDGET) return 0;
+    u32 gmax = (u32)((PTI_SMEM_BUDGET - 4 * row) / row);
+    if (gmax >= 8) gmax -= gmax % 8;   // whole rounds of the CTA's eight warps
+    return gmax;
+}
+
 template <int LOGN>
-static cudaError_t launch_pt_inner_t(const LaunchCtx &lc, const PtInnerArgs &A, cudaStream_t st) {
+static cudaError_t launch_pt_inner_t(const LaunchCtx &lc, const PtInnerArgs &A, u32 gmax, cudaStream_t st) {
     constexpr int NT = 256, MINB = 2;
     auto kern = pt_inner_kernel<LOGN, NT, MINB>;
-    // two CTAs per SM: at most 112 KiB each; the plaintext tile takes nb * 128 bytes per giant step
-    const size_t budget = (size_t)113 << 10, row = (size_t)A.nb * PTI_COEFFS * 8;
-    if (5 * row > budget) return cudaErrorInvalidValue;
-    u32 gmax = (u32)((budget - 4 * row) / row);
-    if (gmax >= NT / 32) gmax -= gmax % (NT / 32);   // whole rounds of warps
     static bool configured[64] = {};
     if (!configured[lc.device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PTI_SMEM_BUDGET);
         if (e != cudaSuccess) return e;
         configured[lc.device & 63] = true;
     }
+    const size_t row = (size_t)A.nb * PTI_COEFFS * 8;
     const unsigned grid = (unsigned)(lc.L * (((size_t)1 << LOGN) / PTI_COEFFS));
     for (u32 g0 = 0; g0 < A.ng; g0 += gmax) {
         const u32 gcnt = A.ng - g0 < gmax ? A.ng - g0 : gmax;
-        const size_t smem = ((size_t)gcnt + 4) * row;
-        kern<<<grid, NT, smem, st>>>(A, lc.lt, g0, gcnt);
+        kern<<<grid, NT, ((size_t)gcnt + 4) * row, st>>>(A, lc.lt, g0, gcnt);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -742,15 +748,13 @@ cudaError_t launch_pt_inner(const LaunchCtx &lc, const u64 *steps, u32 nb, const
     if (!batch || !nb || !ng) return cudaSuccess;
     PtInnerArgs A;
     A.steps = steps; A.pts = pts; A.out = out; A.batch = batch; A.L = lc.L; A.nb = nb; A.ng = ng;
-    const size_t budget = (size_t)113 << 10, row = (size_t)nb * PTI_COEFFS * 8;
-    if (5 * row > budget) return cudaErrorInvalidValue;
-    u32 gmax = (u32)((budget - 4 * row) / row);
-    if (gmax >= 8) gmax -= gmax % 8;
+    const u32 gmax = pt_inner_gmax(nb);
+    if (gmax == 0) return cudaErrorInvalidValue;
     *launches = (ng + gmax - 1) / gmax;
     switch (lc.log_n) {
-        case 12: return launch_pt_inner_t<12>(lc, A, st);
-        case 13: return launch_pt_inner_t<13>(lc, A, st);
-        case 14: return launch_pt_inner_t<14>(lc, A, st);
+        case 12: return launch_pt_inner_t<12>(lc, A, gmax, st);
+        case 13: return launch_pt_inner_t<13>(lc, A, gmax, st);
+        case 14: return launch_pt_inner_t<14>(lc, A, gmax, st);
     }
     return cudaErrorInvalidValue;
 }
