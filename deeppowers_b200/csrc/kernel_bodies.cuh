@@ -815,10 +815,7 @@ DPFHE_HD void pt_inner_tile(CTA &cta, u64 *smem, const PtInnerArgs &A, const Lim
                 }
                 for (u32 b0 = 0; b0 < nb; b0 += PTI_FLUSH) {
                     const u32 b1 = b0 + PTI_FLUSH < nb ? b0 + PTI_FLUSH : nb;
-// unrolled by four: ptxas lowers the accumulation to IMAD.WIDE (no addend) + one three-input IADD3 / IADD3.X pair per
-                    // two products; it does not keep a loop-carried 64-bit addend in the multiplier in any formulation tried
-#pragma unroll 4
-                    for (u32 b = b0; b < b1; ++b) {
+                    auto step = [&](u32 b) {
                         const u64 xv = xrow[b * 32];
                         const u32 x0 = (u32)xv, x1 = (u32)(xv >> 32);
 #pragma unroll
@@ -830,6 +827,15 @@ DPFHE_HD void pt_inner_tile(CTA &cta, u64 *smem, const PtInnerArgs &A, const Lim
                             mad_wide(a1b[j], x1, p0);
                             mad_wide(a2[j], x1, p1);
                         }
+                    };
+                    // ptxas lowers the accumulation to IMAD.WIDE (no addend) + one three-input IADD3 / IADD3.X pair per two
+                    // products; it does not keep a loop-carried 64-bit addend in the multiplier in any formulation tried.
+                    if (b1 - b0 == PTI_FLUSH) {
+#pragma unroll
+                        for (u32 u = 0; u < PTI_FLUSH; ++u) step(b0 + u);   // full group: shared-memory offsets become immediates
+                    } else {
+#pragma unroll 4
+                        for (u32 b = b0; b < b1; ++b) step(b);
                     }
 #pragma unroll
                     for (int j = 0; j < PTI_GBLK; ++j) {
