@@ -338,6 +338,8 @@ def main():
         ok = bool(torch.equal(ho.cuda(), out))     # the host path must reproduce the device path bit for bit
         e2e = {"value": world * B / e2e_s, "unit": "ct-mult/s", "h2d_bytes_per_step": 2 * B * CT_BYTES + 2 * L * P_WORDS * 8,
                "d2h_bytes_per_step": B * CT_BYTES, "ms_per_step": e2e_s * 1e3, "matches_device_path": ok,
+               "pcie": {"h2d_GBps_per_gpu": (2 * B * CT_BYTES + 2 * L * P_WORDS * 8) / e2e_s / 1e9, "d2h_GBps_per_gpu": B * CT_BYTES / e2e_s / 1e9,
+                        "note": "both directions run concurrently; the host-to-device stream (two operand batches per result batch) is the bound"},
                "api": "dpfhe_ct_mul_relin_host (pinned host buffers, 3-stage H2D/compute/D2H pipeline)"}
         del ha, hb, ho, hk
 
