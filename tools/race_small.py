@@ -23,6 +23,14 @@ for log_n, L, B in ((13, 4, 3), (12, 2, 2), (14, 2, 1)):
         c.ct_mul_relin_hybrid(ha, hb, hk, ho, B, 65537)
         c.rotate_hybrid(ha, 5, hk, ho, B, 65537)
         c.mod_switch_down(a, ho, 2 * B, 65537)
+    # hoisted rotations (zero digits included: the filtered fallback kernel runs) and the fused plaintext inner products
+    a[B - 1, 1] = 0
+    keys = torch.empty((2, L, 2, L, N), dtype=torch.int64, device="cuda"); c.fill_uniform(7, keys, 4 * L)
+    hout = torch.empty((2, B, 2, L, N), dtype=torch.int64, device="cuda")
+    c.rotate_hoisted(a, [c.galois_elt(1), c.galois_elt(-2)], [keys[0], keys[1]], hout, B)
+    pts = torch.empty((3, 2, L, N), dtype=torch.int64, device="cuda"); c.fill_uniform(8, pts, 6)
+    iout = torch.empty((3, B, 2, L, N), dtype=torch.int64, device="cuda")
+    c.ct_mul_plain_inner(hout, pts, iout, 2, 3, B)
     torch.cuda.synchronize()
     c.close()
 print("ok")
