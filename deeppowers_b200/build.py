@@ -7,8 +7,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libdpfhe.so")
-SOURCES = ["kernels.cu", "abi.cu", "host_params.cpp"]
-HEADERS = ["modarith.cuh", "ntt_core.cuh", "kernel_bodies.cuh", "launch.hpp", "host_params.hpp",
+# (source, object name, extra flags): kernels.cu is compiled once per arithmetic variant (csrc/types.hpp)
+UNITS = [("kernels.cu", "kernels_gen", ["-DDPFHE_FAST=0"]), ("kernels.cu", "kernels_fast", ["-DDPFHE_FAST=1"]),
+         ("abi.cu", "abi", []), ("host_params.cpp", "host_params", [])]
+SOURCES = sorted({u[0] for u in UNITS})
+HEADERS = ["types.hpp", "modarith.cuh", "ntt_core.cuh", "kernel_bodies.cuh", "launch.hpp", "host_params.hpp",
            os.path.join("..", "..", "include", "dpfhe.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -41,9 +44,9 @@ def build(force=False, verbose=False):
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     procs = []
-    for src in SOURCES:
-        obj = os.path.join(bdir, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+    for src, name, extra in UNITS:
+        obj = os.path.join(bdir, name + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for cmd, p in procs:

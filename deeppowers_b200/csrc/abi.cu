@@ -43,6 +43,9 @@ int fail(int code, const char *fmt, ...) {
 
 constexpr int PIPE_DEPTH = 3;
 
+// launcher of the context's arithmetic variant (launch.hpp): dpfhe::fast when every modulus is k * 2^32 + 1
+#define VCALL(fn, lc, ...) ((lc).fast ? fast::fn((lc), __VA_ARGS__) : gen::fn((lc), __VA_ARGS__))
+
 }  // namespace
 
 struct dpfhe_ctx {
@@ -215,6 +218,9 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     lc.num_sms = prop.multiProcessorCount;
     lc.log_n = ctx->hp.log_n;
     lc.L = ctx->hp.L;
+    lc.fast = true;
+    for (size_t l = 0; l < L; ++l) lc.fast = lc.fast && lps[l].nqh != 0;
+    if (getenv("DPFHE_FORCE_GENERIC")) lc.fast = false;   // diagnostics: run fast-class moduli through the generic kernels
     lc.lp = ctx->d_lp;
     memset(&lc.lt, 0, sizeof(lc.lt));
     for (size_t l = 0; l < L; ++l) lc.lt.lp[l] = lps[l];
@@ -227,6 +233,7 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     // digit-exchange scratch for the fused key-switch kernel: one slot per resident CTA, two parities
     lc.ks_slots = (size_t)lc.num_sms * 4;
     CTX_TRY(cudaMalloc(&lc.ks_scratch, lc.ks_slots * 2 * N * 8));
+    CTX_TRY(cudaMalloc(&lc.ks_acc, lc.ks_slots * 2 * N * 8));
     CTX_TRY(cudaMalloc(&lc.ks_key_s, 2 * L * L * N * 8));
     ctx->device_bytes += 2 * L * L * N * 8;
     CTX_TRY(cudaMalloc(&lc.ks_flags, lc.ks_slots * sizeof(u32)));
@@ -234,7 +241,7 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     CTX_TRY(cudaMalloc(&lc.ks_ticket, 64));
     CTX_TRY(cudaMalloc(&lc.ks_mail, lc.ks_slots * sizeof(u64)));
     CTX_TRY(cudaMemset(lc.ks_mail, 0, lc.ks_slots * sizeof(u64)));
-    ctx->device_bytes += lc.ks_slots * 2 * N * 8 + lc.ks_slots * sizeof(u32);
+    ctx->device_bytes += 2 * lc.ks_slots * 2 * N * 8 + lc.ks_slots * (sizeof(u32) + sizeof(u64)) + 64;
     if (getenv("DPFHE_KS_PROF")) {   // diagnostics: per-phase cycle counters of the fused kernel
         CTX_TRY(cudaMalloc(&lc.ks_prof, lc.ks_slots * 16 * sizeof(unsigned long long)));
         CTX_TRY(cudaMemset(lc.ks_prof, 0, lc.ks_slots * 16 * sizeof(unsigned long long)));
@@ -253,6 +260,8 @@ void dpfhe_context_destroy(dpfhe_ctx *ctx) {
     cudaFree(ctx->d_tw);
     cudaFree(ctx->d_itw);
     cudaFree(ctx->lc.ks_scratch);
+    cudaFree(ctx->lc.ks_acc);
+    cudaFree(ctx->lc.ks_acc_hyb);
     cudaFree(ctx->lc.ks_flags);
     cudaFree(ctx->lc.ks_key_s);
     cudaFree(ctx->lc.ks_ticket);
@@ -311,7 +320,7 @@ int dpfhe_ntt_fwd(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream
     if (rc) return rc;
     if (n_polys == 0) return DPFHE_OK;
     CHECK_PTR(d_data);
-    CU_TRY(launch_ntt(ctx->lc, d_data, n_polys, false, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_ntt, ctx->lc, d_data, n_polys, false, pick(ctx, stream)));
     ctx->launches++;
     return DPFHE_OK;
 }
@@ -320,7 +329,7 @@ int dpfhe_ntt_inv(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream
     if (rc) return rc;
     if (n_polys == 0) return DPFHE_OK;
     CHECK_PTR(d_data);
-    CU_TRY(launch_ntt(ctx->lc, d_data, n_polys, true, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_ntt, ctx->lc, d_data, n_polys, true, pick(ctx, stream)));
     ctx->launches++;
     return DPFHE_OK;
 }
@@ -330,7 +339,7 @@ int dpfhe_poly_mul_pointwise(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t
     if (rc) return rc;
     if (n_polys == 0) return DPFHE_OK;
     CHECK_PTR(d_a); CHECK_PTR(d_b); CHECK_PTR(d_out);
-    CU_TRY(launch_pointwise_mul(ctx->lc, d_a, d_b, d_out, n_polys, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_pointwise_mul, ctx->lc, d_a, d_b, d_out, n_polys, pick(ctx, stream)));
     ctx->launches++;
     return DPFHE_OK;
 }
@@ -340,7 +349,7 @@ int dpfhe_poly_add(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uin
     if (rc) return rc;
     if (n_polys == 0) return DPFHE_OK;
     CHECK_PTR(d_a); CHECK_PTR(d_b); CHECK_PTR(d_out);
-    CU_TRY(launch_poly_add(ctx->lc, d_a, d_b, d_out, n_polys, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_poly_add, ctx->lc, d_a, d_b, d_out, n_polys, pick(ctx, stream)));
     ctx->launches++;
     return DPFHE_OK;
 }
@@ -350,7 +359,7 @@ int dpfhe_ct_tensor(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, ui
     if (rc) return rc;
     if (batch == 0) return DPFHE_OK;
     CHECK_PTR(d_a); CHECK_PTR(d_b); CHECK_PTR(d_d);
-    CU_TRY(launch_ct_tensor(ctx->lc, d_a, d_b, d_d, batch, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_ct_tensor, ctx->lc, d_a, d_b, d_d, batch, pick(ctx, stream)));
     ctx->launches++;
     return DPFHE_OK;
 }
@@ -367,7 +376,7 @@ static int ks_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const uint64_t
         if (!(galois & 1) || galois >= two_n) return fail(DPFHE_ERR_INVALID, "galois element must be odd and < 2N");
     }
     if (out == a || out == b) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
-    CU_TRY(launch_ks(ctx->lc, mode, a, b, key, out, batch, (u32)galois, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_ks, ctx->lc, mode, a, b, key, out, batch, (u32)galois, pick(ctx, stream)));
     ctx->launches += 2;   // key_prepare_kernel + ks_fused_kernel
     return DPFHE_OK;
 }
@@ -402,12 +411,15 @@ static int ks_hybrid_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const u
     if (out == a || out == b) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
     if (!ctx->lc.ks_hyb) {
         u64 *hyb = nullptr;
-        CU_TRY(cudaMalloc(&hyb, (ctx->lc.ks_slots / 2 + 1) * KS_HYB_ROWS * ctx->N() * sizeof(u64)));
+        const size_t hyb_bytes = (ctx->lc.ks_slots / 2 + 1) * KS_HYB_ROWS * ctx->N() * sizeof(u64), acc_bytes = ctx->lc.ks_slots * 4 * ctx->N() * sizeof(u64);
+        CU_TRY(cudaMalloc(&hyb, hyb_bytes));
         ctx->lc.ks_hyb = hyb;
+        CU_TRY(cudaMalloc(&ctx->lc.ks_acc_hyb, acc_bytes));
+        ctx->device_bytes += hyb_bytes + acc_bytes;
     }
     MsConsts K;
     build_ms_consts(ctx->hp, t_plain, K);
-    CU_TRY(launch_ks_hybrid(ctx->lc, mode, a, b, key, out, batch, (u32)galois, K, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_ks_hybrid, ctx->lc, mode, a, b, key, out, batch, (u32)galois, K, pick(ctx, stream)));
     ctx->launches += 2;   // key_prepare_kernel + ks_hybrid_kernel
     return DPFHE_OK;
 }
@@ -479,16 +491,16 @@ int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, con
         const u64 *in = d_ct + first * 2 * P;
         CU_TRY(cudaMemsetAsync(ctx->hoist_zero, 0, cnt * sizeof(u32), st));
         if (L > 1) {
-            CU_TRY(launch_hoist(ctx->lc, in, ctx->hoist_U, ctx->hoist_zero, cnt, st));
+            CU_TRY(VCALL(launch_hoist, ctx->lc, in, ctx->hoist_U, ctx->hoist_zero, cnt, st));
             ctx->launches++;
         }
         for (size_t r = 0; r < n_rot; ++r) {
             u64 *out = d_out + (r * batch + first) * 2 * P;
-            CU_TRY(launch_rot_prepare(ctx->lc, d_gks[r], (u32)galois_elts[r], ctx->hoist_delta, ctx->hoist_M, ctx->hoist_kprime, st));
-            CU_TRY(launch_rot_apply(ctx->lc, in, L > 1 ? ctx->hoist_U : nullptr, d_gks[r], ctx->hoist_kprime, (u32)galois_elts[r], out, cnt, st));
+            CU_TRY(VCALL(launch_rot_prepare, ctx->lc, d_gks[r], (u32)galois_elts[r], ctx->hoist_delta, ctx->hoist_M, ctx->hoist_kprime, st));
+            CU_TRY(VCALL(launch_rot_apply, ctx->lc, in, L > 1 ? ctx->hoist_U : nullptr, d_gks[r], ctx->hoist_kprime, (u32)galois_elts[r], out, cnt, st));
             ctx->launches += 5;   // key_prepare, negmask, ntt, kprime, rot_apply
             if (L > 1) {
-                CU_TRY(launch_ks(ctx->lc, KS_ROTATE, in, nullptr, d_gks[r], out, cnt, (u32)galois_elts[r], st, ctx->hoist_zero, true));
+                CU_TRY(VCALL(launch_ks, ctx->lc, KS_ROTATE, in, nullptr, d_gks[r], out, cnt, (u32)galois_elts[r], st, ctx->hoist_zero, true));
                 ctx->launches++;
             }
         }
@@ -501,7 +513,7 @@ int dpfhe_ct_mul_plain(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_p
     if (rc) return rc;
     if (batch == 0) return DPFHE_OK;
     CHECK_PTR(d_ct); CHECK_PTR(d_pt); CHECK_PTR(d_out);
-    CU_TRY(launch_ct_mul_plain(ctx->lc, d_ct, d_pt, d_out, batch, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_ct_mul_plain, ctx->lc, d_ct, d_pt, d_out, batch, pick(ctx, stream)));
     ctx->launches++;
     return DPFHE_OK;
 }
@@ -511,7 +523,7 @@ int dpfhe_ct_mul_plain_acc(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t 
     if (rc) return rc;
     if (batch == 0) return DPFHE_OK;
     CHECK_PTR(d_ct); CHECK_PTR(d_pt); CHECK_PTR(d_acc);
-    CU_TRY(launch_ct_mul_plain_acc(ctx->lc, d_ct, d_pt, d_acc, batch, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_ct_mul_plain_acc, ctx->lc, d_ct, d_pt, d_acc, batch, pick(ctx, stream)));
     ctx->launches++;
     return DPFHE_OK;
 }
@@ -526,7 +538,7 @@ int dpfhe_ct_mul_plain_inner(dpfhe_ctx *ctx, const uint64_t *d_steps, size_t n_s
     if (n_groups > 65535) return fail(DPFHE_ERR_INVALID, "n_groups must be below 65536");
     if (d_out == d_steps) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
     unsigned launches = 0;
-    CU_TRY(launch_pt_inner(ctx->lc, d_steps, (u32)n_steps, d_pts, (u32)n_groups, d_out, batch, pick(ctx, stream), &launches));
+    CU_TRY(VCALL(launch_pt_inner, ctx->lc, d_steps, (u32)n_steps, d_pts, (u32)n_groups, d_out, batch, pick(ctx, stream), &launches));
     ctx->launches += launches;
     return DPFHE_OK;
 }
@@ -552,7 +564,7 @@ int dpfhe_mod_switch_down(dpfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out,
     }
     MsConsts K;
     build_ms_consts(ctx->hp, t_plain, K);
-    CU_TRY(launch_mod_switch(ctx->lc, d_in, ctx->ms_tau, d_out, K, n_polys, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_mod_switch, ctx->lc, d_in, ctx->ms_tau, d_out, K, n_polys, pick(ctx, stream)));
     ctx->launches += 2;
     return DPFHE_OK;
 }
@@ -562,7 +574,7 @@ int dpfhe_fill_uniform(dpfhe_ctx *ctx, uint64_t seed, uint64_t first_poly, uint6
     if (rc) return rc;
     if (n_polys == 0) return DPFHE_OK;
     CHECK_PTR(d_data);
-    CU_TRY(launch_fill_uniform(ctx->lc, seed, first_poly, d_data, n_polys, pick(ctx, stream)));
+    CU_TRY(VCALL(launch_fill_uniform, ctx->lc, seed, first_poly, d_data, n_polys, pick(ctx, stream)));
     ctx->launches++;
     return DPFHE_OK;
 }
@@ -578,7 +590,7 @@ static int ntt_host(dpfhe_ctx *ctx, uint64_t *h_data, size_t n_polys, bool inver
     const size_t chunk = pick_chunk(ctx, P * 8, n_polys);
     return run_pipeline(ctx, h_data, nullptr, h_data, n_polys, P, P, chunk,
                         [&](u64 *din, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
-                            CU_TRY(launch_ntt(ctx->lc, din, cnt, inverse, st));
+                            CU_TRY(VCALL(launch_ntt, ctx->lc, din, cnt, inverse, st));
                             ctx->launches++;
                             CU_TRY(cudaMemcpyAsync(dout, din, cnt * P * 8, cudaMemcpyDeviceToDevice, st));
                             return DPFHE_OK;
@@ -683,7 +695,7 @@ int dpfhe_ct_mul_plain_host(dpfhe_ctx *ctx, const uint64_t *h_ct, const uint64_t
     const size_t chunk = pick_chunk(ctx, 2 * P * 8, batch);
     return run_pipeline(ctx, h_ct, nullptr, h_out, batch, 2 * P, 2 * P, chunk,
                         [&](u64 *dc, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
-                            CU_TRY(launch_ct_mul_plain(ctx->lc, dc, ctx->stage_key, dout, cnt, st));
+                            CU_TRY(VCALL(launch_ct_mul_plain, ctx->lc, dc, ctx->stage_key, dout, cnt, st));
                             ctx->launches++;
                             return DPFHE_OK;
                         });

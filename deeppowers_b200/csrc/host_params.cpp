@@ -1,8 +1,6 @@
 // host_params.cpp — see host_params.hpp.  Plain C++17, compiled into libdpfhe.so.
 #include "host_params.hpp"
 
-#include "ntt_core.cuh"
-
 namespace dpfhe {
 
 typedef unsigned __int128 u128;
@@ -101,9 +99,11 @@ std::string build_host_params(unsigned log_n, unsigned L, const uint64_t *moduli
             qs.push_back(q);
         }
     } else {
-        uint64_t cand = ((1ull << 60) / two_n) * two_n + 1;
+        // default basis: the L largest primes below 2^60 of the form k * 2^32 + 1.  They are 1 mod 2N
+        // for every supported N, and multiplying by such a modulus costs one 32-bit multiply-add (modarith.cuh, DPFHE_FAST).
+        uint64_t cand = (1ull << 60) + 1;
         while (qs.size() < L) {
-            cand -= two_n;
+            cand -= 1ull << 32;
             if (host_is_prime(cand)) qs.push_back(cand);
         }
     }
@@ -127,6 +127,7 @@ std::string build_host_params(unsigned log_n, unsigned L, const uint64_t *moduli
         LimbParams &lp = hl.lp;
         lp.q = q;
         lp.q2 = 2 * q;
+        lp.qsb = (uint64_t)SB * q;
         lp.q4 = 4 * q;
         lp.q8 = 8 * q;
         lp.nq = 0 - q;
@@ -134,6 +135,8 @@ std::string build_host_params(unsigned log_n, unsigned L, const uint64_t *moduli
         lp.bar_shift = bits - 2;
         lp.bar_mu = (uint64_t)(((u128)1 << (lp.bar_shift + 64)) / q);
         lp.mu32 = (uint32_t)(((u128)1 << 64) / q);
+        lp.nqh = (uint32_t)q == 1u ? 0u - (uint32_t)(q >> 32) : 0u;
+        lp.pad_ = 0;
         lp.ninv = host_powmod((uint64_t)N % q, q - 2, q);
         lp.ninv_s = shoup_of(lp.ninv, q);
         lp.wninv = host_mulmod(hl.inv_root_powers[1], lp.ninv, q);

@@ -6,7 +6,7 @@
 #include <string>
 #include <vector>
 
-#include "modarith.cuh"
+#include "types.hpp"
 
 namespace dpfhe {
 

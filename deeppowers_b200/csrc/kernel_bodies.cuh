@@ -9,6 +9,7 @@
 #include "ntt_core.cuh"
 
 namespace dpfhe {
+namespace DPFHE_VNS {
 
 DPFHE_HD u32 bitrev_n(u32 x, int bits) {
 #if defined(__CUDA_ARCH__)
@@ -131,7 +132,21 @@ DPFHE_HD void mac128(u64 &hi, u64 &lo, u64 a, u64 b) {
 #endif
 }
 
-// tensor of one coefficient: canonical inputs; d0,d2 in [0,2q), d1 in [0,3q)
+// Lazy accumulators gain one Shoup product (< SB*q) per step from a start bound b0 (b0 + SB <= 16).  Whenever the next
+// addition could pass 16q the value takes one csub(8q) right after the current one ([0,16q) -> [0,8q)).
+// Returns whether the addition with 0-based index `step` is followed by that trim; uniform scalar code.
+DPFHE_HD bool acc_trim_after(int b0, int step) {
+    int b = b0;
+    bool t = false;
+    for (int s = 0; s <= step; ++s) {
+        b += SB;
+        t = b + SB > 16;
+        if (t) b = 8;
+    }
+    return t;
+}
+
+// tensor of one coefficient: canonical inputs; d0,d2 in [0,SB*q), d1 in [0,(SB+1)q)
 DPFHE_HD void tensor_coeff(u64 a0, u64 a1, u64 b0, u64 b1, const LimbParams &p, u64 &d0, u64 &d1, u64 &d2) {
     d0 = mulmod_lazy(a0, b0, p);
     d2 = mulmod_lazy(a1, b1, p);
@@ -143,21 +158,22 @@ DPFHE_HD void tensor_coeff(u64 a0, u64 a1, u64 b0, u64 b1, const LimbParams &p, 
 
 // ---- fused key-switch family ------------------------------------------
 // One work item = (ciphertext ct, output limb i).  Shared memory holds only the swizzled transform
-// buffer buf[N]; the two lazy accumulators live in the OUTPUT rows out[ct][0|1][i] themselves
-// (L2-resident read-modify-write by the owning thread, values kept below 16q), which keeps the CTA at
-// one limb of shared memory so that three CTAs share an SM and hide each other's memory phases.
+// buffer buf[N]; the two lazy accumulators live in two scratch rows owned by the CTA's slot (acc_rows:
+// L2-resident read-modify-write by the owning thread, values kept below 16q), which keeps the CTA at
+// one limb of shared memory so that three CTAs share an SM and hide each other's memory phases.  The
+// output rows out[ct][0|1][i] are written exactly once, with the final canonical values — so `out` may
+// be memory of another GPU (peer-mapped: the result gather of a multi-GPU job rides on these stores).
 //   phase 1: build the digit d = d2[i] (tensor / input / permuted c1), write
 //            acc = (own terms) + d o key[i][.][i], INTT(d) -> t_i, publish t_i to the slot.
 //   phase 2: for every other digit j: u = NTT_i(t_j mod q_i); acc += u o key[j][.][i];
-//            the last digit writes canon(acc).
-enum KsMode { KS_MUL_RELIN = 0, KS_PLAIN = 1, KS_ROTATE = 2 };
-
+//            the last digit writes canon(acc) to the output rows.
 struct KsArgs {
     const u64 *a;        // MUL_RELIN: a [batch][2][L][N]; PLAIN: d [batch][L][N]; ROTATE: ct [batch][2][L][N]
     const u64 *b;        // MUL_RELIN: b
     const u64 *key;      // [L][2][L][N]
     const u64 *key_s;    // Shoup companions floor(key * 2^64 / q_limb), same layout (built per launch)
-    u64 *out;            // [batch][2][L][N]
+    u64 *out;            // [batch][2][L][N]: written once, final values (may be peer memory)
+    u64 *acc;            // [slots][acc_par][2][N] lazy accumulators of the resident work items
     u64 *scratch;        // [slots][2 parities][N]
     const Twiddle *tw;   // [L][N] forward tables
     const Twiddle *itw;  // [L][N] inverse tables
@@ -166,9 +182,9 @@ struct KsArgs {
     u32 Lk;              // limbs of a key polynomial: L, or L + 1 with a special prime (hybrid)
     u64 *hyb;            // hybrid only: [groups][KS_HYB_ROWS][N]: special-limb accumulators (rows 0,1) and tau'
     const u32 *only;     // optional [batch]: process only the ciphertexts whose entry is non-zero (hoisted-rotation fallback)
+    u32 acc_par;         // accumulator row pairs per slot: 1, or 2 in hybrid key switching (the division step runs one round late)
 };
-// tau' rows of a hybrid group are double-buffered by round parity (the division step runs one round late)
-constexpr int KS_HYB_ROWS = 6;
+// tau' rows of a hybrid group are double-buffered by round parity (KS_HYB_ROWS, types.hpp)
 DPFHE_HD u32 ks_hyb_tau_row(u32 parity, u32 c) { return 2u + 2u * parity + c; }
 
 // operands of one 16-byte chunk position of phase 1, fetched one iteration ahead of their use
@@ -213,9 +229,9 @@ DPFHE_HD KsP1Operands ks_p1_fetch(const KsP1Pointers &ptr, u32 galois, int c) {
 // HYB: the own terms are scaled by the special prime (pm = p_special mod q_i), so that the final division by it
 // leaves them unchanged: out = ((p*d + sum) - s*u) / p.
 template <int MODE, bool HYB = false>
-DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only, u64 *buf, U64x2 *acc0, U64x2 *acc1, int c, int c_buf,
-                          u64 pm = 0, u64 pm_s = 0) {
-    U64x2 d, s0, s1;   // digit, own contributions to acc0 / acc1 (lazy < 3q)
+DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only, u64 *buf, U64x2 *acc0, U64x2 *acc1, U64x2 *out0, U64x2 *out1,
+                          int c, int c_buf, u64 pm = 0, u64 pm_s = 0) {
+    U64x2 d, s0, s1;   // digit (< SB*q), own contributions to acc0 (< SB*q) / acc1 (< (SB+1) q)
     if (MODE == KS_MUL_RELIN) {
         tensor_coeff(o.a0.x, o.a1.x, o.b0.x, o.b1.x, p, s0.x, s1.x, d.x);
         tensor_coeff(o.a0.y, o.a1.y, o.b0.y, o.b1.y, p, s0.y, s1.y, d.y);
@@ -235,28 +251,33 @@ DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only,
             s1.y = shoup_lazy(s1.y, pm, pm_s, p);
         }
     }
-    // digit enters the inverse transform in [0,2q)
+    // digit enters the inverse transform below SB*q (tensor) or canonical
     reinterpret_cast<U64x2 *>(buf)[swz_chunk(c_buf)] = d;
-    U64x2 r0, r1;   // s < 3q, Shoup term < 2q  ->  accumulator starts below 5q
+    U64x2 r0, r1;   // s < (SB+1) q (< SB*q after the hybrid scaling), Shoup term < SB*q  ->  accumulator starts below (2 SB + 1) q
     r0.x = s0.x + shoup_lazy(d.x, o.kb.x, o.kbs.x, p);
     r0.y = s0.y + shoup_lazy(d.y, o.kb.y, o.kbs.y, p);
     r1.x = s1.x + shoup_lazy(d.x, o.ka.x, o.kas.x, p);
     r1.y = s1.y + shoup_lazy(d.y, o.ka.y, o.kas.y, p);
-    if (only) {
+    if (only) {   // a single digit: this is already the result
         r0.x = canon(r0.x, p); r0.y = canon(r0.y, p);
         r1.x = canon(r1.x, p); r1.y = canon(r1.y, p);
+        st_stream(out0 + c, r0);
+        st_stream(out1 + c, r1);
+    } else {
+        st_cg(acc0 + c, r0);
+        st_cg(acc1 + c, r1);
     }
-    st_cg(acc0 + c, r0);
-    st_cg(acc1 + c, r1);
 }
 
 template <int LOGN, int NT, int MODE, bool HYB = false, class CTA>
-DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot, u64 pm = 0, u64 pm_s = 0) {
+DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot, u64 *acc_rows, u64 pm = 0,
+                        u64 pm_s = 0) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     static_assert((NC / NT) % 2 == 0, "chunk loops may be unrolled by two (ping-pong operand buffers)");
     const size_t P = (size_t)A.L * N, PK = HYB ? (size_t)A.Lk * N : P;
-    U64x2 *acc0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N);
-    U64x2 *acc1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
+    U64x2 *acc0 = reinterpret_cast<U64x2 *>(acc_rows), *acc1 = reinterpret_cast<U64x2 *>(acc_rows + N);
+    U64x2 *out0 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + (size_t)i * N);
+    U64x2 *out1 = reinterpret_cast<U64x2 *>(A.out + ct * 2 * P + P + (size_t)i * N);
     const bool only = !HYB && A.L == 1;   // a single digit: no phase 2, write the canonical result here
     KsP1Pointers ptr;
     {
@@ -283,7 +304,7 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
 #pragma unroll 1
                 for (int lc = tid; lc < n_c; lc += NT) {
                     const KsP1Operands o = ks_p1_fetch<LOGN, MODE>(ptr, galois, c_lo + lc);
-                    ks_p1_chunk<MODE, HYB>(o, p, only, buf, acc0, acc1, c_lo + lc, lc, pm, pm_s);
+                    ks_p1_chunk<MODE, HYB>(o, p, only, buf, acc0, acc1, out0, out1, c_lo + lc, lc, pm, pm_s);
                 }
             } else {
                 // rotate / key switch: the gathered operands have long latency and are few: fetch one chunk ahead
@@ -292,7 +313,7 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
                 for (int lc = tid; lc < n_c; lc += NT) {
                     const KsP1Operands o = nxt;
                     if (lc + NT < n_c) nxt = ks_p1_fetch<LOGN, MODE>(ptr, galois, c_lo + lc + NT);
-                    ks_p1_chunk<MODE, HYB>(o, p, only, buf, acc0, acc1, c_lo + lc, lc, pm, pm_s);
+                    ks_p1_chunk<MODE, HYB>(o, p, only, buf, acc0, acc1, out0, out1, c_lo + lc, lc, pm, pm_s);
                 }
             }
         });
@@ -334,11 +355,11 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
 
 // t_src: the published t of digit j (N words, natural order, canonical mod q_j)
 // HYB: key polynomials carry A.Lk limbs and nothing is final here (the division by the special prime follows).
-// SPECIAL (hybrid only): limb i = A.L is the special prime; jj = 0 .. L-1 counts its digits and its accumulators
-// are the two scratch rows acc_rows[0..N), acc_rows[N..2N), which start from zero.
+// acc_rows: the two accumulator rows of this work item, acc_rows[0..N) and acc_rows[N..2N).
+// SPECIAL (hybrid only): limb i = A.L is the special prime; jj = 0 .. L-1 counts its digits and its accumulators start from zero.
 template <int LOGN, int NT, bool HYB = false, bool SPECIAL = false, class CTA>
 DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u32 j, u32 jj, const u64 *t_src,
-                              u64 *acc_rows = nullptr) {
+                              u64 *acc_rows) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     static_assert(HYB || !SPECIAL, "the special limb exists only in hybrid key switching");
     const size_t P = (size_t)A.L * N, PK = HYB ? (size_t)A.Lk * N : P;
@@ -347,11 +368,14 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
     const size_t koff_b = ((size_t)j * 2 + 0) * PK + (size_t)i * N, koff_a = ((size_t)j * 2 + 1) * PK + (size_t)i * N;
     const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + koff_b), *ka = reinterpret_cast<const U64x2 *>(A.key + koff_a);
     const U64x2 *kbs = reinterpret_cast<const U64x2 *>(A.key_s + koff_b), *kas = reinterpret_cast<const U64x2 *>(A.key_s + koff_a);
-    U64x2 *acc0 = reinterpret_cast<U64x2 *>(SPECIAL ? acc_rows : A.out + ct * 2 * P + (size_t)i * N);
-    U64x2 *acc1 = reinterpret_cast<U64x2 *>(SPECIAL ? acc_rows + N : A.out + ct * 2 * P + P + (size_t)i * N);
-    // lazy accumulator bound: < 5q after phase 1 (0 for the special limb), +2q per digit; every 4th digit one
-    // csub(8q) keeps it <= 16q
-    const bool trim = SPECIAL ? ((jj + 1) & 3u) == 0u : (jj & 3u) == 0u, last = !HYB && jj + 1 == A.L;
+    U64x2 *acc0 = reinterpret_cast<U64x2 *>(acc_rows), *acc1 = reinterpret_cast<U64x2 *>(acc_rows + N);
+    // the output rows, written once by the last digit (unused in hybrid key switching: the division step writes them)
+    U64x2 *out0 = reinterpret_cast<U64x2 *>(HYB ? acc_rows : A.out + ct * 2 * P + (size_t)i * N);
+    U64x2 *out1 = reinterpret_cast<U64x2 *>(HYB ? acc_rows + N : A.out + ct * 2 * P + P + (size_t)i * N);
+    // lazy accumulator bound: below (2 SB + 1) q after phase 1 (0 for the special limb), + SB*q per digit; trimmed
+    // with one csub(8q) whenever the next digit could pass 16q
+    constexpr int B0 = 2 * SB + 1;
+    const bool trim = SPECIAL ? acc_trim_after(0, (int)jj) : acc_trim_after(B0, (int)jj - 1), last = !HYB && jj + 1 == A.L;
     const bool first = SPECIAL && jj == 0;
     struct MacOperands {
         U64x2 vb, va, vbs, vas, r0, r1;
@@ -385,8 +409,8 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
         if (last) {
             m.r0.x = canon(m.r0.x, p); m.r0.y = canon(m.r0.y, p);
             m.r1.x = canon(m.r1.x, p); m.r1.y = canon(m.r1.y, p);
-            st_stream(acc0 + c, m.r0);
-            st_stream(acc1 + c, m.r1);
+            st_stream(out0 + c, m.r0);
+            st_stream(out1 + c, m.r1);
         } else {
             st_cg(acc0 + c, m.r0);
             st_cg(acc1 + c, m.r1);
@@ -451,8 +475,8 @@ DPFHE_HD void ms_tau_body(CTA &cta, u64 *buf, const u64 *row, u64 *work, const T
     auto emit = [&](int c, const U64x2 &v) {
         U64x2 r = v;
         if (has_t) {
-            r.x = csub(shoup_lazy(v.x, K.tinv, K.tinv_s, p), p.q);
-            r.y = csub(shoup_lazy(v.y, K.tinv, K.tinv_s, p), p.q);
+            r.x = csub(shoup_exact(v.x, K.tinv, K.tinv_s, p), p.q);
+            r.y = csub(shoup_exact(v.y, K.tinv, K.tinv_s, p), p.q);
         }
         st_cg(dst + c, r);
     };
@@ -500,8 +524,8 @@ DPFHE_HD void ms_limb_body(CTA &cta, u64 *buf, const u64 *tau, const u64 *c_limb
     auto finish = [&](int c, int c_buf) {
         const U64x2 u = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c_buf)], cv = COHERENT ? ld_cg(cin + c) : ld_stream(cin + c);
         U64x2 r;   // c*inv - u*(s*inv): both Shoup products below 2q, difference kept positive with + 2q
-        r.x = canon4(shoup_lazy(cv.x, inv, inv_s, p) + p.q2 - shoup_lazy(u.x, sinv, sinv_s, p), p);
-        r.y = canon4(shoup_lazy(cv.y, inv, inv_s, p) + p.q2 - shoup_lazy(u.y, sinv, sinv_s, p), p);
+        r.x = canon4(shoup_exact(cv.x, inv, inv_s, p) + p.q2 - shoup_exact(u.x, sinv, sinv_s, p), p);
+        r.y = canon4(shoup_exact(cv.y, inv, inv_s, p) + p.q2 - shoup_exact(u.y, sinv, sinv_s, p), p);
         st_stream(dst + c, r);
     };
     if constexpr (LOGN <= 13 || NT >= 512) {
@@ -666,7 +690,7 @@ DPFHE_HD void rot_apply_rows(CTA &cta, const RotApplyArgs &A, const LimbParams &
                     r0[b].y += shoup_lazy(o.u[b].y, o.vb.y, o.vbs.y, p);
                     r1[b].x += shoup_lazy(o.u[b].x, o.va.x, o.vas.x, p);
                     r1[b].y += shoup_lazy(o.u[b].y, o.va.y, o.vas.y, p);
-                    if (trim) {   // + 2q per digit from below 2q: one csub(8q) every fourth digit keeps the sums below 16q
+                    if (trim) {   // + SB*q per digit from below 2q: csub(8q) whenever the next digit could pass 16q
                         r0[b].x = csub(r0[b].x, p.q8); r0[b].y = csub(r0[b].y, p.q8);
                         r1[b].x = csub(r1[b].x, p.q8); r1[b].y = csub(r1[b].y, p.q8);
                     }
@@ -687,11 +711,11 @@ DPFHE_HD void rot_apply_rows(CTA &cta, const RotApplyArgs &A, const LimbParams &
             }
             for (u32 j = 0; j < L; j += 2) {
                 if (PF && j + 1 < L) fetch(j + 1, ob);
-                mac(oa, false);
+                mac(oa, acc_trim_after(2, (int)j));
                 if (j + 1 < L) {
                     if (!PF) fetch(j + 1, ob);
                     if (PF && j + 2 < L) fetch(j + 2, oa);
-                    mac(ob, (j & 2u) != 0u);   // digits 3, 7, 11, 15
+                    mac(ob, acc_trim_after(2, (int)j + 1));
                     if (!PF && j + 2 < L) fetch(j + 2, oa);
                 }
             }
@@ -871,4 +895,5 @@ DPFHE_HD void pt_inner_tile(CTA &cta, u64 *smem, const PtInnerArgs &A, const Lim
     }
 }
 
+}  // namespace DPFHE_VNS
 }  // namespace dpfhe

@@ -8,10 +8,14 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "kernel_bodies.cuh"
 #include "launch.hpp"
 
+// compiled twice: -DDPFHE_FAST=0 -> namespace dpfhe::gen, -DDPFHE_FAST=1 -> namespace dpfhe::fast (types.hpp)
 namespace dpfhe {
+namespace DPFHE_VNS {
 
 // barrier scopes of the CTA policy (ntt_core.cuh): CTA, 256-thread domain, warp.
 // PROF: thread 0 accumulates clock64() deltas per phase id into prof[blockIdx][id] (diagnostics only).
@@ -179,7 +183,8 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
             }
         }
         const u32 parity = (FILTER ? executed++ : round) & 1u;
-        ks_phase1<LOGN, NT, MODE>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N);
+        u64 *acc_rows = A.acc + (size_t)slot * 2 * N;   // this CTA's two lazy accumulator rows (L2 resident, reused every round)
+        ks_phase1<LOGN, NT, MODE>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N, acc_rows);
         if (L > 1) {
             __threadfence();
             __syncthreads();
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
                 }
                 __syncthreads();
                 cta.mark(3);   // waiting for the sibling's digit
-                ks_phase2_digit<LOGN, NT>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)sib * 2 + parity) * N);
+                ks_phase2_digit<LOGN, NT>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)sib * 2 + parity) * N, acc_rows);
             }
         }
     }
@@ -330,12 +335,13 @@ __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __g
         if (threadIdx.x == 0) st_release_u32(flags + slot, tag);
     };
     // the postponed division of one ciphertext (limb CTAs): needs tau' of that round
+    auto acc_of = [&](u32 parity) { return A.acc + ((size_t)slot * 2 + parity) * 2 * N; };   // accumulator rows, double-buffered by round parity
     auto divide = [&](size_t ct, u32 tag, u32 parity) {
         wait_for(base + L, tag);
         const size_t P = (size_t)L * N;
         for (u32 c = 0; c < 2; ++c) {
-            u64 *row = A.out + ct * 2 * P + c * P + (size_t)i * N;   // lazy accumulator -> final value, in place
-            ms_limb_body<LOGN, NT, true>(cta, buf, hyb + ks_hyb_tau_row(parity, c) * N, row, row, A.tw + (size_t)i * N, p, K, i);
+            u64 *row = A.out + ct * 2 * P + c * P + (size_t)i * N;   // lazy accumulator -> final value in the output row
+            ms_limb_body<LOGN, NT, true>(cta, buf, hyb + ks_hyb_tau_row(parity, c) * N, acc_of(parity) + c * N, row, A.tw + (size_t)i * N, p, K, i);
         }
     };
     bool pending = false;
@@ -360,12 +366,12 @@ __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __g
         const size_t ct = s_ct;
         if (ct >= batch) break;
         if (!special) {
-            ks_phase1<LOGN, NT, MODE, true>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N, K.qlm[i], K.qlm_s[i]);
+            ks_phase1<LOGN, NT, MODE, true>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N, acc_of(parity), K.qlm[i], K.qlm_s[i]);
             publish(tag);
             for (u32 jj = 1; jj < L; ++jj) {
                 const u32 j = (i + jj) % L;
                 wait_for(base + j, tag);
-                ks_phase2_digit<LOGN, NT, true, false>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)(base + j) * 2 + parity) * N);
+                ks_phase2_digit<LOGN, NT, true, false>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)(base + j) * 2 + parity) * N, acc_of(parity));
             }
             if (pending) divide(prev_ct, prev_tag, prev_parity);
             pending = true;
@@ -511,6 +517,14 @@ struct Geometry {
     static constexpr size_t LIMB_BYTES = (size_t)8 << LOGN;
 };
 
+// "already configured on this device" bits of one kernel (a function-local static per launcher instantiation).  Several
+// host threads may drive different devices at once (dpfhe_multi_*): the attribute call is idempotent, the bit set atomic.
+struct ConfiguredMask {
+    std::atomic<unsigned long long> bits{0};
+    bool has(int device) const { return (bits.load(std::memory_order_acquire) >> (device & 63)) & 1ull; }
+    void set(int device) { bits.fetch_or(1ull << (device & 63), std::memory_order_release); }
+};
+
 static unsigned ew_grid(const LaunchCtx &lc, size_t work_items) {
     size_t blocks = (work_items + 255) / 256;
     const size_t cap = (size_t)lc.num_sms * 32;   // 8 resident CTAs of 256 threads per SM, 4 waves
@@ -518,21 +532,15 @@ static unsigned ew_grid(const LaunchCtx &lc, size_t work_items) {
     return (unsigned)(blocks ? blocks : 1);
 }
 
-static int g_num_sms(int dev) {
-    int n = 0;
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-}
-
 template <int LOGN, int NT, int MINB, bool INV>
 static cudaError_t launch_ntt_t(const LaunchCtx &lc, u64 *data, size_t n_limbs, cudaStream_t st) {
     auto kern = ntt_kernel<LOGN, NT, MINB, INV>;
     const size_t smem = Geometry<LOGN>::LIMB_BYTES;
-    static bool configured[64] = {};
-    if (!configured[lc.device & 63]) {
+    static ConfiguredMask configured;
+    if (!configured.has(lc.device)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[lc.device & 63] = true;
+        configured.set(lc.device);
     }
     // one CTA per limb transform; the grid-stride loop only matters beyond 2^31-1 limbs
     const size_t grid = n_limbs < 0x7fffffffull ? n_limbs : 0x7fffffffull;
@@ -567,12 +575,12 @@ static cudaError_t launch_ms_t(const LaunchCtx &lc, const u64 *in, u64 *tau, u64
     auto k1 = ms_tau_kernel<LOGN, NT, MINB>;
     auto k2 = ms_limb_kernel<LOGN, NT, MINB>;
     const size_t smem = Geometry<LOGN>::LIMB_BYTES;
-    static bool configured[64] = {};
-    if (!configured[lc.device & 63]) {
+    static ConfiguredMask configured;
+    if (!configured.has(lc.device)) {
         cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[lc.device & 63] = true;
+        configured.set(lc.device);
     }
     const size_t n_items = n_polys * (lc.L - 1);
     k1<<<(unsigned)(n_polys < 0x7fffffffull ? n_polys : 0x7fffffffull), NT, smem, st>>>(in, tau, lc.itw, lc.lt, K, lc.L, n_polys);
@@ -601,12 +609,12 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
     auto kern = lc.ks_prof ? ks_fused_kernel<LOGN, NT, MINB, MODE, true> : ks_fused_kernel<LOGN, NT, MINB, MODE, false>;
     if (filter) kern = ks_fused_kernel<LOGN, NT, MINB, MODE == KS_ROTATE ? MODE : KS_ROTATE, false, MODE == KS_ROTATE>;
     const size_t smem = LOGN <= 13 ? Geometry<LOGN>::LIMB_BYTES : Geometry<13>::LIMB_BYTES;
-    static bool configured[3][64] = {};
+    static ConfiguredMask configured[3];
     const int variant = filter ? 2 : (lc.ks_prof ? 1 : 0);
-    if (!configured[variant][lc.device & 63]) {
+    if (!configured[variant].has(lc.device)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[variant][lc.device & 63] = true;
+        configured[variant].set(lc.device);
     }
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
@@ -643,11 +651,11 @@ static cudaError_t launch_ks_hybrid_t(LaunchCtx &lc, const KsArgs &A, const MsCo
     constexpr int NT = 256, MINB = 3;
     auto kern = ks_hybrid_kernel<LOGN, NT, MINB, MODE>;
     const size_t smem = LOGN <= 13 ? Geometry<LOGN>::LIMB_BYTES : Geometry<13>::LIMB_BYTES;
-    static bool configured[64] = {};
-    if (!configured[lc.device & 63]) {
+    static ConfiguredMask configured;
+    if (!configured.has(lc.device)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[lc.device & 63] = true;
+        configured.set(lc.device);
     }
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
@@ -677,11 +685,12 @@ static cudaError_t launch_ks_hybrid_t(LaunchCtx &lc, const KsArgs &A, const MsCo
     return e;
 }
 
-// data has L-1 limbs, the key [L-1][2][L][N]; lc.ks_hyb must hold (ks_slots / 2 + 1) * KS_HYB_ROWS * N words
+// data has L-1 limbs, the key [L-1][2][L][N]; lc.ks_hyb must hold (ks_slots / 2 + 1) * KS_HYB_ROWS * N words and
+// lc.ks_acc_hyb ks_slots * 2 * 2 * N words
 cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, u32 galois,
                              const MsConsts &K, cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
-    if (lc.L < 2 || !lc.ks_hyb) return cudaErrorInvalidValue;
+    if (lc.L < 2 || !lc.ks_hyb || !lc.ks_acc_hyb) return cudaErrorInvalidValue;
     {
         const size_t n = (size_t)2 * (lc.L - 1) * lc.L << lc.log_n;
         const unsigned grid = ew_grid(lc, n);
@@ -694,6 +703,7 @@ cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
     A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L - 1; A.galois = galois; A.Lk = lc.L; A.hyb = lc.ks_hyb; A.only = nullptr;
+    A.acc = lc.ks_acc_hyb; A.acc_par = 2;
 #define KS_HYB_DISPATCH(LOGN)                                                                   \
     switch (mode) {                                                                             \
         case KS_MUL_RELIN: return launch_ks_hybrid_t<LOGN, KS_MUL_RELIN>(lc, A, K, batch, st);   \
@@ -724,11 +734,11 @@ template <int LOGN>
 static cudaError_t launch_pt_inner_t(const LaunchCtx &lc, const PtInnerArgs &A, u32 gmax, cudaStream_t st) {
     constexpr int NT = 256, MINB = 2;
     auto kern = pt_inner_kernel<LOGN, NT, MINB>;
-    static bool configured[64] = {};
-    if (!configured[lc.device & 63]) {
+    static ConfiguredMask configured;
+    if (!configured.has(lc.device)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PTI_SMEM_BUDGET);
         if (e != cudaSuccess) return e;
-        configured[lc.device & 63] = true;
+        configured.set(lc.device);
     }
     const size_t row = (size_t)A.nb * PTI_COEFFS * 8;
     const unsigned grid = (unsigned)(lc.L * (((size_t)1 << LOGN) / PTI_COEFFS));
@@ -764,11 +774,11 @@ static cudaError_t launch_hoist_t(LaunchCtx &lc, const HoistArgs &A, size_t batc
     constexpr int NT = 256, MINB = 3;
     auto kern = ks_hoist_kernel<LOGN, NT, MINB>;
     const size_t smem = LOGN <= 13 ? Geometry<LOGN>::LIMB_BYTES : Geometry<13>::LIMB_BYTES;
-    static bool configured[64] = {};
-    if (!configured[lc.device & 63]) {
+    static ConfiguredMask configured;
+    if (!configured.has(lc.device)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[lc.device & 63] = true;
+        configured.set(lc.device);
     }
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
@@ -879,6 +889,7 @@ cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
     A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L; A.galois = galois; A.Lk = lc.L; A.hyb = nullptr; A.only = only;
+    A.acc = lc.ks_acc; A.acc_par = 1;
 #define KS_DISPATCH(LOGN)                                                              \
     switch (mode) {                                                                    \
         case KS_MUL_RELIN: return launch_ks_t<LOGN, KS_MUL_RELIN>(lc, A, batch, st);   \
@@ -975,6 +986,5 @@ cudaError_t launch_fill_uniform(const LaunchCtx &lc, u64 seed, u64 first_poly, u
     return cudaGetLastError();
 }
 
-int query_num_sms(int dev) { return g_num_sms(dev); }
-
+}  // namespace DPFHE_VNS
 }  // namespace dpfhe

@@ -1,21 +1,18 @@
-// launch.hpp — interface between the C ABI (abi.cu) and the kernel launchers (kernels.cu).
+// launch.hpp — interface between the C ABI (abi.cu) and the kernel launchers (kernels.cu, compiled once per arithmetic
+// variant: namespace dpfhe::gen for any moduli, dpfhe::fast for moduli of the form k * 2^32 + 1; types.hpp).
 #pragma once
 #include <cuda_runtime.h>
 
-#include "kernel_bodies.cuh"
+#include "types.hpp"
 
 namespace dpfhe {
-
-// per-limb constants passed by value in the kernel parameter block
-struct LimbTable {
-    LimbParams lp[16];
-};
 
 // device-resident state shared by all launches of one context
 struct LaunchCtx {
     int device = 0;
     int num_sms = 0;
     u32 log_n = 0, L = 0;
+    bool fast = false;                // every modulus is k * 2^32 + 1: launches go to the dpfhe::fast kernels
     const LimbParams *lp = nullptr;   // [L] device copy (element-wise kernels)
     LimbTable lt;                     // host copy, passed by value to the transform kernels
     int rot_cfg = 0;                  // tuning variant of rot_apply_kernel (DPFHE_ROT_CFG)
@@ -24,6 +21,8 @@ struct LaunchCtx {
     const Twiddle *itw = nullptr;     // [L][N] inverse twiddles
     // fused key-switch pipeline
     u64 *ks_scratch = nullptr;        // [ks_slots][2][N] digit exchange buffers
+    u64 *ks_acc = nullptr;            // [ks_slots][2][N] lazy accumulator rows of the resident work items
+    u64 *ks_acc_hyb = nullptr;        // hybrid key switching: [ks_slots][2 parities][2][N], allocated at the first hybrid call
     u32 *ks_flags = nullptr;          // [ks_slots] monotonically increasing round counters
     u32 *ks_ticket = nullptr;         // next ciphertext index (reset per launch)
     u64 *ks_mail = nullptr;           // [ks_slots] per-group mailbox: (round tag << 32) | ciphertext index
@@ -36,25 +35,34 @@ struct LaunchCtx {
     unsigned long long *ks_prof = nullptr;   // [ks_slots][16] phase cycle counters; non-null selects the profiling build
 };
 
-int query_num_sms(int dev);
-cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inverse, cudaStream_t st);
-// only: optional [batch] filter (non-zero = process); key_ready: lc.ks_key_s already holds this key's Shoup companions
-cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch,
-                      u32 galois, cudaStream_t st, const u32 *only = nullptr, bool key_ready = false);
-cudaError_t launch_hoist(LaunchCtx &lc, const u64 *ct, u64 *U, u32 *zero, size_t batch, cudaStream_t st);
-cudaError_t launch_rot_prepare(LaunchCtx &lc, const u64 *key, u32 galois, const u64 *delta, u64 *M, u64 *kprime, cudaStream_t st);
-cudaError_t launch_rot_apply(const LaunchCtx &lc, const u64 *ct, const u64 *U, const u64 *key, const u64 *kprime, u32 galois, u64 *out,
-                             size_t batch, cudaStream_t st);
-cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, u32 galois,
-                             const MsConsts &K, cudaStream_t st);
-cudaError_t launch_pt_inner(const LaunchCtx &lc, const u64 *steps, u32 nb, const u64 *pts, u32 ng, u64 *out, size_t batch, cudaStream_t st,
-                            unsigned *launches);
-cudaError_t launch_pointwise_mul(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *out, size_t n_polys, cudaStream_t st);
-cudaError_t launch_mod_switch(const LaunchCtx &lc, const u64 *in, u64 *tau, u64 *out, const MsConsts &K, size_t n_polys, cudaStream_t st);
-cudaError_t launch_poly_add(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *out, size_t n_polys, cudaStream_t st);
-cudaError_t launch_ct_mul_plain(const LaunchCtx &lc, const u64 *ct, const u64 *pt, u64 *out, size_t batch, cudaStream_t st);
-cudaError_t launch_ct_mul_plain_acc(const LaunchCtx &lc, const u64 *ct, const u64 *pt, u64 *acc, size_t batch, cudaStream_t st);
-cudaError_t launch_ct_tensor(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *d, size_t batch, cudaStream_t st);
-cudaError_t launch_fill_uniform(const LaunchCtx &lc, u64 seed, u64 first_poly, u64 *data, size_t n_polys, cudaStream_t st);
+// the launchers, declared once per variant namespace
+#define DPFHE_DECLARE_LAUNCHERS \
+    cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inverse, cudaStream_t st); \
+    cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, \
+                          u32 galois, cudaStream_t st, const u32 *only = nullptr, bool key_ready = false); \
+    cudaError_t launch_hoist(LaunchCtx &lc, const u64 *ct, u64 *U, u32 *zero, size_t batch, cudaStream_t st); \
+    cudaError_t launch_rot_prepare(LaunchCtx &lc, const u64 *key, u32 galois, const u64 *delta, u64 *M, u64 *kprime, cudaStream_t st); \
+    cudaError_t launch_rot_apply(const LaunchCtx &lc, const u64 *ct, const u64 *U, const u64 *key, const u64 *kprime, u32 galois, u64 *out, \
+                                 size_t batch, cudaStream_t st); \
+    cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, u32 galois, \
+                                 const MsConsts &K, cudaStream_t st); \
+    cudaError_t launch_pt_inner(const LaunchCtx &lc, const u64 *steps, u32 nb, const u64 *pts, u32 ng, u64 *out, size_t batch, cudaStream_t st, \
+                                unsigned *launches); \
+    cudaError_t launch_pointwise_mul(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *out, size_t n_polys, cudaStream_t st); \
+    cudaError_t launch_mod_switch(const LaunchCtx &lc, const u64 *in, u64 *tau, u64 *out, const MsConsts &K, size_t n_polys, cudaStream_t st); \
+    cudaError_t launch_poly_add(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *out, size_t n_polys, cudaStream_t st); \
+    cudaError_t launch_ct_mul_plain(const LaunchCtx &lc, const u64 *ct, const u64 *pt, u64 *out, size_t batch, cudaStream_t st); \
+    cudaError_t launch_ct_mul_plain_acc(const LaunchCtx &lc, const u64 *ct, const u64 *pt, u64 *acc, size_t batch, cudaStream_t st); \
+    cudaError_t launch_ct_tensor(const LaunchCtx &lc, const u64 *a, const u64 *b, u64 *d, size_t batch, cudaStream_t st); \
+    cudaError_t launch_fill_uniform(const LaunchCtx &lc, u64 seed, u64 first_poly, u64 *data, size_t n_polys, cudaStream_t st);
+
+namespace gen {
+DPFHE_DECLARE_LAUNCHERS
+}
+namespace fast {
+DPFHE_DECLARE_LAUNCHERS
+}
+#undef DPFHE_DECLARE_LAUNCHERS
+// launch_ks: `only` = optional [batch] filter (non-zero = process); key_ready: lc.ks_key_s already holds this key's Shoup companions
 
 }  // namespace dpfhe

@@ -3,45 +3,24 @@
 // Everything is __host__ __device__ so the same code is exercised by the host emulator
 // in tests/emu (test infrastructure; never part of libdpfhe.so's product path).
 //
-// Lazy-range conventions ("bound B" means value < B*q; 16q < 2^64 because q < 2^60):
-//   shoup_lazy(x, w)      any 64-bit x        -> [0, 2q)
-//   word_reduce(x)        any 64-bit x        -> [0, 3q)   (3 integer multiplies)
-//   barrett_lazy(a*b)     a*b <= 4 q^2        -> [0, 3q)
+// The functions live in namespace dpfhe::gen or dpfhe::fast (types.hpp: DPFHE_FAST).  In the fast variant every
+// modulus is q = qh * 2^32 + 1, so k*q = k + ((k*qh) << 32): subtracting a multiple of q takes one 32-bit multiply-add
+// instead of one IMAD.WIDE and two IMAD.  What bounds these kernels is the integer multiplier (IMAD.WIDE issues at a
+// quarter of the rate of the other integer instructions on sm_100, profiles/r02), so both variants also use quotient
+// ESTIMATES that skip partial products (DPFHE_SHOUP_APPROX): the result stays congruent, only the lazy range widens.
+//
+// Lazy-range conventions ("bound B" means value < B*q; 16q < 2^64 because q < 2^60), SB = 4 (2 with exact quotients):
+//   shoup_lazy(x, w)      any 64-bit x        -> [0, SB*q)
+//   shoup_exact(x, w)     any 64-bit x        -> [0, 2q)
+//   word_reduce(x)        any 64-bit x        -> [0, 3q)
+//   barrett_lazy(a*b)     a*b <= 4 q^2        -> [0, (SB+1) q), [0, SB*q) for canonical factors
 //   barrett_lazy_long(z)  z < 2^(2b+4)        -> [0, 15q)  (b = bit length of q; sums of up to 16 products)
 //   canon(x)              x < 16q             -> [0, q)
 #pragma once
-#include <stdint.h>
-
-#if defined(__CUDACC__)
-#define DPFHE_HD __host__ __device__ __forceinline__
-#else
-#define DPFHE_HD inline
-#endif
+#include "types.hpp"
 
 namespace dpfhe {
-
-typedef uint64_t u64;
-typedef uint32_t u32;
-
-struct alignas(16) U64x2 {
-    u64 x, y;
-};
-
-// Per-limb constants (host-built in params.cpp, resident in device global memory).
-struct alignas(16) LimbParams {
-    u64 q;           // modulus
-    u64 q2;          // 2q
-    u64 q4;          // 4q
-    u64 q8;          // 8q  (< 2^63)
-    u64 nq;          // 2^64 - q: adding h*nq subtracts h*q without a separate negation
-    u64 bar_mu;      // floor(2^(bar_shift+64) / q)
-    u64 ninv;        // N^-1 mod q                    } folded into the last inverse stage
-    u64 ninv_s;      // Shoup companion of ninv
-    u64 wninv;       // psi^-bitrev(1) * N^-1 mod q
-    u64 wninv_s;     // Shoup companion of wninv
-    u32 bar_shift;   // bitlen(q) - 2
-    u32 mu32;        // floor(2^64 / q)  (< 2^31 because q > 2^33)
-};
+namespace DPFHE_VNS {
 
 DPFHE_HD u64 umulhi64(u64 a, u64 b) {
 #if defined(__CUDA_ARCH__)
@@ -54,6 +33,31 @@ DPFHE_HD u64 umulhi64(u64 a, u64 b) {
 DPFHE_HD u32 umulhi32(u32 a, u32 b) {
     // high half of a 32x32 wide multiply (IMAD.WIDE, not the much slower IMAD.HI)
     return (u32)(((u64)a * b) >> 32);
+}
+
+// 32 x 32 -> 64 product that stays one IMAD.WIDE: opaque to the optimiser, so that the sums built around it keep their shape
+DPFHE_HD u64 mul_wide(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    u64 r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    return (u64)a * b;
+#endif
+}
+
+// hi64(x * y) minus 0, 1 or 2.  Three IMAD.WIDE: the low partial product xl*yl only matters through a carry (<= 1) and
+// so does the sum of the low words of the two middle products (<= 1).  The 33-bit sum of the middle products' high
+// words is formed first (IADD3 + IADD3.X into a register pair) and enters the top product as its 64-bit addend.
+DPFHE_HD u64 mulhi_approx(u64 x, u64 y) {
+#if DPFHE_SHOUP_APPROX == 0
+    return umulhi64(x, y);
+#else
+    const u32 xl = (u32)x, xh = (u32)(x >> 32), yl = (u32)y, yh = (u32)(y >> 32);
+    const u64 a = mul_wide(xh, yl), b = mul_wide(xl, yh);
+    const u64 m = (u64)(u32)(a >> 32) + (u32)(b >> 32);
+    return (u64)xh * yh + m;
+#endif
 }
 
 // x >= m ? x - m : x, branch-free.  Correct for every 64-bit x when m <= 2^63.
@@ -95,15 +99,46 @@ DPFHE_HD u64 mad_lo64(u64 a, u64 b, u64 c) {
 #endif
 }
 
-// Shoup multiplication by a fixed w < q with ws = floor(w * 2^64 / q): valid for ANY 64-bit x.
-// r = x*w - floor(x*ws / 2^64) * q  (mod 2^64), r in [0, 2q).
-// Device form: the quotient uses ptxas' own mul.hi.u64 expansion (4 IMAD.WIDE with carry predicates); the
-// low 64 bits are one explicit chain t = xl*wl + hl*nql (2 IMAD.WIDE), t.hi += xl*wh + xh*wl + hl*nqh + hh*nql
-// (4 IMAD) with nq = 2^64 - q, which avoids the negation and the split adds nvcc otherwise emits.
-DPFHE_HD u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 q, u64 nq) {
+// x - k*q mod 2^64
+DPFHE_HD u64 sub_mul_q(u64 x, u64 k, const LimbParams &p) {
+#if DPFHE_FAST
+    return x - k + ((u64)((u32)k * p.nqh) << 32);   // k*q = k + ((k*qh) << 32)
+#else
+    return mad_lo64(k, p.nq, x);
+#endif
+}
+
+// One-word quotient estimate: k = floor(x_hi * mu32 / 2^32) <= floor(x/q), off by at most 2.
+DPFHE_HD u64 word_reduce(u64 x, const LimbParams &p) {
+    const u32 k = umulhi32((u32)(x >> 32), p.mu32);
+    return sub_mul_q(x, (u64)k, p);   // x - k*q, in [0, 3q)
+}
+
+// shoup_tail: low 64 bits of x*w - h*q.
+// gen:  one multiply-add chain t = xl*wl + hl*nql (2 IMAD.WIDE), t.hi += xl*wh + xh*wl + hl*nqh + hh*nql (4 IMAD) with
+//       nq = 2^64 - q, which avoids the negation and the split adds nvcc otherwise emits.
+// fast: the chain is xl*wl (1 IMAD.WIDE), t.hi += xl*wh + xh*wl + hl*(-qh) (3 IMAD), minus h.
+DPFHE_HD u64 shoup_tail(u64 x, u64 w, u64 h, const LimbParams &p) {
 #if defined(__CUDA_ARCH__)
-    const u64 h = __umul64hi(x, ws);
     u64 t;
+#if DPFHE_FAST
+    asm("{\n\t"
+        ".reg .u32 xl, xh, wl, wh, hl, hh, t0, t1;\n\t"
+        ".reg .u64 T;\n\t"
+        "mov.b64 {xl, xh}, %1;\n\t"
+        "mov.b64 {wl, wh}, %2;\n\t"
+        "mov.b64 {hl, hh}, %3;\n\t"
+        "mul.wide.u32 T, xl, wl;\n\t"
+        "mov.b64 {t0, t1}, T;\n\t"
+        "mad.lo.u32 t1, xl, wh, t1;\n\t"
+        "mad.lo.u32 t1, xh, wl, t1;\n\t"
+        "mad.lo.u32 t1, hl, %4, t1;\n\t"
+        "mov.b64 %0, {t0, t1};\n\t"
+        "}"
+        : "=l"(t)
+        : "l"(x), "l"(w), "l"(h), "r"(p.nqh));
+    return t - h;
+#else
     asm("{\n\t"
         ".reg .u32 xl, xh, wl, wh, hl, hh, nl, nh, t0, t1;\n\t"
         ".reg .u64 T;\n\t"
@@ -121,22 +156,20 @@ DPFHE_HD u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 q, u64 nq) {
         "mov.b64 %0, {t0, t1};\n\t"
         "}"
         : "=l"(t)
-        : "l"(x), "l"(w), "l"(h), "l"(nq));
-    (void)q;
+        : "l"(x), "l"(w), "l"(h), "l"(p.nq));
     return t;
+#endif
 #else
-    (void)nq;
-    u64 h = umulhi64(x, ws);
-    return x * w - h * q;   // in [0, 2q)
+    return x * w - h * p.q;
 #endif
 }
-// One-word quotient estimate: k = floor(x_hi * mu32 / 2^32) <= floor(x/q), off by at most 2.
-DPFHE_HD u64 word_reduce(u64 x, const LimbParams &p) {
-    u32 k = umulhi32((u32)(x >> 32), p.mu32);
-    return mad_lo64((u64)k, p.nq, x);   // x - k*q, in [0, 3q)
-}
 
-DPFHE_HD u64 shoup_lazy(u64 x, u64 w, u64 ws, const LimbParams &p) { return shoup_lazy(x, w, ws, p.q, p.nq); }
+// Shoup multiplication by a fixed w < q with ws = floor(w * 2^64 / q): valid for ANY 64-bit x.
+// r = x*w - h*q (mod 2^64) with h = floor(x*ws / 2^64) - e:  r in [0, (2 + e) q).
+//   shoup_exact: e = 0 (ptxas' own mul.hi.u64 expansion, 4 IMAD.WIDE with carry predicates), r in [0, 2q)
+//   shoup_lazy:  e <= 2 (mulhi_approx, 3 IMAD.WIDE), r in [0, SB*q)
+DPFHE_HD u64 shoup_exact(u64 x, u64 w, u64 ws, const LimbParams &p) { return shoup_tail(x, w, umulhi64(x, ws), p); }
+DPFHE_HD u64 shoup_lazy(u64 x, u64 w, u64 ws, const LimbParams &p) { return shoup_tail(x, w, mulhi_approx(x, ws), p); }
 
 // 128-bit product (hi:lo) of two 64-bit words.  Device: four IMAD.WIDE partial products combined once
 // (nvcc's separate a*b and __umul64hi(a,b) would recompute the low partial product: 5 IMAD.WIDE + 2 IMAD).
@@ -172,8 +205,8 @@ DPFHE_HD void mul128(u64 a, u64 b, u64 &hi, u64 &lo) {
 }
 
 // Barrett reduction of z = hi:lo.  Requires z < 2^(s+64), s = bitlen(q) - 2, i.e. z <= 4 q^2 (factor bounds Ba*Bb <= 4:
-// the shifted value must fit one word), gives [0, 3q).
-// With both factors < q the result is in [0, 2q).
+// the shifted value must fit one word).  With the exact quotient the result is in [0, 3q) ([0, 2q) for canonical
+// factors); the estimate of mulhi_approx adds at most 2q: [0, (SB+1) q) and [0, SB*q).
 DPFHE_HD u64 barrett_lazy(u64 hi, u64 lo, const LimbParams &p) {
     const u32 s = p.bar_shift;                       // 32 <= s <= 58 because 2^33 < q < 2^60
 #if defined(__CUDA_ARCH__)
@@ -184,13 +217,12 @@ DPFHE_HD u64 barrett_lazy(u64 hi, u64 lo, const LimbParams &p) {
 #else
     const u64 zt = (hi << (64 - s)) | (lo >> s);     // floor(z / 2^s) < 2^64
 #endif
-    u64 qh = umulhi64(zt, p.bar_mu);
-    return mad_lo64(qh, p.nq, lo);   // lo - qh*q
+    return sub_mul_q(lo, mulhi_approx(zt, p.bar_mu), p);   // lo - qhat*q
 }
 
 // Barrett reduction of a longer sum z = hi:lo < 2^(2b+4), b = bit length of q (e.g. 16 products of canonical factors):
 // the quotient is estimated from z / 2^(s+2) so that the shifted value still fits one word; 4*qh is within 14 of
-// floor(z/q), so the result is in [0, 15q) (and 15q < 2^64).
+// floor(z/q), so the result is in [0, 15q) (and 15q < 2^64).  Exact high product: once per 16 multiply-accumulates.
 DPFHE_HD u64 barrett_lazy_long(u64 hi, u64 lo, const LimbParams &p) {
     const u32 s = p.bar_shift + 2;                   // 34 <= s <= 60
 #if defined(__CUDA_ARCH__)
@@ -201,9 +233,10 @@ DPFHE_HD u64 barrett_lazy_long(u64 hi, u64 lo, const LimbParams &p) {
     const u64 zt = (hi << (64 - s)) | (lo >> s);     // floor(z / 2^s) < 2^64
 #endif
     const u64 qh = umulhi64(zt, p.bar_mu);
-    return mad_lo64(qh << 2, p.nq, lo);              // lo - 4*qh*q
+    return sub_mul_q(lo, qh << 2, p);                // lo - 4*qh*q
 }
 
+// product of two values whose bounds multiply to at most 4: [0, (SB+1) q); canonical factors: [0, SB*q)
 DPFHE_HD u64 mulmod_lazy(u64 a, u64 b, const LimbParams &p) {
     u64 hi, lo;
     mul128(a, b, hi, lo);
@@ -219,25 +252,8 @@ DPFHE_HD u64 canon(u64 x, const LimbParams &p) {
 // x < 4q -> [0, q)
 DPFHE_HD u64 canon4(u64 x, const LimbParams &p) { return csub(csub(x, p.q2), p.q); }
 
+// canonical factors -> canonical product
 DPFHE_HD u64 mulmod(u64 a, u64 b, const LimbParams &p) { return canon4(mulmod_lazy(a, b, p), p); }
 
-// Modulus switching / special-prime division: constants of one call, built on the host
-// (host_params.cpp:build_ms_consts) and passed by value in the kernel parameter block.
-struct MsConsts {
-    u64 inv[16], inv_s[16];     // q_last^-1 mod q_i and its Shoup companion
-    u64 sinv[16], sinv_s[16];   // s * q_last^-1 mod q_i (s = t_plain, or 1 for plain rounding)
-    u64 qlm[16], qlm_s[16];     // q_last mod q_i and its Shoup companion (hybrid key switching scales by it)
-    u64 tinv, tinv_s;           // t_plain^-1 mod q_last (BGV correction), used when has_t
-    u64 half;                   // floor(q_last / 2)
-    u32 has_t;
-};
-
-// splitmix64 finaliser, the synthetic-data hash of DESIGN.md §5
-DPFHE_HD u64 splitmix64(u64 x) {
-    u64 z = x + 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-
+}  // namespace DPFHE_VNS
 }  // namespace dpfhe

@@ -17,9 +17,7 @@
 #include "modarith.cuh"
 
 namespace dpfhe {
-
-// (w, floor(w*2^64/q)) pairs, 16 B each, so one 128-bit load fetches a twiddle.
-typedef U64x2 Twiddle;
+namespace DPFHE_VNS {
 
 // ---- shared-memory layout -------------------------------------------------------------
 // coefficient index -> u64 slot (TMA SWIZZLE_128B: chunk ^= row & 7)
@@ -27,46 +25,36 @@ DPFHE_HD int swz(int idx) { return idx ^ (((idx >> 4) & 7) << 1); }
 // 16-byte chunk index (two coefficients) -> chunk slot
 DPFHE_HD int swz_chunk(int cg) { return cg ^ ((cg >> 3) & 7); }
 
-// ---- twiddle table layout (must match params.cpp:tw_pos) --------------------------------
-// natural index of the twiddle of group i at stage s is 2^s + i.  Stages of the last
-// register pass (s >= LOGN-4) are stored transposed so that lane-consecutive rows read
-// consecutive table entries:  i = row * 2^u + j  ->  2^s + j * (N/16) + row,  u = s - (LOGN-4).
-template <int LOGN>
-DPFHE_HD int tw_pos(int s, int i) {
-    if (s < LOGN - 4) return (1 << s) + i;
-    const int u = s - (LOGN - 4);
-    const int row = i >> u, j = i & ((1 << u) - 1);
-    return (1 << s) + j * (1 << (LOGN - 4)) + row;
-}
+// twiddle table layout: tw_pos<LOGN>(stage, group) in types.hpp
 
 // ---- butterflies -----------------------------------------------------------------------
-// forward, fully lazy: x' = x + w*y, y' = x - w*y + 2q; bound grows by 2 per stage.
+// forward, fully lazy: x' = x + w*y, y' = x - w*y + SB*q; bound grows by SB per stage (SB*q: bound of shoup_lazy).
 DPFHE_HD void ct_bfly(u64 &x, u64 &y, const Twiddle &w, const LimbParams &p) {
     u64 t = shoup_lazy(y, w.x, w.y, p);
     u64 a = x;
     x = a + t;
-    y = a + p.q2 - t;
+    y = a + p.qsb - t;
 }
-// inverse, Harvey: inputs and outputs in [0, 2q)
+// inverse, Harvey: inputs and outputs in [0, SB*q)
 DPFHE_HD void gs_bfly(u64 &x, u64 &y, const Twiddle &w, const LimbParams &p) {
     u64 a = x, b = y;
-    x = csub(a + b, p.q2);
-    y = shoup_lazy(a + p.q2 - b, w.x, w.y, p);
+    x = csub(a + b, p.qsb);
+    y = shoup_lazy(a + p.qsb - b, w.x, w.y, p);
 }
 
 // ---- lazy-bound schedule of the forward transform ------------------------------------------
 // Values are tracked as "< B*q".  A forward stage maps X-inputs below B*q to outputs below
-// (B+2)*q (shoup_lazy yields < 2q for any 64-bit input).  16*q < 2^64, so when B + 2 would
+// (B+SB)*q (shoup_lazy yields < SB*q for any 64-bit input).  16*q < 2^64, so when B + SB would
 // exceed 16 the X inputs of that stage first take one conditional subtraction of 8q
 // (B <= 16 -> 8).  Everything is resolved at compile time from the bound at entry.
 DPFHE_HD constexpr bool fwd_needs_csub(int bin, int stage) {
     int b = bin;
-    for (int s = 0; s < stage; ++s) b = (b + 2 > 16 ? 8 : b) + 2;
-    return b + 2 > 16;
+    for (int s = 0; s < stage; ++s) b = (b + SB > 16 ? 8 : b) + SB;
+    return b + SB > 16;
 }
 DPFHE_HD constexpr int fwd_bound_after(int bin, int stages) {
     int b = bin;
-    for (int s = 0; s < stages; ++s) b = (b + 2 > 16 ? 8 : b) + 2;
+    for (int s = 0; s < stages; ++s) b = (b + SB > 16 ? 8 : b) + SB;
     return b;
 }
 
@@ -216,7 +204,7 @@ DPFHE_HD void fwd_load_stage(u64 *buf, const Twiddle *__restrict__ tw, const Lim
 #pragma unroll
             for (int b = 0; b < NB; ++b) nxt[b] = src(b * CPB + c + NT);
         }
-        // entry bound is 1 (canonical) or 3 (word-reduced); K <= 2 stages never need a csub
+        // entry bound is at most 4; K <= 2 stages never need a csub (static_assert in fwd_passes_blk)
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             const int half = NB >> (u + 1);
@@ -240,9 +228,9 @@ DPFHE_HD void fwd_load_stage(u64 *buf, const Twiddle *__restrict__ tw, const Lim
     }
 }
 
-// Inverse counterpart: SRC(chunk_index) yields the chunks left by the register passes (values in [0,2q));
+// Inverse counterpart: SRC(chunk_index) yields the chunks left by the register passes (values in [0,SB*q));
 // applies the K outermost Gentleman-Sande stages with N^-1 folded into the very last one, and hands
-// canonical chunks to DST(chunk_index, U64x2).
+// canonical chunks to DST(chunk_index, U64x2) (the last stage uses the exact product so that one csub finishes).
 template <int LOGN, int NT, class SRC, class DST>
 DPFHE_HD void inv_outer_stage(const Twiddle *__restrict__ tw, const LimbParams &p, int tid, SRC src, DST dst) {
     constexpr int K = LOGN - 12;
@@ -277,13 +265,13 @@ DPFHE_HD void inv_outer_stage(const Twiddle *__restrict__ tw, const LimbParams &
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     u64 a = x[i][e], b = x[NB / 2 + i][e];
-                    x[i][e] = csub(shoup_lazy(a + b, p.ninv, p.ninv_s, p), p.q);
-                    x[NB / 2 + i][e] = csub(shoup_lazy(a + p.q2 - b, p.wninv, p.wninv_s, p), p.q);
+                    x[i][e] = csub(shoup_exact(a + b, p.ninv, p.ninv_s, p), p.q);
+                    x[NB / 2 + i][e] = csub(shoup_exact(a + p.qsb - b, p.wninv, p.wninv_s, p), p.q);
                 }
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) x[0][e] = csub(shoup_lazy(x[0][e], p.ninv, p.ninv_s, p), p.q);
+            for (int e = 0; e < 2; ++e) x[0][e] = csub(shoup_exact(x[0][e], p.ninv, p.ninv_s, p), p.q);
         }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -322,12 +310,12 @@ DPFHE_HD void fwd_load_stage_half(u64 *buf, const Twiddle *__restrict__ tw, cons
         for (int e = 0; e < 2; ++e) {
             // stage 0 pairs (0,2) and (1,3); half 0 keeps the sums, half 1 the differences
             const u64 t02 = shoup_lazy(x[2][e], w0.x, w0.y, p), t13 = shoup_lazy(x[3][e], w0.x, w0.y, p);
-            const u64 a = h == 0 ? x[0][e] + t02 : x[0][e] + p.q2 - t02;
-            const u64 b = h == 0 ? x[1][e] + t13 : x[1][e] + p.q2 - t13;
+            const u64 a = h == 0 ? x[0][e] + t02 : x[0][e] + p.qsb - t02;
+            const u64 b = h == 0 ? x[1][e] + t13 : x[1][e] + p.qsb - t13;
             // stage 1 pairs (2h, 2h+1) with the twiddle of group h
             const u64 t = shoup_lazy(b, w1.x, w1.y, p);
             (e == 0 ? o0.x : o0.y) = a + t;
-            (e == 0 ? o1.x : o1.y) = a + p.q2 - t;
+            (e == 0 ? o1.x : o1.y) = a + p.qsb - t;
         }
         reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = o0;
         reinterpret_cast<U64x2 *>(buf)[swz_chunk(CPB + c)] = o1;
@@ -354,7 +342,7 @@ template <int LOGN, int NT, int BIN, int BLKS, class CTA>
 DPFHE_HD void fwd_passes_blk(CTA &cta, u64 *buf, const Twiddle *tw, const LimbParams &p, int blk0) {
     constexpr int K = LOGN - 12;
     constexpr int B0 = fwd_bound_after(BIN, K), B1 = fwd_bound_after(BIN, K + 4), B2 = fwd_bound_after(BIN, K + 8);
-    static_assert(BIN + 2 * K <= 16, "load stage applies no conditional subtraction");
+    static_assert(BIN + SB * K <= 16, "load stage applies no conditional subtraction");
     static_assert(NT % 32 == 0 && (NT >= 256 ? NT % 256 == 0 : true), "thread count must tile the barrier domains");
     static_assert(BLKS == (1 << K) || NT <= 256, "partial-limb buffers use whole-CTA barriers");
     cta.par_dom([&](int tid) { fwd_pass<LOGN, K, NT, B0, BLKS>(buf, tw, p, tid, blk0); });
@@ -365,7 +353,7 @@ template <int LOGN, int NT, int BIN, class CTA>
 DPFHE_HD void fwd_passes(CTA &cta, u64 *buf, const Twiddle *tw, const LimbParams &p) {
     fwd_passes_blk<LOGN, NT, BIN, (1 << (LOGN - 12))>(cta, buf, tw, p, 0);
 }
-// inverse: buf holds [0,2q) values in bit-reversed order; afterwards run inv_store_stage / inv_outer_stage
+// inverse: buf holds [0,SB*q) values in bit-reversed order; afterwards run inv_store_stage / inv_outer_stage
 template <int LOGN, int NT, int BLKS, class CTA>
 DPFHE_HD void inv_passes_blk(CTA &cta, u64 *buf, const Twiddle *itw, const LimbParams &p, int blk0) {
     constexpr int K = LOGN - 12;
@@ -379,4 +367,5 @@ DPFHE_HD void inv_passes(CTA &cta, u64 *buf, const Twiddle *itw, const LimbParam
     inv_passes_blk<LOGN, NT, (1 << (LOGN - 12))>(cta, buf, itw, p, 0);
 }
 
+}  // namespace DPFHE_VNS
 }  // namespace dpfhe

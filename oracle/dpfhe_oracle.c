@@ -154,11 +154,11 @@ dpo_ctx *dpo_create(unsigned logn, unsigned L, const uint64_t *moduli) {
             c->q[l] = q;
         }
     } else {
-        /* the L largest primes below 2^60 with q = 1 mod 2N, descending */
-        uint64_t cand = (((uint64_t)1 << 60) / two_n) * two_n + 1;
+        /* the L largest primes below 2^60 of the form k * 2^32 + 1 (hence 1 mod 2N), descending */
+        uint64_t cand = ((uint64_t)1 << 60) + 1;
         unsigned found = 0;
         while (found < L) {
-            cand -= two_n;
+            cand -= (uint64_t)1 << 32;
             if (dpo_is_prime(cand)) c->q[found++] = cand;
         }
     }

@@ -114,17 +114,17 @@ class Emu:
         return int(getattr(self._l, "emu_" + name)(self._h, l, *[C.c_uint64(int(a)) for a in args]))
 
 
-@pytest.fixture(scope="session")
-def emu_lib():
+def _build_emu(variant):
+    """tests/_emu/libdpfhe_emu_<variant>.so: the kernel bodies of one arithmetic variant (csrc/types.hpp) compiled for the host"""
     out_dir = os.path.join(ROOT, "tests", "_emu")
     os.makedirs(out_dir, exist_ok=True)
-    so = os.path.join(out_dir, "libdpfhe_emu.so")
+    so = os.path.join(out_dir, "libdpfhe_emu_%s.so" % variant)
     csrc = os.path.join(ROOT, "deeppowers_b200", "csrc")
     srcs = [os.path.join(ROOT, "tests", "emu", "emu.cpp"), os.path.join(csrc, "host_params.cpp")]
-    deps = srcs + [os.path.join(csrc, f) for f in ("modarith.cuh", "ntt_core.cuh", "kernel_bodies.cuh", "host_params.hpp")]
+    deps = srcs + [os.path.join(csrc, f) for f in ("types.hpp", "modarith.cuh", "ntt_core.cuh", "kernel_bodies.cuh", "host_params.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        subprocess.check_call([gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-I", csrc] + srcs + ["-o", so])
+        subprocess.check_call([gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DDPFHE_FAST=%d" % (variant == "fast"), "-x", "c++", "-I", csrc] + srcs + ["-o", so])
     lib = C.CDLL(so)
     lib.emu_create.restype = C.c_void_p
     lib.emu_create.argtypes = [C.c_uint, C.c_uint, C.c_void_p]
@@ -140,7 +140,8 @@ def emu_lib():
     lib.emu_rotate_hoisted.argtypes = [C.c_void_p, _u64p, C.c_size_t, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint, C.POINTER(C.c_uint)]
     lib.emu_pt_inner.argtypes = [C.c_void_p, _u64p, C.c_uint, _u64p, C.c_uint, _u64p, C.c_size_t, C.c_uint]
     lib.emu_mod_switch.argtypes = [C.c_void_p, _u64p, _u64p, C.c_size_t, C.c_uint64]
-    for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2), ("barrett_long", 2), ("pti_fold", 4)):
+    for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2), ("barrett_long", 2), ("pti_fold", 4),
+                      ("shoup_lazy", 2), ("shoup_exact", 2)):
         f = getattr(lib, "emu_" + nm)
         f.restype = C.c_uint64
         f.argtypes = [C.c_void_p, C.c_uint] + [C.c_uint64] * nargs
@@ -148,5 +149,20 @@ def emu_lib():
 
 
 @pytest.fixture(scope="session")
-def make_emu(emu_lib):
-    return lambda log_n, L, moduli=None: Emu(emu_lib, log_n, L, moduli)
+def emu_libs():
+    return {v: _build_emu(v) for v in ("gen", "fast")}
+
+
+def is_fast_modulus(q):
+    return q & 0xFFFFFFFF == 1
+
+
+@pytest.fixture(scope="session")
+def make_emu(emu_libs):
+    """make_emu(log_n, L, moduli=None, variant=None): the variant the product would pick for these moduli ("fast" when all are
+    k * 2^32 + 1, which includes the default basis), or an explicit "gen" / "fast"."""
+    def make(log_n, L, moduli=None, variant=None):
+        if variant is None:
+            variant = "fast" if moduli is None or all(is_fast_modulus(int(q)) for q in moduli) else "gen"
+        return Emu(emu_libs[variant], log_n, L, moduli)
+    return make

@@ -15,6 +15,7 @@
 #include "kernel_bodies.cuh"
 
 using namespace dpfhe;
+using namespace dpfhe::DPFHE_VNS;   // built once per arithmetic variant (-DDPFHE_FAST=0 / 1)
 
 namespace {
 struct HostCta {
@@ -74,7 +75,7 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
     for (unsigned s = 0; s < G; ++s) {
         buf[s] = aligned_new<uint64_t>(N);
     }
-    uint64_t *scratch = aligned_new<uint64_t>((size_t)G * 2 * N);
+    uint64_t *scratch = aligned_new<uint64_t>((size_t)G * 2 * N), *acc = aligned_new<uint64_t>((size_t)G * 2 * N);
     // Shoup companions of the key (the device builds them with key_prepare_kernel)
     const size_t key_words = (size_t)2 * L * L * N;
     uint64_t *key_s = aligned_new<uint64_t>(key_words);
@@ -83,6 +84,7 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = key_s; A.out = out; A.scratch = scratch;
     A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois; A.Lk = L; A.hyb = nullptr; A.only = nullptr;
+    A.acc = acc; A.acc_par = 1;
     HostCta cta{NT};
     const size_t n_work = batch * L;
     for (size_t r = 0; r * G < n_work; ++r) {
@@ -90,7 +92,7 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
         for (unsigned s = 0; s < G; ++s) {
             const size_t w = r * G + s;
             if (w >= n_work) break;
-            ks_phase1<LOGN, NT, MODE>(cta, buf[s], A, e.lp[w % L], w / L, (uint32_t)(w % L), scratch + ((size_t)s * 2 + par) * N);
+            ks_phase1<LOGN, NT, MODE>(cta, buf[s], A, e.lp[w % L], w / L, (uint32_t)(w % L), scratch + ((size_t)s * 2 + par) * N, acc + (size_t)s * 2 * N);
         }
         for (unsigned s = 0; s < G; ++s) {
             const size_t w = r * G + s;
@@ -99,7 +101,7 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
             for (uint32_t jj = 1; jj < L; ++jj) {
                 const uint32_t j = (i + jj) % L;
                 const unsigned sib = s - i + j;
-                ks_phase2_digit<LOGN, NT>(cta, buf[s], A, e.lp[i], w / L, i, j, jj, scratch + ((size_t)sib * 2 + par) * N);
+                ks_phase2_digit<LOGN, NT>(cta, buf[s], A, e.lp[i], w / L, i, j, jj, scratch + ((size_t)sib * 2 + par) * N, acc + (size_t)s * 2 * N);
             }
         }
     }
@@ -107,6 +109,7 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
         free(buf[s]);
     }
     free(scratch);
+    free(acc);
     free(key_s);
 }
 
@@ -122,6 +125,7 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
     uint64_t *buf = aligned_new<uint64_t>(N);
     uint64_t *scratch = aligned_new<uint64_t>((size_t)groups * GS * 2 * N);
     uint64_t *hyb_all = aligned_new<uint64_t>((size_t)groups * KS_HYB_ROWS * N);
+    uint64_t *acc = aligned_new<uint64_t>((size_t)groups * GS * 2 * 2 * N);   // [slot][parity][2][N]
     const size_t key_words = (size_t)2 * L * LK * N;
     uint64_t *key_s = aligned_new<uint64_t>(key_words);
     for (size_t k = 0; k < key_words; ++k)
@@ -131,6 +135,8 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = key_s; A.out = out; A.scratch = scratch;
     A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois; A.Lk = LK; A.hyb = hyb_all; A.only = nullptr;
+    A.acc = acc; A.acc_par = 2;
+    auto acc_of = [&](unsigned slot, unsigned parity) { return acc + ((size_t)slot * 2 + parity) * 2 * N; };
     HostCta cta{NT};
     for (size_t r = 0; r * groups < batch; ++r) {
         const unsigned par = (unsigned)(r & 1);
@@ -140,11 +146,11 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
             const unsigned base = g * GS;
             uint64_t *hyb = hyb_all + (size_t)g * KS_HYB_ROWS * N;
             for (unsigned i = 0; i < L; ++i)
-                ks_phase1<LOGN, NT, MODE, true>(cta, buf, A, e.lp[i], ct, i, scratch + ((size_t)(base + i) * 2 + par) * N, K.qlm[i], K.qlm_s[i]);
+                ks_phase1<LOGN, NT, MODE, true>(cta, buf, A, e.lp[i], ct, i, scratch + ((size_t)(base + i) * 2 + par) * N, acc_of(base + i, par), K.qlm[i], K.qlm_s[i]);
             for (unsigned i = 0; i < L; ++i)
                 for (uint32_t jj = 1; jj < L; ++jj) {
                     const uint32_t j = (i + jj) % L;
-                    ks_phase2_digit<LOGN, NT, true, false>(cta, buf, A, e.lp[i], ct, i, j, jj, scratch + ((size_t)(base + j) * 2 + par) * N);
+                    ks_phase2_digit<LOGN, NT, true, false>(cta, buf, A, e.lp[i], ct, i, j, jj, scratch + ((size_t)(base + j) * 2 + par) * N, acc_of(base + i, par));
                 }
             for (uint32_t jj = 0; jj < L; ++jj) {
                 const uint32_t j = (g + jj) % L;
@@ -156,13 +162,14 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
             for (unsigned i = 0; i < L; ++i)
                 for (unsigned c = 0; c < 2; ++c) {
                     uint64_t *row = out + ct * 2 * P + c * P + (size_t)i * N;
-                    ms_limb_body<LOGN, NT, true>(cta, buf, hyb + ks_hyb_tau_row(par, c) * N, row, row, A.tw + (size_t)i * N, e.lp[i], K, i);
+                    ms_limb_body<LOGN, NT, true>(cta, buf, hyb + ks_hyb_tau_row(par, c) * N, acc_of(base + i, par) + c * N, row, A.tw + (size_t)i * N, e.lp[i], K, i);
                 }
         }
     }
     free(buf);
     free(scratch);
     free(hyb_all);
+    free(acc);
     free(key_s);
 }
 
@@ -246,6 +253,13 @@ void *emu_create(unsigned log_n, unsigned L, const uint64_t *moduli) {
         delete e;
         return nullptr;
     }
+#if DPFHE_FAST
+    for (unsigned l = 0; l < L; ++l)   // the fast bodies are only valid for moduli k * 2^32 + 1
+        if (e->hp.limbs[l].lp.nqh == 0) {
+            delete e;
+            return nullptr;
+        }
+#endif
     const size_t N = (size_t)1 << log_n;
     e->tw = aligned_new<Twiddle>(N * L);
     e->itw = aligned_new<Twiddle>(N * L);
@@ -383,6 +397,15 @@ uint64_t emu_mulmod(void *h, unsigned l, uint64_t a, uint64_t b) { return mulmod
 uint64_t emu_word_reduce(void *h, unsigned l, uint64_t x) { return word_reduce(x, ((Emu *)h)->lp[l]); }
 uint64_t emu_canon(void *h, unsigned l, uint64_t x) { return canon(x, ((Emu *)h)->lp[l]); }
 uint64_t emu_mulmod_lazy(void *h, unsigned l, uint64_t a, uint64_t b) { return mulmod_lazy(a, b, ((Emu *)h)->lp[l]); }
+// x * w through the Shoup forms (w < q; the companion is derived here)
+uint64_t emu_shoup_lazy(void *h, unsigned l, uint64_t x, uint64_t w) {
+    const LimbParams &p = ((Emu *)h)->lp[l];
+    return shoup_lazy(x, w, (uint64_t)((((unsigned __int128)w) << 64) / p.q), p);
+}
+uint64_t emu_shoup_exact(void *h, unsigned l, uint64_t x, uint64_t w) {
+    const LimbParams &p = ((Emu *)h)->lp[l];
+    return shoup_exact(x, w, (uint64_t)((((unsigned __int128)w) << 64) / p.q), p);
+}
 // reductions of a two-word value z = hi:lo
 uint64_t emu_barrett_long(void *h, unsigned l, uint64_t hi, uint64_t lo) { return barrett_lazy_long(hi, lo, ((Emu *)h)->lp[l]); }
 uint64_t emu_pti_fold(void *h, unsigned l, uint64_t a0, uint64_t a1a, uint64_t a1b, uint64_t a2) { return pti_fold(a0, a1a, a1b, a2, ((Emu *)h)->lp[l]); }

@@ -20,13 +20,19 @@ def test_host_params_match_oracle(make_emu, oracle_mod, log_n, L):
         assert np.array_equal(e.root_powers(l, inverse=True), o.inv_root_powers(l))
 
 
-def test_device_scalar_arithmetic_bounds(make_emu, oracle_mod):
-    """modarith.cuh on adversarial inputs: every lazy routine stays inside its documented range"""
+@pytest.mark.parametrize("variant", ["gen", "fast"])
+def test_device_scalar_arithmetic_bounds(make_emu, oracle_mod, variant):
+    """modarith.cuh on adversarial inputs: every lazy routine stays inside its documented range (SB = 4: the quotient
+    estimates of the Shoup and Barrett products may be up to two short).  Both arithmetic variants: the generic one on a
+    59-bit and a 34-bit modulus, the k * 2^32 + 1 one on the two largest moduli of the default basis."""
     lib = oracle_mod.lib()
     small = (1 << 34) - (1 << 34) % (2 << 12) + 1
     while not lib.dpo_is_prime(small):
         small += 2 << 12
-    e = make_emu(12, 2, [oracle_mod.Oracle(12, 1).moduli[0], small])
+    defaults = oracle_mod.Oracle(12, 2).moduli
+    assert all(q & 0xFFFFFFFF == 1 for q in defaults)
+    e = make_emu(12, 2, defaults if variant == "fast" else [defaults[0] - 0, small], variant=variant)
+    SB = 4
     rng = np.random.default_rng(2)
     for l, q in enumerate(e.moduli):
         xs = [0, 1, q - 1, q, 2 * q, 3 * q - 1, 2**64 - 1, 2**63, 16 * q - 1 if 16 * q < 2**64 else 2**64 - 1]
@@ -40,7 +46,17 @@ def test_device_scalar_arithmetic_bounds(make_emu, oracle_mod):
         for a, b in zip(vals, reversed(vals)):
             assert e.scalar("mulmod", l, a, b) == (a * b) % q
             r = e.scalar("mulmod_lazy", l, a, b)
-            assert r % q == (a * b) % q and r < 2 * q
+            assert r % q == (a * b) % q and r < SB * q
+        # Shoup products accept ANY 64-bit multiplicand: the lazy form lands below SB*q, the exact one below 2q
+        for x, w in zip(xs[:600], vals[:600]):
+            r = e.scalar("shoup_lazy", l, x, w)
+            assert r % q == (x * w) % q and r < SB * q
+            r = e.scalar("shoup_exact", l, x, w)
+            assert r % q == (x * w) % q and r < 2 * q
+        for x in (2**64 - 1, 16 * q - 1 if 16 * q < 2**64 else 2**64 - 1, 2**32 - 1, 2**32, (2**32 - 1) << 32):
+            for w in (q - 1, 1, 0, q // 2, (q - 1) & ~0xFFFFFFFF, 0xFFFFFFFF):
+                r = e.scalar("shoup_lazy", l, x, w)
+                assert r % q == (x * w) % q and r < SB * q
         # sums of up to 16 products (the plaintext inner products): z < 16 q^2 -> [0, 15q), and the split-operand fold -> [0, 3q)
         zs = [0, 16 * (q - 1) ** 2, (q - 1) ** 2, 2**64 - 1, 2**64] + [int(a) * int(b) * k for a, b, k in zip(vals[:200], vals[200:400], range(1, 201)) if k <= 16]
         for z in zs:
@@ -56,11 +72,11 @@ def test_device_scalar_arithmetic_bounds(make_emu, oracle_mod):
             assert max(a0, a1a, a1b, a2) < 2**64
             r = e.scalar("pti_fold", l, a0, a1a, a1b, a2)
             assert r % q == sum(x * y for x, y in pairs) % q and r < 3 * q
-        # lazy operands as used by the fused kernel: u < 3q times key < q stays below 3q
+        # lazy operands (factor bounds multiplying to at most 4): below (SB + 1) q
         for a in (3 * q - 1, 2 * q + 5, q):
             for b in (q - 1, 1, q // 3):
                 r = e.scalar("mulmod_lazy", l, a, b)
-                assert r % q == (a * b) % q and r < 3 * q
+                assert r % q == (a * b) % q and r < (SB + 1) * q
 
 
 @pytest.mark.parametrize("log_n,L,n_polys", [(12, 1, 1), (12, 3, 2), (13, 4, 2), (14, 2, 1)])
@@ -159,6 +175,27 @@ def test_emulated_hybrid_keyswitch_bodies(make_emu, oracle_mod, log_n, L, batch,
     for k in range(batch):
         c0, c1 = o.keyswitch_hybrid(d[k], key, t)
         assert np.array_equal(got[k, 0], c0) and np.array_equal(got[k, 1], c1)
+
+
+@pytest.mark.parametrize("log_n,L", [(12, 3), (13, 4), (14, 2)])
+def test_generic_variant_on_the_default_basis(make_emu, oracle_mod, log_n, L):
+    """the generic kernels must also be right for k * 2^32 + 1 moduli (DPFHE_FORCE_GENERIC runs them on the default basis)"""
+    e, o = make_emu(log_n, L, variant="gen"), oracle_mod.Oracle(log_n, L)
+    assert e.moduli == o.moduli
+    x = o.fill_uniform(31, 2)
+    x[0] = (np.array(o.moduli, dtype=np.uint64) - 1)[:, None]
+    y = e.ntt(x)
+    assert np.array_equal(y, o.ntt_fwd(x)) and np.array_equal(e.ntt(y, inverse=True), x)
+    s = o.keygen_secret(1)
+    evk = o.keygen_relin(2, 65537, s)
+    a = o.fill_uniform(3, 4).reshape(2, 2, L, o.N)
+    b = o.fill_uniform(4, 4).reshape(2, 2, L, o.N)
+    assert np.array_equal(e.ks(0, a, b, evk, 2, G=L), o.ct_mul_relin(a, b, evk))
+    g = o.galois_elt(5)
+    gk = o.keygen_galois(6, 65537, s, g)
+    assert np.array_equal(e.ks(2, a, None, gk, 2, galois=g, G=2 * L), o.rotate(a, g, gk))
+    if L >= 3:
+        assert np.array_equal(e.mod_switch(x, 65537), o.mod_switch_down(x, 65537))
 
 
 def test_emulated_mixed_size_moduli(make_emu, oracle_mod):

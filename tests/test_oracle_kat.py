@@ -54,12 +54,11 @@ def test_parameter_derivation(oracle_mod, kat):
             assert q < (1 << 60) and q % two_n == 1 and oracle_mod.lib().dpo_is_prime(q)
             assert pow(psi, two_n // 2, q) == q - 1          # primitive 2N-th root
         assert o.moduli == sorted(o.moduli, reverse=True)
-    # the moduli are the LARGEST such primes: nothing prime in between
+    # the moduli are the LARGEST primes k * 2^32 + 1 below 2^60: nothing prime of that form in between
     o = oracle_mod.Oracle(13, 4)
-    two_n = 2 << 13
-    cand, found = ((1 << 60) // two_n) * two_n + 1, []
+    cand, found = (1 << 60) + 1, []
     while len(found) < 4:
-        cand -= two_n
+        cand -= 1 << 32
         if oracle_mod.lib().dpo_is_prime(cand):
             found.append(cand)
     assert found == o.moduli

@@ -11,15 +11,16 @@ from sympy.ntheory import isprime, n_order  # noqa: E402
 
 
 def test_moduli_are_the_largest_ntt_primes(oracle_mod):
+    """the default basis is the L largest primes below 2^60 of the form k * 2^32 + 1 (so 1 mod 2N for every N)"""
     for log_n, L in ((12, 3), (13, 4), (14, 8)):
         o = oracle_mod.Oracle(log_n, L)
-        two_n = 2 << log_n
-        found, cand = [], ((1 << 60) // two_n) * two_n + 1
+        found, cand = [], (1 << 60) + 1
         while len(found) < L:
-            cand -= two_n
+            cand -= 1 << 32
             if isprime(cand):
                 found.append(cand)
         assert found == o.moduli
+        assert all(q % (2 << log_n) == 1 for q in o.moduli)
 
 
 def test_psi_has_order_2n_and_is_minimal(oracle_mod):
