@@ -4,15 +4,20 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
     python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle port, all host threads)
 
-One "step" = one pass of ct x ct multiply + relinearise (dpfhe_ct_mul_relin) over one batch of
-synthetic ciphertexts at BASELINE.json config 2: N = 8192, L = 4, batch = 4096 per GPU.
+One "step" = one pass of ct x ct multiply + relinearise (dpfhe_ct_mul_relin) over one batch of synthetic ciphertexts,
+N = 8192, L = 4: BASELINE.json config 2 (batch 4096) on one GPU, config 5 (65,536 ciphertexts over 8 GPUs = 8192 per GPU)
+when launched on several.
   value      whole-job ct-mults/s, inputs resident in HBM, timed with CUDA events on the launch stream
-  e2e        the same metric through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside)
-  roofline   the fused key-switch kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  ntt        NTTs/s of the standalone forward transform on the same data, with its own roofline
-  cpu_baseline  the CPU oracle (kind "port": the reference has no CPU evaluator) on a bounded sample
-Multi-GPU: one process per GPU (torchrun), ciphertexts sharded by rank, no collective on the data path
-(weak scaling); the final NCCL gather to rank 0 is timed separately and reported under "gather".
+  e2e        the same metric through the host-buffer C-ABI call (pinned host memory on the GPU's NUMA node, H2D + D2H inside)
+  roofline   the fused key-switch kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json); int_pipe = what
+             actually limits it (the integer multiplier), from the committed ncu capture
+  ntt        NTTs/s of the standalone forward and inverse transforms (N = 8192 and N = 16384), with their rooflines
+  cpu_baseline  the CPU oracle (kind "port": the reference has no CPU evaluator) on the SAME batch; its output is
+             also the checker of the timed GPU result ("parity")
+Multi-GPU: one process per GPU (torchrun), ciphertexts sharded by rank, no collective while computing (weak scaling).
+The final result gather to rank 0 rides on the kernel's own output stores: every rank writes its finished rows straight
+into rank 0's buffer (CUDA IPC mapping, NVLink), so the gather overlaps the compute ("gather"; the NCCL gather that
+would otherwise follow the compute is timed beside it).
 """
 import argparse
 import json
@@ -25,7 +30,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LOG_N, L, BATCH = 13, 4, 4096
+LOG_N, L, BATCH, BATCH_MULTI = 13, 4, 4096, 8192     # config 2 / the per-GPU shard of config 5
 N = 1 << LOG_N
 P_WORDS = L * N
 CT_BYTES = 2 * P_WORDS * 8
@@ -40,11 +45,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dpfhe", choices=["dpfhe", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="ciphertexts per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="ciphertexts per GPU per step (default: 4096 on one GPU, 8192 per GPU on several)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational hybrid key-switching timing")
+    ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -202,6 +208,42 @@ def run_reference(args):
     return 0
 
 
+def pipe_profile(kernel):
+    """pipe utilisation of `kernel` from the committed ncu --set full capture (profiles/pipes.json, written by
+    tools/summarize_ncu.py from the .ncu-rep of the bench batch); None if absent"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pipes.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class DevMem:
+    """raw device memory as a torch-visible array (__cuda_array_interface__), for buffers owned by the library / another process"""
+
+    def __init__(self, ptr, n_words):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def cpu_leg(o, threads, ha, hb, hk, gpu_out, seconds):
+    """the CPU arm on the SAME batch the GPU just processed: oracle ct_mul_relin over all of it, repeated for about `seconds`;
+    its output is compared bit for bit with the GPU's.  Returns (cpu_baseline, parity)."""
+    import numpy as np
+    n = ha.shape[0]
+    t, out = o.time_ct_mul_relin(ha, hb, hk, threads)       # first pass: page faults of the output buffer, thread pool
+    exact = bool(np.array_equal(out, gpu_out))
+    done, total = 0, 0.0
+    while total < seconds and done < 64 * n:
+        t, _ = o.time_ct_mul_relin(ha, hb, hk, threads, out=out)
+        total += t
+        done += n
+    cpu = {"value": done / total, "unit": "ct-mult/s", "cores": threads, "kind": "port",
+           "sample": "%d ct-mults in %.1f s: the bench batch itself (%d ciphertexts, repeated), oracle/dpfhe_oracle.c with OpenMP "
+                     "(the reference has no CPU evaluator)" % (done, total, n)}
+    parity = {"checked_ciphertexts": n, "bit_exact": exact, "against": "oracle/dpfhe_oracle.c ct_mul_relin on the timed batch"}
+    return cpu, parity
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -225,8 +267,10 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B = args.batch
+    B = args.batch or (BATCH if world == 1 else BATCH_MULTI)
     ctx = dp.Context(LOG_N, L, device=local_rank)
+    # this rank's thread (and what it first-touches) stays on the socket its GPU hangs off
+    numa = {"node": ctx.numa_node(), "cpus_bound": ctx.bind_thread_near() if world > 1 else 0}
     shape = (B, 2, L, N)
     a = torch.empty(shape, dtype=torch.int64, device="cuda")
     b = torch.empty(shape, dtype=torch.int64, device="cuda")
@@ -269,36 +313,42 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
     peak, peak_src = peaks()
+    kern = "ks_fused_kernel<13,256,3,MUL_RELIN> (dpfhe::fast, persistent cooperative, 3 CTAs/SM)"
     kern_gbs = B * ALGO_BYTES_CT_MUL / (ms_per_step * 1e-3) / 1e9      # per GPU: one launch per step
-    roofline = {"bound": "hbm", "kernel": "ks_fused_kernel<13,256,3,MUL_RELIN> (persistent cooperative, 3 CTAs/SM)", "achieved": kern_gbs, "peak": peak,
-                "unit": "GB/s", "frac": kern_gbs / peak, "traffic": traffic_for("ks_fused_kernel_mul_relin", B),
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": B * ALGO_BYTES_CT_MUL,
-                "note": "64-bit modular integer work: integer issue (IMAD 2.0, IMAD.WIDE 2.55, IADD3 1.5 clk per warp-instruction per SM sub-partition, no ALU/IMAD overlap: profiles/r01/int_pipes*.txt) bounds this kernel below the HBM roofline; ncu: issue slots 56% busy (DESIGN.md section 6)"}
+    roofline = {"bound": "hbm", "kernel": kern, "achieved": kern_gbs, "peak": peak, "unit": "GB/s", "frac": kern_gbs / peak,
+                "traffic": traffic_for("ks_fused_kernel_mul_relin", B), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": B * ALGO_BYTES_CT_MUL,
+                "limiter": "integer multiplier: 64-bit modular arithmetic has no tensor-core form, and IMAD.WIDE issues at a quarter of the "
+                           "rate of the other integer instructions (fmaheavy pipe); DRAM stays far below its peak (DESIGN.md section 6)",
+                "int_pipe": pipe_profile("ks_fused_kernel_mul_relin")}
 
-    # Secondary, explanatory roofline: issued warp-instructions per second against what the integer pipes sustain for
-    # this instruction mix (profiles/r01/int_pipes_final.txt: IMAD.WIDE 2.55, IMAD 2.0, ALU ~1.4 clk per warp-instruction
-    # per SM sub-partition, not overlapping; mix and instructions per ciphertext from profiles/r01/ncu_full_summary.json).
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            instr_per_ct = float(json.load(f)["ks_fused_kernel_mul_relin"]["warp_instructions_per_unit"])
-        mix_clk = 0.28 * 2.55 + 0.24 * 2.0 + 0.40 * 1.4 + 0.08 * 1.0          # clocks per warp-instruction per sub-partition
-        sm_clock = 1.965e9
-        int_peak = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * sm_clock / mix_clk
-        achieved_int = (B / (ms_per_step * 1e-3)) * instr_per_ct
-        roofline["int_issue"] = {"achieved_warp_instr_per_s": achieved_int, "peak_warp_instr_per_s": int_peak,
-                                 "frac": achieved_int / int_peak, "warp_instr_per_ct_mult": instr_per_ct,
-                                 "source": "ncu smsp__inst_executed.sum per launch / batch; pipe costs from the committed microbenchmark"}
-    except Exception:
-        pass
-
-    # standalone NTT on the same data (NTTs/s half of the BASELINE metric)
-    ntt_ms = timed(lambda: ctx.ntt_fwd(a, 2 * B), max(3, args.steps // 2), 2) / max(3, args.steps // 2)
+    # standalone transforms on the same data (the NTTs/s half of the BASELINE metric): forward and inverse
+    k_ntt = max(3, args.steps // 2)
     n_ntt = 2 * B * L
-    ntt_gbs = n_ntt * ALGO_BYTES_NTT / (ntt_ms * 1e-3) / 1e9
-    ntt = {"metric": "ntt_fwd_per_s", "value": world * n_ntt / (ntt_ms * 1e-3), "unit": "NTT/s", "ms_per_step": ntt_ms,
-           "roofline": {"bound": "hbm", "kernel": "ntt_kernel<13,256,3,fwd> (one CTA per limb, 3 CTAs/SM)", "achieved": ntt_gbs, "peak": peak, "unit": "GB/s",
-                        "frac": ntt_gbs / peak, "traffic": traffic_for("ntt_kernel_fwd", n_ntt)}}
-    ctx.fill_uniform(SEED, a, 2 * B, first_poly=first)     # restore `a` (the NTT ran in place)
+
+    def ntt_entry(ms, n, nbytes, kernel, tkey):
+        gbs = n * nbytes / (ms * 1e-3) / 1e9
+        return {"value": world * n / (ms * 1e-3), "unit": "NTT/s", "ms_per_step": ms,
+                "roofline": {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                             "traffic": traffic_for(tkey, n), "int_pipe": pipe_profile(tkey)}}
+
+    fwd_ms = timed(lambda: ctx.ntt_fwd(a, 2 * B), k_ntt, 2) / k_ntt
+    inv_ms = timed(lambda: ctx.ntt_inv(a, 2 * B), k_ntt, 2) / k_ntt
+    ntt = ntt_entry(fwd_ms, n_ntt, ALGO_BYTES_NTT, "ntt_kernel<13,256,3,fwd> (dpfhe::fast, one CTA per limb, 3 CTAs/SM)", "ntt_kernel_fwd")
+    ntt["metric"] = "ntt_fwd_per_s"
+    ntt["inverse"] = ntt_entry(inv_ms, n_ntt, ALGO_BYTES_NTT, "ntt_kernel<13,256,3,inv>", "ntt_kernel_inv")
+    ctx.fill_uniform(SEED, a, 2 * B, first_poly=first)     # restore `a` (the transforms ran in place)
+    if not args.no_extras:
+        # config 3's ring: N = 16384, L = 8 (1024 ciphertexts = 16384 limb transforms of 128 KiB)
+        ctx14 = dp.Context(14, 8, device=local_rank)
+        x14 = torch.empty((2048, 8, 1 << 14), dtype=torch.int64, device="cuda")
+        ctx14.fill_uniform(SEED + 7, x14, 2048)
+        f14 = timed(lambda: ctx14.ntt_fwd(x14, 2048), 3, 2) / 3
+        i14 = timed(lambda: ctx14.ntt_inv(x14, 2048), 3, 2) / 3
+        ntt["n16384"] = {"fwd": ntt_entry(f14, 2048 * 8, 2 * (1 << 14) * 8, "ntt_kernel<14,...,fwd>", "ntt_kernel_fwd_n16384"),
+                         "inv": ntt_entry(i14, 2048 * 8, 2 * (1 << 14) * 8, "ntt_kernel<14,...,inv>", "ntt_kernel_inv_n16384")}
+        ctx14.close()
+        del x14
 
     # SURVEY.md section 8 row f-2 (informational, not the headline): the same ciphertexts through special-prime hybrid
     # key switching (context = the four ciphertext moduli + one special prime; 30 transforms per ct-mult instead of 16)
@@ -314,18 +364,23 @@ def main():
                                           "note": "4 ciphertext limbs + 1 special prime, BGV rounding t=65537 (DESIGN.md 2.10)"}}
         ctx5.close()
         del hkey
-        ctx.ct_mul_relin(a, b, evk, out, B)     # `out` is compared with the end-to-end result below
+    ctx.ct_mul_relin(a, b, evk, out, B)     # `out` = the reference result for the comparisons below
+    torch.cuda.synchronize()
 
-    # end to end through the host-buffer ABI: pinned host memory, H2D + D2H inside the timed region
+    # end to end through the host-buffer ABI: pinned host memory on this GPU's NUMA node, H2D + D2H inside the timed region
     e2e = None
-    if not args.no_e2e:
-        ha = torch.empty(shape, dtype=torch.int64, pin_memory=True)
-        hb = torch.empty(shape, dtype=torch.int64, pin_memory=True)
-        ho = torch.empty(shape, dtype=torch.int64, pin_memory=True)
-        hk = torch.empty((L, 2, L, N), dtype=torch.int64, pin_memory=True)
-        ha.copy_(a); hb.copy_(b); hk.copy_(evk)
+    host = None
+    if not args.no_e2e or (rank == 0 and world == 1 and not args.no_cpu):
+        n_words = B * 2 * P_WORDS
+        bufs = [ctx.pinned_near(n_words) for _ in range(3)] + [ctx.pinned_near(2 * L * P_WORDS)]
+        na, nb, no = (x.array.reshape(shape) for x in bufs[:3])
+        nk = bufs[3].array.reshape(L, 2, L, N)
+        for dst, src in ((na, a), (nb, b), (nk, evk)):
+            torch.from_numpy(dst.view(np.int64)).copy_(src)
         torch.cuda.synchronize()
-        na, nb, no, nk = (t.numpy().view(np.uint64) for t in (ha, hb, ho, hk))
+        host = (na, nb, nk, no, bufs)
+    if not args.no_e2e:
+        na, nb, nk, no, bufs = host
         ctx.ct_mul_relin_host(na, nb, nk, no)       # warm-up (allocates the staging buffers)
         barrier()
         t0 = time.perf_counter()
@@ -335,52 +390,89 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e_s = float(dt.item())
-        ok = bool(torch.equal(ho.cuda(), out))     # the host path must reproduce the device path bit for bit
-        e2e = {"value": world * B / e2e_s, "unit": "ct-mult/s", "h2d_bytes_per_step": 2 * B * CT_BYTES + 2 * L * P_WORDS * 8,
-               "d2h_bytes_per_step": B * CT_BYTES, "ms_per_step": e2e_s * 1e3, "matches_device_path": ok,
-               "pcie": {"h2d_GBps_per_gpu": (2 * B * CT_BYTES + 2 * L * P_WORDS * 8) / e2e_s / 1e9, "d2h_GBps_per_gpu": B * CT_BYTES / e2e_s / 1e9,
+        ok = bool(torch.equal(torch.from_numpy(no.view(np.int64)).cuda(), out))     # the host path must reproduce the device path bit for bit
+        h2d, d2h = 2 * B * CT_BYTES + 2 * L * P_WORDS * 8, B * CT_BYTES
+        e2e = {"value": world * B / e2e_s, "unit": "ct-mult/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_s * 1e3, "matches_device_path": ok,
+               "pcie": {"h2d_GBps_per_gpu": h2d / e2e_s / 1e9, "d2h_GBps_per_gpu": d2h / e2e_s / 1e9,
                         "note": "both directions run concurrently; the host-to-device stream (two operand batches per result batch) is the bound"},
-               "api": "dpfhe_ct_mul_relin_host (pinned host buffers, 3-stage H2D/compute/D2H pipeline)"}
-        del ha, hb, ho, hk
+               "host_memory": {"gpu_numa_node": numa["node"], "pages_placed_on_node": bufs[0].node, "cpus_bound": numa["cpus_bound"],
+                               "allocator": "dpfhe_host_alloc_near (mmap + mbind + cudaHostRegister)"},
+               "api": "dpfhe_ct_mul_relin_host (pinned host buffers, 3-stage H2D/compute/D2H pipeline; one call per rank, no collective)"}
 
-    # final result gather (the only collective): NCCL gather of every rank's output to rank 0
+    # The final result gather.  Every rank's kernel writes its finished output rows straight into rank 0's buffer (opened here
+    # through a CUDA IPC handle), so the gather is spread over the compute instead of following it.
     gather = None
-    if world > 1:
-        bufs = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+    if world > 1 and not args.no_gather:
+        ct_words = 2 * P_WORDS
+        root_ptr = ctx.device_alloc(world * B * CT_BYTES) if rank == 0 else None
+        handles = [ctx.ipc_export(root_ptr) if rank == 0 else None]
+        dist.broadcast_object_list(handles, src=0)
+        base = root_ptr if rank == 0 else ctx.ipc_open(handles[0])
+        mine = base + rank * B * CT_BYTES
+        g_ms = timed(lambda: ctx.ct_mul_relin(a, b, evk, mine, B), max(3, args.steps // 2), 2) / max(3, args.steps // 2)
+        # verification: rank 0 compares every slice of its buffer with the checksums of the ranks' local results
+        def checks(t):
+            v = t.view(-1)
+            return torch.stack([v.sum(), (v * 0x1E3779B97F4A7C15 - (v >> 17)).sum()])
+        local = checks(out)
+        allc = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(allc, local)
+        verified = None
+        if rank == 0:
+            root = torch.as_tensor(DevMem(root_ptr, world * B * ct_words), device="cuda")
+            verified = all(bool(torch.equal(checks(root[r * B * ct_words:(r + 1) * B * ct_words]), allc[r])) for r in range(world))
+        # the collective this replaces: NCCL gather of the finished outputs to rank 0, after the compute
+        nb_ = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
         warm = [torch.empty_like(out[:8]) for _ in range(world)] if rank == 0 else None
         dist.gather(out[:8].contiguous(), warm, dst=0)      # NCCL channel set-up happens on the first call
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        dist.gather(out, bufs, dst=0)
+        dist.gather(out, nb_, dst=0)
         g1.record()
         barrier()
-        gms = torch.tensor([g0.elapsed_time(g1)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(gms.item()), "bytes_into_root": (world - 1) * B * CT_BYTES,
-                  "GBps_into_root": (world - 1) * B * CT_BYTES / (float(gms.item()) * 1e-3) / 1e9,
-                  "value_with_gather": world * B / ((ms_per_step + float(gms.item())) * 1e-3), "collective": "ncclGather via torch.distributed"}
-        del bufs
+        nccl_ms = torch.tensor([g0.elapsed_time(g1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(nccl_ms, op=dist.ReduceOp.MAX)
+        nccl_ms = float(nccl_ms.item())
+        into_root = (world - 1) * B * CT_BYTES
+        gather = {"collective": "none: peer stores of the fused kernel into rank 0's IPC-mapped buffer over NVLink (overlapped with the compute)",
+                  "ms_per_step_with_gather": g_ms, "value_with_gather": world * B / (g_ms * 1e-3),
+                  "bytes_into_root": into_root, "GBps_into_root": into_root / (g_ms * 1e-3) / 1e9,
+                  "nvlink_ingress_bound_ms": into_root / 770e9 * 1e3,
+                  "verified_against_local_results": verified,
+                  "nccl_gather_after_compute": {"ms": nccl_ms, "GBps_into_root": into_root / (nccl_ms * 1e-3) / 1e9,
+                                                "value_with_gather": world * B / ((ms_per_step + nccl_ms) * 1e-3),
+                                                "collective": "ncclGather via torch.distributed (not overlapped)"}}
+        del nb_
+        barrier()
+        if rank != 0:
+            ctx.ipc_close(base)
+        barrier()
+        if rank == 0:
+            ctx.device_free(root_ptr)
 
     if rank == 0:
-        cpu = None
+        cpu = parity = None
         if not args.no_cpu and world == 1:
             import oracle
             oracle.build()
             o = oracle.Oracle(LOG_N, L)
             threads = pick_threads(o)
-            rate, n, t = cpu_sample(o, args.cpu_seconds, threads)
-            cpu = {"value": rate, "unit": "ct-mult/s", "cores": threads, "kind": "port",
-                   "sample": "%d ct-mults in %.1f s, oracle/dpfhe_oracle.c with OpenMP (the reference has no CPU evaluator)" % (n, t)}
+            na, nb, nk, _, _ = host
+            cpu, parity = cpu_leg(o, threads, na, nb, nk, out.cpu().numpy().view(np.uint64), args.cpu_seconds)
+        workload = ("ct x ct multiply + relinearise, N=8192, L=4, batch=%d (BASELINE.json config 2)" % B if world == 1 else
+                    "ct x ct multiply + relinearise, N=8192, L=4, batch=%d sharded over %d GPUs, %d per GPU (BASELINE.json config 5: 65536 over 8)" % (world * B, world, B))
         line = {
             "metric": "ct_mult_relin_per_s", "value": value, "unit": "ct-mult/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "ct x ct multiply + relinearise, N=8192, L=4, batch=%d per GPU (BASELINE.json config 2)" % B,
-                       "global_batch": world * B, "parallelism": "batch-sharded x%d, no data-path collective" % world,
+            "config": {"workload": workload,
+                       "global_batch": world * B, "parallelism": "batch-sharded x%d, no collective while computing" % world,
+                       "moduli": "the %d largest primes k*2^32+1 below 2^60 (default basis, DESIGN.md 2.1)" % L,
                        "l2": "inputs+outputs are %.1f GiB per GPU (>> 126 MB L2), no flush needed" % (3 * B * CT_BYTES / 2**30),
                        "seed": hex(SEED)},
-            "roofline": roofline, "ntt": ntt, "extras": extras, "cpu_baseline": cpu, "e2e": e2e, "gather": gather,
+            "roofline": roofline, "ntt": ntt, "extras": extras, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gather": gather,
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line))

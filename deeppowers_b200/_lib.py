@@ -45,6 +45,27 @@ SYMBOLS = {
     "dpfhe_ct_mul_relin_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "dpfhe_ct_mul_plain_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "dpfhe_rotate_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dpfhe_context_device": (C.c_int, [C.c_void_p]),
+    "dpfhe_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "dpfhe_synchronize": (C.c_int, [C.c_void_p]),
+    "dpfhe_galois_element": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "dpfhe_rotate_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dpfhe_host_alloc_near": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(C.c_int)]),
+    "dpfhe_device_numa_node": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "dpfhe_bind_thread_near": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "dpfhe_device_alloc": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t]),
+    "dpfhe_device_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dpfhe_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
+    "dpfhe_ipc_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "dpfhe_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dpfhe_multi_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "dpfhe_multi_destroy": (None, [C.c_void_p]),
+    "dpfhe_multi_device_count": (C.c_int, [C.c_void_p]),
+    "dpfhe_multi_context": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "dpfhe_multi_shard": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "dpfhe_multi_ct_mul_relin_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dpfhe_multi_rotate_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dpfhe_multi_ct_mul_relin_gather": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_size_t]),
     "dpfhe_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "dpfhe_host_free": (C.c_int, [C.c_void_p]),
     "dpfhe_launch_count": (C.c_uint64, [C.c_void_p]),

@@ -9,9 +9,9 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libdpfhe.so")
 # (source, object name, extra flags): kernels.cu is compiled once per arithmetic variant (csrc/types.hpp)
 UNITS = [("kernels.cu", "kernels_gen", ["-DDPFHE_FAST=0"]), ("kernels.cu", "kernels_fast", ["-DDPFHE_FAST=1"]),
-         ("abi.cu", "abi", []), ("host_params.cpp", "host_params", [])]
+         ("abi.cu", "abi", []), ("multi.cu", "multi", []), ("hostmem.cu", "hostmem", []), ("host_params.cpp", "host_params", [])]
 SOURCES = sorted({u[0] for u in UNITS})
-HEADERS = ["types.hpp", "modarith.cuh", "ntt_core.cuh", "kernel_bodies.cuh", "launch.hpp", "host_params.hpp",
+HEADERS = ["types.hpp", "modarith.cuh", "ntt_core.cuh", "kernel_bodies.cuh", "launch.hpp", "host_params.hpp", "ctx.hpp",
            os.path.join("..", "..", "include", "dpfhe.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

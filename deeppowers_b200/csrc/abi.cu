@@ -15,24 +15,18 @@
 #include <vector>
 
 #include "../../include/dpfhe.h"
-#include "host_params.hpp"
-#include "launch.hpp"
+#include "ctx.hpp"
 
 using namespace dpfhe;
+
+// sets the thread-local message of dpfhe_last_error() and returns `code` (shared with multi.cu / hostmem.cu: ctx.hpp)
+int dpfhe_fail(int code, const char *fmt, ...);
 
 namespace {
 
 thread_local std::string g_err;
 
-int fail(int code, const char *fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return code;
-}
+#define fail dpfhe_fail
 
 #define CU_TRY(expr)                                                                                          \
     do {                                                                                                      \
@@ -41,36 +35,12 @@ int fail(int code, const char *fmt, ...) {
             return fail(DPFHE_ERR_CUDA, "CUDA error at %s:%d: %s (%s)", __FILE__, __LINE__, cudaGetErrorString(e_), #expr); \
     } while (0)
 
-constexpr int PIPE_DEPTH = 3;
+constexpr int PIPE_DEPTH = DPFHE_PIPE_DEPTH;
 
 // launcher of the context's arithmetic variant (launch.hpp): dpfhe::fast when every modulus is k * 2^32 + 1
 #define VCALL(fn, lc, ...) ((lc).fast ? fast::fn((lc), __VA_ARGS__) : gen::fn((lc), __VA_ARGS__))
 
 }  // namespace
-
-struct dpfhe_ctx {
-    HostParams hp;
-    LaunchCtx lc;
-    cudaStream_t stream = nullptr;          // the context's own stream (used when the caller passes NULL)
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    LimbParams *d_lp = nullptr;
-    Twiddle *d_tw = nullptr, *d_itw = nullptr;
-    size_t device_bytes = 0;
-    uint64_t launches = 0;
-    // staging for the host-buffer entry points (allocated on first use)
-    u64 *ms_tau = nullptr;                   // scratch of dpfhe_mod_switch_down: [n_polys][N]
-    size_t ms_tau_bytes = 0;
-    // hoisted rotations (allocated on first use): shared transforms U [chunk][L][L][N], zero flags [chunk],
-    // per-rotation constants M [L][N] and kprime [2][L][N], and the table delta[j][i] = q_j mod q_i
-    u64 *hoist_U = nullptr, *hoist_M = nullptr, *hoist_kprime = nullptr, *hoist_delta = nullptr;
-    u32 *hoist_zero = nullptr;
-    size_t hoist_chunk = 0;                  // ciphertexts the current U / zero buffers hold
-    u64 *stage_in[PIPE_DEPTH] = {}, *stage_out[PIPE_DEPTH] = {}, *stage_key = nullptr;
-    size_t stage_in_bytes = 0, stage_out_bytes = 0, stage_key_bytes = 0;
-    cudaEvent_t ev_h2d[PIPE_DEPTH] = {}, ev_comp[PIPE_DEPTH] = {}, ev_d2h[PIPE_DEPTH] = {};
-    size_t N() const { return (size_t)1 << hp.log_n; }
-    size_t P() const { return N() * hp.L; }
-};
 
 namespace {
 
@@ -82,7 +52,22 @@ int enter(const dpfhe_ctx *ctx) {
     return DPFHE_OK;
 }
 
-cudaStream_t pick(dpfhe_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+// The stream of this call (NULL = the context's own).  If the previous call ran on a different stream, this one waits for it:
+// all calls share the context's scratch (key companions, digit slots, tickets), so they must not overlap.
+cudaStream_t pick(dpfhe_ctx *ctx, void *stream) {
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if (ctx->have_last && ctx->last_stream != st) cudaStreamWaitEvent(st, ctx->ev_last, 0);
+    ctx->cur = st;
+    return st;
+}
+// counts `n` launches just issued on the stream chosen by pick() and marks the point later calls have to wait for
+void note_launch(dpfhe_ctx *ctx, uint64_t n) {
+    ctx->launches += n;
+    if (ctx->cur && cudaEventRecord(ctx->ev_last, ctx->cur) == cudaSuccess) {
+        ctx->last_stream = ctx->cur;
+        ctx->have_last = true;
+    }
+}
 
 int ensure_staging(dpfhe_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t key_bytes) {
     if (in_bytes > ctx->stage_in_bytes) {
@@ -156,6 +141,16 @@ size_t pick_chunk(const dpfhe_ctx *ctx, size_t item_bytes, size_t n_items) {
 
 }  // namespace
 
+int dpfhe_fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
 extern "C" {
 
 const char *dpfhe_last_error(void) { return g_err.c_str(); }
@@ -202,6 +197,7 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
         CTX_TRY(cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming));
         CTX_TRY(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
     }
+    CTX_TRY(cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming));
     const size_t N = ctx->N(), L = ctx->hp.L;
     CTX_TRY(cudaMalloc(&ctx->d_lp, L * sizeof(LimbParams)));
     CTX_TRY(cudaMalloc(&ctx->d_tw, L * N * sizeof(Twiddle)));
@@ -282,6 +278,7 @@ void dpfhe_context_destroy(dpfhe_ctx *ctx) {
         if (ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
         if (ctx->ev_d2h[k]) cudaEventDestroy(ctx->ev_d2h[k]);
     }
+    if (ctx->ev_last) cudaEventDestroy(ctx->ev_last);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -321,7 +318,7 @@ int dpfhe_ntt_fwd(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream
     if (n_polys == 0) return DPFHE_OK;
     CHECK_PTR(d_data);
     CU_TRY(VCALL(launch_ntt, ctx->lc, d_data, n_polys, false, pick(ctx, stream)));
-    ctx->launches++;
+    note_launch(ctx, 1);
     return DPFHE_OK;
 }
 int dpfhe_ntt_inv(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream) {
@@ -330,7 +327,7 @@ int dpfhe_ntt_inv(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream
     if (n_polys == 0) return DPFHE_OK;
     CHECK_PTR(d_data);
     CU_TRY(VCALL(launch_ntt, ctx->lc, d_data, n_polys, true, pick(ctx, stream)));
-    ctx->launches++;
+    note_launch(ctx, 1);
     return DPFHE_OK;
 }
 
@@ -340,7 +337,7 @@ int dpfhe_poly_mul_pointwise(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t
     if (n_polys == 0) return DPFHE_OK;
     CHECK_PTR(d_a); CHECK_PTR(d_b); CHECK_PTR(d_out);
     CU_TRY(VCALL(launch_pointwise_mul, ctx->lc, d_a, d_b, d_out, n_polys, pick(ctx, stream)));
-    ctx->launches++;
+    note_launch(ctx, 1);
     return DPFHE_OK;
 }
 
@@ -350,7 +347,7 @@ int dpfhe_poly_add(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uin
     if (n_polys == 0) return DPFHE_OK;
     CHECK_PTR(d_a); CHECK_PTR(d_b); CHECK_PTR(d_out);
     CU_TRY(VCALL(launch_poly_add, ctx->lc, d_a, d_b, d_out, n_polys, pick(ctx, stream)));
-    ctx->launches++;
+    note_launch(ctx, 1);
     return DPFHE_OK;
 }
 
@@ -360,7 +357,7 @@ int dpfhe_ct_tensor(dpfhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, ui
     if (batch == 0) return DPFHE_OK;
     CHECK_PTR(d_a); CHECK_PTR(d_b); CHECK_PTR(d_d);
     CU_TRY(VCALL(launch_ct_tensor, ctx->lc, d_a, d_b, d_d, batch, pick(ctx, stream)));
-    ctx->launches++;
+    note_launch(ctx, 1);
     return DPFHE_OK;
 }
 
@@ -377,7 +374,7 @@ static int ks_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const uint64_t
     }
     if (out == a || out == b) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
     CU_TRY(VCALL(launch_ks, ctx->lc, mode, a, b, key, out, batch, (u32)galois, pick(ctx, stream)));
-    ctx->launches += 2;   // key_prepare_kernel + ks_fused_kernel
+    note_launch(ctx, 2);   // key_prepare_kernel + ks_fused_kernel
     return DPFHE_OK;
 }
 
@@ -420,7 +417,7 @@ static int ks_hybrid_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const u
     MsConsts K;
     build_ms_consts(ctx->hp, t_plain, K);
     CU_TRY(VCALL(launch_ks_hybrid, ctx->lc, mode, a, b, key, out, batch, (u32)galois, K, pick(ctx, stream)));
-    ctx->launches += 2;   // key_prepare_kernel + ks_hybrid_kernel
+    note_launch(ctx, 2);   // key_prepare_kernel + ks_hybrid_kernel
     return DPFHE_OK;
 }
 int dpfhe_keyswitch_hybrid(dpfhe_ctx *ctx, const uint64_t *d_d, const uint64_t *d_key, uint64_t *d_out, size_t batch, uint64_t t_plain,
@@ -492,16 +489,16 @@ int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, con
         CU_TRY(cudaMemsetAsync(ctx->hoist_zero, 0, cnt * sizeof(u32), st));
         if (L > 1) {
             CU_TRY(VCALL(launch_hoist, ctx->lc, in, ctx->hoist_U, ctx->hoist_zero, cnt, st));
-            ctx->launches++;
+            note_launch(ctx, 1);
         }
         for (size_t r = 0; r < n_rot; ++r) {
             u64 *out = d_out + (r * batch + first) * 2 * P;
             CU_TRY(VCALL(launch_rot_prepare, ctx->lc, d_gks[r], (u32)galois_elts[r], ctx->hoist_delta, ctx->hoist_M, ctx->hoist_kprime, st));
             CU_TRY(VCALL(launch_rot_apply, ctx->lc, in, L > 1 ? ctx->hoist_U : nullptr, d_gks[r], ctx->hoist_kprime, (u32)galois_elts[r], out, cnt, st));
-            ctx->launches += 5;   // key_prepare, negmask, ntt, kprime, rot_apply
+            note_launch(ctx, 5);   // key_prepare, negmask, ntt, kprime, rot_apply
             if (L > 1) {
                 CU_TRY(VCALL(launch_ks, ctx->lc, KS_ROTATE, in, nullptr, d_gks[r], out, cnt, (u32)galois_elts[r], st, ctx->hoist_zero, true));
-                ctx->launches++;
+                note_launch(ctx, 1);
             }
         }
     }
@@ -514,7 +511,7 @@ int dpfhe_ct_mul_plain(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_p
     if (batch == 0) return DPFHE_OK;
     CHECK_PTR(d_ct); CHECK_PTR(d_pt); CHECK_PTR(d_out);
     CU_TRY(VCALL(launch_ct_mul_plain, ctx->lc, d_ct, d_pt, d_out, batch, pick(ctx, stream)));
-    ctx->launches++;
+    note_launch(ctx, 1);
     return DPFHE_OK;
 }
 
@@ -524,7 +521,7 @@ int dpfhe_ct_mul_plain_acc(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t 
     if (batch == 0) return DPFHE_OK;
     CHECK_PTR(d_ct); CHECK_PTR(d_pt); CHECK_PTR(d_acc);
     CU_TRY(VCALL(launch_ct_mul_plain_acc, ctx->lc, d_ct, d_pt, d_acc, batch, pick(ctx, stream)));
-    ctx->launches++;
+    note_launch(ctx, 1);
     return DPFHE_OK;
 }
 
@@ -539,7 +536,7 @@ int dpfhe_ct_mul_plain_inner(dpfhe_ctx *ctx, const uint64_t *d_steps, size_t n_s
     if (d_out == d_steps) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
     unsigned launches = 0;
     CU_TRY(VCALL(launch_pt_inner, ctx->lc, d_steps, (u32)n_steps, d_pts, (u32)n_groups, d_out, batch, pick(ctx, stream), &launches));
-    ctx->launches += launches;
+    note_launch(ctx, launches);
     return DPFHE_OK;
 }
 
@@ -565,7 +562,7 @@ int dpfhe_mod_switch_down(dpfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out,
     MsConsts K;
     build_ms_consts(ctx->hp, t_plain, K);
     CU_TRY(VCALL(launch_mod_switch, ctx->lc, d_in, ctx->ms_tau, d_out, K, n_polys, pick(ctx, stream)));
-    ctx->launches += 2;
+    note_launch(ctx, 2);
     return DPFHE_OK;
 }
 
@@ -575,7 +572,7 @@ int dpfhe_fill_uniform(dpfhe_ctx *ctx, uint64_t seed, uint64_t first_poly, uint6
     if (n_polys == 0) return DPFHE_OK;
     CHECK_PTR(d_data);
     CU_TRY(VCALL(launch_fill_uniform, ctx->lc, seed, first_poly, d_data, n_polys, pick(ctx, stream)));
-    ctx->launches++;
+    note_launch(ctx, 1);
     return DPFHE_OK;
 }
 
@@ -591,7 +588,7 @@ static int ntt_host(dpfhe_ctx *ctx, uint64_t *h_data, size_t n_polys, bool inver
     return run_pipeline(ctx, h_data, nullptr, h_data, n_polys, P, P, chunk,
                         [&](u64 *din, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
                             CU_TRY(VCALL(launch_ntt, ctx->lc, din, cnt, inverse, st));
-                            ctx->launches++;
+                            note_launch(ctx, 1);
                             CU_TRY(cudaMemcpyAsync(dout, din, cnt * P * 8, cudaMemcpyDeviceToDevice, st));
                             return DPFHE_OK;
                         });
@@ -602,7 +599,7 @@ int dpfhe_ntt_inv_host(dpfhe_ctx *ctx, uint64_t *h_data, size_t n_polys) { retur
 static int upload_key(dpfhe_ctx *ctx, const uint64_t *h_key, size_t words) {
     int rc = ensure_staging(ctx, 0, 0, words * 8);
     if (rc) return rc;
-    CU_TRY(cudaMemcpyAsync(ctx->stage_key, h_key, words * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(ctx->stage_key, h_key, words * 8, cudaMemcpyHostToDevice, pick(ctx, nullptr)));
     return DPFHE_OK;
 }
 
@@ -696,19 +693,91 @@ int dpfhe_ct_mul_plain_host(dpfhe_ctx *ctx, const uint64_t *h_ct, const uint64_t
     return run_pipeline(ctx, h_ct, nullptr, h_out, batch, 2 * P, 2 * P, chunk,
                         [&](u64 *dc, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
                             CU_TRY(VCALL(launch_ct_mul_plain, ctx->lc, dc, ctx->stage_key, dout, cnt, st));
-                            ctx->launches++;
+                            note_launch(ctx, 1);
                             return DPFHE_OK;
                         });
 }
 
-int dpfhe_host_alloc(void **out, size_t bytes) {
-    if (!out) return fail(DPFHE_ERR_INVALID, "null argument");
-    CU_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+// waits for everything this context has in flight, whatever stream it was issued on
+int dpfhe_synchronize(dpfhe_ctx *ctx) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (ctx->have_last) CU_TRY(cudaEventSynchronize(ctx->ev_last));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->s_h2d));
+    CU_TRY(cudaStreamSynchronize(ctx->s_d2h));
     return DPFHE_OK;
 }
-int dpfhe_host_free(void *p) {
-    if (!p) return DPFHE_OK;
-    CU_TRY(cudaFreeHost(p));
+
+int dpfhe_device_count(int *out) {
+    if (!out) return fail(DPFHE_ERR_INVALID, "null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    *out = e == cudaSuccess ? n : 0;
+    if (e != cudaSuccess) return fail(DPFHE_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return DPFHE_OK;
+}
+
+int dpfhe_context_device(const dpfhe_ctx *ctx) { return ctx ? ctx->lc.device : -1; }
+
+// rotation by k slots (k may be negative): the Galois element is 5^k mod 2N
+int dpfhe_galois_element(const dpfhe_ctx *ctx, int k, uint64_t *galois_elt) {
+    if (!ctx || !galois_elt) return fail(DPFHE_ERR_INVALID, "null argument");
+    const uint64_t two_n = (uint64_t)2 << ctx->hp.log_n, order = two_n / 4;   // 5 has order N/2 in Z_2N^*
+    uint64_t e = (uint64_t)(((long long)k % (long long)order + (long long)order) % (long long)order), g = 1, b = 5;
+    for (; e; e >>= 1) {
+        if (e & 1) g = g * b % two_n;
+        b = b * b % two_n;
+    }
+    *galois_elt = g;
+    return DPFHE_OK;
+}
+int dpfhe_rotate_steps(dpfhe_ctx *ctx, const uint64_t *d_ct, int k, const uint64_t *d_gk, uint64_t *d_out, size_t batch, void *stream) {
+    uint64_t g = 0;
+    int rc = dpfhe_galois_element(ctx, k, &g);
+    if (rc) return rc;
+    return dpfhe_rotate(ctx, d_ct, g, d_gk, d_out, batch, stream);
+}
+
+// ---------------------------------------------------------------- device memory that other processes / devices can map
+int dpfhe_device_alloc(dpfhe_ctx *ctx, void **d_out, size_t bytes) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (!d_out) return fail(DPFHE_ERR_INVALID, "null argument");
+    *d_out = nullptr;
+    CU_TRY(cudaMalloc(d_out, bytes));   // a whole allocation of its own, so that an IPC handle maps exactly this buffer
+    return DPFHE_OK;
+}
+int dpfhe_device_free(dpfhe_ctx *ctx, void *d_ptr) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (d_ptr) CU_TRY(cudaFree(d_ptr));
+    return DPFHE_OK;
+}
+int dpfhe_ipc_export(dpfhe_ctx *ctx, const void *d_ptr, unsigned char handle[DPFHE_IPC_HANDLE_BYTES]) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (!d_ptr || !handle) return fail(DPFHE_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == DPFHE_IPC_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    memcpy(handle, &h, sizeof(h));
+    return DPFHE_OK;
+}
+int dpfhe_ipc_open(dpfhe_ctx *ctx, const unsigned char handle[DPFHE_IPC_HANDLE_BYTES], void **d_out) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (!handle || !d_out) return fail(DPFHE_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    *d_out = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(d_out, h, cudaIpcMemLazyEnablePeerAccess));   // maps the peer's buffer into this context's device
+    return DPFHE_OK;
+}
+int dpfhe_ipc_close(dpfhe_ctx *ctx, void *d_ptr) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (d_ptr) CU_TRY(cudaIpcCloseMemHandle(d_ptr));
     return DPFHE_OK;
 }
 

@@ -56,19 +56,23 @@ def _stream(s):
 class Context:
     """One parameter set bound to one GPU (dpfhe_ctx).  Not thread-safe; one per GPU/process."""
 
-    def __init__(self, log_n, n_limbs, moduli=None, device=0):
+    def __init__(self, log_n, n_limbs, moduli=None, device=0, _borrowed=None):
         self._l = _lib.load()
         self._h = C.c_void_p()
-        arr = None
-        if moduli is not None:
-            if len(moduli) != n_limbs:
-                raise ValueError("need exactly n_limbs moduli")
-            arr = (C.c_uint64 * n_limbs)(*[int(m) for m in moduli])
-        p = _lib.dpfhe_params(log_n, n_limbs, arr)
-        rc = self._l.dpfhe_context_create(C.byref(p), int(device), C.byref(self._h))
-        if rc != 0:
-            self._h = C.c_void_p()
-            raise DpfheError(self._l.dpfhe_last_error().decode())
+        self._owned = _borrowed is None
+        if _borrowed is not None:     # a context owned by a MultiContext
+            self._h = C.c_void_p(_borrowed)
+        else:
+            arr = None
+            if moduli is not None:
+                if len(moduli) != n_limbs:
+                    raise ValueError("need exactly n_limbs moduli")
+                arr = (C.c_uint64 * n_limbs)(*[int(m) for m in moduli])
+            p = _lib.dpfhe_params(log_n, n_limbs, arr)
+            rc = self._l.dpfhe_context_create(C.byref(p), int(device), C.byref(self._h))
+            if rc != 0:
+                self._h = C.c_void_p()
+                raise DpfheError(self._l.dpfhe_last_error().decode())
         self.log_n, self.L, self.N = log_n, n_limbs, 1 << log_n
         self.P = self.L * self.N
         self.device = device
@@ -82,10 +86,53 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            self._l.dpfhe_context_destroy(self._h)
+            if self._owned:
+                self._l.dpfhe_context_destroy(self._h)
             self._h = C.c_void_p()
 
     __del__ = close
+
+    def synchronize(self):
+        """waits for everything issued through this context, on whatever stream"""
+        self._chk(self._l.dpfhe_synchronize(self._h))
+
+    # ---- memory other GPUs / processes can write results into (the overlapped gather, DESIGN.md 7)
+    def device_alloc(self, n_bytes):
+        p = C.c_void_p()
+        self._chk(self._l.dpfhe_device_alloc(self._h, C.byref(p), n_bytes))
+        return p.value
+
+    def device_free(self, ptr):
+        self._chk(self._l.dpfhe_device_free(self._h, C.c_void_p(ptr)))
+
+    def ipc_export(self, ptr):
+        buf = C.create_string_buffer(64)
+        self._chk(self._l.dpfhe_ipc_export(self._h, C.c_void_p(ptr), buf))
+        return bytes(buf.raw)
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._chk(self._l.dpfhe_ipc_open(self._h, C.create_string_buffer(bytes(handle), 64), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._chk(self._l.dpfhe_ipc_close(self._h, C.c_void_p(ptr)))
+
+    # ---- host placement
+    def numa_node(self):
+        v = C.c_int(-1)
+        self._chk(self._l.dpfhe_device_numa_node(self._h, C.byref(v)))
+        return v.value
+
+    def bind_thread_near(self):
+        """restricts the calling thread to the CPUs of this GPU's NUMA node; returns the number of CPUs (0: unknown topology)"""
+        v = C.c_int(0)
+        self._chk(self._l.dpfhe_bind_thread_near(self._h, C.byref(v)))
+        return v.value
+
+    def pinned_near(self, n_words):
+        """pinned host staging memory on this GPU's NUMA node (PinnedBuffer with .array and .node)"""
+        return PinnedBuffer(n_words, near=self)
 
     def _chk(self, rc):
         if rc != 0:
@@ -201,6 +248,10 @@ class Context:
     def rotate(self, ct, galois_elt, gk, out, batch, stream=None):
         self._chk(self._l.dpfhe_rotate(self._h, _ptr(ct), int(galois_elt), _ptr(gk), _ptr(out), batch, _stream(stream)))
 
+    def rotate_steps(self, ct, k, gk, out, batch, stream=None):
+        """rotation by k slots (the Galois element 5^k mod 2N is derived by the library)"""
+        self._chk(self._l.dpfhe_rotate_steps(self._h, _ptr(ct), int(k), _ptr(gk), _ptr(out), batch, _stream(stream)))
+
     def rotate_hoisted(self, ct, galois_elts, gks, out, batch, stream=None):
         """out[r] = rotate(ct, galois_elts[r], gks[r]) for all r, sharing the digit decomposition (bit-identical to rotate);
         gks: list of device tensors, out: [n_rot][batch][2][L][N]"""
@@ -261,12 +312,20 @@ class Context:
 
 
 class PinnedBuffer:
-    """Pinned host memory from dpfhe_host_alloc, exposed as a numpy uint64 array (`.array`); freed on close()/GC."""
+    """Pinned host memory from dpfhe_host_alloc (or, with near=Context, dpfhe_host_alloc_near: pages on that GPU's NUMA
+    node, `.node` = the node or -1), exposed as a numpy uint64 array (`.array`); freed on close()/GC."""
 
-    def __init__(self, n_words):
+    def __init__(self, n_words, near=None):
         self._l = _lib.load()
         self._p = C.c_void_p()
-        if self._l.dpfhe_host_alloc(C.byref(self._p), n_words * 8) != 0:
+        self.node = -1
+        if near is not None:
+            node = C.c_int(-1)
+            rc = self._l.dpfhe_host_alloc_near(near._h, C.byref(self._p), n_words * 8, C.byref(node))
+            self.node = node.value
+        else:
+            rc = self._l.dpfhe_host_alloc(C.byref(self._p), n_words * 8)
+        if rc != 0:
             raise DpfheError(self._l.dpfhe_last_error().decode())
         self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint64)), shape=(n_words,))
 
@@ -277,6 +336,60 @@ class PinnedBuffer:
             self._p = C.c_void_p()
 
     __del__ = close
+
+
+class MultiContext:
+    """Several GPUs in one process (dpfhe_multi_*): one context per device, contiguous shards of the batch, no collective
+    while computing.  `devices`: list of CUDA device ids (a device may be listed twice), None = all visible devices."""
+
+    def __init__(self, log_n, n_limbs, moduli=None, devices=None):
+        self._l = _lib.load()
+        self._h = C.c_void_p()
+        arr = None
+        if moduli is not None:
+            arr = (C.c_uint64 * n_limbs)(*[int(m) for m in moduli])
+        p = _lib.dpfhe_params(log_n, n_limbs, arr)
+        ids = (C.c_int * len(devices))(*devices) if devices else None
+        rc = self._l.dpfhe_multi_create(C.byref(p), ids, len(devices) if devices else 0, C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise DpfheError(self._l.dpfhe_last_error().decode())
+        self.n = int(self._l.dpfhe_multi_device_count(self._h))
+        self.contexts = [Context(log_n, n_limbs, _borrowed=self._l.dpfhe_multi_context(self._h, r)) for r in range(self.n)]
+        self.devices = [int(self._l.dpfhe_context_device(c._h)) for c in self.contexts]
+        self.log_n, self.L, self.N = log_n, n_limbs, 1 << log_n
+        self.P = self.L * self.N
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            for c in self.contexts:
+                c.close()
+            self._l.dpfhe_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise DpfheError(self._l.dpfhe_last_error().decode())
+
+    def shard(self, batch, index):
+        first, count = C.c_size_t(), C.c_size_t()
+        self._chk(self._l.dpfhe_multi_shard(self._h, batch, index, C.byref(first), C.byref(count)))
+        return first.value, count.value
+
+    def ct_mul_relin_host(self, a, b, evk, out):
+        self._chk(self._l.dpfhe_multi_ct_mul_relin_host(self._h, _hptr(a), _hptr(b), _hptr(evk), _hptr(out, True), a.size // (2 * self.P)))
+
+    def rotate_host(self, ct, galois_elt, gk, out):
+        self._chk(self._l.dpfhe_multi_rotate_host(self._h, _hptr(ct), int(galois_elt), _hptr(gk), _hptr(out, True), ct.size // (2 * self.P)))
+
+    def ct_mul_relin_gather(self, a_shards, b_shards, evk_copies, out_root, root, batch):
+        """a_shards[r], b_shards[r], evk_copies[r]: device tensors / pointers on device r; out_root: [batch][2][L][N] on the
+        device of shard `root`.  Every device writes its rows of out_root directly (peer stores); synchronous."""
+        n = self.n
+        mk = lambda xs: (C.c_void_p * n)(*[_ptr(x) for x in xs])
+        self._chk(self._l.dpfhe_multi_ct_mul_relin_gather(self._h, mk(a_shards), mk(b_shards), mk(evk_copies), _ptr(out_root), int(root), batch))
 
 
 def pinned_empty(n_words):

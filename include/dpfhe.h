@@ -30,8 +30,11 @@
  *
  * Threading: a context is bound to one device and is NOT thread-safe; use one context
  * per host thread / GPU (matches the reference's one-default-stream-per-device usage).
+ * Different contexts may be used from different threads at the same time (dpfhe_multi_* does).
  * `stream` is a cudaStream_t passed as void* (NULL = the context's own stream).
- * Device-pointer entry points are asynchronous with respect to the host.
+ * Device-pointer entry points are asynchronous with respect to the host.  All calls on one context share
+ * its scratch, so the library orders them itself: a call issued on a different stream than the previous
+ * one first waits (on the device) for that previous call.  dpfhe_synchronize() waits for all of them.
  * There is no CPU fallback: without a usable CUDA device dpfhe_context_create fails.
  */
 #ifndef DPFHE_H
@@ -51,8 +54,10 @@ typedef struct dpfhe_ctx dpfhe_ctx;
 typedef struct dpfhe_params {
     uint32_t log_n;         /* N = 1 << log_n; supported: 12, 13, 14                       */
     uint32_t n_limbs;       /* L in [1, DPFHE_MAX_LIMBS]                                   */
-    const uint64_t *moduli; /* L distinct primes, 2^33 < q < 2^60, q = 1 mod 2N; NULL =    */
-                            /* derive the L largest such primes below 2^60 */
+    const uint64_t *moduli; /* L distinct primes, 2^33 < q < 2^60, q = 1 mod 2N; NULL = the */
+                            /* default basis: the L largest primes k*2^32+1 below 2^60      */
+                            /* (DESIGN.md §2.1).  Bases made only of k*2^32+1 primes run    */
+                            /* the faster kernel variant; any other basis the generic one.  */
 } dpfhe_params;
 
 enum {
@@ -76,6 +81,12 @@ int dpfhe_get_psi(const dpfhe_ctx *ctx, uint32_t limb, uint64_t *psi);
 int dpfhe_get_root_powers(const dpfhe_ctx *ctx, uint32_t limb, int inverse, uint64_t *h_out);
 /* bytes of device scratch the context holds (tables + pipeline scratch), for reporting */
 size_t dpfhe_context_device_bytes(const dpfhe_ctx *ctx);
+/* the CUDA device the context is bound to */
+int dpfhe_context_device(const dpfhe_ctx *ctx);
+/* number of CUDA devices visible to this process (0 and an error status without a driver) */
+int dpfhe_device_count(int *out);
+/* waits for everything issued through this context, on whatever stream */
+int dpfhe_synchronize(dpfhe_ctx *ctx);
 
 /* ---- transforms: d_data is [n_polys][L][N], in place ---- */
 int dpfhe_ntt_fwd(dpfhe_ctx *ctx, uint64_t *d_data, size_t n_polys, void *stream);
@@ -109,6 +120,13 @@ int dpfhe_ct_mul_plain_acc(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t 
  * out must not alias ct */
 int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk,
                  uint64_t *d_out, size_t batch, void *stream);
+
+/* rotation by k slots (k < 0: the other direction): dpfhe_rotate with the Galois element 5^k mod 2N, which
+ * dpfhe_galois_element returns (SURVEY.md §8b declared rotate with an `int k`; the Galois-element form above
+ * also covers the conjugation 2N-1) */
+int dpfhe_galois_element(const dpfhe_ctx *ctx, int k, uint64_t *galois_elt);
+int dpfhe_rotate_steps(dpfhe_ctx *ctx, const uint64_t *d_ct, int k, const uint64_t *d_gk, uint64_t *d_out,
+                       size_t batch, void *stream);
 
 /* ---- hoisted rotations: n_rot rotations of the SAME batch, out[r] = rotate(ct, galois_elts[r], gks[r]).
  *      galois_elts and d_gks are HOST arrays of n_rot entries (d_gks[r] is a device pointer to a key [L][2][L][N]);
@@ -168,7 +186,46 @@ int dpfhe_rotate_host(dpfhe_ctx *ctx, const uint64_t *h_ct, uint64_t galois_elt,
                       uint64_t *h_out, size_t batch);
 /* pinned host memory helpers so callers can reach full PCIe bandwidth */
 int dpfhe_host_alloc(void **out, size_t bytes);
-int dpfhe_host_free(void *p);
+/* the same, with the pages placed on the NUMA node of the context's GPU (what multi-GPU hosts need: DESIGN.md §7);
+ * *placed_node (may be NULL) = that node, or -1 if the placement could not be enforced */
+int dpfhe_host_alloc_near(const dpfhe_ctx *ctx, void **out, size_t bytes, int *placed_node);
+int dpfhe_host_free(void *p);   /* frees memory of either allocator */
+/* NUMA node of the context's GPU (-1: unknown), and a helper that restricts the CALLING thread to that node's CPUs */
+int dpfhe_device_numa_node(const dpfhe_ctx *ctx, int *node);
+int dpfhe_bind_thread_near(const dpfhe_ctx *ctx, int *n_cpus);
+
+/* ---- device buffers other GPUs can write into.  The output of dpfhe_ct_mul_relin / dpfhe_keyswitch / dpfhe_rotate is
+ *      written exactly once, by the kernel's final stores, so `d_out` may be memory of ANOTHER GPU: a peer-mapped
+ *      buffer of the same process (dpfhe_multi_*), or, with one process per GPU, a buffer exported by the owning
+ *      process and opened here.  That is how a multi-GPU job gathers its result while it computes. ---- */
+#define DPFHE_IPC_HANDLE_BYTES 64
+int dpfhe_device_alloc(dpfhe_ctx *ctx, void **d_out, size_t bytes);   /* a cudaMalloc of its own on the context's device */
+int dpfhe_device_free(dpfhe_ctx *ctx, void *d_ptr);
+int dpfhe_ipc_export(dpfhe_ctx *ctx, const void *d_ptr, unsigned char handle[DPFHE_IPC_HANDLE_BYTES]);
+int dpfhe_ipc_open(dpfhe_ctx *ctx, const unsigned char handle[DPFHE_IPC_HANDLE_BYTES], void **d_out);
+int dpfhe_ipc_close(dpfhe_ctx *ctx, void *d_ptr);
+
+/* ---- several GPUs in one process: one context per device, contiguous shards of the batch
+ *      (the first batch % n shards hold one ciphertext more), no collective while computing.
+ *      device_ids NULL = devices 0..n-1; n_devices <= 0 = all visible devices.  A device may be listed twice
+ *      (two logical shards on one GPU).  Contrast with the reference's one-MPI-rank-per-GPU DistributedContext,
+ *      src/core/distributed/distributed_context.cpp:242-250. ---- */
+typedef struct dpfhe_multi dpfhe_multi;
+int dpfhe_multi_create(const dpfhe_params *p, const int *device_ids, int n_devices, dpfhe_multi **out);
+void dpfhe_multi_destroy(dpfhe_multi *m);
+int dpfhe_multi_device_count(const dpfhe_multi *m);
+dpfhe_ctx *dpfhe_multi_context(dpfhe_multi *m, int index);   /* borrowed: shard `index`'s context */
+int dpfhe_multi_shard(const dpfhe_multi *m, size_t batch, int index, size_t *first, size_t *count);
+/* host buffers [batch][2][L][N]: every device pipelines its own shard (H2D, compute, D2H) — no gather needed */
+int dpfhe_multi_ct_mul_relin_host(dpfhe_multi *m, const uint64_t *h_a, const uint64_t *h_b, const uint64_t *h_evk,
+                                  uint64_t *h_out, size_t batch);
+int dpfhe_multi_rotate_host(dpfhe_multi *m, const uint64_t *h_ct, uint64_t galois_elt, const uint64_t *h_gk,
+                            uint64_t *h_out, size_t batch);
+/* device buffers: d_a[r], d_b[r] = shard r of the operands and d_evk[r] = the key, all on device r; the whole result
+ * [batch][2][L][N] is gathered on the device of shard `root` (d_out_root), written there directly by every device's
+ * kernel through NVLink while it computes.  Synchronous. */
+int dpfhe_multi_ct_mul_relin_gather(dpfhe_multi *m, const uint64_t *const *d_a, const uint64_t *const *d_b,
+                                    const uint64_t *const *d_evk, uint64_t *d_out_root, int root, size_t batch);
 
 /* ---- diagnostics ---- */
 /* number of kernel launches issued through this context since creation */
