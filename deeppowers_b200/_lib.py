@@ -45,6 +45,7 @@ SYMBOLS = {
     "dpfhe_ct_mul_relin_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "dpfhe_ct_mul_plain_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "dpfhe_rotate_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dpfhe_context_trim": (C.c_int, [C.c_void_p]),
     "dpfhe_context_device": (C.c_int, [C.c_void_p]),
     "dpfhe_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "dpfhe_synchronize": (C.c_int, [C.c_void_p]),

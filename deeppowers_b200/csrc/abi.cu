@@ -46,6 +46,13 @@ namespace {
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// byte ranges [a, a + na) and [b, b + nb) intersect (unified addressing: valid across devices too)
+bool overlaps(const void *a, size_t na, const void *b, size_t nb) {
+    if (!a || !b || !na || !nb) return false;
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(a), b0 = reinterpret_cast<uintptr_t>(b);
+    return a0 < b0 + nb && b0 < a0 + na;
+}
+
 int enter(const dpfhe_ctx *ctx) {
     if (!ctx) return fail(DPFHE_ERR_INVALID, "null context");
     CU_TRY(cudaSetDevice(ctx->lc.device));
@@ -70,7 +77,9 @@ void note_launch(dpfhe_ctx *ctx, uint64_t n) {
 }
 
 int ensure_staging(dpfhe_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t key_bytes) {
+    // a size is only recorded once every buffer of its group exists: a failed cudaMalloc leaves the group marked empty
     if (in_bytes > ctx->stage_in_bytes) {
+        ctx->stage_in_bytes = 0;
         for (int k = 0; k < PIPE_DEPTH; ++k) {
             if (ctx->stage_in[k]) cudaFree(ctx->stage_in[k]);
             ctx->stage_in[k] = nullptr;
@@ -79,6 +88,7 @@ int ensure_staging(dpfhe_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t key
         ctx->stage_in_bytes = in_bytes;
     }
     if (out_bytes > ctx->stage_out_bytes) {
+        ctx->stage_out_bytes = 0;
         for (int k = 0; k < PIPE_DEPTH; ++k) {
             if (ctx->stage_out[k]) cudaFree(ctx->stage_out[k]);
             ctx->stage_out[k] = nullptr;
@@ -87,6 +97,7 @@ int ensure_staging(dpfhe_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t key
         ctx->stage_out_bytes = out_bytes;
     }
     if (key_bytes > ctx->stage_key_bytes) {
+        ctx->stage_key_bytes = 0;
         if (ctx->stage_key) cudaFree(ctx->stage_key);
         ctx->stage_key = nullptr;
         CU_TRY(cudaMalloc(&ctx->stage_key, key_bytes));
@@ -99,8 +110,8 @@ int ensure_staging(dpfhe_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t key
 //   upload(chunk -> stage_in[slot]) on s_h2d, compute on ctx->stream, download(stage_out[slot]) on s_d2h.
 // in_item_bytes / out_item_bytes are per item; h_in may be two arrays (a and b) laid out back to back in the stage.
 template <class Compute>
-int run_pipeline(dpfhe_ctx *ctx, const u64 *h_in0, const u64 *h_in1, u64 *h_out, size_t n_items, size_t in_item_words,
-                 size_t out_item_words, size_t chunk_items, Compute compute) {
+int run_pipeline_body(dpfhe_ctx *ctx, const u64 *h_in0, const u64 *h_in1, u64 *h_out, size_t n_items, size_t in_item_words,
+                      size_t out_item_words, size_t chunk_items, Compute compute) {
     const size_t n_in = h_in1 ? 2 : 1;
     int rc = ensure_staging(ctx, n_in * chunk_items * in_item_words * 8, chunk_items * out_item_words * 8, 0);
     if (rc) return rc;
@@ -126,6 +137,23 @@ int run_pipeline(dpfhe_ctx *ctx, const u64 *h_in0, const u64 *h_in1, u64 *h_out,
     CU_TRY(cudaStreamSynchronize(ctx->s_d2h));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     return DPFHE_OK;
+}
+
+// runs the pipeline; on failure the three streams are drained before returning, so that no copy is still reading or writing
+// the caller's host buffers (or the staging slots) when the error is reported
+template <class Compute>
+int run_pipeline(dpfhe_ctx *ctx, const u64 *h_in0, const u64 *h_in1, u64 *h_out, size_t n_items, size_t in_item_words,
+                 size_t out_item_words, size_t chunk_items, Compute compute) {
+    const int rc = run_pipeline_body(ctx, h_in0, h_in1, h_out, n_items, in_item_words, out_item_words, chunk_items, compute);
+    if (rc != DPFHE_OK) {
+        const std::string why = g_err;   // the drains below must not replace the message of the failure
+        cudaStreamSynchronize(ctx->s_h2d);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->s_d2h);
+        cudaGetLastError();
+        g_err = why;
+    }
+    return rc;
 }
 
 size_t pick_chunk(const dpfhe_ctx *ctx, size_t item_bytes, size_t n_items) {
@@ -228,8 +256,20 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     lc.itw = ctx->d_itw;
     // digit-exchange scratch for the fused key-switch kernel: one slot per resident CTA, two parities
     lc.ks_slots = (size_t)lc.num_sms * 4;
-    CTX_TRY(cudaMalloc(&lc.ks_scratch, lc.ks_slots * 2 * N * 8));
-    CTX_TRY(cudaMalloc(&lc.ks_acc, lc.ks_slots * 2 * N * 8));
+    // digit slots and accumulator rows: ONE allocation, so that a single L2 access-policy window can cover the whole
+    // cross-phase working set of the fused kernel (launch_ks_t)
+    CTX_TRY(cudaMalloc(&lc.ks_scratch, 2 * lc.ks_slots * 2 * N * 8));
+    lc.ks_acc = lc.ks_scratch + lc.ks_slots * 2 * N;
+    lc.ks_window_bytes = 2 * lc.ks_slots * 2 * N * 8;
+    {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device_id);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device_id);
+        lc.l2_persist_max = (size_t)(max_persist > 0 ? max_persist : 0);
+        if ((size_t)max_window < lc.ks_window_bytes) lc.ks_window_bytes = (size_t)(max_window > 0 ? max_window : 0);
+        if (const char *env = getenv("DPFHE_L2_PERSIST")) lc.l2_persist = atoi(env);
+        if (lc.l2_persist && lc.l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lc.l2_persist_max);
+    }
     CTX_TRY(cudaMalloc(&lc.ks_key_s, 2 * L * L * N * 8));
     ctx->device_bytes += 2 * L * L * N * 8;
     CTX_TRY(cudaMalloc(&lc.ks_flags, lc.ks_slots * sizeof(u32)));
@@ -255,8 +295,7 @@ void dpfhe_context_destroy(dpfhe_ctx *ctx) {
     cudaFree(ctx->d_lp);
     cudaFree(ctx->d_tw);
     cudaFree(ctx->d_itw);
-    cudaFree(ctx->lc.ks_scratch);
-    cudaFree(ctx->lc.ks_acc);
+    cudaFree(ctx->lc.ks_scratch);   // ks_acc is the second half of the same allocation
     cudaFree(ctx->lc.ks_acc_hyb);
     cudaFree(ctx->lc.ks_flags);
     cudaFree(ctx->lc.ks_key_s);
@@ -302,7 +341,33 @@ int dpfhe_get_root_powers(const dpfhe_ctx *ctx, uint32_t limb, int inverse, uint
     return DPFHE_OK;
 }
 size_t dpfhe_context_device_bytes(const dpfhe_ctx *ctx) {
-    return ctx ? ctx->device_bytes + PIPE_DEPTH * (ctx->stage_in_bytes + ctx->stage_out_bytes) + ctx->stage_key_bytes : 0;
+    if (!ctx) return 0;
+    const size_t P8 = ctx->P() * 8, L = ctx->hp.L;
+    size_t n = ctx->device_bytes;                                                    // tables, key companions, digit slots, accumulators, flags (+ hybrid rows)
+    n += PIPE_DEPTH * (ctx->stage_in_bytes + ctx->stage_out_bytes) + ctx->stage_key_bytes;   // host-entry staging
+    n += ctx->ms_tau_bytes;                                                          // modulus-switch scratch
+    n += ctx->hoist_chunk * (L * P8 + sizeof(u32));                                  // hoisted rotations: shared transforms + zero flags
+    if (ctx->hoist_M) n += 3 * P8 + L * L * 8;                                       //   per-rotation constants
+    if (ctx->lc.ks_prof) n += ctx->lc.ks_slots * 16 * sizeof(unsigned long long);
+    return n;
+}
+
+// frees the scratch that grows with use (hoisted-rotation transforms, modulus-switch rows, host staging); it comes back on demand
+int dpfhe_context_trim(dpfhe_ctx *ctx) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    rc = dpfhe_synchronize(ctx);
+    if (rc) return rc;
+    cudaFree(ctx->hoist_U); cudaFree(ctx->hoist_zero); cudaFree(ctx->ms_tau); cudaFree(ctx->stage_key);
+    ctx->hoist_U = nullptr; ctx->hoist_zero = nullptr; ctx->hoist_chunk = 0;
+    ctx->ms_tau = nullptr; ctx->ms_tau_bytes = 0;
+    ctx->stage_key = nullptr; ctx->stage_key_bytes = 0;
+    for (int k = 0; k < PIPE_DEPTH; ++k) {
+        cudaFree(ctx->stage_in[k]); cudaFree(ctx->stage_out[k]);
+        ctx->stage_in[k] = ctx->stage_out[k] = nullptr;
+    }
+    ctx->stage_in_bytes = ctx->stage_out_bytes = 0;
+    return DPFHE_OK;
 }
 uint64_t dpfhe_launch_count(const dpfhe_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
@@ -372,7 +437,11 @@ static int ks_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const uint64_t
         const uint64_t two_n = (uint64_t)2 << ctx->hp.log_n;
         if (!(galois & 1) || galois >= two_n) return fail(DPFHE_ERR_INVALID, "galois element must be odd and < 2N");
     }
-    if (out == a || out == b) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
+    {   // the output rows are written while other work items still read their inputs: no overlap at all, not only out == in
+        const size_t ct_bytes = 2 * ctx->P() * 8, in_bytes = batch * (mode == KS_PLAIN ? ct_bytes / 2 : ct_bytes);
+        if (overlaps(out, batch * ct_bytes, a, in_bytes) || overlaps(out, batch * ct_bytes, b, in_bytes))
+            return fail(DPFHE_ERR_INVALID, "output must not overlap an input");
+    }
     CU_TRY(VCALL(launch_ks, ctx->lc, mode, a, b, key, out, batch, (u32)galois, pick(ctx, stream)));
     note_launch(ctx, 2);   // key_prepare_kernel + ks_fused_kernel
     return DPFHE_OK;
@@ -405,7 +474,11 @@ static int ks_hybrid_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const u
         const uint64_t two_n = (uint64_t)2 << ctx->hp.log_n;
         if (!(galois & 1) || galois >= two_n) return fail(DPFHE_ERR_INVALID, "galois element must be odd and < 2N");
     }
-    if (out == a || out == b) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
+    {
+        const size_t ct_bytes = 2 * (size_t)(L - 1) * ctx->N() * 8, in_bytes = batch * (mode == KS_PLAIN ? ct_bytes / 2 : ct_bytes);
+        if (overlaps(out, batch * ct_bytes, a, in_bytes) || overlaps(out, batch * ct_bytes, b, in_bytes))
+            return fail(DPFHE_ERR_INVALID, "output must not overlap an input");
+    }
     if (!ctx->lc.ks_hyb) {
         u64 *hyb = nullptr;
         const size_t hyb_bytes = (ctx->lc.ks_slots / 2 + 1) * KS_HYB_ROWS * ctx->N() * sizeof(u64), acc_bytes = ctx->lc.ks_slots * 4 * ctx->N() * sizeof(u64);
@@ -449,9 +522,8 @@ int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, con
     for (size_t r = 0; r < n_rot; ++r) {
         if (!(galois_elts[r] & 1) || galois_elts[r] >= two_n) return fail(DPFHE_ERR_INVALID, "galois element must be odd and < 2N");
         if (!d_gks[r] || !aligned16(d_gks[r])) return fail(DPFHE_ERR_INVALID, "null or misaligned Galois key");
-        const uint64_t *o = d_out + r * batch * 2 * P;
-        if (o == d_ct) return fail(DPFHE_ERR_INVALID, "output must not alias the input");
     }
+    if (overlaps(d_out, n_rot * batch * 2 * P * 8, d_ct, batch * 2 * P * 8)) return fail(DPFHE_ERR_INVALID, "output must not overlap the input");
     cudaStream_t st = pick(ctx, stream);
     // scratch: at most ~4 GiB of shared transforms at a time (the batch is processed in chunks of that many ciphertexts)
     const size_t per_ct = L * L * N * sizeof(u64);
@@ -533,7 +605,8 @@ int dpfhe_ct_mul_plain_inner(dpfhe_ctx *ctx, const uint64_t *d_steps, size_t n_s
     CHECK_PTR(d_steps); CHECK_PTR(d_pts); CHECK_PTR(d_out);
     if (n_steps == 0 || n_steps > 128) return fail(DPFHE_ERR_INVALID, "n_steps must be in [1, 128]");
     if (n_groups > 65535) return fail(DPFHE_ERR_INVALID, "n_groups must be below 65536");
-    if (d_out == d_steps) return fail(DPFHE_ERR_INVALID, "output must not alias an input");
+    if (overlaps(d_out, n_groups * batch * 2 * ctx->P() * 8, d_steps, n_steps * batch * 2 * ctx->P() * 8))
+        return fail(DPFHE_ERR_INVALID, "output must not overlap an input");
     unsigned launches = 0;
     CU_TRY(VCALL(launch_pt_inner, ctx->lc, d_steps, (u32)n_steps, d_pts, (u32)n_groups, d_out, batch, pick(ctx, stream), &launches));
     note_launch(ctx, launches);
@@ -547,7 +620,8 @@ int dpfhe_mod_switch_down(dpfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out,
     CHECK_PTR(d_in); CHECK_PTR(d_out);
     const unsigned L = ctx->hp.L;
     if (L < 2) return fail(DPFHE_ERR_INVALID, "mod_switch_down needs at least two limbs");
-    if (d_in == d_out) return fail(DPFHE_ERR_INVALID, "output must not alias the input");
+    if (overlaps(d_out, n_polys * (size_t)(L - 1) * ctx->N() * 8, d_in, n_polys * ctx->P() * 8))
+        return fail(DPFHE_ERR_INVALID, "output must not overlap the input");
     const uint64_t ql = ctx->hp.limbs[L - 1].lp.q;
     if (t_plain >= ql || (t_plain && t_plain % ql == 0)) return fail(DPFHE_ERR_INVALID, "plaintext modulus must be below the dropped modulus");
     const size_t need = n_polys * ctx->N() * 8;

@@ -641,7 +641,30 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
     u64 *mail = lc.ks_mail;
     u32 pf_dist = (u32)lc.ks_prefetch;
     void *params[] = {&args, &lt, &batch_arg, &flags, &epoch, &ticket, &mail, &prof, &pf_dist};
-    e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)G), dim3(NT), params, smem, st);
+    if (lc.l2_persist && lc.l2_persist_max && lc.ks_window_bytes) {
+        // tuning (DPFHE_L2_PERSIST): the digit slots and accumulator rows are re-read within microseconds, the ciphertext
+        // streams never; a persisting access-policy window over the scratch keeps the streams from evicting it
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)G);
+        cfg.blockDim = dim3(NT);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[1].val.accessPolicyWindow.base_ptr = lc.ks_scratch;
+        attr[1].val.accessPolicyWindow.num_bytes = lc.ks_window_bytes;
+        const double ratio = (double)lc.l2_persist_max / (double)lc.ks_window_bytes;
+        attr[1].val.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+        attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
+        e = cudaLaunchKernelExC(&cfg, (const void *)kern, params);
+    } else {
+        e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)G), dim3(NT), params, smem, st);
+    }
     lc.ks_epoch += rounds;
     return e;
 }

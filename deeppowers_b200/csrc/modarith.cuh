@@ -47,12 +47,15 @@ DPFHE_HD u64 mul_wide(u32 a, u32 b) {
 }
 
 // hi64(x * y) minus 0, 1 or 2.  Three IMAD.WIDE: the low partial product xl*yl only matters through a carry (<= 1) and
-// so does the sum of the low words of the two middle products (<= 1).  The 33-bit sum of the middle products' high
-// words is formed first (IADD3 + IADD3.X into a register pair) and enters the top product as its 64-bit addend.
+// so does the sum of the low words of the two middle products (<= 1).
 DPFHE_HD u64 mulhi_approx(u64 x, u64 y) {
 #if DPFHE_SHOUP_APPROX == 0
     return umulhi64(x, y);
 #else
+    // Written with plain sums on purpose.  Pinning the shape in one asm block (no register-pair moves, 21.7 instead of 21.4
+    // instructions per butterfly but fewer of them on the multiplier pipe) measured 1-3 % SLOWER, and so did keeping the
+    // carry additions off IMAD.X with an opaque third addend: ptxas' own split of the adds and moves between the ALU and
+    // the multiplier pipe is the better one — both pipes are close to full (profiles/r02).
     const u32 xl = (u32)x, xh = (u32)(x >> 32), yl = (u32)y, yh = (u32)(y >> 32);
     const u64 a = mul_wide(xh, yl), b = mul_wide(xl, yh);
     const u64 m = (u64)(u32)(a >> 32) + (u32)(b >> 32);

@@ -9,9 +9,13 @@ _HDR = struct.Struct("<8sIIIIQ16Q")
 
 
 def payload_words(log_n, n_limbs, kind, count):
+    if not (1 <= log_n <= 17 and 1 <= n_limbs <= 16):
+        raise ValueError("bad parameters")
+    if kind not in (CIPHERTEXTS, SWITCH_KEY, PLAINTEXTS, HYBRID_SWITCH_KEY):
+        raise ValueError("unknown kind")
     poly = (1 << log_n) * n_limbs
     return {CIPHERTEXTS: count * 2 * poly, SWITCH_KEY: 2 * n_limbs * poly, PLAINTEXTS: count * poly,
-            HYBRID_SWITCH_KEY: 2 * max(n_limbs - 1, 0) * poly}[kind]
+            HYBRID_SWITCH_KEY: 2 * (n_limbs - 1) * poly}[kind]
 
 
 def write(path, log_n, n_limbs, kind, count, moduli, payload, form=1):
@@ -33,6 +37,10 @@ def read(path):
         if magic != MAGIC:
             raise ValueError("not a DPFHEv1 file")
         words = payload_words(log_n, n_limbs, kind, count)
+        f.seek(0, 2)
+        if f.tell() != _HDR.size + 8 * words:      # the header is untrusted: it must describe exactly this file
+            raise ValueError("file size does not match the header")
+        f.seek(_HDR.size)
         data = np.frombuffer(f.read(words * 8), dtype="<u8")
         if data.size != words:
             raise ValueError("truncated payload")

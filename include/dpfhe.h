@@ -81,6 +81,8 @@ int dpfhe_get_psi(const dpfhe_ctx *ctx, uint32_t limb, uint64_t *psi);
 int dpfhe_get_root_powers(const dpfhe_ctx *ctx, uint32_t limb, int inverse, uint64_t *h_out);
 /* bytes of device scratch the context holds (tables + pipeline scratch), for reporting */
 size_t dpfhe_context_device_bytes(const dpfhe_ctx *ctx);
+/* releases the scratch that grows with use (up to 4 GiB of hoisted-rotation transforms, host staging, ...) */
+int dpfhe_context_trim(dpfhe_ctx *ctx);
 /* the CUDA device the context is bound to */
 int dpfhe_context_device(const dpfhe_ctx *ctx);
 /* number of CUDA devices visible to this process (0 and an error status without a driver) */

@@ -39,13 +39,21 @@ struct WireHeader {
 };
 static_assert(sizeof(WireHeader) == 160, "wire header must be 160 bytes");
 
+// words of payload a header announces; throws on an unknown kind, bad parameters or a count whose byte size does not fit
+// size_t (a header is untrusted input: the count of a file must never be able to wrap the size computation)
 inline std::size_t wire_payload_words(const WireHeader &h) {
-    const std::size_t poly = (std::size_t(1) << h.log_n) * h.n_limbs;
+    if (h.log_n < 1 || h.log_n > 17 || h.n_limbs < 1 || h.n_limbs > 16) throw std::runtime_error("dpfhe wire: bad parameters");
+    const std::size_t poly = (std::size_t(1) << h.log_n) * h.n_limbs;   // <= 2^21 words
+    const std::size_t max_words = static_cast<std::size_t>(-1) / 8;
+    auto checked = [&](std::uint64_t count, std::size_t per_item) -> std::size_t {
+        if (count > max_words / per_item) throw std::runtime_error("dpfhe wire: count does not fit in memory");
+        return static_cast<std::size_t>(count) * per_item;
+    };
     switch (static_cast<WireKind>(h.kind)) {
-        case WireKind::Ciphertexts: return h.count * 2 * poly;
+        case WireKind::Ciphertexts: return checked(h.count, 2 * poly);
         case WireKind::SwitchKey: return std::size_t(2) * h.n_limbs * poly;
-        case WireKind::Plaintexts: return h.count * poly;
-        case WireKind::HybridSwitchKey: return h.n_limbs ? std::size_t(2) * (h.n_limbs - 1) * poly : 0;
+        case WireKind::Plaintexts: return checked(h.count, poly);
+        case WireKind::HybridSwitchKey: return std::size_t(2) * (h.n_limbs - 1) * poly;
     }
     throw std::runtime_error("dpfhe wire: unknown kind");
 }
@@ -72,22 +80,31 @@ inline void write_wire_file(const std::string &path, const WireHeader &h, const 
     if (!ok) throw std::runtime_error("dpfhe wire: short write to " + path);
 }
 
+// Reads a whole file.  The header is validated before anything is sized from it: the payload the header announces must be
+// exactly what the file holds (so a forged count can neither wrap the size computation nor make the caller trust more
+// items than were read), and the file is closed on every path.
 inline WireHeader read_wire_file(const std::string &path, std::vector<std::uint64_t> &payload) {
-    std::FILE *f = std::fopen(path.c_str(), "rb");
-    if (!f) throw std::runtime_error("dpfhe wire: cannot open " + path);
+    struct Closer {
+        std::FILE *f;
+        ~Closer() { if (f) std::fclose(f); }
+    } file{std::fopen(path.c_str(), "rb")};
+    if (!file.f) throw std::runtime_error("dpfhe wire: cannot open " + path);
     WireHeader h;
-    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "DPFHEv1", 8) != 0) {
-        std::fclose(f);
+    if (std::fread(&h, sizeof(h), 1, file.f) != 1 || std::memcmp(h.magic, "DPFHEv1", 8) != 0)
         throw std::runtime_error("dpfhe wire: " + path + " is not a DPFHEv1 file");
+    std::size_t words = 0;
+    try {
+        words = wire_payload_words(h);
+    } catch (const std::runtime_error &e) {
+        throw std::runtime_error(std::string(e.what()) + " in " + path);
     }
-    if (h.log_n < 1 || h.log_n > 17 || h.n_limbs < 1 || h.n_limbs > 16) {
-        std::fclose(f);
-        throw std::runtime_error("dpfhe wire: bad parameters in " + path);
-    }
-    payload.resize(wire_payload_words(h));
-    const bool ok = std::fread(payload.data(), 8, payload.size(), f) == payload.size();
-    std::fclose(f);
-    if (!ok) throw std::runtime_error("dpfhe wire: truncated payload in " + path);
+    if (std::fseek(file.f, 0, SEEK_END) != 0) throw std::runtime_error("dpfhe wire: cannot seek in " + path);
+    const long end = std::ftell(file.f);
+    if (end < 0 || static_cast<unsigned long long>(end) != sizeof(h) + 8ull * words)
+        throw std::runtime_error("dpfhe wire: size of " + path + " does not match its header");
+    if (std::fseek(file.f, static_cast<long>(sizeof(h)), SEEK_SET) != 0) throw std::runtime_error("dpfhe wire: cannot seek in " + path);
+    payload.resize(words);
+    if (std::fread(payload.data(), 8, words, file.f) != words) throw std::runtime_error("dpfhe wire: truncated payload in " + path);
     return h;
 }
 

@@ -170,6 +170,9 @@ private:
         for (unsigned l = 0; l < ev.limbs(); ++l)
             if (ha.moduli[l] != ev.modulus(l) || hb.moduli[l] != ev.modulus(l) || hk.moduli[l] != ev.modulus(l))
                 throw std::runtime_error("fhe job: moduli differ from the evaluator's");
+        const std::size_t ct_words = 2 * ev.limbs() * ev.poly_degree();
+        if (a.size() != ha.count * ct_words || b.size() != a.size() || k.size() != std::size_t(2) * ev.limbs() * ev.limbs() * ev.poly_degree())
+            throw std::runtime_error("fhe job: payload sizes do not match the headers");
         std::vector<std::uint64_t> out(a.size());
         ev.multiply_relin({a.data(), (std::size_t)ha.count}, {b.data(), (std::size_t)ha.count}, k.data(), {out.data(), (std::size_t)ha.count});
         fhe::write_wire_file(fo, ha, out.data());
@@ -205,7 +208,10 @@ inline bool cuda_available() {
         return false;
     }
 }
-inline size_t cuda_device_count() { return cuda_available() ? 1 : 0; }
+inline size_t cuda_device_count() {
+    int n = 0;
+    return dpfhe_device_count(&n) == 0 && n > 0 ? (size_t)n : 0;
+}
 
 }  // namespace api
 }  // namespace deeppowers

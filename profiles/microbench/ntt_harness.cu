@@ -1,7 +1,7 @@
 // ntt_harness.cu — times the library's own forward / inverse limb transforms (kernel_bodies.cuh) for one arithmetic
 // variant selected at compile time (-DDPFHE_FAST=0|1 -DDPFHE_SHOUP_APPROX=0|1|2), checked against a plain host NTT.
 // Build (from the repo root):
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DDPFHE_FAST=1 -DDPFHE_SHOUP_APPROX=2 -I deeppowers_b200/csrc \
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DDPFHE_FAST=1 -I deeppowers_b200/csrc \
 //        profiles/microbench/ntt_harness.cu deeppowers_b200/csrc/host_params.cpp -o profiles/microbench/ntt_f1_a2
 #include <cstdio>
 #include <vector>
@@ -9,8 +9,7 @@
 #include "host_params.hpp"
 #include "kernel_bodies.cuh"
 using namespace dpfhe;
-
-struct LimbTable { LimbParams lp[16]; };
+using namespace dpfhe::DPFHE_VNS;
 
 template <int NT>
 struct DevCta {

@@ -76,3 +76,52 @@ def test_model_api_encrypted_route_matches_oracle(tmp_path, oracle_mod):
     hdr, data = wire.read(fo)
     assert hdr["count"] == B and hdr["kind"] == wire.CIPHERTEXTS
     assert np.array_equal(data.reshape(a.shape), o.ct_mul_relin(a, b, evk))
+
+
+def test_wire_reader_rejects_forged_headers(tmp_path, oracle_mod):
+    """A header is untrusted input: a count that wraps the size computation, a count larger than the file, an
+    unknown kind or trailing bytes must all be refused by the C++ reader the shim uses (include/dpfhe_wire.hpp)."""
+    import struct
+    from deeppowers_b200 import wire
+    o = oracle_mod.Oracle(12, 1)
+    ct = o.fill_uniform(5, 2).reshape(1, 2, 1, o.N)
+    good = str(tmp_path / "good.dpfhe")
+    wire.write(good, 12, 1, wire.CIPHERTEXTS, 1, o.moduli, ct)
+    raw = open(good, "rb").read()
+
+    def forged(name, count=None, kind=None, extra=b""):
+        hdr = list(wire._HDR.unpack(raw[:160]))
+        if count is not None:
+            hdr[5] = count
+        if kind is not None:
+            hdr[3] = kind
+        path = str(tmp_path / name)
+        with open(path, "wb") as f:
+            f.write(wire._HDR.pack(*hdr) + raw[160:] + extra)
+        return path
+
+    bad = [forged("wrap.dpfhe", count=(1 << 48) + 1), forged("big.dpfhe", count=2), forged("kind.dpfhe", kind=9),
+           forged("tail.dpfhe", extra=b"\0" * 8), forged("huge.dpfhe", count=(1 << 64) - 1)]
+    for path in bad:
+        with pytest.raises(ValueError):
+            wire.read(path)
+    src = tmp_path / "rd.cpp"
+    src.write_text("""
+#include "dpfhe_wire.hpp"
+#include <iostream>
+int main(int argc, char **argv) {
+    using namespace deeppowers::api::fhe;
+    int refused = 0;
+    for (int i = 1; i < argc; ++i) {
+        std::vector<std::uint64_t> payload;
+        try { WireHeader h = read_wire_file(argv[i], payload); std::cout << "accepted " << argv[i] << " count " << h.count << " words " << payload.size() << "\\n"; }
+        catch (const std::runtime_error &e) { ++refused; }
+    }
+    std::cout << "refused " << refused << "\\n";
+    return 0;
+}
+""")
+    exe = str(tmp_path / "rd")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe])
+    out = subprocess.run([exe, good] + bad, capture_output=True, text=True, check=True).stdout
+    assert "accepted " + good in out and "refused %d" % len(bad) in out, out
