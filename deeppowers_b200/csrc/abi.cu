@@ -274,6 +274,9 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     ctx->device_bytes += 2 * L * L * N * 8;
     CTX_TRY(cudaMalloc(&lc.ks_flags, lc.ks_slots * sizeof(u32)));
     CTX_TRY(cudaMemset(lc.ks_flags, 0, lc.ks_slots * sizeof(u32)));
+    CTX_TRY(cudaMalloc(&lc.ks_consumed, lc.ks_slots * sizeof(u32)));
+    CTX_TRY(cudaMemset(lc.ks_consumed, 0, lc.ks_slots * sizeof(u32)));
+    if (const char *env = getenv("DPFHE_KS_SINGLE")) lc.ks_single = atoi(env);
     CTX_TRY(cudaMalloc(&lc.ks_ticket, 64));
     CTX_TRY(cudaMalloc(&lc.ks_mail, lc.ks_slots * sizeof(u64)));
     CTX_TRY(cudaMemset(lc.ks_mail, 0, lc.ks_slots * sizeof(u64)));
@@ -298,6 +301,7 @@ void dpfhe_context_destroy(dpfhe_ctx *ctx) {
     cudaFree(ctx->lc.ks_scratch);   // ks_acc is the second half of the same allocation
     cudaFree(ctx->lc.ks_acc_hyb);
     cudaFree(ctx->lc.ks_flags);
+    cudaFree(ctx->lc.ks_consumed);
     cudaFree(ctx->lc.ks_key_s);
     cudaFree(ctx->lc.ks_ticket);
     cudaFree(ctx->lc.ks_mail);

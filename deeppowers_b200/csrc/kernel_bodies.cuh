@@ -53,8 +53,20 @@ DPFHE_HD void st_stream(U64x2 *p, const U64x2 &v) {
     *p = v;
 #endif
 }
+#if defined(__CUDA_ARCH__) && defined(DPFHE_L2_KEEP)
+// tuning variant: cross-CTA scratch marked evict-last in L2 (measured: no fewer write-backs, profiles/r02)
+__device__ __forceinline__ u64 l2_keep_policy() {
+    u64 pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+#endif
 DPFHE_HD U64x2 ld_cg(const U64x2 *p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(DPFHE_L2_KEEP)
+    U64x2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(l2_keep_policy()) : "memory");
+    return v;
+#elif defined(__CUDA_ARCH__)
     U64x2 v;
     asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
     return v;
@@ -63,7 +75,9 @@ DPFHE_HD U64x2 ld_cg(const U64x2 *p) {
 #endif
 }
 DPFHE_HD void st_cg(U64x2 *p, const U64x2 &v) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(DPFHE_L2_KEEP)
+    asm volatile("st.global.cg.L2::cache_hint.v2.u64 [%0], {%1,%2}, %3;" ::"l"(p), "l"(v.x), "l"(v.y), "l"(l2_keep_policy()) : "memory");
+#elif defined(__CUDA_ARCH__)
     asm volatile("st.global.cg.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 #else
     *p = v;
@@ -269,9 +283,12 @@ DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only,
     }
 }
 
+// slot_free / slot_free_target: when non-null, the digit slot is single-buffered and may only be overwritten once the counter has
+// reached the target (every reader of the previous digit has signalled); cta.wait_ge spins on it (a no-op in the host emulator,
+// whose sequential order already guarantees it).
 template <int LOGN, int NT, int MODE, bool HYB = false, class CTA>
 DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot, u64 *acc_rows, u64 pm = 0,
-                        u64 pm_s = 0) {
+                        u64 pm_s = 0, const u32 *slot_free = nullptr, u32 slot_free_target = 0) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     static_assert((NC / NT) % 2 == 0, "chunk loops may be unrolled by two (ping-pong operand buffers)");
     const size_t P = (size_t)A.L * N, PK = HYB ? (size_t)A.Lk * N : P;
@@ -326,6 +343,7 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
         if (only) return;   // no other digit needs t
         inv_passes<LOGN, NT>(cta, buf, itw, p);
         cta.mark(1);   // inverse register passes
+        if (slot_free) cta.wait_ge(slot_free, slot_free_target);
         cta.par([&](int tid) {
             inv_store_stage<LOGN, NT>(buf, itw, p, tid, [&](int c, const U64x2 &v) { st_cg(dst + c, v); });
         });
@@ -341,6 +359,7 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
             if (only) continue;
             inv_passes_blk<LOGN, NT, 2>(cta, buf, itw, p, 2 * h);
             cta.mark(1);
+            if (slot_free && h == 0) cta.wait_ge(slot_free, slot_free_target);
             cta.par([&](int tid) {
                 for (int lc = tid; lc < HC; lc += NT) st_cg(dst + h * HC + lc, reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lc)]);
             });

@@ -35,6 +35,15 @@ struct DevCta {
         f((int)threadIdx.x);
         __syncthreads();
     }
+    // blocks the CTA until the monotone counter *flag has reached `target` (wrap-safe comparison)
+    __device__ __forceinline__ void wait_ge(const u32 *flag, u32 target) {
+        if (threadIdx.x == 0) {
+            u32 v;
+            do asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            while ((int)(v - target) < 0);
+        }
+        __syncthreads();
+    }
     template <class F>
     __device__ __forceinline__ void par_dom(F f) {
         f((int)threadIdx.x);
@@ -129,7 +138,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, u32 bytes) {
 // alternate over the rounds that actually run.
 template <int LOGN, int NT, int MINB, int MODE, bool PROF, bool FILTER = false>
 __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __grid_constant__ LimbTable lt, size_t batch, u32 *flags, u32 epoch,
-                                                            u32 *ticket, u64 *mail, unsigned long long *prof, u32 pf_dist) {
+                                                            u32 *ticket, u64 *mail, unsigned long long *prof, u32 pf_dist, u32 *consumed) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr size_t N = (size_t)1 << LOGN;
     u64 *buf = reinterpret_cast<u64 *>(smem_raw);
@@ -145,6 +154,15 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
     const u32 L = A.L, slot = blockIdx.x, i = slot % L, group = slot / L;
     const LimbParams &p = lt.lp[i];
     u32 executed = 0;
+    // Single-buffered digit slots (consumed != nullptr): slot s holds ONE digit; its owner may overwrite it only after the L-1
+    // siblings that read the previous digit have signalled.  The counters are monotone across launches: the value found at
+    // kernel start is the base (no reader of an earlier launch is still running).  One slot per CTA instead of two keeps
+    // 28 MB (N = 8192, 444 CTAs) of the kernel's cross-phase working set out of the L2.
+    __shared__ u32 s_base;
+    if (consumed && threadIdx.x == 0) s_base = ld_acquire_u32(consumed + slot);
+    __syncthreads();
+    const u32 consumed_base = consumed ? s_base : 0u;
+    u32 published = 0;   // digits this CTA has published in this launch
     for (u32 round = 0;; ++round) {
         if (!FILTER && threadIdx.x == 0) {
             const u32 tag = epoch + round + 1;
@@ -182,9 +200,12 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
                 }
             }
         }
-        const u32 parity = (FILTER ? executed++ : round) & 1u;
+        const u32 parity = consumed ? 0u : (FILTER ? executed++ : round) & 1u;
+        const size_t slot_stride = consumed ? 1 : 2;      // digit slots per CTA
         u64 *acc_rows = A.acc + (size_t)slot * 2 * N;   // this CTA's two lazy accumulator rows (L2 resident, reused every round)
-        ks_phase1<LOGN, NT, MODE>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N, acc_rows);
+        ks_phase1<LOGN, NT, MODE>(cta, buf, A, p, ct, i, A.scratch + ((size_t)slot * slot_stride + parity) * N, acc_rows, 0, 0,
+                                  consumed && L > 1 ? consumed + slot : nullptr, consumed_base + published * (L - 1));
+        ++published;
         if (L > 1) {
             __threadfence();
             __syncthreads();
@@ -197,7 +218,12 @@ __global__ void __launch_bounds__(NT, MINB) ks_fused_kernel(KsArgs A, const __gr
                 }
                 __syncthreads();
                 cta.mark(3);   // waiting for the sibling's digit
-                ks_phase2_digit<LOGN, NT>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)sib * 2 + parity) * N, acc_rows);
+                ks_phase2_digit<LOGN, NT>(cta, buf, A, p, ct, i, j, jj, A.scratch + ((size_t)sib * slot_stride + parity) * N, acc_rows);
+                // every thread is past its last read of the sibling's digit (the body ends with a CTA barrier): hand the slot back
+                if (consumed && threadIdx.x == 0) {
+                    __threadfence();
+                    atomicAdd(consumed + sib, 1u);
+                }
             }
         }
     }
@@ -640,7 +666,8 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
     u32 *ticket = lc.ks_ticket;
     u64 *mail = lc.ks_mail;
     u32 pf_dist = (u32)lc.ks_prefetch;
-    void *params[] = {&args, &lt, &batch_arg, &flags, &epoch, &ticket, &mail, &prof, &pf_dist};
+    u32 *consumed = lc.ks_single ? lc.ks_consumed : nullptr;
+    void *params[] = {&args, &lt, &batch_arg, &flags, &epoch, &ticket, &mail, &prof, &pf_dist, &consumed};
     if (lc.l2_persist && lc.l2_persist_max && lc.ks_window_bytes) {
         // tuning (DPFHE_L2_PERSIST): the digit slots and accumulator rows are re-read within microseconds, the ciphertext
         // streams never; a persisting access-policy window over the scratch keeps the streams from evicting it

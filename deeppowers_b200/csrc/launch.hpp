@@ -27,6 +27,9 @@ struct LaunchCtx {
     int l2_persist = 0;               // DPFHE_L2_PERSIST: 1 = mark the fused kernel's scratch as persisting in L2
     u64 *ks_acc_hyb = nullptr;        // hybrid key switching: [ks_slots][2 parities][2][N], allocated at the first hybrid call
     u32 *ks_flags = nullptr;          // [ks_slots] monotonically increasing round counters
+    u32 *ks_consumed = nullptr;       // [ks_slots] monotone counters: readers of a single-buffered digit slot that have finished
+    int ks_single = 0;                // tuning (DPFHE_KS_SINGLE=1): digit slots single-buffered with consumed counters instead of two per CTA
+                                      // (by round parity); measured neutral in time and DRAM traffic (profiles/r02/ks_single.txt)
     u32 *ks_ticket = nullptr;         // next ciphertext index (reset per launch)
     u64 *ks_mail = nullptr;           // [ks_slots] per-group mailbox: (round tag << 32) | ciphertext index
     u64 *ks_key_s = nullptr;          // [L][2][L][N] Shoup companions of the current switch key

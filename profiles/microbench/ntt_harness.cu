@@ -14,6 +14,7 @@ using namespace dpfhe::DPFHE_VNS;
 template <int NT>
 struct DevCta {
     __device__ __forceinline__ void mark(int) {}
+    __device__ __forceinline__ void wait_ge(const u32 *, u32) {}
     template <class F> __device__ __forceinline__ void par(F f) { f((int)threadIdx.x); __syncthreads(); }
     template <class F> __device__ __forceinline__ void par_dom(F f) { f((int)threadIdx.x); __syncthreads(); }
     template <class F> __device__ __forceinline__ void par_warp(F f) { f((int)threadIdx.x); __syncwarp(); }

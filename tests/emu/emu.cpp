@@ -30,6 +30,7 @@ struct HostCta {
     template <class F>
     void par_warp(F f) { par(f); }
     void mark(int) {}
+    void wait_ge(const uint32_t *, uint32_t) {}   // sequential order: the readers of a slot have always finished
 };
 
 template <class T>

@@ -121,3 +121,93 @@ def test_shard_equality_on_one_gpu():
                 c.ct_mul_relin(a[lo:hi], b[lo:hi], evk, parts[lo:hi], hi - lo)
         assert torch.equal(parts, whole)
     c.close()
+
+
+# ---- one digest per BASELINE.json configuration at its full batch size (tests/golden/configs.json) ----
+@pytest.fixture(scope="module")
+def cfg_golden():
+    path = os.path.join(HERE, "golden", "configs.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/configs.json not generated")
+    with open(path) as f:
+        return json.load(f)
+
+
+def _sha_parallel(tensors):
+    """SHA-256 of several device tensors, downloads and hashes overlapped on a few host threads"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(8) as ex:
+        return list(ex.map(sha, tensors))
+
+
+def test_config2_full_batch_digest(cfg_golden):
+    """ct x ct + relinearise on all 4096 ciphertexts of config 2: one digest, no oracle in the loop"""
+    import deeppowers_b200 as dp
+    g = cfg_golden["config2"]
+    L, B, N = g["L"], g["batch"], 1 << g["log_n"]
+    c = dp.Context(g["log_n"], L)
+    a = torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda")
+    b, out = torch.empty_like(a), torch.empty_like(a)
+    evk = torch.empty((L, 2, L, N), dtype=torch.int64, device="cuda")
+    c.fill_uniform(g["seeds"]["a"], a, 2 * B)
+    c.fill_uniform(g["seeds"]["b"], b, 2 * B)
+    c.fill_uniform(g["seeds"]["evk"], evk, 2 * L)
+    assert sha(evk) == g["in_sha256"]["evk"] and sha(a) == g["in_sha256"]["a"]
+    c.ct_mul_relin(a, b, evk, out, B)
+    torch.cuda.synchronize()
+    assert sha(out) == g["out_sha256"]
+    # and through the host-buffer pipeline (chunked): the same digest
+    ha, hb, hk, ho = (t.cpu().numpy().view(np.uint64) for t in (a, b, evk, torch.zeros_like(out)))
+    c.ct_mul_relin_host(ha, hb, hk, ho)
+    assert hashlib.sha256(ho.tobytes()).hexdigest() == g["out_sha256"]
+    c.close()
+
+
+def test_config3_hoisted_sweep_digest(cfg_golden):
+    """the 26-index rotation sweep of config 3 (N=16384, L=8, 1024 ciphertexts) through dpfhe_rotate_hoisted at full size"""
+    import deeppowers_b200 as dp
+    g = cfg_golden["config3"]
+    L, B, N = g["L"], g["batch"], 1 << g["log_n"]
+    c = dp.Context(g["log_n"], L)
+    ct = torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda")
+    c.fill_uniform(0xD3390003, ct, 2 * B)
+    assert sha(ct) == g["in_sha256"]["ct"]
+    gs = g["galois"]
+    keys = []
+    for r in range(len(gs)):
+        k = torch.empty((L, 2, L, N), dtype=torch.int64, device="cuda")
+        c.fill_uniform(0xD3390003 + 100 + r, k, 2 * L)
+        keys.append(k)
+    out = torch.empty((len(gs), B, 2, L, N), dtype=torch.int64, device="cuda")
+    c.rotate_hoisted(ct, gs, keys, out, B)
+    torch.cuda.synchronize()
+    digests = _sha_parallel([out[r] for r in range(len(gs))])
+    assert digests == g["out_sha256_per_rotation"]
+    assert hashlib.sha256("".join(digests).encode()).hexdigest() == g["out_sha256"]
+    # one index of the sweep through the ordinary rotate kernel as well
+    one = torch.empty_like(ct)
+    c.rotate(ct, gs[5], keys[5], one, B)
+    torch.cuda.synchronize()
+    assert sha(one) == g["out_sha256_per_rotation"][5]
+    c.close()
+
+
+def test_config4_linear_layer_digest(cfg_golden):
+    """the 768 x 768 layer of config 4 on all 512 prompts: baby steps hoisted, inner products fused, Horner over the giant steps"""
+    import deeppowers_b200 as dp
+    g = cfg_golden["config4"]
+    L, B, N, n, baby = g["L"], g["batch"], 1 << g["log_n"], g["diagonals"], g["baby"]
+    c = dp.Context(g["log_n"], L)
+    x = torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda")
+    diags = torch.empty((n, L, N), dtype=torch.int64, device="cuda")
+    c.fill_uniform(0xD3390004, x, 2 * B)
+    c.fill_uniform(0xD3390004 + 1, diags, n)
+    assert sha(x) == g["in_sha256"]["x"] and sha(diags) == g["in_sha256"]["diags"]
+    key = lambda seed: (lambda k: (c.fill_uniform(seed, k, 2 * L), k)[1])(torch.empty((L, 2, L, N), dtype=torch.int64, device="cuda"))
+    gk_baby = [key(0xD3390004 + 10 + b) for b in range(1, baby)]
+    gk_giant = key(0xD3390004 + 99)
+    out = torch.empty_like(x)
+    c.linear_bsgs(x, diags, gk_baby, gk_giant, baby, out, B)
+    torch.cuda.synchronize()
+    assert sha(out) == g["out_sha256"]
+    c.close()

@@ -399,7 +399,7 @@ def test_mod_switch_errors(dp, ctxs):
         c.mod_switch_down(x, x.clone(), 1)
     c3, _ = ctxs(12, 3)
     y = torch.zeros((1, 3, o.N), dtype=torch.int64, device="cuda")
-    with pytest.raises(RuntimeError, match="alias"):
+    with pytest.raises(RuntimeError, match="overlap"):
         c3.mod_switch_down(y, y, 1)
 
 
@@ -432,6 +432,12 @@ def test_errors_are_reported(dp, ctxs):
         c.rotate(d, 4, d, torch.zeros_like(d), 1)   # even Galois element
     with pytest.raises(dp.DpfheError):
         c.ct_mul_relin(d, d, d, d, 1)          # aliasing output
+    # partial overlap is refused too: the output of ciphertexts 1..2 lands on input ciphertexts 2..3
+    big = torch.zeros((4, 2, 2, o.N), dtype=torch.int64, device="cuda")
+    with pytest.raises(dp.DpfheError, match="overlap"):
+        c.ct_mul_relin(big[1:3], torch.zeros_like(big[1:3]), d, big[2:4], 2)
+    with pytest.raises(dp.DpfheError, match="overlap"):
+        c.rotate(big[0:2], 5, d, big[1:3], 2)
     c.ntt_fwd(d, 0)                            # empty batch is a no-op
 
 
