@@ -6,6 +6,7 @@
 // code plus thread-local message, because exceptions cannot cross a C ABI.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -880,6 +881,142 @@ int dpfhe_debug_phase_cycles(dpfhe_ctx *ctx, uint64_t *out16) {
         if (!out16[12] || ns < out16[12]) out16[12] = ns;
     }
     return DPFHE_OK;
+}
+
+// ---------------------------------------------------------------- encrypted linear layer (BASELINE config 4)
+// y = sum_g rot_{g*baby}( sum_b D[g*baby + b] o rot_b(x) ): baby-step/giant-step diagonals on top of the hot-path ops.
+// The weights (diagonal plaintexts) and Galois keys are uploaded ONCE when the layer is created; an application is
+//   baby-1 hoisted rotations of the input (one shared digit decomposition)  -> dpfhe_rotate_hoisted
+//   all giant-step inner sums in one pass over the baby steps               -> dpfhe_ct_mul_plain_inner
+//   Horner over the giant steps: acc = rot_baby(acc) + inner[g]              -> dpfhe_rotate + dpfhe_poly_add
+// and the host-buffer form pipelines chunks of the batch through it (upload / compute / download overlapped).
+struct dpfhe_linear {
+    dpfhe_ctx *ctx = nullptr;
+    size_t n = 0, baby = 0, giant = 0;
+    u64 *d_diags = nullptr;                 // [n][L][N]
+    u64 *d_keys = nullptr;                  // [baby-1 + 1][L][2][L][N]: baby-step keys, then the giant-step key
+    std::vector<uint64_t> g_baby;           // Galois elements 5^b, b = 1 .. baby-1
+    std::vector<const uint64_t *> k_baby;   // device pointers of the baby-step keys
+    uint64_t g_giant = 0;
+    u64 *scratch = nullptr;                 // [baby + giant + 1][cap][2][L][N]
+    size_t cap = 0;                         // ciphertexts the scratch holds
+};
+
+static int linear_reserve(dpfhe_linear *lin, size_t batch) {
+    if (batch <= lin->cap) return DPFHE_OK;
+    dpfhe_ctx *ctx = lin->ctx;
+    int rc = dpfhe_synchronize(ctx);
+    if (rc) return rc;
+    cudaFree(lin->scratch);
+    lin->scratch = nullptr;
+    lin->cap = 0;
+    CU_TRY(cudaMalloc(&lin->scratch, (lin->baby + lin->giant + 1) * batch * 2 * ctx->P() * 8));
+    lin->cap = batch;
+    return DPFHE_OK;
+}
+
+int dpfhe_linear_create(dpfhe_ctx *ctx, const uint64_t *h_diags, size_t n_diags, size_t baby, const uint64_t *h_gk_baby, const uint64_t *h_gk_giant,
+                        dpfhe_linear **out) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (!out || !h_diags) return fail(DPFHE_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (baby == 0 || baby > 128 || n_diags == 0 || n_diags % baby) return fail(DPFHE_ERR_INVALID, "need 1 <= baby <= 128 and a multiple of baby diagonals");
+    const size_t giant = n_diags / baby;
+    if (giant > 65535) return fail(DPFHE_ERR_INVALID, "too many giant steps");
+    if ((baby > 1 && !h_gk_baby) || (giant > 1 && !h_gk_giant)) return fail(DPFHE_ERR_INVALID, "missing Galois keys");
+    dpfhe_linear *lin = new (std::nothrow) dpfhe_linear();
+    if (!lin) return fail(DPFHE_ERR_NOMEM, "out of host memory");
+    lin->ctx = ctx; lin->n = n_diags; lin->baby = baby; lin->giant = giant;
+    const size_t P8 = ctx->P() * 8, key_bytes = 2 * ctx->hp.L * P8;
+    cudaError_t e = cudaMalloc(&lin->d_diags, n_diags * P8);
+    if (e == cudaSuccess) e = cudaMalloc(&lin->d_keys, baby * key_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(lin->d_diags, h_diags, n_diags * P8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && baby > 1) e = cudaMemcpy(lin->d_keys, h_gk_baby, (baby - 1) * key_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && giant > 1) e = cudaMemcpy(lin->d_keys + (baby - 1) * key_bytes / 8, h_gk_giant, key_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        dpfhe_linear_destroy(lin);
+        return fail(DPFHE_ERR_CUDA, "linear layer upload: %s", cudaGetErrorString(e));
+    }
+    for (size_t b = 1; b < baby; ++b) {
+        uint64_t g = 0;
+        dpfhe_galois_element(ctx, (int)b, &g);
+        lin->g_baby.push_back(g);
+        lin->k_baby.push_back(lin->d_keys + (b - 1) * key_bytes / 8);
+    }
+    dpfhe_galois_element(ctx, (int)baby, &lin->g_giant);
+    *out = lin;
+    return DPFHE_OK;
+}
+
+void dpfhe_linear_destroy(dpfhe_linear *lin) {
+    if (!lin) return;
+    if (lin->ctx) {
+        cudaSetDevice(lin->ctx->lc.device);
+        dpfhe_synchronize(lin->ctx);
+    }
+    cudaFree(lin->d_diags);
+    cudaFree(lin->d_keys);
+    cudaFree(lin->scratch);
+    delete lin;
+}
+
+static int linear_apply_on(dpfhe_linear *lin, const uint64_t *d_ct, uint64_t *d_out, size_t batch, void *stream) {
+    dpfhe_ctx *ctx = lin->ctx;
+    const size_t ctb = batch * 2 * ctx->P();                 // words of one ciphertext batch
+    u64 *steps = lin->scratch, *inner = steps + lin->baby * ctb, *tmp = inner + lin->giant * ctb;
+    cudaStream_t st = pick(ctx, stream);
+    CU_TRY(cudaMemcpyAsync(steps, d_ct, ctb * 8, cudaMemcpyDeviceToDevice, st));
+    int rc = DPFHE_OK;
+    if (lin->baby > 1) rc = dpfhe_rotate_hoisted(ctx, steps, lin->baby - 1, lin->g_baby.data(), lin->k_baby.data(), steps + ctb, batch, stream);
+    if (rc) return rc;
+    rc = dpfhe_ct_mul_plain_inner(ctx, steps, lin->baby, lin->d_diags, lin->giant, inner, batch, stream);
+    if (rc) return rc;
+    st = pick(ctx, stream);
+    CU_TRY(cudaMemcpyAsync(d_out, inner + (lin->giant - 1) * ctb, ctb * 8, cudaMemcpyDeviceToDevice, st));
+    const u64 *gk_giant = lin->d_keys + (lin->baby - 1) * 2 * ctx->hp.L * ctx->P();
+    for (size_t g = lin->giant - 1; g-- > 0;) {
+        rc = dpfhe_rotate(ctx, d_out, lin->g_giant, gk_giant, tmp, batch, stream);           // Horner step: acc = rot_baby(acc) + inner[g]
+        if (rc) return rc;
+        rc = dpfhe_poly_add(ctx, tmp, inner + g * ctb, d_out, 2 * batch, stream);
+        if (rc) return rc;
+    }
+    return DPFHE_OK;
+}
+
+int dpfhe_linear_apply(dpfhe_linear *lin, const uint64_t *d_ct, uint64_t *d_out, size_t batch, void *stream) {
+    if (!lin) return fail(DPFHE_ERR_INVALID, "null layer");
+    int rc = enter(lin->ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    CHECK_PTR(d_ct); CHECK_PTR(d_out);
+    if (overlaps(d_out, batch * 2 * lin->ctx->P() * 8, d_ct, batch * 2 * lin->ctx->P() * 8)) return fail(DPFHE_ERR_INVALID, "output must not overlap the input");
+    rc = linear_reserve(lin, batch);
+    if (rc) return rc;
+    return linear_apply_on(lin, d_ct, d_out, batch, stream);
+}
+
+int dpfhe_linear_apply_host(dpfhe_linear *lin, const uint64_t *h_ct, uint64_t *h_out, size_t batch) {
+    if (!lin) return fail(DPFHE_ERR_INVALID, "null layer");
+    dpfhe_ctx *ctx = lin->ctx;
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    if (!h_ct || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
+    // Chunks of about a third of the batch, rounded to whole rounds of the persistent key-switch grid (3 CTAs per SM, L CTAs
+    // per ciphertext): a chunk that leaves the grid's last round mostly empty costs more than the transfers it hides.  The
+    // first upload and the last download are the only transfers not overlapped with a neighbouring chunk's compute.
+    const size_t groups = std::max<size_t>(1, (size_t)ctx->lc.num_sms * 3 / ctx->hp.L);
+    size_t rounds = (batch / 3 + groups / 2) / groups;
+    if (rounds < 1) rounds = 1;
+    size_t chunk = rounds * groups;
+    if (chunk > 512) chunk = std::max<size_t>(groups, 512 / groups * groups);
+    if (chunk > batch) chunk = batch;
+    rc = linear_reserve(lin, chunk);
+    if (rc) return rc;
+    const size_t ct_words = 2 * ctx->P();
+    return run_pipeline(ctx, h_ct, nullptr, h_out, batch, ct_words, ct_words, chunk,
+                        [&](u64 *din, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int { return linear_apply_on(lin, din, dout, cnt, st); });
 }
 
 int dpfhe_describe(const dpfhe_ctx *ctx, char *buf, size_t buf_len) {

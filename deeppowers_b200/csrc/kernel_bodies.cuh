@@ -125,6 +125,62 @@ DPFHE_HD void ntt_inv_body(CTA &cta, u64 *buf, u64 *data, const Twiddle *itw, co
     });
 }
 
+// ---- N = 16384 standalone transforms by a PAIR of CTAs (a thread-block cluster of two) ------------------------------
+// A 128 KiB limb in one CTA's shared memory allows one CTA per SM; the transform kernels need about three to hide each
+// other's memory phases.  So the limb is split as in the fused kernel: CTA h of the pair owns the two
+// 4096-point blocks {2h, 2h+1} in 64 KiB of shared memory.
+//   forward: both CTAs read the whole limb (the outer radix-4 step needs all four blocks) and keep their half of its
+//            result; a cluster barrier separates the reads from the in-place stores.
+//   inverse: each CTA runs the block-local passes on its half; the outer radix-4 step then reads two blocks from its own
+//            shared memory and two from the partner's (distributed shared memory), each CTA finishing half of the columns.
+constexpr int NTT_PAIR_LOGN = 14;
+
+template <int NT, class CTA>
+DPFHE_HD void ntt_fwd_half_load(CTA &cta, u64 *buf, const u64 *data, const Twiddle *tw, const LimbParams &p, int h) {
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(data);
+    cta.par([&](int tid) {
+        fwd_load_stage_half<NTT_PAIR_LOGN, NT, false>(buf, tw, p, tid, [&](int c) { return ld_stream(src + c); }, h);
+    });
+}
+template <int NT, class CTA>
+DPFHE_HD void ntt_fwd_half_finish(CTA &cta, u64 *buf, u64 *data, const Twiddle *tw, const LimbParams &p, int h) {
+    constexpr int HC = 1 << (NTT_PAIR_LOGN - 2);   // chunks of half a limb
+    fwd_passes_blk<NTT_PAIR_LOGN, NT, 1, 2>(cta, buf, tw, p, 2 * h);
+    U64x2 *dst = reinterpret_cast<U64x2 *>(data) + h * HC;
+    cta.par([&](int tid) {
+        for (int lc = tid; lc < HC; lc += NT) {
+            U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lc)];
+            v.x = canon(v.x, p);
+            v.y = canon(v.y, p);
+            st_stream(dst + lc, v);
+        }
+    });
+}
+template <int NT, class CTA>
+DPFHE_HD void ntt_inv_half_passes(CTA &cta, u64 *buf, const u64 *data, const Twiddle *itw, const LimbParams &p, int h) {
+    constexpr int HC = 1 << (NTT_PAIR_LOGN - 2);
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(data) + h * HC;
+    cta.par([&](int tid) {
+        for (int lc = tid; lc < HC; lc += NT) reinterpret_cast<U64x2 *>(buf)[swz_chunk(lc)] = ld_stream(src + lc);
+    });
+    inv_passes_blk<NTT_PAIR_LOGN, NT, 2>(cta, buf, itw, p, 2 * h);
+}
+// peer: the partner CTA's buffer (its shared memory through the cluster mapping; a plain second buffer in the emulator)
+template <int NT, class CTA>
+DPFHE_HD void ntt_inv_half_outer(CTA &cta, const u64 *buf, const u64 *peer, u64 *data, const Twiddle *itw, const LimbParams &p, int h) {
+    constexpr int CPB = 1 << (NTT_PAIR_LOGN - 3);   // chunks per 4096-point block
+    U64x2 *dst = reinterpret_cast<U64x2 *>(data);
+    cta.par([&](int tid) {
+        inv_outer_stage<NTT_PAIR_LOGN, NT>(
+            itw, p, tid,
+            [&](int c) {   // chunk c of the limb lives in block c / CPB: blocks {2h, 2h+1} here, the other two at the partner
+                const int b = c / CPB, lc = (b & 1) * CPB + (c - b * CPB);
+                return reinterpret_cast<const U64x2 *>((b >> 1) == h ? buf : peer)[swz_chunk(lc)];
+            },
+            [&](int c, const U64x2 &v) { st_stream(dst + c, v); }, h * (CPB / 2), (h + 1) * (CPB / 2));
+    });
+}
+
 // ---- element-wise kernels -------------------------------------------------------------
 // chunk-granular (two coefficients); `l` is the limb of the chunk.
 DPFHE_HD U64x2 mul_chunk(const U64x2 &a, const U64x2 &b, const LimbParams &p) {

@@ -75,6 +75,36 @@ __global__ void __launch_bounds__(NT, MINB) ntt_kernel(u64 *data, const Twiddle 
     }
 }
 
+// N = 16384: one limb per CLUSTER of two CTAs (64 KiB of shared memory each, so three CTAs still share an SM); see
+// kernel_bodies.cuh "transforms by a PAIR of CTAs".  The inverse reads the partner's half through distributed shared memory.
+template <int NT, int MINB, bool INVERSE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, MINB)
+    ntt_pair_kernel(u64 *data, const Twiddle *__restrict__ tables, const __grid_constant__ LimbTable lt, u32 L, size_t n_limbs) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    constexpr size_t N = (size_t)1 << NTT_PAIR_LOGN;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int h = (int)cluster.block_rank();
+    const u64 *peer = cluster.map_shared_rank(buf, h ^ 1);
+    DevCta<NT> cta;
+    for (size_t w = blockIdx.x / 2; w < n_limbs; w += gridDim.x / 2) {
+        const u32 l = (u32)(w % L);
+        const LimbParams &p = lt.lp[l];
+        const Twiddle *tw = tables + (size_t)l * N;
+        if (!INVERSE) {
+            ntt_fwd_half_load<NT>(cta, buf, data + w * N, tw, p, h);
+            cluster.sync();   // both CTAs have read the whole limb: the in-place stores may begin
+            ntt_fwd_half_finish<NT>(cta, buf, data + w * N, tw, p, h);
+        } else {
+            ntt_inv_half_passes<NT>(cta, buf, data + w * N, tw, p, h);
+            cluster.sync();   // the partner's half is complete in its shared memory
+            ntt_inv_half_outer<NT>(cta, buf, peer, data + w * N, tw, p, h);
+            cluster.sync();   // the partner has finished reading this CTA's shared memory
+        }
+    }
+}
+
 // ------------------------------------------------------------------ modulus switching (two launches)
 template <int LOGN, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) ms_tau_kernel(const u64 *in, u64 *tau, const Twiddle *__restrict__ itw,
@@ -579,6 +609,25 @@ static cudaError_t launch_ntt_dir(const LaunchCtx &lc, u64 *data, size_t n_limbs
     return inverse ? launch_ntt_t<LOGN, NT, MINB, true>(lc, data, n_limbs, st) : launch_ntt_t<LOGN, NT, MINB, false>(lc, data, n_limbs, st);
 }
 
+template <bool INV>
+static cudaError_t launch_ntt_pair_t(const LaunchCtx &lc, u64 *data, size_t n_limbs, cudaStream_t st) {
+    constexpr int NT = 256, MINB = 3;
+    auto kern = ntt_pair_kernel<NT, MINB, INV>;
+    const size_t smem = Geometry<13>::LIMB_BYTES;   // half a limb
+    static ConfiguredMask configured;
+    if (!configured.has(lc.device)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured.set(lc.device);
+    }
+    const size_t pairs = n_limbs < 0x3fffffffull ? n_limbs : 0x3fffffffull;
+    kern<<<(unsigned)(2 * pairs), NT, smem, st>>>(data, INV ? lc.itw : lc.tw, lc.lt, lc.L, n_limbs);
+    return cudaGetLastError();
+}
+static cudaError_t launch_ntt_pair(const LaunchCtx &lc, u64 *data, size_t n_limbs, bool inverse, cudaStream_t st) {
+    return inverse ? launch_ntt_pair_t<true>(lc, data, n_limbs, st) : launch_ntt_pair_t<false>(lc, data, n_limbs, st);
+}
+
 cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inverse, cudaStream_t st) {
     const size_t n_limbs = n_polys * lc.L;
     if (n_limbs == 0) return cudaSuccess;
@@ -591,7 +640,9 @@ cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inve
                 case 3: return launch_ntt_dir<13, 256, 2>(lc, data, n_limbs, inverse, st);   // 12.3 M
                 default: return launch_ntt_dir<13, 256, 3>(lc, data, n_limbs, inverse, st);  // 13.2 M: 3 CTAs/SM (smem-limited), 80 regs
             }
-        case 14: return launch_ntt_dir<14, 512, 1>(lc, data, n_limbs, inverse, st);
+        case 14:
+            if (lc.ntt_cfg == 1) return launch_ntt_dir<14, 512, 1>(lc, data, n_limbs, inverse, st);   // whole limb per CTA, 1 CTA/SM
+            return launch_ntt_pair(lc, data, n_limbs, inverse, st);                                   // CTA pair per limb, 3 CTAs/SM
     }
     return cudaErrorInvalidValue;
 }

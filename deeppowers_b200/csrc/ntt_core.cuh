@@ -231,13 +231,15 @@ DPFHE_HD void fwd_load_stage(u64 *buf, const Twiddle *__restrict__ tw, const Lim
 // Inverse counterpart: SRC(chunk_index) yields the chunks left by the register passes (values in [0,SB*q));
 // applies the K outermost Gentleman-Sande stages with N^-1 folded into the very last one, and hands
 // canonical chunks to DST(chunk_index, U64x2) (the last stage uses the exact product so that one csub finishes).
+// [c_lo, c_hi): the chunk columns this call handles (all of them by default; a CTA pair splits them, ntt_inv_half_outer).
 template <int LOGN, int NT, class SRC, class DST>
-DPFHE_HD void inv_outer_stage(const Twiddle *__restrict__ tw, const LimbParams &p, int tid, SRC src, DST dst) {
+DPFHE_HD void inv_outer_stage(const Twiddle *__restrict__ tw, const LimbParams &p, int tid, SRC src, DST dst, int c_lo = 0,
+                              int c_hi = (1 << (LOGN - 1)) >> (LOGN - 12)) {
     constexpr int K = LOGN - 12;
     constexpr int NB = 1 << K;
     constexpr int CPB = (1 << (LOGN - 1)) / NB;
 #pragma unroll 1
-    for (int c = tid; c < CPB; c += NT) {
+    for (int c = c_lo + tid; c < c_hi; c += NT) {
         u64 x[NB][2];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {

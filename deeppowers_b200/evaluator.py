@@ -338,6 +338,35 @@ class PinnedBuffer:
     __del__ = close
 
 
+class LinearLayer:
+    """Encrypted linear layer as a library object (dpfhe_linear_*): diagonal plaintexts and Galois keys live on the device; apply()
+    takes device buffers, apply_host() host buffers (pipelined in chunks).  diags [n][L][N], gk_baby [baby-1][L][2][L][N] (keys of the
+    rotations by 1 .. baby-1), gk_giant [L][2][L][N] (rotation by `baby`): C-contiguous numpy uint64 arrays."""
+
+    def __init__(self, ctx, diags, baby, gk_baby, gk_giant):
+        self._l, self.ctx = ctx._l, ctx
+        self._h = C.c_void_p()
+        n = diags.shape[0]
+        rc = self._l.dpfhe_linear_create(ctx._h, _hptr(diags), n, int(baby), _hptr(gk_baby) if gk_baby is not None else None,
+                                         _hptr(gk_giant) if gk_giant is not None else None, C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise DpfheError(self._l.dpfhe_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._l.dpfhe_linear_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def apply(self, ct, out, batch, stream=None):
+        self.ctx._chk(self._l.dpfhe_linear_apply(self._h, _ptr(ct), _ptr(out), batch, _stream(stream)))
+
+    def apply_host(self, ct, out):
+        self.ctx._chk(self._l.dpfhe_linear_apply_host(self._h, _hptr(ct), _hptr(out, True), ct.size // (2 * self.ctx.P)))
+
+
 class MultiContext:
     """Several GPUs in one process (dpfhe_multi_*): one context per device, contiguous shards of the batch, no collective
     while computing.  `devices`: list of CUDA device ids (a device may be listed twice), None = all visible devices."""

@@ -145,6 +145,21 @@ int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, con
 int dpfhe_ct_mul_plain_inner(dpfhe_ctx *ctx, const uint64_t *d_steps, size_t n_steps, const uint64_t *d_pts, size_t n_groups,
                              uint64_t *d_out, size_t batch, void *stream);
 
+/* ---- encrypted linear layer (BASELINE.json config 4): y = W x by baby-step/giant-step diagonals,
+ *      y = sum_g rot_{g*baby}( sum_b D[g*baby + b] o rot_b(x) ), a composition of the calls above that runs entirely on
+ *      the device.  h_diags [n_diags][L][N]: the diagonal plaintexts in evaluation form, diagonal g*baby + b pre-rotated by
+ *      -g*baby (the caller encodes them so); n_diags a multiple of baby (<= 128).  h_gk_baby [baby-1][L][2][L][N]: Galois
+ *      keys of the rotations by 1 .. baby-1 slots; h_gk_giant [L][2][L][N]: key of the rotation by `baby` slots.
+ *      Weights and keys are uploaded once, at creation.  apply: d_ct, d_out [batch][2][L][N] device buffers (asynchronous);
+ *      apply_host: host buffers, the batch pipelined in chunks (upload / compute / download overlapped; synchronous).
+ *      Uses (baby-1) + (n_diags/baby - 1) rotations per ciphertext instead of n_diags - 1. ---- */
+typedef struct dpfhe_linear dpfhe_linear;
+int dpfhe_linear_create(dpfhe_ctx *ctx, const uint64_t *h_diags, size_t n_diags, size_t baby, const uint64_t *h_gk_baby,
+                        const uint64_t *h_gk_giant, dpfhe_linear **out);
+void dpfhe_linear_destroy(dpfhe_linear *layer);
+int dpfhe_linear_apply(dpfhe_linear *layer, const uint64_t *d_ct, uint64_t *d_out, size_t batch, void *stream);
+int dpfhe_linear_apply_host(dpfhe_linear *layer, const uint64_t *h_ct, uint64_t *h_out, size_t batch);
+
 /* ---- modulus switching / rescale: drop the last limb of every polynomial.
  *      in [n_polys][L][N] -> out [n_polys][L-1][N] (a ciphertext is two polynomials), evaluation form.
  *      t_plain > 0: BGV modulus switch (the plaintext is scaled by q_last^-1 mod t); t_plain == 0: plain rounding.

@@ -65,6 +65,12 @@ class Emu:
         self._l.emu_root_powers(self._h, l, int(inverse), out)
         return out
 
+    def ntt_pair(self, data, inverse=False):
+        """N = 16384 only: the CTA-pair bodies (ntt_pair_kernel)"""
+        d = np.ascontiguousarray(data, dtype=np.uint64).copy()
+        assert self._l.emu_ntt_pair(self._h, d.reshape(-1), d.size // (self.L * self.N), int(inverse)) == 0
+        return d
+
     def ntt(self, data, inverse=False):
         d = np.ascontiguousarray(data, dtype=np.uint64).copy()
         assert self._l.emu_ntt(self._h, d.reshape(-1), d.size // (self.L * self.N), int(inverse)) == 0
@@ -135,6 +141,7 @@ def _build_emu(variant):
     lib.emu_psi.argtypes = [C.c_void_p, C.c_uint]
     lib.emu_root_powers.argtypes = [C.c_void_p, C.c_uint, C.c_int, _u64p]
     lib.emu_ntt.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int]
+    lib.emu_ntt_pair.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int]
     lib.emu_ks.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint]
     lib.emu_ks_hybrid.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_uint]
     lib.emu_rotate_hoisted.argtypes = [C.c_void_p, _u64p, C.c_size_t, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint, C.POINTER(C.c_uint)]

@@ -64,6 +64,28 @@ void run_ntt(Emu &e, uint64_t *data, size_t n_polys, bool inverse) {
     free(buf);
 }
 
+// N = 16384 by a pair of CTAs (ntt_pair_kernel): two half buffers; the cluster barriers become the order of the phases
+template <int NT>
+void run_ntt_pair(Emu &e, uint64_t *data, size_t n_polys, bool inverse) {
+    const size_t N = (size_t)1 << NTT_PAIR_LOGN;
+    uint64_t *buf[2] = {aligned_new<uint64_t>(N / 2), aligned_new<uint64_t>(N / 2)};
+    HostCta cta{NT};
+    for (size_t w = 0; w < n_polys * e.hp.L; ++w) {
+        const unsigned l = (unsigned)(w % e.hp.L);
+        const LimbParams p = e.lp[l];
+        uint64_t *limb = data + w * N;
+        if (!inverse) {
+            for (int h = 0; h < 2; ++h) ntt_fwd_half_load<NT>(cta, buf[h], limb, e.tw + l * N, p, h);
+            for (int h = 0; h < 2; ++h) ntt_fwd_half_finish<NT>(cta, buf[h], limb, e.tw + l * N, p, h);
+        } else {
+            for (int h = 0; h < 2; ++h) ntt_inv_half_passes<NT>(cta, buf[h], limb, e.itw + l * N, p, h);
+            for (int h = 0; h < 2; ++h) ntt_inv_half_outer<NT>(cta, buf[h], buf[h ^ 1], limb, e.itw + l * N, p, h);
+        }
+    }
+    free(buf[0]);
+    free(buf[1]);
+}
+
 // persistent-grid emulation: G slots, rounds of G work items; all phase 1 of a round before its phase 2
 template <int LOGN, int NT, int MODE>
 void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, uint64_t *out, size_t batch,
@@ -288,6 +310,14 @@ int emu_ntt(void *h, uint64_t *data, size_t n_polys, int inverse) {
         case 14: run_ntt<14, 512>(*e, data, n_polys, inverse != 0); return 0;
     }
     return -1;
+}
+
+// the CTA-pair form of the N = 16384 transforms
+int emu_ntt_pair(void *h, uint64_t *data, size_t n_polys, int inverse) {
+    Emu *e = (Emu *)h;
+    if (e->hp.log_n != 14) return -1;
+    run_ntt_pair<256>(*e, data, n_polys, inverse != 0);
+    return 0;
 }
 
 // mode: 0 ct_mul_relin (a,b), 1 keyswitch (a = d), 2 rotate (a = ct, galois)

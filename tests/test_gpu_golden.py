@@ -210,4 +210,17 @@ def test_config4_linear_layer_digest(cfg_golden):
     c.linear_bsgs(x, diags, gk_baby, gk_giant, baby, out, B)
     torch.cuda.synchronize()
     assert sha(out) == g["out_sha256"]
+    # the same layer as a library object (dpfhe_linear_*): weights and keys uploaded once, device and host-buffer forms
+    h = lambda t: t.cpu().numpy().view(np.uint64)
+    layer = dp.LinearLayer(c, h(diags), baby, h(torch.stack(gk_baby)), h(gk_giant))
+    out2 = torch.zeros_like(x)
+    layer.apply(x, out2, B)
+    torch.cuda.synchronize()
+    assert sha(out2) == g["out_sha256"]
+    hx, ho = h(x), np.zeros((B, 2, L, N), dtype=np.uint64)
+    layer.apply_host(hx, ho)
+    assert hashlib.sha256(ho.tobytes()).hexdigest() == g["out_sha256"]
+    layer.apply_host(hx[:37], ho[:37])                      # ragged batch, one chunk
+    assert np.array_equal(ho[:37], h(out2)[:37])
+    layer.close()
     c.close()

@@ -88,6 +88,9 @@ def test_emulated_ntt_bodies(make_emu, oracle_mod, log_n, L, n_polys):
     y = e.ntt(x)
     assert np.array_equal(y, o.ntt_fwd(x))
     assert np.array_equal(e.ntt(y, inverse=True), x)
+    if log_n == 14:   # the CTA-pair form (half a limb per CTA, the inverse reading the partner's half)
+        assert np.array_equal(e.ntt_pair(x), y)
+        assert np.array_equal(e.ntt_pair(y, inverse=True), x)
 
 
 @pytest.mark.parametrize("log_n,L,batch,G", [(12, 2, 3, 2), (12, 3, 4, 9), (13, 4, 2, 8), (12, 1, 2, 1), (14, 2, 2, 4), (12, 9, 2, 9)])

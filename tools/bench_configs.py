@@ -110,12 +110,42 @@ def cfg4():
     ms_bsgs_h = timed(lambda: c.linear_bsgs(cur, diag, [baby_keys[i] for i in range(BABY - 1)], gkb, BABY, acc, B, scratch=scratch), 2)
     t_inner = timed(lambda: c.ct_mul_plain_inner(scratch[:BABY], diag, scratch[BABY:BABY + GIANT], BABY, GIANT, B), 3)
     t_fma = timed(lambda: c.ct_mul_plain_acc(cur, diag[1], acc, B), 20)
+    # the layer as a library object (dpfhe_linear_*): weights and keys resident, one C call per application; and end to end
+    # from HOST buffers (pinned, on the GPU's NUMA node), chunks of the batch pipelined through upload / compute / download
+    import time
+    import numpy as np
+    h = lambda t: t.cpu().numpy().view(np.uint64)
+    del scratch
+    lay = dp.LinearLayer(c, h(diag), BABY, h(baby_keys), h(gkb))
+    out_lib = torch.empty_like(cur)
+    ms_lib = timed(lambda: lay.apply(cur, out_lib, B), 3)
+    scratch = torch.empty((BABY + GIANT + 1, B, 2, L, N), dtype=torch.int64, device="cuda")
+    c.linear_bsgs(cur, diag, [baby_keys[i] for i in range(BABY - 1)], gkb, BABY, acc, B, scratch=scratch)
+    torch.cuda.synchronize()
+    same_lib = bool(torch.equal(out_lib, acc))      # the Python composition of the same calls
+    del scratch
+    n_words = B * 2 * L * N
+    hin, hout = c.pinned_near(n_words), c.pinned_near(n_words)
+    torch.from_numpy(hin.array.view(np.int64)).copy_(cur.view(-1))
+    torch.cuda.synchronize()
+    lay.apply_host(hin.array, hout.array)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        lay.apply_host(hin.array, hout.array)
+    s_host = (time.perf_counter() - t0) / 3
+    same_host = bool(torch.equal(torch.from_numpy(hout.array.view(np.int64)).cuda().view_as(cur), out_lib))
+    lay.close()
     c.close()
     return {"config": "cfg4 encrypted 768x768 linear layer N=8192 L=4 batch=512 (diagonal method, one Galois key)",
             "ms_per_layer_batch": ms, "prompts_per_s": B / ms * 1e3,
             "bsgs": {"baby": BABY, "rotations": BABY - 1 + DIM // BABY - 1, "ms_per_layer_batch": ms_bsgs, "prompts_per_s": B / ms_bsgs * 1e3,
                      "unfused_ms_per_layer_batch": ms_bsgs_unfused, "unfused_prompts_per_s": B / ms_bsgs_unfused * 1e3,
                      "hoisted_baby_steps_ms_per_layer_batch": ms_bsgs_h, "hoisted_baby_steps_prompts_per_s": B / ms_bsgs_h * 1e3},
+            "library_layer": {"api": "dpfhe_linear_apply (device buffers, weights and keys resident)", "ms_per_batch": ms_lib,
+                              "prompts_per_s": B / ms_lib * 1e3, "matches_python_composition": same_lib},
+            "library_layer_host": {"api": "dpfhe_linear_apply_host (pinned host buffers, chunks of the batch pipelined)", "ms_per_batch": s_host * 1e3,
+                                   "prompts_per_s": B / s_host, "matches": same_host, "h2d_bytes": n_words * 8, "d2h_bytes": n_words * 8,
+                                   "fraction_of_device_resident_rate": (B / s_host) / (B / ms_lib * 1e3)},
             "ct_mul_plain_inner": {"ms": t_inner, "ct_pt_products_per_s": B * DIM / t_inner * 1e3,
                                    "GBps": B * (BABY + GIANT) * 2 * P / t_inner / 1e6, "frac_hbm": B * (BABY + GIANT) * 2 * P / t_inner / 1e6 / PEAK,
                                    "note": "768 ct x pt products per prompt in one launch; traffic = 32 ciphertext rows in + 24 out per prompt"},
