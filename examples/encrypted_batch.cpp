@@ -35,7 +35,14 @@ int main() {
         auto dt = duration_cast<microseconds>(high_resolution_clock::now() - t0).count() / 1e6;
         std::cout << "Total time: " << dt << " seconds" << std::endl;
         std::cout << "Throughput: " << batch / dt << " ct-mults per second (host buffers, H2D+D2H included)" << std::endl;
-        return 0;
+
+        // the same batch sharded over every GPU of the box (BASELINE.json config 5's layout): one object, no MPI, no collective —
+        // each device pipelines its own contiguous shard and writes its slice of `out`
+        MultiEvaluator all(parms);
+        std::vector<std::uint64_t> out_multi(a.size());
+        all.multiply_relin({a.data(), batch}, {b.data(), batch}, relin_key.data(), {out_multi.data(), batch});
+        std::cout << "Sharded over " << all.device_count() << " GPU(s): " << (out_multi == out ? "identical result" : "RESULT DIFFERS") << std::endl;
+        return out_multi == out ? 0 : 2;
     } catch (const std::exception &e) {
         std::cerr << "Error: " << e.what() << std::endl;
         return 1;

@@ -29,7 +29,7 @@ namespace fhe {
 struct EncryptionParameters {
     unsigned log_n = 13;                   // N = 8192
     unsigned n_limbs = 4;                  // L
-    std::vector<std::uint64_t> moduli;     // empty: the L largest NTT-friendly primes below 2^60
+    std::vector<std::uint64_t> moduli;     // empty: the L largest primes k*2^32+1 below 2^60 (the default basis)
 };
 
 // Non-owning view of `count` ciphertexts [count][2][L][N] (evaluation form) in host or device memory.
@@ -171,9 +171,13 @@ public:
         check(dpfhe_ntt_inv(ctx_, polys, n_polys, stream));
     }
 
+    // waits for every call issued through this evaluator, whatever stream it ran on
+    void synchronize() { check(dpfhe_synchronize(ctx_)); }
+
     dpfhe_ctx *native_handle() { return ctx_; }
 
 private:
+    friend class LinearLayer;
     static void check(int status) {
         if (status != DPFHE_OK) throw std::runtime_error(dpfhe_last_error());
     }
@@ -181,6 +185,75 @@ private:
         if (a != b || a != c) throw std::runtime_error("ciphertext batches must have the same count");
     }
     dpfhe_ctx *ctx_ = nullptr;
+    unsigned log_n_, limbs_;
+};
+
+// An encrypted linear layer y = W x (baby-step/giant-step diagonals) whose weights and Galois keys live on the device.
+// diagonals: [n][L][N] plaintexts in evaluation form (diagonal g*baby + b pre-rotated by -g*baby), n a multiple of baby;
+// baby_keys: [baby-1][L][2][L][N] keys of the rotations by 1 .. baby-1 slots; giant_key: [L][2][L][N], rotation by `baby`.
+class LinearLayer {
+public:
+    LinearLayer(Evaluator &ev, const std::uint64_t *diagonals, std::size_t n_diagonals, std::size_t baby, const std::uint64_t *baby_keys,
+                const std::uint64_t *giant_key) {
+        Evaluator::check(dpfhe_linear_create(ev.native_handle(), diagonals, n_diagonals, baby, baby_keys, giant_key, &h_));
+    }
+    ~LinearLayer() { dpfhe_linear_destroy(h_); }
+    LinearLayer(const LinearLayer &) = delete;
+    LinearLayer &operator=(const LinearLayer &) = delete;
+    void apply(ConstCiphertextBatch in, CiphertextBatch out) {   // host buffers, pipelined
+        if (in.count != out.count) throw std::runtime_error("ciphertext batches must have the same count");
+        Evaluator::check(dpfhe_linear_apply_host(h_, in.data, out.data, in.count));
+    }
+    void apply_device(const std::uint64_t *in, std::uint64_t *out, std::size_t count, void *stream = nullptr) {
+        Evaluator::check(dpfhe_linear_apply(h_, in, out, count, stream));
+    }
+
+private:
+    dpfhe_linear *h_ = nullptr;
+};
+
+// Several GPUs behind one object (dpfhe_multi_*): contiguous shards of every batch, one context and host thread per device, no
+// collective.  The reference's distributed layer is one MPI rank per GPU (src/core/distributed/distributed_context.cpp:242-250).
+class MultiEvaluator {
+public:
+    // devices empty = every visible GPU
+    explicit MultiEvaluator(const EncryptionParameters &parms, const std::vector<int> &devices = {}) : log_n_(parms.log_n), limbs_(parms.n_limbs) {
+        dpfhe_params p;
+        p.log_n = parms.log_n;
+        p.n_limbs = parms.n_limbs;
+        p.moduli = parms.moduli.empty() ? nullptr : parms.moduli.data();
+        check(dpfhe_multi_create(&p, devices.empty() ? nullptr : devices.data(), (int)devices.size(), &m_));
+    }
+    ~MultiEvaluator() { dpfhe_multi_destroy(m_); }
+    MultiEvaluator(const MultiEvaluator &) = delete;
+    MultiEvaluator &operator=(const MultiEvaluator &) = delete;
+    int device_count() const { return dpfhe_multi_device_count(m_); }
+    std::size_t poly_degree() const { return std::size_t(1) << log_n_; }
+    unsigned limbs() const { return limbs_; }
+    std::uint64_t modulus(unsigned limb) const {
+        std::uint64_t q = 0;
+        check(dpfhe_get_modulus(dpfhe_multi_context(m_, 0), limb, &q));
+        return q;
+    }
+    // host buffers: every device pipelines its own shard; the result needs no gather
+    void multiply_relin(ConstCiphertextBatch a, ConstCiphertextBatch b, const std::uint64_t *relin_key, CiphertextBatch out) {
+        if (a.count != b.count || a.count != out.count) throw std::runtime_error("ciphertext batches must have the same count");
+        check(dpfhe_multi_ct_mul_relin_host(m_, a.data, b.data, relin_key, out.data, a.count));
+    }
+    // device buffers: a[r], b[r], relin_key[r] on device r (shard r of the batch); the whole result on device `root`
+    void multiply_relin_gather_device(const std::vector<const std::uint64_t *> &a, const std::vector<const std::uint64_t *> &b,
+                                      const std::vector<const std::uint64_t *> &relin_key, std::uint64_t *out_on_root, int root, std::size_t count) {
+        if ((int)a.size() != device_count() || a.size() != b.size() || a.size() != relin_key.size())
+            throw std::runtime_error("one operand pointer per device");
+        check(dpfhe_multi_ct_mul_relin_gather(m_, a.data(), b.data(), relin_key.data(), out_on_root, root, count));
+    }
+    dpfhe_multi *native_handle() { return m_; }
+
+private:
+    static void check(int status) {
+        if (status != DPFHE_OK) throw std::runtime_error(dpfhe_last_error());
+    }
+    dpfhe_multi *m_ = nullptr;
     unsigned log_n_, limbs_;
 };
 

@@ -75,6 +75,7 @@ public:
         config_["fhe.log_n"] = "13";
         config_["fhe.n_limbs"] = "4";
         config_["fhe.device"] = "0";
+        config_["fhe.devices"] = "one";   // "all": shard every encrypted batch over all visible GPUs (dpfhe_multi_*)
     }
 
     GenerationResult generate(const std::string &prompt, const GenerationConfig &config = GenerationConfig()) {
@@ -144,16 +145,23 @@ public:
 
     // ---- the encrypted route ----
     fhe::Evaluator &fhe_evaluator() {
-        if (!evaluator_) {
-            fhe::EncryptionParameters parms;
-            parms.log_n = (unsigned)std::stoul(get_config("fhe.log_n"));
-            parms.n_limbs = (unsigned)std::stoul(get_config("fhe.n_limbs"));
-            evaluator_ = std::make_unique<fhe::Evaluator>(parms, std::stoi(get_config("fhe.device")));
-        }
+        if (!evaluator_) evaluator_ = std::make_unique<fhe::Evaluator>(fhe_parameters(), std::stoi(get_config("fhe.device")));
         return *evaluator_;
+    }
+    // every visible GPU behind one evaluator: set_config("fhe.devices", "all") (BASELINE.json config 5: the batch of
+    // examples/batch_generation's encrypted path sharded over the GPUs of the box)
+    fhe::MultiEvaluator &fhe_multi_evaluator() {
+        if (!multi_) multi_ = std::make_unique<fhe::MultiEvaluator>(fhe_parameters());
+        return *multi_;
     }
 
 private:
+    fhe::EncryptionParameters fhe_parameters() {
+        fhe::EncryptionParameters parms;
+        parms.log_n = (unsigned)std::stoul(get_config("fhe.log_n"));
+        parms.n_limbs = (unsigned)std::stoul(get_config("fhe.n_limbs"));
+        return parms;
+    }
     GenerationResult run_encrypted_job(const std::string &line) {
         const auto t0 = std::chrono::steady_clock::now();
         std::istringstream in(line);
@@ -174,12 +182,20 @@ private:
         if (a.size() != ha.count * ct_words || b.size() != a.size() || k.size() != std::size_t(2) * ev.limbs() * ev.limbs() * ev.poly_degree())
             throw std::runtime_error("fhe job: payload sizes do not match the headers");
         std::vector<std::uint64_t> out(a.size());
-        ev.multiply_relin({a.data(), (std::size_t)ha.count}, {b.data(), (std::size_t)ha.count}, k.data(), {out.data(), (std::size_t)ha.count});
+        int devices = 1;
+        if (get_config("fhe.devices") == "all") {
+            fhe::MultiEvaluator &mev = fhe_multi_evaluator();   // contiguous shards, one GPU each, no collective
+            devices = mev.device_count();
+            mev.multiply_relin({a.data(), (std::size_t)ha.count}, {b.data(), (std::size_t)ha.count}, k.data(), {out.data(), (std::size_t)ha.count});
+        } else {
+            ev.multiply_relin({a.data(), (std::size_t)ha.count}, {b.data(), (std::size_t)ha.count}, k.data(), {out.data(), (std::size_t)ha.count});
+        }
         fhe::write_wire_file(fo, ha, out.data());
         GenerationResult r;
         r.generation_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::ostringstream msg;
-        msg << "wrote " << fo << ": " << ha.count << " ciphertext products (N=" << ev.poly_degree() << ", L=" << ev.limbs() << ")";
+        msg << "wrote " << fo << ": " << ha.count << " ciphertext products (N=" << ev.poly_degree() << ", L=" << ev.limbs() << ", " << devices
+            << (devices == 1 ? " GPU)" : " GPUs)");
         r.texts.push_back(msg.str());
         r.stop_reasons = std::vector<std::string>{"fhe_job_done"};
         return r;
@@ -190,6 +206,7 @@ private:
     QuantizationConfig quant_;
     bool quant_applied_ = false;
     std::unique_ptr<fhe::Evaluator> evaluator_;
+    std::unique_ptr<fhe::MultiEvaluator> multi_;
 };
 
 inline std::shared_ptr<Model> load_model(const std::string &model_path) { return std::make_shared<Model>(model_path); }

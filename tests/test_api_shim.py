@@ -76,6 +76,12 @@ def test_model_api_encrypted_route_matches_oracle(tmp_path, oracle_mod):
     hdr, data = wire.read(fo)
     assert hdr["count"] == B and hdr["kind"] == wire.CIPHERTEXTS
     assert np.array_equal(data.reshape(a.shape), o.ct_mul_relin(a, b, evk))
+    # the same job sharded over every visible GPU (config 5's route through the Model API)
+    os.remove(fo)
+    r = subprocess.run([exe, fa, fb, fk, fo, str(log_n), str(L), "all"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "GPU" in r.stdout, r.stderr
+    hdr, data = wire.read(fo)
+    assert np.array_equal(data.reshape(a.shape), o.ct_mul_relin(a, b, evk))
 
 
 def test_wire_reader_rejects_forged_headers(tmp_path, oracle_mod):

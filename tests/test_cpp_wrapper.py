@@ -35,3 +35,4 @@ def test_cpp_example_runs_on_gpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert "ct-mults per second" in r.stdout
+    assert "identical result" in r.stdout          # MultiEvaluator over every visible GPU reproduces the single-device bits
