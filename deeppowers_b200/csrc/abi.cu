@@ -246,6 +246,14 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     lc.fast = true;
     for (size_t l = 0; l < L; ++l) lc.fast = lc.fast && lps[l].nqh != 0;
     if (getenv("DPFHE_FORCE_GENERIC")) lc.fast = false;   // diagnostics: run fast-class moduli through the generic kernels
+    {
+        uint64_t qmin = ~0ull, qmax = 0;
+        for (size_t l = 0; l < L; ++l) {
+            qmin = lps[l].q < qmin ? lps[l].q : qmin;
+            qmax = lps[l].q > qmax ? lps[l].q : qmax;
+        }
+        lc.lift_reduce = !(qmax < 2 * qmin) || getenv("DPFHE_LIFT_REDUCE") != nullptr;
+    }
     lc.lp = ctx->d_lp;
     memset(&lc.lt, 0, sizeof(lc.lt));
     for (size_t l = 0; l < L; ++l) lc.lt.lp[l] = lps[l];
@@ -515,8 +523,23 @@ int dpfhe_rotate_hybrid(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_el
 // decomposition and its L(L-1) forward transforms are done once per ciphertext (kernels.cu: ks_hoist_kernel), each
 // rotation is then gathers + multiply-accumulates (rot_apply_kernel).  Ciphertexts whose digit has a zero coefficient
 // (where the shared-transform identity does not hold) are recomputed by the ordinary rotate kernel.
-int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, const uint64_t *galois_elts, const uint64_t *const *d_gks,
-                         uint64_t *d_out, size_t batch, void *stream) {
+// prepared: optional per-rotation constants kept by the caller (a linear layer applies the same rotations to every batch):
+// for rotation r, prepared[2r] = the key's Shoup companions [L][2][L][N], prepared[2r+1] = kprime [2][L][N].
+static int ensure_hoist_consts(dpfhe_ctx *ctx) {
+    const size_t L = ctx->hp.L, P = ctx->P();
+    if (ctx->hoist_M) return DPFHE_OK;
+    CU_TRY(cudaMalloc(&ctx->hoist_M, P * sizeof(u64)));
+    CU_TRY(cudaMalloc(&ctx->hoist_kprime, 2 * P * sizeof(u64)));
+    CU_TRY(cudaMalloc(&ctx->hoist_delta, L * L * sizeof(u64)));
+    std::vector<u64> delta(L * L);
+    for (size_t j = 0; j < L; ++j)
+        for (size_t i = 0; i < L; ++i) delta[j * L + i] = ctx->hp.limbs[j].lp.q % ctx->hp.limbs[i].lp.q;
+    CU_TRY(cudaMemcpy(ctx->hoist_delta, delta.data(), delta.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    return DPFHE_OK;
+}
+
+static int rotate_hoisted_impl(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, const uint64_t *galois_elts, const uint64_t *const *d_gks,
+                               const uint64_t *const *prepared, uint64_t *d_out, size_t batch, void *stream) {
     int rc = enter(ctx);
     if (rc) return rc;
     if (batch == 0 || n_rot == 0) return DPFHE_OK;
@@ -551,15 +574,8 @@ int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, con
         CU_TRY(cudaMalloc(&ctx->hoist_zero, chunk * sizeof(u32)));
         ctx->hoist_chunk = chunk;
     }
-    if (!ctx->hoist_M) {
-        CU_TRY(cudaMalloc(&ctx->hoist_M, P * sizeof(u64)));
-        CU_TRY(cudaMalloc(&ctx->hoist_kprime, 2 * P * sizeof(u64)));
-        CU_TRY(cudaMalloc(&ctx->hoist_delta, L * L * sizeof(u64)));
-        std::vector<u64> delta(L * L);
-        for (size_t j = 0; j < L; ++j)
-            for (size_t i = 0; i < L; ++i) delta[j * L + i] = ctx->hp.limbs[j].lp.q % ctx->hp.limbs[i].lp.q;
-        CU_TRY(cudaMemcpy(ctx->hoist_delta, delta.data(), delta.size() * sizeof(u64), cudaMemcpyHostToDevice));
-    }
+    rc = ensure_hoist_consts(ctx);
+    if (rc) return rc;
     for (size_t first = 0; first < batch; first += chunk) {
         const size_t cnt = batch - first < chunk ? batch - first : chunk;
         const u64 *in = d_ct + first * 2 * P;
@@ -570,16 +586,25 @@ int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, con
         }
         for (size_t r = 0; r < n_rot; ++r) {
             u64 *out = d_out + (r * batch + first) * 2 * P;
-            CU_TRY(VCALL(launch_rot_prepare, ctx->lc, d_gks[r], (u32)galois_elts[r], ctx->hoist_delta, ctx->hoist_M, ctx->hoist_kprime, st));
-            CU_TRY(VCALL(launch_rot_apply, ctx->lc, in, L > 1 ? ctx->hoist_U : nullptr, d_gks[r], ctx->hoist_kprime, (u32)galois_elts[r], out, cnt, st));
-            note_launch(ctx, 5);   // key_prepare, negmask, ntt, kprime, rot_apply
+            const u64 *key_s = prepared ? prepared[2 * r] : nullptr, *kprime = prepared ? prepared[2 * r + 1] : ctx->hoist_kprime;
+            if (!prepared) {
+                CU_TRY(VCALL(launch_rot_prepare, ctx->lc, d_gks[r], (u32)galois_elts[r], ctx->hoist_delta, ctx->hoist_M, ctx->hoist_kprime, st));
+                note_launch(ctx, 4);   // key_prepare, negmask, ntt, kprime
+            }
+            CU_TRY(VCALL(launch_rot_apply, ctx->lc, in, L > 1 ? ctx->hoist_U : nullptr, d_gks[r], kprime, (u32)galois_elts[r], out, cnt, st, key_s));
+            note_launch(ctx, 1);
             if (L > 1) {
-                CU_TRY(VCALL(launch_ks, ctx->lc, KS_ROTATE, in, nullptr, d_gks[r], out, cnt, (u32)galois_elts[r], st, ctx->hoist_zero, true));
+                CU_TRY(VCALL(launch_ks, ctx->lc, KS_ROTATE, in, nullptr, d_gks[r], out, cnt, (u32)galois_elts[r], st, ctx->hoist_zero, true, key_s));
                 note_launch(ctx, 1);
             }
         }
     }
     return DPFHE_OK;
+}
+
+int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, const uint64_t *galois_elts, const uint64_t *const *d_gks,
+                         uint64_t *d_out, size_t batch, void *stream) {
+    return rotate_hoisted_impl(ctx, d_ct, n_rot, galois_elts, d_gks, nullptr, d_out, batch, stream);
 }
 
 int dpfhe_ct_mul_plain(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_pt, uint64_t *d_out, size_t batch, void *stream) {
@@ -897,6 +922,8 @@ struct dpfhe_linear {
     u64 *d_keys = nullptr;                  // [baby-1 + 1][L][2][L][N]: baby-step keys, then the giant-step key
     std::vector<uint64_t> g_baby;           // Galois elements 5^b, b = 1 .. baby-1
     std::vector<const uint64_t *> k_baby;   // device pointers of the baby-step keys
+    u64 *d_prep = nullptr;                  // per baby step: Shoup companions of its key [L][2][L][N] + kprime [2][L][N], built once
+    std::vector<const uint64_t *> prep;     // {companions, kprime} pointers per baby step (rotate_hoisted_impl)
     uint64_t g_giant = 0;
     u64 *scratch = nullptr;                 // [baby + giant + 1][cap][2][L][N]
     size_t cap = 0;                         // ciphertexts the scratch holds
@@ -945,6 +972,26 @@ int dpfhe_linear_create(dpfhe_ctx *ctx, const uint64_t *h_diags, size_t n_diags,
         lin->k_baby.push_back(lin->d_keys + (b - 1) * key_bytes / 8);
     }
     dpfhe_galois_element(ctx, (int)baby, &lin->g_giant);
+    // the constants of the baby-step rotations do not depend on the data: prepare them once (four small launches per rotation
+    // that every hoisted call would otherwise repeat — a tenth of a 31-rotation call at batch 512, more for smaller chunks)
+    if (baby > 1) {
+        const size_t ks_words = 2 * ctx->hp.L * ctx->P(), kp_words = 2 * ctx->P();
+        int rc2 = ensure_hoist_consts(ctx);
+        e = rc2 == DPFHE_OK ? cudaMalloc(&lin->d_prep, (baby - 1) * (ks_words + kp_words) * 8) : cudaErrorMemoryAllocation;
+        cudaStream_t st = pick(ctx, nullptr);
+        for (size_t b = 1; b < baby && e == cudaSuccess; ++b) {
+            u64 *ks = lin->d_prep + (b - 1) * (ks_words + kp_words), *kp = ks + ks_words;
+            e = VCALL(launch_rot_prepare, ctx->lc, lin->k_baby[b - 1], (u32)lin->g_baby[b - 1], ctx->hoist_delta, ctx->hoist_M, kp, st, ks);
+            note_launch(ctx, 4);
+            lin->prep.push_back(ks);
+            lin->prep.push_back(kp);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            dpfhe_linear_destroy(lin);
+            return fail(DPFHE_ERR_CUDA, "linear layer constants: %s", cudaGetErrorString(e));
+        }
+    }
     *out = lin;
     return DPFHE_OK;
 }
@@ -957,6 +1004,7 @@ void dpfhe_linear_destroy(dpfhe_linear *lin) {
     }
     cudaFree(lin->d_diags);
     cudaFree(lin->d_keys);
+    cudaFree(lin->d_prep);
     cudaFree(lin->scratch);
     delete lin;
 }
@@ -968,7 +1016,8 @@ static int linear_apply_on(dpfhe_linear *lin, const uint64_t *d_ct, uint64_t *d_
     cudaStream_t st = pick(ctx, stream);
     CU_TRY(cudaMemcpyAsync(steps, d_ct, ctb * 8, cudaMemcpyDeviceToDevice, st));
     int rc = DPFHE_OK;
-    if (lin->baby > 1) rc = dpfhe_rotate_hoisted(ctx, steps, lin->baby - 1, lin->g_baby.data(), lin->k_baby.data(), steps + ctb, batch, stream);
+    if (lin->baby > 1)
+        rc = rotate_hoisted_impl(ctx, steps, lin->baby - 1, lin->g_baby.data(), lin->k_baby.data(), lin->prep.data(), steps + ctb, batch, stream);
     if (rc) return rc;
     rc = dpfhe_ct_mul_plain_inner(ctx, steps, lin->baby, lin->d_diags, lin->giant, inner, batch, stream);
     if (rc) return rc;

@@ -253,6 +253,7 @@ struct KsArgs {
     u64 *hyb;            // hybrid only: [groups][KS_HYB_ROWS][N]: special-limb accumulators (rows 0,1) and tau'
     const u32 *only;     // optional [batch]: process only the ciphertexts whose entry is non-zero (hoisted-rotation fallback)
     u32 acc_par;         // accumulator row pairs per slot: 1, or 2 in hybrid key switching (the division step runs one round late)
+    u32 lift_reduce;     // 0: every modulus is below twice every other one, a digit needs no reduction when it changes limb; 1: reduce
 };
 // tau' rows of a hybrid group are double-buffered by round parity (KS_HYB_ROWS, types.hpp)
 DPFHE_HD u32 ks_hyb_tau_row(u32 parity, u32 c) { return 2u + 2u * parity + c; }
@@ -503,9 +504,13 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
             }
         });
     };
+    // lift of the digit into Z_{q_i}: t_j < q_j.  When every modulus of the basis is below twice every other one (the default
+    // basis: all within 2^-22 of 2^60), t_j < 2 q_i already and the word reduction (three multiplies per coefficient) is skipped.
+    const bool lift = A.lift_reduce != 0u;
     if constexpr (LOGN <= 13) {
         cta.par([&](int tid) {
-            fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); });
+            if (lift) fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); });
+            else fwd_load_stage<LOGN, NT, false>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); });
         });
         cta.mark(4);   // digit fetch + lift + outer forward stage
         fwd_passes<LOGN, NT, 3>(cta, buf, tw, p);
@@ -517,7 +522,8 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
         constexpr int HC = NC / 2;
         for (int h = 0; h < 2; ++h) {
             cta.par([&](int tid) {
-                fwd_load_stage_half<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); }, h);
+                if (lift) fwd_load_stage_half<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); }, h);
+                else fwd_load_stage_half<LOGN, NT, false>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); }, h);
             });
             cta.mark(4);
             fwd_passes_blk<LOGN, NT, 3, 2>(cta, buf, tw, p, 2 * h);

@@ -804,7 +804,7 @@ cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
     A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L - 1; A.galois = galois; A.Lk = lc.L; A.hyb = lc.ks_hyb; A.only = nullptr;
-    A.acc = lc.ks_acc_hyb; A.acc_par = 2;
+    A.acc = lc.ks_acc_hyb; A.acc_par = 2; A.lift_reduce = lc.lift_reduce ? 1u : 0u;
 #define KS_HYB_DISPATCH(LOGN)                                                                   \
     switch (mode) {                                                                             \
         case KS_MUL_RELIN: return launch_ks_hybrid_t<LOGN, KS_MUL_RELIN>(lc, A, K, batch, st);   \
@@ -919,11 +919,12 @@ cudaError_t launch_hoist(LaunchCtx &lc, const u64 *ct, u64 *U, u32 *zero, size_t
 }
 
 // per-rotation constants: Shoup companions of the key (lc.ks_key_s), M = NTT(negmask_g) (in `M`, [L][N]) and kprime [2][L][N]
-cudaError_t launch_rot_prepare(LaunchCtx &lc, const u64 *key, u32 galois, const u64 *delta, u64 *M, u64 *kprime, cudaStream_t st) {
+cudaError_t launch_rot_prepare(LaunchCtx &lc, const u64 *key, u32 galois, const u64 *delta, u64 *M, u64 *kprime, cudaStream_t st, u64 *key_s_out) {
+    u64 *key_s = key_s_out ? key_s_out : lc.ks_key_s;   // a caller that keeps the constants of a rotation supplies its own buffer
     const size_t n = (size_t)2 * lc.L * lc.L << lc.log_n;
     const unsigned grid = ew_grid(lc, n), gsmall = ew_grid(lc, (size_t)2 * lc.L << lc.log_n);
 #define ROT_PREP(LOGN)                                                                              \
-    key_prepare_kernel<LOGN><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);               \
+    key_prepare_kernel<LOGN><<<grid, 256, 0, st>>>(key, key_s, lc.lp, lc.L, n);                      \
     negmask_kernel<LOGN><<<(1u << LOGN) / 256, 256, 0, st>>>(M, galois, lc.L);
     switch (lc.log_n) {
         case 12: ROT_PREP(12) break;
@@ -945,10 +946,10 @@ cudaError_t launch_rot_prepare(LaunchCtx &lc, const u64 *key, u32 galois, const 
 
 // hoisted rotations, step 2: one rotation of `batch` ciphertexts from the shared transforms (constants from launch_rot_prepare)
 cudaError_t launch_rot_apply(const LaunchCtx &lc, const u64 *ct, const u64 *U, const u64 *key, const u64 *kprime, u32 galois, u64 *out,
-                             size_t batch, cudaStream_t st) {
+                             size_t batch, cudaStream_t st, const u64 *key_s) {
     if (batch == 0) return cudaSuccess;
     RotApplyArgs A;
-    A.ct = ct; A.U = U; A.key = key; A.key_s = lc.ks_key_s; A.kprime = kprime; A.out = out; A.L = lc.L; A.galois = galois;
+    A.ct = ct; A.U = U; A.key = key; A.key_s = key_s ? key_s : lc.ks_key_s; A.kprime = kprime; A.out = out; A.L = lc.L; A.galois = galois;
     // rows are cut into up to NC / 256 segments so that small batches still fill the machine several times over
     // tuning variant (DPFHE_ROT_CFG): 0 (default) = two ciphertexts share each key chunk, next digit prefetched;
     // 1 = one ciphertext per item, prefetched; 2 = one ciphertext, no prefetch.  Measured 11.1 / 12.1 / 11.9 ms for 31
@@ -975,7 +976,7 @@ cudaError_t launch_rot_apply(const LaunchCtx &lc, const u64 *ct, const u64 *U, c
 }
 
 cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch,
-                      u32 galois, cudaStream_t st, const u32 *only, bool key_ready) {
+                      u32 galois, cudaStream_t st, const u32 *only, bool key_ready, const u64 *key_s) {
     if (batch == 0) return cudaSuccess;
     // Shoup companions of the key for this launch (2*L*P words, a few microseconds; batch-amortised)
     if (!key_ready) {
@@ -988,9 +989,9 @@ cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const
         if (e != cudaSuccess) return e;
     }
     KsArgs A;
-    A.a = a; A.b = b; A.key = key; A.key_s = lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
+    A.a = a; A.b = b; A.key = key; A.key_s = key_ready && key_s ? key_s : lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
     A.tw = lc.tw; A.itw = lc.itw; A.L = lc.L; A.galois = galois; A.Lk = lc.L; A.hyb = nullptr; A.only = only;
-    A.acc = lc.ks_acc; A.acc_par = 1;
+    A.acc = lc.ks_acc; A.acc_par = 1; A.lift_reduce = lc.lift_reduce ? 1u : 0u;
 #define KS_DISPATCH(LOGN)                                                              \
     switch (mode) {                                                                    \
         case KS_MUL_RELIN: return launch_ks_t<LOGN, KS_MUL_RELIN>(lc, A, batch, st);   \

@@ -13,6 +13,7 @@ struct LaunchCtx {
     int num_sms = 0;
     u32 log_n = 0, L = 0;
     bool fast = false;                // every modulus is k * 2^32 + 1: launches go to the dpfhe::fast kernels
+    bool lift_reduce = true;          // some modulus is at least twice another: digits are word-reduced when they change limb
     const LimbParams *lp = nullptr;   // [L] device copy (element-wise kernels)
     LimbTable lt;                     // host copy, passed by value to the transform kernels
     int rot_cfg = 0;                  // tuning variant of rot_apply_kernel (DPFHE_ROT_CFG)
@@ -45,11 +46,12 @@ struct LaunchCtx {
 #define DPFHE_DECLARE_LAUNCHERS \
     cudaError_t launch_ntt(const LaunchCtx &lc, u64 *data, size_t n_polys, bool inverse, cudaStream_t st); \
     cudaError_t launch_ks(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, \
-                          u32 galois, cudaStream_t st, const u32 *only = nullptr, bool key_ready = false); \
+                          u32 galois, cudaStream_t st, const u32 *only = nullptr, bool key_ready = false, const u64 *key_s = nullptr); \
     cudaError_t launch_hoist(LaunchCtx &lc, const u64 *ct, u64 *U, u32 *zero, size_t batch, cudaStream_t st); \
-    cudaError_t launch_rot_prepare(LaunchCtx &lc, const u64 *key, u32 galois, const u64 *delta, u64 *M, u64 *kprime, cudaStream_t st); \
+    cudaError_t launch_rot_prepare(LaunchCtx &lc, const u64 *key, u32 galois, const u64 *delta, u64 *M, u64 *kprime, cudaStream_t st, \
+                                   u64 *key_s_out = nullptr); \
     cudaError_t launch_rot_apply(const LaunchCtx &lc, const u64 *ct, const u64 *U, const u64 *key, const u64 *kprime, u32 galois, u64 *out, \
-                                 size_t batch, cudaStream_t st); \
+                                 size_t batch, cudaStream_t st, const u64 *key_s = nullptr); \
     cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, u32 galois, \
                                  const MsConsts &K, cudaStream_t st); \
     cudaError_t launch_pt_inner(const LaunchCtx &lc, const u64 *steps, u32 nb, const u64 *pts, u32 ng, u64 *out, size_t batch, cudaStream_t st, \
@@ -69,6 +71,7 @@ namespace fast {
 DPFHE_DECLARE_LAUNCHERS
 }
 #undef DPFHE_DECLARE_LAUNCHERS
-// launch_ks: `only` = optional [batch] filter (non-zero = process); key_ready: lc.ks_key_s already holds this key's Shoup companions
+// launch_ks: `only` = optional [batch] filter (non-zero = process); key_ready: the key's Shoup companions are already in key_s
+// (or, with key_s == nullptr, in lc.ks_key_s).  launch_rot_prepare / launch_rot_apply: key_s(_out) == nullptr means lc.ks_key_s.
 
 }  // namespace dpfhe

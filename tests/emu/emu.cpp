@@ -43,6 +43,7 @@ T *aligned_new(size_t n) {
 struct Emu {
     HostParams hp;
     std::vector<LimbParams> lp;
+    uint32_t lift_reduce = 1;   // as abi.cu: 0 when every modulus is below twice every other one
     Twiddle *tw = nullptr, *itw = nullptr;
     ~Emu() {
         free(tw);
@@ -107,7 +108,7 @@ void run_ks(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t *key, u
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = key_s; A.out = out; A.scratch = scratch;
     A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois; A.Lk = L; A.hyb = nullptr; A.only = nullptr;
-    A.acc = acc; A.acc_par = 1;
+    A.acc = acc; A.acc_par = 1; A.lift_reduce = e.lift_reduce;
     HostCta cta{NT};
     const size_t n_work = batch * L;
     for (size_t r = 0; r * G < n_work; ++r) {
@@ -158,7 +159,7 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
     KsArgs A;
     A.a = a; A.b = b; A.key = key; A.key_s = key_s; A.out = out; A.scratch = scratch;
     A.tw = e.tw; A.itw = e.itw; A.L = L; A.galois = galois; A.Lk = LK; A.hyb = hyb_all; A.only = nullptr;
-    A.acc = acc; A.acc_par = 2;
+    A.acc = acc; A.acc_par = 2; A.lift_reduce = e.lift_reduce;
     auto acc_of = [&](unsigned slot, unsigned parity) { return acc + ((size_t)slot * 2 + parity) * 2 * N; };
     HostCta cta{NT};
     for (size_t r = 0; r * groups < batch; ++r) {
@@ -291,6 +292,12 @@ void *emu_create(unsigned log_n, unsigned L, const uint64_t *moduli) {
         memcpy(e->tw + l * N, e->hp.limbs[l].tw.data(), N * sizeof(Twiddle));
         memcpy(e->itw + l * N, e->hp.limbs[l].itw.data(), N * sizeof(Twiddle));
     }
+    uint64_t qmin = ~0ull, qmax = 0;
+    for (unsigned l = 0; l < L; ++l) {
+        qmin = e->lp[l].q < qmin ? e->lp[l].q : qmin;
+        qmax = e->lp[l].q > qmax ? e->lp[l].q : qmax;
+    }
+    e->lift_reduce = qmax < 2 * qmin ? 0u : 1u;
     return e;
 }
 void emu_destroy(void *h) { delete (Emu *)h; }

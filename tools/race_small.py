@@ -33,4 +33,34 @@ for log_n, L, B in ((13, 4, 3), (12, 2, 2), (14, 2, 1)):
     c.ct_mul_plain_inner(hout, pts, iout, 2, 3, B)
     torch.cuda.synchronize()
     c.close()
+# round 2: the generic arithmetic variant on the same basis, single-buffered digit slots, logical multi-device shards with the
+# peer-store gather (outputs written once into another context's buffer), the linear-layer object
+import numpy as np
+for env in ({"DPFHE_FORCE_GENERIC": "1"}, {"DPFHE_KS_SINGLE": "1"}):
+    os.environ.update(env)
+    c = dp.Context(13, 4)
+    N, L, B = 8192, 4, 3
+    a = torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda"); b = torch.empty_like(a); out = torch.empty_like(a)
+    evk = torch.empty((L, 2, L, N), dtype=torch.int64, device="cuda")
+    c.fill_uniform(1, a, 2 * B); c.fill_uniform(2, b, 2 * B); c.fill_uniform(3, evk, 2 * L)
+    c.ntt_fwd(a, 2 * B); c.ntt_inv(a, 2 * B)
+    c.ct_mul_relin(a, b, evk, out, B); c.ct_mul_relin(a, b, evk, out, B); c.rotate(a, 5, evk, out, B)
+    torch.cuda.synchronize()
+    c.close()
+    for k in env:
+        del os.environ[k]
+m = dp.MultiContext(12, 2, devices=[0, 0])
+B, L, N = 5, 2, 4096
+ha = np.zeros((B, 2, L, N), dtype=np.uint64); hk = np.zeros((L, 2, L, N), dtype=np.uint64); ho = np.zeros_like(ha)
+m.ct_mul_relin_host(ha, ha, hk, ho)
+sh = [m.shard(B, r) for r in range(2)]
+da = [torch.zeros((cnt, 2, L, N), dtype=torch.int64, device="cuda") for _, cnt in sh]
+dk = [torch.zeros((L, 2, L, N), dtype=torch.int64, device="cuda") for _ in sh]
+root = torch.zeros((B, 2, L, N), dtype=torch.int64, device="cuda")
+torch.cuda.synchronize()
+m.ct_mul_relin_gather(da, da, dk, root, 1, B)
+lay = dp.LinearLayer(m.contexts[0], np.zeros((4, L, N), dtype=np.uint64), 2, np.zeros((1, L, 2, L, N), dtype=np.uint64), hk)
+lay.apply_host(ha, ho)
+lay.close()
+m.close()
 print("ok")
