@@ -1052,11 +1052,12 @@ int dpfhe_linear_apply_host(dpfhe_linear *lin, const uint64_t *h_ct, uint64_t *h
     if (rc) return rc;
     if (batch == 0) return DPFHE_OK;
     if (!h_ct || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
-    // Chunks of about a third of the batch, rounded to whole rounds of the persistent key-switch grid (3 CTAs per SM, L CTAs
+    // Chunks of about a fifth of the batch, rounded to whole rounds of the persistent key-switch grid (3 CTAs per SM, L CTAs
     // per ciphertext): a chunk that leaves the grid's last round mostly empty costs more than the transfers it hides.  The
     // first upload and the last download are the only transfers not overlapped with a neighbouring chunk's compute.
     const size_t groups = std::max<size_t>(1, (size_t)ctx->lc.num_sms * 3 / ctx->hp.L);
-    size_t rounds = (batch / 3 + groups / 2) / groups;
+    size_t rounds = (batch / 5 + groups / 2) / groups;
+    if (const char *e = getenv("DPFHE_LINEAR_CHUNK_ROUNDS")) rounds = (size_t)atol(e);   // tuning
     if (rounds < 1) rounds = 1;
     size_t chunk = rounds * groups;
     if (chunk > 512) chunk = std::max<size_t>(groups, 512 / groups * groups);
