@@ -515,3 +515,35 @@ def test_explicit_stream_and_two_contexts(dp, ctxs):
     assert np.array_equal(host(out1).reshape(ref.shape), ref)
     assert np.array_equal(host(out2).reshape(ref.shape), ref)
     c2.close()
+
+
+def test_generic_kernels_on_the_default_basis(dp, oracle_mod, monkeypatch):
+    """The default basis (k * 2^32 + 1 moduli) selects the dpfhe::fast kernels; DPFHE_FORCE_GENERIC runs the same basis through
+    dpfhe::gen, which must give the same bits (both variants are products, not one a fallback of the other), and
+    DPFHE_LIFT_REDUCE keeps the word reduction of the digit lift that the default basis may skip."""
+    log_n, L, B = 13, 4, 40
+    o = oracle_mod.Oracle(log_n, L)
+    s = o.keygen_secret(1)
+    evk = o.keygen_relin(2, 65537, s)
+    g = o.galois_elt(-3)
+    gk = o.keygen_galois(4, 65537, s, g)
+    a = edge_polys(o, 2 * B, 51).reshape(B, 2, L, o.N)
+    b = edge_polys(o, 2 * B, 52).reshape(B, 2, L, o.N)
+    want_mul, want_rot, want_ntt = o.ct_mul_relin(a, b, evk), o.rotate(a, g, gk), o.ntt_fwd(a.reshape(2 * B, L, o.N))
+    for env in ({"DPFHE_FORCE_GENERIC": "1"}, {"DPFHE_LIFT_REDUCE": "1"}, {"DPFHE_KS_SINGLE": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c = dp.Context(log_n, L)
+        out = torch.zeros((B, 2, L, o.N), dtype=torch.int64, device="cuda")
+        c.ct_mul_relin(dev(a), dev(b), dev(evk), out, B)
+        assert np.array_equal(host(out), want_mul), env
+        c.rotate(dev(a), g, dev(gk), out, B)
+        assert np.array_equal(host(out), want_rot), env
+        d = dev(a)
+        c.ntt_fwd(d, 2 * B)
+        assert np.array_equal(host(d).reshape(want_ntt.shape), want_ntt), env
+        c.ntt_inv(d, 2 * B)
+        assert np.array_equal(host(d), a), env
+        c.close()
+        for k in env:
+            monkeypatch.delenv(k)
