@@ -169,6 +169,15 @@ def cpu_sample(oracle_ctx, seconds, threads):
     return done / total, done, total
 
 
+def workload_name(world, batch):
+    """config.workload of both arms: BASELINE.json config 2 on one GPU, config 5's layout (8192 per GPU) on several"""
+    B = batch or (BATCH if world == 1 else BATCH_MULTI)
+    if world == 1:
+        return "ct x ct multiply + relinearise, N=8192, L=4, batch=%d (BASELINE.json config 2)" % B
+    return ("ct x ct multiply + relinearise, N=8192, L=4, batch=%d sharded over %d GPUs, %d per GPU (BASELINE.json config 5: 65536 over 8)"
+            % (world * B, world, B))
+
+
 def run_reference(args):
     """CPU arm: the oracle port on all host threads (the reference has no implementation to run)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -182,7 +191,7 @@ def run_reference(args):
     evk = o.keygen_relin(2, 65537, s)
     # bounded sample per step: about 2 s of CPU work, at most 1024 ciphertexts
     rate, _, _ = cpu_sample(o, 1.0, threads)
-    n = int(max(threads, min(1024, args.batch, rate * 2.0)))
+    n = int(max(threads, min(1024, args.batch or BATCH, rate * 2.0)))
     a = o.fill_uniform(SEED, 2 * n).reshape(n, 2, L, N)
     b = o.fill_uniform(SEED, 2 * n, first_poly=2 * n).reshape(n, 2, L, N)
     _, out = o.time_ct_mul_relin(a, b, evk, threads)     # the output buffer is touched once and reused: no page faults in the timed steps
@@ -197,8 +206,8 @@ def run_reference(args):
         "impl": "reference", "metric": "ct_mult_relin_per_s", "value": value, "unit": "ct-mult/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "ct x ct multiply + relinearise, N=8192, L=4 (BASELINE.json config 2)",
-                   "sample": "%d ciphertexts per step on the host CPU" % n},
+        "config": {"workload": workload_name(int(os.environ.get("WORLD_SIZE", "1")), args.batch),
+                   "sample": "%d ciphertexts per step on the host CPU (a bounded sample of that workload)" % n},
         "cpu_baseline": {"value": value, "unit": "ct-mult/s", "cores": threads, "kind": "port",
                          "sample": "%d ct-mults per step x %d steps, oracle/dpfhe_oracle.c with OpenMP" % (n, args.steps)},
         "e2e": {"value": value, "unit": "ct-mult/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -461,8 +470,7 @@ def main():
             threads = pick_threads(o)
             na, nb, nk, _, _ = host
             cpu, parity = cpu_leg(o, threads, na, nb, nk, out.cpu().numpy().view(np.uint64), args.cpu_seconds)
-        workload = ("ct x ct multiply + relinearise, N=8192, L=4, batch=%d (BASELINE.json config 2)" % B if world == 1 else
-                    "ct x ct multiply + relinearise, N=8192, L=4, batch=%d sharded over %d GPUs, %d per GPU (BASELINE.json config 5: 65536 over 8)" % (world * B, world, B))
+        workload = workload_name(world, args.batch)
         line = {
             "metric": "ct_mult_relin_per_s", "value": value, "unit": "ct-mult/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
