@@ -59,6 +59,13 @@ def lib():
         "dpo_keyswitch_hybrid": (None, [vp, u64p, u64p, u64, u64p, u64p]),
         "dpo_ct_mul_relin_hybrid": (None, [vp, u64p, u64p, u64p, u64, u64p, sz]),
         "dpo_rotate_hybrid": (None, [vp, u64p, u64, u64p, u64, u64p, sz]),
+        "dpo_grouped_digits": (C.c_uint, [vp, C.c_uint]),
+        "dpo_mod_down_special": (None, [vp, C.c_uint, u64p, u64, u64p, sz]),
+        "dpo_keyswitch_grouped": (None, [vp, C.c_uint, u64p, u64p, u64, u64p, u64p]),
+        "dpo_ct_mul_relin_grouped": (None, [vp, C.c_uint, u64p, u64p, u64p, u64, u64p, sz]),
+        "dpo_rotate_grouped": (None, [vp, C.c_uint, u64p, u64, u64p, u64, u64p, sz]),
+        "dpo_keygen_relin_grouped": (None, [vp, C.c_uint, u64, u64, u64p, u64p]),
+        "dpo_keygen_galois_grouped": (None, [vp, C.c_uint, u64, u64, u64p, u64, u64p]),
         "dpo_keygen_relin_hybrid": (None, [vp, u64, u64, u64p, u64p]),
         "dpo_keygen_galois_hybrid": (None, [vp, u64, u64, u64p, u64, u64p]),
         "dpo_galois_perm": (None, [vp, u64, u32p]),
@@ -225,6 +232,48 @@ class Oracle:
     def keygen_galois_hybrid(self, seed, t, s, g):
         k = np.empty((self.L - 1, 2, self.L, self.N), dtype=np.uint64)
         self._l.dpo_keygen_galois_hybrid(self._c, int(seed), int(t), s.reshape(-1), int(g), k.reshape(-1))
+        return k
+
+    # grouped hybrid key switching: the last K limbs are special primes, data has L-K limbs, keys have ceil((L-K)/K) digits
+    def grouped_digits(self, K):
+        return int(self._l.dpo_grouped_digits(self._c, int(K)))
+
+    def mod_down_special(self, K, polys, t_plain=0):
+        x = np.ascontiguousarray(polys, dtype=np.uint64).reshape(-1, self.L, self.N)
+        out = np.empty((x.shape[0], self.L - K, self.N), dtype=np.uint64)
+        self._l.dpo_mod_down_special(self._c, int(K), x.reshape(-1), int(t_plain), out.reshape(-1), x.shape[0])
+        return out
+
+    def keyswitch_grouped(self, K, d, key, t_plain=0):
+        c0 = np.empty((self.L - K, self.N), dtype=np.uint64)
+        c1 = np.empty((self.L - K, self.N), dtype=np.uint64)
+        self._l.dpo_keyswitch_grouped(self._c, int(K), np.ascontiguousarray(d).reshape(-1), np.ascontiguousarray(key).reshape(-1), int(t_plain),
+                                      c0.reshape(-1), c1.reshape(-1))
+        return c0, c1
+
+    def ct_mul_relin_grouped(self, K, a, b, evk, t_plain=0):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        self._l.dpo_ct_mul_relin_grouped(self._c, int(K), a.reshape(-1), np.ascontiguousarray(b).reshape(-1),
+                                         np.ascontiguousarray(evk).reshape(-1), int(t_plain), out.reshape(-1),
+                                         a.size // (2 * (self.L - K) * self.N))
+        return out
+
+    def rotate_grouped(self, K, ct, galois_elt, gk, t_plain=0):
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        out = np.empty_like(ct)
+        self._l.dpo_rotate_grouped(self._c, int(K), ct.reshape(-1), int(galois_elt), np.ascontiguousarray(gk).reshape(-1), int(t_plain),
+                                   out.reshape(-1), ct.size // (2 * (self.L - K) * self.N))
+        return out
+
+    def keygen_relin_grouped(self, K, seed, t, s):
+        k = np.empty((self.grouped_digits(K), 2, self.L, self.N), dtype=np.uint64)
+        self._l.dpo_keygen_relin_grouped(self._c, int(K), int(seed), int(t), s.reshape(-1), k.reshape(-1))
+        return k
+
+    def keygen_galois_grouped(self, K, seed, t, s, g):
+        k = np.empty((self.grouped_digits(K), 2, self.L, self.N), dtype=np.uint64)
+        self._l.dpo_keygen_galois_grouped(self._c, int(K), int(seed), int(t), s.reshape(-1), int(g), k.reshape(-1))
         return k
 
     def galois_perm(self, g):

@@ -591,6 +591,164 @@ void dpo_rotate_hybrid(const dpo_ctx *c, const uint64_t *ct, uint64_t g, const u
     free(perm);
 }
 
+/* ------------------------------------------------------------------ grouped hybrid key switching (dnum < L)
+ * DESIGN.md §2.11.  The last K limbs of the context are special primes p_0..p_{K-1} (P = prod p_k); ciphertext
+ * polynomials carry Lq = L - K limbs, grouped into dnum = ceil(Lq / K) digits of alpha = K consecutive limbs (the last
+ * one may be shorter).  Q_g = product of the moduli of group g, Qhat_j = Q_g / q_j for a member j.
+ *   mod-up   (fast basis conversion, no correction: the lift is t + e*Q_g with 0 <= e < alpha):
+ *       y_j = INTT_j(d[j]) * Qhat_j^-1 mod q_j;   u_gi = NTT_i( sum_{j in g} y_j * (Qhat_j mod q_i)  mod q_i )   (i not in g)
+ *       u_gi = d[i]                                                                                            (i in g)
+ *   acc_c[i] = sum_g u_gi o key[g][c][i]                       key: [dnum][2][L][N], encrypts P * (1 on group g, 0 elsewhere) * target
+ *   mod-down (every special residue lifted centred, so delta lies in (-K P / 2, K P / 2)):
+ *       y_k = INTT(acc[Lq+k]) * (t * Phat_k)^-1 mod p_k  (t = 0: Phat_k^-1),  Phat_k = P / p_k
+ *       w_i = sum_k ( y_k * (Phat_k mod q_i) - [y_k > p_k/2] * (P mod q_i) )  mod q_i
+ *       out[i] = (acc[i] - s * NTT_i(w_i)) * P^-1 mod q_i        (s = t, or 1 when t = 0)
+ * With K = 1 every formula reduces to dpo_mod_switch_down / dpo_keyswitch_hybrid above (tests check the equality). */
+static uint64_t prod_mod(const dpo_ctx *c, unsigned lo, unsigned hi, unsigned skip, uint64_t q) {
+    uint64_t r = 1 % q;
+    for (unsigned m = lo; m < hi; m++)
+        if (m != skip) r = mulmod(r, c->q[m] % q, q);
+    return r;
+}
+
+/* in: [n_polys][L][N], out: [n_polys][L-K][N], evaluation form */
+void dpo_mod_down_special(const dpo_ctx *c, unsigned K, const uint64_t *in, uint64_t t_plain, uint64_t *out, size_t n_polys) {
+    const size_t N = c->N;
+    const unsigned L = c->L;
+    if (K < 1 || K >= L) return;
+    const unsigned Lq = L - K;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long pidx = 0; pidx < (long)n_polys; pidx++) {
+        uint64_t *y = (uint64_t *)malloc((size_t)K * N * 8), *u = (uint64_t *)malloc(N * 8);
+        const uint64_t *src = in + (size_t)pidx * L * N;
+        for (unsigned k = 0; k < K; k++) {
+            const unsigned s = Lq + k;
+            const uint64_t p = c->q[s];
+            uint64_t f = prod_mod(c, Lq, L, s, p);                       /* Phat_k mod p_k */
+            if (t_plain) f = mulmod(f, t_plain % p, p);
+            f = dpo_invmod(f, p);
+            memcpy(y + (size_t)k * N, src + (size_t)s * N, N * 8);
+            ntt_inv_limb(c, s, y + (size_t)k * N);
+            for (size_t n = 0; n < N; n++) y[(size_t)k * N + n] = mulmod(y[(size_t)k * N + n], f, p);
+        }
+        for (unsigned i = 0; i < Lq; i++) {
+            const uint64_t q = c->q[i];
+            const uint64_t Pm = prod_mod(c, Lq, L, L, q), inv = dpo_invmod(Pm, q), sfac = t_plain ? t_plain % q : 1;
+            for (size_t n = 0; n < N; n++) u[n] = 0;
+            for (unsigned k = 0; k < K; k++) {
+                const uint64_t p = c->q[Lq + k], half = p >> 1, ph = prod_mod(c, Lq, L, Lq + k, q);
+                for (size_t n = 0; n < N; n++) {
+                    const uint64_t v = y[(size_t)k * N + n];
+                    uint64_t r = mulmod(v % q, ph, q);
+                    if (v > half) r = submod(r, Pm, q);                  /* centred: (v - p_k) * Phat_k */
+                    u[n] = addmod(u[n], r, q);
+                }
+            }
+            ntt_fwd_limb(c, i, u);
+            uint64_t *dst = out + ((size_t)pidx * Lq + i) * N;
+            for (size_t n = 0; n < N; n++)
+                dst[n] = mulmod(submod(src[(size_t)i * N + n], mulmod(u[n], sfac, q), q), inv, q);
+        }
+        free(y);
+        free(u);
+    }
+}
+
+unsigned dpo_grouped_digits(const dpo_ctx *c, unsigned K) { return K >= 1 && K < c->L ? (c->L - K + K - 1) / K : 0; }
+
+/* d: [Lq][N]; key: [dnum][2][L][N]; c0, c1: [Lq][N] */
+void dpo_keyswitch_grouped(const dpo_ctx *c, unsigned K, const uint64_t *d, const uint64_t *key, uint64_t t_plain, uint64_t *c0, uint64_t *c1) {
+    const size_t N = c->N, PK = c->L * N;
+    const unsigned L = c->L, Lq = L - K, dnum = dpo_grouped_digits(c, K);
+    uint64_t *y = (uint64_t *)malloc((size_t)K * N * 8), *u = (uint64_t *)malloc(N * 8);
+    uint64_t *acc = (uint64_t *)calloc(2 * PK, 8), *low = (uint64_t *)malloc(2 * (size_t)Lq * N * 8);
+    for (unsigned g = 0; g < dnum; g++) {
+        const unsigned lo = g * K, hi = lo + K < Lq ? lo + K : Lq;
+        for (unsigned j = lo; j < hi; j++) {
+            const uint64_t qj = c->q[j], f = dpo_invmod(prod_mod(c, lo, hi, j, qj), qj);
+            uint64_t *yj = y + (size_t)(j - lo) * N;
+            memcpy(yj, d + (size_t)j * N, N * 8);
+            ntt_inv_limb(c, j, yj);
+            for (size_t n = 0; n < N; n++) yj[n] = mulmod(yj[n], f, qj);
+        }
+        for (unsigned i = 0; i < L; i++) {
+            const uint64_t q = c->q[i], r0 = c->br0[i], r1 = c->br1[i];
+            const uint64_t *src;
+            if (i >= lo && i < hi) src = d + (size_t)i * N;
+            else {
+                for (size_t n = 0; n < N; n++) u[n] = 0;
+                for (unsigned j = lo; j < hi; j++) {
+                    const uint64_t qh = prod_mod(c, lo, hi, j, q);
+                    const uint64_t *yj = y + (size_t)(j - lo) * N;
+                    for (size_t n = 0; n < N; n++) u[n] = addmod(u[n], mulmod(yj[n] % q, qh, q), q);
+                }
+                ntt_fwd_limb(c, i, u);
+                src = u;
+            }
+            const uint64_t *kb = key + ((size_t)g * 2 + 0) * PK + i * N;
+            const uint64_t *ka = key + ((size_t)g * 2 + 1) * PK + i * N;
+            for (size_t n = 0; n < N; n++) {
+                acc[i * N + n] = addmod(acc[i * N + n], barrett_mul(src[n], kb[n], q, r0, r1), q);
+                acc[PK + i * N + n] = addmod(acc[PK + i * N + n], barrett_mul(src[n], ka[n], q, r0, r1), q);
+            }
+        }
+    }
+    dpo_mod_down_special(c, K, acc, t_plain, low, 2);
+    memcpy(c0, low, (size_t)Lq * N * 8);
+    memcpy(c1, low + (size_t)Lq * N, (size_t)Lq * N * 8);
+    free(y); free(u); free(acc); free(low);
+}
+
+/* a, b, out: [batch][2][Lq][N]; evk: [dnum][2][L][N] */
+void dpo_ct_mul_relin_grouped(const dpo_ctx *c, unsigned K, const uint64_t *a, const uint64_t *b, const uint64_t *evk, uint64_t t_plain,
+                              uint64_t *out, size_t batch) {
+    if (K < 1 || K >= c->L) return;
+    const unsigned Lq = c->L - K;
+    const size_t N = c->N, P = (size_t)Lq * N;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long b_i = 0; b_i < (long)batch; b_i++) {
+        uint64_t *d = (uint64_t *)malloc(3 * P * 8), *k = (uint64_t *)malloc(2 * P * 8);
+        uint64_t *dst = out + 2 * P * b_i;
+        ct_tensor_limbs(c, Lq, a + 2 * P * b_i, b + 2 * P * b_i, d);
+        dpo_keyswitch_grouped(c, K, d + 2 * P, evk, t_plain, k, k + P);
+        for (unsigned l = 0; l < Lq; l++)
+            for (size_t n = 0; n < N; n++) {
+                size_t o = l * N + n;
+                dst[o] = addmod(d[o], k[o], c->q[l]);
+                dst[P + o] = addmod(d[P + o], k[P + o], c->q[l]);
+            }
+        free(d); free(k);
+    }
+}
+
+/* ct, out: [batch][2][Lq][N]; gk: [dnum][2][L][N] */
+void dpo_rotate_grouped(const dpo_ctx *c, unsigned K, const uint64_t *ct, uint64_t g, const uint64_t *gk, uint64_t t_plain, uint64_t *out,
+                        size_t batch) {
+    if (K < 1 || K >= c->L) return;
+    const unsigned Lq = c->L - K;
+    const size_t N = c->N, P = (size_t)Lq * N;
+    uint32_t *perm = (uint32_t *)malloc(N * 4);
+    dpo_galois_perm(c, g, perm);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long b = 0; b < (long)batch; b++) {
+        const uint64_t *src = ct + 2 * P * b;
+        uint64_t *dst = out + 2 * P * b;
+        uint64_t *p = (uint64_t *)malloc(2 * P * 8), *k = (uint64_t *)malloc(2 * P * 8);
+        for (unsigned comp = 0; comp < 2; comp++)
+            for (unsigned l = 0; l < Lq; l++)
+                for (size_t n = 0; n < N; n++) p[comp * P + l * N + n] = src[comp * P + l * N + perm[n]];
+        dpo_keyswitch_grouped(c, K, p + P, gk, t_plain, k, k + P);
+        for (unsigned l = 0; l < Lq; l++)
+            for (size_t n = 0; n < N; n++) {
+                size_t o = l * N + n;
+                dst[o] = addmod(p[o], k[o], c->q[l]);
+                dst[P + o] = k[P + o];
+            }
+        free(p); free(k);
+    }
+    free(perm);
+}
+
 /* ------------------------------------------------------------------ synthetic data */
 
 uint64_t dpo_splitmix64(uint64_t x) {
@@ -712,6 +870,57 @@ void dpo_keygen_switch_hybrid(const dpo_ctx *c, uint64_t seed, uint64_t t_plain,
     }
     free(e);
     free(e_eval);
+}
+
+/* grouped hybrid key: digits g < dnum, limbs over all L moduli; b_g = -a_g*s + t*e_g + P*F_g*target with
+ * F_g = 1 on the limbs of group g and 0 on every other limb, i.e. (P mod q_l) * target in the limbs of the group and nothing
+ * elsewhere.  K = 1 draws the same random stream as dpo_keygen_switch_hybrid. */
+void dpo_keygen_switch_grouped(const dpo_ctx *c, unsigned K, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
+                               const uint64_t *target_eval, uint64_t *key) {
+    size_t N = c->N, P = c->L * N;
+    const unsigned L = c->L, Lq = L - K, dnum = dpo_grouped_digits(c, K);
+    xo_t x; xo_seed(&x, seed);
+    int64_t *e = (int64_t *)malloc(N * 8);
+    uint64_t *e_eval = (uint64_t *)malloc(P * 8);
+    for (unsigned g = 0; g < dnum; g++) {
+        const unsigned lo = g * K, hi = lo + K < Lq ? lo + K : Lq;
+        uint64_t *kb = key + ((size_t)g * 2 + 0) * P, *ka = key + ((size_t)g * 2 + 1) * P;
+        for (unsigned l = 0; l < L; l++)
+            for (size_t n = 0; n < N; n++) ka[l * N + n] = xo_uniform(&x, c->q[l]);
+        for (size_t n = 0; n < N; n++) e[n] = xo_cbd(&x);
+        small_to_eval(c, e, t_plain, e_eval);
+        for (unsigned l = 0; l < L; l++) {
+            uint64_t q = c->q[l];
+            const uint64_t Pm = prod_mod(c, Lq, L, L, q);
+            for (size_t n = 0; n < N; n++) {
+                size_t o = l * N + n;
+                uint64_t v = submod(e_eval[o], mulmod(ka[o], s_eval[o], q), q);
+                if (l >= lo && l < hi) v = addmod(v, mulmod(target_eval[o], Pm, q), q);
+                kb[o] = v;
+            }
+        }
+    }
+    free(e);
+    free(e_eval);
+}
+void dpo_keygen_relin_grouped(const dpo_ctx *c, unsigned K, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t *evk) {
+    size_t P = c->L * c->N;
+    uint64_t *s2 = (uint64_t *)malloc(P * 8);
+    for (unsigned l = 0; l < c->L; l++)
+        for (size_t n = 0; n < c->N; n++) s2[l * c->N + n] = mulmod(s_eval[l * c->N + n], s_eval[l * c->N + n], c->q[l]);
+    dpo_keygen_switch_grouped(c, K, seed, t_plain, s_eval, s2, evk);
+    free(s2);
+}
+void dpo_keygen_galois_grouped(const dpo_ctx *c, unsigned K, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t g, uint64_t *gk) {
+    size_t N = c->N, P = c->L * N;
+    uint32_t *perm = (uint32_t *)malloc(N * 4);
+    uint64_t *sg = (uint64_t *)malloc(P * 8);
+    dpo_galois_perm(c, g, perm);
+    for (unsigned l = 0; l < c->L; l++)
+        for (size_t n = 0; n < N; n++) sg[l * N + n] = s_eval[l * N + perm[n]];
+    dpo_keygen_switch_grouped(c, K, seed, t_plain, s_eval, sg, gk);
+    free(perm);
+    free(sg);
 }
 
 /* hybrid != 0: special-prime key layout [L-1][2][L][N] */

@@ -93,6 +93,17 @@ void dpo_ct_mul_relin_hybrid(const dpo_ctx *, const uint64_t *a, const uint64_t 
                              uint64_t *out, size_t batch);
 void dpo_rotate_hybrid(const dpo_ctx *, const uint64_t *ct, uint64_t galois_elt, const uint64_t *gk, uint64_t t_plain,
                        uint64_t *out, size_t batch);
+/* grouped hybrid key switching (dnum < L), DESIGN.md §2.11: the context's last K limbs are special primes, ciphertext
+ * polynomials carry Lq = L-K limbs in digits of K consecutive limbs, keys are [dnum = ceil(Lq/K)][2][L][N].
+ * K = 1 is the hybrid variant above, bit for bit. */
+unsigned dpo_grouped_digits(const dpo_ctx *, unsigned K);
+/* in [n_polys][L][N] -> out [n_polys][L-K][N]: division by the product of the special primes */
+void dpo_mod_down_special(const dpo_ctx *, unsigned K, const uint64_t *in, uint64_t t_plain, uint64_t *out, size_t n_polys);
+void dpo_keyswitch_grouped(const dpo_ctx *, unsigned K, const uint64_t *d, const uint64_t *key, uint64_t t_plain, uint64_t *c0, uint64_t *c1);
+void dpo_ct_mul_relin_grouped(const dpo_ctx *, unsigned K, const uint64_t *a, const uint64_t *b, const uint64_t *evk, uint64_t t_plain,
+                              uint64_t *out, size_t batch);
+void dpo_rotate_grouped(const dpo_ctx *, unsigned K, const uint64_t *ct, uint64_t galois_elt, const uint64_t *gk, uint64_t t_plain,
+                        uint64_t *out, size_t batch);
 /* permutation table of sigma_g in evaluation form: out[i] = in[perm[i]] */
 void dpo_galois_perm(const dpo_ctx *, uint64_t galois_elt, uint32_t *perm);
 /* sigma_g in coefficient form on one limb: out(X) = in(X^g) */
@@ -117,6 +128,11 @@ void dpo_keygen_switch_hybrid(const dpo_ctx *, uint64_t seed, uint64_t t_plain, 
 void dpo_keygen_relin_hybrid(const dpo_ctx *, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t *evk);
 void dpo_keygen_galois_hybrid(const dpo_ctx *, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
                               uint64_t galois_elt, uint64_t *gk);
+void dpo_keygen_switch_grouped(const dpo_ctx *, unsigned K, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
+                               const uint64_t *target_eval, uint64_t *key);
+void dpo_keygen_relin_grouped(const dpo_ctx *, unsigned K, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval, uint64_t *evk);
+void dpo_keygen_galois_grouped(const dpo_ctx *, unsigned K, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
+                               uint64_t galois_elt, uint64_t *gk);
 /* msg: N coefficients in [0,t); ct out [2][L][N] eval form */
 void dpo_encrypt(const dpo_ctx *, uint64_t seed, uint64_t t_plain, const uint64_t *s_eval,
                  const uint64_t *msg, uint64_t *ct);
