@@ -473,22 +473,33 @@ int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, cons
 }
 
 // hybrid (special-prime) variants: the context's last limb is the special prime, data carries L-1 limbs
+// n_special = K: the last K limbs are special primes and the digits are groups of K limbs; K = 1 is §2.10
+static int check_special(dpfhe_ctx *ctx, unsigned n_special) {
+    const unsigned L = ctx->hp.L;
+    if (L < 2) return fail(DPFHE_ERR_INVALID, "hybrid key switching needs a special prime: create the context with at least two limbs");
+    if (n_special < 1 || n_special > (unsigned)KS_MAX_SPECIAL || 2 * n_special > L)
+        return fail(DPFHE_ERR_INVALID, "n_special must be between 1 and %d and at most half of the context's %u limbs", KS_MAX_SPECIAL, L);
+    return DPFHE_OK;
+}
+
 static int ks_hybrid_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const uint64_t *b, const uint64_t *key, uint64_t *out,
-                            size_t batch, uint64_t galois, uint64_t t_plain, void *stream) {
+                            size_t batch, uint64_t galois, uint64_t t_plain, void *stream, unsigned n_special = 1) {
     int rc = enter(ctx);
     if (rc) return rc;
     if (batch == 0) return DPFHE_OK;
     CHECK_PTR(a); CHECK_PTR(key); CHECK_PTR(out);
     if (mode == KS_MUL_RELIN) CHECK_PTR(b);
     const unsigned L = ctx->hp.L;
-    if (L < 2) return fail(DPFHE_ERR_INVALID, "hybrid key switching needs a special prime: create the context with at least two limbs");
-    if (t_plain >= ctx->hp.limbs[L - 1].lp.q) return fail(DPFHE_ERR_INVALID, "plaintext modulus must be below the special prime");
+    rc = check_special(ctx, n_special);
+    if (rc) return rc;
+    for (unsigned k = 0; k < n_special; ++k)
+        if (t_plain >= ctx->hp.limbs[L - 1 - k].lp.q) return fail(DPFHE_ERR_INVALID, "plaintext modulus must be below the special prime");
     if (mode == KS_ROTATE) {
         const uint64_t two_n = (uint64_t)2 << ctx->hp.log_n;
         if (!(galois & 1) || galois >= two_n) return fail(DPFHE_ERR_INVALID, "galois element must be odd and < 2N");
     }
     {
-        const size_t ct_bytes = 2 * (size_t)(L - 1) * ctx->N() * 8, in_bytes = batch * (mode == KS_PLAIN ? ct_bytes / 2 : ct_bytes);
+        const size_t ct_bytes = 2 * (size_t)(L - n_special) * ctx->N() * 8, in_bytes = batch * (mode == KS_PLAIN ? ct_bytes / 2 : ct_bytes);
         if (overlaps(out, batch * ct_bytes, a, in_bytes) || overlaps(out, batch * ct_bytes, b, in_bytes))
             return fail(DPFHE_ERR_INVALID, "output must not overlap an input");
     }
@@ -501,9 +512,34 @@ static int ks_hybrid_common(dpfhe_ctx *ctx, int mode, const uint64_t *a, const u
         ctx->device_bytes += hyb_bytes + acc_bytes;
     }
     MsConsts K;
-    build_ms_consts(ctx->hp, t_plain, K);
-    CU_TRY(VCALL(launch_ks_hybrid, ctx->lc, mode, a, b, key, out, batch, (u32)galois, K, pick(ctx, stream)));
-    note_launch(ctx, 2);   // key_prepare_kernel + ks_hybrid_kernel
+    if (n_special == 1) {
+        build_ms_consts(ctx->hp, t_plain, K);
+        CU_TRY(VCALL(launch_ks_hybrid, ctx->lc, mode, a, b, key, out, batch, (u32)galois, K, pick(ctx, stream)));
+    } else {
+        GroupConsts G;
+        build_group_consts(ctx->hp, n_special, t_plain, G, K);
+        CU_TRY(VCALL(launch_ks_grouped, ctx->lc, mode, a, b, key, out, batch, (u32)galois, K, G, pick(ctx, stream)));
+    }
+    note_launch(ctx, 2);   // key_prepare_kernel + ks_hybrid_kernel / ks_grouped_kernel
+    return DPFHE_OK;
+}
+int dpfhe_keyswitch_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_d, const uint64_t *d_key, uint64_t *d_out, size_t batch,
+                            uint64_t t_plain, void *stream) {
+    return ks_hybrid_common(ctx, KS_PLAIN, d_d, nullptr, d_key, d_out, batch, 0, t_plain, stream, n_special);
+}
+int dpfhe_ct_mul_relin_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_a, const uint64_t *d_b, const uint64_t *d_evk,
+                               uint64_t *d_out, size_t batch, uint64_t t_plain, void *stream) {
+    return ks_hybrid_common(ctx, KS_MUL_RELIN, d_a, d_b, d_evk, d_out, batch, 0, t_plain, stream, n_special);
+}
+int dpfhe_rotate_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk, uint64_t *d_out,
+                         size_t batch, uint64_t t_plain, void *stream) {
+    return ks_hybrid_common(ctx, KS_ROTATE, d_ct, nullptr, d_gk, d_out, batch, galois_elt, t_plain, stream, n_special);
+}
+int dpfhe_grouped_digits(const dpfhe_ctx *ctx, unsigned n_special, unsigned *digits) {
+    if (!ctx || !digits) return fail(DPFHE_ERR_INVALID, "null argument");
+    int rc = check_special(const_cast<dpfhe_ctx *>(ctx), n_special);
+    if (rc) return rc;
+    *digits = (ctx->hp.L - n_special + n_special - 1) / n_special;
     return DPFHE_OK;
 }
 int dpfhe_keyswitch_hybrid(dpfhe_ctx *ctx, const uint64_t *d_d, const uint64_t *d_key, uint64_t *d_out, size_t batch, uint64_t t_plain,
@@ -670,6 +706,37 @@ int dpfhe_mod_switch_down(dpfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out,
     return DPFHE_OK;
 }
 
+// division by the product of the last n_special limbs; n_special = 1 is dpfhe_mod_switch_down
+int dpfhe_mod_down_special(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_in, uint64_t *d_out, size_t n_polys, uint64_t t_plain,
+                           void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (n_polys == 0) return DPFHE_OK;
+    CHECK_PTR(d_in); CHECK_PTR(d_out);
+    const unsigned L = ctx->hp.L;
+    if (n_special < 1 || n_special > (unsigned)KS_MAX_SPECIAL || n_special >= L)
+        return fail(DPFHE_ERR_INVALID, "n_special must be between 1 and %d and below the context's %u limbs", KS_MAX_SPECIAL, L);
+    if (overlaps(d_out, n_polys * (size_t)(L - n_special) * ctx->N() * 8, d_in, n_polys * ctx->P() * 8))
+        return fail(DPFHE_ERR_INVALID, "output must not overlap the input");
+    for (unsigned k = 0; k < n_special; ++k)
+        if (t_plain >= ctx->hp.limbs[L - 1 - k].lp.q) return fail(DPFHE_ERR_INVALID, "plaintext modulus must be below the dropped moduli");
+    const size_t need = n_polys * n_special * ctx->N() * 8;
+    if (need > ctx->ms_tau_bytes) {
+        CU_TRY(cudaStreamSynchronize(pick(ctx, stream)));   // the old scratch may still be in use on this stream
+        if (ctx->ms_tau) cudaFree(ctx->ms_tau);
+        ctx->ms_tau = nullptr;
+        ctx->ms_tau_bytes = 0;
+        CU_TRY(cudaMalloc(&ctx->ms_tau, need));
+        ctx->ms_tau_bytes = need;
+    }
+    MsConsts K;
+    GroupConsts G;
+    build_group_consts(ctx->hp, n_special, t_plain, G, K);
+    CU_TRY(VCALL(launch_mod_down_special, ctx->lc, d_in, ctx->ms_tau, d_out, K, G, n_polys, pick(ctx, stream)));
+    note_launch(ctx, 2);
+    return DPFHE_OK;
+}
+
 int dpfhe_fill_uniform(dpfhe_ctx *ctx, uint64_t seed, uint64_t first_poly, uint64_t *d_data, size_t n_polys, void *stream) {
     int rc = enter(ctx);
     if (rc) return rc;
@@ -771,6 +838,42 @@ int dpfhe_rotate_hybrid_host(dpfhe_ctx *ctx, const uint64_t *h_ct, uint64_t galo
                         });
 }
 
+int dpfhe_ct_mul_relin_grouped_host(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *h_a, const uint64_t *h_b, const uint64_t *h_evk,
+                                    uint64_t *h_out, size_t batch, uint64_t t_plain) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    if (!h_a || !h_b || !h_evk || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
+    rc = check_special(ctx, n_special);
+    if (rc) return rc;
+    const size_t Lq = ctx->hp.L - n_special, Pq = Lq * ctx->N(), dnum = (Lq + n_special - 1) / n_special;
+    rc = upload_key(ctx, h_evk, 2 * dnum * ctx->P());
+    if (rc) return rc;
+    const size_t chunk = pick_chunk(ctx, 2 * Pq * 8, batch);
+    return run_pipeline(ctx, h_a, h_b, h_out, batch, 2 * Pq, 2 * Pq, chunk,
+                        [&](u64 *da, u64 *db, u64 *dout, size_t cnt, cudaStream_t st) -> int {
+                            return ks_hybrid_common(ctx, KS_MUL_RELIN, da, db, ctx->stage_key, dout, cnt, 0, t_plain, st, n_special);
+                        });
+}
+
+int dpfhe_rotate_grouped_host(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *h_ct, uint64_t galois_elt, const uint64_t *h_gk,
+                              uint64_t *h_out, size_t batch, uint64_t t_plain) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0) return DPFHE_OK;
+    if (!h_ct || !h_gk || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
+    rc = check_special(ctx, n_special);
+    if (rc) return rc;
+    const size_t Lq = ctx->hp.L - n_special, Pq = Lq * ctx->N(), dnum = (Lq + n_special - 1) / n_special;
+    rc = upload_key(ctx, h_gk, 2 * dnum * ctx->P());
+    if (rc) return rc;
+    const size_t chunk = pick_chunk(ctx, 2 * Pq * 8, batch);
+    return run_pipeline(ctx, h_ct, nullptr, h_out, batch, 2 * Pq, 2 * Pq, chunk,
+                        [&](u64 *dc, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
+                            return ks_hybrid_common(ctx, KS_ROTATE, dc, nullptr, ctx->stage_key, dout, cnt, galois_elt, t_plain, st, n_special);
+                        });
+}
+
 int dpfhe_mod_switch_down_host(dpfhe_ctx *ctx, const uint64_t *h_in, uint64_t *h_out, size_t n_polys, uint64_t t_plain) {
     int rc = enter(ctx);
     if (rc) return rc;
@@ -782,6 +885,20 @@ int dpfhe_mod_switch_down_host(dpfhe_ctx *ctx, const uint64_t *h_in, uint64_t *h
     return run_pipeline(ctx, h_in, nullptr, h_out, n_polys, P, Pq, chunk,
                         [&](u64 *din, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
                             return dpfhe_mod_switch_down(ctx, din, dout, cnt, t_plain, st);
+                        });
+}
+
+int dpfhe_mod_down_special_host(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *h_in, uint64_t *h_out, size_t n_polys, uint64_t t_plain) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (n_polys == 0) return DPFHE_OK;
+    if (!h_in || !h_out) return fail(DPFHE_ERR_INVALID, "null host pointer");
+    if (n_special < 1 || n_special >= ctx->hp.L) return fail(DPFHE_ERR_INVALID, "n_special must be at least 1 and below the context's limbs");
+    const size_t P = ctx->P(), Pq = (ctx->hp.L - n_special) * ctx->N();
+    const size_t chunk = pick_chunk(ctx, P * 8, n_polys);
+    return run_pipeline(ctx, h_in, nullptr, h_out, n_polys, P, Pq, chunk,
+                        [&](u64 *din, u64 *, u64 *dout, size_t cnt, cudaStream_t st) -> int {
+                            return dpfhe_mod_down_special(ctx, n_special, din, dout, cnt, t_plain, st);
                         });
 }
 

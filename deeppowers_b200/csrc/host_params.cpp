@@ -171,4 +171,64 @@ void build_ms_consts(const HostParams &hp, uint64_t t_plain, MsConsts &K) {
     }
 }
 
+void build_group_consts(const HostParams &hp, unsigned K, uint64_t t_plain, GroupConsts &G, MsConsts &Km) {
+    typedef unsigned __int128 u128;
+    auto shoup = [](uint64_t w, uint64_t q) { return (uint64_t)((((u128)w) << 64) / q); };
+    const unsigned L = hp.L, Lq = L - K;
+    auto q_of = [&](unsigned l) { return hp.limbs[l].lp.q; };
+    // product of the moduli lo .. hi-1 except `skip`, modulo q
+    auto prod_mod = [&](unsigned lo, unsigned hi, unsigned skip, uint64_t q) {
+        uint64_t r = 1 % q;
+        for (unsigned m = lo; m < hi; ++m)
+            if (m != skip) r = host_mulmod(r, q_of(m) % q, q);
+        return r;
+    };
+    G = GroupConsts();
+    G.Lq = Lq;
+    G.K = K;
+    G.dnum = (Lq + K - 1) / K;
+    auto fold = [&](unsigned l, uint64_t f) {   // limb l with N^-1 replaced by N^-1 * f
+        LimbParams p = hp.limbs[l].lp;
+        p.ninv = host_mulmod(p.ninv, f, p.q);
+        p.ninv_s = shoup(p.ninv, p.q);
+        p.wninv = host_mulmod(p.wninv, f, p.q);
+        p.wninv_s = shoup(p.wninv, p.q);
+        return p;
+    };
+    for (unsigned j = 0; j < Lq; ++j) {
+        const unsigned lo = j / K * K, hi = lo + K < Lq ? lo + K : Lq;
+        const uint64_t qj = q_of(j);
+        G.lp_up[j] = fold(j, host_powmod(prod_mod(lo, hi, j, qj), qj - 2, qj));
+        for (unsigned i = 0; i < L; ++i) {
+            G.up[j][i] = prod_mod(lo, hi, j, q_of(i));
+            G.up_s[j][i] = shoup(G.up[j][i], q_of(i));
+        }
+    }
+    for (unsigned k = 0; k < K; ++k) {
+        const unsigned s = Lq + k;
+        const uint64_t p = q_of(s);
+        uint64_t f = prod_mod(Lq, L, s, p);
+        if (t_plain) f = host_mulmod(f, t_plain % p, p);
+        G.lp_up[s] = fold(s, host_powmod(f, p - 2, p));
+        G.half[k] = p >> 1;
+        for (unsigned i = 0; i < Lq; ++i) {
+            G.dn[k][i] = prod_mod(Lq, L, s, q_of(i));
+            G.dn_s[k][i] = shoup(G.dn[k][i], q_of(i));
+        }
+    }
+    Km = MsConsts();
+    Km.has_t = 0;   // t^-1 is folded into lp_up of the special limbs
+    Km.tinv = 1;
+    for (unsigned i = 0; i < Lq; ++i) {
+        const uint64_t q = q_of(i), Pm = prod_mod(Lq, L, L, q);
+        G.neg_p[i] = q - Pm;
+        Km.qlm[i] = Pm;
+        Km.qlm_s[i] = shoup(Pm, q);
+        Km.inv[i] = host_powmod(Pm, q - 2, q);
+        Km.inv_s[i] = shoup(Km.inv[i], q);
+        Km.sinv[i] = t_plain ? host_mulmod(t_plain % q, Km.inv[i], q) : Km.inv[i];
+        Km.sinv_s[i] = shoup(Km.sinv[i], q);
+    }
+}
+
 }  // namespace dpfhe

@@ -30,6 +30,10 @@ std::string build_host_params(unsigned log_n, unsigned L, const uint64_t *moduli
 // constants for dropping the last limb of `hp` (t_plain = 0: plain rounding); requires hp.L >= 2 and t_plain < q_last
 void build_ms_consts(const HostParams &hp, uint64_t t_plain, MsConsts &K);
 
+// constants of grouped hybrid key switching with the last K limbs of `hp` as special primes (types.hpp: GroupConsts); Km
+// receives the constants of the division by P.  Requires 1 <= K <= KS_MAX_SPECIAL, K < hp.L, t_plain < every special prime.
+void build_group_consts(const HostParams &hp, unsigned K, uint64_t t_plain, GroupConsts &G, MsConsts &Km);
+
 uint64_t host_mulmod(uint64_t a, uint64_t b, uint64_t q);
 uint64_t host_powmod(uint64_t a, uint64_t e, uint64_t q);
 bool host_is_prime(uint64_t n);

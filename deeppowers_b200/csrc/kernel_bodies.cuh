@@ -345,7 +345,7 @@ DPFHE_HD void ks_p1_chunk(const KsP1Operands &o, const LimbParams &p, bool only,
 // whose sequential order already guarantees it).
 template <int LOGN, int NT, int MODE, bool HYB = false, class CTA>
 DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot, u64 *acc_rows, u64 pm = 0,
-                        u64 pm_s = 0, const u32 *slot_free = nullptr, u32 slot_free_target = 0) {
+                        u64 pm_s = 0, const u32 *slot_free = nullptr, u32 slot_free_target = 0, u32 key_digit = ~0u) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     static_assert((NC / NT) % 2 == 0, "chunk loops may be unrolled by two (ping-pong operand buffers)");
     const size_t P = (size_t)A.L * N, PK = HYB ? (size_t)A.Lk * N : P;
@@ -355,7 +355,8 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
     const bool only = !HYB && A.L == 1;   // a single digit: no phase 2, write the canonical result here
     KsP1Pointers ptr;
     {
-        const size_t koff_b = ((size_t)i * 2 + 0) * PK + (size_t)i * N, koff_a = ((size_t)i * 2 + 1) * PK + (size_t)i * N;
+        const u32 kd = key_digit == ~0u ? i : key_digit;   // the key digit that limb i belongs to (grouped digits: i / K)
+        const size_t koff_b = ((size_t)kd * 2 + 0) * PK + (size_t)i * N, koff_a = ((size_t)kd * 2 + 1) * PK + (size_t)i * N;
         ptr.kb = reinterpret_cast<const U64x2 *>(A.key + koff_b);
         ptr.ka = reinterpret_cast<const U64x2 *>(A.key + koff_a);
         ptr.kbs = reinterpret_cast<const U64x2 *>(A.key_s + koff_b);
@@ -433,14 +434,15 @@ DPFHE_HD void ks_phase1(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p
 // HYB: key polynomials carry A.Lk limbs and nothing is final here (the division by the special prime follows).
 // acc_rows: the two accumulator rows of this work item, acc_rows[0..N) and acc_rows[N..2N).
 // SPECIAL (hybrid only): limb i = A.L is the special prime; jj = 0 .. L-1 counts its digits and its accumulators start from zero.
-template <int LOGN, int NT, bool HYB = false, bool SPECIAL = false, class CTA>
-DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u32 j, u32 jj, const u64 *t_src,
-                              u64 *acc_rows) {
+// LOAD(h): fills the transform buffer with the first forward stage(s) of the lifted digit (h = half for N = 16384, else 0), from
+// values below BIN*q.  n_digits: how many digits the accumulation runs over (the last one finishes a non-hybrid result).
+template <int LOGN, int NT, bool HYB, bool SPECIAL, int BIN, class CTA, class LOAD>
+DPFHE_HD void ks_phase2_core(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u32 j, u32 jj, u32 n_digits, LOAD load,
+                             u64 *acc_rows) {
     constexpr int N = 1 << LOGN, NC = N / 2;
     static_assert(HYB || !SPECIAL, "the special limb exists only in hybrid key switching");
     const size_t P = (size_t)A.L * N, PK = HYB ? (size_t)A.Lk * N : P;
     const Twiddle *tw = A.tw + (size_t)i * N;
-    const U64x2 *src = reinterpret_cast<const U64x2 *>(t_src);
     const size_t koff_b = ((size_t)j * 2 + 0) * PK + (size_t)i * N, koff_a = ((size_t)j * 2 + 1) * PK + (size_t)i * N;
     const U64x2 *kb = reinterpret_cast<const U64x2 *>(A.key + koff_b), *ka = reinterpret_cast<const U64x2 *>(A.key + koff_a);
     const U64x2 *kbs = reinterpret_cast<const U64x2 *>(A.key_s + koff_b), *kas = reinterpret_cast<const U64x2 *>(A.key_s + koff_a);
@@ -451,7 +453,7 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
     // lazy accumulator bound: below (2 SB + 1) q after phase 1 (0 for the special limb), + SB*q per digit; trimmed
     // with one csub(8q) whenever the next digit could pass 16q
     constexpr int B0 = 2 * SB + 1;
-    const bool trim = SPECIAL ? acc_trim_after(0, (int)jj) : acc_trim_after(B0, (int)jj - 1), last = !HYB && jj + 1 == A.L;
+    const bool trim = SPECIAL ? acc_trim_after(0, (int)jj) : acc_trim_after(B0, (int)jj - 1), last = !HYB && jj + 1 == n_digits;
     const bool first = SPECIAL && jj == 0;
     struct MacOperands {
         U64x2 vb, va, vbs, vas, r0, r1;
@@ -504,16 +506,10 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
             }
         });
     };
-    // lift of the digit into Z_{q_i}: t_j < q_j.  When every modulus of the basis is below twice every other one (the default
-    // basis: all within 2^-22 of 2^60), t_j < 2 q_i already and the word reduction (three multiplies per coefficient) is skipped.
-    const bool lift = A.lift_reduce != 0u;
     if constexpr (LOGN <= 13) {
-        cta.par([&](int tid) {
-            if (lift) fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); });
-            else fwd_load_stage<LOGN, NT, false>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); });
-        });
+        load(0);
         cta.mark(4);   // digit fetch + lift + outer forward stage
-        fwd_passes<LOGN, NT, 3>(cta, buf, tw, p);
+        fwd_passes<LOGN, NT, BIN>(cta, buf, tw, p);
         cta.mark(5);   // forward register passes
         mac_range(0, NC);
         cta.mark(6);   // multiply-accumulate with the key column (the last digit also canonicalises and stores)
@@ -521,17 +517,67 @@ DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbPar
         // N = 16384: two halves of two 4096-blocks; each half re-reads the digit and keeps its two output blocks
         constexpr int HC = NC / 2;
         for (int h = 0; h < 2; ++h) {
-            cta.par([&](int tid) {
-                if (lift) fwd_load_stage_half<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); }, h);
-                else fwd_load_stage_half<LOGN, NT, false>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); }, h);
-            });
+            load(h);
             cta.mark(4);
-            fwd_passes_blk<LOGN, NT, 3, 2>(cta, buf, tw, p, 2 * h);
+            fwd_passes_blk<LOGN, NT, BIN, 2>(cta, buf, tw, p, 2 * h);
             cta.mark(5);
             mac_range(h * HC, HC);
             cta.mark(6);
         }
     }
+}
+
+// one digit = one limb (BV-RNS, and hybrid key switching with one special prime): the lift is t_j itself
+template <int LOGN, int NT, bool HYB = false, bool SPECIAL = false, class CTA>
+DPFHE_HD void ks_phase2_digit(CTA &cta, u64 *buf, const KsArgs &A, const LimbParams &p, size_t ct, u32 i, u32 j, u32 jj, const u64 *t_src,
+                              u64 *acc_rows) {
+    const Twiddle *tw = A.tw + (size_t)i * ((size_t)1 << LOGN);
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(t_src);
+    // lift of the digit into Z_{q_i}: t_j < q_j.  When every modulus of the basis is below twice every other one (the default
+    // basis: all within 2^-22 of 2^60), t_j < 2 q_i already and the word reduction (three multiplies per coefficient) is skipped.
+    const bool lift = A.lift_reduce != 0u;
+    auto get = [&](int c) { return ld_cg(src + c); };
+    auto load = [&](int h) {
+        cta.par([&](int tid) {
+            if constexpr (LOGN <= 13) {
+                if (lift) fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, get);
+                else fwd_load_stage<LOGN, NT, false>(buf, tw, p, tid, get);
+            } else {
+                if (lift) fwd_load_stage_half<LOGN, NT, true>(buf, tw, p, tid, get, h);
+                else fwd_load_stage_half<LOGN, NT, false>(buf, tw, p, tid, get, h);
+            }
+        });
+    };
+    ks_phase2_core<LOGN, NT, HYB, SPECIAL, 3>(cta, buf, A, p, ct, i, j, jj, A.L, load, acc_rows);
+}
+
+// a digit of several limbs (grouped hybrid key switching): the lift of group g into limb i is the fast basis
+// conversion sum_{j in g} y_j * (Qhat_j mod q_i), y_j = the scaled inverse transforms the members published.
+// t_rows + j * t_stride: the published row of limb j.
+template <int LOGN, int NT, bool SPECIAL, class CTA>
+DPFHE_HD void ks_phase2_group(CTA &cta, u64 *buf, const KsArgs &A, const GroupConsts &G, const LimbParams &p, size_t ct, u32 i, u32 g, u32 jj,
+                              const u64 *t_rows, size_t t_stride, u64 *acc_rows) {
+    const Twiddle *tw = A.tw + (size_t)i * ((size_t)1 << LOGN);
+    const u32 lo = g * G.K, hi = lo + G.K < G.Lq ? lo + G.K : G.Lq;
+    auto get = [&](int c) {
+        U64x2 r;
+        r.x = r.y = 0;
+        for (u32 j = lo; j < hi; ++j) {   // each term below 2q; at most KS_MAX_SPECIAL = 4 of them
+            const U64x2 v = ld_cg(reinterpret_cast<const U64x2 *>(t_rows + (size_t)j * t_stride) + c);
+            r.x += csub(shoup_lazy(v.x, G.up[j][i], G.up_s[j][i], p), p.q2);
+            r.y += csub(shoup_lazy(v.y, G.up[j][i], G.up_s[j][i], p), p.q2);
+        }
+        r.x = csub(r.x, p.q4);   // < 8q  ->  < 4q
+        r.y = csub(r.y, p.q4);
+        return r;
+    };
+    auto load = [&](int h) {
+        cta.par([&](int tid) {
+            if constexpr (LOGN <= 13) fwd_load_stage<LOGN, NT, false>(buf, tw, p, tid, get);
+            else fwd_load_stage_half<LOGN, NT, false>(buf, tw, p, tid, get, h);
+        });
+    };
+    ks_phase2_core<LOGN, NT, true, SPECIAL, 4>(cta, buf, A, p, ct, i, g, jj, G.dnum, load, acc_rows);
 }
 
 // ---- modulus switching: drop the last limb -------------------------------------
@@ -585,19 +631,11 @@ DPFHE_HD void ms_tau_body(CTA &cta, u64 *buf, const u64 *row, u64 *work, const T
 
 // step 2, one (polynomial, kept limb i): out = (c[i] - s * NTT_i(centred(tau') mod q_i)) * q_last^-1 mod q_i.
 // COHERENT: c[i] is an L2-resident lazy accumulator written in this launch (any 64-bit value; may be `out_limb`).
-template <int LOGN, int NT, bool COHERENT = false, class CTA>
-DPFHE_HD void ms_limb_body(CTA &cta, u64 *buf, const u64 *tau, const u64 *c_limb, u64 *out_limb, const Twiddle *tw, const LimbParams &p,
+// LIFT(chunk): the residue mod q_i of the (centred) value to subtract, lazy below 4q.
+template <int LOGN, int NT, bool COHERENT, class CTA, class LIFT>
+DPFHE_HD void ms_limb_core(CTA &cta, u64 *buf, LIFT lift, const u64 *c_limb, u64 *out_limb, const Twiddle *tw, const LimbParams &p,
                            const MsConsts &K, u32 i) {
     constexpr int NC = 1 << (LOGN - 1);
-    const U64x2 *src = reinterpret_cast<const U64x2 *>(tau);
-    const u64 half = K.half, neg_ql = p.q - K.qlm[i];   // adding (q_i - q_last mod q_i) subtracts q_last
-    auto lift = [&](int c) {
-        const U64x2 v = ld_cg(src + c);
-        U64x2 r;                                 // centred lift, lazy: < 3q (+ < q when tau' is "negative")
-        r.x = word_reduce(v.x, p) + (v.x > half ? neg_ql : 0);
-        r.y = word_reduce(v.y, p) + (v.y > half ? neg_ql : 0);
-        return r;
-    };
     const U64x2 *cin = reinterpret_cast<const U64x2 *>(c_limb);
     U64x2 *dst = reinterpret_cast<U64x2 *>(out_limb);
     const u64 inv = K.inv[i], inv_s = K.inv_s[i], sinv = K.sinv[i], sinv_s = K.sinv_s[i];
@@ -625,6 +663,42 @@ DPFHE_HD void ms_limb_body(CTA &cta, u64 *buf, const u64 *tau, const u64 *c_limb
             });
         }
     }
+}
+
+template <int LOGN, int NT, bool COHERENT = false, class CTA>
+DPFHE_HD void ms_limb_body(CTA &cta, u64 *buf, const u64 *tau, const u64 *c_limb, u64 *out_limb, const Twiddle *tw, const LimbParams &p,
+                           const MsConsts &K, u32 i) {
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(tau);
+    const u64 half = K.half, neg_ql = p.q - K.qlm[i];   // adding (q_i - q_last mod q_i) subtracts q_last
+    auto lift = [&](int c) {
+        const U64x2 v = ld_cg(src + c);
+        U64x2 r;                                 // centred lift, lazy: < 3q (+ < q when tau' is "negative")
+        r.x = word_reduce(v.x, p) + (v.x > half ? neg_ql : 0);
+        r.y = word_reduce(v.y, p) + (v.y > half ? neg_ql : 0);
+        return r;
+    };
+    ms_limb_core<LOGN, NT, COHERENT>(cta, buf, lift, c_limb, out_limb, tw, p, K, i);
+}
+
+// division by the product P of K special primes: tau_rows + k * tau_stride is y_k = tau'_k * Phat_k^-1 of
+// special prime k; the value to subtract is sum_k centred(y_k) * Phat_k, converted term by term.
+template <int LOGN, int NT, bool COHERENT = true, class CTA>
+DPFHE_HD void ms_limb_group(CTA &cta, u64 *buf, const u64 *tau_rows, size_t tau_stride, const u64 *c_limb, u64 *out_limb, const Twiddle *tw,
+                            const LimbParams &p, const MsConsts &K, const GroupConsts &G, u32 i) {
+    const u64 neg_p = G.neg_p[i];
+    auto lift = [&](int c) {
+        U64x2 r;
+        r.x = r.y = 0;
+        for (u32 k = 0; k < G.K; ++k) {   // each term below 3q; at most four of them
+            const U64x2 v = ld_cg(reinterpret_cast<const U64x2 *>(tau_rows + (size_t)k * tau_stride) + c);
+            r.x += csub(shoup_lazy(v.x, G.dn[k][i], G.dn_s[k][i], p), p.q2) + (v.x > G.half[k] ? neg_p : 0);
+            r.y += csub(shoup_lazy(v.y, G.dn[k][i], G.dn_s[k][i], p), p.q2) + (v.y > G.half[k] ? neg_p : 0);
+        }
+        r.x = csub(csub(r.x, p.q8), p.q4);   // < 12q  ->  < 4q
+        r.y = csub(csub(r.y, p.q8), p.q4);
+        return r;
+    };
+    ms_limb_core<LOGN, NT, COHERENT>(cta, buf, lift, c_limb, out_limb, tw, p, K, i);
 }
 
 // ---- hoisted rotations ---------------------------------------------------

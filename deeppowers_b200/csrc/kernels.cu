@@ -135,6 +135,39 @@ __global__ void __launch_bounds__(NT, MINB) ms_limb_kernel(const u64 *in, const 
     }
 }
 
+// division by the product of the last K limbs: tau' of every special limb, then one item per kept limb
+template <int LOGN, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) md_tau_kernel(const u64 *in, u64 *tau, const Twiddle *__restrict__ itw, const __grid_constant__ MsConsts K,
+                                                           const __grid_constant__ GroupConsts G, size_t n_items) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    constexpr size_t N = (size_t)1 << LOGN;
+    DevCta<NT> cta;
+    const u32 L = G.Lq + G.K;
+    for (size_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const size_t poly = w / G.K;
+        const u32 s = G.Lq + (u32)(w % G.K);
+        ms_tau_body<LOGN, NT>(cta, buf, in + (poly * L + s) * N, nullptr, itw + (size_t)s * N, G.lp_up[s], tau + w * N, K);
+    }
+}
+
+template <int LOGN, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) md_limb_kernel(const u64 *in, const u64 *tau, u64 *out, const Twiddle *__restrict__ tw,
+                                                            const __grid_constant__ LimbTable lt, const __grid_constant__ MsConsts K,
+                                                            const __grid_constant__ GroupConsts G, size_t n_items) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    constexpr size_t N = (size_t)1 << LOGN;
+    DevCta<NT> cta;
+    const u32 Lq = G.Lq, L = Lq + G.K;
+    for (size_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const size_t poly = w / Lq;
+        const u32 i = (u32)(w % Lq);
+        ms_limb_group<LOGN, NT, false>(cta, buf, tau + poly * G.K * N, N, in + (poly * L + i) * N, out + (poly * Lq + i) * N, tw + (size_t)i * N,
+                                       lt.lp[i], K, G, i);
+    }
+}
+
 // ------------------------------------------------------------------ fused key-switch family
 __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
     u32 v;
@@ -448,6 +481,101 @@ __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __g
     if (pending) divide(prev_ct, prev_tag, prev_parity);   // the group's last ciphertext
 }
 
+// Grouped hybrid variant (dnum < L), DESIGN.md §2.11.  A group is Lq + K CTAs: CTA i < Lq owns ciphertext limb i, CTA Lq + k
+// special prime k.  The roles are those of ks_hybrid_kernel with digits of K limbs:
+//   limb CTA    tensor/permute, P*own terms + the key term of its own digit, INTT (scaled by Qhat^-1), publish
+//               (dnum-1) x [basis conversion of a foreign digit + NTT + MAC]
+//               2 x [basis conversion of the K tau' rows + NTT], out = (acc - s*u) / P     (one round late, as above)
+//   special CTA dnum x [basis conversion + NTT + MAC into its scratch rows]; 2 x INTT (* (t Phat)^-1) -> tau', publish
+// With Lq = 4, K = 2 every CTA runs four transforms per ciphertext (24 in all, against 30 for one special prime).
+template <int LOGN, int NT, int MINB, int MODE>
+__global__ void __launch_bounds__(NT, MINB) ks_grouped_kernel(KsArgs A, const __grid_constant__ LimbTable lt, const __grid_constant__ MsConsts K,
+                                                              const __grid_constant__ GroupConsts G, size_t batch, u32 *flags, u32 epoch,
+                                                              u32 *ticket, u64 *mail) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr size_t N = (size_t)1 << LOGN;
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    DevCta<NT> cta;
+    __shared__ u32 s_ct;
+    const u32 Lq = G.Lq, Ks = G.K, dnum = G.dnum, GS = Lq + Ks, slot = blockIdx.x, i = slot % GS, group = slot / GS, base = slot - i;
+    const bool special = i >= Lq;
+    const LimbParams &p = lt.lp[i];
+    // rows of special prime k of this group: accumulators (0, 1) and tau' (double-buffered by round parity)
+    auto hyb_of = [&](u32 k) { return A.hyb + ((size_t)group * Ks + k) * KS_HYB_ROWS * N; };
+    auto wait_for = [&](u32 first, u32 count, u32 tag) {
+        if (threadIdx.x < count) {
+            while ((int)(ld_acquire_u32(flags + first + threadIdx.x) - tag) < 0) {
+            }
+        }
+        __syncthreads();
+    };
+    auto publish = [&](u32 tag) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_u32(flags + slot, tag);
+    };
+    auto acc_of = [&](u32 parity) { return A.acc + ((size_t)slot * 2 + parity) * 2 * N; };
+    auto divide = [&](size_t ct, u32 tag, u32 parity) {
+        wait_for(base + Lq, Ks, tag);
+        const size_t P = (size_t)Lq * N;
+        for (u32 c = 0; c < 2; ++c) {
+            u64 *row = A.out + ct * 2 * P + c * P + (size_t)i * N;
+            ms_limb_group<LOGN, NT>(cta, buf, hyb_of(0) + ks_hyb_tau_row(parity, c) * N, (size_t)KS_HYB_ROWS * N, acc_of(parity) + c * N, row,
+                                    A.tw + (size_t)i * N, p, K, G, i);
+        }
+    };
+    bool pending = false;
+    size_t prev_ct = 0;
+    u32 prev_tag = 0, prev_parity = 0;
+    for (u32 round = 0;; ++round) {
+        const u32 tag = epoch + round + 1, parity = round & 1u;
+        if (threadIdx.x == 0) {
+            u64 *box = mail + (size_t)group * 2 + parity;
+            if (i == 0) {
+                const u32 t = atomicAdd(ticket, 1u);
+                st_release_u64(box, ((u64)tag << 32) | t);
+                s_ct = t;
+            } else {
+                u64 m;
+                do m = ld_acquire_u64(box);
+                while ((u32)(m >> 32) != tag);
+                s_ct = (u32)m;
+            }
+        }
+        __syncthreads();
+        const size_t ct = s_ct;
+        if (ct >= batch) break;
+        const u64 *t_rows = A.scratch + ((size_t)base * 2 + parity) * N;   // row of limb j: + j * 2N
+        if (!special) {
+            const u32 g_own = i / Ks;
+            ks_phase1<LOGN, NT, MODE, true>(cta, buf, A, G.lp_up[i], ct, i, A.scratch + ((size_t)slot * 2 + parity) * N, acc_of(parity), K.qlm[i],
+                                            K.qlm_s[i], nullptr, 0, g_own);
+            publish(tag);
+            for (u32 jj = 1; jj < dnum; ++jj) {
+                const u32 g = (g_own + jj) % dnum, lo = g * Ks, cnt = lo + Ks < Lq ? Ks : Lq - lo;
+                wait_for(base + lo, cnt, tag);
+                ks_phase2_group<LOGN, NT, false>(cta, buf, A, G, p, ct, i, g, jj, t_rows, 2 * N, acc_of(parity));
+            }
+            if (pending) divide(prev_ct, prev_tag, prev_parity);
+            pending = true;
+            prev_ct = ct;
+            prev_tag = tag;
+            prev_parity = parity;
+        } else {
+            u64 *hyb = hyb_of(i - Lq);
+            for (u32 jj = 0; jj < dnum; ++jj) {
+                const u32 g = (group + jj) % dnum, lo = g * Ks, cnt = lo + Ks < Lq ? Ks : Lq - lo;
+                wait_for(base + lo, cnt, tag);
+                ks_phase2_group<LOGN, NT, true>(cta, buf, A, G, p, ct, i, g, jj, t_rows, 2 * N, hyb);
+            }
+            for (u32 c = 0; c < 2; ++c)
+                ms_tau_body<LOGN, NT, true>(cta, buf, hyb + c * N, hyb + c * N, A.itw + (size_t)i * N, G.lp_up[i], hyb + ks_hyb_tau_row(parity, c) * N, K);
+            publish(tag);
+        }
+    }
+    if (pending) divide(prev_ct, prev_tag, prev_parity);   // the group's last ciphertext
+}
+
 // ------------------------------------------------------------------ plaintext inner products (BSGS inner loop)
 template <int LOGN, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) pt_inner_kernel(PtInnerArgs A, const __grid_constant__ LimbTable lt, u32 g0, u32 gcnt) {
@@ -677,6 +805,40 @@ cudaError_t launch_mod_switch(const LaunchCtx &lc, const u64 *in, u64 *tau, u64 
     return cudaErrorInvalidValue;
 }
 
+template <int LOGN, int NT, int MINB>
+static cudaError_t launch_md_t(const LaunchCtx &lc, const u64 *in, u64 *tau, u64 *out, const MsConsts &K, const GroupConsts &G, size_t n_polys,
+                               cudaStream_t st) {
+    auto k1 = md_tau_kernel<LOGN, NT, MINB>;
+    auto k2 = md_limb_kernel<LOGN, NT, MINB>;
+    const size_t smem = Geometry<LOGN>::LIMB_BYTES;
+    static ConfiguredMask configured;
+    if (!configured.has(lc.device)) {
+        cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured.set(lc.device);
+    }
+    const size_t n_tau = n_polys * G.K, n_items = n_polys * G.Lq;
+    k1<<<(unsigned)(n_tau < 0x7fffffffull ? n_tau : 0x7fffffffull), NT, smem, st>>>(in, tau, lc.itw, K, G, n_tau);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k2<<<(unsigned)(n_items < 0x7fffffffull ? n_items : 0x7fffffffull), NT, smem, st>>>(in, tau, out, lc.tw, lc.lt, K, G, n_items);
+    return cudaGetLastError();
+}
+
+// in [n_polys][L][N] -> out [n_polys][L-K][N]; tau: n_polys * K * N words of scratch
+cudaError_t launch_mod_down_special(const LaunchCtx &lc, const u64 *in, u64 *tau, u64 *out, const MsConsts &K, const GroupConsts &G, size_t n_polys,
+                                    cudaStream_t st) {
+    if (n_polys == 0) return cudaSuccess;
+    if (G.Lq + G.K != lc.L) return cudaErrorInvalidValue;
+    switch (lc.log_n) {
+        case 12: return launch_md_t<12, 256, 2>(lc, in, tau, out, K, G, n_polys, st);
+        case 13: return launch_md_t<13, 256, 3>(lc, in, tau, out, K, G, n_polys, st);
+        case 14: return launch_md_t<14, 512, 1>(lc, in, tau, out, K, G, n_polys, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <int LOGN, int MODE>
 static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cudaStream_t st) {
     // at most 64 KiB of shared memory per CTA (N = 16384 is processed as two half-limbs) -> three CTAs per SM
@@ -816,6 +978,80 @@ cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b
         case 12: KS_HYB_DISPATCH(12)
         case 13: KS_HYB_DISPATCH(13)
         case 14: KS_HYB_DISPATCH(14)
+    }
+    return cudaErrorNotSupported;
+}
+
+template <int LOGN, int MODE>
+static cudaError_t launch_ks_grouped_t(LaunchCtx &lc, const KsArgs &A, const MsConsts &K, const GroupConsts &Gc, size_t batch, cudaStream_t st) {
+    constexpr int NT = 256, MINB = 3;
+    auto kern = ks_grouped_kernel<LOGN, NT, MINB, MODE>;
+    const size_t smem = LOGN <= 13 ? Geometry<LOGN>::LIMB_BYTES : Geometry<13>::LIMB_BYTES;
+    static ConfiguredMask configured;
+    if (!configured.has(lc.device)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured.set(lc.device);
+    }
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    if (lc.ks_occ_cap > 0 && occ > lc.ks_occ_cap) occ = lc.ks_occ_cap;
+    const size_t GS = lc.L;   // group size: every limb of the context, ciphertext and special
+    size_t G = (size_t)lc.num_sms * occ;
+    if (G > lc.ks_slots) G = lc.ks_slots;
+    G = (G / GS) * GS;
+    if (G > batch * GS) G = batch * GS;
+    if (G == 0) return cudaErrorInvalidConfiguration;
+    const u32 rounds = (u32)(batch + 1);
+    cudaError_t em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
+    if (em != cudaSuccess) return em;
+    KsArgs args = A;
+    LimbTable lt = lc.lt;
+    MsConsts consts = K;
+    GroupConsts gc = Gc;
+    size_t batch_arg = batch;
+    u32 *flags = lc.ks_flags;
+    u32 epoch = lc.ks_epoch;
+    u32 *ticket = lc.ks_ticket;
+    u64 *mail = lc.ks_mail;
+    void *params[] = {&args, &lt, &consts, &gc, &batch_arg, &flags, &epoch, &ticket, &mail};
+    e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)G), dim3(NT), params, smem, st);
+    lc.ks_epoch += rounds;
+    return e;
+}
+
+// data has Lq = L - K limbs, the key [dnum][2][L][N]; scratch requirements as launch_ks_hybrid (K <= Lq keeps the special
+// CTAs' rows within lc.ks_hyb)
+cudaError_t launch_ks_grouped(LaunchCtx &lc, int mode, const u64 *a, const u64 *b, const u64 *key, u64 *out, size_t batch, u32 galois,
+                              const MsConsts &K, const GroupConsts &Gc, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    if (lc.L < 2 || !lc.ks_hyb || !lc.ks_acc_hyb || Gc.Lq + Gc.K != lc.L || Gc.K > Gc.Lq || Gc.K > (u32)KS_MAX_SPECIAL) return cudaErrorInvalidValue;
+    {
+        const size_t n = (size_t)2 * Gc.dnum * lc.L << lc.log_n;
+        const unsigned grid = ew_grid(lc, n);
+        if (lc.log_n == 12) key_prepare_kernel<12><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        else if (lc.log_n == 13) key_prepare_kernel<13><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        else key_prepare_kernel<14><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    KsArgs A;
+    A.a = a; A.b = b; A.key = key; A.key_s = lc.ks_key_s; A.out = out; A.scratch = lc.ks_scratch;
+    A.tw = lc.tw; A.itw = lc.itw; A.L = Gc.Lq; A.galois = galois; A.Lk = lc.L; A.hyb = lc.ks_hyb; A.only = nullptr;
+    A.acc = lc.ks_acc_hyb; A.acc_par = 2; A.lift_reduce = 0u;
+#define KS_GRP_DISPATCH(LOGN)                                                                        \
+    switch (mode) {                                                                                  \
+        case KS_MUL_RELIN: return launch_ks_grouped_t<LOGN, KS_MUL_RELIN>(lc, A, K, Gc, batch, st);   \
+        case KS_PLAIN: return launch_ks_grouped_t<LOGN, KS_PLAIN>(lc, A, K, Gc, batch, st);           \
+        case KS_ROTATE: return launch_ks_grouped_t<LOGN, KS_ROTATE>(lc, A, K, Gc, batch, st);         \
+    }                                                                                                \
+    return cudaErrorInvalidValue;
+    switch (lc.log_n) {
+        case 12: KS_GRP_DISPATCH(12)
+        case 13: KS_GRP_DISPATCH(13)
+        case 14: KS_GRP_DISPATCH(14)
     }
     return cudaErrorNotSupported;
 }

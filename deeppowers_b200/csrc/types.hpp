@@ -78,6 +78,23 @@ struct MsConsts {
     u32 has_t;
 };
 
+// Grouped hybrid key switching: the last K limbs of the context are special primes (P = their product), the
+// Lq = L - K ciphertext limbs form dnum = ceil(Lq / K) digits of K consecutive limbs.  Constants of one call, built on the
+// host (host_params.cpp:build_group_consts) and passed by value in the kernel parameter block, so that every use is a
+// constant-bank operand with a CTA-uniform index.  The MsConsts of such a call describe the division by P (inv = P^-1 ...).
+constexpr int KS_MAX_SPECIAL = 4;
+struct GroupConsts {
+    u32 Lq, K, dnum, pad_;
+    // limb parameters whose N^-1 (ninv, wninv) carries the factor that the basis conversion wants on the inverse transform's
+    // output: Qhat_j^-1 mod q_j for a ciphertext limb j (Qhat_j = product of the other moduli of its group), and
+    // (t * Phat_k)^-1 mod p_k for special limb Lq + k (Phat_k = P / p_k; t = 1 for plain rounding)
+    LimbParams lp_up[16];
+    u64 up[16][16], up_s[16][16];                                // [j][i]: Qhat_j mod q_i, with its Shoup companion (j < Lq, i < L)
+    u64 dn[KS_MAX_SPECIAL][16], dn_s[KS_MAX_SPECIAL][16];      // [k][i]: Phat_k mod q_i (i < Lq)
+    u64 neg_p[16];                                               // q_i - (P mod q_i): adding it subtracts P
+    u64 half[KS_MAX_SPECIAL];                                    // floor(p_k / 2)
+};
+
 // ---- twiddle table layout (host_params.cpp writes it, ntt_core.cuh reads it) -----------------------------
 // natural index of the twiddle of group i at stage s is 2^s + i.  Stages of the last
 // register pass (s >= LOGN-4) are stored transposed so that lane-consecutive rows read

@@ -303,6 +303,40 @@ class Context:
         pq = 2 * (self.L - 1) * self.N
         self._chk(self._l.dpfhe_rotate_hybrid_host(self._h, _hptr(ct), int(galois_elt), _hptr(gk), _hptr(out, True), ct.size // pq, int(t_plain)))
 
+
+    # grouped hybrid key switching: the last n_special limbs are special primes, data has L - n_special
+    # limbs in digits of n_special limbs, keys [grouped_digits(n_special)][2][L][N]
+    def grouped_digits(self, n_special):
+        d = C.c_uint(0)
+        self._chk(self._l.dpfhe_grouped_digits(self._h, int(n_special), C.byref(d)))
+        return int(d.value)
+
+    def keyswitch_grouped(self, n_special, d, key, out, batch, t_plain=0, stream=None):
+        self._chk(self._l.dpfhe_keyswitch_grouped(self._h, int(n_special), _ptr(d), _ptr(key), _ptr(out), batch, int(t_plain), _stream(stream)))
+
+    def ct_mul_relin_grouped(self, n_special, a, b, evk, out, batch, t_plain=0, stream=None):
+        self._chk(self._l.dpfhe_ct_mul_relin_grouped(self._h, int(n_special), _ptr(a), _ptr(b), _ptr(evk), _ptr(out), batch, int(t_plain),
+                                                     _stream(stream)))
+
+    def rotate_grouped(self, n_special, ct, galois_elt, gk, out, batch, t_plain=0, stream=None):
+        self._chk(self._l.dpfhe_rotate_grouped(self._h, int(n_special), _ptr(ct), int(galois_elt), _ptr(gk), _ptr(out), batch, int(t_plain),
+                                               _stream(stream)))
+
+    def mod_down_special(self, n_special, polys, out, n_polys, t_plain=0, stream=None):
+        self._chk(self._l.dpfhe_mod_down_special(self._h, int(n_special), _ptr(polys), _ptr(out), n_polys, int(t_plain), _stream(stream)))
+
+    def mod_down_special_host(self, n_special, polys, out, t_plain=0):
+        self._chk(self._l.dpfhe_mod_down_special_host(self._h, int(n_special), _hptr(polys), _hptr(out, True), polys.size // self.P, int(t_plain)))
+
+    def ct_mul_relin_grouped_host(self, n_special, a, b, evk, out, t_plain=0):
+        pq = 2 * (self.L - n_special) * self.N
+        self._chk(self._l.dpfhe_ct_mul_relin_grouped_host(self._h, int(n_special), _hptr(a), _hptr(b), _hptr(evk), _hptr(out, True), a.size // pq,
+                                                          int(t_plain)))
+
+    def rotate_grouped_host(self, n_special, ct, galois_elt, gk, out, t_plain=0):
+        pq = 2 * (self.L - n_special) * self.N
+        self._chk(self._l.dpfhe_rotate_grouped_host(self._h, int(n_special), _hptr(ct), int(galois_elt), _hptr(gk), _hptr(out, True), ct.size // pq,
+                                                    int(t_plain)))
     def mod_switch_down_host(self, polys, out, t_plain=0):
         self._chk(self._l.dpfhe_mod_switch_down_host(self._h, _hptr(polys), _hptr(out, True), polys.size // self.P, int(t_plain)))
 

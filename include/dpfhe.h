@@ -186,6 +186,33 @@ int dpfhe_rotate_hybrid_host(dpfhe_ctx *ctx, const uint64_t *h_ct, uint64_t galo
                              uint64_t *h_out, size_t batch, uint64_t t_plain);
 int dpfhe_mod_switch_down_host(dpfhe_ctx *ctx, const uint64_t *h_in, uint64_t *h_out, size_t n_polys, uint64_t t_plain);
 
+/* ---- grouped hybrid key switching: digits of several limbs, dnum < L.  The context's last n_special = K
+ *      limbs are special primes (P = their product); ciphertexts carry Lq = L-K limbs ([batch][2][Lq][N]), grouped into
+ *      dnum = ceil(Lq / K) digits of K consecutive limbs (the last digit may be shorter).  Switch keys are
+ *      [dnum][2][L limbs][N] and encrypt P * F_g * target, F_g = 1 on the limbs of digit g and 0 on the others.  Every digit
+ *      is raised to all L limbs by fast basis conversion, accumulated against its key, and the pair is divided by P (rounding
+ *      as in dpfhe_mod_switch_down, every special residue lifted centred).  Against one special prime this needs fewer
+ *      transforms (24 instead of 30 per ct x ct at Lq = 4, K = 2) and keys of dnum instead of Lq digits.
+ *      1 <= K <= 4, 2K <= L; K = 1 is the hybrid variant above, bit for bit.  dpfhe_grouped_digits returns dnum.
+ *      The reference has no counterpart (SURVEY.md §8 row f-2 widening). ---- */
+int dpfhe_grouped_digits(const dpfhe_ctx *ctx, unsigned n_special, unsigned *digits);
+int dpfhe_keyswitch_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_d, const uint64_t *d_key, uint64_t *d_out,
+                            size_t batch, uint64_t t_plain, void *stream);
+int dpfhe_ct_mul_relin_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_a, const uint64_t *d_b,
+                               const uint64_t *d_evk, uint64_t *d_out, size_t batch, uint64_t t_plain, void *stream);
+int dpfhe_rotate_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk,
+                         uint64_t *d_out, size_t batch, uint64_t t_plain, void *stream);
+/* division by the product of the last n_special limbs alone (the mod-down half of the calls above; n_special = 1 is
+ * dpfhe_mod_switch_down): in [n_polys][L][N] -> out [n_polys][L - n_special][N], 1 <= n_special <= 4, n_special < L */
+int dpfhe_mod_down_special(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_in, uint64_t *d_out, size_t n_polys,
+                           uint64_t t_plain, void *stream);
+int dpfhe_mod_down_special_host(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *h_in, uint64_t *h_out, size_t n_polys,
+                                uint64_t t_plain);
+int dpfhe_ct_mul_relin_grouped_host(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *h_a, const uint64_t *h_b,
+                                    const uint64_t *h_evk, uint64_t *h_out, size_t batch, uint64_t t_plain);
+int dpfhe_rotate_grouped_host(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *h_ct, uint64_t galois_elt,
+                              const uint64_t *h_gk, uint64_t *h_out, size_t batch, uint64_t t_plain);
+
 /* ---- synthetic data: x[k] = mulhi64(splitmix64(seed + k), q_limb),
  *      k = (first_poly + p)*L*N + l*N + n.  Fills [n_polys][L][N]. ---- */
 int dpfhe_fill_uniform(dpfhe_ctx *ctx, uint64_t seed, uint64_t first_poly, uint64_t *d_data,

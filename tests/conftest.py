@@ -92,6 +92,14 @@ class Emu:
                                      out.reshape(-1), batch, int(galois), int(t_plain), G or 2 * self.L) == 0
         return out
 
+
+    def ks_grouped(self, K, mode, a, b, key, batch, galois=0, t_plain=0, G=None):
+        out = np.zeros((batch, 2, self.L - K, self.N), dtype=np.uint64)
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64)
+        assert self._l.emu_ks_grouped(self._h, int(K), mode, a.reshape(-1), b.reshape(-1), np.ascontiguousarray(key).reshape(-1),
+                                      out.reshape(-1), batch, int(galois), int(t_plain), G or 2 * self.L) == 0
+        return out
     def rotate_hoisted(self, ct, galois, keys, G=None):
         ct = np.ascontiguousarray(ct, dtype=np.uint64)
         batch = ct.size // (2 * self.L * self.N)
@@ -114,6 +122,12 @@ class Emu:
         x = np.ascontiguousarray(polys, dtype=np.uint64).reshape(-1, self.L, self.N)
         out = np.zeros((x.shape[0], self.L - 1, self.N), dtype=np.uint64)
         assert self._l.emu_mod_switch(self._h, x.reshape(-1), out.reshape(-1), x.shape[0], int(t_plain)) == 0
+        return out
+
+    def mod_down_special(self, K, polys, t_plain=0):
+        x = np.ascontiguousarray(polys, dtype=np.uint64).reshape(-1, self.L, self.N)
+        out = np.zeros((x.shape[0], self.L - K, self.N), dtype=np.uint64)
+        assert self._l.emu_mod_down_special(self._h, int(K), x.reshape(-1), out.reshape(-1), x.shape[0], int(t_plain)) == 0
         return out
 
     def scalar(self, name, l, *args):
@@ -143,9 +157,11 @@ def _build_emu(variant):
     lib.emu_ntt.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int]
     lib.emu_ntt_pair.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int]
     lib.emu_ks.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint]
+    lib.emu_ks_grouped.argtypes = [C.c_void_p, C.c_uint, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_uint]
     lib.emu_ks_hybrid.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_uint]
     lib.emu_rotate_hoisted.argtypes = [C.c_void_p, _u64p, C.c_size_t, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint, C.POINTER(C.c_uint)]
     lib.emu_pt_inner.argtypes = [C.c_void_p, _u64p, C.c_uint, _u64p, C.c_uint, _u64p, C.c_size_t, C.c_uint]
+    lib.emu_mod_down_special.argtypes = [C.c_void_p, C.c_uint, _u64p, _u64p, C.c_size_t, C.c_uint64]
     lib.emu_mod_switch.argtypes = [C.c_void_p, _u64p, _u64p, C.c_size_t, C.c_uint64]
     for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2), ("barrett_long", 2), ("pti_fold", 4),
                       ("shoup_lazy", 2), ("shoup_exact", 2)):

@@ -197,6 +197,70 @@ void run_ks_hybrid(Emu &e, const uint64_t *a, const uint64_t *b, const uint64_t 
     free(key_s);
 }
 
+// grouped hybrid key switching: groups of Lq + K slots, the role programs of ks_grouped_kernel in dependency order
+template <int LOGN, int NT, int MODE>
+void run_ks_grouped(Emu &e, unsigned Ks, const uint64_t *a, const uint64_t *b, const uint64_t *key, uint64_t *out, size_t batch,
+                    uint32_t galois, uint64_t t_plain, unsigned G) {
+    const size_t N = (size_t)1 << LOGN;
+    const unsigned LK = e.hp.L, Lq = LK - Ks, GS = LK;
+    unsigned groups = G / GS;
+    if (groups == 0) groups = 1;
+    MsConsts K;
+    GroupConsts Gc;
+    build_group_consts(e.hp, Ks, t_plain, Gc, K);
+    const unsigned dnum = Gc.dnum;
+    uint64_t *buf = aligned_new<uint64_t>(N);
+    uint64_t *scratch = aligned_new<uint64_t>((size_t)groups * GS * 2 * N);
+    uint64_t *hyb_all = aligned_new<uint64_t>((size_t)groups * Ks * KS_HYB_ROWS * N);
+    uint64_t *acc = aligned_new<uint64_t>((size_t)groups * GS * 2 * 2 * N);   // [slot][parity][2][N]
+    const size_t key_words = (size_t)2 * dnum * LK * N;
+    uint64_t *key_s = aligned_new<uint64_t>(key_words);
+    for (size_t k = 0; k < key_words; ++k)
+        key_s[k] = (uint64_t)((((unsigned __int128)key[k]) << 64) / e.lp[(k / N) % LK].q);
+    KsArgs A;
+    A.a = a; A.b = b; A.key = key; A.key_s = key_s; A.out = out; A.scratch = scratch;
+    A.tw = e.tw; A.itw = e.itw; A.L = Lq; A.galois = galois; A.Lk = LK; A.hyb = hyb_all; A.only = nullptr;
+    A.acc = acc; A.acc_par = 2; A.lift_reduce = 0;
+    auto acc_of = [&](unsigned slot, unsigned parity) { return acc + ((size_t)slot * 2 + parity) * 2 * N; };
+    HostCta cta{NT};
+    for (size_t r = 0; r * groups < batch; ++r) {
+        const unsigned par = (unsigned)(r & 1);
+        for (unsigned g = 0; g < groups; ++g) {
+            const size_t ct = r * groups + g;
+            if (ct >= batch) break;
+            const unsigned base = g * GS;
+            auto hyb_of = [&](unsigned k) { return hyb_all + ((size_t)g * Ks + k) * KS_HYB_ROWS * N; };
+            const uint64_t *t_rows = scratch + ((size_t)base * 2 + par) * N;
+            for (unsigned i = 0; i < Lq; ++i)
+                ks_phase1<LOGN, NT, MODE, true>(cta, buf, A, Gc.lp_up[i], ct, i, scratch + ((size_t)(base + i) * 2 + par) * N, acc_of(base + i, par),
+                                                K.qlm[i], K.qlm_s[i], nullptr, 0, i / Ks);
+            for (unsigned i = 0; i < Lq; ++i)
+                for (uint32_t jj = 1; jj < dnum; ++jj)
+                    ks_phase2_group<LOGN, NT, false>(cta, buf, A, Gc, e.lp[i], ct, i, (i / Ks + jj) % dnum, jj, t_rows, 2 * N, acc_of(base + i, par));
+            for (unsigned k = 0; k < Ks; ++k) {
+                const unsigned i = Lq + k;
+                uint64_t *hyb = hyb_of(k);
+                for (uint32_t jj = 0; jj < dnum; ++jj)
+                    ks_phase2_group<LOGN, NT, true>(cta, buf, A, Gc, e.lp[i], ct, i, (g + jj) % dnum, jj, t_rows, 2 * N, hyb);
+                for (unsigned c = 0; c < 2; ++c)
+                    ms_tau_body<LOGN, NT, true>(cta, buf, hyb + c * N, hyb + c * N, A.itw + (size_t)i * N, Gc.lp_up[i], hyb + ks_hyb_tau_row(par, c) * N, K);
+            }
+            const size_t P = (size_t)Lq * N;
+            for (unsigned i = 0; i < Lq; ++i)
+                for (unsigned c = 0; c < 2; ++c) {
+                    uint64_t *row = out + ct * 2 * P + c * P + (size_t)i * N;
+                    ms_limb_group<LOGN, NT>(cta, buf, hyb_of(0) + ks_hyb_tau_row(par, c) * N, (size_t)KS_HYB_ROWS * N, acc_of(base + i, par) + c * N, row,
+                                            A.tw + (size_t)i * N, e.lp[i], K, Gc, i);
+                }
+        }
+    }
+    free(buf);
+    free(scratch);
+    free(hyb_all);
+    free(acc);
+    free(key_s);
+}
+
 // hoisted rotations: the device bodies (hoist_phase1/2, rot_apply_row) in kernel order, the per-rotation constants
 // computed the way launch_rot_prepare does (negmask -> NTT -> kprime), flagged ciphertexts through the ordinary rotate
 template <int LOGN, int NT>
@@ -362,6 +426,24 @@ int emu_ks_hybrid(void *h, int mode, const uint64_t *a, const uint64_t *b, const
     return -1;
 }
 
+// grouped hybrid variants: the context's last K limbs are special primes, data has L-K limbs, keys ceil((L-K)/K) digits
+int emu_ks_grouped(void *h, unsigned K, int mode, const uint64_t *a, const uint64_t *b, const uint64_t *key, uint64_t *out, size_t batch,
+                   uint32_t galois, uint64_t t_plain, unsigned G) {
+    Emu *e = (Emu *)h;
+    if (K < 1 || K > (unsigned)KS_MAX_SPECIAL || 2 * K > e->hp.L) return -1;
+#define DISPATCH_G(LOGN, NT)                                                                                   \
+    if (mode == 0) run_ks_grouped<LOGN, NT, KS_MUL_RELIN>(*e, K, a, b, key, out, batch, galois, t_plain, G);    \
+    else if (mode == 1) run_ks_grouped<LOGN, NT, KS_PLAIN>(*e, K, a, b, key, out, batch, galois, t_plain, G);   \
+    else run_ks_grouped<LOGN, NT, KS_ROTATE>(*e, K, a, b, key, out, batch, galois, t_plain, G);                 \
+    return 0;
+    switch (e->hp.log_n) {
+        case 12: DISPATCH_G(12, 256)
+        case 13: DISPATCH_G(13, 256)
+        case 14: DISPATCH_G(14, 256)
+    }
+    return -1;
+}
+
 int emu_rotate_hoisted(void *h, const uint64_t *ct, size_t n_rot, const uint64_t *galois, const uint64_t *keys, uint64_t *out, size_t batch,
                        unsigned G, unsigned *n_flagged) {
     Emu *e = (Emu *)h;
@@ -397,6 +479,39 @@ int emu_pt_inner(void *h, const uint64_t *steps, unsigned nb, const uint64_t *pt
         default: rc = -1;
     }
     free(smem);
+    return rc;
+}
+
+// division by the product of the last Ks limbs through the bodies of md_tau_kernel / md_limb_kernel
+int emu_mod_down_special(void *h, unsigned Ks, const uint64_t *in, uint64_t *out, size_t n_polys, uint64_t t_plain) {
+    Emu *e = (Emu *)h;
+    const unsigned L = e->hp.L;
+    const size_t N = (size_t)1 << e->hp.log_n;
+    if (Ks < 1 || Ks > (unsigned)KS_MAX_SPECIAL || Ks >= L) return -1;
+    const unsigned Lq = L - Ks;
+    MsConsts K;
+    GroupConsts G;
+    build_group_consts(e->hp, Ks, t_plain, G, K);
+    uint64_t *buf = aligned_new<uint64_t>(N), *tau = aligned_new<uint64_t>((size_t)Ks * N);
+    auto run = [&](auto logn_tag, auto nt_tag) {
+        constexpr int LOGN = decltype(logn_tag)::value, NT = decltype(nt_tag)::value;
+        HostCta cta{NT};
+        for (size_t w = 0; w < n_polys; ++w) {
+            for (unsigned k = 0; k < Ks; ++k)
+                ms_tau_body<LOGN, NT>(cta, buf, in + (w * L + Lq + k) * N, nullptr, e->itw + (size_t)(Lq + k) * N, G.lp_up[Lq + k], tau + (size_t)k * N, K);
+            for (unsigned i = 0; i < Lq; ++i)
+                ms_limb_group<LOGN, NT, false>(cta, buf, tau, N, in + (w * L + i) * N, out + (w * Lq + i) * N, e->tw + (size_t)i * N, e->lp[i], K, G, i);
+        }
+    };
+    int rc = 0;
+    switch (e->hp.log_n) {
+        case 12: run(std::integral_constant<int, 12>{}, std::integral_constant<int, 256>{}); break;
+        case 13: run(std::integral_constant<int, 13>{}, std::integral_constant<int, 256>{}); break;
+        case 14: run(std::integral_constant<int, 14>{}, std::integral_constant<int, 512>{}); break;
+        default: rc = -1;
+    }
+    free(buf);
+    free(tau);
     return rc;
 }
 

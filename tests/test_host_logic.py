@@ -180,6 +180,53 @@ def test_emulated_hybrid_keyswitch_bodies(make_emu, oracle_mod, log_n, L, batch,
         assert np.array_equal(got[k, 0], c0) and np.array_equal(got[k, 1], c1)
 
 
+@pytest.mark.parametrize("log_n,L,K,t", [(12, 4, 2, 65537), (13, 5, 3, 0), (14, 3, 2, 65537), (12, 6, 4, 65537), (12, 3, 1, 65537)])
+def test_emulated_mod_down_special(make_emu, oracle_mod, log_n, L, K, t):
+    """division by the product of the last K limbs (md_tau / md_limb kernel bodies); K = 1 is the one-limb modulus switch"""
+    e, o = make_emu(log_n, L), oracle_mod.Oracle(log_n, L)
+    x = o.fill_uniform(41, 3)
+    x[0, :, ::3] = 0
+    x[1] = (np.array(o.moduli, dtype=np.uint64) - 1)[:, None]
+    got = e.mod_down_special(K, x, t)
+    assert np.array_equal(got, o.mod_down_special(K, x, t))
+    if K == 1:
+        assert np.array_equal(got, e.mod_switch(x, t))
+
+
+def _grouped_inputs(o, K, batch, seed):
+    """[batch][2][L-K][N] uniform residues (with edge rows) under the first L-K moduli, and a uniform grouped key"""
+    Lq = o.L - K
+    x = o.fill_uniform(seed, 2 * batch)[:, :Lq].reshape(batch, 2, Lq, o.N).copy()
+    q = np.array(o.moduli[:Lq], dtype=np.uint64)
+    x[0, 0] = (q - 1)[:, None]
+    x[0, 1, :, ::2] = 0
+    dnum = o.grouped_digits(K)
+    key = o.fill_uniform(seed + 1, 2 * dnum).reshape(dnum, 2, o.L, o.N)
+    return x, key
+
+
+@pytest.mark.parametrize("log_n,L,K,batch,t,G,variant", [(12, 6, 2, 3, 65537, 13, "fast"), (12, 5, 2, 2, 65537, None, "fast"), (13, 6, 2, 2, 0, None, "fast"),
+                                                         (14, 4, 2, 1, 65537, None, "fast"), (12, 10, 3, 2, 65537, None, "fast"),
+                                                         (12, 12, 4, 1, 0, None, "fast"), (12, 4, 1, 2, 65537, None, "fast"),
+                                                         (12, 6, 2, 2, 65537, None, "gen")])
+def test_emulated_grouped_keyswitch_bodies(make_emu, oracle_mod, log_n, L, K, batch, t, G, variant):
+    """digits of K limbs and K special primes: the device bodies in the role order of ks_grouped_kernel against the oracle, all
+    three modes (ragged last digit, three and four special primes, one special prime = the hybrid variant)"""
+    e, o = make_emu(log_n, L, variant=variant), oracle_mod.Oracle(log_n, L)
+    a, key = _grouped_inputs(o, K, batch, 31)
+    b, _ = _grouped_inputs(o, K, batch, 33)
+    assert np.array_equal(e.ks_grouped(K, 0, a, b, key, batch, t_plain=t, G=G), o.ct_mul_relin_grouped(K, a, b, key, t))
+    g = o.galois_elt(3)
+    assert np.array_equal(e.ks_grouped(K, 2, a, None, key, batch, galois=g, t_plain=t, G=G), o.rotate_grouped(K, a, g, key, t))
+    d = a[:, 1]
+    got = e.ks_grouped(K, 1, d, None, key, batch, t_plain=t, G=G)
+    for k in range(batch):
+        c0, c1 = o.keyswitch_grouped(K, d[k], key, t)
+        assert np.array_equal(got[k, 0], c0) and np.array_equal(got[k, 1], c1)
+    if K == 1:
+        assert np.array_equal(e.ks_grouped(1, 0, a, b, key, batch, t_plain=t, G=G), e.ks_hybrid(0, a, b, key, batch, t_plain=t, G=G))
+
+
 @pytest.mark.parametrize("log_n,L", [(12, 3), (13, 4), (14, 2)])
 def test_generic_variant_on_the_default_basis(make_emu, oracle_mod, log_n, L):
     """the generic kernels must also be right for k * 2^32 + 1 moduli (DPFHE_FORCE_GENERIC runs them on the default basis)"""

@@ -49,6 +49,20 @@ for env in ({"DPFHE_FORCE_GENERIC": "1"}, {"DPFHE_KS_SINGLE": "1"}):
     c.close()
     for k in env:
         del os.environ[k]
+# grouped hybrid key switching: digits of two limbs, two special primes (ks_grouped_kernel), ragged last digit as well
+for L, K in ((6, 2), (5, 2)):
+    c = dp.Context(12, L)
+    N, B, Lq = 4096, 3, L - K
+    dn = c.grouped_digits(K)
+    cq = dp.Context(12, Lq, c.moduli[:Lq])
+    ga = torch.empty((B, 2, Lq, N), dtype=torch.int64, device="cuda"); gb = torch.empty_like(ga); go = torch.empty_like(ga)
+    cq.fill_uniform(11, ga, 2 * B); cq.fill_uniform(12, gb, 2 * B)
+    cq.close()
+    gk = torch.empty((dn, 2, L, N), dtype=torch.int64, device="cuda"); c.fill_uniform(13, gk, 2 * dn)
+    c.ct_mul_relin_grouped(K, ga, gb, gk, go, B, 65537); c.ct_mul_relin_grouped(K, ga, gb, gk, go, B, 65537)
+    c.rotate_grouped(K, ga, 5, gk, go, B, 0)
+    torch.cuda.synchronize()
+    c.close()
 m = dp.MultiContext(12, 2, devices=[0, 0])
 B, L, N = 5, 2, 4096
 ha = np.zeros((B, 2, L, N), dtype=np.uint64); hk = np.zeros((L, 2, L, N), dtype=np.uint64); ho = np.zeros_like(ha)
