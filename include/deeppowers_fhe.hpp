@@ -103,6 +103,36 @@ public:
         same(ct.count, ct.count, out.count);
         check(dpfhe_rotate_hybrid_host(ctx_, ct.data, galois_element(steps), galois_key, out.data, ct.count, plain_modulus));
     }
+    // grouped hybrid forms (digits of `special` limbs, `special` special primes at the end of the basis; dpfhe.h): batches hold
+    // limbs()-special limbs, keys grouped_digits(special) digits
+    unsigned grouped_digits(unsigned special) const {
+        unsigned d = 0;
+        check(dpfhe_grouped_digits(ctx_, special, &d));
+        return d;
+    }
+    void multiply_relin_grouped(unsigned special, ConstCiphertextBatch a, ConstCiphertextBatch b, const std::uint64_t *relin_key, CiphertextBatch out,
+                                std::uint64_t plain_modulus = 0) {
+        same(a.count, b.count, out.count);
+        check(dpfhe_ct_mul_relin_grouped_host(ctx_, special, a.data, b.data, relin_key, out.data, a.count, plain_modulus));
+    }
+    void rotate_grouped(unsigned special, ConstCiphertextBatch ct, long steps, const std::uint64_t *galois_key, CiphertextBatch out,
+                        std::uint64_t plain_modulus = 0) {
+        same(ct.count, ct.count, out.count);
+        check(dpfhe_rotate_grouped_host(ctx_, special, ct.data, galois_element(steps), galois_key, out.data, ct.count, plain_modulus));
+    }
+    void multiply_relin_grouped_device(unsigned special, const std::uint64_t *a, const std::uint64_t *b, const std::uint64_t *relin_key,
+                                       std::uint64_t *out, std::size_t count, std::uint64_t plain_modulus = 0, void *stream = nullptr) {
+        check(dpfhe_ct_mul_relin_grouped(ctx_, special, a, b, relin_key, out, count, plain_modulus, stream));
+    }
+    void rotate_grouped_device(unsigned special, const std::uint64_t *ct, long steps, const std::uint64_t *galois_key, std::uint64_t *out,
+                               std::size_t count, std::uint64_t plain_modulus = 0, void *stream = nullptr) {
+        check(dpfhe_rotate_grouped(ctx_, special, ct, galois_element(steps), galois_key, out, count, plain_modulus, stream));
+    }
+    // divide by the product of the last `special` limbs: in holds limbs() limbs per polynomial, out limbs()-special
+    void mod_down_special_device(unsigned special, const std::uint64_t *ct, std::uint64_t *out, std::size_t count, std::uint64_t plain_modulus = 0,
+                                 void *stream = nullptr) {
+        check(dpfhe_mod_down_special(ctx_, special, ct, out, 2 * count, plain_modulus, stream));
+    }
     // drop the last limb: in holds limbs() limbs per polynomial, out limbs()-1
     void mod_switch_to_next(ConstCiphertextBatch in, CiphertextBatch out, std::uint64_t plain_modulus = 0) {
         same(in.count, in.count, out.count);
