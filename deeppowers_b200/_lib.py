@@ -40,6 +40,8 @@ SYMBOLS = {
     "dpfhe_keyswitch_grouped": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]),
     "dpfhe_ct_mul_relin_grouped": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]),
     "dpfhe_rotate_grouped": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]),
+    "dpfhe_rotate_hoisted_grouped": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64,
+                                               C.c_void_p]),
     "dpfhe_mod_down_special": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]),
     "dpfhe_mod_down_special_host": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]),
     "dpfhe_ct_mul_relin_grouped_host": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]),

@@ -281,15 +281,15 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     }
     CTX_TRY(cudaMalloc(&lc.ks_key_s, 2 * L * L * N * 8));
     ctx->device_bytes += 2 * L * L * N * 8;
-    CTX_TRY(cudaMalloc(&lc.ks_flags, lc.ks_slots * sizeof(u32)));
-    CTX_TRY(cudaMemset(lc.ks_flags, 0, lc.ks_slots * sizeof(u32)));
+    CTX_TRY(cudaMalloc(&lc.ks_flags, 2 * lc.ks_slots * sizeof(u32)));   // digit flags, then the "round finished" marks of ks_hoistg_kernel
+    CTX_TRY(cudaMemset(lc.ks_flags, 0, 2 * lc.ks_slots * sizeof(u32)));
     CTX_TRY(cudaMalloc(&lc.ks_consumed, lc.ks_slots * sizeof(u32)));
     CTX_TRY(cudaMemset(lc.ks_consumed, 0, lc.ks_slots * sizeof(u32)));
     if (const char *env = getenv("DPFHE_KS_SINGLE")) lc.ks_single = atoi(env);
     CTX_TRY(cudaMalloc(&lc.ks_ticket, 64));
     CTX_TRY(cudaMalloc(&lc.ks_mail, lc.ks_slots * sizeof(u64)));
     CTX_TRY(cudaMemset(lc.ks_mail, 0, lc.ks_slots * sizeof(u64)));
-    ctx->device_bytes += 2 * lc.ks_slots * 2 * N * 8 + lc.ks_slots * (sizeof(u32) + sizeof(u64)) + 64;
+    ctx->device_bytes += 2 * lc.ks_slots * 2 * N * 8 + lc.ks_slots * (2 * sizeof(u32) + sizeof(u64)) + 64;
     if (getenv("DPFHE_KS_PROF")) {   // diagnostics: per-phase cycle counters of the fused kernel
         CTX_TRY(cudaMalloc(&lc.ks_prof, lc.ks_slots * 16 * sizeof(unsigned long long)));
         CTX_TRY(cudaMemset(lc.ks_prof, 0, lc.ks_slots * 16 * sizeof(unsigned long long)));
@@ -322,6 +322,7 @@ void dpfhe_context_destroy(dpfhe_ctx *ctx) {
     cudaFree(ctx->hoist_kprime);
     cudaFree(ctx->hoist_delta);
     cudaFree(ctx->hoist_zero);
+    cudaFree(ctx->hoistg_buf);
     cudaFree(ctx->lc.ks_hyb);
     for (int k = 0; k < PIPE_DEPTH; ++k) {
         cudaFree(ctx->stage_in[k]);
@@ -361,6 +362,7 @@ size_t dpfhe_context_device_bytes(const dpfhe_ctx *ctx) {
     n += ctx->ms_tau_bytes;                                                          // modulus-switch scratch
     n += ctx->hoist_chunk * (L * P8 + sizeof(u32));                                  // hoisted rotations: shared transforms + zero flags
     if (ctx->hoist_M) n += 3 * P8 + L * L * 8;                                       //   per-rotation constants
+    n += ctx->hoistg_bytes;                                                          //   grouped hybrid keys: lifted digits + accumulators
     if (ctx->lc.ks_prof) n += ctx->lc.ks_slots * 16 * sizeof(unsigned long long);
     return n;
 }
@@ -373,6 +375,8 @@ int dpfhe_context_trim(dpfhe_ctx *ctx) {
     if (rc) return rc;
     cudaFree(ctx->hoist_U); cudaFree(ctx->hoist_zero); cudaFree(ctx->ms_tau); cudaFree(ctx->stage_key);
     ctx->hoist_U = nullptr; ctx->hoist_zero = nullptr; ctx->hoist_chunk = 0;
+    cudaFree(ctx->hoistg_buf);
+    ctx->hoistg_buf = nullptr; ctx->hoistg_bytes = 0;
     ctx->ms_tau = nullptr; ctx->ms_tau_bytes = 0;
     ctx->stage_key = nullptr; ctx->stage_key_bytes = 0;
     for (int k = 0; k < PIPE_DEPTH; ++k) {
@@ -641,6 +645,66 @@ static int rotate_hoisted_impl(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_ro
 int dpfhe_rotate_hoisted(dpfhe_ctx *ctx, const uint64_t *d_ct, size_t n_rot, const uint64_t *galois_elts, const uint64_t *const *d_gks,
                          uint64_t *d_out, size_t batch, void *stream) {
     return rotate_hoisted_impl(ctx, d_ct, n_rot, galois_elts, d_gks, nullptr, d_out, batch, stream);
+}
+
+// Hoisted rotations with grouped hybrid keys: the mod-up of c1 is done once per ciphertext
+// (ks_hoistg_kernel), every rotation is then gathers + multiply-accumulates over all L limbs (rot_apply_grouped_kernel) and
+// the division by P (md_tau / md_limb kernels).  Same plaintexts as n_rot calls of dpfhe_rotate_grouped, not the same bits.
+int dpfhe_rotate_hoisted_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_ct, size_t n_rot, const uint64_t *galois_elts,
+                                 const uint64_t *const *d_gks, uint64_t *d_out, size_t batch, uint64_t t_plain, void *stream) {
+    int rc = enter(ctx);
+    if (rc) return rc;
+    if (batch == 0 || n_rot == 0) return DPFHE_OK;
+    CHECK_PTR(d_ct); CHECK_PTR(d_out);
+    if (!galois_elts || !d_gks) return fail(DPFHE_ERR_INVALID, "null argument");
+    rc = check_special(ctx, n_special);
+    if (rc) return rc;
+    const uint64_t two_n = (uint64_t)2 << ctx->hp.log_n;
+    const size_t N = ctx->N(), L = ctx->hp.L, Lq = L - n_special, Pq = Lq * N, dnum = (Lq + n_special - 1) / n_special;
+    for (unsigned k = 0; k < n_special; ++k)
+        if (t_plain >= ctx->hp.limbs[L - 1 - k].lp.q) return fail(DPFHE_ERR_INVALID, "plaintext modulus must be below the special prime");
+    for (size_t r = 0; r < n_rot; ++r) {
+        if (!(galois_elts[r] & 1) || galois_elts[r] >= two_n) return fail(DPFHE_ERR_INVALID, "galois element must be odd and < 2N");
+        if (!d_gks[r] || !aligned16(d_gks[r])) return fail(DPFHE_ERR_INVALID, "null or misaligned Galois key");
+    }
+    if (overlaps(d_out, n_rot * batch * 2 * Pq * 8, d_ct, batch * 2 * Pq * 8)) return fail(DPFHE_ERR_INVALID, "output must not overlap the input");
+    cudaStream_t st = pick(ctx, stream);
+    // scratch per ciphertext: lifted digits [dnum][L][N], accumulators [2][L][N], tau' rows [2][K][N]; at most ~4 GiB at a time
+    const size_t u_words = dnum * L * N, acc_words = 2 * L * N, tau_words = 2 * (size_t)n_special * N;
+    const size_t per_ct = (u_words + acc_words + tau_words) * sizeof(u64);
+    size_t cap = (size_t)4 << 30;
+    if (const char *e = getenv("DPFHE_HOIST_CAP_MB")) {
+        const long mb = atol(e);
+        if (mb > 0) cap = (size_t)mb << 20;
+    }
+    size_t chunk = cap / per_ct;
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    if (chunk * per_ct > ctx->hoistg_bytes) {
+        CU_TRY(cudaStreamSynchronize(st));
+        cudaFree(ctx->hoistg_buf);
+        ctx->hoistg_buf = nullptr;
+        ctx->hoistg_bytes = 0;
+        CU_TRY(cudaMalloc(&ctx->hoistg_buf, chunk * per_ct));
+        ctx->hoistg_bytes = chunk * per_ct;
+    }
+    u64 *U = ctx->hoistg_buf, *acc = U + chunk * u_words, *tau = acc + chunk * acc_words;
+    MsConsts K;
+    GroupConsts G;
+    build_group_consts(ctx->hp, n_special, t_plain, G, K);
+    for (size_t first = 0; first < batch; first += chunk) {
+        const size_t cnt = batch - first < chunk ? batch - first : chunk;
+        const u64 *in = d_ct + first * 2 * Pq;
+        CU_TRY(VCALL(launch_hoist_grouped, ctx->lc, in, U, G, cnt, st));
+        note_launch(ctx, 1);
+        for (size_t r = 0; r < n_rot; ++r) {
+            u64 *out = d_out + (r * batch + first) * 2 * Pq;
+            CU_TRY(VCALL(launch_rot_apply_grouped, ctx->lc, in, U, d_gks[r], nullptr, (u32)galois_elts[r], acc, K, G, cnt, st));
+            CU_TRY(VCALL(launch_mod_down_special, ctx->lc, acc, tau, out, K, G, 2 * cnt, st));
+            note_launch(ctx, 4);   // key_prepare, rot_apply_grouped, md_tau, md_limb
+        }
+    }
+    return DPFHE_OK;
 }
 
 int dpfhe_ct_mul_plain(dpfhe_ctx *ctx, const uint64_t *d_ct, const uint64_t *d_pt, uint64_t *d_out, size_t batch, void *stream) {

@@ -33,6 +33,8 @@ struct dpfhe_ctx {
     dpfhe::u64 *hoist_U = nullptr, *hoist_M = nullptr, *hoist_kprime = nullptr, *hoist_delta = nullptr;
     dpfhe::u32 *hoist_zero = nullptr;
     size_t hoist_chunk = 0;                  // ciphertexts the current U / zero buffers hold
+    dpfhe::u64 *hoistg_buf = nullptr;        // hoisted rotations with grouped hybrid keys: lifted digits, accumulators and tau' rows of a chunk
+    size_t hoistg_bytes = 0;
     dpfhe::u64 *stage_in[DPFHE_PIPE_DEPTH] = {}, *stage_out[DPFHE_PIPE_DEPTH] = {}, *stage_key = nullptr;
     size_t stage_in_bytes = 0, stage_out_bytes = 0, stage_key_bytes = 0;
     cudaEvent_t ev_h2d[DPFHE_PIPE_DEPTH] = {}, ev_comp[DPFHE_PIPE_DEPTH] = {}, ev_d2h[DPFHE_PIPE_DEPTH] = {};

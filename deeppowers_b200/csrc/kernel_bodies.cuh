@@ -718,17 +718,14 @@ struct HoistArgs {
     u32 L;
 };
 
-// digit = c1[i] as it is; publish its inverse transform
+// digit = the limb `row` as it is: copy it to `own` (its entry of U) and publish its inverse transform; zero (optional) is set when
+// a coefficient of the inverse transform is zero
 template <int LOGN, int NT, class CTA>
-DPFHE_HD void hoist_phase1(CTA &cta, u64 *buf, const HoistArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot) {
+DPFHE_HD void hoist_phase1_core(CTA &cta, u64 *buf, const u64 *row, u64 *own, u32 *zero, const Twiddle *itw, const LimbParams &p, u64 *t_slot) {
     constexpr int N = 1 << LOGN, NC = N / 2;
-    const size_t P = (size_t)A.L * N;
-    const U64x2 *src = reinterpret_cast<const U64x2 *>(A.ct + ct * 2 * P + P + (size_t)i * N);
-    const Twiddle *itw = A.itw + (size_t)i * N;
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(row);
     U64x2 *dst = reinterpret_cast<U64x2 *>(t_slot);
-    u32 *zero = A.zero + ct;
-    // the digit itself is the i == j entry of U (a plain copy), so that the apply step reads every digit the same way
-    U64x2 *diag = reinterpret_cast<U64x2 *>(A.U + ((ct * A.L + i) * A.L + i) * N);
+    U64x2 *diag = reinterpret_cast<U64x2 *>(own);
     auto build = [&](int c_lo, int n_c) {
         cta.par([&](int tid) {
             for (int lc = tid; lc < n_c; lc += NT) {
@@ -739,7 +736,7 @@ DPFHE_HD void hoist_phase1(CTA &cta, u64 *buf, const HoistArgs &A, const LimbPar
         });
     };
     auto emit = [&](int c, const U64x2 &v) {
-        if (v.x == 0 || v.y == 0) *zero = 1u;
+        if (zero && (v.x == 0 || v.y == 0)) *zero = 1u;
         st_cg(dst + c, v);
     };
     if constexpr (LOGN <= 13) {
@@ -759,29 +756,176 @@ DPFHE_HD void hoist_phase1(CTA &cta, u64 *buf, const HoistArgs &A, const LimbPar
     }
 }
 
-// U[ct][j][i] = NTT_i(t_j mod q_i)
+// digit = c1[i] as it is
 template <int LOGN, int NT, class CTA>
-DPFHE_HD void hoist_phase2(CTA &cta, u64 *buf, const HoistArgs &A, const LimbParams &p, size_t ct, u32 i, u32 j, const u64 *t_src) {
+DPFHE_HD void hoist_phase1(CTA &cta, u64 *buf, const HoistArgs &A, const LimbParams &p, size_t ct, u32 i, u64 *t_slot) {
+    constexpr size_t N = (size_t)1 << LOGN;
+    const size_t P = (size_t)A.L * N;
+    // the digit itself is the i == j entry of U (a plain copy), so that the apply step reads every digit the same way
+    hoist_phase1_core<LOGN, NT>(cta, buf, A.ct + ct * 2 * P + P + (size_t)i * N, A.U + ((ct * A.L + i) * A.L + i) * N, A.zero + ct,
+                                A.itw + (size_t)i * N, p, t_slot);
+}
+
+// forward transform of a lifted digit into `out_row` (lazy, below 16q).  LOAD(h) as in ks_phase2_core, values below BIN*q.
+template <int LOGN, int NT, int BIN, class CTA, class LOAD>
+DPFHE_HD void hoist_phase2_core(CTA &cta, u64 *buf, const Twiddle *tw, const LimbParams &p, LOAD load, u64 *out_row) {
     constexpr int N = 1 << LOGN, NC = N / 2;
-    const Twiddle *tw = A.tw + (size_t)i * N;
-    const U64x2 *src = reinterpret_cast<const U64x2 *>(t_src);
-    U64x2 *dst = reinterpret_cast<U64x2 *>(A.U + ((ct * A.L + j) * A.L + i) * N);
+    U64x2 *dst = reinterpret_cast<U64x2 *>(out_row);
     if constexpr (LOGN <= 13) {
-        cta.par([&](int tid) { fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); }); });
-        fwd_passes<LOGN, NT, 3>(cta, buf, tw, p);
+        load(0);
+        fwd_passes<LOGN, NT, BIN>(cta, buf, tw, p);
         cta.par([&](int tid) {
             for (int c = tid; c < NC; c += NT) st_stream(dst + c, reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)]);
         });
     } else {
         constexpr int HC = NC / 2;
         for (int h = 0; h < 2; ++h) {
-            cta.par([&](int tid) { fwd_load_stage_half<LOGN, NT, true>(buf, tw, p, tid, [&](int c) { return ld_cg(src + c); }, h); });
-            fwd_passes_blk<LOGN, NT, 3, 2>(cta, buf, tw, p, 2 * h);
+            load(h);
+            fwd_passes_blk<LOGN, NT, BIN, 2>(cta, buf, tw, p, 2 * h);
             cta.par([&](int tid) {
                 for (int lc = tid; lc < HC; lc += NT) st_stream(dst + h * HC + lc, reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lc)]);
             });
         }
     }
+}
+
+// U[ct][j][i] = NTT_i(t_j mod q_i)
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void hoist_phase2(CTA &cta, u64 *buf, const HoistArgs &A, const LimbParams &p, size_t ct, u32 i, u32 j, const u64 *t_src) {
+    constexpr size_t N = (size_t)1 << LOGN;
+    const Twiddle *tw = A.tw + (size_t)i * N;
+    const U64x2 *src = reinterpret_cast<const U64x2 *>(t_src);
+    auto get = [&](int c) { return ld_cg(src + c); };
+    auto load = [&](int h) {
+        cta.par([&](int tid) {
+            if constexpr (LOGN <= 13) fwd_load_stage<LOGN, NT, true>(buf, tw, p, tid, get);
+            else fwd_load_stage_half<LOGN, NT, true>(buf, tw, p, tid, get, h);
+        });
+    };
+    hoist_phase2_core<LOGN, NT, 3>(cta, buf, tw, p, load, A.U + ((ct * A.L + j) * A.L + i) * N);
+}
+
+// ---- hoisted rotations with grouped hybrid keys ------------------------------------
+// The rotations of one batch share the whole mod-up: U[ct][g][i] = the lift of digit g of the UNPERMUTED c1 in limb i (evaluation
+// form; the member limbs hold c1[i] itself).  A rotation permutes the rows of U instead of lifting the permuted digits: the same
+// plaintext and noise bound, not the bits of the non-hoisted rotate.
+struct HoistGArgs {
+    const u64 *ct;       // [batch][2][Lq][N]
+    u64 *U;              // [batch][dnum][L][N]
+    u64 *scratch;        // digit exchange slots, as KsArgs::scratch
+    const Twiddle *tw, *itw;
+};
+
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void hoistg_phase1(CTA &cta, u64 *buf, const HoistGArgs &A, const GroupConsts &G, size_t ct, u32 i, u64 *t_slot) {
+    constexpr size_t N = (size_t)1 << LOGN;
+    const size_t Pq = (size_t)G.Lq * N, L = G.Lq + G.K;
+    hoist_phase1_core<LOGN, NT>(cta, buf, A.ct + ct * 2 * Pq + Pq + (size_t)i * N, A.U + ((ct * G.dnum + i / G.K) * L + i) * N, nullptr,
+                                A.itw + (size_t)i * N, G.lp_up[i], t_slot);
+}
+
+// U[ct][g][i] for a limb i outside digit g (ciphertext or special limb): the basis conversion of ks_phase2_group, then the transform
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void hoistg_phase2(CTA &cta, u64 *buf, const HoistGArgs &A, const GroupConsts &G, const LimbParams &p, size_t ct, u32 i, u32 g,
+                            const u64 *t_rows, size_t t_stride) {
+    constexpr size_t N = (size_t)1 << LOGN;
+    const Twiddle *tw = A.tw + (size_t)i * N;
+    const u32 lo = g * G.K, hi = lo + G.K < G.Lq ? lo + G.K : G.Lq, L = G.Lq + G.K;
+    auto get = [&](int c) {
+        U64x2 r;
+        r.x = r.y = 0;
+        for (u32 j = lo; j < hi; ++j) {
+            const U64x2 v = ld_cg(reinterpret_cast<const U64x2 *>(t_rows + (size_t)j * t_stride) + c);
+            r.x += csub(shoup_lazy(v.x, G.up[j][i], G.up_s[j][i], p), p.q2);
+            r.y += csub(shoup_lazy(v.y, G.up[j][i], G.up_s[j][i], p), p.q2);
+        }
+        r.x = csub(r.x, p.q4);
+        r.y = csub(r.y, p.q4);
+        return r;
+    };
+    auto load = [&](int h) {
+        cta.par([&](int tid) {
+            if constexpr (LOGN <= 13) fwd_load_stage<LOGN, NT, false>(buf, tw, p, tid, get);
+            else fwd_load_stage_half<LOGN, NT, false>(buf, tw, p, tid, get, h);
+        });
+    };
+    hoist_phase2_core<LOGN, NT, 4>(cta, buf, tw, p, load, A.U + ((ct * G.dnum + g) * L + i) * N);
+}
+
+// one rotation applied to the shared lifts: acc[ct][c][i] = [i < Lq, c = 0] P * perm(c0[i]) + sum_g perm(U[ct][g][i]) o key[g][c][i]
+// for all L limbs, canonical; the division by P (md_tau / md_limb kernels) then yields (perm(c0) + ks0, ks1).
+struct RotApplyGArgs {
+    const u64 *ct;       // [batch][2][Lq][N]
+    const u64 *U;        // [batch][dnum][L][N]
+    const u64 *key;      // [dnum][2][L][N] Galois key of this rotation
+    const u64 *key_s;    // its Shoup companions
+    u64 *acc;            // [batch][2][L][N]
+    u32 galois;
+};
+
+template <int LOGN, int NT, int CB, class CTA>
+DPFHE_HD void rot_apply_grouped_rows(CTA &cta, const RotApplyGArgs &A, const GroupConsts &G, const MsConsts &K, const LimbParams &p, size_t ct0,
+                                     u32 n_ct, u32 i, int c_lo = 0, int c_hi = 1 << (LOGN - 1)) {
+    constexpr int N = 1 << LOGN;
+    const u32 L = G.Lq + G.K, D = G.dnum, g = A.galois;
+    const size_t P = (size_t)L * N, Pq = (size_t)G.Lq * N;
+    const bool limb = i < G.Lq;
+    const u64 pm = limb ? K.qlm[i] : 0, pm_s = limb ? K.qlm_s[i] : 0;   // P mod q_i: the c0 term is carried through the division
+    cta.par([&](int tid) {
+#pragma unroll 1
+        for (int c = c_lo + tid; c < c_hi; c += NT) {
+            const int pi0 = galois_index<LOGN>(2 * c, g);
+            const int pc = pi0 >> 1;
+            const bool swap = (pi0 & 1) != 0;
+            auto gather = [&](const u64 *row) {
+                const U64x2 v = ld_stream(reinterpret_cast<const U64x2 *>(row) + pc);
+                U64x2 r;
+                r.x = swap ? v.y : v.x;
+                r.y = swap ? v.x : v.y;
+                return r;
+            };
+            U64x2 r0[CB], r1[CB];
+#pragma unroll
+            for (int b = 0; b < CB; ++b) {
+                r0[b].x = r0[b].y = r1[b].x = r1[b].y = 0;
+                if (limb) {
+                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);   // rows past the end repeat the last one, not stored
+                    const U64x2 s0 = gather(A.ct + ct * 2 * Pq + (size_t)i * N);
+                    r0[b].x = shoup_lazy(s0.x, pm, pm_s, p);   // < SB*q
+                    r0[b].y = shoup_lazy(s0.y, pm, pm_s, p);
+                }
+            }
+            for (u32 d = 0; d < D; ++d) {
+                const size_t kb = ((size_t)d * 2 + 0) * P + (size_t)i * N, ka = ((size_t)d * 2 + 1) * P + (size_t)i * N;
+                const U64x2 vb = ld_keep(reinterpret_cast<const U64x2 *>(A.key + kb) + c), vbs = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + kb) + c);
+                const U64x2 va = ld_keep(reinterpret_cast<const U64x2 *>(A.key + ka) + c), vas = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + ka) + c);
+                const bool trim = acc_trim_after(SB, (int)d);
+#pragma unroll
+                for (int b = 0; b < CB; ++b) {
+                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);
+                    const U64x2 u = gather(A.U + ((ct * D + d) * L + i) * N);
+                    r0[b].x += shoup_lazy(u.x, vb.x, vbs.x, p);
+                    r0[b].y += shoup_lazy(u.y, vb.y, vbs.y, p);
+                    r1[b].x += shoup_lazy(u.x, va.x, vas.x, p);
+                    r1[b].y += shoup_lazy(u.y, va.y, vas.y, p);
+                    if (trim) {
+                        r0[b].x = csub(r0[b].x, p.q8); r0[b].y = csub(r0[b].y, p.q8);
+                        r1[b].x = csub(r1[b].x, p.q8); r1[b].y = csub(r1[b].y, p.q8);
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < CB; ++b) {
+                if ((u32)b < n_ct) {
+                    U64x2 o0, o1;
+                    o0.x = canon(r0[b].x, p); o0.y = canon(r0[b].y, p);
+                    o1.x = canon(r1[b].x, p); o1.y = canon(r1[b].y, p);
+                    st_stream(reinterpret_cast<U64x2 *>(A.acc + (ct0 + b) * 2 * P + (size_t)i * N) + c, o0);
+                    st_stream(reinterpret_cast<U64x2 *>(A.acc + (ct0 + b) * 2 * P + P + (size_t)i * N) + c, o1);
+                }
+            }
+        }
+    });
 }
 
 // one (ciphertext, limb i) row pair of one rotation: out = (perm(c0) + ks0, ks1) with the switched pair assembled from the

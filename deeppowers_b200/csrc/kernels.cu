@@ -576,6 +576,86 @@ __global__ void __launch_bounds__(NT, MINB) ks_grouped_kernel(KsArgs A, const __
     if (pending) divide(prev_ct, prev_tag, prev_parity);   // the group's last ciphertext
 }
 
+// Hoisted rotations with grouped hybrid keys, step 1: groups of L CTAs (every limb of the context) build
+// U[ct][g][i]; ticket / mailbox / flag machinery as in ks_hoist_kernel, the digits converted as in ks_grouped_kernel.
+// A limb CTA waits only for the digits of foreign groups and a special CTA publishes no digit, so the rounds of a group are
+// not held together by the digit flags alone: every CTA also publishes done[slot] = tag at the end of a round, and enters round
+// r only when the whole group has finished round r - 2 — the round whose digit slots and mailbox (both double-buffered by
+// round parity) round r overwrites.
+template <int LOGN, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ks_hoistg_kernel(HoistGArgs A, const __grid_constant__ LimbTable lt, const __grid_constant__ GroupConsts G,
+                                                             size_t batch, u32 *flags, u32 *done, u32 epoch, u32 *ticket, u64 *mail) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr size_t N = (size_t)1 << LOGN;
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    DevCta<NT> cta;
+    __shared__ u32 s_ct;
+    const u32 Lq = G.Lq, Ks = G.K, dnum = G.dnum, GS = Lq + Ks, slot = blockIdx.x, i = slot % GS, group = slot / GS, base = slot - i;
+    const LimbParams &p = lt.lp[i];
+    auto wait_for = [&](const u32 *f, u32 first, u32 count, u32 tag) {
+        if (threadIdx.x < count) {
+            while ((int)(ld_acquire_u32(f + first + threadIdx.x) - tag) < 0) {
+            }
+        }
+        __syncthreads();
+    };
+    for (u32 round = 0;; ++round) {
+        const u32 tag = epoch + round + 1, parity = round & 1u;
+        if (round >= 2) wait_for(done, base, GS, tag - 2);
+        if (threadIdx.x == 0) {
+            u64 *box = mail + (size_t)group * 2 + parity;
+            if (i == 0) {
+                const u32 t = atomicAdd(ticket, 1u);
+                st_release_u64(box, ((u64)tag << 32) | t);
+                s_ct = t;
+            } else {
+                u64 m;
+                do m = ld_acquire_u64(box);
+                while ((u32)(m >> 32) != tag);
+                s_ct = (u32)m;
+            }
+        }
+        __syncthreads();
+        const size_t ct = s_ct;
+        if (ct >= batch) break;
+        const u64 *t_rows = A.scratch + ((size_t)base * 2 + parity) * N;
+        u32 g_own = dnum;   // a special limb belongs to no digit
+        if (i < Lq) {
+            g_own = i / Ks;
+            hoistg_phase1<LOGN, NT>(cta, buf, A, G, ct, i, A.scratch + ((size_t)slot * 2 + parity) * N);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_u32(flags + slot, tag);
+        }
+        for (u32 jj = 0; jj < dnum; ++jj) {
+            const u32 g = (group + i + jj) % dnum;
+            if (g == g_own) continue;
+            const u32 lo = g * Ks, cnt = lo + Ks < Lq ? Ks : Lq - lo;
+            wait_for(flags, base + lo, cnt, tag);
+            hoistg_phase2<LOGN, NT>(cta, buf, A, G, p, ct, i, g, t_rows, 2 * N);
+        }
+        __syncthreads();   // every thread is past its last read of the group's digit slots
+        if (threadIdx.x == 0) st_release_u32(done + slot, tag);
+    }
+}
+
+// step 2: one rotation applied to blocks of ROT_CB ciphertexts x one limb of the context (gathers + multiply-accumulates)
+template <int LOGN, int NT, int MINB, int ROT_CB>
+__global__ void __launch_bounds__(NT, MINB) rot_apply_grouped_kernel(RotApplyGArgs A, const __grid_constant__ LimbTable lt, const __grid_constant__ MsConsts K,
+                                                                     const __grid_constant__ GroupConsts G, size_t batch, u32 nseg) {
+    DevCta<NT> cta;
+    constexpr int NC = 1 << (LOGN - 1);
+    const u32 L = G.Lq + G.K;
+    const size_t n_blocks = (batch + ROT_CB - 1) / ROT_CB, n_items = n_blocks * L * nseg;
+    const int seg_chunks = NC / (int)nseg;
+    for (size_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const u32 seg = (u32)(w % nseg), i = (u32)((w / nseg) % L);
+        const size_t ct0 = (w / nseg / L) * ROT_CB;
+        const u32 n_ct = (u32)(batch - ct0 < (size_t)ROT_CB ? batch - ct0 : (size_t)ROT_CB);
+        rot_apply_grouped_rows<LOGN, NT, ROT_CB>(cta, A, G, K, lt.lp[i], ct0, n_ct, i, (int)seg * seg_chunks, ((int)seg + 1) * seg_chunks);
+    }
+}
+
 // ------------------------------------------------------------------ plaintext inner products (BSGS inner loop)
 template <int LOGN, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) pt_inner_kernel(PtInnerArgs A, const __grid_constant__ LimbTable lt, u32 g0, u32 gcnt) {
@@ -1152,6 +1232,89 @@ cudaError_t launch_hoist(LaunchCtx &lc, const u64 *ct, u64 *U, u32 *zero, size_t
         case 14: return launch_hoist_t<14>(lc, A, batch, st);
     }
     return cudaErrorInvalidValue;
+}
+
+template <int LOGN>
+static cudaError_t launch_hoistg_t(LaunchCtx &lc, const HoistGArgs &A, const GroupConsts &Gc, size_t batch, cudaStream_t st) {
+    constexpr int NT = 256, MINB = 3;
+    auto kern = ks_hoistg_kernel<LOGN, NT, MINB>;
+    const size_t smem = LOGN <= 13 ? Geometry<LOGN>::LIMB_BYTES : Geometry<13>::LIMB_BYTES;
+    static ConfiguredMask configured;
+    if (!configured.has(lc.device)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured.set(lc.device);
+    }
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    size_t G = (size_t)lc.num_sms * occ;
+    if (G > lc.ks_slots) G = lc.ks_slots;
+    G = (G / lc.L) * lc.L;
+    if (G > batch * lc.L) G = batch * lc.L;
+    if (G == 0) return cudaErrorInvalidConfiguration;
+    cudaError_t em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
+    if (em != cudaSuccess) return em;
+    HoistGArgs args = A;
+    LimbTable lt = lc.lt;
+    GroupConsts gc = Gc;
+    size_t batch_arg = batch;
+    u32 *flags = lc.ks_flags;
+    u32 *done = lc.ks_flags + lc.ks_slots;   // second half of the flag array: "round finished" marks
+    u32 epoch = lc.ks_epoch;
+    u32 *ticket = lc.ks_ticket;
+    u64 *mail = lc.ks_mail;
+    void *params[] = {&args, &lt, &gc, &batch_arg, &flags, &done, &epoch, &ticket, &mail};
+    e = cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)G), dim3(NT), params, smem, st);
+    lc.ks_epoch += (u32)(batch + 1);
+    return e;
+}
+
+// hoisted rotations with grouped hybrid keys, step 1: U [batch][dnum][L][N]
+cudaError_t launch_hoist_grouped(LaunchCtx &lc, const u64 *ct, u64 *U, const GroupConsts &G, size_t batch, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    if (G.Lq + G.K != lc.L) return cudaErrorInvalidValue;
+    HoistGArgs A;
+    A.ct = ct; A.U = U; A.scratch = lc.ks_scratch; A.tw = lc.tw; A.itw = lc.itw;
+    switch (lc.log_n) {
+        case 12: return launch_hoistg_t<12>(lc, A, G, batch, st);
+        case 13: return launch_hoistg_t<13>(lc, A, G, batch, st);
+        case 14: return launch_hoistg_t<14>(lc, A, G, batch, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// step 2: acc [batch][2][L][N] of one rotation (key companions built here into lc.ks_key_s unless the caller supplies them)
+cudaError_t launch_rot_apply_grouped(LaunchCtx &lc, const u64 *ct, const u64 *U, const u64 *key, const u64 *key_s, u32 galois, u64 *acc,
+                                     const MsConsts &K, const GroupConsts &G, size_t batch, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    if (!key_s) {
+        const size_t n = (size_t)2 * G.dnum * lc.L << lc.log_n;
+        const unsigned grid = ew_grid(lc, n);
+        if (lc.log_n == 12) key_prepare_kernel<12><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        else if (lc.log_n == 13) key_prepare_kernel<13><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        else key_prepare_kernel<14><<<grid, 256, 0, st>>>(key, lc.ks_key_s, lc.lp, lc.L, n);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        key_s = lc.ks_key_s;
+    }
+    RotApplyGArgs A;
+    A.ct = ct; A.U = U; A.key = key; A.key_s = key_s; A.acc = acc; A.galois = galois;
+    constexpr size_t cb = 2;
+    const size_t rows = ((batch + cb - 1) / cb) * lc.L, want = (size_t)lc.num_sms * 12;
+    u32 nseg = 1;
+    const u32 max_seg = (1u << (lc.log_n - 1)) / 256;
+    while (nseg < max_seg && rows * nseg < want) nseg *= 2;
+    const size_t n_items = rows * nseg, cap = (size_t)lc.num_sms * 8;
+    const unsigned grid = (unsigned)(n_items < cap ? n_items : cap);
+    switch (lc.log_n) {
+        case 12: rot_apply_grouped_kernel<12, 256, 3, 2><<<grid, 256, 0, st>>>(A, lc.lt, K, G, batch, nseg); break;
+        case 13: rot_apply_grouped_kernel<13, 256, 3, 2><<<grid, 256, 0, st>>>(A, lc.lt, K, G, batch, nseg); break;
+        case 14: rot_apply_grouped_kernel<14, 256, 3, 2><<<grid, 256, 0, st>>>(A, lc.lt, K, G, batch, nseg); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
 }
 
 // per-rotation constants: Shoup companions of the key (lc.ks_key_s), M = NTT(negmask_g) (in `M`, [L][N]) and kprime [2][L][N]

@@ -322,6 +322,15 @@ class Context:
         self._chk(self._l.dpfhe_rotate_grouped(self._h, int(n_special), _ptr(ct), int(galois_elt), _ptr(gk), _ptr(out), batch, int(t_plain),
                                                _stream(stream)))
 
+    def rotate_hoisted_grouped(self, n_special, ct, galois_elts, gks, out, batch, t_plain=0, stream=None):
+        """out[r] = a rotation of ct by galois_elts[r] with the grouped hybrid key gks[r], all rotations sharing the mod-up of ct (same
+        plaintexts as rotate_grouped, not the same bits); gks: list of device tensors, out: [n_rot][batch][2][L-n_special][N]"""
+        n = len(galois_elts)
+        assert len(gks) == n
+        ge = (C.c_uint64 * n)(*[int(g) for g in galois_elts])
+        kp = (C.c_void_p * n)(*[_ptr(k) for k in gks])
+        self._chk(self._l.dpfhe_rotate_hoisted_grouped(self._h, int(n_special), _ptr(ct), n, ge, kp, _ptr(out), batch, int(t_plain), _stream(stream)))
+
     def mod_down_special(self, n_special, polys, out, n_polys, t_plain=0, stream=None):
         self._chk(self._l.dpfhe_mod_down_special(self._h, int(n_special), _ptr(polys), _ptr(out), n_polys, int(t_plain), _stream(stream)))
 

@@ -202,6 +202,14 @@ int dpfhe_ct_mul_relin_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_
                                const uint64_t *d_evk, uint64_t *d_out, size_t batch, uint64_t t_plain, void *stream);
 int dpfhe_rotate_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_ct, uint64_t galois_elt, const uint64_t *d_gk,
                          uint64_t *d_out, size_t batch, uint64_t t_plain, void *stream);
+/* n_rot rotations of the SAME ciphertexts with grouped hybrid keys (d_gks[r]: [dnum][2][L][N], Galois key of galois_elts[r]),
+ * sharing the basis conversion and the forward transforms of c1 ("hoisting"): one mod-up per ciphertext,
+ * then per rotation only multiply-accumulates over the L limbs and the division by P (2K + 2Lq transforms instead of all of
+ * them).  d_out: [n_rot][batch][2][L-K][N].  A rotation permutes the lifted digits instead of lifting the permuted digits:
+ * the results decrypt to the same plaintexts with the same noise bound as dpfhe_rotate_grouped but are not the same bits
+ *.  Works for n_special = 1 (hybrid keys) as well. */
+int dpfhe_rotate_hoisted_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_ct, size_t n_rot, const uint64_t *galois_elts,
+                                 const uint64_t *const *d_gks, uint64_t *d_out, size_t batch, uint64_t t_plain, void *stream);
 /* division by the product of the last n_special limbs alone (the mod-down half of the calls above; n_special = 1 is
  * dpfhe_mod_switch_down): in [n_polys][L][N] -> out [n_polys][L - n_special][N], 1 <= n_special <= 4, n_special < L */
 int dpfhe_mod_down_special(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_in, uint64_t *d_out, size_t n_polys,

@@ -64,6 +64,7 @@ def lib():
         "dpo_keyswitch_grouped": (None, [vp, C.c_uint, u64p, u64p, u64, u64p, u64p]),
         "dpo_ct_mul_relin_grouped": (None, [vp, C.c_uint, u64p, u64p, u64p, u64, u64p, sz]),
         "dpo_rotate_grouped": (None, [vp, C.c_uint, u64p, u64, u64p, u64, u64p, sz]),
+        "dpo_rotate_hoisted_grouped": (None, [vp, C.c_uint, u64p, sz, u64p, u64p, u64, u64p, sz]),
         "dpo_keygen_relin_grouped": (None, [vp, C.c_uint, u64, u64, u64p, u64p]),
         "dpo_keygen_galois_grouped": (None, [vp, C.c_uint, u64, u64, u64p, u64, u64p]),
         "dpo_keygen_relin_hybrid": (None, [vp, u64, u64, u64p, u64p]),
@@ -264,6 +265,16 @@ class Oracle:
         out = np.empty_like(ct)
         self._l.dpo_rotate_grouped(self._c, int(K), ct.reshape(-1), int(galois_elt), np.ascontiguousarray(gk).reshape(-1), int(t_plain),
                                    out.reshape(-1), ct.size // (2 * (self.L - K) * self.N))
+        return out
+
+    def rotate_hoisted_grouped(self, K, ct, galois, gks, t_plain=0):
+        """ct [batch][2][L-K][N], gks [n_rot][dnum][2][L][N] -> [n_rot][batch][2][L-K][N]"""
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        g = np.ascontiguousarray(galois, dtype=np.uint64)
+        batch = ct.size // (2 * (self.L - K) * self.N)
+        out = np.empty((len(g), batch) + ct.shape[-3:], dtype=np.uint64)
+        self._l.dpo_rotate_hoisted_grouped(self._c, int(K), ct.reshape(-1), len(g), g, np.ascontiguousarray(gks, dtype=np.uint64).reshape(-1),
+                                           int(t_plain), out.reshape(-1), batch)
         return out
 
     def keygen_relin_grouped(self, K, seed, t, s):

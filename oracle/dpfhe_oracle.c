@@ -656,12 +656,12 @@ void dpo_mod_down_special(const dpo_ctx *c, unsigned K, const uint64_t *in, uint
 
 unsigned dpo_grouped_digits(const dpo_ctx *c, unsigned K) { return K >= 1 && K < c->L ? (c->L - K + K - 1) / K : 0; }
 
-/* d: [Lq][N]; key: [dnum][2][L][N]; c0, c1: [Lq][N] */
-void dpo_keyswitch_grouped(const dpo_ctx *c, unsigned K, const uint64_t *d, const uint64_t *key, uint64_t t_plain, uint64_t *c0, uint64_t *c1) {
-    const size_t N = c->N, PK = c->L * N;
+/* mod-up of one polynomial d [Lq][N]: U [dnum][L][N], U[g][i] = the lift of digit g in limb i, evaluation form (d[i] itself for
+ * the limbs of the digit) */
+static void grouped_mod_up(const dpo_ctx *c, unsigned K, const uint64_t *d, uint64_t *U) {
+    const size_t N = c->N;
     const unsigned L = c->L, Lq = L - K, dnum = dpo_grouped_digits(c, K);
-    uint64_t *y = (uint64_t *)malloc((size_t)K * N * 8), *u = (uint64_t *)malloc(N * 8);
-    uint64_t *acc = (uint64_t *)calloc(2 * PK, 8), *low = (uint64_t *)malloc(2 * (size_t)Lq * N * 8);
+    uint64_t *y = (uint64_t *)malloc((size_t)K * N * 8);
     for (unsigned g = 0; g < dnum; g++) {
         const unsigned lo = g * K, hi = lo + K < Lq ? lo + K : Lq;
         for (unsigned j = lo; j < hi; j++) {
@@ -672,31 +672,54 @@ void dpo_keyswitch_grouped(const dpo_ctx *c, unsigned K, const uint64_t *d, cons
             for (size_t n = 0; n < N; n++) yj[n] = mulmod(yj[n], f, qj);
         }
         for (unsigned i = 0; i < L; i++) {
-            const uint64_t q = c->q[i], r0 = c->br0[i], r1 = c->br1[i];
-            const uint64_t *src;
-            if (i >= lo && i < hi) src = d + (size_t)i * N;
-            else {
-                for (size_t n = 0; n < N; n++) u[n] = 0;
-                for (unsigned j = lo; j < hi; j++) {
-                    const uint64_t qh = prod_mod(c, lo, hi, j, q);
-                    const uint64_t *yj = y + (size_t)(j - lo) * N;
-                    for (size_t n = 0; n < N; n++) u[n] = addmod(u[n], mulmod(yj[n] % q, qh, q), q);
-                }
-                ntt_fwd_limb(c, i, u);
-                src = u;
+            const uint64_t q = c->q[i];
+            uint64_t *u = U + ((size_t)g * L + i) * N;
+            if (i >= lo && i < hi) {
+                memcpy(u, d + (size_t)i * N, N * 8);
+                continue;
             }
+            for (size_t n = 0; n < N; n++) u[n] = 0;
+            for (unsigned j = lo; j < hi; j++) {
+                const uint64_t qh = prod_mod(c, lo, hi, j, q);
+                const uint64_t *yj = y + (size_t)(j - lo) * N;
+                for (size_t n = 0; n < N; n++) u[n] = addmod(u[n], mulmod(yj[n] % q, qh, q), q);
+            }
+            ntt_fwd_limb(c, i, u);
+        }
+    }
+    free(y);
+}
+
+/* acc [2][L][N] = sum_g U[g][.][perm] o key[g]  (perm == NULL: identity), then the division by P: c0, c1 [Lq][N] */
+static void grouped_mac_and_down(const dpo_ctx *c, unsigned K, const uint64_t *U, const uint32_t *perm, const uint64_t *key, uint64_t t_plain,
+                                 uint64_t *c0, uint64_t *c1) {
+    const size_t N = c->N, PK = c->L * N;
+    const unsigned L = c->L, Lq = L - K, dnum = dpo_grouped_digits(c, K);
+    uint64_t *acc = (uint64_t *)calloc(2 * PK, 8), *low = (uint64_t *)malloc(2 * (size_t)Lq * N * 8);
+    for (unsigned g = 0; g < dnum; g++)
+        for (unsigned i = 0; i < L; i++) {
+            const uint64_t q = c->q[i], r0 = c->br0[i], r1 = c->br1[i];
+            const uint64_t *src = U + ((size_t)g * L + i) * N;
             const uint64_t *kb = key + ((size_t)g * 2 + 0) * PK + i * N;
             const uint64_t *ka = key + ((size_t)g * 2 + 1) * PK + i * N;
             for (size_t n = 0; n < N; n++) {
-                acc[i * N + n] = addmod(acc[i * N + n], barrett_mul(src[n], kb[n], q, r0, r1), q);
-                acc[PK + i * N + n] = addmod(acc[PK + i * N + n], barrett_mul(src[n], ka[n], q, r0, r1), q);
+                const uint64_t u = src[perm ? perm[n] : n];
+                acc[i * N + n] = addmod(acc[i * N + n], barrett_mul(u, kb[n], q, r0, r1), q);
+                acc[PK + i * N + n] = addmod(acc[PK + i * N + n], barrett_mul(u, ka[n], q, r0, r1), q);
             }
         }
-    }
     dpo_mod_down_special(c, K, acc, t_plain, low, 2);
     memcpy(c0, low, (size_t)Lq * N * 8);
     memcpy(c1, low + (size_t)Lq * N, (size_t)Lq * N * 8);
-    free(y); free(u); free(acc); free(low);
+    free(acc); free(low);
+}
+
+/* d: [Lq][N]; key: [dnum][2][L][N]; c0, c1: [Lq][N] */
+void dpo_keyswitch_grouped(const dpo_ctx *c, unsigned K, const uint64_t *d, const uint64_t *key, uint64_t t_plain, uint64_t *c0, uint64_t *c1) {
+    uint64_t *U = (uint64_t *)malloc((size_t)dpo_grouped_digits(c, K) * c->L * c->N * 8);
+    grouped_mod_up(c, K, d, U);
+    grouped_mac_and_down(c, K, U, NULL, key, t_plain, c0, c1);
+    free(U);
 }
 
 /* a, b, out: [batch][2][Lq][N]; evk: [dnum][2][L][N] */
@@ -745,6 +768,41 @@ void dpo_rotate_grouped(const dpo_ctx *c, unsigned K, const uint64_t *ct, uint64
                 dst[P + o] = k[P + o];
             }
         free(p); free(k);
+    }
+    free(perm);
+}
+
+/* Hoisted rotations with grouped hybrid keys: n_rot rotations of the same ciphertexts share the mod-up of the
+ * UNPERMUTED c1; rotation r applies its permutation to the lifted digits:
+ *     acc_c[i] = sum_g perm_r(U[g][i]) o gk_r[g][c][i],   out_r = (perm_r(c0) + ks0, ks1),  (ks0, ks1) = acc / P.
+ * perm_r(U[g]) is the residue vector of sigma_r(lift of digit g) - a lift of the rotated digit of the same size, but not the
+ * canonical one dpo_rotate_grouped would build - so the result encrypts the same plaintext with the same noise bound, and is
+ * NOT bit-identical to dpo_rotate_grouped.
+ * ct: [batch][2][Lq][N]; gks: [n_rot][dnum][2][L][N]; out: [n_rot][batch][2][Lq][N] */
+void dpo_rotate_hoisted_grouped(const dpo_ctx *c, unsigned K, const uint64_t *ct, size_t n_rot, const uint64_t *galois, const uint64_t *gks,
+                                uint64_t t_plain, uint64_t *out, size_t batch) {
+    if (K < 1 || K >= c->L) return;
+    const unsigned L = c->L, Lq = L - K, dnum = dpo_grouped_digits(c, K);
+    const size_t N = c->N, P = (size_t)Lq * N, key_words = (size_t)dnum * 2 * L * N;
+    uint32_t *perm = (uint32_t *)malloc(n_rot * N * 4);
+    for (size_t r = 0; r < n_rot; r++) dpo_galois_perm(c, galois[r], perm + r * N);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long b = 0; b < (long)batch; b++) {
+        const uint64_t *src = ct + 2 * P * b;
+        uint64_t *U = (uint64_t *)malloc((size_t)dnum * L * N * 8), *k = (uint64_t *)malloc(2 * P * 8);
+        grouped_mod_up(c, K, src + P, U);
+        for (size_t r = 0; r < n_rot; r++) {
+            const uint32_t *pr = perm + r * N;
+            uint64_t *dst = out + (r * batch + (size_t)b) * 2 * P;
+            grouped_mac_and_down(c, K, U, pr, gks + r * key_words, t_plain, k, k + P);
+            for (unsigned l = 0; l < Lq; l++)
+                for (size_t n = 0; n < N; n++) {
+                    size_t o = l * N + n;
+                    dst[o] = addmod(src[l * N + pr[n]], k[o], c->q[l]);
+                    dst[P + o] = k[P + o];
+                }
+        }
+        free(U); free(k);
     }
     free(perm);
 }

@@ -104,6 +104,10 @@ void dpo_ct_mul_relin_grouped(const dpo_ctx *, unsigned K, const uint64_t *a, co
                               uint64_t *out, size_t batch);
 void dpo_rotate_grouped(const dpo_ctx *, unsigned K, const uint64_t *ct, uint64_t galois_elt, const uint64_t *gk, uint64_t t_plain,
                         uint64_t *out, size_t batch);
+/* n_rot rotations of the same ciphertexts sharing the mod-up (hoisting); same plaintexts as dpo_rotate_grouped, not the same bits.
+ * gks [n_rot][dnum][2][L][N], out [n_rot][batch][2][L-K][N] */
+void dpo_rotate_hoisted_grouped(const dpo_ctx *, unsigned K, const uint64_t *ct, size_t n_rot, const uint64_t *galois, const uint64_t *gks,
+                                uint64_t t_plain, uint64_t *out, size_t batch);
 /* permutation table of sigma_g in evaluation form: out[i] = in[perm[i]] */
 void dpo_galois_perm(const dpo_ctx *, uint64_t galois_elt, uint32_t *perm);
 /* sigma_g in coefficient form on one limb: out(X) = in(X^g) */

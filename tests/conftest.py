@@ -130,6 +130,15 @@ class Emu:
         assert self._l.emu_mod_down_special(self._h, int(K), x.reshape(-1), out.reshape(-1), x.shape[0], int(t_plain)) == 0
         return out
 
+    def rotate_hoisted_grouped(self, K, ct, galois, keys, t_plain=0):
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        g = np.ascontiguousarray(galois, dtype=np.uint64)
+        batch = ct.size // (2 * (self.L - K) * self.N)
+        out = np.zeros((len(g), batch, 2, self.L - K, self.N), dtype=np.uint64)
+        assert self._l.emu_rotate_hoisted_grouped(self._h, int(K), ct.reshape(-1), len(g), g, np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1),
+                                                  out.reshape(-1), batch, int(t_plain)) == 0
+        return out
+
     def scalar(self, name, l, *args):
         return int(getattr(self._l, "emu_" + name)(self._h, l, *[C.c_uint64(int(a)) for a in args]))
 
@@ -162,6 +171,7 @@ def _build_emu(variant):
     lib.emu_rotate_hoisted.argtypes = [C.c_void_p, _u64p, C.c_size_t, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint, C.POINTER(C.c_uint)]
     lib.emu_pt_inner.argtypes = [C.c_void_p, _u64p, C.c_uint, _u64p, C.c_uint, _u64p, C.c_size_t, C.c_uint]
     lib.emu_mod_down_special.argtypes = [C.c_void_p, C.c_uint, _u64p, _u64p, C.c_size_t, C.c_uint64]
+    lib.emu_rotate_hoisted_grouped.argtypes = [C.c_void_p, C.c_uint, _u64p, C.c_size_t, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint64]
     lib.emu_mod_switch.argtypes = [C.c_void_p, _u64p, _u64p, C.c_size_t, C.c_uint64]
     for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2), ("barrett_long", 2), ("pti_fold", 4),
                       ("shoup_lazy", 2), ("shoup_exact", 2)):

@@ -261,6 +261,52 @@ void run_ks_grouped(Emu &e, unsigned Ks, const uint64_t *a, const uint64_t *b, c
     free(key_s);
 }
 
+// hoisted rotations with grouped hybrid keys: hoistg_phase1/2 in the role order of ks_hoistg_kernel, then per rotation the rows of
+// rot_apply_grouped_kernel and the division by P (md_tau / md_limb bodies)
+template <int LOGN, int NT, int NT_MD>
+void run_rotate_hoisted_grouped(Emu &e, unsigned Ks, const uint64_t *ct, size_t n_rot, const uint64_t *galois, const uint64_t *keys, uint64_t *out,
+                                size_t batch, uint64_t t_plain) {
+    const size_t N = (size_t)1 << LOGN;
+    const unsigned L = e.hp.L, Lq = L - Ks;
+    MsConsts K;
+    GroupConsts G;
+    build_group_consts(e.hp, Ks, t_plain, G, K);
+    const unsigned dnum = G.dnum;
+    const size_t P = (size_t)L * N, Pq = (size_t)Lq * N, key_words = (size_t)2 * dnum * L * N;
+    uint64_t *buf = aligned_new<uint64_t>(N), *scratch = aligned_new<uint64_t>((size_t)L * 2 * N);
+    uint64_t *U = aligned_new<uint64_t>(batch * dnum * L * N), *acc = aligned_new<uint64_t>(batch * 2 * P), *tau = aligned_new<uint64_t>((size_t)Ks * N);
+    uint64_t *key_s = aligned_new<uint64_t>(key_words);
+    HoistGArgs H;
+    H.ct = ct; H.U = U; H.scratch = scratch; H.tw = e.tw; H.itw = e.itw;
+    HostCta cta{NT}, cta_md{NT_MD};
+    for (size_t c = 0; c < batch; ++c) {
+        const unsigned par = (unsigned)(c & 1);
+        const uint64_t *t_rows = scratch + (size_t)par * N;
+        for (unsigned i = 0; i < Lq; ++i) hoistg_phase1<LOGN, NT>(cta, buf, H, G, c, i, scratch + ((size_t)i * 2 + par) * N);
+        for (unsigned i = 0; i < L; ++i)
+            for (unsigned g = 0; g < dnum; ++g)
+                if (i >= Lq || i / Ks != g) hoistg_phase2<LOGN, NT>(cta, buf, H, G, e.lp[i], c, i, g, t_rows, 2 * N);
+    }
+    for (size_t r = 0; r < n_rot; ++r) {
+        const uint64_t *key = keys + r * key_words;
+        for (size_t k = 0; k < key_words; ++k) key_s[k] = (uint64_t)((((unsigned __int128)key[k]) << 64) / e.lp[(k / N) % L].q);
+        RotApplyGArgs A;
+        A.ct = ct; A.U = U; A.key = key; A.key_s = key_s; A.acc = acc; A.galois = (uint32_t)galois[r];
+        for (size_t c0 = 0; c0 < batch; c0 += 2)
+            for (unsigned i = 0; i < L; ++i)
+                rot_apply_grouped_rows<LOGN, NT, 2>(cta, A, G, K, e.lp[i], c0, (uint32_t)(batch - c0 < 2 ? batch - c0 : 2), i);
+        for (size_t w = 0; w < 2 * batch; ++w) {   // the division by P, one polynomial at a time
+            for (unsigned k = 0; k < Ks; ++k)
+                ms_tau_body<LOGN, NT_MD>(cta_md, buf, acc + (w * L + Lq + k) * N, nullptr, e.itw + (size_t)(Lq + k) * N, G.lp_up[Lq + k], tau + (size_t)k * N, K);
+            for (unsigned i = 0; i < Lq; ++i)
+                ms_limb_group<LOGN, NT_MD, false>(cta_md, buf, tau, N, acc + (w * L + i) * N, out + ((r * batch * 2 + w) * Lq + i) * N, e.tw + (size_t)i * N,
+                                               e.lp[i], K, G, i);
+        }
+    }
+    (void)Pq;
+    free(buf); free(scratch); free(U); free(acc); free(tau); free(key_s);
+}
+
 // hoisted rotations: the device bodies (hoist_phase1/2, rot_apply_row) in kernel order, the per-rotation constants
 // computed the way launch_rot_prepare does (negmask -> NTT -> kprime), flagged ciphertexts through the ordinary rotate
 template <int LOGN, int NT>
@@ -440,6 +486,18 @@ int emu_ks_grouped(void *h, unsigned K, int mode, const uint64_t *a, const uint6
         case 12: DISPATCH_G(12, 256)
         case 13: DISPATCH_G(13, 256)
         case 14: DISPATCH_G(14, 256)
+    }
+    return -1;
+}
+
+int emu_rotate_hoisted_grouped(void *h, unsigned K, const uint64_t *ct, size_t n_rot, const uint64_t *galois, const uint64_t *keys, uint64_t *out,
+                               size_t batch, uint64_t t_plain) {
+    Emu *e = (Emu *)h;
+    if (K < 1 || K > (unsigned)KS_MAX_SPECIAL || 2 * K > e->hp.L) return -1;
+    switch (e->hp.log_n) {
+        case 12: run_rotate_hoisted_grouped<12, 256, 256>(*e, K, ct, n_rot, galois, keys, out, batch, t_plain); return 0;
+        case 13: run_rotate_hoisted_grouped<13, 256, 256>(*e, K, ct, n_rot, galois, keys, out, batch, t_plain); return 0;
+        case 14: run_rotate_hoisted_grouped<14, 256, 512>(*e, K, ct, n_rot, galois, keys, out, batch, t_plain); return 0;
     }
     return -1;
 }

@@ -122,6 +122,52 @@ def test_mod_down_special(ctxs, log_n, L, K, t):
         assert np.array_equal(host(out).reshape(exp.shape), exp)
 
 
+@pytest.mark.parametrize("log_n,L,K,batch,t", [(12, 6, 2, 5, 65537), (13, 6, 2, 37, 0), (13, 4, 1, 3, 65537), (14, 4, 2, 2, 65537), (12, 9, 3, 2, 65537),
+                                               (12, 8, 4, 3, 65537)])
+def test_rotate_hoisted_grouped(ctxs, log_n, L, K, batch, t, monkeypatch):
+    """rotations sharing the mod-up (ks_hoistg_kernel, rot_apply_grouped_kernel, md kernels) against the oracle's hoisted definition;
+    the small scratch cap makes the large batch run in several chunks"""
+    c, o = ctxs(log_n, L)
+    if batch > 16:
+        monkeypatch.setenv("DPFHE_HOIST_CAP_MB", "16")
+    ct, _ = grouped_inputs(o, K, batch, 51)
+    galois = [o.galois_elt(1), o.galois_elt(-2), 2 * o.N - 1]
+    dnum = o.grouped_digits(K)
+    keys = [o.fill_uniform(60 + r, 2 * dnum).reshape(dnum, 2, L, o.N) for r in range(len(galois))]
+    out = torch.full((len(galois), batch, 2, L - K, o.N), -1, dtype=torch.int64, device="cuda")
+    dkeys = [dev(k) for k in keys]
+    c.rotate_hoisted_grouped(K, dev(ct), galois, dkeys, out, batch, t)
+    exp = o.rotate_hoisted_grouped(K, ct, galois, np.stack(keys), t)
+    assert np.array_equal(host(out).reshape(exp.shape), exp)
+    c.rotate_hoisted_grouped(K, dev(ct), galois, dkeys, out, batch, t)      # a second call: epochs, flags and round marks carry over
+    assert np.array_equal(host(out).reshape(exp.shape), exp)
+
+
+def test_rotate_hoisted_grouped_semantics(ctxs, oracle_mod):
+    """the GPU's hoisted rotations decrypt to the rotated messages"""
+    L, K = 6, 2
+    c, o = ctxs(12, L)
+    Lq = L - K
+    oq = oracle_mod.Oracle(12, Lq, o.moduli[:Lq])
+    t = 65537
+    rng = np.random.default_rng(11)
+    s = o.keygen_secret(71)
+    sq = np.ascontiguousarray(s[:Lq])
+    m = rng.integers(0, t, o.N).astype(np.uint64)
+    ct = oq.encrypt(72, t, sq, m)
+    galois = [o.galois_elt(1), o.galois_elt(5)]
+    gks = [dev(o.keygen_galois_grouped(K, 80 + r, t, s, g)) for r, g in enumerate(galois)]
+    out = torch.zeros((2, 1, 2, Lq, o.N), dtype=torch.int64, device="cuda")
+    c.rotate_hoisted_grouped(K, dev(ct[None]), galois, gks, out, 1, t)
+    got = host(out).reshape(2, 2, Lq, o.N)
+    for r, g in enumerate(galois):
+        exp = np.zeros(o.N, dtype=np.uint64)
+        for k in range(o.N):
+            e = (k * g) % (2 * o.N)
+            exp[e % o.N] = m[k] if e < o.N else (t - m[k]) % t
+        assert np.array_equal(oq.decrypt(sq, got[r].copy(), t), exp)
+
+
 def test_grouped_errors(ctxs):
     c, o = ctxs(12, 4)
     x = torch.zeros((1, 2, 2, o.N), dtype=torch.int64, device="cuda")

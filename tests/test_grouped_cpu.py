@@ -97,3 +97,40 @@ def test_semantics_and_noise(oracle_mod, L, K):
         e = (k * g) % (2 * o.N)
         exp[e % o.N] = m1[k] if e < o.N else (t - m1[k]) % t
     assert np.array_equal(oq.decrypt(sq, rot, t), exp)
+
+
+@pytest.mark.parametrize("L,K", [(6, 2), (4, 1)])
+def test_hoisted_rotations_decrypt_to_the_rotated_message(oracle_mod, L, K):
+    """hoisting shares the mod-up of the unpermuted c1: not the bits of rotate_grouped, but the same plaintext and noise level"""
+    o = oracle_mod.Oracle(11, L)
+    Lq = L - K
+    oq = oracle_mod.Oracle(11, Lq, o.moduli[:Lq])
+    t = 65537
+    rng = np.random.default_rng(5)
+    s = o.keygen_secret(71)
+    sq = np.ascontiguousarray(s[:Lq])
+    msgs = [rng.integers(0, t, o.N).astype(np.uint64) for _ in range(2)]
+    cts = np.stack([oq.encrypt(72 + k, t, sq, m) for k, m in enumerate(msgs)])
+    galois = [o.galois_elt(1), o.galois_elt(-3), 2 * o.N - 1]
+    gks = np.stack([o.keygen_galois_grouped(K, 80 + r, t, s, g) for r, g in enumerate(galois)])
+    out = o.rotate_hoisted_grouped(K, cts, galois, gks, t)
+    assert out.shape == (3, 2, 2, Lq, o.N)
+
+    def noise_bits(ct):
+        ph = oq.phase(sq, ct)
+        worst = 0
+        for n in range(0, o.N, 61):
+            v, Q = crt(oq, ph, n, range(Lq))
+            worst = max(worst, min(v, Q - v))
+        return worst.bit_length()
+
+    for r, g in enumerate(galois):
+        plain = o.rotate_grouped(K, cts, g, gks[r], t)
+        for b, m in enumerate(msgs):
+            exp = np.zeros(o.N, dtype=np.uint64)
+            for k in range(o.N):
+                e = (k * g) % (2 * o.N)
+                exp[e % o.N] = m[k] if e < o.N else (t - m[k]) % t
+            assert np.array_equal(oq.decrypt(sq, out[r, b], t), exp)
+            assert abs(noise_bits(out[r, b]) - noise_bits(plain[b])) <= 2
+        assert not np.array_equal(out[r], plain)      # a different lift of the rotated digits: different bits, same plaintext

@@ -227,6 +227,17 @@ def test_emulated_grouped_keyswitch_bodies(make_emu, oracle_mod, log_n, L, K, ba
         assert np.array_equal(e.ks_grouped(1, 0, a, b, key, batch, t_plain=t, G=G), e.ks_hybrid(0, a, b, key, batch, t_plain=t, G=G))
 
 
+@pytest.mark.parametrize("log_n,L,K,batch,t", [(12, 6, 2, 3, 65537), (12, 5, 2, 2, 0), (13, 4, 1, 2, 65537), (14, 4, 2, 1, 65537), (12, 9, 3, 2, 65537)])
+def test_emulated_hoisted_grouped_rotations(make_emu, oracle_mod, log_n, L, K, batch, t):
+    """hoisting with grouped hybrid keys: hoistg bodies, rot_apply_grouped rows and the division by P against the oracle"""
+    e, o = make_emu(log_n, L), oracle_mod.Oracle(log_n, L)
+    ct, _ = _grouped_inputs(o, K, batch, 51)
+    galois = [o.galois_elt(1), o.galois_elt(-2), 2 * o.N - 1]
+    dnum = o.grouped_digits(K)
+    keys = np.stack([o.fill_uniform(60 + r, 2 * dnum).reshape(dnum, 2, L, o.N) for r in range(len(galois))])
+    assert np.array_equal(e.rotate_hoisted_grouped(K, ct, galois, keys, t), o.rotate_hoisted_grouped(K, ct, galois, keys, t))
+
+
 @pytest.mark.parametrize("log_n,L", [(12, 3), (13, 4), (14, 2)])
 def test_generic_variant_on_the_default_basis(make_emu, oracle_mod, log_n, L):
     """the generic kernels must also be right for k * 2^32 + 1 moduli (DPFHE_FORCE_GENERIC runs them on the default basis)"""

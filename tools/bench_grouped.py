@@ -36,4 +36,39 @@ for K in (1, 2, 4):
     res["K=%d" % K] = {"context_limbs": L, "digits": dn, "key_MiB": dn * 2 * L * N * 8 / 2**20, "ms_per_step": ms, "ct_mult_per_s": BATCH / ms * 1e3,
                        "transforms_per_ct": LQ + dn * L - LQ + 2 * K + 2 * LQ}
     c.close()
+# rotation sweep (26 rotations of one batch, as BASELINE.json config 3 does with per-limb digits): independent rotations against hoisting
+sweep = {}
+RB = int(os.environ.get("ROT_BATCH", "512"))
+for K in (1, 2):
+    L = LQ + K
+    c = dp.Context(LOG_N, L)
+    dn = c.grouped_digits(K)
+    cq = dp.Context(LOG_N, LQ, c.moduli[:LQ])
+    a = torch.empty((RB, 2, LQ, N), dtype=torch.int64, device="cuda")
+    cq.fill_uniform(1, a, 2 * RB)
+    cq.close()
+    steps = [s for s in range(1, 14)] + [-s for s in range(1, 14)]
+    galois = [c.galois_elt(s) for s in steps]
+    keys = []
+    for r in range(len(steps)):
+        k = torch.empty((dn, 2, L, N), dtype=torch.int64, device="cuda"); c.fill_uniform(100 + r, k, 2 * dn); keys.append(k)
+    out = torch.empty((len(steps), RB, 2, LQ, N), dtype=torch.int64, device="cuda")
+    def indep():
+        for r, g in enumerate(galois):
+            c.rotate_grouped(K, a, g, keys[r], out[r], RB, 65537)
+    def hoisted():
+        c.rotate_hoisted_grouped(K, a, galois, keys, out, RB, 65537)
+    row = {}
+    for name, fn in (("independent", indep), ("hoisted", hoisted)):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        row[name] = {"ms_per_sweep": ms, "rotations_per_s": len(steps) * RB / ms * 1e3}
+    sweep["K=%d" % K] = row
+    c.close()
+res["rotation_sweep_26x%d" % RB] = sweep
 print(json.dumps({"workload": "ct x ct + relinearise with special primes, N=8192, 4 ciphertext limbs, batch=%d, t=65537" % BATCH, "results": res}))

@@ -61,6 +61,10 @@ for L, K in ((6, 2), (5, 2)):
     gk = torch.empty((dn, 2, L, N), dtype=torch.int64, device="cuda"); c.fill_uniform(13, gk, 2 * dn)
     c.ct_mul_relin_grouped(K, ga, gb, gk, go, B, 65537); c.ct_mul_relin_grouped(K, ga, gb, gk, go, B, 65537)
     c.rotate_grouped(K, ga, 5, gk, go, B, 0)
+    ho = torch.empty((2, B, 2, Lq, N), dtype=torch.int64, device="cuda")
+    c.rotate_hoisted_grouped(K, ga, [c.galois_elt(1), c.galois_elt(-2)], [gk, gk], ho, B, 65537)
+    md = torch.empty((2 * B, Lq, N), dtype=torch.int64, device="cuda"); full = torch.empty((2 * B, L, N), dtype=torch.int64, device="cuda")
+    c.fill_uniform(14, full, 2 * B); c.mod_down_special(K, full, md, 2 * B, 65537)
     torch.cuda.synchronize()
     c.close()
 m = dp.MultiContext(12, 2, devices=[0, 0])
