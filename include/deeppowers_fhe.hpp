@@ -128,6 +128,16 @@ public:
                                std::size_t count, std::uint64_t plain_modulus = 0, void *stream = nullptr) {
         check(dpfhe_rotate_grouped(ctx_, special, ct, galois_element(steps), galois_key, out, count, plain_modulus, stream));
     }
+    // out[r] = ct rotated by steps[r] with galois_keys[r], the rotations sharing the basis conversion of ct (same plaintexts as
+    // rotate_grouped_device, not the same bits); out holds n_rot * count ciphertexts
+    void rotate_hoisted_grouped_device(unsigned special, const std::uint64_t *ct, const std::vector<long> &steps,
+                                       const std::vector<const std::uint64_t *> &galois_keys, std::uint64_t *out, std::size_t count,
+                                       std::uint64_t plain_modulus = 0, void *stream = nullptr) {
+        if (steps.size() != galois_keys.size()) throw std::invalid_argument("one Galois key per rotation");
+        std::vector<std::uint64_t> elts(steps.size());
+        for (std::size_t r = 0; r < steps.size(); ++r) elts[r] = galois_element(steps[r]);
+        check(dpfhe_rotate_hoisted_grouped(ctx_, special, ct, steps.size(), elts.data(), galois_keys.data(), out, count, plain_modulus, stream));
+    }
     // divide by the product of the last `special` limbs: in holds limbs() limbs per polynomial, out limbs()-special
     void mod_down_special_device(unsigned special, const std::uint64_t *ct, std::uint64_t *out, std::size_t count, std::uint64_t plain_modulus = 0,
                                  void *stream = nullptr) {

@@ -207,7 +207,8 @@ int dpfhe_rotate_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_c
  * then per rotation only multiply-accumulates over the L limbs and the division by P (2K + 2Lq transforms instead of all of
  * them).  d_out: [n_rot][batch][2][L-K][N].  A rotation permutes the lifted digits instead of lifting the permuted digits:
  * the results decrypt to the same plaintexts with the same noise bound as dpfhe_rotate_grouped but are not the same bits
- *.  Works for n_special = 1 (hybrid keys) as well. */
+ * (the parity tests check them against the oracle's restatement of exactly this definition).  Works for n_special = 1 (hybrid
+ * keys) as well. */
 int dpfhe_rotate_hoisted_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_ct, size_t n_rot, const uint64_t *galois_elts,
                                  const uint64_t *const *d_gks, uint64_t *d_out, size_t batch, uint64_t t_plain, void *stream);
 /* division by the product of the last n_special limbs alone (the mod-down half of the calls above; n_special = 1 is

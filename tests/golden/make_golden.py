@@ -23,7 +23,7 @@ def h(a):
 
 def main():
     out = {"params": {}, "cases": []}
-    for log_n, L in [(12, 1), (12, 3), (13, 4), (13, 5), (14, 8)]:
+    for log_n, L in [(12, 1), (12, 3), (13, 4), (13, 5), (13, 6), (14, 8)]:
         o = Oracle(log_n, L)
         out["params"]["%d,%d" % (log_n, L)] = {"moduli": [str(q) for q in o.moduli], "psi": [str(p) for p in o.psi]}
     # config 1 of BASELINE.json: single forward NTT, N=4096, one 60-bit modulus
@@ -71,6 +71,21 @@ def main():
                          "evk_sha256": h(hk), "out_sha256": h(hr), "out_head": [str(v) for v in hr.reshape(-1)[:8]]})
     out["cases"].append({"name": "rotate1_hybrid_n8192_l4p1", "log_n": 13, "L": 5, "seed": 0xD3390002, "t": 65537, "galois": int(g),
                          "gk_sha256": h(hgk), "out_sha256": h(hrot), "out_head": [str(v) for v in hrot.reshape(-1)[:8]]})
+    # grouped hybrid key switching: context (13, 6) = the same four ciphertext moduli + two special primes, digits of
+    # two limbs; the plain and the hoisted rotation (2.11b) are different bits by definition, both pinned
+    o6 = Oracle(13, 6)
+    assert o6.moduli[:4] == o.moduli
+    s6 = o6.keygen_secret(1)
+    gek = o6.keygen_relin_grouped(2, 2, 65537, s6)
+    ger = o6.ct_mul_relin_grouped(2, a, b, gek, 65537)
+    ggk = o6.keygen_galois_grouped(2, 3, 65537, s6, g)
+    grot = o6.rotate_grouped(2, a, g, ggk, 65537)
+    ghoist = o6.rotate_hoisted_grouped(2, a, [g], ggk[None], 65537)
+    out["cases"].append({"name": "ct_mul_relin_grouped_n8192_l4p2", "log_n": 13, "L": 6, "K": 2, "seed": 0xD3390002, "t": 65537,
+                         "evk_sha256": h(gek), "out_sha256": h(ger), "out_head": [str(v) for v in ger.reshape(-1)[:8]]})
+    out["cases"].append({"name": "rotate1_grouped_n8192_l4p2", "log_n": 13, "L": 6, "K": 2, "seed": 0xD3390002, "t": 65537, "galois": int(g),
+                         "gk_sha256": h(ggk), "out_sha256": h(grot), "hoisted_sha256": h(ghoist),
+                         "out_head": [str(v) for v in grot.reshape(-1)[:8]]})
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kat.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)

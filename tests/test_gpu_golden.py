@@ -99,6 +99,34 @@ def test_golden_mod_switch_and_hybrid(kat, oracle_mod):
     c5.close()
 
 
+def test_golden_grouped(kat, oracle_mod):
+    """digits of two limbs and two special primes against the committed hashes: ct x ct, rotate, and the hoisted rotate"""
+    import deeppowers_b200 as dp
+    mul = next(c for c in kat["cases"] if c["name"] == "ct_mul_relin_grouped_n8192_l4p2")
+    rot = next(c for c in kat["cases"] if c["name"] == "rotate1_grouped_n8192_l4p2")
+    c4, c6 = dp.Context(13, 4), dp.Context(13, 6)
+    assert [str(q) for q in c6.moduli] == kat["params"]["13,6"]["moduli"] and c6.moduli[:4] == c4.moduli
+    a = torch.empty((2, 2, 4, 8192), dtype=torch.int64, device="cuda")
+    b = torch.empty_like(a)
+    c4.fill_uniform(mul["seed"], a, 4, first_poly=0)
+    c4.fill_uniform(mul["seed"], b, 4, first_poly=4)
+    o6 = oracle_mod.Oracle(13, 6)
+    s6 = o6.keygen_secret(1)
+    evk = o6.keygen_relin_grouped(2, 2, mul["t"], s6)
+    gk = o6.keygen_galois_grouped(2, 3, rot["t"], s6, rot["galois"])
+    assert hashlib.sha256(evk.tobytes()).hexdigest() == mul["evk_sha256"]
+    assert hashlib.sha256(gk.tobytes()).hexdigest() == rot["gk_sha256"]
+    out = torch.zeros_like(a)
+    c6.ct_mul_relin_grouped(2, a, b, dev(evk), out, 2, mul["t"])
+    assert sha(out) == mul["out_sha256"]
+    c6.rotate_grouped(2, a, rot["galois"], dev(gk), out, 2, rot["t"])
+    assert sha(out) == rot["out_sha256"]
+    c6.rotate_hoisted_grouped(2, a, [rot["galois"]], [dev(gk)], out, 2, rot["t"])
+    assert sha(out) == rot["hoisted_sha256"]
+    c4.close()
+    c6.close()
+
+
 def test_shard_equality_on_one_gpu():
     """G-way sharded evaluation == 1-way evaluation, byte for byte (logical shards on one device)"""
     import deeppowers_b200 as dp

@@ -125,6 +125,21 @@ def test_golden_vectors(oracle_mod, kat):
             y = o.ntt_fwd(x)
             assert sha(y) == case["out_sha256"]
             assert [str(v) for v in y.reshape(-1)[:8]] == case["out_head"]
+        elif "grouped" in case["name"]:
+            o4 = oracle_mod.Oracle(13, 4)
+            K = case["K"]
+            s = o.keygen_secret(1)
+            a = o4.fill_uniform(case["seed"], 4).reshape(2, 2, 4, o.N)
+            b = o4.fill_uniform(case["seed"], 4, first_poly=4).reshape(2, 2, 4, o.N)
+            if "rotate" in case["name"]:
+                gk = o.keygen_galois_grouped(K, 3, case["t"], s, case["galois"])
+                assert sha(gk) == case["gk_sha256"]
+                assert sha(o.rotate_grouped(K, a, case["galois"], gk, case["t"])) == case["out_sha256"]
+                assert sha(o.rotate_hoisted_grouped(K, a, [case["galois"]], gk[None], case["t"])) == case["hoisted_sha256"]
+            else:
+                evk = o.keygen_relin_grouped(K, 2, case["t"], s)
+                assert sha(evk) == case["evk_sha256"]
+                assert sha(o.ct_mul_relin_grouped(K, a, b, evk, case["t"])) == case["out_sha256"]
         elif "hybrid" in case["name"]:
             o4 = oracle_mod.Oracle(13, 4)
             s = o.keygen_secret(1)
