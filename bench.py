@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the informational hybrid key-switching timing")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational timings (special-prime key switching, N=16384 transforms)")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -373,6 +373,17 @@ def main():
                                           "note": "4 ciphertext limbs + 1 special prime, BGV rounding t=65537 (DESIGN.md 2.10)"}}
         ctx5.close()
         del hkey
+        # the same ciphertexts with digits of two limbs and two special primes (24 transforms, a 1.5 MiB key)
+        ctx6 = dp.Context(LOG_N, L + 2, device=local_rank)
+        dn = ctx6.grouped_digits(2)
+        gkey = torch.empty((dn, 2, L + 2, N), dtype=torch.int64, device="cuda")
+        ctx6.fill_uniform(SEED + 4, gkey, 2 * dn)
+        grp_ms = timed(lambda: ctx6.ct_mul_relin_grouped(2, a, b, gkey, out, B, 65537), k, 2) / k
+        extras["ct_mul_relin_grouped"] = {"value": world * B / (grp_ms * 1e-3), "unit": "ct-mult/s", "ms_per_step": grp_ms,
+                                          "kernel": "ks_grouped_kernel<13,256,3,MUL_RELIN>", "GBps": B * ALGO_BYTES_CT_MUL / (grp_ms * 1e-3) / 1e9,
+                                          "note": "4 ciphertext limbs in 2 digits + 2 special primes, BGV rounding t=65537 (DESIGN.md 2.11)"}
+        ctx6.close()
+        del gkey
     ctx.ct_mul_relin(a, b, evk, out, B)     # `out` = the reference result for the comparisons below
     torch.cuda.synchronize()
 

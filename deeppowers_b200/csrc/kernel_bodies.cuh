@@ -111,6 +111,17 @@ DPFHE_HD void ntt_fwd_body(CTA &cta, u64 *buf, u64 *data, const Twiddle *tw, con
     });
 }
 
+// the limb already sits in shared memory in the swizzled layout (copied by the threads below, or by the TMA unit:
+// ntt_inv_tma_kernel): register passes, then the outermost stage straight to global memory
+template <int LOGN, int NT, class CTA>
+DPFHE_HD void ntt_inv_resident(CTA &cta, u64 *buf, u64 *data, const Twiddle *itw, const LimbParams &p) {
+    inv_passes<LOGN, NT>(cta, buf, itw, p);
+    U64x2 *dst = reinterpret_cast<U64x2 *>(data);
+    cta.par([&](int tid) {
+        inv_store_stage<LOGN, NT>(buf, itw, p, tid, [&](int c, const U64x2 &v) { st_stream(dst + c, v); });
+    });
+}
+
 template <int LOGN, int NT, class CTA>
 DPFHE_HD void ntt_inv_body(CTA &cta, u64 *buf, u64 *data, const Twiddle *itw, const LimbParams &p) {
     const U64x2 *src = reinterpret_cast<const U64x2 *>(data);
@@ -118,11 +129,7 @@ DPFHE_HD void ntt_inv_body(CTA &cta, u64 *buf, u64 *data, const Twiddle *itw, co
         for (int c = tid; c < (1 << (LOGN - 1)); c += NT)
             reinterpret_cast<U64x2 *>(buf)[swz_chunk(c)] = ld_stream(src + c);
     });
-    inv_passes<LOGN, NT>(cta, buf, itw, p);
-    U64x2 *dst = reinterpret_cast<U64x2 *>(data);
-    cta.par([&](int tid) {
-        inv_store_stage<LOGN, NT>(buf, itw, p, tid, [&](int c, const U64x2 &v) { st_stream(dst + c, v); });
-    });
+    ntt_inv_resident<LOGN, NT>(cta, buf, data, itw, p);
 }
 
 // ---- N = 16384 standalone transforms by a PAIR of CTAs (a thread-block cluster of two) ------------------------------

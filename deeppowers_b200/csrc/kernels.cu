@@ -6,6 +6,7 @@
 //                         -> (L-1) x [lift + NTT + multiply-accumulate with the switch key] -> out
 //   pointwise kernels     128-bit vectorised grid-stride loops
 #include <cooperative_groups.h>
+#include <cuda.h>   // CUtensorMap (types only: the driver entry point is fetched at run time, libcuda is not linked)
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -73,6 +74,51 @@ __global__ void __launch_bounds__(NT, MINB) ntt_kernel(u64 *data, const Twiddle 
         if (INVERSE) ntt_inv_body<LOGN, NT>(cta, buf, data + w * N, tables + (size_t)l * N, p);
         else ntt_fwd_body<LOGN, NT>(cta, buf, data + w * N, tables + (size_t)l * N, p);
     }
+}
+
+// Inverse transform whose input copy is done by the TMA unit: the swizzled shared-memory layout of ntt_core.cuh IS the layout a
+// 2-D tensor map with CU_TENSOR_MAP_SWIZZLE_128B produces (rows of 128 bytes = 16 coefficients, 16-byte chunk index XOR row & 7),
+// so one elected thread issues cp.async.bulk.tensor for the whole limb (boxes of 256 rows = 32 KiB) and everybody waits on the
+// mbarrier, instead of 256 threads looping over LDG.128 + STS.128.  One limb per CTA (grid = n_limbs): the barrier is used once.
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+template <int LOGN, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ntt_inv_tma_kernel(const __grid_constant__ CUtensorMap tm, u64 *data, const Twiddle *__restrict__ itw,
+                                                                const __grid_constant__ LimbTable lt, u32 L) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
+    constexpr size_t N = (size_t)1 << LOGN;
+    constexpr int ROWS = (int)(N * 8 / 128), BOX_ROWS = ROWS < 256 ? ROWS : 256, BOXES = ROWS / BOX_ROWS;
+    DevCta<NT> cta;
+    const size_t w = blockIdx.x;
+    const u32 l = (u32)(w % L);
+    const u32 bar_a = smem_addr(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((u32)(N * 8)) : "memory");
+#pragma unroll
+        for (int b = 0; b < BOXES; ++b) {
+            const int row = (int)(w * ROWS) + b * BOX_ROWS;
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(smem_addr(smem_raw + (size_t)b * BOX_ROWS * 128)), "l"(reinterpret_cast<unsigned long long>(&tm)), "r"(0), "r"(row), "r"(bar_a)
+                         : "memory");
+        }
+    }
+    {   // every thread waits for the bytes to land (phase 0 of the barrier)
+        u32 done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done)
+                         : "r"(bar_a)
+                         : "memory");
+        }
+    }
+    ntt_inv_resident<LOGN, NT>(cta, buf, data + w * N, itw + (size_t)l * N, lt.lp[l]);
 }
 
 // N = 16384: one limb per CLUSTER of two CTAs (64 KiB of shared memory each, so three CTAs still share an SM); see
@@ -812,8 +858,54 @@ static cudaError_t launch_ntt_t(const LaunchCtx &lc, u64 *data, size_t n_limbs, 
     return cudaGetLastError();
 }
 
+// tensor map of the caller's array seen as rows of 128 bytes; the encode function comes from the driver through the runtime
+// (cudaGetDriverEntryPoint), so libdpfhe.so does not link libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static std::atomic<EncodeTiledFn> cached{nullptr};
+    EncodeTiledFn f = cached.load();
+    if (f) return f;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p)
+        return nullptr;
+    cached.store(reinterpret_cast<EncodeTiledFn>(p));
+    return reinterpret_cast<EncodeTiledFn>(p);
+}
+
+// returns cudaErrorNotSupported when the TMA path does not apply (no driver entry point, too many rows for 32-bit coordinates):
+// the caller then runs the ordinary kernel
+template <int LOGN, int NT, int MINB>
+static cudaError_t launch_ntt_inv_tma(const LaunchCtx &lc, u64 *data, size_t n_limbs, cudaStream_t st) {
+    constexpr size_t ROWS = ((size_t)1 << LOGN) * 8 / 128;
+    const size_t rows = n_limbs * ROWS;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || rows >= 0x7fffffffull || n_limbs >= 0x7fffffffull) return cudaErrorNotSupported;
+    CUtensorMap tm;
+    const cuuint64_t dims[2] = {16, (cuuint64_t)rows}, strides[1] = {128};
+    const cuuint32_t box[2] = {16, (cuuint32_t)(ROWS < 256 ? ROWS : 256)}, estr[2] = {1, 1};
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorNotSupported;
+    auto kern = ntt_inv_tma_kernel<LOGN, NT, MINB>;
+    const size_t smem = Geometry<LOGN>::LIMB_BYTES;
+    static ConfiguredMask configured;
+    if (!configured.has(lc.device)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured.set(lc.device);
+    }
+    kern<<<(unsigned)n_limbs, NT, smem, st>>>(tm, data, lc.itw, lc.lt, lc.L);
+    return cudaGetLastError();
+}
+
 template <int LOGN, int NT, int MINB>
 static cudaError_t launch_ntt_dir(const LaunchCtx &lc, u64 *data, size_t n_limbs, bool inverse, cudaStream_t st) {
+    if (inverse && lc.ntt_tma && LOGN <= 13 && NT == 256) {
+        cudaError_t e = launch_ntt_inv_tma<LOGN, NT, MINB>(lc, data, n_limbs, st);
+        if (e != cudaErrorNotSupported) return e;
+    }
     return inverse ? launch_ntt_t<LOGN, NT, MINB, true>(lc, data, n_limbs, st) : launch_ntt_t<LOGN, NT, MINB, false>(lc, data, n_limbs, st);
 }
 

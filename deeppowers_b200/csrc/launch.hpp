@@ -18,6 +18,7 @@ struct LaunchCtx {
     LimbTable lt;                     // host copy, passed by value to the transform kernels
     int rot_cfg = 0;                  // tuning variant of rot_apply_kernel (DPFHE_ROT_CFG)
     int ntt_cfg = 0;                  // tuning variant of the N=8192 transform kernel (DPFHE_NTT_CFG)
+    int ntt_tma = 1;                  // inverse transforms (N <= 8192) fetch their limb with the TMA unit (DPFHE_NTT_TMA=0: thread copies)
     const Twiddle *tw = nullptr;      // [L][N] forward twiddles, device layout (ntt_core.cuh:tw_pos)
     const Twiddle *itw = nullptr;     // [L][N] inverse twiddles
     // fused key-switch pipeline
