@@ -345,7 +345,7 @@ def main():
     inv_ms = timed(lambda: ctx.ntt_inv(a, 2 * B), k_ntt, 2) / k_ntt
     ntt = ntt_entry(fwd_ms, n_ntt, ALGO_BYTES_NTT, "ntt_kernel<13,256,3,fwd> (dpfhe::fast, one CTA per limb, 3 CTAs/SM)", "ntt_kernel_fwd")
     ntt["metric"] = "ntt_fwd_per_s"
-    ntt["inverse"] = ntt_entry(inv_ms, n_ntt, ALGO_BYTES_NTT, "ntt_kernel<13,256,3,inv>", "ntt_kernel_inv")
+    ntt["inverse"] = ntt_entry(inv_ms, n_ntt, ALGO_BYTES_NTT, "ntt_inv_tma_kernel<13,256,3> (inverse passes of ntt_kernel, limb fetched by TMA)", "ntt_kernel_inv")
     ctx.fill_uniform(SEED, a, 2 * B, first_poly=first)     # restore `a` (the transforms ran in place)
     if not args.no_extras:
         # config 3's ring: N = 16384, L = 8 (1024 ciphertexts = 16384 limb transforms of 128 KiB)

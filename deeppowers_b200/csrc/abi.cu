@@ -259,6 +259,7 @@ int dpfhe_context_create(const dpfhe_params *p, int device_id, dpfhe_ctx **out) 
     for (size_t l = 0; l < L; ++l) lc.lt.lp[l] = lps[l];
     if (const char *env = getenv("DPFHE_NTT_CFG")) lc.ntt_cfg = atoi(env);
     if (const char *env = getenv("DPFHE_NTT_TMA")) lc.ntt_tma = atoi(env);
+    if (const char *env = getenv("DPFHE_EPOCH_LIMIT")) lc.ks_epoch_limit = strtoull(env, nullptr, 10);
     if (const char *env = getenv("DPFHE_ROT_CFG")) lc.rot_cfg = atoi(env);
     if (const char *env = getenv("DPFHE_KS_OCC")) lc.ks_occ_cap = atoi(env);
     if (const char *env = getenv("DPFHE_KS_PF")) lc.ks_prefetch = atoi(env);

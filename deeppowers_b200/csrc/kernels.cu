@@ -1011,6 +1011,22 @@ cudaError_t launch_mod_down_special(const LaunchCtx &lc, const u64 *in, u64 *tau
     return cudaErrorInvalidValue;
 }
 
+// Flag, round-mark and mailbox tags are 32-bit round numbers compared by signed difference, so a slot last written more than 2^31
+// rounds ago would look "published" (a context that has multiplied 2^31 ciphertexts: an hour of work).  Long before that the
+// numbering restarts: flags, marks, mailboxes and hand-back counters are cleared in stream order - after every earlier launch of
+// the context (abi.cu orders its calls) and before this one - and the epoch returns to zero.
+static cudaError_t epoch_guard(LaunchCtx &lc, size_t batch, cudaStream_t st) {
+    if (batch + 1 >= 0x40000000ull) return cudaErrorInvalidValue;
+    if ((unsigned long long)lc.ks_epoch + batch + 1 < lc.ks_epoch_limit) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(lc.ks_flags, 0, 2 * lc.ks_slots * sizeof(u32), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(lc.ks_mail, 0, lc.ks_slots * sizeof(u64), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(lc.ks_consumed, 0, lc.ks_slots * sizeof(u32), st);
+    if (e != cudaSuccess) return e;
+    lc.ks_epoch = 0;
+    ++lc.ks_epoch_restarts;
+    return cudaSuccess;
+}
+
 template <int LOGN, int MODE>
 static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cudaStream_t st) {
     // at most 64 KiB of shared memory per CTA (N = 16384 is processed as two half-limbs) -> three CTAs per SM
@@ -1040,7 +1056,9 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
     if (G == 0) return cudaErrorInvalidConfiguration;
     // flag / mailbox tags this launch may consume: one per round, and a group runs at most batch + 1 rounds
     const u32 rounds = (u32)(batch + 1);
-    cudaError_t em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
+    cudaError_t em = epoch_guard(lc, batch, st);
+    if (em != cudaSuccess) return em;
+    em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
     if (em != cudaSuccess) return em;
     KsArgs args = A;
     size_t batch_arg = batch;
@@ -1104,7 +1122,9 @@ static cudaError_t launch_ks_hybrid_t(LaunchCtx &lc, const KsArgs &A, const MsCo
     if (G > batch * GS) G = batch * GS;
     if (G == 0) return cudaErrorInvalidConfiguration;
     const u32 rounds = (u32)(batch + 1);
-    cudaError_t em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
+    cudaError_t em = epoch_guard(lc, batch, st);
+    if (em != cudaSuccess) return em;
+    em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
     if (em != cudaSuccess) return em;
     KsArgs args = A;
     LimbTable lt = lc.lt;
@@ -1177,7 +1197,9 @@ static cudaError_t launch_ks_grouped_t(LaunchCtx &lc, const KsArgs &A, const MsC
     if (G > batch * GS) G = batch * GS;
     if (G == 0) return cudaErrorInvalidConfiguration;
     const u32 rounds = (u32)(batch + 1);
-    cudaError_t em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
+    cudaError_t em = epoch_guard(lc, batch, st);
+    if (em != cudaSuccess) return em;
+    em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
     if (em != cudaSuccess) return em;
     KsArgs args = A;
     LimbTable lt = lc.lt;
@@ -1298,7 +1320,9 @@ static cudaError_t launch_hoist_t(LaunchCtx &lc, const HoistArgs &A, size_t batc
     G = (G / lc.L) * lc.L;
     if (G > batch * lc.L) G = batch * lc.L;
     if (G == 0) return cudaErrorInvalidConfiguration;
-    cudaError_t em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
+    cudaError_t em = epoch_guard(lc, batch, st);
+    if (em != cudaSuccess) return em;
+    em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
     if (em != cudaSuccess) return em;
     HoistArgs args = A;
     LimbTable lt = lc.lt;
@@ -1346,7 +1370,9 @@ static cudaError_t launch_hoistg_t(LaunchCtx &lc, const HoistGArgs &A, const Gro
     G = (G / lc.L) * lc.L;
     if (G > batch * lc.L) G = batch * lc.L;
     if (G == 0) return cudaErrorInvalidConfiguration;
-    cudaError_t em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
+    cudaError_t em = epoch_guard(lc, batch, st);
+    if (em != cudaSuccess) return em;
+    em = cudaMemsetAsync(lc.ks_ticket, 0, sizeof(u32), st);
     if (em != cudaSuccess) return em;
     HoistGArgs args = A;
     LimbTable lt = lc.lt;

@@ -38,6 +38,8 @@ struct LaunchCtx {
     u64 *ks_hyb = nullptr;            // hybrid key switching: [ks_slots / 2 + 1][KS_HYB_ROWS][N], allocated at the first hybrid call
     size_t ks_slots = 0;
     u32 ks_epoch = 0;                 // rounds consumed so far (flag values already used)
+    unsigned long long ks_epoch_limit = 1ull << 30;   // the round numbering restarts before it gets here (DPFHE_EPOCH_LIMIT: tests)
+    unsigned ks_epoch_restarts = 0;
     int ks_prefetch = 0;              // ciphertexts ahead for the bulk L2 prefetch of inputs (DPFHE_KS_PF), 0 = off
     int ks_occ_cap = 0;               // tuning: cap on resident fused-kernel CTAs per SM (DPFHE_KS_OCC), 0 = no cap
     unsigned long long *ks_prof = nullptr;   // [ks_slots][16] phase cycle counters; non-null selects the profiling build

@@ -179,3 +179,43 @@ def test_grouped_errors(ctxs):
         c.ct_mul_relin_grouped(2, x, x.clone(), k, x, 1)
     with pytest.raises(RuntimeError, match="below the special prime"):
         c.ct_mul_relin_grouped(2, x, x.clone(), k, x.clone(), 1, 1 << 61)
+
+
+def test_round_numbering_restarts(oracle_mod, monkeypatch):
+    """the flag / mailbox tags restart long before 32-bit round numbers could wrap (here: every few launches); every kernel family
+    that uses them keeps producing the oracle's bits across restarts"""
+    import deeppowers_b200
+    monkeypatch.setenv("DPFHE_EPOCH_LIMIT", "40")
+    c = deeppowers_b200.Context(12, 6)
+    monkeypatch.delenv("DPFHE_EPOCH_LIMIT")
+    o = oracle_mod.Oracle(12, 6)
+    batch = 9
+    x = o.fill_uniform(7, 2 * batch).reshape(batch, 2, 6, o.N)
+    y = o.fill_uniform(8, 2 * batch).reshape(batch, 2, 6, o.N)
+    evk = o.fill_uniform(9, 12).reshape(6, 2, 6, o.N)
+    exp_bv = o.ct_mul_relin(x, y, evk)
+    a, key = grouped_inputs(o, 2, batch, 81)
+    b, _ = grouped_inputs(o, 2, batch, 83)
+    exp_g = o.ct_mul_relin_grouped(2, a, b, key, 65537)
+    h, hkey = a[:, :, :], o.fill_uniform(85, 10).reshape(5, 2, 6, o.N)
+    a5 = o.fill_uniform(86, 2 * batch)[:, :5].reshape(batch, 2, 5, o.N).copy()
+    exp_h = o.ct_mul_relin_hybrid(a5, a5, hkey, 65537)
+    g = o.galois_elt(1)
+    exp_r = o.rotate_hoisted_grouped(2, a, [g], key[None], 65537)
+    out6 = torch.zeros((batch, 2, 6, o.N), dtype=torch.int64, device="cuda")
+    out5 = torch.zeros((batch, 2, 5, o.N), dtype=torch.int64, device="cuda")
+    out4 = torch.zeros((batch, 2, 4, o.N), dtype=torch.int64, device="cuda")
+    outr = torch.zeros((1, batch, 2, 4, o.N), dtype=torch.int64, device="cuda")
+    dx, dy, dk, da, db, dkey, da5, dhk = (dev(v) for v in (x, y, evk, a, b, key, a5, hkey))
+    for _ in range(4):   # ~10 rounds per launch against a limit of 40: a restart every few launches, at different places in the cycle
+        c.ct_mul_relin(dx, dy, dk, out6, batch)
+        assert np.array_equal(host(out6).reshape(x.shape), exp_bv)
+        c.ct_mul_relin_grouped(2, da, db, dkey, out4, batch, 65537)
+        assert np.array_equal(host(out4).reshape(a.shape), exp_g)
+        c.ct_mul_relin_hybrid(da5, da5.clone(), dhk, out5, batch, 65537)
+        assert np.array_equal(host(out5).reshape(a5.shape), exp_h)
+        c.rotate_hoisted_grouped(2, da, [g], [dkey], outr, batch, 65537)
+        assert np.array_equal(host(outr).reshape(exp_r.shape), exp_r)
+        c.ct_mul_relin(dx[:3], dy[:3], dk, out6[:3], 3)
+        assert np.array_equal(host(out6[:3]).reshape(3, 2, 6, o.N), exp_bv[:3])
+    c.close()

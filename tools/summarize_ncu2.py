@@ -30,6 +30,9 @@ def short_name(name):
         logn, inv = targs[0], targs[3] == 1
         base = "ntt_kernel_inv" if inv else "ntt_kernel_fwd"
         return (base if logn == 13 else "%s_n%d" % (base, 1 << logn)), variant
+    if "ntt_inv_tma_kernel" in name:   # the inverse direction's kernel since the TMA-fed load (same passes, same summary key)
+        logn = int(re.search(r"ntt_inv_tma_kernel<(?:\(int\))?(\d+)", name).group(1))
+        return ("ntt_kernel_inv" if logn == 13 else "ntt_kernel_inv_n%d" % (1 << logn)), variant
     if "ks_fused_kernel" in name:
         return "ks_fused_kernel_mul_relin", variant
     return re.sub(r"[^a-z_]", "", name.split("<")[0].split("::")[-1]), variant
