@@ -40,6 +40,27 @@ def test_wire_hybrid_key_roundtrip(tmp_path, oracle_mod):
     assert hdr["kind"] == wire.HYBRID_SWITCH_KEY and hdr["moduli"] == o.moduli and np.array_equal(data.reshape(key.shape), key)
 
 
+def test_wire_grouped_key_roundtrip(tmp_path, oracle_mod):
+    """kind 5: a grouped hybrid key announces its number of special primes in `count`; C++ and Python agree on the payload size"""
+    from deeppowers_b200 import wire
+    o = oracle_mod.Oracle(12, 5)
+    key = o.fill_uniform(6, 4).reshape(2, 2, 5, o.N)      # K = 2: ceil(3 / 2) = 2 digits, [2][2][L][N]
+    p = str(tmp_path / "gk.dpfhe")
+    wire.write(p, 12, 5, wire.GROUPED_SWITCH_KEY, 2, o.moduli, key)
+    hdr, data = wire.read(p)
+    assert hdr["kind"] == wire.GROUPED_SWITCH_KEY and hdr["count"] == 2 and np.array_equal(data.reshape(key.shape), key)
+    with pytest.raises(ValueError):
+        wire.write(p, 12, 5, wire.GROUPED_SWITCH_KEY, 3, o.moduli, key)      # 2K > L
+    src = str(tmp_path / "w.cpp")
+    with open(src, "w") as f:
+        f.write('#include <dpfhe_wire.hpp>\n#include <iostream>\nint main(int, char **v) { std::vector<std::uint64_t> d; '
+                'auto h = deeppowers::api::fhe::read_wire_file(v[1], d); std::cout << h.kind << " " << h.count << " " << d.size() << " " << d[5]; }\n')
+    exe = str(tmp_path / "w")
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+    out = subprocess.run([exe, p], capture_output=True, text=True, check=True).stdout.split()
+    assert out == ["5", "2", str(key.size), str(int(key.reshape(-1)[5]))]
+
+
 def test_wire_format_roundtrip(tmp_path, oracle_mod):
     from deeppowers_b200 import wire
     o = oracle_mod.Oracle(12, 2)
