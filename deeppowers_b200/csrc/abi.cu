@@ -480,7 +480,7 @@ int dpfhe_rotate(dpfhe_ctx *ctx, const uint64_t *d_ct, uint64_t galois_elt, cons
 
 // hybrid (special-prime) variants: the context's last limb is the special prime, data carries L-1 limbs
 // n_special = K: the last K limbs are special primes and the digits are groups of K limbs; K = 1 is §2.10
-static int check_special(dpfhe_ctx *ctx, unsigned n_special) {
+static int check_special(const dpfhe_ctx *ctx, unsigned n_special) {
     const unsigned L = ctx->hp.L;
     if (L < 2) return fail(DPFHE_ERR_INVALID, "hybrid key switching needs a special prime: create the context with at least two limbs");
     if (n_special < 1 || n_special > (unsigned)KS_MAX_SPECIAL || 2 * n_special > L)
@@ -543,7 +543,7 @@ int dpfhe_rotate_grouped(dpfhe_ctx *ctx, unsigned n_special, const uint64_t *d_c
 }
 int dpfhe_grouped_digits(const dpfhe_ctx *ctx, unsigned n_special, unsigned *digits) {
     if (!ctx || !digits) return fail(DPFHE_ERR_INVALID, "null argument");
-    int rc = check_special(const_cast<dpfhe_ctx *>(ctx), n_special);
+    int rc = check_special(ctx, n_special);
     if (rc) return rc;
     *digits = (ctx->hp.L - n_special + n_special - 1) / n_special;
     return DPFHE_OK;

@@ -272,7 +272,7 @@ void run_rotate_hoisted_grouped(Emu &e, unsigned Ks, const uint64_t *ct, size_t 
     GroupConsts G;
     build_group_consts(e.hp, Ks, t_plain, G, K);
     const unsigned dnum = G.dnum;
-    const size_t P = (size_t)L * N, Pq = (size_t)Lq * N, key_words = (size_t)2 * dnum * L * N;
+    const size_t P = (size_t)L * N, key_words = (size_t)2 * dnum * L * N;
     uint64_t *buf = aligned_new<uint64_t>(N), *scratch = aligned_new<uint64_t>((size_t)L * 2 * N);
     uint64_t *U = aligned_new<uint64_t>(batch * dnum * L * N), *acc = aligned_new<uint64_t>(batch * 2 * P), *tau = aligned_new<uint64_t>((size_t)Ks * N);
     uint64_t *key_s = aligned_new<uint64_t>(key_words);
@@ -303,7 +303,6 @@ void run_rotate_hoisted_grouped(Emu &e, unsigned Ks, const uint64_t *ct, size_t 
                                                e.lp[i], K, G, i);
         }
     }
-    (void)Pq;
     free(buf); free(scratch); free(U); free(acc); free(tau); free(key_s);
 }
 
