@@ -135,3 +135,140 @@ def test_real_keys_decrypt_through_the_bigint_path(oracle_mod):
             v = int(m1[i]) * int(m2[j])
             neg[k % o.N] = (neg[k % o.N] + (v if k < o.N else -v)) % t
     assert [int(v) for v in o.decrypt(s, prod, t)] == neg
+
+
+class SpecialPrimeRing(Ring):
+    """The special-prime family over the same evaluation points: the last K moduli are special primes, the
+    first Lq = L - K carry the ciphertexts.  Digits, lifts and the division are written with Python integers in COEFFICIENT form
+    (the oracle and the kernels work limb-wise in evaluation form): a digit is the integer vector v = sum_j y_j * Qhat_j, a lift is
+    v mod q_i, the division is ((acc - s * delta) * P^-1) mod q_i with delta the centred recombination of the special residues."""
+
+    def __init__(self, log_n, moduli, psi, K):
+        super().__init__(log_n, moduli, psi)
+        self.K, self.L, self.Lq = K, len(self.q), len(self.q) - K
+        self.dnum = -(-self.Lq // K)
+        self.P = 1
+        for p in self.q[self.Lq:]:
+            self.P *= p
+
+    def group(self, g):
+        return range(g * self.K, min((g + 1) * self.K, self.Lq))
+
+    def digit_vectors(self, d):
+        """d [Lq][N] evaluation form -> per digit g the integer coefficient vector sum_j y_j * Qhat_j (a lift of the digit: congruent
+        to its value modulo Q_g, below |g| * Q_g)"""
+        out = []
+        for g in range(self.dnum):
+            Qg = 1
+            for j in self.group(g):
+                Qg *= self.q[j]
+            v = [0] * self.N
+            for j in self.group(g):
+                Qhat = Qg // self.q[j]
+                y = [c * pow(Qhat, -1, self.q[j]) % self.q[j] for c in self.interpolate(d[j], j)]
+                v = [a + b * Qhat for a, b in zip(v, y)]
+            out.append(v)
+        return out
+
+    def lifted(self, d, vectors):
+        """U[g][i]: evaluation form in limb i of digit g's lift; the member limbs keep the ciphertext's own residues"""
+        return [[d[i] if i in self.group(g) else self.evaluate([x % self.q[i] for x in vectors[g]], i) for i in range(self.L)]
+                for g in range(self.dnum)]
+
+    def divide_by_P(self, acc, t_plain):
+        """acc [L][N] evaluation form -> [Lq][N]: (acc - s * delta) / P, delta = t^-1 acc mod P recombined from centred residues"""
+        s = t_plain if t_plain else 1
+        delta = [0] * self.N
+        for k in range(self.K):
+            l = self.Lq + k
+            p = self.q[l]
+            Phat = self.P // p
+            f = pow(s * Phat, -1, p)
+            for n, c in enumerate(self.interpolate(acc[l], l)):
+                y = c * f % p
+                delta[n] += (y - p if y > p // 2 else y) * Phat
+        out = []
+        for i in range(self.Lq):
+            q = self.q[i]
+            Pinv = pow(self.P, -1, q)
+            coeffs = [(c - s * dl) * Pinv % q for c, dl in zip(self.interpolate(acc[i], i), delta)]
+            out.append(self.evaluate(coeffs, i))
+        return out
+
+    def mac(self, U, key, perm=None):
+        acc = [[[0] * self.N for _ in range(self.L)] for _ in range(2)]
+        for g in range(self.dnum):
+            for i in range(self.L):
+                u = U[g][i] if perm is None else [U[g][i][perm[n]] for n in range(self.N)]
+                for comp in range(2):
+                    row = acc[comp][i]
+                    for n in range(self.N):
+                        row[n] = (row[n] + u[n] * key[g][comp][i][n]) % self.q[i]
+        return acc
+
+    def keyswitch(self, d, key, t_plain, perm=None, vectors=None):
+        U = self.lifted(d, vectors if vectors is not None else self.digit_vectors(d))
+        acc = self.mac(U, key, perm)
+        return [self.divide_by_P(acc[0], t_plain), self.divide_by_P(acc[1], t_plain)]
+
+    def ct_mul_relin(self, a, b, evk, t_plain):
+        Lq = self.Lq
+        d0 = [[a[0][l][n] * b[0][l][n] % self.q[l] for n in range(self.N)] for l in range(Lq)]
+        d1 = [[(a[0][l][n] * b[1][l][n] + a[1][l][n] * b[0][l][n]) % self.q[l] for n in range(self.N)] for l in range(Lq)]
+        d2 = [[a[1][l][n] * b[1][l][n] % self.q[l] for n in range(self.N)] for l in range(Lq)]
+        ks = self.keyswitch(d2, evk, t_plain)
+        return [[[(x + y) % self.q[l] for x, y in zip(d[l], ks[comp][l])] for l in range(Lq)] for comp, d in enumerate((d0, d1))]
+
+    def rotate(self, ct, g, gk, t_plain):
+        Lq = self.Lq
+        sig = [[self.evaluate(self.automorphism(self.interpolate(ct[comp][l], l), g, self.q[l]), l) for l in range(Lq)] for comp in range(2)]
+        ks = self.keyswitch(sig[1], gk, t_plain)
+        return [[[(x + y) % self.q[l] for x, y in zip(sig[0][l], ks[0][l])] for l in range(Lq)], ks[1]]
+
+    def rotate_hoisted(self, ct, g, gk, t_plain):
+        """the automorphism applied to the LIFT of the unrotated digits (integer vectors, signs and all), then lifted limb by limb"""
+        Lq = self.Lq
+        vec = [[(-c if neg else c) for c, neg in self._signed(v, g)] for v in self.digit_vectors(ct[1])]
+        sig = [[self.evaluate(self.automorphism(self.interpolate(ct[comp][l], l), g, self.q[l]), l) for l in range(Lq)] for comp in range(2)]
+        ks = self.keyswitch(sig[1], gk, t_plain, vectors=vec)
+        return [[[(x + y) % self.q[l] for x, y in zip(sig[0][l], ks[0][l])] for l in range(Lq)], ks[1]]
+
+    def _signed(self, v, g):
+        """X -> X^g on an integer coefficient vector: [(coefficient, negated?)] in the new order"""
+        out = [None] * self.N
+        for k, c in enumerate(v):
+            e = k * g % (2 * self.N)
+            out[e % self.N] = (c, e >= self.N)
+        return out
+
+
+@pytest.mark.parametrize("log_n,L,K", [(4, 2, 1), (4, 4, 2), (5, 5, 2), (4, 7, 3), (3, 8, 4)])
+def test_special_prime_family_from_the_definitions(oracle_mod, log_n, L, K):
+    o = oracle_mod.Oracle(log_n, L)
+    ring = SpecialPrimeRing(log_n, o.moduli, o.psi, K)
+    Lq, N, t = L - K, o.N, 65537
+    oq = oracle_mod.Oracle(log_n, Lq, o.moduli[:Lq])
+    a = oq.fill_uniform(21, 2).reshape(2, Lq, N)
+    b = oq.fill_uniform(22, 2).reshape(2, Lq, N)
+    q = np.array(o.moduli[:Lq], dtype=np.uint64)
+    a[1, :, 0] = q - 1
+    b[0, :, 1] = 0
+    dnum = o.grouped_digits(K)
+    assert dnum == ring.dnum
+    key = o.fill_uniform(23, 2 * dnum).reshape(dnum, 2, L, N)
+    x = o.fill_uniform(24, 1)
+    for tp in (0, t):
+        assert as_lists(o.mod_down_special(K, x, tp)[0]) == ring.divide_by_P(as_lists(x[0]), tp)
+        if K == 1:
+            assert as_lists(o.mod_switch_down(x, tp)[0]) == ring.divide_by_P(as_lists(x[0]), tp)
+        d = a[1]
+        c0, c1 = o.keyswitch_grouped(K, d, key, tp)
+        want = ring.keyswitch(as_lists(d), as_lists(key), tp)
+        assert as_lists(c0) == want[0] and as_lists(c1) == want[1]
+        if K == 1:
+            h0, h1 = o.keyswitch_hybrid(d, key, tp)
+            assert as_lists(h0) == want[0] and as_lists(h1) == want[1]
+    assert as_lists(o.ct_mul_relin_grouped(K, a[None], b[None], key, t)[0]) == ring.ct_mul_relin(as_lists(a), as_lists(b), as_lists(key), t)
+    for g in (o.galois_elt(1), o.galois_elt(-1), 2 * N - 1):
+        assert as_lists(o.rotate_grouped(K, a[None], g, key, t)[0]) == ring.rotate(as_lists(a), g, as_lists(key), t)
+        assert as_lists(o.rotate_hoisted_grouped(K, a[None], [g], key[None], t)[0, 0]) == ring.rotate_hoisted(as_lists(a), g, as_lists(key), t)
