@@ -14,6 +14,14 @@
 #include "kernel_bodies.cuh"
 #include "launch.hpp"
 
+// The file is large (every kernel x three ring degrees x three modes); the build compiles it in two parts per variant, in parallel:
+// -DDPFHE_PART=1 everything but the special-prime key-switch family, -DDPFHE_PART=2 that family; no flag = all of it.
+#ifndef DPFHE_PART
+#define DPFHE_PART 0
+#endif
+#define DPFHE_PART_MAIN (DPFHE_PART == 0 || DPFHE_PART == 1)
+#define DPFHE_PART_SPECIAL (DPFHE_PART == 0 || DPFHE_PART == 2)
+
 // compiled twice: -DDPFHE_FAST=0 -> namespace dpfhe::gen, -DDPFHE_FAST=1 -> namespace dpfhe::fast (types.hpp)
 namespace dpfhe {
 namespace DPFHE_VNS {
@@ -58,6 +66,7 @@ struct DevCta {
     }
 };
 
+#if DPFHE_PART_MAIN
 // ------------------------------------------------------------------ standalone transforms
 // The per-limb constants travel in the kernel parameter block (constant bank), so q, 2q, 8q ...
 // are read through uniform registers / constant operands instead of occupying vector registers.
@@ -214,6 +223,7 @@ __global__ void __launch_bounds__(NT, MINB) md_limb_kernel(const u64 *in, const 
     }
 }
 
+#endif
 // ------------------------------------------------------------------ fused key-switch family
 __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
     u32 v;
@@ -237,6 +247,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, u32 bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+#if DPFHE_PART_MAIN
 // grid = G CTAs, G a multiple of L, all co-resident (cooperative launch).  The L CTAs of slots
 // [g*L, (g+1)*L) form a group that processes one ciphertext at a time: CTA `slot` owns output limb
 // i = slot % L.  The group leader (i == 0) draws the next ciphertext index from a global ticket counter
@@ -435,6 +446,8 @@ __global__ void __launch_bounds__(256) kprime_kernel(const u64 *__restrict__ key
     }
 }
 
+#endif
+#if DPFHE_PART_SPECIAL
 // Hybrid (special-prime) variant, DESIGN.md §2.10.  A group is L + 1 CTAs: CTA i < L owns ciphertext limb i,
 // CTA L owns the special limb.  Per ciphertext:
 //   limb CTA    tensor/permute, p*own terms + first key term, INTT, publish digit        (as above)
@@ -702,6 +715,8 @@ __global__ void __launch_bounds__(NT, MINB) rot_apply_grouped_kernel(RotApplyGAr
     }
 }
 
+#endif
+#if DPFHE_PART_MAIN
 // ------------------------------------------------------------------ plaintext inner products (BSGS inner loop)
 template <int LOGN, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) pt_inner_kernel(PtInnerArgs A, const __grid_constant__ LimbTable lt, u32 g0, u32 gcnt) {
@@ -810,6 +825,7 @@ __global__ void __launch_bounds__(256) fill_uniform_kernel(U64x2 *__restrict__ o
     }
 }
 
+#endif
 // Shoup companions of a switch key: ks[e] = floor(key[e] * 2^64 / q_limb(e)); layout [L][2][L][N]
 template <int LOGN>
 __global__ void __launch_bounds__(256) key_prepare_kernel(const u64 *__restrict__ key, u64 *__restrict__ key_s,
@@ -842,6 +858,7 @@ static unsigned ew_grid(const LaunchCtx &lc, size_t work_items) {
     return (unsigned)(blocks ? blocks : 1);
 }
 
+#if DPFHE_PART_MAIN
 template <int LOGN, int NT, int MINB, bool INV>
 static cudaError_t launch_ntt_t(const LaunchCtx &lc, u64 *data, size_t n_limbs, cudaStream_t st) {
     auto kern = ntt_kernel<LOGN, NT, MINB, INV>;
@@ -902,9 +919,11 @@ static cudaError_t launch_ntt_inv_tma(const LaunchCtx &lc, u64 *data, size_t n_l
 
 template <int LOGN, int NT, int MINB>
 static cudaError_t launch_ntt_dir(const LaunchCtx &lc, u64 *data, size_t n_limbs, bool inverse, cudaStream_t st) {
-    if (inverse && lc.ntt_tma && LOGN <= 13 && NT == 256) {
-        cudaError_t e = launch_ntt_inv_tma<LOGN, NT, MINB>(lc, data, n_limbs, st);
-        if (e != cudaErrorNotSupported) return e;
+    if constexpr (LOGN <= 13 && NT == 256) {
+        if (inverse && lc.ntt_tma) {
+            cudaError_t e = launch_ntt_inv_tma<LOGN, NT, MINB>(lc, data, n_limbs, st);
+            if (e != cudaErrorNotSupported) return e;
+        }
     }
     return inverse ? launch_ntt_t<LOGN, NT, MINB, true>(lc, data, n_limbs, st) : launch_ntt_t<LOGN, NT, MINB, false>(lc, data, n_limbs, st);
 }
@@ -1011,6 +1030,7 @@ cudaError_t launch_mod_down_special(const LaunchCtx &lc, const u64 *in, u64 *tau
     return cudaErrorInvalidValue;
 }
 
+#endif
 // Flag, round-mark and mailbox tags are 32-bit round numbers compared by signed difference, so a slot last written more than 2^31
 // rounds ago would look "published" (a context that has multiplied 2^31 ciphertexts: an hour of work).  Long before that the
 // numbering restarts: flags, marks, mailboxes and hand-back counters are cleared in stream order - after every earlier launch of
@@ -1027,17 +1047,21 @@ static cudaError_t epoch_guard(LaunchCtx &lc, size_t batch, cudaStream_t st) {
     return cudaSuccess;
 }
 
+#if DPFHE_PART_MAIN
 template <int LOGN, int MODE>
 static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cudaStream_t st) {
     // at most 64 KiB of shared memory per CTA (N = 16384 is processed as two half-limbs) -> three CTAs per SM
     constexpr int NT = 256, MINB = 3;
     const bool filter = A.only != nullptr;
     if (filter && MODE != KS_ROTATE) return cudaErrorInvalidValue;
-    auto kern = lc.ks_prof ? ks_fused_kernel<LOGN, NT, MINB, MODE, true> : ks_fused_kernel<LOGN, NT, MINB, MODE, false>;
+    auto kern = ks_fused_kernel<LOGN, NT, MINB, MODE, false>;
+    if constexpr (MODE == KS_MUL_RELIN) {   // the per-phase clock counters (DPFHE_KS_PROF, tools/phase_prof.py) exist for ct x ct only
+        if (lc.ks_prof) kern = ks_fused_kernel<LOGN, NT, MINB, MODE, true>;
+    }
     if (filter) kern = ks_fused_kernel<LOGN, NT, MINB, MODE == KS_ROTATE ? MODE : KS_ROTATE, false, MODE == KS_ROTATE>;
     const size_t smem = LOGN <= 13 ? Geometry<LOGN>::LIMB_BYTES : Geometry<13>::LIMB_BYTES;
     static ConfiguredMask configured[3];
-    const int variant = filter ? 2 : (lc.ks_prof ? 1 : 0);
+    const int variant = filter ? 2 : (lc.ks_prof && MODE == KS_MUL_RELIN ? 1 : 0);
     if (!configured[variant].has(lc.device)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1099,6 +1123,8 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
     return e;
 }
 
+#endif
+#if DPFHE_PART_SPECIAL
 template <int LOGN, int MODE>
 static cudaError_t launch_ks_hybrid_t(LaunchCtx &lc, const KsArgs &A, const MsConsts &K, size_t batch, cudaStream_t st) {
     constexpr int NT = 256, MINB = 3;
@@ -1250,6 +1276,8 @@ cudaError_t launch_ks_grouped(LaunchCtx &lc, int mode, const u64 *a, const u64 *
     return cudaErrorNotSupported;
 }
 
+#endif
+#if DPFHE_PART_MAIN
 // shared-memory plan of pt_inner_kernel: two CTAs per SM (113 KiB each); the plaintext tile takes nb * 128 bytes per
 // giant step and the two ciphertext-row buffers 2 * nb * 128 bytes each.  Returns giant steps per launch (0: nb too large).
 static constexpr size_t PTI_SMEM_BUDGET = (size_t)113 << 10;
@@ -1350,6 +1378,8 @@ cudaError_t launch_hoist(LaunchCtx &lc, const u64 *ct, u64 *U, u32 *zero, size_t
     return cudaErrorInvalidValue;
 }
 
+#endif
+#if DPFHE_PART_SPECIAL
 template <int LOGN>
 static cudaError_t launch_hoistg_t(LaunchCtx &lc, const HoistGArgs &A, const GroupConsts &Gc, size_t batch, cudaStream_t st) {
     constexpr int NT = 256, MINB = 3;
@@ -1435,6 +1465,8 @@ cudaError_t launch_rot_apply_grouped(LaunchCtx &lc, const u64 *ct, const u64 *U,
     return cudaGetLastError();
 }
 
+#endif
+#if DPFHE_PART_MAIN
 // per-rotation constants: Shoup companions of the key (lc.ks_key_s), M = NTT(negmask_g) (in `M`, [L][N]) and kprime [2][L][N]
 cudaError_t launch_rot_prepare(LaunchCtx &lc, const u64 *key, u32 galois, const u64 *delta, u64 *M, u64 *kprime, cudaStream_t st, u64 *key_s_out) {
     u64 *key_s = key_s_out ? key_s_out : lc.ks_key_s;   // a caller that keeps the constants of a rotation supplies its own buffer
@@ -1605,5 +1637,6 @@ cudaError_t launch_fill_uniform(const LaunchCtx &lc, u64 seed, u64 first_poly, u
     return cudaGetLastError();
 }
 
+#endif
 }  // namespace DPFHE_VNS
 }  // namespace dpfhe
