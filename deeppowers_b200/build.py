@@ -8,9 +8,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libdpfhe.so")
 # (source, object name, extra flags): kernels.cu is compiled once per arithmetic variant (csrc/types.hpp) and, to keep the
-# wall-clock time of a clean build down, in two parts each (DPFHE_PART: 1 = everything but the special-prime family, 2 = that family)
-UNITS = [("kernels.cu", "kernels_gen_main", ["-DDPFHE_FAST=0", "-DDPFHE_PART=1"]), ("kernels.cu", "kernels_gen_special", ["-DDPFHE_FAST=0", "-DDPFHE_PART=2"]),
-         ("kernels.cu", "kernels_fast_main", ["-DDPFHE_FAST=1", "-DDPFHE_PART=1"]), ("kernels.cu", "kernels_fast_special", ["-DDPFHE_FAST=1", "-DDPFHE_PART=2"]),
+# wall-clock time of a clean build down, in three parts each (DPFHE_PART: 1 = everything but the special-prime family, 2 = its
+# one-special-prime kernel, 3 = the grouped kernels)
+UNITS = [("kernels.cu", "kernels_%s_%s" % (v, n), ["-DDPFHE_FAST=%d" % f, "-DDPFHE_PART=%d" % part])
+         for v, f in (("gen", 0), ("fast", 1)) for n, part in (("main", 1), ("hybrid", 2), ("grouped", 3))] + [
          ("abi.cu", "abi", []), ("multi.cu", "multi", []), ("hostmem.cu", "hostmem", []), ("host_params.cpp", "host_params", [])]
 SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = ["types.hpp", "modarith.cuh", "ntt_core.cuh", "kernel_bodies.cuh", "launch.hpp", "host_params.hpp", "ctx.hpp",

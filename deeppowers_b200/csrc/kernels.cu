@@ -15,12 +15,13 @@
 #include "launch.hpp"
 
 // The file is large (every kernel x three ring degrees x three modes); the build compiles it in two parts per variant, in parallel:
-// -DDPFHE_PART=1 everything but the special-prime key-switch family, -DDPFHE_PART=2 that family; no flag = all of it.
+// -DDPFHE_PART=1 everything but the special-prime key-switch family, 2 its one-special-prime kernel, 3 the grouped kernels; no flag = all.
 #ifndef DPFHE_PART
 #define DPFHE_PART 0
 #endif
 #define DPFHE_PART_MAIN (DPFHE_PART == 0 || DPFHE_PART == 1)
-#define DPFHE_PART_SPECIAL (DPFHE_PART == 0 || DPFHE_PART == 2)
+#define DPFHE_PART_HYBRID (DPFHE_PART == 0 || DPFHE_PART == 2)
+#define DPFHE_PART_GROUPED (DPFHE_PART == 0 || DPFHE_PART == 3)
 
 // compiled twice: -DDPFHE_FAST=0 -> namespace dpfhe::gen, -DDPFHE_FAST=1 -> namespace dpfhe::fast (types.hpp)
 namespace dpfhe {
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(256) kprime_kernel(const u64 *__restrict__ key
 }
 
 #endif
-#if DPFHE_PART_SPECIAL
+#if DPFHE_PART_HYBRID
 // Hybrid (special-prime) variant, DESIGN.md §2.10.  A group is L + 1 CTAs: CTA i < L owns ciphertext limb i,
 // CTA L owns the special limb.  Per ciphertext:
 //   limb CTA    tensor/permute, p*own terms + first key term, INTT, publish digit        (as above)
@@ -540,6 +541,8 @@ __global__ void __launch_bounds__(NT, MINB) ks_hybrid_kernel(KsArgs A, const __g
     if (pending) divide(prev_ct, prev_tag, prev_parity);   // the group's last ciphertext
 }
 
+#endif
+#if DPFHE_PART_GROUPED
 // Grouped hybrid variant (dnum < L), DESIGN.md §2.11.  A group is Lq + K CTAs: CTA i < Lq owns ciphertext limb i, CTA Lq + k
 // special prime k.  The roles are those of ks_hybrid_kernel with digits of K limbs:
 //   limb CTA    tensor/permute, P*own terms + the key term of its own digit, INTT (scaled by Qhat^-1), publish
@@ -1124,7 +1127,7 @@ static cudaError_t launch_ks_t(LaunchCtx &lc, const KsArgs &A, size_t batch, cud
 }
 
 #endif
-#if DPFHE_PART_SPECIAL
+#if DPFHE_PART_HYBRID
 template <int LOGN, int MODE>
 static cudaError_t launch_ks_hybrid_t(LaunchCtx &lc, const KsArgs &A, const MsConsts &K, size_t batch, cudaStream_t st) {
     constexpr int NT = 256, MINB = 3;
@@ -1200,6 +1203,8 @@ cudaError_t launch_ks_hybrid(LaunchCtx &lc, int mode, const u64 *a, const u64 *b
     return cudaErrorNotSupported;
 }
 
+#endif
+#if DPFHE_PART_GROUPED
 template <int LOGN, int MODE>
 static cudaError_t launch_ks_grouped_t(LaunchCtx &lc, const KsArgs &A, const MsConsts &K, const GroupConsts &Gc, size_t batch, cudaStream_t st) {
     constexpr int NT = 256, MINB = 3;
@@ -1379,7 +1384,7 @@ cudaError_t launch_hoist(LaunchCtx &lc, const u64 *ct, u64 *U, u32 *zero, size_t
 }
 
 #endif
-#if DPFHE_PART_SPECIAL
+#if DPFHE_PART_GROUPED
 template <int LOGN>
 static cudaError_t launch_hoistg_t(LaunchCtx &lc, const HoistGArgs &A, const GroupConsts &Gc, size_t batch, cudaStream_t st) {
     constexpr int NT = 256, MINB = 3;
