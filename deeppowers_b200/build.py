@@ -60,6 +60,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", SO] + objs
     subprocess.check_call(link)
+    shutil.rmtree(bdir, ignore_errors=True)   # every unit is recompiled whenever a source changes: the objects are of no further use
     return SO
 
 

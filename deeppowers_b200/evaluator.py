@@ -381,6 +381,36 @@ class PinnedBuffer:
     __del__ = close
 
 
+def linear_bsgs_grouped(ctx, ctx_q, n_special, ct, diags, gk_baby, gk_giant, baby, out, batch, t_plain=0, scratch=None, stream=None):
+    """The baby-step/giant-step matrix-vector product of Context.linear_bsgs with special-prime keys: `ctx` is the
+    key-switching context (ciphertext moduli + n_special special primes), `ctx_q` a context over the ciphertext moduli alone for
+    the element-wise steps.  ct / out: [batch][2][Lq][N]; diags: [n][Lq][N]; gk_baby: the baby-1 grouped Galois keys of the
+    rotations by 1 .. baby-1 (the baby steps are hoisted: one mod-up of the input); gk_giant: the key of the rotation by `baby`.
+    scratch: baby + n/baby + 1 ciphertext batches."""
+    import torch
+    n = diags.shape[0]
+    assert n % baby == 0 and len(gk_baby) == baby - 1
+    giant = n // baby
+    Lq = ctx.L - n_special
+    assert ctx_q.L == Lq and ctx_q.moduli == ctx.moduli[:Lq], "ctx_q must be the context of the ciphertext moduli"
+    shape = (batch, 2, Lq, ctx.N)
+    need = baby + giant + 1
+    if scratch is None:
+        scratch = torch.empty((need,) + shape, dtype=torch.int64, device=ct.device)
+    assert scratch.shape[0] >= need
+    steps, inner, tmp = scratch[:baby], scratch[baby:baby + giant], scratch[baby + giant]
+    steps[0].copy_(ct.view(shape))
+    ctx.rotate_hoisted_grouped(n_special, steps[0], [ctx.galois_elt(b) for b in range(1, baby)], list(gk_baby), steps[1:], batch, t_plain, stream)
+    ctx_q.ct_mul_plain_inner(steps, diags, inner, baby, giant, batch, stream)
+    acc = out
+    acc.view(shape).copy_(inner[giant - 1])
+    gb = ctx.galois_elt(baby)
+    for g in range(giant - 2, -1, -1):
+        ctx.rotate_grouped(n_special, acc, gb, gk_giant, tmp, batch, t_plain, stream)      # Horner step: acc = rot_baby(acc) + inner_g
+        ctx_q.poly_add(tmp, inner[g], acc, 2 * batch, stream)
+    return out
+
+
 class LinearLayer:
     """Encrypted linear layer as a library object (dpfhe_linear_*): diagonal plaintexts and Galois keys live on the device; apply()
     takes device buffers, apply_host() host buffers (pipelined in chunks).  diags [n][L][N], gk_baby [baby-1][L][2][L][N] (keys of the

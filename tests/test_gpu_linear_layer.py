@@ -172,3 +172,66 @@ def test_plain_inner_products(oracle_mod, log_n, L, nb, ng, batch):
     with pytest.raises(RuntimeError, match="n_steps"):
         ctx.ct_mul_plain_inner(dev(steps), dev(pts), out, 129, ng, batch)
     ctx.close()
+
+
+def test_encrypted_linear_layer_special_prime_keys(oracle_mod):
+    """the same 768x768 layer with grouped special-prime Galois keys (two special primes, digits of two limbs): hoisted baby steps
+    (one mod-up of the input), fused inner products on the ciphertext moduli, giant steps with rotate_grouped.  Decrypts to W @ x,
+    with far less noise than per-limb-digit keys leave."""
+    import deeppowers_b200 as dp
+    log_n, Lq, K, B, BABY = 13, 4, 2, 2, 32
+    L = Lq + K
+    o = oracle_mod.Oracle(log_n, L)
+    oq = oracle_mod.Oracle(log_n, Lq, o.moduli[:Lq])
+    ctx, ctx_q = dp.Context(log_n, L), dp.Context(log_n, Lq, o.moduli[:Lq])
+    N = o.N
+    enc = SlotEncoder(N, T_PLAIN)
+    rng = np.random.default_rng(0xD3390045)
+    W = rng.integers(-127, 128, (DIM, DIM))
+    X = rng.integers(-127, 128, (B, DIM))
+    s = o.keygen_secret(1)
+    sq = np.ascontiguousarray(s[:Lq])
+    cts = []
+    for b in range(B):
+        slots = np.zeros((2, N // 2), dtype=np.int64)
+        slots[0, :DIM] = X[b]
+        slots[0, DIM:2 * DIM] = X[b]
+        cts.append(oq.encrypt(10 + b, T_PLAIN, sq, enc.encode(slots)))
+    ct = np.stack(cts)
+    diag = torch.empty((DIM, Lq, N), dtype=torch.int64, device="cuda")
+    ar = np.arange(DIM)
+    for d in range(DIM):
+        g = d // BABY
+        slots = np.zeros((2, N // 2), dtype=np.int64)
+        slots[0, :DIM] = W[ar, (ar + d) % DIM]
+        slots = np.roll(slots, g * BABY, axis=1)
+        diag[d] = dev(to_rns_eval(oq, enc.encode(slots)))
+    baby_keys = [dev(o.keygen_galois_grouped(K, 100 + b, T_PLAIN, s, o.galois_elt(b))) for b in range(1, BABY)]
+    gkb = dev(o.keygen_galois_grouped(K, 3, T_PLAIN, s, o.galois_elt(BABY)))
+    out = torch.empty((B, 2, Lq, N), dtype=torch.int64, device="cuda")
+    dp.linear_bsgs_grouped(ctx, ctx_q, K, dev(ct), diag, baby_keys, gkb, BABY, out, B, T_PLAIN)
+    res = host(out).reshape(B, 2, Lq, N)
+
+    def noise_bits(o_, s_, c):
+        ph = o_.phase(s_, c)
+        Q = 1
+        for q in o_.moduli:
+            Q *= q
+        coef = [(Q // q) * pow(Q // q, -1, q) for q in o_.moduli]
+        worst = 0
+        for n in range(0, N, 257):
+            v = sum(int(ph[l][n]) * coef[l] for l in range(len(o_.moduli))) % Q
+            worst = max(worst, min(v, Q - v))
+        return worst.bit_length()
+
+    for b in range(B):
+        y = enc.decode(oq.decrypt(sq, res[b], T_PLAIN))[0, :DIM].astype(np.int64)
+        assert np.array_equal(np.where(y > T_PLAIN // 2, y - T_PLAIN, y), W @ X[b])
+    # the per-limb-digit layer on the same ciphertext moduli, for the noise comparison
+    bv_keys = [dev(oq.keygen_galois(100 + b, T_PLAIN, sq, oq.galois_elt(b))) for b in range(1, BABY)]
+    bv_out = torch.empty_like(out)
+    ctx_q.linear_bsgs(dev(ct), diag, bv_keys, dev(oq.keygen_galois(3, T_PLAIN, sq, oq.galois_elt(BABY))), BABY, bv_out, B)
+    bv = host(bv_out).reshape(B, 2, Lq, N)
+    assert noise_bits(oq, sq, res[0]) + 20 < noise_bits(oq, sq, bv[0])
+    ctx.close()
+    ctx_q.close()

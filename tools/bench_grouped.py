@@ -71,4 +71,35 @@ for K in (1, 2):
     sweep["K=%d" % K] = row
     c.close()
 res["rotation_sweep_26x%d" % RB] = sweep
+# BASELINE.json config 4's layer (768 x 768, 32 baby x 24 giant steps) with special-prime keys: hoisted baby steps, fused inner products on
+# the ciphertext moduli, 23 giant-step rotations (deeppowers_b200.linear_bsgs_grouped), next to the per-limb-digit composition
+LB = int(os.environ.get("LAYER_BATCH", "256"))
+layer = {}
+for K in (0, 1, 2):
+    L = LQ + K
+    c = dp.Context(LOG_N, L)
+    cq = dp.Context(LOG_N, LQ, c.moduli[:LQ])
+    x = torch.empty((LB, 2, LQ, N), dtype=torch.int64, device="cuda"); cq.fill_uniform(1, x, 2 * LB)
+    diags = torch.empty((768, LQ, N), dtype=torch.int64, device="cuda"); cq.fill_uniform(2, diags, 768)
+    dn = c.grouped_digits(K) if K else LQ
+    keys = []
+    for r in range(32):
+        k = torch.empty((dn, 2, L, N), dtype=torch.int64, device="cuda"); c.fill_uniform(200 + r, k, 2 * dn); keys.append(k)
+    out = torch.empty_like(x)
+    scratch = torch.empty((32 + 24 + 1, LB, 2, LQ, N), dtype=torch.int64, device="cuda")
+    if K:
+        fn = lambda: dp.linear_bsgs_grouped(c, cq, K, x, diags, keys[:31], keys[31], 32, out, LB, 65537, scratch)
+    else:
+        fn = lambda: c.linear_bsgs(x, diags, keys[:31], keys[31], 32, out, LB, scratch)
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    layer["per-limb digits" if K == 0 else "K=%d" % K] = {"ms_per_batch": ms, "prompts_per_s": LB / ms * 1e3}
+    del scratch, keys, diags
+    c.close(); cq.close()
+res["config4_layer_batch%d" % LB] = layer
 print(json.dumps({"workload": "ct x ct + relinearise with special primes, N=8192, 4 ciphertext limbs, batch=%d, t=65537" % BATCH, "results": res}))
