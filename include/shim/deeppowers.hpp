@@ -75,6 +75,7 @@ public:
         config_["fhe.log_n"] = "13";
         config_["fhe.n_limbs"] = "4";
         config_["fhe.device"] = "0";
+        config_["fhe.plain_modulus"] = "0";   // BGV plaintext modulus of special-prime key switching (0: plain rounding)
         config_["fhe.devices"] = "one";   // "all": shard every encrypted batch over all visible GPUs (dpfhe_multi_*)
     }
 
@@ -170,6 +171,8 @@ private:
         std::vector<std::uint64_t> a, b, k;
         const fhe::WireHeader ha = fhe::read_wire_file(fa, a), hb = fhe::read_wire_file(fb, b), hk = fhe::read_wire_file(fk, k);
         fhe::Evaluator &ev = fhe_evaluator();
+        if (hk.kind == (std::uint32_t)fhe::WireKind::HybridSwitchKey || hk.kind == (std::uint32_t)fhe::WireKind::GroupedSwitchKey)
+            return run_special_prime_job(ev, ha, hb, hk, a, b, k, fo, t0);
         if (ha.kind != (std::uint32_t)fhe::WireKind::Ciphertexts || hb.kind != ha.kind || hk.kind != (std::uint32_t)fhe::WireKind::SwitchKey)
             throw std::runtime_error("fhe job: wrong file kinds");
         if (ha.log_n != hb.log_n || ha.n_limbs != hb.n_limbs || ha.count != hb.count || ha.n_limbs != ev.limbs() ||
@@ -196,6 +199,37 @@ private:
         std::ostringstream msg;
         msg << "wrote " << fo << ": " << ha.count << " ciphertext products (N=" << ev.poly_degree() << ", L=" << ev.limbs() << ", " << devices
             << (devices == 1 ? " GPU)" : " GPUs)");
+        r.texts.push_back(msg.str());
+        r.stop_reasons = std::vector<std::string>{"fhe_job_done"};
+        return r;
+    }
+
+    // relinearisation key with special primes (wire kinds 4 and 5): the evaluator's basis is the key's (ciphertext moduli + K special
+    // primes), the ciphertext files carry the first limbs() - K moduli; set_config("fhe.plain_modulus", t) selects the BGV rounding
+    GenerationResult run_special_prime_job(fhe::Evaluator &ev, const fhe::WireHeader &ha, const fhe::WireHeader &hb, const fhe::WireHeader &hk,
+                                           const std::vector<std::uint64_t> &a, const std::vector<std::uint64_t> &b, const std::vector<std::uint64_t> &k,
+                                           const std::string &fo, std::chrono::steady_clock::time_point t0) {
+        const unsigned special = hk.kind == (std::uint32_t)fhe::WireKind::HybridSwitchKey ? 1u : (unsigned)hk.count;
+        if (ha.kind != (std::uint32_t)fhe::WireKind::Ciphertexts || hb.kind != ha.kind) throw std::runtime_error("fhe job: wrong file kinds");
+        if (hk.n_limbs != ev.limbs() || (std::size_t(1) << hk.log_n) != ev.poly_degree() || ha.log_n != hk.log_n || hb.log_n != hk.log_n ||
+            ha.n_limbs + special != hk.n_limbs || hb.n_limbs != ha.n_limbs || ha.count != hb.count)
+            throw std::runtime_error("fhe job: parameter mismatch between files and evaluator");
+        for (unsigned l = 0; l < ev.limbs(); ++l)
+            if (hk.moduli[l] != ev.modulus(l) || (l < ha.n_limbs && (ha.moduli[l] != ev.modulus(l) || hb.moduli[l] != ev.modulus(l))))
+                throw std::runtime_error("fhe job: moduli differ from the evaluator's");
+        const std::size_t ct_words = 2 * (std::size_t)ha.n_limbs * ev.poly_degree();
+        if (a.size() != ha.count * ct_words || b.size() != a.size() ||
+            k.size() != std::size_t(2) * ev.grouped_digits(special) * ev.limbs() * ev.poly_degree())
+            throw std::runtime_error("fhe job: payload sizes do not match the headers");
+        const std::uint64_t t = std::stoull(get_config("fhe.plain_modulus"));
+        std::vector<std::uint64_t> out(a.size());
+        ev.multiply_relin_grouped(special, {a.data(), (std::size_t)ha.count}, {b.data(), (std::size_t)ha.count}, k.data(), {out.data(), (std::size_t)ha.count}, t);
+        fhe::write_wire_file(fo, ha, out.data());
+        GenerationResult r;
+        r.generation_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::ostringstream msg;
+        msg << "wrote " << fo << ": " << ha.count << " ciphertext products (N=" << ev.poly_degree() << ", " << ha.n_limbs << " limbs + " << special
+            << " special prime" << (special == 1 ? "" : "s") << ", 1 GPU)";
         r.texts.push_back(msg.str());
         r.stop_reasons = std::vector<std::string>{"fhe_job_done"};
         return r;

@@ -105,6 +105,32 @@ def test_model_api_encrypted_route_matches_oracle(tmp_path, oracle_mod):
     assert np.array_equal(data.reshape(a.shape), o.ct_mul_relin(a, b, evk))
 
 
+@pytest.mark.gpu
+def test_model_api_encrypted_route_with_special_prime_keys(tmp_path, oracle_mod):
+    """the same Model API route with a grouped relinearisation key file (wire kind 5, two special primes) and a hybrid one (kind 4)"""
+    from deeppowers_b200 import wire
+    exe = str(tmp_path / "encrypted_job")
+    _link(os.path.join(ROOT, "examples", "encrypted_job.cpp"), exe)
+    log_n, B, t = 12, 4, 65537
+    for L, K, kind in ((6, 2, wire.GROUPED_SWITCH_KEY), (4, 1, wire.HYBRID_SWITCH_KEY)):
+        o = oracle_mod.Oracle(log_n, L)
+        Lq = L - K
+        oq = oracle_mod.Oracle(log_n, Lq, o.moduli[:Lq])
+        s = o.keygen_secret(1)
+        evk = o.keygen_relin_grouped(K, 2, t, s)
+        a = oq.fill_uniform(3, 2 * B).reshape(B, 2, Lq, o.N)
+        b = oq.fill_uniform(4, 2 * B).reshape(B, 2, Lq, o.N)
+        fa, fb, fk, fo = (str(tmp_path / (n + str(K))) for n in ("a.dpfhe", "b.dpfhe", "k.dpfhe", "o.dpfhe"))
+        wire.write(fa, log_n, Lq, wire.CIPHERTEXTS, B, oq.moduli, a)
+        wire.write(fb, log_n, Lq, wire.CIPHERTEXTS, B, oq.moduli, b)
+        wire.write(fk, log_n, L, kind, K if kind == wire.GROUPED_SWITCH_KEY else 1, o.moduli, evk)
+        r = subprocess.run([exe, fa, fb, fk, fo, str(log_n), str(L), "one", str(t)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "special prime" in r.stdout, r.stderr
+        hdr, data = wire.read(fo)
+        assert hdr["count"] == B and hdr["n_limbs"] == Lq
+        assert np.array_equal(data.reshape(a.shape), o.ct_mul_relin_grouped(K, a, b, evk, t))
+
+
 def test_wire_reader_rejects_forged_headers(tmp_path, oracle_mod):
     """A header is untrusted input: a count that wraps the size computation, a count larger than the file, an
     unknown kind or trailing bytes must all be refused by the C++ reader the shim uses (include/dpfhe_wire.hpp)."""
