@@ -131,6 +131,22 @@ int dpfhe_multi_ct_mul_relin_host(dpfhe_multi *m, const uint64_t *h_a, const uin
     });
 }
 
+// special-prime key switching (dpfhe_ct_mul_relin_grouped_host) sharded the same way: ciphertexts carry L - n_special limbs
+int dpfhe_multi_ct_mul_relin_grouped_host(dpfhe_multi *m, unsigned n_special, const uint64_t *h_a, const uint64_t *h_b, const uint64_t *h_evk,
+                                          uint64_t *h_out, size_t batch, uint64_t t_plain) {
+    if (!m || m->ctx.empty()) return dpfhe_fail(DPFHE_ERR_INVALID, "null multi-device context");
+    if (batch == 0) return DPFHE_OK;
+    if (!h_a || !h_b || !h_evk || !h_out) return dpfhe_fail(DPFHE_ERR_INVALID, "null host pointer");
+    if (n_special < 1 || n_special >= m->ctx[0]->hp.L) return dpfhe_fail(DPFHE_ERR_INVALID, "n_special must be at least 1 and below the context's limbs");
+    const size_t ct_words = 2 * (m->ctx[0]->hp.L - n_special) * m->ctx[0]->N();
+    return for_each_device(m, [&](size_t r) {
+        size_t first, count;
+        shard_of(batch, m->ctx.size(), r, &first, &count);
+        return dpfhe_ct_mul_relin_grouped_host(m->ctx[r], n_special, h_a + first * ct_words, h_b + first * ct_words, h_evk, h_out + first * ct_words, count,
+                                               t_plain);
+    });
+}
+
 int dpfhe_multi_rotate_host(dpfhe_multi *m, const uint64_t *h_ct, uint64_t galois_elt, const uint64_t *h_gk, uint64_t *h_out, size_t batch) {
     if (!m || m->ctx.empty()) return dpfhe_fail(DPFHE_ERR_INVALID, "null multi-device context");
     if (batch == 0) return DPFHE_OK;

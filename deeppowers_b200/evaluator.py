@@ -483,6 +483,12 @@ class MultiContext:
     def ct_mul_relin_host(self, a, b, evk, out):
         self._chk(self._l.dpfhe_multi_ct_mul_relin_host(self._h, _hptr(a), _hptr(b), _hptr(evk), _hptr(out, True), a.size // (2 * self.P)))
 
+    def ct_mul_relin_grouped_host(self, n_special, a, b, evk, out, t_plain=0):
+        """special-prime key switching sharded over the devices; a, b, out: [batch][2][L - n_special][N] host arrays"""
+        pq = 2 * (self.L - n_special) * self.N
+        self._chk(self._l.dpfhe_multi_ct_mul_relin_grouped_host(self._h, int(n_special), _hptr(a), _hptr(b), _hptr(evk), _hptr(out, True), a.size // pq,
+                                                                int(t_plain)))
+
     def rotate_host(self, ct, galois_elt, gk, out):
         self._chk(self._l.dpfhe_multi_rotate_host(self._h, _hptr(ct), int(galois_elt), _hptr(gk), _hptr(out, True), ct.size // (2 * self.P)))
 

@@ -280,6 +280,13 @@ public:
         if (a.count != b.count || a.count != out.count) throw std::runtime_error("ciphertext batches must have the same count");
         check(dpfhe_multi_ct_mul_relin_host(m_, a.data, b.data, relin_key, out.data, a.count));
     }
+    // the same with a special-prime relinearisation key (digits of `special` limbs, `special` special primes; batches hold
+    // limbs() - special limbs)
+    void multiply_relin_grouped(unsigned special, ConstCiphertextBatch a, ConstCiphertextBatch b, const std::uint64_t *relin_key, CiphertextBatch out,
+                                std::uint64_t plain_modulus = 0) {
+        if (a.count != b.count || a.count != out.count) throw std::runtime_error("ciphertext batches must have the same count");
+        check(dpfhe_multi_ct_mul_relin_grouped_host(m_, special, a.data, b.data, relin_key, out.data, a.count, plain_modulus));
+    }
     // device buffers: a[r], b[r], relin_key[r] on device r (shard r of the batch); the whole result on device `root`
     void multiply_relin_gather_device(const std::vector<const std::uint64_t *> &a, const std::vector<const std::uint64_t *> &b,
                                       const std::vector<const std::uint64_t *> &relin_key, std::uint64_t *out_on_root, int root, std::size_t count) {

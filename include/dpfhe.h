@@ -272,6 +272,9 @@ int dpfhe_multi_shard(const dpfhe_multi *m, size_t batch, int index, size_t *fir
 /* host buffers [batch][2][L][N]: every device pipelines its own shard (H2D, compute, D2H) — no gather needed */
 int dpfhe_multi_ct_mul_relin_host(dpfhe_multi *m, const uint64_t *h_a, const uint64_t *h_b, const uint64_t *h_evk,
                                   uint64_t *h_out, size_t batch);
+/* the special-prime form (dpfhe_ct_mul_relin_grouped_host) sharded the same way; ciphertexts carry L - n_special limbs */
+int dpfhe_multi_ct_mul_relin_grouped_host(dpfhe_multi *m, unsigned n_special, const uint64_t *h_a, const uint64_t *h_b,
+                                          const uint64_t *h_evk, uint64_t *h_out, size_t batch, uint64_t t_plain);
 int dpfhe_multi_rotate_host(dpfhe_multi *m, const uint64_t *h_ct, uint64_t galois_elt, const uint64_t *h_gk,
                             uint64_t *h_out, size_t batch);
 /* device buffers: d_a[r], d_b[r] = shard r of the operands and d_evk[r] = the key, all on device r; the whole result

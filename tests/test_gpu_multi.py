@@ -196,3 +196,22 @@ def test_gather_across_processes_through_ipc(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29731", str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "IPC_GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_multi_grouped_host_shards_equal_oracle(dp, oracle_mod):
+    """special-prime key switching sharded over the devices (dpfhe_multi_ct_mul_relin_grouped_host): every device list gives the
+    oracle's bits, ragged shards included"""
+    log_n, L, K, batch, t = 12, 6, 2, 11, 65537
+    o = oracle_mod.Oracle(log_n, L)
+    Lq = L - K
+    oq = oracle_mod.Oracle(log_n, Lq, o.moduli[:Lq])
+    a = oq.fill_uniform(3, 2 * batch).reshape(batch, 2, Lq, o.N)
+    b = oq.fill_uniform(4, 2 * batch).reshape(batch, 2, Lq, o.N)
+    key = o.fill_uniform(5, 2 * o.grouped_digits(K)).reshape(-1, 2, L, o.N)
+    exp = o.ct_mul_relin_grouped(K, a, b, key, t)
+    for devices in device_lists():
+        m = dp.MultiContext(log_n, L, devices=devices)
+        out = np.zeros_like(a)
+        m.ct_mul_relin_grouped_host(K, a, b, key, out, t)
+        assert np.array_equal(out, exp), devices
+        m.close()
