@@ -859,6 +859,14 @@ DPFHE_HD void hoistg_phase2(CTA &cta, u64 *buf, const HoistGArgs &A, const Group
     hoist_phase2_core<LOGN, NT, 4>(cta, buf, tw, p, load, A.U + ((ct * G.dnum + g) * L + i) * N);
 }
 
+// CB ciphertexts ct0 .. ct0+n_ct-1 (n_ct <= CB) share every key chunk they multiply with.  PF: the operands of digit
+// j + 1 (gathered transforms and key chunks) are requested before the arithmetic of digit j, which is what this
+// latency-bound loop needs (measured: sharing key chunks between ciphertexts does not help, more loads in flight do).
+template <int CB>
+struct RotOperands {
+    U64x2 vb, vbs, va, vas, u[CB];
+};
+
 // one rotation applied to the shared lifts: acc[ct][c][i] = [i < Lq, c = 0] P * perm(c0[i]) + sum_g perm(U[ct][g][i]) o key[g][c][i]
 // for all L limbs, canonical; the division by P (md_tau / md_limb kernels) then yields (perm(c0) + ks0, ks1).
 struct RotApplyGArgs {
@@ -891,34 +899,52 @@ DPFHE_HD void rot_apply_grouped_rows(CTA &cta, const RotApplyGArgs &A, const Gro
                 r.y = swap ? v.x : v.y;
                 return r;
             };
+            // the operands of digit d + 1 (key chunks and gathered rows) are requested before the arithmetic of digit d: the loop
+            // is bound by the latency of the gathers (ncu: long-scoreboard stalls), as in rot_apply_rows
+            auto fetch = [&](u32 d, RotOperands<CB> &o) {
+                const size_t kb = ((size_t)d * 2 + 0) * P + (size_t)i * N, ka = ((size_t)d * 2 + 1) * P + (size_t)i * N;
+                o.vb = ld_keep(reinterpret_cast<const U64x2 *>(A.key + kb) + c);
+                o.vbs = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + kb) + c);
+                o.va = ld_keep(reinterpret_cast<const U64x2 *>(A.key + ka) + c);
+                o.vas = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + ka) + c);
+#pragma unroll
+                for (int b = 0; b < CB; ++b) {
+                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);   // rows past the end repeat the last one, not stored
+                    o.u[b] = gather(A.U + ((ct * D + d) * L + i) * N);
+                }
+            };
             U64x2 r0[CB], r1[CB];
+            auto mac = [&](const RotOperands<CB> &o, bool trim) {
+#pragma unroll
+                for (int b = 0; b < CB; ++b) {
+                    r0[b].x += shoup_lazy(o.u[b].x, o.vb.x, o.vbs.x, p);
+                    r0[b].y += shoup_lazy(o.u[b].y, o.vb.y, o.vbs.y, p);
+                    r1[b].x += shoup_lazy(o.u[b].x, o.va.x, o.vas.x, p);
+                    r1[b].y += shoup_lazy(o.u[b].y, o.va.y, o.vas.y, p);
+                    if (trim) {
+                        r0[b].x = csub(r0[b].x, p.q8); r0[b].y = csub(r0[b].y, p.q8);
+                        r1[b].x = csub(r1[b].x, p.q8); r1[b].y = csub(r1[b].y, p.q8);
+                    }
+                }
+            };
+            RotOperands<CB> oa, ob;
+            fetch(0, oa);
 #pragma unroll
             for (int b = 0; b < CB; ++b) {
                 r0[b].x = r0[b].y = r1[b].x = r1[b].y = 0;
                 if (limb) {
-                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);   // rows past the end repeat the last one, not stored
+                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);
                     const U64x2 s0 = gather(A.ct + ct * 2 * Pq + (size_t)i * N);
                     r0[b].x = shoup_lazy(s0.x, pm, pm_s, p);   // < SB*q
                     r0[b].y = shoup_lazy(s0.y, pm, pm_s, p);
                 }
             }
-            for (u32 d = 0; d < D; ++d) {
-                const size_t kb = ((size_t)d * 2 + 0) * P + (size_t)i * N, ka = ((size_t)d * 2 + 1) * P + (size_t)i * N;
-                const U64x2 vb = ld_keep(reinterpret_cast<const U64x2 *>(A.key + kb) + c), vbs = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + kb) + c);
-                const U64x2 va = ld_keep(reinterpret_cast<const U64x2 *>(A.key + ka) + c), vas = ld_keep(reinterpret_cast<const U64x2 *>(A.key_s + ka) + c);
-                const bool trim = acc_trim_after(SB, (int)d);
-#pragma unroll
-                for (int b = 0; b < CB; ++b) {
-                    const size_t ct = ct0 + ((u32)b < n_ct ? (u32)b : n_ct - 1);
-                    const U64x2 u = gather(A.U + ((ct * D + d) * L + i) * N);
-                    r0[b].x += shoup_lazy(u.x, vb.x, vbs.x, p);
-                    r0[b].y += shoup_lazy(u.y, vb.y, vbs.y, p);
-                    r1[b].x += shoup_lazy(u.x, va.x, vas.x, p);
-                    r1[b].y += shoup_lazy(u.y, va.y, vas.y, p);
-                    if (trim) {
-                        r0[b].x = csub(r0[b].x, p.q8); r0[b].y = csub(r0[b].y, p.q8);
-                        r1[b].x = csub(r1[b].x, p.q8); r1[b].y = csub(r1[b].y, p.q8);
-                    }
+            for (u32 d = 0; d < D; d += 2) {
+                if (d + 1 < D) fetch(d + 1, ob);
+                mac(oa, acc_trim_after(SB, (int)d));
+                if (d + 1 < D) {
+                    if (d + 2 < D) fetch(d + 2, oa);
+                    mac(ob, acc_trim_after(SB, (int)d + 1));
                 }
             }
 #pragma unroll
@@ -948,13 +974,6 @@ struct RotApplyArgs {
     u32 L, galois;
 };
 
-// CB ciphertexts ct0 .. ct0+n_ct-1 (n_ct <= CB) share every key chunk they multiply with.  PF: the operands of digit
-// j + 1 (gathered transforms and key chunks) are requested before the arithmetic of digit j, which is what this
-// latency-bound loop needs (measured: sharing key chunks between ciphertexts does not help, more loads in flight do).
-template <int CB>
-struct RotOperands {
-    U64x2 vb, vbs, va, vas, u[CB];
-};
 
 template <int LOGN, int NT, int CB, bool PF, class CTA>
 DPFHE_HD void rot_apply_rows(CTA &cta, const RotApplyArgs &A, const LimbParams &p, size_t ct0, u32 n_ct, u32 i, int c_lo = 0,
