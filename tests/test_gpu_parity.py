@@ -74,6 +74,26 @@ def test_ntt_fwd_inv(ctxs, log_n, L, n_polys):
     assert np.array_equal(host(d).reshape(x.shape), x)
 
 
+@pytest.mark.parametrize("log_n,L,n_polys", [(12, 2, 5), (13, 4, 9)])
+def test_ntt_inv_thread_copy_and_tma_paths(dp, oracle_mod, monkeypatch, log_n, L, n_polys):
+    """the inverse transform fetches its limb through a TMA tensor map by default and by thread copies with DPFHE_NTT_TMA=0:
+    both must give the oracle's bits (and an offset, unaligned-to-the-allocation view exercises the tensor map's base address)"""
+    o = oracle_mod.Oracle(log_n, L)
+    x = edge_polys(o, n_polys, 0xD3390011)
+    exp = o.ntt_inv(x)
+    for env in ("1", "0"):
+        monkeypatch.setenv("DPFHE_NTT_TMA", env)
+        c = dp.Context(log_n, L)
+        big = torch.zeros((n_polys + 1, L, o.N), dtype=torch.int64, device="cuda")
+        d = big[1:]                                   # starts one polynomial into the allocation
+        d.copy_(dev(x))
+        c.ntt_inv(d, n_polys)
+        assert np.array_equal(host(d).reshape(x.shape), exp), env
+        assert int(big[0].abs().sum()) == 0           # nothing written before the view
+        c.close()
+    monkeypatch.delenv("DPFHE_NTT_TMA")
+
+
 def test_ntt_custom_moduli(ctxs, oracle_mod):
     # 50-bit and 36-bit NTT-friendly primes exercise the generic Barrett / word-reduce constants
     mods = []
