@@ -569,10 +569,14 @@ DPFHE_HD void ks_phase2_group(CTA &cta, u64 *buf, const KsArgs &A, const GroupCo
     auto get = [&](int c) {
         U64x2 r;
         r.x = r.y = 0;
-        for (u32 j = lo; j < hi; ++j) {   // each term below 2q; at most KS_MAX_SPECIAL = 4 of them
+        for (u32 j = lo; j < hi; ++j) {   // each term below SB*q = 4q; at most KS_MAX_SPECIAL = 4 of them: the sum stays below 16q
             const U64x2 v = ld_cg(reinterpret_cast<const U64x2 *>(t_rows + (size_t)j * t_stride) + c);
-            r.x += csub(shoup_lazy(v.x, G.up[j][i], G.up_s[j][i], p), p.q2);
-            r.y += csub(shoup_lazy(v.y, G.up[j][i], G.up_s[j][i], p), p.q2);
+            r.x += shoup_lazy(v.x, G.up[j][i], G.up_s[j][i], p);
+            r.y += shoup_lazy(v.y, G.up[j][i], G.up_s[j][i], p);
+        }
+        if (hi - lo > 2) {   // < 16q -> < 8q
+            r.x = csub(r.x, p.q8);
+            r.y = csub(r.y, p.q8);
         }
         r.x = csub(r.x, p.q4);   // < 8q  ->  < 4q
         r.y = csub(r.y, p.q4);
@@ -696,12 +700,18 @@ DPFHE_HD void ms_limb_group(CTA &cta, u64 *buf, const u64 *tau_rows, size_t tau_
     auto lift = [&](int c) {
         U64x2 r;
         r.x = r.y = 0;
-        for (u32 k = 0; k < G.K; ++k) {   // each term below 3q; at most four of them
+        const bool slim = G.K <= 3;   // terms below SB*q + q = 5q: three of them stay below 16q, four need the per-term reduction (3q each)
+        for (u32 k = 0; k < G.K; ++k) {
             const U64x2 v = ld_cg(reinterpret_cast<const U64x2 *>(tau_rows + (size_t)k * tau_stride) + c);
-            r.x += csub(shoup_lazy(v.x, G.dn[k][i], G.dn_s[k][i], p), p.q2) + (v.x > G.half[k] ? neg_p : 0);
-            r.y += csub(shoup_lazy(v.y, G.dn[k][i], G.dn_s[k][i], p), p.q2) + (v.y > G.half[k] ? neg_p : 0);
+            u64 tx = shoup_lazy(v.x, G.dn[k][i], G.dn_s[k][i], p), ty = shoup_lazy(v.y, G.dn[k][i], G.dn_s[k][i], p);
+            if (!slim) {
+                tx = csub(tx, p.q2);
+                ty = csub(ty, p.q2);
+            }
+            r.x += tx + (v.x > G.half[k] ? neg_p : 0);
+            r.y += ty + (v.y > G.half[k] ? neg_p : 0);
         }
-        r.x = csub(csub(r.x, p.q8), p.q4);   // < 12q  ->  < 4q
+        r.x = csub(csub(r.x, p.q8), p.q4);   // < 16q  ->  < 4q
         r.y = csub(csub(r.y, p.q8), p.q4);
         return r;
     };
@@ -841,10 +851,14 @@ DPFHE_HD void hoistg_phase2(CTA &cta, u64 *buf, const HoistGArgs &A, const Group
     auto get = [&](int c) {
         U64x2 r;
         r.x = r.y = 0;
-        for (u32 j = lo; j < hi; ++j) {
+        for (u32 j = lo; j < hi; ++j) {   // bounds as in ks_phase2_group
             const U64x2 v = ld_cg(reinterpret_cast<const U64x2 *>(t_rows + (size_t)j * t_stride) + c);
-            r.x += csub(shoup_lazy(v.x, G.up[j][i], G.up_s[j][i], p), p.q2);
-            r.y += csub(shoup_lazy(v.y, G.up[j][i], G.up_s[j][i], p), p.q2);
+            r.x += shoup_lazy(v.x, G.up[j][i], G.up_s[j][i], p);
+            r.y += shoup_lazy(v.y, G.up[j][i], G.up_s[j][i], p);
+        }
+        if (hi - lo > 2) {
+            r.x = csub(r.x, p.q8);
+            r.y = csub(r.y, p.q8);
         }
         r.x = csub(r.x, p.q4);
         r.y = csub(r.y, p.q4);
