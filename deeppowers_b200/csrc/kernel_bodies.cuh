@@ -460,7 +460,10 @@ DPFHE_HD void ks_phase2_core(CTA &cta, u64 *buf, const KsArgs &A, const LimbPara
     // lazy accumulator bound: below (2 SB + 1) q after phase 1 (0 for the special limb), + SB*q per digit; trimmed
     // with one csub(8q) whenever the next digit could pass 16q
     constexpr int B0 = 2 * SB + 1;
-    const bool trim = SPECIAL ? acc_trim_after(0, (int)jj) : acc_trim_after(B0, (int)jj - 1), last = !HYB && jj + 1 == n_digits;
+    // no trim after the final digit: nothing is added any more, and whoever reads the accumulator next (canon below, the division
+    // step of the special-prime variants) accepts any value below 16q
+    const bool final_digit = jj + 1 == n_digits, last = !HYB && final_digit;
+    const bool trim = !final_digit && (SPECIAL ? acc_trim_after(0, (int)jj) : acc_trim_after(B0, (int)jj - 1));
     const bool first = SPECIAL && jj == 0;
     struct MacOperands {
         U64x2 vb, va, vbs, vas, r0, r1;
@@ -955,10 +958,10 @@ DPFHE_HD void rot_apply_grouped_rows(CTA &cta, const RotApplyGArgs &A, const Gro
             }
             for (u32 d = 0; d < D; d += 2) {
                 if (d + 1 < D) fetch(d + 1, ob);
-                mac(oa, acc_trim_after(SB, (int)d));
+                mac(oa, d + 1 < D && acc_trim_after(SB, (int)d));   // no trim after the last digit: canon takes any value below 16q
                 if (d + 1 < D) {
                     if (d + 2 < D) fetch(d + 2, oa);
-                    mac(ob, acc_trim_after(SB, (int)d + 1));
+                    mac(ob, d + 2 < D && acc_trim_after(SB, (int)d + 1));
                 }
             }
 #pragma unroll
@@ -1050,11 +1053,11 @@ DPFHE_HD void rot_apply_rows(CTA &cta, const RotApplyArgs &A, const LimbParams &
             }
             for (u32 j = 0; j < L; j += 2) {
                 if (PF && j + 1 < L) fetch(j + 1, ob);
-                mac(oa, acc_trim_after(2, (int)j));
+                mac(oa, j + 1 < L && acc_trim_after(2, (int)j));   // no trim after the last digit: canon takes any value below 16q
                 if (j + 1 < L) {
                     if (!PF) fetch(j + 1, ob);
                     if (PF && j + 2 < L) fetch(j + 2, oa);
-                    mac(ob, acc_trim_after(2, (int)j + 1));
+                    mac(ob, j + 2 < L && acc_trim_after(2, (int)j + 1));
                     if (!PF && j + 2 < L) fetch(j + 2, oa);
                 }
             }
