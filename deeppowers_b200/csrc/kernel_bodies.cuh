@@ -104,8 +104,8 @@ DPFHE_HD void ntt_fwd_body(CTA &cta, u64 *buf, u64 *data, const Twiddle *tw, con
     cta.par([&](int tid) {
         for (int c = tid; c < (1 << (LOGN - 1)); c += NT) {
             U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(c)];
-            v.x = canon(v.x, p);
-            v.y = canon(v.y, p);
+            v.x = canon_store(v.x, p);
+            v.y = canon_store(v.y, p);
             st_stream(dst + c, v);
         }
     });

@@ -252,6 +252,15 @@ DPFHE_HD u64 canon(u64 x, const LimbParams &p) {
     r = csub(r, p.q2);
     return csub(r, p.q);
 }
+// canon for a modulus with floor(2^64 / q) == 16, i.e. q > 2^64 / 17 (the default basis and any other modulus within 6 % of 2^60):
+// the quotient estimate is then k = x >> 60 without a multiplication, and x/q - x/2^60 = x (2^60 - q) / (q 2^60) < 16 (2^60 - q) / q
+// < 1, so floor(x/q) - k is 0 or 1: x - k q < 2q for ANY 64-bit x and ONE conditional subtraction finishes.  Used by the store loop
+// of the forward transform, where the uniform branch is hoisted out of the loop (+2.5 % on the transform); inside the fused
+// kernels the second code path costs more in register pressure than it saves.
+DPFHE_HD bool canon_near60_applies(const LimbParams &p) { return p.mu32 == 16u; }
+DPFHE_HD u64 canon_near60(u64 x, const LimbParams &p) { return csub(sub_mul_q(x, x >> 60, p), p.q); }
+// uniform branch per value (the limb constants sit in the constant bank)
+DPFHE_HD u64 canon_store(u64 x, const LimbParams &p) { return canon_near60_applies(p) ? canon_near60(x, p) : canon(x, p); }
 // x < 4q -> [0, q)
 DPFHE_HD u64 canon4(u64 x, const LimbParams &p) { return csub(csub(x, p.q2), p.q); }
 

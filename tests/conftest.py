@@ -173,7 +173,7 @@ def _build_emu(variant):
     lib.emu_mod_down_special.argtypes = [C.c_void_p, C.c_uint, _u64p, _u64p, C.c_size_t, C.c_uint64]
     lib.emu_rotate_hoisted_grouped.argtypes = [C.c_void_p, C.c_uint, _u64p, C.c_size_t, _u64p, _u64p, _u64p, C.c_size_t, C.c_uint64]
     lib.emu_mod_switch.argtypes = [C.c_void_p, _u64p, _u64p, C.c_size_t, C.c_uint64]
-    for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("mulmod_lazy", 2), ("barrett_long", 2), ("pti_fold", 4),
+    for nm, nargs in (("mulmod", 2), ("word_reduce", 1), ("canon", 1), ("canon_store", 1), ("mulmod_lazy", 2), ("barrett_long", 2), ("pti_fold", 4),
                       ("shoup_lazy", 2), ("shoup_exact", 2)):
         f = getattr(lib, "emu_" + nm)
         f.restype = C.c_uint64

@@ -606,6 +606,8 @@ int emu_mod_switch(void *h, const uint64_t *in, uint64_t *out, size_t n_polys, u
 uint64_t emu_mulmod(void *h, unsigned l, uint64_t a, uint64_t b) { return mulmod(a, b, ((Emu *)h)->lp[l]); }
 uint64_t emu_word_reduce(void *h, unsigned l, uint64_t x) { return word_reduce(x, ((Emu *)h)->lp[l]); }
 uint64_t emu_canon(void *h, unsigned l, uint64_t x) { return canon(x, ((Emu *)h)->lp[l]); }
+// the one-subtraction form where it applies (moduli above 2^64 / 17), else the general one: what ntt_fwd_body's store loop runs
+uint64_t emu_canon_store(void *h, unsigned l, uint64_t x) { return canon_store(x, ((Emu *)h)->lp[l]); }
 uint64_t emu_mulmod_lazy(void *h, unsigned l, uint64_t a, uint64_t b) { return mulmod_lazy(a, b, ((Emu *)h)->lp[l]); }
 // x * w through the Shoup forms (w < q; the companion is derived here)
 uint64_t emu_shoup_lazy(void *h, unsigned l, uint64_t x, uint64_t w) {

@@ -20,6 +20,35 @@ def test_host_params_match_oracle(make_emu, oracle_mod, log_n, L):
         assert np.array_equal(e.root_powers(l, inverse=True), o.inv_root_powers(l))
 
 
+def test_canon_shortcut_threshold(make_emu, oracle_mod):
+    """the forward transform's store loop canonicalises with ONE conditional subtraction when floor(2^64/q) == 16 (canon_near60:
+    k = x >> 60 is then at most one short): moduli on either side of 2^64/17, the largest modulus the context accepts, every
+    multiple of q +- 1 and the top of the 64-bit range"""
+    lib = oracle_mod.lib()
+    two_n = 2 << 12
+    thr = 2**64 // 17
+    above = thr - thr % two_n + two_n + 1
+    while not lib.dpo_is_prime(above):
+        above += two_n
+    below = thr - thr % two_n + 1
+    while not lib.dpo_is_prime(below):
+        below -= two_n
+    top = oracle_mod.Oracle(12, 1).moduli[0]
+    assert 2**64 // above == 16 and 2**64 // below == 17 and 2**64 // top == 16
+    e = make_emu(12, 3, [above, below, top], variant="gen")
+    for l, q in enumerate(e.moduli):
+        xs = {0, q - 1, 2**64 - 1, 2**64 - 2, 2**63, 2**60 - 1, 2**60, 2**60 + 1}
+        for m in range(1, 2**64 // q + 1):
+            xs.update(v for v in (m * q - 1, m * q, m * q + 1, m * 2**60 - 1, m * 2**60) if 0 <= v < 2**64)
+        for x in xs:
+            assert e.scalar("canon_store", l, x) == x % q, (q, x)      # takes ANY 64-bit value
+            if x < 16 * q:                                               # the documented domain of canon
+                assert e.scalar("canon", l, x) == x % q, (q, x)
+    o = oracle_mod.Oracle(12, 3, [above, below, top])                    # and the transform itself on such a basis
+    x = o.fill_uniform(9, 2)
+    assert np.array_equal(e.ntt(x), o.ntt_fwd(x))
+
+
 @pytest.mark.parametrize("variant", ["gen", "fast"])
 def test_device_scalar_arithmetic_bounds(make_emu, oracle_mod, variant):
     """modarith.cuh on adversarial inputs: every lazy routine stays inside its documented range (SB = 4: the quotient
