@@ -157,8 +157,8 @@ DPFHE_HD void ntt_fwd_half_finish(CTA &cta, u64 *buf, u64 *data, const Twiddle *
     cta.par([&](int tid) {
         for (int lc = tid; lc < HC; lc += NT) {
             U64x2 v = reinterpret_cast<const U64x2 *>(buf)[swz_chunk(lc)];
-            v.x = canon(v.x, p);
-            v.y = canon(v.y, p);
+            v.x = canon_store(v.x, p);
+            v.y = canon_store(v.y, p);
             st_stream(dst + lc, v);
         }
     });
