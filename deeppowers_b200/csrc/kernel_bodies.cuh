@@ -225,12 +225,26 @@ DPFHE_HD bool acc_trim_after(int b0, int step) {
 
 // tensor of one coefficient: canonical inputs; d0,d2 in [0,SB*q), d1 in [0,(SB+1)q)
 DPFHE_HD void tensor_coeff(u64 a0, u64 a1, u64 b0, u64 b1, const LimbParams &p, u64 &d0, u64 &d1, u64 &d2) {
+#if DPFHE_TENSOR_KARATSUBA
+    // three 128-bit products instead of four (the multiplier is the scarce unit): a0 b1 + a1 b0 =
+    // (a0 + a1)(b0 + b1) - a0 b0 - a1 b1 over the integers; the sums are below 2^61, every term fits 128 bits
+    u64 h0, l0, h2, l2, hk, lk;
+    mul128(a0, b0, h0, l0);
+    mul128(a1, b1, h2, l2);
+    mul128(a0 + a1, b0 + b1, hk, lk);
+    sub128(hk, lk, h0, l0);
+    sub128(hk, lk, h2, l2);
+    d0 = barrett_lazy(h0, l0, p);
+    d2 = barrett_lazy(h2, l2, p);
+    d1 = barrett_lazy(hk, lk, p);
+#else
     d0 = mulmod_lazy(a0, b0, p);
     d2 = mulmod_lazy(a1, b1, p);
     u64 hi, lo;
     mul128(a0, b1, hi, lo);
     mac128(hi, lo, a1, b0);
     d1 = barrett_lazy(hi, lo, p);
+#endif
 }
 
 // ---- fused key-switch family ------------------------------------------

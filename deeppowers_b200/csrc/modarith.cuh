@@ -207,6 +207,17 @@ DPFHE_HD void mul128(u64 a, u64 b, u64 &hi, u64 &lo) {
 #endif
 }
 
+// (hi:lo) -= (bh:bl), no borrow out expected
+DPFHE_HD void sub128(u64 &hi, u64 &lo, u64 bh, u64 bl) {
+#if defined(__CUDA_ARCH__)
+    asm("sub.cc.u64 %0, %0, %2;\n\tsubc.u64 %1, %1, %3;" : "+l"(lo), "+l"(hi) : "l"(bl), "l"(bh));
+#else
+    const unsigned __int128 z = (((unsigned __int128)hi << 64) | lo) - (((unsigned __int128)bh << 64) | bl);
+    lo = (u64)z;
+    hi = (u64)(z >> 64);
+#endif
+}
+
 // Barrett reduction of z = hi:lo.  Requires z < 2^(s+64), s = bitlen(q) - 2, i.e. z <= 4 q^2 (factor bounds Ba*Bb <= 4:
 // the shifted value must fit one word).  With the exact quotient the result is in [0, 3q) ([0, 2q) for canonical
 // factors); the estimate of mulhi_approx adds at most 2q: [0, (SB+1) q) and [0, SB*q).

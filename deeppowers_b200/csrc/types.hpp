@@ -29,6 +29,11 @@
 #define DPFHE_SHOUP_APPROX 2
 #endif
 
+// 1: the ct x ct tensor product forms a0 b1 + a1 b0 from three 128-bit products (Karatsuba) instead of four
+#ifndef DPFHE_TENSOR_KARATSUBA
+#define DPFHE_TENSOR_KARATSUBA 1
+#endif
+
 namespace dpfhe {
 
 typedef uint64_t u64;
