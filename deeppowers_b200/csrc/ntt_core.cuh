@@ -228,6 +228,19 @@ DPFHE_HD void fwd_load_stage(u64 *buf, const Twiddle *__restrict__ tw, const Lim
     }
 }
 
+// canonical product of the last inverse stage: exact quotient + one conditional subtraction.  -DDPFHE_INV_FINAL_LAZY=1 selects the
+// quotient estimate (one IMAD.WIDE less) + two conditional subtractions; measured slower (15.72 -> 15.37 M NTT/s)
+#ifndef DPFHE_INV_FINAL_LAZY
+#define DPFHE_INV_FINAL_LAZY 0
+#endif
+DPFHE_HD u64 inv_final_product(u64 x, u64 w, u64 ws, const LimbParams &p) {
+#if DPFHE_INV_FINAL_LAZY && DPFHE_SHOUP_APPROX
+    return canon4(shoup_lazy(x, w, ws, p), p);   // < SB*q = 4q  ->  [0, q)
+#else
+    return csub(shoup_exact(x, w, ws, p), p.q);
+#endif
+}
+
 // Inverse counterpart: SRC(chunk_index) yields the chunks left by the register passes (values in [0,SB*q));
 // applies the K outermost Gentleman-Sande stages with N^-1 folded into the very last one, and hands
 // canonical chunks to DST(chunk_index, U64x2) (the last stage uses the exact product so that one csub finishes).
@@ -267,13 +280,13 @@ DPFHE_HD void inv_outer_stage(const Twiddle *__restrict__ tw, const LimbParams &
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     u64 a = x[i][e], b = x[NB / 2 + i][e];
-                    x[i][e] = csub(shoup_exact(a + b, p.ninv, p.ninv_s, p), p.q);
-                    x[NB / 2 + i][e] = csub(shoup_exact(a + p.qsb - b, p.wninv, p.wninv_s, p), p.q);
+                    x[i][e] = inv_final_product(a + b, p.ninv, p.ninv_s, p);
+                    x[NB / 2 + i][e] = inv_final_product(a + p.qsb - b, p.wninv, p.wninv_s, p);
                 }
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) x[0][e] = csub(shoup_exact(x[0][e], p.ninv, p.ninv_s, p), p.q);
+            for (int e = 0; e < 2; ++e) x[0][e] = inv_final_product(x[0][e], p.ninv, p.ninv_s, p);
         }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
